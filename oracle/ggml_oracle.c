@@ -1,0 +1,573 @@
+/*
+ * ggml_oracle.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).  See ggml_oracle.h.
+ *
+ * Each function cites what it follows.  "[UPSTREAM]" = semantics of the un-vendored ggml
+ * (ggml.c / ggml-quants.c, llama.cpp circa Feb-Mar 2024) restated from its published
+ * algorithm; "ref:" = a file:line under /root/reference.
+ * Build: gcc -O2 -ffp-contract=off (no FMA contraction, no fast-math).
+ */
+#include "ggml_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ fp16 */
+
+/* [UPSTREAM] GGML_FP16_TO_FP32: IEEE binary16 -> binary32, exact. */
+float orc_fp16_to_fp32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    const uint32_t exp = (h >> 10) & 0x1fu;
+    uint32_t man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else { /* subnormal: normalise */
+            int e = -1;
+            do {
+                man <<= 1;
+                e++;
+            } while ((man & 0x400u) == 0);
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 112u) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+/* [UPSTREAM] GGML_FP32_TO_FP16: binary32 -> binary16, round-to-nearest-even (F16C semantics). */
+uint16_t orc_fp32_to_fp16(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    const uint32_t absx = x & 0x7fffffffu;
+    if (absx >= 0x7f800000u) { /* inf / nan */
+        if (absx > 0x7f800000u) return (uint16_t)(sign | 0x7e00u | ((absx >> 13) & 0x3ffu));
+        return (uint16_t)(sign | 0x7c00u);
+    }
+    if (absx >= 0x477ff000u) { /* >= 65520 rounds to inf */
+        return (uint16_t)(sign | 0x7c00u);
+    }
+    if (absx < 0x33000001u) { /* <= 2^-25 rounds to zero (tie at exactly 2^-25 -> even = 0) */
+        return sign;
+    }
+    int32_t e = (int32_t)(absx >> 23) - 127;
+    uint32_t m = (absx & 0x7fffffu) | 0x800000u; /* 24-bit significand */
+    uint32_t shift, half_bits;
+    if (e < -14) { /* subnormal half: value = m * 2^(e-23); unit = 2^-24 */
+        shift = (uint32_t)(-1 - e); /* m >> shift gives multiples of 2^-24: 23 - (e + 24) */
+        half_bits = 0;
+    } else {
+        shift = 13;
+        half_bits = (uint32_t)(e + 15) << 10;
+        m &= 0x7fffffu;
+    }
+    uint32_t q = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u);
+    const uint32_t halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (q & 1u))) q++;
+    /* carry out of the mantissa naturally bumps the exponent */
+    return (uint16_t)(sign | (half_bits + q));
+}
+
+/* ---------------------------------------------------------------- codecs */
+
+size_t orc_row_size(int type, int64_t k) {
+    switch (type) {
+    case ORC_TYPE_F32: return (size_t)k * 4;
+    case ORC_TYPE_F16: return (size_t)k * 2;
+    case ORC_TYPE_Q4_0: return (size_t)(k / ORC_QK) * sizeof(orc_block_q4_0);
+    case ORC_TYPE_Q8_0: return (size_t)(k / ORC_QK) * sizeof(orc_block_q8_0);
+    default: return 0;
+    }
+}
+
+/* [UPSTREAM] quantize_row_q4_0_reference; cross-checked vs gguf/quants.py:222-238. */
+void orc_quantize_row_q4_0(const float *x, orc_block_q4_0 *y, int64_t k) {
+    const int64_t nb = k / ORC_QK;
+    for (int64_t i = 0; i < nb; i++) {
+        float amax = 0.0f, max = 0.0f;
+        for (int j = 0; j < ORC_QK; j++) {
+            const float v = x[i * ORC_QK + j];
+            if (amax < fabsf(v)) {
+                amax = fabsf(v);
+                max = v;
+            }
+        }
+        const float d = max / -8;
+        const float id = d ? 1.0f / d : 0.0f;
+        y[i].d = orc_fp32_to_fp16(d);
+        for (int j = 0; j < ORC_QK / 2; ++j) {
+            const float x0 = x[i * ORC_QK + 0 + j] * id;
+            const float x1 = x[i * ORC_QK + ORC_QK / 2 + j] * id;
+            int a = (int)(int8_t)(x0 + 8.5f);
+            int b = (int)(int8_t)(x1 + 8.5f);
+            const uint8_t xi0 = (uint8_t)(a < 15 ? a : 15);
+            const uint8_t xi1 = (uint8_t)(b < 15 ? b : 15);
+            y[i].qs[j] = (uint8_t)(xi0 | (xi1 << 4));
+        }
+    }
+}
+
+/* [UPSTREAM] quantize_row_q8_0_reference (scalar: roundf, id = 1/d); gguf/quants.py:381-393. */
+void orc_quantize_row_q8_0(const float *x, orc_block_q8_0 *y, int64_t k) {
+    const int64_t nb = k / ORC_QK;
+    for (int64_t i = 0; i < nb; i++) {
+        float amax = 0.0f;
+        for (int j = 0; j < ORC_QK; j++) {
+            const float v = fabsf(x[i * ORC_QK + j]);
+            if (amax < v) amax = v;
+        }
+        const float d = amax / ((1 << 7) - 1);
+        const float id = d ? 1.0f / d : 0.0f;
+        y[i].d = orc_fp32_to_fp16(d);
+        for (int j = 0; j < ORC_QK; ++j) {
+            const float x0 = x[i * ORC_QK + j] * id;
+            y[i].qs[j] = (int8_t)roundf(x0);
+        }
+    }
+}
+
+/* [UPSTREAM] dequantize_row_q4_0: (q - 8) * d; element j = low nibble, j+16 = high nibble. */
+void orc_dequantize_row_q4_0(const orc_block_q4_0 *x, float *y, int64_t k) {
+    const int64_t nb = k / ORC_QK;
+    for (int64_t i = 0; i < nb; i++) {
+        const float d = orc_fp16_to_fp32(x[i].d);
+        for (int j = 0; j < ORC_QK / 2; ++j) {
+            const int x0 = (x[i].qs[j] & 0x0F) - 8;
+            const int x1 = (x[i].qs[j] >> 4) - 8;
+            y[i * ORC_QK + j] = x0 * d;
+            y[i * ORC_QK + j + ORC_QK / 2] = x1 * d;
+        }
+    }
+}
+
+/* [UPSTREAM] dequantize_row_q8_0: q * d. */
+void orc_dequantize_row_q8_0(const orc_block_q8_0 *x, float *y, int64_t k) {
+    const int64_t nb = k / ORC_QK;
+    for (int64_t i = 0; i < nb; i++) {
+        const float d = orc_fp16_to_fp32(x[i].d);
+        for (int j = 0; j < ORC_QK; ++j) y[i * ORC_QK + j] = x[i].qs[j] * d;
+    }
+}
+
+void orc_dequantize_row(int type, const void *x, float *y, int64_t k) {
+    if (type == ORC_TYPE_Q4_0) orc_dequantize_row_q4_0((const orc_block_q4_0 *)x, y, k);
+    else if (type == ORC_TYPE_Q8_0) orc_dequantize_row_q8_0((const orc_block_q8_0 *)x, y, k);
+    else if (type == ORC_TYPE_F32) memcpy(y, x, (size_t)k * 4);
+    else if (type == ORC_TYPE_F16) {
+        for (int64_t i = 0; i < k; i++) y[i] = orc_fp16_to_fp32(((const uint16_t *)x)[i]);
+    }
+}
+
+/* ---------------------------------------------------------- dot products */
+
+static inline int q4_block_sumi(const orc_block_q4_0 *x, const orc_block_q8_0 *y) {
+    int sumi = 0;
+    for (int j = 0; j < ORC_QK / 2; ++j) {
+        const int v0 = (x->qs[j] & 0x0F) - 8;
+        const int v1 = (x->qs[j] >> 4) - 8;
+        sumi += (v0 * y->qs[j]) + (v1 * y->qs[j + ORC_QK / 2]);
+    }
+    return sumi;
+}
+
+static inline int q8_block_sumi(const orc_block_q8_0 *x, const orc_block_q8_0 *y) {
+    int sumi = 0;
+    for (int j = 0; j < ORC_QK; j++) sumi += x->qs[j] * y->qs[j];
+    return sumi;
+}
+
+/* one block's contribution, exactly as the scalar loops write it:
+ * q4_0: sumi*d_x*d_y  (left to right)      q8_0: sumi*(d_x*d_y) */
+static inline float q4_block_term(const orc_block_q4_0 *x, const orc_block_q8_0 *y) {
+    return q4_block_sumi(x, y) * orc_fp16_to_fp32(x->d) * orc_fp16_to_fp32(y->d);
+}
+static inline float q8_block_term(const orc_block_q8_0 *x, const orc_block_q8_0 *y) {
+    return q8_block_sumi(x, y) * (orc_fp16_to_fp32(x->d) * orc_fp16_to_fp32(y->d));
+}
+
+/* [UPSTREAM] ggml_vec_dot_q4_0_q8_0, scalar branch; called through the fn pointer at
+ * ref: src/hpc.cpp:35 with nrc = 1. */
+void orc_vec_dot_q4_0_q8_0(int n, float *s, const void *vx, const void *vy) {
+    const int nb = n / ORC_QK;
+    const orc_block_q4_0 *x = (const orc_block_q4_0 *)vx;
+    const orc_block_q8_0 *y = (const orc_block_q8_0 *)vy;
+    float sumf = 0.0f;
+    for (int i = 0; i < nb; i++) sumf += q4_block_term(&x[i], &y[i]);
+    *s = sumf;
+}
+
+/* [UPSTREAM] ggml_vec_dot_q8_0_q8_0, scalar branch. */
+void orc_vec_dot_q8_0_q8_0(int n, float *s, const void *vx, const void *vy) {
+    const int nb = n / ORC_QK;
+    const orc_block_q8_0 *x = (const orc_block_q8_0 *)vx;
+    const orc_block_q8_0 *y = (const orc_block_q8_0 *)vy;
+    float sumf = 0.0f;
+    for (int i = 0; i < nb; i++) sumf += q8_block_term(&x[i], &y[i]);
+    *s = sumf;
+}
+
+/* xor-butterfly over 32 lanes, offsets 16,8,4,2,1: every lane ends with the same value. */
+static float butterfly32f(float lane[32]) {
+    for (int off = 16; off >= 1; off >>= 1) {
+        float nxt[32];
+        for (int l = 0; l < 32; l++) nxt[l] = lane[l] + lane[l ^ off];
+        memcpy(lane, nxt, sizeof(nxt));
+    }
+    return lane[0];
+}
+static double butterfly32d(double lane[32]) {
+    for (int off = 16; off >= 1; off >>= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; l++) nxt[l] = lane[l] + lane[l ^ off];
+        memcpy(lane, nxt, sizeof(nxt));
+    }
+    return lane[0];
+}
+
+/* DEV order of the sm_100a mat-vec kernels (gemma.ggml_b200/csrc/matvec.cuh): same per-block
+ * terms as the scalar loops, summed as: segments of 128 blocks; lane l of a warp sums blocks
+ * seg+l, seg+l+32, seg+l+64, seg+l+96 (those < nb) sequentially from 0.0f; xor-butterfly;
+ * segment totals added in order. */
+#define ORC_DEV_DOT(NAME, XT, TERM)                                                         \
+    void NAME(int n, float *s, const void *vx, const void *vy) {                           \
+        const int nb = n / ORC_QK;                                                          \
+        const XT *x = (const XT *)vx;                                                       \
+        const orc_block_q8_0 *y = (const orc_block_q8_0 *)vy;                               \
+        float total = 0.0f;                                                                 \
+        for (int seg = 0, si = 0; seg < nb; seg += ORC_DEV_SEG_BLOCKS, si++) {              \
+            float lane[32];                                                                 \
+            for (int l = 0; l < 32; l++) {                                                  \
+                float acc = 0.0f;                                                           \
+                for (int t = 0; t < ORC_DEV_SEG_BLOCKS / 32; t++) {                         \
+                    const int b = seg + l + 32 * t;                                         \
+                    if (b < nb) acc += TERM(&x[b], &y[b]);                                  \
+                }                                                                           \
+                lane[l] = acc;                                                              \
+            }                                                                               \
+            const float segsum = butterfly32f(lane);                                        \
+            total = (si == 0) ? segsum : total + segsum;                                    \
+        }                                                                                   \
+        *s = total;                                                                         \
+    }
+ORC_DEV_DOT(orc_vec_dot_q4_0_q8_0_dev, orc_block_q4_0, q4_block_term)
+ORC_DEV_DOT(orc_vec_dot_q8_0_q8_0_dev, orc_block_q8_0, q8_block_term)
+
+/* [UPSTREAM] ggml_vec_dot_f16 scalar branch; ref: src/kernals.cl:158-164 (double accumulator). */
+void orc_vec_dot_f16(int n, float *s, const uint16_t *x, const uint16_t *y) {
+    double sumf = 0.0;
+    for (int i = 0; i < n; ++i) sumf += (double)(orc_fp16_to_fp32(x[i]) * orc_fp16_to_fp32(y[i]));
+    *s = (float)sumf;
+}
+
+void orc_vec_dot(int type, int order, int n, float *s, const void *vx, const void *vy) {
+    if (type == ORC_TYPE_Q4_0) {
+        if (order) orc_vec_dot_q4_0_q8_0_dev(n, s, vx, vy);
+        else orc_vec_dot_q4_0_q8_0(n, s, vx, vy);
+    } else if (type == ORC_TYPE_Q8_0) {
+        if (order) orc_vec_dot_q8_0_q8_0_dev(n, s, vx, vy);
+        else orc_vec_dot_q8_0_q8_0(n, s, vx, vy);
+    } else if (type == ORC_TYPE_F16) {
+        orc_vec_dot_f16(n, s, (const uint16_t *)vx, (const uint16_t *)vy);
+    } else {
+        *s = NAN;
+    }
+}
+
+/* ref: src/hpc.cpp:15-41 (mul_mat_sub with MUL_MAT_BLOCK_SIZE 1, src/macro.h:23):
+ * dst[(col % ne1)*nb1 + (col / ne1)*nb2 + row*4] = vec_dot(K, src0 + row*nb01, src1 + col*row_size). */
+void orc_mul_mat_sub(int64_t start_row, int64_t end_row, int64_t shared_edge, int64_t col_num,
+                     int64_t ne01, int64_t ne1, int64_t nb01, int64_t nb1, int64_t nb2,
+                     int64_t row_size, const char *src0, const char *src1, char *dst,
+                     int type, int order) {
+    for (int64_t row0 = start_row; row0 < end_row && row0 < ne01; row0++) {
+        for (int64_t col_i = 0; col_i < col_num; col_i++) {
+            const int64_t mat_i = col_i / ne1;
+            const int64_t mat_col_i = col_i % ne1;
+            const char *src1_col = src1 + col_i * row_size;
+            float *dst_col = (float *)(dst + (mat_col_i * nb1 + mat_i * nb2));
+            orc_vec_dot(type, order, (int)shared_edge, &dst_col[row0], src0 + row0 * nb01, src1_col);
+        }
+    }
+}
+
+/* ------------------------------------------------------------ element-wise */
+
+/* [UPSTREAM] ggml_compute_forward_rms_norm_f32: sum in double of (double)(x*x) with the product
+ * rounded to fp32 first; mean = sum/n (to float); scale = 1/sqrtf(mean + eps). */
+void orc_rms_norm(int64_t n, const float *x, float eps, float *y) {
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; i++) sum += (double)(x[i] * x[i]);
+    const float mean = (float)(sum / (double)n);
+    const float scale = 1.0f / sqrtf(mean + eps);
+    for (int64_t i = 0; i < n; i++) y[i] = x[i] * scale;
+}
+
+/* DEV order (csrc/common.cuh block_sum_f64): 256 threads, thread t sums i = t, t+256, ... in
+ * double from 0.0; xor-butterfly per warp; the 8 warp totals added in warp order. */
+void orc_rms_norm_dev(int64_t n, const float *x, float eps, float *y) {
+    double warp_tot[ORC_DEV_NORM_THREADS / 32];
+    for (int w = 0; w < ORC_DEV_NORM_THREADS / 32; w++) {
+        double lane[32];
+        for (int l = 0; l < 32; l++) {
+            double acc = 0.0;
+            for (int64_t i = w * 32 + l; i < n; i += ORC_DEV_NORM_THREADS) acc += (double)(x[i] * x[i]);
+            lane[l] = acc;
+        }
+        warp_tot[w] = butterfly32d(lane);
+    }
+    double sum = warp_tot[0];
+    for (int w = 1; w < ORC_DEV_NORM_THREADS / 32; w++) sum += warp_tot[w];
+    const float mean = (float)(sum / (double)n);
+    const float scale = 1.0f / sqrtf(mean + eps);
+    for (int64_t i = 0; i < n; i++) y[i] = x[i] * scale;
+}
+
+void orc_mul(int64_t n, const float *a, const float *b, float *y) {
+    for (int64_t i = 0; i < n; i++) y[i] = a[i] * b[i];
+}
+void orc_add(int64_t n, const float *a, const float *b, float *y) {
+    for (int64_t i = 0; i < n; i++) y[i] = a[i] + b[i];
+}
+void orc_scale(int64_t n, const float *x, float s, float *y) {
+    for (int64_t i = 0; i < n; i++) y[i] = x[i] * s;
+}
+
+/* [UPSTREAM] ggml_compute_forward_rope_f32, NEOX branch (mode & 2), ext_factor = 0,
+ * freq_scale = 1, attn_factor = 1 (ref: src/macro.h:12-18, src/gemma_model.cpp:698-716):
+ * theta_scale = powf(freq_base, -2/n_dims); theta starts at pos and is multiplied each step. */
+void orc_rope_cache(int32_t pos, int n_dims, float freq_base, float *cos_out, float *sin_out) {
+    const float theta_scale = powf(freq_base, -2.0f / n_dims);
+    float theta = (float)pos;
+    for (int i = 0; i < n_dims / 2; i++) {
+        cos_out[i] = cosf(theta);
+        sin_out[i] = sinf(theta);
+        theta *= theta_scale;
+    }
+}
+
+/* x, y: [n_heads][n_dims]; pairs (i, i + n_dims/2). */
+void orc_rope_neox(int n_dims, int n_heads, int32_t pos, float freq_base, const float *x, float *y) {
+    float *c = (float *)malloc(sizeof(float) * (size_t)n_dims);
+    float *s = c + n_dims / 2;
+    orc_rope_cache(pos, n_dims, freq_base, c, s);
+    for (int h = 0; h < n_heads; h++) {
+        const float *xh = x + (size_t)h * n_dims;
+        float *yh = y + (size_t)h * n_dims;
+        for (int i = 0; i < n_dims / 2; i++) {
+            const float x0 = xh[i];
+            const float x1 = xh[i + n_dims / 2];
+            yh[i] = x0 * c[i] - x1 * s[i];
+            yh[i + n_dims / 2] = x0 * s[i] + x1 * c[i];
+        }
+    }
+    free(c);
+}
+
+/* [UPSTREAM] ggml_init table construction: table[i] = FP32_TO_FP16(f(FP16_TO_FP32(i))). */
+void orc_build_exp_table(uint16_t *table) {
+    for (uint32_t i = 0; i < 65536; i++) table[i] = orc_fp32_to_fp16(expf(orc_fp16_to_fp32((uint16_t)i)));
+}
+static inline float gelu_f32(float x) {
+    const float GELU_COEF_A = 0.044715f;
+    const float SQRT_2_OVER_PI = 0.79788456080286535587989211986876f;
+    return 0.5f * x * (1.0f + tanhf(SQRT_2_OVER_PI * x * (1.0f + GELU_COEF_A * x * x)));
+}
+void orc_build_gelu_table(uint16_t *table) {
+    for (uint32_t i = 0; i < 65536; i++) table[i] = orc_fp32_to_fp16(gelu_f32(orc_fp16_to_fp32((uint16_t)i)));
+}
+
+static uint16_t g_exp_table[65536], g_gelu_table[65536];
+static int g_tables_ready = 0;
+static void ensure_tables(void) {
+    if (!g_tables_ready) {
+        orc_build_exp_table(g_exp_table);
+        orc_build_gelu_table(g_gelu_table);
+        g_tables_ready = 1;
+    }
+}
+const uint16_t *orc_exp_table(void) {
+    ensure_tables();
+    return g_exp_table;
+}
+const uint16_t *orc_gelu_table(void) {
+    ensure_tables();
+    return g_gelu_table;
+}
+
+/* [UPSTREAM] ggml_vec_gelu_f32 with GGML_GELU_FP16: y = table[f16(x)]. */
+void orc_gelu(int64_t n, const float *x, float *y) {
+    const uint16_t *t = orc_gelu_table();
+    for (int64_t i = 0; i < n; i++) y[i] = orc_fp16_to_fp32(t[orc_fp32_to_fp16(x[i])]);
+}
+
+/* [UPSTREAM] ggml_compute_forward_soft_max_f32 (max_bias = 0, no pos): w = x*scale + mask;
+ * p = exp_table[f16(w - max)] (0 where w == -inf); sum in double; p *= (float)(1/sum). */
+void orc_soft_max_ext(int64_t nc, const float *x, const float *mask, float scale, float *y) {
+    const uint16_t *t = orc_exp_table();
+    float *wp = (float *)malloc(sizeof(float) * (size_t)nc);
+    for (int64_t i = 0; i < nc; i++) wp[i] = x[i];
+    for (int64_t i = 0; i < nc; i++) wp[i] *= scale;
+    if (mask)
+        for (int64_t i = 0; i < nc; i++) wp[i] += mask[i];
+    float max = -INFINITY;
+    for (int64_t i = 0; i < nc; i++) max = wp[i] > max ? wp[i] : max;
+    double sum = 0.0;
+    for (int64_t i = 0; i < nc; i++) {
+        if (wp[i] == -INFINITY) {
+            y[i] = 0.0f;
+        } else {
+            const float val = orc_fp16_to_fp32(t[orc_fp32_to_fp16(wp[i] - max)]);
+            sum += (double)val;
+            y[i] = val;
+        }
+    }
+    sum = 1.0 / sum;
+    const float fs = (float)sum;
+    for (int64_t i = 0; i < nc; i++) y[i] *= fs;
+    free(wp);
+}
+
+/* ref: src/gemma_model.cpp:532-546 */
+int32_t orc_argmax(int64_t n, const float *x) {
+    float max_val = -INFINITY;
+    int32_t max_idx = -1;
+    for (int64_t i = 0; i < n; i++) {
+        if (x[i] > max_val) {
+            max_val = x[i];
+            max_idx = (int32_t)i;
+        }
+    }
+    return max_idx;
+}
+
+/* -------------------------------------------------------------- attention */
+
+/* REF decode attention for one token (ref: src/gemma_model.cpp:454-496 graph_build_kqv;
+ * mask / n_kv: :326-335, :428-436).  q is converted to fp16 by the mul_mat INIT stage
+ * (vec_dot_type of F16 is F16), as are the soft-max probabilities before kqv. */
+void orc_attn_decode_ref(int H, int Hkv, int d, int64_t n_pos, int64_t n_ctx, const float *q,
+                         const uint16_t *kcache, const uint16_t *vcache, int64_t kv_stride, float *out) {
+    int64_t n_kv = ((n_pos / 32) + 1) * 32; /* input.size() == n_pos for decode */
+    if (n_kv > n_ctx) n_kv = n_ctx;
+    const int G = H / Hkv;
+    uint16_t *q16 = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)d);
+    float *kq = (float *)malloc(sizeof(float) * (size_t)n_kv);
+    float *mask = (float *)malloc(sizeof(float) * (size_t)n_kv);
+    float *p = (float *)malloc(sizeof(float) * (size_t)n_kv);
+    uint16_t *p16 = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)n_kv);
+    uint16_t *vcol = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)n_kv);
+    for (int64_t j = 0; j < n_kv; j++) mask[j] = (j > n_pos - 1) ? -INFINITY : 0.0f;
+    for (int h = 0; h < H; h++) {
+        const int g = h / G;
+        for (int i = 0; i < d; i++) q16[i] = orc_fp32_to_fp16(q[(size_t)h * d + i]);
+        for (int64_t pz = 0; pz < n_kv; pz++)
+            orc_vec_dot_f16(d, &kq[pz], kcache + pz * kv_stride + (size_t)g * d, q16);
+        orc_soft_max_ext(n_kv, kq, mask, 1.0f, p);
+        for (int64_t pz = 0; pz < n_kv; pz++) p16[pz] = orc_fp32_to_fp16(p[pz]);
+        for (int i = 0; i < d; i++) {
+            for (int64_t pz = 0; pz < n_kv; pz++) vcol[pz] = vcache[pz * kv_stride + (size_t)g * d + i];
+            orc_vec_dot_f16((int)n_kv, &out[(size_t)h * d + i], vcol, p16);
+        }
+    }
+    free(q16); free(kq); free(mask); free(p); free(p16); free(vcol);
+}
+
+/* DEV decode attention (csrc/attention.cu): split-K over chunks of 32 positions.
+ * Per (head, chunk): score = 32 lane partials (lane l: elements 8l..8l+7, fp32, sequential)
+ * + butterfly; m = chunk max; e = exp_table[f16(score - m)]; l = butterfly sum of e over the
+ * 32 positions (absent positions contribute 0.0f); acc[i] = sum_p e_p * V[p][i] sequential in p.
+ * Combine (per head): M = max m_c; w_c = exp_table[f16(m_c - M)]; L = sum l_c*w_c and
+ * O[i] = sum acc_c[i]*w_c sequential in c (mul then add); out = O / L. */
+void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
+                         const uint16_t *kcache, const uint16_t *vcache, int64_t kv_stride, float *out) {
+    const uint16_t *t = orc_exp_table();
+    const int G = H / Hkv;
+    const int C = ORC_DEV_ATTN_CHUNK;
+    const int64_t nchunk = (n_pos + C - 1) / C;
+    float *pm = (float *)malloc(sizeof(float) * (size_t)nchunk);
+    float *pl = (float *)malloc(sizeof(float) * (size_t)nchunk);
+    float *pacc = (float *)malloc(sizeof(float) * (size_t)nchunk * d);
+    float *q16f = (float *)malloc(sizeof(float) * (size_t)d);
+    for (int h = 0; h < H; h++) {
+        const int g = h / G;
+        for (int i = 0; i < d; i++) q16f[i] = orc_fp16_to_fp32(orc_fp32_to_fp16(q[(size_t)h * d + i]));
+        for (int64_t c = 0; c < nchunk; c++) {
+            const int64_t p0 = c * C;
+            const int np = (int)((n_pos - p0) < C ? (n_pos - p0) : C);
+            float s[ORC_DEV_ATTN_CHUNK], e[ORC_DEV_ATTN_CHUNK];
+            float m = -INFINITY;
+            for (int j = 0; j < np; j++) {
+                const uint16_t *krow = kcache + (p0 + j) * kv_stride + (size_t)g * d;
+                float lane[32];
+                for (int l = 0; l < 32; l++) {
+                    float acc = 0.0f;
+                    for (int i = 8 * l; i < 8 * l + 8 && i < d; i++) acc += orc_fp16_to_fp32(krow[i]) * q16f[i];
+                    lane[l] = acc;
+                }
+                s[j] = butterfly32f(lane);
+                m = s[j] > m ? s[j] : m;
+            }
+            float lane[32];
+            for (int j = 0; j < 32; j++) {
+                if (j < np) {
+                    e[j] = orc_fp16_to_fp32(t[orc_fp32_to_fp16(s[j] - m)]);
+                    lane[j] = e[j];
+                } else {
+                    lane[j] = 0.0f;
+                }
+            }
+            pm[c] = m;
+            pl[c] = butterfly32f(lane);
+            for (int i = 0; i < d; i++) {
+                float acc = 0.0f;
+                for (int j = 0; j < np; j++)
+                    acc += e[j] * orc_fp16_to_fp32(vcache[(p0 + j) * kv_stride + (size_t)g * d + i]);
+                pacc[(size_t)c * d + i] = acc;
+            }
+        }
+        float M = -INFINITY;
+        for (int64_t c = 0; c < nchunk; c++) M = pm[c] > M ? pm[c] : M;
+        float L = 0.0f;
+        for (int i = 0; i < d; i++) out[(size_t)h * d + i] = 0.0f;
+        for (int64_t c = 0; c < nchunk; c++) {
+            const float w = orc_fp16_to_fp32(t[orc_fp32_to_fp16(pm[c] - M)]);
+            L += pl[c] * w;
+            for (int i = 0; i < d; i++) out[(size_t)h * d + i] += pacc[(size_t)c * d + i] * w;
+        }
+        for (int i = 0; i < d; i++) out[(size_t)h * d + i] = out[(size_t)h * d + i] / L;
+    }
+    free(pm); free(pl); free(pacc); free(q16f);
+}
+
+/* ------------------------------------------------------- synthetic weights */
+
+uint64_t orc_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+/* Approximately N(0, sigma^2): Irwin-Hall sum of four 16-bit uniforms, centred, scaled by ONE
+ * fp32 multiply of an exactly representable integer -> bit-reproducible on CPU and GPU
+ * (no libm).  std of the integer sum = sqrt(4*(65536^2-1)/12) = 37837.2274... */
+float orc_synth_value(uint64_t seed, uint64_t tensor_id, uint64_t index, float sigma) {
+    const uint64_t r = orc_splitmix64(orc_splitmix64(seed + tensor_id * 0xD1B54A32D192ED03ull) + index);
+    const int32_t sum = (int32_t)(r & 0xffff) + (int32_t)((r >> 16) & 0xffff) + (int32_t)((r >> 32) & 0xffff) +
+                        (int32_t)((r >> 48) & 0xffff) - 131070;
+    const float unit = sigma * (1.0f / 37837.2274f);
+    return (float)sum * unit;
+}
+
+void orc_synth_row(uint64_t seed, uint64_t tensor_id, int64_t row, int64_t k, float sigma, float bias, float *out) {
+    for (int64_t i = 0; i < k; i++)
+        out[i] = bias + orc_synth_value(seed, tensor_id, (uint64_t)(row * k + i), sigma);
+}
