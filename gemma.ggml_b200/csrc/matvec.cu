@@ -1,0 +1,319 @@
+// matvec.cu — K2/K3: Q4_0 / Q8_0 weight rows · Q8_0 activations (decode mat-vec), the hot loop
+// of the reference (ref: src/hpc.cpp:15-41 mul_mat_sub -> vec_dot, 99.98 % of mul_mat time,
+// notes.md:87).  Not a port of src/kernals.cl (one work-item per output, serial K loop):
+//
+//   * a warp owns a row (or, for K > 4096, one 128-block segment of a row); lane l owns blocks
+//     l, l+32, l+64, l+96 of the segment, so the activation blocks a lane needs never change
+//     from row to row and live in REGISTERS for the whole kernel;
+//   * weight payloads stream with one coalesced 128-bit load per lane per block (SoA planes,
+//     L1 no-allocate), nibbles are unpacked in registers and dotted with dp4a; the "-8" of
+//     Q4_0 is folded into a per-lane constant (-8 * sum of the activation block);
+//   * per-block terms are the scalar reference's ((float)sumi*dx)*dy, summed in the DEV order
+//     documented in include/ggml_b200.h; reduction is warp shuffles (+ smem across segments).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxMats = 3;
+constexpr int kTPB = GGB_DEV_SEG_BLOCKS / 32; // blocks per lane per segment = 4
+
+struct MatvecMat {
+    const uint8_t *qs;
+    const __half *d;
+    float *dst;
+    const float *resid;
+    int64_t rows;
+};
+
+struct MatvecArgs {
+    MatvecMat m[kMaxMats];
+    int n_mats;
+    int64_t total_rows;
+    int64_t nb;
+    const uint8_t *act; // planar q8 rows
+    int64_t act_stride; // bytes between activation rows (T > 1)
+    int64_t dst_stride; // floats between dst rows
+    int64_t cols;
+    int ksegs;         // ceil(nb / 128)
+    int rows_per_iter; // warps per CTA / ksegs
+    int64_t rows_per_cta;
+};
+
+template <int TYPE> struct Payload;
+template <> struct Payload<GGB_TYPE_Q4_0> {
+    uint4 v;
+    __device__ __forceinline__ void load(const uint8_t *qs, int64_t blk) { v = ldg_stream_u4(qs + blk * 16); }
+};
+template <> struct Payload<GGB_TYPE_Q8_0> {
+    uint4 v0, v1;
+    __device__ __forceinline__ void load(const uint8_t *qs, int64_t blk) {
+        v0 = ldg_stream_u4(qs + blk * 32);
+        v1 = ldg_stream_u4(qs + blk * 32 + 16);
+    }
+};
+
+// activation block held by a lane
+struct ActBlock {
+    int a[8];  // 32 int8
+    float d;   // fp16 scale widened
+    int bias;  // -8 * sum(a) (Q4_0 only)
+};
+
+__device__ __forceinline__ void load_act(ActBlock &ab, const uint8_t *act, int64_t cols, int64_t b, bool valid) {
+    if (valid) {
+        const uint4 lo = *reinterpret_cast<const uint4 *>(act + b * 32);
+        const uint4 hi = *reinterpret_cast<const uint4 *>(act + b * 32 + 16);
+        ab.a[0] = lo.x; ab.a[1] = lo.y; ab.a[2] = lo.z; ab.a[3] = lo.w;
+        ab.a[4] = hi.x; ab.a[5] = hi.y; ab.a[6] = hi.z; ab.a[7] = hi.w;
+        ab.d = __half2float(reinterpret_cast<const __half *>(act + cols)[b]);
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s = __dp4a(ab.a[i], 0x01010101, s);
+        ab.bias = -8 * s;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) ab.a[i] = 0;
+        ab.d = 0.f;
+        ab.bias = 0;
+    }
+}
+
+// one block's contribution, exactly the scalar loops' expression:
+//   Q4_0: sumi * d_x * d_y  (left to right)        Q8_0: sumi * (d_x * d_y)
+__device__ __forceinline__ float block_term(const Payload<GGB_TYPE_Q4_0> &w, float dx, const ActBlock &ab) {
+    int sumi = ab.bias;
+    const uint32_t q[4] = {w.v.x, w.v.y, w.v.z, w.v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int lo = (int)(q[i] & 0x0F0F0F0Fu);
+        const int hi = (int)((q[i] >> 4) & 0x0F0F0F0Fu);
+        sumi = __dp4a(lo, ab.a[i], sumi);
+        sumi = __dp4a(hi, ab.a[4 + i], sumi);
+    }
+    return __fmul_rn(__fmul_rn((float)sumi, dx), ab.d);
+}
+__device__ __forceinline__ float block_term(const Payload<GGB_TYPE_Q8_0> &w, float dx, const ActBlock &ab) {
+    int sumi = 0;
+    sumi = __dp4a((int)w.v0.x, ab.a[0], sumi);
+    sumi = __dp4a((int)w.v0.y, ab.a[1], sumi);
+    sumi = __dp4a((int)w.v0.z, ab.a[2], sumi);
+    sumi = __dp4a((int)w.v0.w, ab.a[3], sumi);
+    sumi = __dp4a((int)w.v1.x, ab.a[4], sumi);
+    sumi = __dp4a((int)w.v1.y, ab.a[5], sumi);
+    sumi = __dp4a((int)w.v1.z, ab.a[6], sumi);
+    sumi = __dp4a((int)w.v1.w, ab.a[7], sumi);
+    return __fmul_rn((float)sumi, __fmul_rn(dx, ab.d));
+}
+
+// dot of one segment of one row: lane partial (blocks in order, from 0.0f) + butterfly
+template <int TYPE>
+__device__ __forceinline__ float segment_dot(const uint8_t *qs, const __half *d, int64_t row, int64_t nb, int64_t b0,
+                                             const ActBlock (&ab)[kTPB], const bool (&valid)[kTPB]) {
+    Payload<TYPE> w[kTPB];
+    float dx[kTPB];
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        if (valid[t]) {
+            const int64_t blk = row * nb + b0 + 32 * t;
+            w[t].load(qs, blk);
+            dx[t] = __half2float(d[blk]);
+        }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        if (valid[t]) acc = __fadd_rn(acc, block_term(w[t], dx[t], ab[t]));
+    }
+    return warp_sum_f32(acc);
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(384) matvec_kernel(const MatvecArgs a) {
+    extern __shared__ float s_part[]; // [rows_per_iter][ksegs]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int kseg = warp % a.ksegs;
+    const int rsub = warp / a.ksegs;
+    const uint8_t *act = a.act + (int64_t)blockIdx.y * a.act_stride;
+
+    ActBlock ab[kTPB];
+    bool valid[kTPB];
+    const int64_t b0 = (int64_t)kseg * GGB_DEV_SEG_BLOCKS + lane;
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        valid[t] = b0 + 32 * t < a.nb;
+        load_act(ab[t], act, a.cols, b0 + 32 * t, valid[t]);
+    }
+
+    const int64_t row_begin = (int64_t)blockIdx.x * a.rows_per_cta;
+    int64_t row_end = row_begin + a.rows_per_cta;
+    if (row_end > a.total_rows) row_end = a.total_rows;
+    for (int64_t base = row_begin; base < row_end; base += a.rows_per_iter) {
+        const int64_t gr = base + rsub;
+        const bool live = gr < row_end;
+        // locate the matrix this global row belongs to
+        int mi = 0;
+        int64_t r = gr;
+        if (live) {
+            while (mi + 1 < a.n_mats && r >= a.m[mi].rows) {
+                r -= a.m[mi].rows;
+                mi++;
+            }
+        }
+        float seg = 0.0f;
+        if (live) seg = segment_dot<TYPE>(a.m[mi].qs, a.m[mi].d, r, a.nb, b0, ab, valid);
+        if (a.ksegs == 1) {
+            if (live && lane == 0) {
+                float *dst = a.m[mi].dst + (int64_t)blockIdx.y * a.dst_stride;
+                float v = seg;
+                if (a.m[mi].resid) v = __fadd_rn(v, a.m[mi].resid[(int64_t)blockIdx.y * a.dst_stride + r]);
+                dst[r] = v;
+            }
+        } else {
+            if (lane == 0) s_part[rsub * a.ksegs + kseg] = seg;
+            __syncthreads();
+            if (live && kseg == 0 && lane == 0) {
+                float total = s_part[rsub * a.ksegs];
+                for (int s = 1; s < a.ksegs; s++) total = __fadd_rn(total, s_part[rsub * a.ksegs + s]);
+                float *dst = a.m[mi].dst + (int64_t)blockIdx.y * a.dst_stride;
+                if (a.m[mi].resid) total = __fadd_rn(total, a.m[mi].resid[(int64_t)blockIdx.y * a.dst_stride + r]);
+                dst[r] = total;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// FFN front half: one CTA per 32 output rows: gate and up dots, GeGLU through the fp16 gelu
+// table ([UPSTREAM] ggml_vec_gelu_f32), then quantize_row_q8_0 of the 32 products — the
+// activation of the down projection never exists in fp32 in HBM (unless act_f32 asks for a dump).
+struct GateUpArgs {
+    const uint8_t *gate_qs, *up_qs;
+    const __half *gate_d, *up_d;
+    int64_t nb, cols, rows;
+    const uint8_t *act;
+    const uint16_t *gelu_table;
+    int8_t *out_qs;
+    __half *out_d;
+    float *act_f32;
+};
+
+template <int TYPE>
+__global__ void __launch_bounds__(256) gate_up_kernel(const GateUpArgs a) {
+    __shared__ float s_g[32], s_u[32];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    ActBlock ab[kTPB];
+    bool valid[kTPB];
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        valid[t] = lane + 32 * t < a.nb;
+        load_act(ab[t], a.act, a.cols, lane + 32 * t, valid[t]);
+    }
+    const int64_t tile_row0 = (int64_t)blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t r = tile_row0 + warp * 4 + i;
+        const float g = segment_dot<TYPE>(a.gate_qs, a.gate_d, r, a.nb, lane, ab, valid);
+        const float u = segment_dot<TYPE>(a.up_qs, a.up_d, r, a.nb, lane, ab, valid);
+        if (lane == 0) {
+            s_g[warp * 4 + i] = g;
+            s_u[warp * 4 + i] = u;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float g = s_g[lane];
+        const float gl = half_bits_to_float(a.gelu_table[float_to_half_bits(g)]);
+        const float x = __fmul_rn(gl, s_u[lane]);
+        if (a.act_f32) a.act_f32[tile_row0 + lane] = x;
+        float d;
+        const int q = quantize_q8_lane(x, d);
+        a.out_qs[tile_row0 + lane] = (int8_t)q;
+        if (lane == 0) a.out_d[blockIdx.x] = __float2half_rn(d);
+    }
+}
+
+int launch_matvec(int n, const ggb_weight *const *w, const void *q8, int64_t T, float *const *dst,
+                  int64_t dst_stride, const float *const *resid) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(n >= 1 && n <= kMaxMats, "n_mats %d out of range", n);
+    GGB_CHECK_ARG(q8 != nullptr && T >= 1, "null activations");
+    MatvecArgs a{};
+    a.n_mats = n;
+    a.total_rows = 0;
+    for (int i = 0; i < n; i++) {
+        GGB_CHECK_ARG(w[i] && dst[i], "null weight/dst %d", i);
+        GGB_CHECK_ARG(w[i]->type == w[0]->type && w[i]->cols == w[0]->cols, "mixed types/cols in one launch");
+        a.m[i].qs = w[i]->qs;
+        a.m[i].d = w[i]->d;
+        a.m[i].dst = dst[i];
+        a.m[i].resid = resid ? resid[i] : nullptr;
+        a.m[i].rows = w[i]->rows;
+        a.total_rows += w[i]->rows;
+    }
+    a.nb = w[0]->nb;
+    a.cols = w[0]->cols;
+    a.act = (const uint8_t *)q8;
+    a.act_stride = (int64_t)ggb_q8_row_bytes(a.cols);
+    a.dst_stride = dst_stride;
+    a.ksegs = (int)((a.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS);
+    GGB_CHECK_ARG(a.ksegs <= 12, "K = %lld too large for one CTA (max 49152)", (long long)a.cols);
+    a.rows_per_iter = a.ksegs >= 8 ? 1 : 8 / a.ksegs;
+    const int warps = a.rows_per_iter * a.ksegs;
+    const int64_t target_ctas = (int64_t)ggb_sm_count() * 8;
+    int64_t rpc = (a.total_rows + target_ctas - 1) / target_ctas;
+    rpc = ((rpc + a.rows_per_iter - 1) / a.rows_per_iter) * a.rows_per_iter;
+    if (rpc < a.rows_per_iter) rpc = a.rows_per_iter;
+    a.rows_per_cta = rpc;
+    const unsigned grid_x = (unsigned)((a.total_rows + rpc - 1) / rpc);
+    const dim3 grid(grid_x, (unsigned)T);
+    const size_t smem = sizeof(float) * (size_t)warps;
+    if (w[0]->type == GGB_TYPE_Q4_0)
+        matvec_kernel<GGB_TYPE_Q4_0><<<grid, warps * 32, smem, ggb_cuda_stream()>>>(a);
+    else
+        matvec_kernel<GGB_TYPE_Q8_0><<<grid, warps * 32, smem, ggb_cuda_stream()>>>(a);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+size_t ggb_q8_row_bytes(int64_t cols) { return (size_t)((cols + cols / 16 + 15) & ~(int64_t)15); }
+
+int ggb_op_mul_mat_q8(const ggb_weight *w, const void *q8, int64_t T, float *dst, int64_t dst_stride,
+                      const float *residual) {
+    const ggb_weight *ws[1] = {w};
+    float *ds[1] = {dst};
+    const float *rs[1] = {residual};
+    return launch_matvec(1, ws, q8, T, ds, dst_stride, rs);
+}
+
+int ggb_op_mul_mat_q8_multi(int n, const ggb_weight *const *w, const void *q8, float *const *dst) {
+    return launch_matvec(n, w, q8, 1, dst, 0, nullptr);
+}
+
+int ggb_op_ffn_gate_up(const ggb_weight *gate, const ggb_weight *up, const void *q8, void *q8_out, float *act_f32) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(gate && up && q8 && q8_out, "null pointer");
+    GGB_CHECK_ARG(gate->type == up->type && gate->rows == up->rows && gate->cols == up->cols, "gate/up mismatch");
+    GGB_CHECK_ARG(gate->nb <= GGB_DEV_SEG_BLOCKS, "ffn_gate_up needs n_embd <= 4096 (got %lld)", (long long)gate->cols);
+    GGB_CHECK_ARG(gate->rows % 32 == 0, "n_ff %lld not a multiple of 32", (long long)gate->rows);
+    GateUpArgs a{};
+    a.gate_qs = gate->qs; a.up_qs = up->qs; a.gate_d = gate->d; a.up_d = up->d;
+    a.nb = gate->nb; a.cols = gate->cols; a.rows = gate->rows;
+    a.act = (const uint8_t *)q8;
+    a.gelu_table = ggb_gelu_table_dev();
+    a.out_qs = (int8_t *)q8_out;
+    a.out_d = (__half *)((uint8_t *)q8_out + gate->rows);
+    a.act_f32 = act_f32;
+    const unsigned grid = (unsigned)(gate->rows / 32);
+    if (gate->type == GGB_TYPE_Q4_0) gate_up_kernel<GGB_TYPE_Q4_0><<<grid, 256, 0, ggb_cuda_stream()>>>(a);
+    else gate_up_kernel<GGB_TYPE_Q8_0><<<grid, 256, 0, ggb_cuda_stream()>>>(a);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+} // extern "C"

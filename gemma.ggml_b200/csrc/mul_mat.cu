@@ -1,0 +1,116 @@
+// mul_mat.cu — the drop-in for the reference's offload entry point
+//   extern "C" void mul_mat(...)   ref: src/hpc.h:22-32, src/hpc.cpp:216-277
+// Same fields, HOST pointers, synchronous.  Where the reference split rows 90/10 between a CPU
+// thread pool and a verify-only OpenCL kernel (src/hpc.cpp:245-277, src/kernals.cl:203-211), every
+// row is computed on the B200; src0 is uploaded + repacked once and cached, only the activations
+// (wdata) and the result cross PCIe per call.
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace {
+
+struct CacheKey {
+    const void *ptr;
+    int type;
+    int64_t rows, cols, nb01;
+    bool operator<(const CacheKey &o) const {
+        return std::tie(ptr, type, rows, cols, nb01) < std::tie(o.ptr, o.type, o.rows, o.cols, o.nb01);
+    }
+};
+
+std::map<CacheKey, ggb_weight *> g_cache;
+std::mutex g_mu;
+void *g_act_raw = nullptr, *g_act_q8 = nullptr;
+float *g_dst = nullptr;
+size_t g_act_raw_cap = 0, g_act_q8_cap = 0, g_dst_cap = 0;
+
+int ensure(void **p, size_t *cap, size_t need) {
+    if (*cap >= need) return GGB_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    GGB_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return GGB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int ggb_mul_mat(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64_t ne1, int64_t nb1, int64_t nb2,
+                size_t row_size, int64_t shared_edge, const void *src0_data, void *dst_data, int src0_type,
+                const char *wdata) {
+    GGB_REQUIRE_INIT();
+    if (src0_type != GGB_TYPE_Q4_0 && src0_type != GGB_TYPE_Q8_0) {
+        ggb_set_error("mul_mat: no kernel for src0 type %d (ref behaviour: \"kernel is null\", src/hpc.cpp:162-166)",
+                      src0_type);
+        return GGB_ERR_UNSUPPORTED;
+    }
+    GGB_CHECK_ARG(src0_data && dst_data && wdata, "mul_mat: null pointer");
+    GGB_CHECK_ARG(ne01 > 0 && ne11 > 0 && ne12 > 0 && ne1 > 0, "mul_mat: bad extents");
+    GGB_CHECK_ARG(shared_edge > 0 && shared_edge % GGB_QK == 0, "mul_mat: K %lld not a multiple of 32",
+                  (long long)shared_edge);
+    const int64_t K = shared_edge, nb = K / GGB_QK;
+    GGB_CHECK_ARG((int64_t)row_size >= nb * 34, "mul_mat: row_size %zu < Q8_0 row (%lld)", row_size, (long long)nb * 34);
+    GGB_CHECK_ARG(nb1 % 4 == 0 && nb2 % 4 == 0 && nb1 >= ne01 * 4, "mul_mat: dst strides must hold %lld floats",
+                  (long long)ne01);
+    std::lock_guard<std::mutex> lk(g_mu);
+
+    // 1. resident weight (uploaded + repacked once)
+    ggb_weight *w = nullptr;
+    const CacheKey key{src0_data, src0_type, ne01, K, nb01};
+    auto it = g_cache.find(key);
+    if (it == g_cache.end()) {
+        int rc = ggb_weight_upload(src0_type, ne01, K, src0_data, nb01, &w);
+        if (rc) return rc;
+        g_cache[key] = w;
+    } else {
+        w = it->second;
+    }
+
+    // 2. activations: AoS Q8_0 rows -> device -> planar
+    const int64_t col_num = ne11 * ne12; // ref: src/hpc.cpp:232
+    const size_t q8_stride = ggb_q8_row_bytes(K);
+    int rc;
+    if ((rc = ensure(&g_act_raw, &g_act_raw_cap, (size_t)col_num * row_size))) return rc;
+    if ((rc = ensure(&g_act_q8, &g_act_q8_cap, (size_t)col_num * q8_stride))) return rc;
+    if ((rc = ensure((void **)&g_dst, &g_dst_cap, (size_t)col_num * ne01 * 4))) return rc;
+    cudaStream_t st = ggb_cuda_stream();
+    GGB_CUDA(cudaMemcpyAsync(g_act_raw, wdata, (size_t)col_num * row_size, cudaMemcpyHostToDevice, st));
+    if ((rc = ggb_op_q8_from_blocks(g_act_raw, K, col_num, (int64_t)row_size, g_act_q8))) return rc;
+
+    // 3. every column through the mat-vec kernel (grid.y = column)
+    if ((rc = ggb_op_mul_mat_q8(w, g_act_q8, col_num, g_dst, ne01, nullptr))) return rc;
+
+    // 4. result back with the reference's addressing (ref: src/hpc.cpp:26-31):
+    //    dst + (col % ne1)*nb1 + (col / ne1)*nb2 + row*4
+    if (nb1 == ne01 * 4 && (ne12 == 1 || nb2 == nb1 * ne1)) {
+        GGB_CUDA(cudaMemcpyAsync(dst_data, g_dst, (size_t)col_num * ne01 * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (int64_t col = 0; col < col_num; col++) {
+            char *dcol = (char *)dst_data + (col % ne1) * nb1 + (col / ne1) * nb2;
+            GGB_CUDA(cudaMemcpyAsync(dcol, g_dst + col * ne01, (size_t)ne01 * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    GGB_CUDA(cudaStreamSynchronize(st));
+    return GGB_OK;
+}
+
+int ggb_mul_mat_forget(const void *src0_data) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto it = g_cache.begin(); it != g_cache.end();) {
+        if (src0_data == nullptr || it->first.ptr == src0_data) {
+            ggb_weight_free(it->second);
+            it = g_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    return GGB_OK;
+}
+
+} // extern "C"

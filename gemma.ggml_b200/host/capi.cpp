@@ -1,0 +1,46 @@
+// capi.cpp — flat C entry points over gemma_model so tests / bench.py can drive the host side with
+// ctypes (the reference drives its model from app::run, ref: src/app.cpp:30-44).
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gemma_model.h"
+
+extern "C" {
+
+void *gm_create(const gemma_config *cfg) { return new gemma_model(*cfg); }
+void gm_free(void *m) { delete (gemma_model *)m; }
+int gm_init_synthetic_weights(void *m) { return ((gemma_model *)m)->init_synthetic_weights(); }
+int gm_set_tensor(void *m, int tensor_id, const void *host, int64_t nbytes) {
+    return ((gemma_model *)m)->set_tensor(tensor_id, host, nbytes);
+}
+int gm_init_kv_cache(void *m) { return ((gemma_model *)m)->init_kv_cache(); }
+int gm_fill_kv_cache_synthetic(void *m, uint64_t seed) { return ((gemma_model *)m)->fill_kv_cache_synthetic(seed); }
+int gm_build_compute_graph(void *m, int capture_acts) { return ((gemma_model *)m)->build_compute_graph(capture_acts != 0); }
+int gm_decode_step(void *m, int32_t token, int32_t pos, int32_t *next) {
+    return ((gemma_model *)m)->decode_step(token, pos, next);
+}
+int gm_set_state(void *m, int32_t token, int32_t pos, int32_t pos_step) {
+    return ((gemma_model *)m)->set_state(token, pos, pos_step);
+}
+int gm_run_steps(void *m, int steps) { return ((gemma_model *)m)->run_steps(steps); }
+int gm_run_steps_profiled(void *m, int steps) { return ((gemma_model *)m)->run_steps_profiled(steps); }
+int gm_get_state(void *m, int32_t *token, int32_t *pos) { return ((gemma_model *)m)->get_state(token, pos); }
+int gm_generate(void *m, const int32_t *prompt, int n_prompt, int n_decode, int32_t *out, int *n_out, double *prefill_ms,
+                double *decode_ms) {
+    std::vector<token_id> p(prompt, prompt + n_prompt), o;
+    const int rc = ((gemma_model *)m)->generate(p, n_decode, o, prefill_ms, decode_ms);
+    if (rc) return rc;
+    if (n_out) *n_out = (int)o.size();
+    memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    return 0;
+}
+int gm_get_logits(void *m, float *host) { return ((gemma_model *)m)->get_logits(host); }
+int gm_get_capture(void *m, const char *name, int layer, float *host, int64_t n) {
+    return ((gemma_model *)m)->get_capture(name, layer, host, n);
+}
+int gm_get_kv(void *m, int layer, void *k_host, void *v_host) { return ((gemma_model *)m)->get_kv(layer, k_host, v_host); }
+int gm_kernels_per_step(void *m) { return ((gemma_model *)m)->kernels_per_step(); }
+uint64_t gm_weight_bytes(void *m) { return (uint64_t)((gemma_model *)m)->weight_bytes(); }
+
+} // extern "C"

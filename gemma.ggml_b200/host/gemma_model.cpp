@@ -1,0 +1,352 @@
+// gemma_model.cpp — host side of the decode path.  Mirrors ref: src/gemma_model.cpp
+// (tensor binding :159-194, KV cache :361-401 / :428-436, graph builder :438-530 / :665-747,
+// inference :231-286, greedy round :548-575) with every node lowered to the C-ABI CUDA layer.
+#include "gemma_model.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#define GM_TRY(call)          \
+    do {                      \
+        int rc__ = (call);    \
+        if (rc__) return rc__; \
+    } while (0)
+
+static constexpr float kNormSigma = 0.02f; // norm weights: 1 + N(0, 0.02^2)
+
+gemma_model::gemma_model(const gemma_config &cfg) : cfg_(cfg) { layers_.resize((size_t)cfg.n_layer); }
+
+gemma_model::~gemma_model() { free_all(); }
+
+void gemma_model::free_all() {
+    ggb_sync();
+    ggb_graph_free(graph_);
+    graph_ = nullptr;
+    ggb_weight_free(token_embd_);
+    token_embd_ = nullptr;
+    for (auto &l : layers_) {
+        ggb_weight *ws[] = {l.attn_q, l.attn_k, l.attn_v, l.attn_output, l.ffn_gate, l.ffn_up, l.ffn_down};
+        for (auto *w : ws) ggb_weight_free(w);
+        if (l.attn_norm) ggb_buffer_free(l.attn_norm);
+        if (l.ffn_norm) ggb_buffer_free(l.ffn_norm);
+        l = gemma_layer();
+    }
+    void *bufs[] = {output_norm_, state_, history_, x0_, q_, k_, v_, logits_, result_norm_, sa_out_, l_out_, kqv_,
+                    ffn_act_, act_e_, act_q_, act_f_, attn_scratch_, sample_scratch_};
+    for (void *b : bufs)
+        if (b) ggb_buffer_free(b);
+    output_norm_ = nullptr; state_ = history_ = nullptr; x0_ = q_ = k_ = v_ = logits_ = result_norm_ = nullptr;
+    sa_out_ = l_out_ = kqv_ = ffn_act_ = nullptr; act_e_ = act_q_ = act_f_ = attn_scratch_ = sample_scratch_ = nullptr;
+    for (void *b : k_cache_) ggb_buffer_free(b);
+    for (void *b : v_cache_) ggb_buffer_free(b);
+    k_cache_.clear();
+    v_cache_.clear();
+    if (h_state_) ggb_host_free(h_state_);
+    h_state_ = nullptr;
+}
+
+// ref: composite_model / load_tensors (src/gemma_model.cpp:159-194): token_embd (also the output
+// projection), output_norm, and nine tensors per block.  Here every matrix is generated and
+// quantised ON the device with the shared counter-based generator (seed, tensor id).
+int gemma_model::init_synthetic_weights() {
+    const gemma_config &c = cfg_;
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
+    weight_bytes_ = 0;
+    auto mat = [&](int tid, int64_t rows, int64_t cols, ggb_weight **out) -> int {
+        const float sigma = tid == GM_T_TOKEN_EMBD ? c.sigma_embd : c.sigma_mat;
+        GM_TRY(ggb_weight_synth(c.wtype, rows, cols, c.seed, (uint64_t)tid, sigma, out));
+        weight_bytes_ += ggb_weight_algorithmic_bytes(*out);
+        return 0;
+    };
+    auto vec = [&](int tid, int64_t n, float **out) -> int {
+        GM_TRY(ggb_buffer_alloc((size_t)n * 4, (void **)out));
+        return ggb_vector_synth(*out, n, c.seed, (uint64_t)tid, kNormSigma, 1.0f);
+    };
+    GM_TRY(mat(GM_T_TOKEN_EMBD, V, E, &token_embd_));
+    GM_TRY(vec(GM_T_OUTPUT_NORM, E, &output_norm_));
+    for (int il = 0; il < c.n_layer; il++) {
+        const int b = GM_T_LAYER0 + GM_T_PER_LAYER * il;
+        gemma_layer &l = layers_[(size_t)il];
+        GM_TRY(vec(b + GM_L_ATTN_NORM, E, &l.attn_norm));
+        GM_TRY(mat(b + GM_L_ATTN_Q, QD, E, &l.attn_q));
+        GM_TRY(mat(b + GM_L_ATTN_K, KD, E, &l.attn_k));
+        GM_TRY(mat(b + GM_L_ATTN_V, KD, E, &l.attn_v));
+        GM_TRY(mat(b + GM_L_ATTN_OUT, E, QD, &l.attn_output));
+        GM_TRY(vec(b + GM_L_FFN_NORM, E, &l.ffn_norm));
+        GM_TRY(mat(b + GM_L_FFN_GATE, F, E, &l.ffn_gate));
+        GM_TRY(mat(b + GM_L_FFN_UP, F, E, &l.ffn_up));
+        GM_TRY(mat(b + GM_L_FFN_DOWN, E, F, &l.ffn_down));
+    }
+    return ggb_sync();
+}
+
+// upload one tensor from host memory (ggml AoS blocks for matrices, f32 for norms)
+int gemma_model::set_tensor(int tensor_id, const void *host_data, int64_t nbytes) {
+    const gemma_config &c = cfg_;
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
+    auto mat = [&](ggb_weight **slot, int64_t rows, int64_t cols) -> int {
+        const int64_t need = rows * (cols / 32) * (c.wtype == GGB_TYPE_Q4_0 ? 18 : 34);
+        if (nbytes != need) return GGB_ERR_ARG;
+        if (*slot) weight_bytes_ -= ggb_weight_algorithmic_bytes(*slot);
+        ggb_weight_free(*slot);
+        *slot = nullptr;
+        GM_TRY(ggb_weight_upload(c.wtype, rows, cols, host_data, 0, slot));
+        weight_bytes_ += ggb_weight_algorithmic_bytes(*slot);
+        return 0;
+    };
+    auto vec = [&](float **slot, int64_t n) -> int {
+        if (nbytes != n * 4) return GGB_ERR_ARG;
+        if (!*slot) GM_TRY(ggb_buffer_alloc((size_t)n * 4, (void **)slot));
+        GM_TRY(ggb_upload(*slot, host_data, (size_t)n * 4));
+        return ggb_sync();
+    };
+    if (tensor_id == GM_T_TOKEN_EMBD) return mat(&token_embd_, V, E);
+    if (tensor_id == GM_T_OUTPUT_NORM) return vec(&output_norm_, E);
+    const int rel = tensor_id - GM_T_LAYER0;
+    if (rel < 0 || rel >= GM_T_PER_LAYER * c.n_layer) return GGB_ERR_ARG;
+    gemma_layer &l = layers_[(size_t)(rel / GM_T_PER_LAYER)];
+    switch (rel % GM_T_PER_LAYER) {
+    case GM_L_ATTN_NORM: return vec(&l.attn_norm, E);
+    case GM_L_ATTN_Q: return mat(&l.attn_q, QD, E);
+    case GM_L_ATTN_K: return mat(&l.attn_k, KD, E);
+    case GM_L_ATTN_V: return mat(&l.attn_v, KD, E);
+    case GM_L_ATTN_OUT: return mat(&l.attn_output, E, QD);
+    case GM_L_FFN_NORM: return vec(&l.ffn_norm, E);
+    case GM_L_FFN_GATE: return mat(&l.ffn_gate, F, E);
+    case GM_L_FFN_UP: return mat(&l.ffn_up, F, E);
+    case GM_L_FFN_DOWN: return mat(&l.ffn_down, E, F);
+    }
+    return GGB_ERR_ARG;
+}
+
+// ref: init_kv_cache (:361-401): per layer one F16 K and one F16 V tensor, zeroed.  Device layout is
+// position-major [n_ctx][n_head_kv*head_dim] for both (see csrc/attention.cu).
+int gemma_model::init_kv_cache() {
+    const size_t bytes = (size_t)cfg_.n_ctx * cfg_.n_head_kv * cfg_.head_dim * 2;
+    for (int il = 0; il < cfg_.n_layer; il++) {
+        void *k = nullptr, *v = nullptr;
+        if ((int)k_cache_.size() <= il) {
+            GM_TRY(ggb_buffer_alloc(bytes, &k));
+            GM_TRY(ggb_buffer_alloc(bytes, &v));
+            k_cache_.push_back(k);
+            v_cache_.push_back(v);
+        }
+        GM_TRY(ggb_buffer_memset(k_cache_[(size_t)il], 0, bytes));
+        GM_TRY(ggb_buffer_memset(v_cache_[(size_t)il], 0, bytes));
+    }
+    GM_TRY(ggb_rope_table_init(cfg_.n_ctx, cfg_.head_dim, cfg_.rope_base));
+    return ggb_sync();
+}
+
+int gemma_model::fill_kv_cache_synthetic(uint64_t seed) {
+    const int64_t n = (int64_t)cfg_.n_ctx * cfg_.n_head_kv * cfg_.head_dim;
+    float *tmp = nullptr;
+    GM_TRY(ggb_buffer_alloc((size_t)n * 4, (void **)&tmp));
+    for (int il = 0; il < cfg_.n_layer; il++) {
+        GM_TRY(ggb_vector_synth(tmp, n, seed, (uint64_t)(2 * il), 1.0f, 0.0f));
+        GM_TRY(ggb_op_cpy_f32_f16(tmp, n, k_cache_[(size_t)il]));
+        GM_TRY(ggb_vector_synth(tmp, n, seed, (uint64_t)(2 * il + 1), 1.0f, 0.0f));
+        GM_TRY(ggb_op_cpy_f32_f16(tmp, n, v_cache_[(size_t)il]));
+    }
+    GM_TRY(ggb_sync());
+    return ggb_buffer_free(tmp);
+}
+
+int gemma_model::alloc_buffers() {
+    const gemma_config &c = cfg_;
+    const size_t E = (size_t)c.n_embd, F = (size_t)c.n_ff, V = (size_t)c.n_vocab, L = (size_t)c.n_layer;
+    const size_t QD = (size_t)c.n_head * c.head_dim, KD = (size_t)c.n_head_kv * c.head_dim;
+    if (state_) return 0;
+    GM_TRY(ggb_buffer_alloc(16, (void **)&state_));
+    GM_TRY(ggb_buffer_alloc(((size_t)c.n_ctx + 2) * 4, (void **)&history_));
+    GM_TRY(ggb_host_alloc(32, (void **)&h_state_));
+    GM_TRY(ggb_buffer_alloc(E * 4, (void **)&x0_));
+    GM_TRY(ggb_buffer_alloc(QD * 4, (void **)&q_));
+    GM_TRY(ggb_buffer_alloc(KD * 4, (void **)&k_));
+    GM_TRY(ggb_buffer_alloc(KD * 4, (void **)&v_));
+    GM_TRY(ggb_buffer_alloc(V * 4, (void **)&logits_));
+    GM_TRY(ggb_buffer_alloc(E * 4, (void **)&result_norm_));
+    GM_TRY(ggb_buffer_alloc(L * E * 4, (void **)&sa_out_));
+    GM_TRY(ggb_buffer_alloc(L * E * 4, (void **)&l_out_));
+    GM_TRY(ggb_buffer_alloc(L * QD * 4, (void **)&kqv_));
+    GM_TRY(ggb_buffer_alloc(L * F * 4, (void **)&ffn_act_));
+    GM_TRY(ggb_buffer_alloc(ggb_q8_row_bytes((int64_t)E), &act_e_));
+    GM_TRY(ggb_buffer_alloc(ggb_q8_row_bytes((int64_t)QD), &act_q_));
+    GM_TRY(ggb_buffer_alloc(ggb_q8_row_bytes((int64_t)F), &act_f_));
+    GM_TRY(ggb_buffer_alloc(ggb_attn_scratch_bytes(c.n_head, c.head_dim, c.n_ctx), &attn_scratch_));
+    GM_TRY(ggb_buffer_alloc(ggb_sample_scratch_bytes((int64_t)V), &sample_scratch_));
+    GM_TRY(ggb_buffer_memset(state_, 0, 16));
+    GM_TRY(ggb_buffer_memset(history_, 0, ((size_t)c.n_ctx + 2) * 4));
+    return ggb_sync();
+}
+
+// The op sequence of ONE token — the reference's per-layer node list (SURVEY.md §3.3,
+// ref: src/gemma_model.cpp:688-740) with adjacent nodes fused:
+//   norm+mul+quantize | Q,K,V mat-vecs | rope+scale+KV store | kq/softmax/kqv split-K (+quantize)
+//   | o-proj + residual | norm+mul+quantize | gate,up mat-vecs + gelu*up + quantize | down + residual
+// profiling probe with the reference's name keys (ref: notes.md:68-91 "op_mul_mat", "op_rms_norm", ...;
+// src/profiling.h:14-18 profile(str, code)); a no-op unless ggb_prof_enable(1) and not capturing
+#define PROFILE(name, call)          \
+    do {                             \
+        ggb_prof_start(name);        \
+        const int rc__ = (call);     \
+        ggb_prof_stop(name);         \
+        if (rc__) return rc__;       \
+    } while (0)
+
+int gemma_model::emit_decode_step() {
+    const gemma_config &c = cfg_;
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim;
+    const float q_scale = 1.0f / sqrtf((float)c.head_dim);                                          // :708
+    PROFILE("op_get_rows", ggb_op_embed_token(token_embd_, state_, sqrtf((float)c.n_embd), x0_));   // :675-679
+    const float *x_in = x0_;
+    for (int il = 0; il < c.n_layer; il++) {
+        const gemma_layer &l = layers_[(size_t)il];
+        float *sa = sa_out_ + (size_t)il * E, *lo = l_out_ + (size_t)il * E, *kqv = kqv_ + (size_t)il * QD;
+        PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, l.attn_norm, c.eps, E, 1, nullptr, act_e_));   // :690
+        const ggb_weight *qkv[3] = {l.attn_q, l.attn_k, l.attn_v};
+        float *qkv_dst[3] = {q_, k_, v_};
+        PROFILE("op_mul_mat", ggb_op_mul_mat_q8_multi(3, qkv, act_e_, qkv_dst));                    // :692-696
+        PROFILE("op_rope", ggb_op_rope_kv_store(q_, k_, v_, state_ + 1, c.n_head, c.n_head_kv, c.head_dim, q_scale,
+                                                k_cache_[(size_t)il], v_cache_[(size_t)il]));       // :698-716, :499-518
+        PROFILE("op_attn", ggb_op_attn_decode(q_, k_cache_[(size_t)il], v_cache_[(size_t)il], state_ + 1, c.n_head,
+                                              c.n_head_kv, c.head_dim, c.n_ctx, attn_scratch_, kqv, act_q_)); // :454-489
+        PROFILE("op_mul_mat", ggb_op_mul_mat_q8(l.attn_output, act_q_, 1, sa, E, x_in));            // :493 + :723
+        PROFILE("op_rms_norm", ggb_op_rms_norm(sa, l.ffn_norm, c.eps, E, 1, nullptr, act_e_));      // :724
+        PROFILE("op_mul_mat", ggb_op_ffn_gate_up(l.ffn_gate, l.ffn_up, act_e_, act_f_,
+                                                 capture_acts_ ? ffn_act_ + (size_t)il * F : nullptr)); // :446-449
+        PROFILE("op_mul_mat", ggb_op_mul_mat_q8(l.ffn_down, act_f_, 1, lo, E, sa));                 // :450 + :731
+        x_in = lo;
+    }
+    PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, output_norm_, c.eps, E, 1, result_norm_, act_e_)); // :738
+    PROFILE("op_mul_mat", ggb_op_mul_mat_q8(token_embd_, act_e_, 1, logits_, V, nullptr));          // :740 (tied)
+    PROFILE("op_argmax", ggb_op_sample_greedy(logits_, V, state_, history_, sample_scratch_));      // :532-546
+    return 0;
+}
+
+// eager (un-captured) steps with the cudaEvent probes live: per-op-class device time
+int gemma_model::run_steps_profiled(int steps) {
+    if (!graph_) return GGB_ERR_ARG;
+    ggb_prof_enable(1);
+    int rc = 0;
+    for (int i = 0; i < steps && !rc; i++) rc = emit_decode_step();
+    ggb_sync();
+    ggb_prof_enable(0);
+    return rc;
+}
+
+int gemma_model::build_compute_graph(bool capture_acts) {
+    if (!token_embd_ || k_cache_.empty()) return GGB_ERR_ARG;
+    GM_TRY(alloc_buffers());
+    capture_acts_ = capture_acts;
+    ggb_graph_free(graph_);
+    graph_ = nullptr;
+    GM_TRY(ggb_sync());
+    GM_TRY(ggb_capture_begin());
+    const int rc = emit_decode_step();
+    ggb_graph *g = nullptr;
+    const int rc2 = ggb_capture_end(&g);
+    if (rc) {
+        ggb_graph_free(g);
+        return rc;
+    }
+    GM_TRY(rc2);
+    graph_ = g;
+    return 0;
+}
+
+int gemma_model::set_state(token_id token, int32_t pos, int32_t pos_step) {
+    if (pos < 0 || pos >= cfg_.n_ctx) return GGB_ERR_ARG;
+    h_state_[0] = token;
+    h_state_[1] = pos;
+    h_state_[2] = pos_step;
+    h_state_[3] = 0;
+    return ggb_upload(state_, h_state_, 16);
+}
+
+int gemma_model::run_steps(int steps) {
+    if (!graph_) return GGB_ERR_ARG;
+    for (int i = 0; i < steps; i++) GM_TRY(ggb_graph_launch(graph_));
+    return 0;
+}
+
+int gemma_model::get_state(token_id *token, int32_t *pos) {
+    int32_t tmp[4];
+    GM_TRY(ggb_download(tmp, state_, 16));
+    if (token) *token = tmp[0];
+    if (pos) *pos = tmp[1];
+    return 0;
+}
+
+// host-buffer step: the e2e path (pinned H2D of the inputs, graph, D2H of the sampled token)
+int gemma_model::decode_step(token_id token, int32_t pos, token_id *next) {
+    GM_TRY(set_state(token, pos, 1));
+    GM_TRY(ggb_graph_launch(graph_));
+    GM_TRY(ggb_download(h_state_ + 4, state_, 4)); // pinned: a true async D2H + stream sync
+    if (next) *next = h_state_[4];
+    return 0;
+}
+
+// ref: inference() (:231-286).  PREFILL walks the prompt one position at a time through the decode
+// graph (bit-identical to the reference's batched prefill because every column of a ggml mul_mat and
+// every soft-max row is computed independently); the tcgen05 GEMM prefill is a separate path.
+int gemma_model::inference(std::vector<token_id> &input, inference_stage stage) {
+    if (input.empty() || !graph_) return GGB_ERR_ARG;
+    token_id next = -1;
+    if (stage == inference_stage::PREFILL) {
+        for (size_t t = 0; t < input.size(); t++) GM_TRY(decode_step(input[t], (int32_t)t, &next));
+    } else {
+        GM_TRY(decode_step(input.back(), (int32_t)input.size() - 1, &next));
+    }
+    input.push_back(next);
+    return 0;
+}
+
+// ref: begin_one_round_inference (:548-575) with a caller-supplied prompt and token budget
+int gemma_model::generate(const std::vector<token_id> &prompt, int n_decode, std::vector<token_id> &out,
+                          double *prefill_ms, double *decode_ms) {
+    using clk = std::chrono::high_resolution_clock;
+    std::vector<token_id> input = prompt;
+    GM_TRY(init_kv_cache());
+    const auto t0 = clk::now();
+    GM_TRY(inference(input, inference_stage::PREFILL));
+    const auto t1 = clk::now();
+    while ((int)(input.size() - prompt.size()) < n_decode && (int)input.size() < cfg_.n_ctx)
+        GM_TRY(inference(input, inference_stage::DECODE));
+    const auto t2 = clk::now();
+    out.assign(input.begin() + (long)prompt.size(), input.end());
+    if (prefill_ms) *prefill_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (decode_ms) *decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    return 0;
+}
+
+int gemma_model::get_logits(float *host) const { return ggb_download(host, logits_, (size_t)cfg_.n_vocab * 4); }
+
+// tensor_dump-style access to named intermediates of the last step (ref: src/tensor_dump.cpp:11-27)
+int gemma_model::get_capture(const std::string &name, int layer, float *host, int64_t n) const {
+    const size_t E = (size_t)cfg_.n_embd, F = (size_t)cfg_.n_ff, QD = (size_t)cfg_.n_head * cfg_.head_dim;
+    const float *src = nullptr;
+    size_t len = 0;
+    if (layer < 0 || layer >= cfg_.n_layer) layer = 0;
+    if (name == "l_out") { src = l_out_ + (size_t)layer * E; len = E; }
+    else if (name == "sa_out") { src = sa_out_ + (size_t)layer * E; len = E; }
+    else if (name == "kqv_out") { src = kqv_ + (size_t)layer * QD; len = QD; }
+    else if (name == "ffn_act") { src = capture_acts_ ? ffn_act_ + (size_t)layer * F : nullptr; len = F; }
+    else if (name == "result_norm") { src = result_norm_; len = E; }
+    else if (name == "result_output") { src = logits_; len = (size_t)cfg_.n_vocab; }
+    if (!src || (size_t)n != len) return GGB_ERR_ARG;
+    return ggb_download(host, src, len * 4);
+}
+
+int gemma_model::get_kv(int layer, void *k_host, void *v_host) const {
+    if (layer < 0 || layer >= (int)k_cache_.size()) return GGB_ERR_ARG;
+    const size_t bytes = (size_t)cfg_.n_ctx * cfg_.n_head_kv * cfg_.head_dim * 2;
+    if (k_host) GM_TRY(ggb_download(k_host, k_cache_[(size_t)layer], bytes));
+    if (v_host) GM_TRY(ggb_download(v_host, v_cache_[(size_t)layer], bytes));
+    return 0;
+}

@@ -1,0 +1,95 @@
+// gemma_model.h — host-side model: tensor binding, KV cache, graph builder, greedy sampler.
+// Mirrors the reference's class of the same name (ref: src/gemma_model.h:100-236,
+// src/gemma_model.cpp) with the graph builder rewired to the C-ABI CUDA layer: instead of ggml
+// nodes evaluated by ggml_graph_compute_with_ctx (ref: src/gemma_model.cpp:237) the builder
+// enqueues ggb_op_* calls that are captured once into a CUDA graph and replayed per token.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "ggml_b200.h"
+
+typedef int32_t token_id; // ref: src/type.h
+
+enum class inference_stage { PREFILL, DECODE }; // ref: src/gemma_model.h:25-28
+
+// ref: gemma_hyper_param (src/gemma_model.h:30-40), read from GGUF keys at :403-415.  head_dim is
+// explicit (the reference derives n_embd/n_head, wrong for Gemma-7B).
+struct gemma_config {
+    int32_t n_embd, n_layer, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
+    float eps, rope_base;
+    int32_t wtype;
+    int32_t pad_;
+    uint64_t seed;
+    float sigma_embd, sigma_mat;
+};
+
+// tensor ids in the reference's binding order (ref: src/gemma_model.cpp:159-194)
+enum { GM_T_TOKEN_EMBD = 0, GM_T_OUTPUT_NORM = 1, GM_T_LAYER0 = 2, GM_T_PER_LAYER = 9 };
+enum { GM_L_ATTN_NORM = 0, GM_L_ATTN_Q, GM_L_ATTN_K, GM_L_ATTN_V, GM_L_ATTN_OUT,
+       GM_L_FFN_NORM, GM_L_FFN_GATE, GM_L_FFN_UP, GM_L_FFN_DOWN };
+
+struct gemma_layer { // ref: gemma_layer (src/gemma_model.h:42-50 region)
+    float *attn_norm = nullptr, *ffn_norm = nullptr;
+    ggb_weight *attn_q = nullptr, *attn_k = nullptr, *attn_v = nullptr, *attn_output = nullptr;
+    ggb_weight *ffn_gate = nullptr, *ffn_up = nullptr, *ffn_down = nullptr;
+};
+
+class gemma_model {
+  public:
+    explicit gemma_model(const gemma_config &cfg);
+    ~gemma_model();
+
+    // weights: synthetic (generated on the device) or uploaded tensor by tensor
+    int init_synthetic_weights();
+    int set_tensor(int tensor_id, const void *host_data, int64_t nbytes);
+    int init_kv_cache();                       // ref: :361-401
+    int fill_kv_cache_synthetic(uint64_t seed); // bandwidth sweeps
+    int build_compute_graph(bool capture_acts); // ref: :665-747
+
+    // ref: inference() (:231-286): appends the sampled token to `input`
+    int inference(std::vector<token_id> &input, inference_stage stage);
+    // ref: begin_one_round_inference() (:548-575)
+    int generate(const std::vector<token_id> &prompt, int n_decode, std::vector<token_id> &out, double *prefill_ms,
+                 double *decode_ms);
+
+    // one decode step through host buffers: H2D (token,pos), graph, D2H next token
+    int decode_step(token_id token, int32_t pos, token_id *next);
+    // device-resident loop: `steps` graph launches, no host round trip; pos_step 0 pins n_kv
+    int set_state(token_id token, int32_t pos, int32_t pos_step);
+    int run_steps(int steps);
+    int run_steps_profiled(int steps); // eager, cudaEvent probes per op class
+    int get_state(token_id *token, int32_t *pos);
+
+    int get_logits(float *host) const;
+    int get_capture(const std::string &name, int layer, float *host, int64_t n) const;
+    int get_kv(int layer, void *k_host, void *v_host) const;
+    int kernels_per_step() const { return graph_ ? ggb_graph_kernel_count(graph_) : 0; }
+    size_t weight_bytes() const { return weight_bytes_; }
+    const gemma_config &config() const { return cfg_; }
+
+  private:
+    int alloc_buffers();
+    int emit_decode_step(); // the op sequence of one token
+    void free_all();
+
+    gemma_config cfg_;
+    ggb_weight *token_embd_ = nullptr; // also the output projection (tied, ref: :163)
+    float *output_norm_ = nullptr;
+    std::vector<gemma_layer> layers_;
+    std::vector<void *> k_cache_, v_cache_; // ref: kv_cache (src/gemma_model.h:83-97)
+    size_t weight_bytes_ = 0;
+
+    // device-resident step state: [token, pos, pos_step]
+    int32_t *state_ = nullptr, *history_ = nullptr;
+    int32_t *h_state_ = nullptr; // pinned
+    // activations
+    float *x0_ = nullptr, *q_ = nullptr, *k_ = nullptr, *v_ = nullptr, *logits_ = nullptr, *result_norm_ = nullptr;
+    float *sa_out_ = nullptr, *l_out_ = nullptr, *kqv_ = nullptr, *ffn_act_ = nullptr; // per layer slots
+    void *act_e_ = nullptr, *act_q_ = nullptr, *act_f_ = nullptr;                      // planar Q8_0
+    void *attn_scratch_ = nullptr, *sample_scratch_ = nullptr;
+    bool capture_acts_ = false;
+    ggb_graph *graph_ = nullptr;
+};

@@ -1,0 +1,193 @@
+/*
+ * ggml_b200.h — the C-ABI CUDA layer (libggb_cuda.so) that replaces the reference's OpenCL
+ * offload: src/opencl.{h,cpp} (device runtime) and src/kernals.cl (kernels), and is what
+ * the rewired src/hpc.cpp dispatch and the graph builder of src/gemma_model.cpp call.
+ *
+ * Plain C: pointers, sizes, ints.  No torch / C++ types.  Every entry returns GGB_OK (0) or a
+ * negative ggb_status; ggb_last_error() gives the text (the reference exits the process on
+ * error, src/opencl.cpp:13-17 — a library cannot, so failures are returned and are loud).
+ * There is no CPU fallback anywhere below this header: with no CUDA device ggb_init fails.
+ *
+ * Unless stated otherwise "device pointer" arguments come from ggb_buffer_alloc and every
+ * ggb_op_* call is ASYNCHRONOUS on the library's stream; ggb_sync() waits
+ * (ref: wait_queue_finish, src/opencl.h:37).
+ */
+#ifndef GGML_B200_H
+#define GGML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GGB_OK = 0,
+    GGB_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+    GGB_ERR_ARG = -2,         /* bad argument / unsupported shape */
+    GGB_ERR_NOT_INIT = -3,    /* ggb_init not called or failed */
+    GGB_ERR_UNSUPPORTED = -4, /* tensor type without a kernel (ref: "kernel is null", src/hpc.cpp:162-166) */
+    GGB_ERR_NCCL = -5
+} ggb_status;
+
+/* ggml_type values the path uses (upstream enum ids; ref: src/hpc.cpp:132-143) */
+enum { GGB_TYPE_F32 = 0, GGB_TYPE_F16 = 1, GGB_TYPE_Q4_0 = 2, GGB_TYPE_Q8_0 = 8 };
+
+/* Deterministic reduction orders of the kernels ("DEV order"; the oracle mirrors them):
+ * mat-vec: K cut into segments of GGB_DEV_SEG_BLOCKS blocks, 32 lane-strided partials per
+ * segment, xor-butterfly, segments added in order.  rms_norm: GGB_DEV_NORM_THREADS strided
+ * double partials.  attention: split-K chunks of GGB_DEV_ATTN_CHUNK positions. */
+#define GGB_DEV_SEG_BLOCKS 128
+#define GGB_DEV_NORM_THREADS 256
+#define GGB_DEV_ATTN_CHUNK 32
+
+/* ------------------------------------------------------------------ runtime
+ * replaces: init_opencl / set_platform_and_device / setup_opencl_env / build_all_kernels
+ * (src/opencl.h:22-30, src/opencl.cpp:161-245, 350-356), print_now_using (:100),
+ * wait_queue_finish (:309), release_opencl_env (:247). */
+int ggb_init(int device);
+int ggb_shutdown(void);
+const char *ggb_last_error(void);
+int ggb_device_info(char *buf, size_t buflen); /* name, SMs, memory, compute capability */
+int ggb_sm_count(void);
+int ggb_sync(void);
+void *ggb_stream(void); /* the cudaStream_t all ops are enqueued on */
+int64_t ggb_launch_count(void); /* kernels launched (or replayed via graphs) since init */
+
+/* replaces: create_buffer / release_buffer_in_set (src/opencl.h:35,38; src/opencl.cpp:313-348).
+ * Buffers are device-resident and live until freed (the reference re-wraps host memory per
+ * mul_mat call, src/hpc.cpp:168-170,196 — only viable on a zero-copy iGPU). */
+int ggb_buffer_alloc(size_t bytes, void **dptr);
+int ggb_buffer_free(void *dptr);
+int ggb_buffer_memset(void *dptr, int value, size_t bytes);
+int ggb_upload(void *dst_dev, const void *src_host, size_t bytes);   /* async if src is pinned */
+int ggb_download(void *dst_host, const void *src_dev, size_t bytes); /* synchronous */
+int ggb_host_alloc(size_t bytes, void **hptr); /* pinned host memory */
+int ggb_host_free(void *hptr);
+
+/* replaces the profiling probes (src/profiling.h:10-57: _start_recording/_stop_recording/
+ * _print_profiling_result) with cudaEvent pairs keyed by the same kind of name strings. */
+int ggb_prof_enable(int on);
+int ggb_prof_start(const char *name);
+int ggb_prof_stop(const char *name);
+int ggb_prof_reset(void);
+/* total ms and call count accumulated under `name` (resolves pending events; syncs) */
+int ggb_prof_get(const char *name, double *total_ms, int64_t *calls);
+int ggb_prof_report(char *buf, size_t buflen);
+
+/* CUDA-graph capture of a sequence of ggb_op_* calls (one decode step) */
+typedef struct ggb_graph ggb_graph;
+int ggb_capture_begin(void);
+int ggb_capture_end(ggb_graph **out);
+int ggb_graph_launch(ggb_graph *g);
+int ggb_graph_free(ggb_graph *g);
+int ggb_graph_kernel_count(const ggb_graph *g);
+
+/* ------------------------------------------------------------------ weights
+ * A quantised matrix [rows][cols] uploaded ONCE and repacked to the device layout
+ * (SoA: one plane of 16 B (Q4_0) / 32 B (Q8_0) quant payloads, one plane of fp16 scales). */
+typedef struct ggb_weight ggb_weight;
+int ggb_weight_upload(int type, int64_t rows, int64_t cols, const void *host_blocks, int64_t nb01,
+                      ggb_weight **out);
+/* synthetic matrix generated and quantised on the device (SURVEY.md §8d generator):
+ * value(row, col) = synth(seed, tensor_id, row*cols + col) * sigma; bit-identical to the oracle's. */
+int ggb_weight_synth(int type, int64_t rows, int64_t cols, uint64_t seed, uint64_t tensor_id, float sigma,
+                     ggb_weight **out);
+/* rows [row0, row0+nrows) of an existing weight as a new handle (no copy) — TP row shards */
+int ggb_weight_slice(const ggb_weight *w, int64_t row0, int64_t nrows, ggb_weight **out);
+int ggb_weight_download(const ggb_weight *w, void *host_blocks); /* back to ggml AoS blocks */
+int ggb_weight_free(ggb_weight *w);
+int64_t ggb_weight_rows(const ggb_weight *w);
+int64_t ggb_weight_cols(const ggb_weight *w);
+int ggb_weight_type(const ggb_weight *w);
+size_t ggb_weight_algorithmic_bytes(const ggb_weight *w); /* rows * cols/32 * (18|34) */
+/* f32 vector filled with bias + synth()*sigma (norm weights) */
+int ggb_vector_synth(float *dst_dev, int64_t n, uint64_t seed, uint64_t tensor_id, float sigma, float bias);
+
+/* ------------------------------------------------------------------ drop-in mul_mat
+ * replaces: extern "C" void mul_mat(...) (src/hpc.h:22-32, src/hpc.cpp:216-277) — same
+ * fields, HOST pointers, synchronous: on return all of dst is written.  src0_data/dst_data
+ * are src0->data / dst->data of the ggml tensors; vec_dot is gone (the kernel is chosen by
+ * src0_type).  wdata = src1 already converted to Q8_0 rows of `row_size` bytes by ggml's INIT
+ * stage.  src0 is uploaded and repacked on first use and cached by (pointer, shape); call
+ * ggb_mul_mat_forget(ptr) if the host copy changes. */
+int ggb_mul_mat(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64_t ne1, int64_t nb1, int64_t nb2,
+                size_t row_size, int64_t shared_edge, const void *src0_data, void *dst_data, int src0_type,
+                const char *wdata);
+int ggb_mul_mat_forget(const void *src0_data);
+
+/* ------------------------------------------------------------------ device operators
+ * One entry per graph node kind the builder emits (ref: src/gemma_model.cpp:438-530, 665-747),
+ * plus the fused forms the decode step uses.  All pointers are device pointers. */
+
+/* planar Q8_0 activations: per row `cols` int8 followed by cols/32 fp16 scales */
+size_t ggb_q8_row_bytes(int64_t cols);
+/* K1 — quantize_row_q8_0 (ggml mul_mat INIT stage): T rows of `cols` floats -> planar Q8_0 */
+int ggb_op_quantize_q8_0(const float *x, int64_t cols, int64_t T, void *q8);
+int ggb_op_q8_to_blocks(const void *q8, int64_t cols, int64_t T, void *blocks);   /* planar -> ggml AoS (34 B) */
+int ggb_op_q8_from_blocks(const void *blocks, int64_t cols, int64_t T, int64_t row_size, void *q8);
+
+/* K2/K3 — dst[t][row] = dot(w[row], q8[t]) (+ residual[t][row]); dst row pitch dst_stride floats */
+int ggb_op_mul_mat_q8(const ggb_weight *w, const void *q8, int64_t T, float *dst, int64_t dst_stride,
+                      const float *residual);
+/* up to 3 weights sharing one activation row, one launch (Q/K/V) */
+int ggb_op_mul_mat_q8_multi(int n, const ggb_weight *const *w, const void *q8, float *const *dst);
+/* FFN front half: q8_out = quantize( gelu(gate·x) * (up·x) ); act_f32 optional (dump) */
+int ggb_op_ffn_gate_up(const ggb_weight *gate, const ggb_weight *up, const void *q8, void *q8_out,
+                       float *act_f32);
+
+/* K5 — rms_norm (+ weight mul when w != NULL) over T rows of E floats; y and/or q8 may be NULL */
+int ggb_op_rms_norm(const float *x, const float *w, float eps, int64_t E, int64_t T, float *y, void *q8);
+/* element-wise nodes */
+int ggb_op_add(const float *a, const float *b, int64_t n, float *y);
+int ggb_op_mul(const float *a, const float *b, int64_t n, float *y);
+int ggb_op_scale(const float *x, float s, int64_t n, float *y);
+int ggb_op_gelu(const float *x, int64_t n, float *y);
+/* soft_max_ext(x*scale + mask), max_bias 0 (standalone node, REF semantics except the
+ * double sum is a 256-way strided reduction); rows of nc floats; mask may be NULL */
+int ggb_op_soft_max_ext(const float *x, const float *mask, float scale, int64_t nc, int64_t nrows, float *y);
+/* K6 — rope NEOX on [n_heads][n_dims] rows for T tokens with positions pos[T] (device int32) */
+int ggb_op_rope_neox(const float *x, const int32_t *pos, int n_dims, int n_heads, int64_t T, float *y);
+/* K8 — get_rows(token_embd, ids) * scale */
+int ggb_op_get_rows(const ggb_weight *table, const int32_t *ids, int64_t T, float scale, float *y);
+/* K9 — first maximum (strict >); result index written to *out (device int32) */
+int ggb_op_argmax(const float *x, int64_t n, int32_t *out);
+int ggb_op_cpy_f32_f16(const float *x, int64_t n, void *y_f16);
+
+/* rope tables (host libm recurrence, uploaded once); must be called before rope / decode ops */
+int ggb_rope_table_init(int n_ctx, int n_dims, float freq_base);
+
+/* K6 fused: q <- rope(q)*q_scale in place; kcache[pos] <- f16(rope(k)); vcache[pos] <- f16(v).
+ * caches are position-major fp16 [n_ctx][Hkv*d]; *pos is a device int32 */
+int ggb_op_rope_kv_store(float *q, const float *k, const float *v, const int32_t *pos, int H, int Hkv, int d,
+                         float q_scale, void *kcache, void *vcache);
+/* K4 — split-K decode attention over positions [0, *pos]; scratch from ggb_attn_scratch_bytes.
+ * out f32 [H*d] and/or q8 (planar, cols = H*d) */
+size_t ggb_attn_scratch_bytes(int H, int d, int n_ctx);
+int ggb_op_attn_decode(const float *q, const void *kcache, const void *vcache, const int32_t *pos, int H, int Hkv,
+                       int d, int n_ctx, void *scratch, float *out, void *q8_out);
+
+/* decode-step glue kept on the device so a captured step can be replayed:
+ * state[0] = current token id, state[1] = its position, state[2] = position increment per step
+ * (1 for generation; 0 pins n_kv for fixed-context bandwidth measurements) */
+int ggb_op_embed_token(const ggb_weight *table, const int32_t *state, float scale, float *y);
+/* state[0] <- argmax(logits), state[1] += state[2], history[state[1]] <- token (history may be NULL) */
+int ggb_op_sample_greedy(const float *logits, int64_t n, int32_t *state, int32_t *history, void *scratch);
+size_t ggb_sample_scratch_bytes(int64_t n);
+
+/* ------------------------------------------------------------------ multi-GPU (row-sharded TP)
+ * one process per GPU; the 128-byte NCCL unique id is created on rank 0 and shipped by the
+ * caller (torch.distributed / any transport). */
+int ggb_comm_unique_id(void *id128);
+int ggb_comm_init(const void *id128, int rank, int world);
+int ggb_comm_destroy(void);
+int ggb_comm_rank(void);
+int ggb_comm_size(void);
+/* allgather of `bytes` per rank, in place layout: recv[rank*bytes .. ) */
+int ggb_op_allgather(const void *send, void *recv, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGML_B200_H */

@@ -238,6 +238,18 @@ void orc_model_reset(orc_model *m) {
     }
 }
 
+/* KV cache pre-filled with seeded ~N(0,1) values rounded to fp16 (bandwidth sweeps);
+ * same generator and tensor ids (2*layer, 2*layer+1) as the device-side fill. */
+void orc_model_fill_kv_synth(orc_model *m, uint64_t seed) {
+    const int64_t n = (int64_t)m->cfg.n_ctx * m->cfg.n_head_kv * m->cfg.head_dim;
+    for (int il = 0; il < m->cfg.n_layer; il++) {
+        for (int64_t i = 0; i < n; i++) {
+            m->kc[il][i] = orc_fp32_to_fp16(0.0f + orc_synth_value(seed, (uint64_t)(2 * il), (uint64_t)i, 1.0f));
+            m->vc[il][i] = orc_fp32_to_fp16(0.0f + orc_synth_value(seed, (uint64_t)(2 * il + 1), (uint64_t)i, 1.0f));
+        }
+    }
+}
+
 uint16_t *orc_model_kcache(orc_model *m, int layer) { return m->kc[layer]; }
 uint16_t *orc_model_vcache(orc_model *m, int layer) { return m->vc[layer]; }
 

@@ -81,6 +81,7 @@ def lib():
         "orc_model_free": (None, [vp]),
         "orc_model_tensor": (vp, [vp, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "orc_model_reset": (None, [vp]),
+        "orc_model_fill_kv_synth": (None, [vp, u64]),
         "orc_model_forward": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "orc_model_generate": (i32, [vp, vp, i32, i32, i32, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "orc_model_capture": (vp, [vp, C.c_char_p, i32, C.POINTER(i64)]),
@@ -259,6 +260,9 @@ class Model:
 
     def reset(self):
         lib().orc_model_reset(self.h)
+
+    def fill_kv_synth(self, seed=99):
+        lib().orc_model_fill_kv_synth(self.h, seed)
 
     def forward(self, tokens, pos0, order=REF, logits_all=False):
         tokens = np.ascontiguousarray(tokens, dtype=np.int32)
