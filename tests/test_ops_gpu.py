@@ -343,7 +343,7 @@ def test_rope_store_and_attention_decode(gpu, H, Hkv, d, n_ctx, positions):
         q_r = O.rope_neox(q, pos) * q_scale
         kc_h[pos] = O.rope_neox(k, pos).astype(np.float16).reshape(-1)
         vc_h[pos] = v.astype(np.float16).reshape(-1)
-        assert np.array_equal(bits(qd.download(np.float32)), bits(q_r))
+        assert np.array_equal(bits(qd.download(np.float32)).reshape(H, d), bits(q_r))
         assert np.array_equal(kc.download(np.uint16).reshape(n_ctx, kv)[pos], kc_h[pos].view(np.uint16))
         assert np.array_equal(vc.download(np.uint16).reshape(n_ctx, kv)[pos], vc_h[pos].view(np.uint16))
         dev = O.attn_decode(O.DEV, q_r, kc_h.view(np.uint16), vc_h.view(np.uint16), pos + 1)
