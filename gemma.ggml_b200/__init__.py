@@ -100,6 +100,8 @@ _CUDA_SIG = {
     "ggb_op_attn_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "ggb_op_embed_token": (i32, [vp, vp, f32, vp]),
     "ggb_op_sample_greedy": (i32, [vp, i64, vp, vp, vp]), "ggb_sample_scratch_bytes": (sz, [i64]),
+    "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]), "ggb_decoder_step": (i32, [vp]),
+    "ggb_decoder_free": (i32, [vp]),
     "ggb_comm_unique_id": (i32, [vp]), "ggb_comm_init": (i32, [vp, i32, i32]), "ggb_comm_destroy": (i32, []),
     "ggb_comm_rank": (i32, []), "ggb_comm_size": (i32, []), "ggb_op_allgather": (i32, [vp, vp, sz]),
 }
@@ -108,7 +110,7 @@ _HOST_SIG = {
     "gm_create": (vp, [P(Config)]), "gm_free": (None, [vp]),
     "gm_init_synthetic_weights": (i32, [vp]), "gm_set_tensor": (i32, [vp, i32, vp, i64]),
     "gm_init_kv_cache": (i32, [vp]), "gm_fill_kv_cache_synthetic": (i32, [vp, u64]),
-    "gm_build_compute_graph": (i32, [vp, i32]), "gm_decode_step": (i32, [vp, i32, i32, P(i32)]),
+    "gm_build_compute_graph": (i32, [vp, i32, i32]), "gm_is_fused": (i32, [vp]), "gm_decode_step": (i32, [vp, i32, i32, P(i32)]),
     "gm_set_state": (i32, [vp, i32, i32, i32]), "gm_run_steps": (i32, [vp, i32]), "gm_run_steps_profiled": (i32, [vp, i32]),
     "gm_get_state": (i32, [vp, P(i32), P(i32)]),
     "gm_generate": (i32, [vp, vp, i32, i32, vp, P(i32), P(C.c_double), P(C.c_double)]),
@@ -352,8 +354,14 @@ class GemmaModel:
     def fill_kv_cache_synthetic(self, seed=99):
         check(self.H.gm_fill_kv_cache_synthetic(self.h, seed), "gm_fill_kv_cache_synthetic")
 
-    def build_compute_graph(self, capture_acts=False):
-        check(self.H.gm_build_compute_graph(self.h, int(capture_acts)), "gm_build_compute_graph")
+    def build_compute_graph(self, capture_acts=False, fused=True):
+        """fused=True: the persistent decode kernel (falls back to the per-operator sequence when the
+        shape is outside its envelope; see .is_fused); fused=False: one kernel per (group of) node(s)."""
+        check(self.H.gm_build_compute_graph(self.h, int(capture_acts), int(fused)), "gm_build_compute_graph")
+
+    @property
+    def is_fused(self):
+        return bool(self.H.gm_is_fused(self.h))
 
     def decode_step(self, token, pos):
         nxt = i32()

@@ -1,0 +1,935 @@
+// decoder.cu — the persistent decode kernel: ONE cooperative launch per token.
+//
+// Why: a Gemma-2B Q4_0 token is 1.41 GB of weights + 38 MB of KV = ~220 us of HBM time on a B200,
+// spread over 163 mat-vecs and ~450 small nodes (ref: src/gemma_model.cpp:688-740).  Launched as
+// separate kernels the HBM pipe drains and refills ~170 times per token and the step takes 1.6 ms.
+// Here one CTA per SM stays resident for the whole token:
+//
+//   * warp 12 lane 0 is the PRODUCER: it walks the static per-CTA tile schedule of the whole token
+//     and streams every weight tile (and KV chunk) into a 7 x 27 KiB shared-memory ring with
+//     cp.async.bulk (TMA, SASS UBLKCP) completing on mbarriers.  Weights do not depend on
+//     activations, so the producer runs AHEAD across phase boundaries: while the consumers sit in a
+//     grid barrier or a norm prologue, HBM keeps streaming the next phase's tiles.
+//   * warps 0-11 are CONSUMERS: per phase they build their activation registers (rms_norm + Q8_0
+//     quantisation is recomputed by every CTA, 8 KB from L2, instead of being a phase of its own),
+//     then dot ring tiles exactly like matvec.cu (same lane->block map, same DEV summation order).
+//   * phases are separated by a grid barrier (monotonic 64-bit counter in global memory).
+//
+// Phases per layer: QKV | ATTN (split-K partials; rope, Q scale and the KV-cache store of the new
+// position are folded in) | COMBINE (+ Q8_0 quantise) | O (+ residual) | GATE_UP (+ GeGLU + quantise)
+// | DOWN (+ residual); then LOGITS (+ per-CTA argmax) | SAMPLE.
+// Numerics are bit-identical to the per-operator kernels (same DEV order; tests compare both).
+#include <cooperative_groups.h>
+
+#include <vector>
+
+#include "dot.cuh"
+
+namespace {
+
+constexpr int kConsumerWarps = 12;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;
+constexpr int kSlotBytes = 27648; // 24 rows of K=2048 Q4_0 (1152 B/row); 16 of K=3072; 3 of K=16384; 2 of K=24576
+constexpr int kSlots = 7;
+constexpr int kChunk = GGB_DEV_ATTN_CHUNK;
+constexpr int kMaxG = 8;
+constexpr int kMaxE = 4096; // n_embd limit of the fused path (one K segment for the norm-fed mat-vecs)
+
+enum PhaseKind { PH_QKV = 0, PH_ATTN, PH_COMBINE, PH_O, PH_GATE_UP, PH_DOWN, PH_LOGITS, PH_SAMPLE };
+
+struct Mat {
+    const uint8_t *qs;
+    const __half *d;
+    int rows;
+    int n_tiles;
+};
+
+struct PhaseDesc {
+    int kind, layer;
+    Mat m[3];
+    int n_mats;
+    int nb;            // blocks per weight row
+    int cols;          // nb * 32
+    int rows_per_tile; // weight rows per ring slot (GATE_UP: gate rows per sub-tile; the slot also holds the up rows)
+    int ksegs;         // ceil(nb / 128)
+    int n_tiles;       // schedulable units: tiles (mat-vec), super-tiles of 32 rows (GATE_UP)
+    int rot;           // CTA rotation so small phases do not always land on the same SMs
+    const float *x_in;    // fp32 input of a norm-fed phase (null in layer 0: embedding row)
+    const float *norm_w;
+    const uint8_t *act_in; // planar Q8_0 input (O, DOWN)
+    float *out[3];
+    const float *resid;
+    uint8_t *act_out; // planar Q8_0 output (COMBINE, GATE_UP)
+    float *f32_out;   // COMBINE: kqv; GATE_UP: optional ffn_act dump; LOGITS: result_norm
+    __half *kcache, *vcache;
+};
+
+struct DecoderParams {
+    const PhaseDesc *phases;
+    int n_phases;
+    int type; // weight type
+    int E, H, Hkv, d, F, V, n_ctx;
+    float eps, q_scale, emb_scale;
+    // embedding
+    const uint8_t *emb_qs;
+    const __half *emb_d;
+    float *x0;
+    // decode state
+    int32_t *state, *history;
+    // scratch
+    float *q, *k, *v; // fp32 Q/K/V of the current token
+    float *attn_m, *attn_l, *attn_acc;
+    int max_chunks;
+    float *cand_v;
+    int *cand_i;
+    unsigned long long *bar_count, *bar_base;
+    const uint16_t *exp_table, *gelu_table;
+    const float *rope_cos, *rope_sin;
+};
+
+struct SmemLayout {
+    alignas(128) uint8_t ring[kSlots][kSlotBytes];
+    alignas(16) uint8_t act[kMaxE + kMaxE / 16]; // planar Q8_0 activation built by the norm prologue
+    alignas(16) float q[kMaxG][256];
+    float s[kMaxG][kChunk];
+    float e[kMaxG][kChunk];
+    alignas(16) __half knew[256];
+    alignas(16) __half vnew[256];
+    float part[2][24][kConsumerWarps];
+    float stage[2][32];
+    double red[kConsumerWarps];
+    float cand_v[kConsumerWarps];
+    int cand_i[kConsumerWarps];
+    alignas(8) unsigned long long full_bar[kSlots];
+    alignas(8) unsigned long long empty_bar[kSlots];
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// grid barrier over the consumer threads of all CTAs
+__device__ __forceinline__ void grid_barrier(const DecoderParams &P, unsigned long long target) {
+    consumer_bar();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(P.bar_count, 1ull);
+        while (ld_acquire_u64(P.bar_count) < target) {
+        }
+        __threadfence();
+    }
+    consumer_bar();
+}
+
+// ---------------------------------------------------------------- schedule helpers (producer and consumers agree)
+struct TileInfo {
+    int mat, row0, nrows;
+};
+__device__ __forceinline__ TileInfo locate_tile(const PhaseDesc &ph, int t) {
+    TileInfo ti;
+    int m = 0;
+    while (m + 1 < ph.n_mats && t >= ph.m[m].n_tiles) {
+        t -= ph.m[m].n_tiles;
+        m++;
+    }
+    ti.mat = m;
+    ti.row0 = t * ph.rows_per_tile;
+    ti.nrows = min(ph.rows_per_tile, ph.m[m].rows - ti.row0);
+    return ti;
+}
+__device__ __forceinline__ int first_unit(const PhaseDesc &ph, int cta, int G) {
+    return ((cta - ph.rot) % G + G) % G;
+}
+
+struct RingPos {
+    uint32_t seq;
+    __device__ __forceinline__ int slot() const { return (int)(seq % kSlots); }
+    __device__ __forceinline__ uint32_t parity() const { return (seq / kSlots) & 1u; }
+};
+
+// ---------------------------------------------------------------- producer
+template <int TYPE>
+__device__ void producer_loop(const DecoderParams &P, SmemLayout &S, int cta, int G, int n_pos) {
+    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
+    RingPos rp{0};
+    const int nchunk = (n_pos + kChunk - 1) / kChunk;
+    for (int pi = 0; pi < P.n_phases; pi++) {
+        const PhaseDesc &ph = P.phases[pi];
+        if (ph.kind == PH_QKV || ph.kind == PH_O || ph.kind == PH_DOWN || ph.kind == PH_LOGITS) {
+            for (int t = first_unit(ph, cta, G); t < ph.n_tiles; t += G) {
+                const TileInfo ti = locate_tile(ph, t);
+                const uint32_t pbytes = (uint32_t)ti.nrows * ph.nb * PB, sbytes = (uint32_t)ti.nrows * ph.nb * 2;
+                const int s = rp.slot();
+                mbar_wait(&S.empty_bar[s], rp.parity() ^ 1u);
+                mbar_expect_tx(&S.full_bar[s], pbytes + sbytes);
+                bulk_g2s(S.ring[s], ph.m[ti.mat].qs + (size_t)ti.row0 * ph.nb * PB, pbytes, &S.full_bar[s]);
+                bulk_g2s(S.ring[s] + pbytes, ph.m[ti.mat].d + (size_t)ti.row0 * ph.nb, sbytes, &S.full_bar[s]);
+                rp.seq++;
+            }
+        } else if (ph.kind == PH_GATE_UP) {
+            for (int st = first_unit(ph, cta, G); st < ph.n_tiles; st += G) {
+                for (int r0 = 0; r0 < 32; r0 += ph.rows_per_tile) {
+                    const int nrows = min(ph.rows_per_tile, 32 - r0);
+                    const size_t row = (size_t)st * 32 + r0;
+                    const uint32_t pbytes = (uint32_t)nrows * ph.nb * PB, sbytes = (uint32_t)nrows * ph.nb * 2;
+                    const int s = rp.slot();
+                    mbar_wait(&S.empty_bar[s], rp.parity() ^ 1u);
+                    mbar_expect_tx(&S.full_bar[s], 2 * (pbytes + sbytes));
+                    uint8_t *dst = S.ring[s];
+                    bulk_g2s(dst, ph.m[0].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
+                    bulk_g2s(dst + pbytes, ph.m[0].d + row * ph.nb, sbytes, &S.full_bar[s]);
+                    bulk_g2s(dst + pbytes + sbytes, ph.m[1].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
+                    bulk_g2s(dst + 2 * pbytes + sbytes, ph.m[1].d + row * ph.nb, sbytes, &S.full_bar[s]);
+                    rp.seq++;
+                }
+            }
+        } else if (ph.kind == PH_ATTN) {
+            const int n_items = P.Hkv * nchunk;
+            const uint32_t row_bytes = (uint32_t)P.d * 2;
+            const size_t kv_stride = (size_t)P.Hkv * P.d;
+            for (int it = first_unit(ph, cta, G); it < n_items; it += G) {
+                const int g = it / nchunk, c = it % nchunk;
+                const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
+                for (int which = 0; which < 2; which++) {
+                    const __half *base = (which == 0 ? ph.kcache : ph.vcache) + (size_t)p0 * kv_stride + (size_t)g * P.d;
+                    const int s = rp.slot();
+                    mbar_wait(&S.empty_bar[s], rp.parity() ^ 1u);
+                    mbar_expect_tx(&S.full_bar[s], (uint32_t)np * row_bytes);
+                    if (P.Hkv == 1) {
+                        bulk_g2s(S.ring[s], base, (uint32_t)np * row_bytes, &S.full_bar[s]);
+                    } else {
+                        for (int j = 0; j < np; j++)
+                            bulk_g2s(S.ring[s] + (size_t)j * row_bytes, base + (size_t)j * kv_stride, row_bytes,
+                                     &S.full_bar[s]);
+                    }
+                    rp.seq++;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- consumer pieces
+
+// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into S.act (every CTA recomputes it).
+// Sum of squares in the DEV order: threads 0..255 hold the strided double partials.
+__device__ void norm_prologue(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int token, bool write_x0,
+                              float *f32_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = P.E;
+    auto load_x = [&](int i) -> float {
+        if (ph.x_in) return __ldcg(ph.x_in + i);
+        // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
+        const int nb = E / 32, b = i >> 5, j = i & 31;
+        const float dd = __half2float(P.emb_d[(size_t)token * nb + b]);
+        float val;
+        if (P.type == GGB_TYPE_Q4_0) {
+            const uint8_t byte = P.emb_qs[((size_t)token * nb + b) * 16 + (j & 15)];
+            val = __fmul_rn((float)((j < 16 ? (byte & 0x0F) : (byte >> 4)) - 8), dd);
+        } else {
+            val = __fmul_rn((float)((const int8_t *)P.emb_qs)[((size_t)token * nb + b) * 32 + j], dd);
+        }
+        return __fmul_rn(val, P.emb_scale);
+    };
+    double acc = 0.0;
+    if (tid < GGB_DEV_NORM_THREADS) {
+        for (int i = tid; i < E; i += GGB_DEV_NORM_THREADS) {
+            const float v = load_x(i);
+            acc = __dadd_rn(acc, (double)__fmul_rn(v, v));
+        }
+        acc = warp_sum_f64(acc);
+        if (lane == 0) S.red[warp] = acc;
+    }
+    consumer_bar();
+    double sum = S.red[0];
+#pragma unroll
+    for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
+    const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+    for (int i = tid; i < E; i += kConsumerThreads) { // E % 32 == 0: a warp's 32 elements are one Q8_0 block
+        const float x = load_x(i);
+        if (write_x0) P.x0[i] = x;
+        const float v = __fmul_rn(__fmul_rn(x, scale), ph.norm_w[i]);
+        if (f32_out) f32_out[i] = v;
+        float d;
+        const int q = quantize_q8_lane(v, d);
+        ((int8_t *)S.act)[i] = (int8_t)q;
+        if (lane == 0) reinterpret_cast<__half *>(S.act + E)[i >> 5] = __float2half_rn(d);
+    }
+    consumer_bar();
+}
+
+struct Best {
+    float v;
+    int i;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {
+    if (b.i < 0) return a;
+    if (a.i < 0) return b;
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+// mat-vec phases: QKV, O, DOWN, LOGITS
+template <int TYPE>
+__device__ void matvec_phase(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int cta, int G, RingPos &rp,
+                             const uint8_t *act, bool act_in_smem, Best &best) {
+    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ksegs = ph.ksegs;
+    const int rows_per_round = kConsumerWarps / ksegs;
+    const int kseg = warp % ksegs, rsub = warp / ksegs;
+    const bool warp_live = rsub < rows_per_round;
+    const int b0 = kseg * GGB_DEV_SEG_BLOCKS + lane;
+    if (first_unit(ph, cta, G) >= ph.n_tiles) return;
+
+    ActBlock ab[kTPB];
+    bool valid[kTPB];
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        valid[t] = warp_live && (b0 + 32 * t < ph.nb);
+        if (act_in_smem) load_act(ab[t], act, ph.cols, b0 + 32 * t, valid[t]);
+        else load_act_cg(ab[t], act, ph.cols, b0 + 32 * t, valid[t]);
+    }
+    int pbuf = 0;
+    for (int t = first_unit(ph, cta, G); t < ph.n_tiles; t += G) {
+        const TileInfo ti = locate_tile(ph, t);
+        const int s = rp.slot();
+        mbar_wait(&S.full_bar[s], rp.parity());
+        const uint8_t *pay = S.ring[s];
+        const __half *scl = reinterpret_cast<const __half *>(S.ring[s] + (size_t)ti.nrows * ph.nb * PB);
+        float *out = ph.out[ti.mat];
+        if (ksegs == 1) {
+            for (int r = rsub; r < ti.nrows; r += rows_per_round) {
+                const float seg = segment_dot_smem<TYPE>(pay + (size_t)r * ph.nb * PB, scl + (size_t)r * ph.nb, b0, ab, valid);
+                if (lane == 0) {
+                    const int row = ti.row0 + r;
+                    float v = seg;
+                    if (ph.resid) v = __fadd_rn(v, __ldcg(ph.resid + row));
+                    out[row] = v;
+                    if (ph.kind == PH_LOGITS) best = better(best, Best{v, row});
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+        } else {
+            for (int r = rsub; r < ti.nrows; r += rows_per_round) {
+                float seg = 0.0f;
+                if (warp_live)
+                    seg = segment_dot_smem<TYPE>(pay + (size_t)r * ph.nb * PB, scl + (size_t)r * ph.nb, b0, ab, valid);
+                if (lane == 0 && warp_live) S.part[pbuf][r][kseg] = seg;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            consumer_bar();
+            if (warp_live && kseg == 0 && lane == 0) {
+                for (int r = rsub; r < ti.nrows; r += rows_per_round) {
+                    float total = S.part[pbuf][r][0];
+                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][r][k]);
+                    const int row = ti.row0 + r;
+                    if (ph.resid) total = __fadd_rn(total, __ldcg(ph.resid + row));
+                    out[row] = total;
+                    if (ph.kind == PH_LOGITS) best = better(best, Best{total, row});
+                }
+            }
+            pbuf ^= 1;
+        }
+        rp.seq++;
+    }
+}
+
+// GATE_UP: super-tiles of 32 output rows; gate and up rows of a sub-tile share a ring slot; GeGLU through
+// the fp16 gelu table, then quantize_row_q8_0 of the 32 products ([UPSTREAM] ggml_vec_gelu_f32, ggml_mul;
+// ref: src/gemma_model.cpp:444-452)
+template <int TYPE>
+__device__ void gate_up_phase(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int cta, int G, RingPos &rp) {
+    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (first_unit(ph, cta, G) >= ph.n_tiles) return;
+    ActBlock ab[kTPB];
+    bool valid[kTPB];
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        valid[t] = lane + 32 * t < ph.nb;
+        load_act(ab[t], S.act, ph.cols, lane + 32 * t, valid[t]);
+    }
+    int sbuf = 0;
+    for (int st = first_unit(ph, cta, G); st < ph.n_tiles; st += G) {
+        for (int r0 = 0; r0 < 32; r0 += ph.rows_per_tile) {
+            const int nrows = min(ph.rows_per_tile, 32 - r0);
+            const int s = rp.slot();
+            mbar_wait(&S.full_bar[s], rp.parity());
+            const size_t pbytes = (size_t)nrows * ph.nb * PB, sbytes = (size_t)nrows * ph.nb * 2;
+            const uint8_t *gp = S.ring[s], *up = S.ring[s] + pbytes + sbytes;
+            const __half *gs = reinterpret_cast<const __half *>(gp + pbytes);
+            const __half *us = reinterpret_cast<const __half *>(up + pbytes);
+            for (int r = warp; r < nrows; r += kConsumerWarps) {
+                const float g = segment_dot_smem<TYPE>(gp + (size_t)r * ph.nb * PB, gs + (size_t)r * ph.nb, lane, ab, valid);
+                const float u = segment_dot_smem<TYPE>(up + (size_t)r * ph.nb * PB, us + (size_t)r * ph.nb, lane, ab, valid);
+                if (lane == 0) {
+                    const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(g)]);
+                    S.stage[sbuf][r0 + r] = __fmul_rn(gl, u);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            rp.seq++;
+        }
+        consumer_bar();
+        if (warp == 0) {
+            const float x = S.stage[sbuf][lane];
+            const size_t row = (size_t)st * 32 + lane;
+            if (ph.f32_out) ph.f32_out[row] = x;
+            float d;
+            const int q = quantize_q8_lane(x, d);
+            ((int8_t *)ph.act_out)[row] = (int8_t)q;
+            if (lane == 0) reinterpret_cast<__half *>(ph.act_out + P.F)[st] = __float2half_rn(d);
+        }
+        sbuf ^= 1;
+    }
+}
+
+// ATTN: items (kv head g, chunk of 32 positions); K chunk and V chunk arrive in two ring slots.
+// Same arithmetic as attention.cu attn_partial_kernel; rope + Q scale are applied to q on load, and the
+// item that owns the newest position ropes K, rounds K/V to fp16, stores them in the cache and uses them.
+__device__ void attn_phase(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int cta, int G, RingPos &rp,
+                           int n_pos) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = P.d, halfd = d / 2, Gq = P.H / P.Hkv;
+    const int nchunk = (n_pos + kChunk - 1) / kChunk;
+    const int n_items = P.Hkv * nchunk;
+    const int pos = n_pos - 1;
+    const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
+    for (int it = first_unit(ph, cta, G); it < n_items; it += G) {
+        const int g = it / nchunk, c = it % nchunk;
+        const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
+        const int h0 = g * Gq;
+        const bool owns_new = (pos >= p0 && pos < p0 + np);
+        // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
+        for (int i = tid; i < Gq * halfd; i += kConsumerThreads) {
+            const int jh = i / halfd, e = i % halfd;
+            const float *qh = P.q + (size_t)(h0 + jh) * d;
+            const float x0 = __ldcg(qh + e), x1 = __ldcg(qh + e + halfd);
+            const float cs = cosr[e], sn = sinr[e];
+            const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
+            const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
+            S.q[jh][e] = __half2float(__float2half_rn(r0));
+            S.q[jh][e + halfd] = __half2float(__float2half_rn(r1));
+        }
+        if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
+            for (int e = tid; e < halfd; e += kConsumerThreads) {
+                const float x0 = __ldcg(P.k + (size_t)g * d + e), x1 = __ldcg(P.k + (size_t)g * d + e + halfd);
+                const float cs = cosr[e], sn = sinr[e];
+                const __half k0 = __float2half_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)));
+                const __half k1 = __float2half_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)));
+                S.knew[e] = k0;
+                S.knew[e + halfd] = k1;
+                __half *krow = ph.kcache + ((size_t)pos * P.Hkv + g) * d;
+                krow[e] = k0;
+                krow[e + halfd] = k1;
+            }
+            for (int e = tid; e < d; e += kConsumerThreads) {
+                const __half vv = __float2half_rn(__ldcg(P.v + (size_t)g * d + e));
+                S.vnew[e] = vv;
+                ph.vcache[((size_t)pos * P.Hkv + g) * d + e] = vv;
+            }
+        }
+        consumer_bar();
+        // scores: warp w takes positions w, w+12, w+24
+        {
+            const int s = rp.slot();
+            mbar_wait(&S.full_bar[s], rp.parity());
+            const __half *kchunk = reinterpret_cast<const __half *>(S.ring[s]);
+            for (int j = warp; j < np; j += kConsumerWarps) {
+                float kf[8];
+                if (8 * lane < d) {
+                    const __half *krow = (owns_new && p0 + j == pos) ? S.knew : kchunk + (size_t)j * d;
+                    const uint4 raw = *reinterpret_cast<const uint4 *>(krow + 8 * lane);
+                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float2 f = __half22float2(h2[e]);
+                        kf[2 * e] = f.x;
+                        kf[2 * e + 1] = f.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) kf[e] = 0.f;
+                }
+                for (int jh = 0; jh < Gq; jh++) {
+                    float acc = 0.0f;
+                    if (8 * lane < d) {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) acc = __fadd_rn(acc, __fmul_rn(kf[e], S.q[jh][8 * lane + e]));
+                    }
+                    acc = warp_sum_f32(acc);
+                    if (lane == 0) S.s[jh][j] = acc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            rp.seq++;
+        }
+        consumer_bar();
+        // per-head chunk soft-max through the fp16 exp table
+        if (warp < Gq) {
+            const float sv = lane < np ? S.s[warp][lane] : -INFINITY;
+            const float m = warp_max_f32(sv);
+            const float e = lane < np ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sv, m))]) : 0.0f;
+            const float l = warp_sum_f32(e);
+            S.e[warp][lane] = e;
+            if (lane == 0) {
+                P.attn_m[(size_t)(h0 + warp) * P.max_chunks + c] = m;
+                P.attn_l[(size_t)(h0 + warp) * P.max_chunks + c] = l;
+            }
+        }
+        consumer_bar();
+        // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p
+        {
+            const int s = rp.slot();
+            mbar_wait(&S.full_bar[s], rp.parity());
+            const __half *vchunk = reinterpret_cast<const __half *>(S.ring[s]);
+            const int dp = tid % 128, hs = tid / 128;
+            if (tid < 256 && dp < halfd) {
+                float a0[kMaxG / 2], a1[kMaxG / 2];
+#pragma unroll
+                for (int u = 0; u < kMaxG / 2; u++) a0[u] = a1[u] = 0.0f;
+                for (int j = 0; j < np; j++) {
+                    const __half *vrow = (owns_new && p0 + j == pos) ? S.vnew : vchunk + (size_t)j * d;
+                    const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(vrow + 2 * dp));
+#pragma unroll
+                    for (int u = 0; u < kMaxG / 2; u++) {
+                        const int jh = 2 * u + hs;
+                        if (jh < Gq) {
+                            const float e = S.e[jh][j];
+                            a0[u] = __fadd_rn(a0[u], __fmul_rn(e, vf.x));
+                            a1[u] = __fadd_rn(a1[u], __fmul_rn(e, vf.y));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kMaxG / 2; u++) {
+                    const int jh = 2 * u + hs;
+                    if (jh < Gq) {
+                        float *out = P.attn_acc + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
+                        *reinterpret_cast<float2 *>(out) = make_float2(a0[u], a1[u]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            rp.seq++;
+        }
+        consumer_bar();
+    }
+}
+
+// COMBINE: one warp per (head, 32-dim slice): M = max m_c; w_c = exp_table[f16(m_c - M)];
+// L = sum l_c*w_c; O = sum acc_c*w_c (sequential in c); out = O / L; the slice is one Q8_0 block.
+__device__ void combine_phase(const DecoderParams &P, const PhaseDesc &ph, int cta, int G, int n_pos) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = P.d, slices = d / 32;
+    const int n_tasks = P.H * slices;
+    const int nchunk = (n_pos + kChunk - 1) / kChunk;
+    for (int task = warp * G + ((cta - ph.rot) % G + G) % G; task < n_tasks; task += kConsumerWarps * G) {
+        const int h = task / slices, sl = task % slices;
+        const float *pm = P.attn_m + (size_t)h * P.max_chunks;
+        const float *pl = P.attn_l + (size_t)h * P.max_chunks;
+        const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32 + lane;
+        float mx = -INFINITY;
+        for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, __ldcg(pm + c));
+        mx = warp_max_f32(mx);
+        float L = 0.0f, O = 0.0f;
+        for (int c0 = 0; c0 < nchunk; c0 += 8) {
+            float a[8], l[8], m[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (c0 + u < nchunk) {
+                    a[u] = __ldcg(pa + (size_t)(c0 + u) * d);
+                    l[u] = __ldcg(pl + c0 + u);
+                    m[u] = __ldcg(pm + c0 + u);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (c0 + u < nchunk) {
+                    const float w = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(m[u], mx))]);
+                    L = __fadd_rn(L, __fmul_rn(l[u], w));
+                    O = __fadd_rn(O, __fmul_rn(a[u], w));
+                }
+            }
+        }
+        const float r = __fdiv_rn(O, L);
+        const size_t idx = (size_t)h * d + sl * 32 + lane;
+        ph.f32_out[idx] = r;
+        float dd;
+        const int qv = quantize_q8_lane(r, dd);
+        ((int8_t *)ph.act_out)[idx] = (int8_t)qv;
+        if (lane == 0) reinterpret_cast<__half *>(ph.act_out + (size_t)P.H * d)[idx >> 5] = __float2half_rn(dd);
+    }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const DecoderParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    SmemLayout &S = *reinterpret_cast<SmemLayout *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int cta = blockIdx.x, G = gridDim.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) {
+        for (int i = 0; i < kSlots; i++) {
+            mbar_init(&S.full_bar[i], 1);
+            mbar_init(&S.empty_bar[i], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int token = min(max(P.state[0], 0), P.V - 1);
+    const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
+    const unsigned long long base = *P.bar_base;
+
+    if (warp == kConsumerWarps) {
+        if (tid == kConsumerThreads) producer_loop<TYPE>(P, S, cta, G, n_pos);
+        return;
+    }
+
+    // ---- consumers
+    RingPos rp{0};
+    unsigned long long bar_target = base;
+    Best best{-INFINITY, -1};
+    for (int pi = 0; pi < P.n_phases; pi++) {
+        const PhaseDesc &ph = P.phases[pi];
+        switch (ph.kind) {
+        case PH_QKV:
+        case PH_LOGITS: {
+            const bool mine = first_unit(ph, cta, G) < ph.n_tiles;
+            const bool write_x0 = (ph.kind == PH_QKV && ph.x_in == nullptr && cta == 0);
+            // LOGITS has rot = 0, so CTA 0 owns tile 0 and also writes the result_norm dump
+            if (mine || write_x0)
+                norm_prologue(P, S, ph, token, write_x0, (ph.kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
+            matvec_phase<TYPE>(P, S, ph, cta, G, rp, S.act, true, best);
+            break;
+        }
+        case PH_GATE_UP: {
+            if (first_unit(ph, cta, G) < ph.n_tiles) norm_prologue(P, S, ph, token, false, nullptr);
+            gate_up_phase<TYPE>(P, S, ph, cta, G, rp);
+            break;
+        }
+        case PH_O:
+        case PH_DOWN:
+            matvec_phase<TYPE>(P, S, ph, cta, G, rp, ph.act_in, false, best);
+            break;
+        case PH_ATTN:
+            attn_phase(P, S, ph, cta, G, rp, n_pos);
+            break;
+        case PH_COMBINE:
+            combine_phase(P, ph, cta, G, n_pos);
+            break;
+        case PH_SAMPLE: {
+            // per-CTA candidates were published before the previous barrier; CTA 0 picks the first maximum
+            if (cta == 0 && warp == 0) {
+                const int lane = tid & 31;
+                Best b{-INFINITY, -1};
+                for (int i = lane; i < G; i += 32) b = better(b, Best{__ldcg(P.cand_v + i), __ldcg(P.cand_i + i)});
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    Best o;
+                    o.v = __shfl_xor_sync(0xffffffffu, b.v, off);
+                    o.i = __shfl_xor_sync(0xffffffffu, b.i, off);
+                    b = better(b, o);
+                }
+                if (lane == 0) {
+                    P.state[0] = b.i;
+                    P.state[1] += P.state[2];
+                    if (P.history) P.history[P.state[1]] = b.i;
+                }
+            }
+            break;
+        }
+        }
+        if (ph.kind == PH_LOGITS) { // publish this CTA's arg-max candidate (strict '>' / lowest index, ref: :538-543)
+            const int lane = tid & 31;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                Best o;
+                o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
+                o.i = __shfl_xor_sync(0xffffffffu, best.i, off);
+                best = better(best, o);
+            }
+            if (lane == 0) {
+                S.cand_v[warp] = best.v;
+                S.cand_i[warp] = best.i;
+            }
+            consumer_bar();
+            if (tid == 0) {
+                Best b{S.cand_v[0], S.cand_i[0]};
+                for (int w = 1; w < kConsumerWarps; w++) b = better(b, Best{S.cand_v[w], S.cand_i[w]});
+                P.cand_v[cta] = b.v;
+                P.cand_i[cta] = b.i;
+            }
+        }
+        if (ph.kind != PH_SAMPLE) {
+            bar_target += (unsigned long long)G;
+            grid_barrier(P, bar_target);
+        }
+    }
+    if (cta == 0 && tid == 0) *P.bar_base = bar_target;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- host side
+struct ggb_decoder {
+    DecoderParams P{};
+    std::vector<PhaseDesc> phases;
+    PhaseDesc *d_phases = nullptr;
+    void *scratch = nullptr;
+    int grid = 0;
+    size_t smem = 0;
+    int n_barriers = 0;
+};
+
+extern "C" {
+
+int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
+                       const float *output_norm, const ggb_decoder_io *io, ggb_decoder **out) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(dims && layers && token_embd && output_norm && io && out, "null pointer");
+    const int E = dims->n_embd, L = dims->n_layer, H = dims->n_head, Hkv = dims->n_head_kv, d = dims->head_dim;
+    const int F = dims->n_ff, V = dims->n_vocab;
+    const int type = token_embd->type;
+    const int PB = ggb_payload_bytes(type);
+    if (!(E % 256 == 0 && E <= kMaxE && (H * d) % 256 == 0 && H * d <= kMaxE && F % 256 == 0 && d % 32 == 0 &&
+          d <= 256 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= kMaxG && F % 32 == 0 && F / 32 * 2 % 16 == 0)) {
+        ggb_set_error("decoder: shape outside the fused kernel's envelope (E=%d H=%d Hkv=%d d=%d F=%d)", E, H, Hkv, d, F);
+        return GGB_ERR_UNSUPPORTED;
+    }
+    GGB_CHECK_ARG(ggb_rope_cos_dev() && ggb_rope_n_dims() == d && ggb_rope_n_ctx() >= dims->n_ctx,
+                  "rope table not initialised for head_dim %d / ctx %d", d, dims->n_ctx);
+    ggb_decoder *D = new ggb_decoder();
+    DecoderParams &P = D->P;
+    P.type = type; P.E = E; P.H = H; P.Hkv = Hkv; P.d = d; P.F = F; P.V = V; P.n_ctx = dims->n_ctx;
+    P.eps = dims->eps;
+    P.q_scale = 1.0f / sqrtf((float)d);
+    P.emb_scale = sqrtf((float)E);
+    P.emb_qs = token_embd->qs; P.emb_d = token_embd->d;
+    P.state = io->state; P.history = io->history;
+    P.exp_table = ggb_exp_table_dev(); P.gelu_table = ggb_gelu_table_dev();
+    P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
+    P.max_chunks = (dims->n_ctx + kChunk - 1) / kChunk;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    D->grid = sms;
+    // scratch: x0 | q | k | v | attn m,l,acc | cand | barrier words | planar activations
+    const size_t QD = (size_t)H * d, KD = (size_t)Hkv * d;
+    const size_t act_q_bytes = ggb_q8_row_bytes((int64_t)QD), act_f_bytes = ggb_q8_row_bytes((int64_t)F);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_x0 = carve((size_t)E * 4), o_q = carve(QD * 4), o_k = carve(KD * 4), o_v = carve(KD * 4);
+    const size_t o_m = carve((size_t)H * P.max_chunks * 4), o_l = carve((size_t)H * P.max_chunks * 4);
+    const size_t o_acc = carve((size_t)H * P.max_chunks * d * 4);
+    const size_t o_cv = carve((size_t)sms * 4), o_ci = carve((size_t)sms * 4), o_bar = carve(16);
+    const size_t o_aq = carve(act_q_bytes), o_af = carve(act_f_bytes);
+    cudaError_t e = cudaMalloc(&D->scratch, off);
+    if (e != cudaSuccess) {
+        ggb_set_error("decoder scratch cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e));
+        delete D;
+        return GGB_ERR_CUDA;
+    }
+    cudaMemsetAsync(D->scratch, 0, off, ggb_cuda_stream());
+    uint8_t *sb = (uint8_t *)D->scratch;
+    P.x0 = (float *)(sb + o_x0); P.q = (float *)(sb + o_q); P.k = (float *)(sb + o_k); P.v = (float *)(sb + o_v);
+    P.attn_m = (float *)(sb + o_m); P.attn_l = (float *)(sb + o_l); P.attn_acc = (float *)(sb + o_acc);
+    P.cand_v = (float *)(sb + o_cv); P.cand_i = (int *)(sb + o_ci);
+    P.bar_count = (unsigned long long *)(sb + o_bar); P.bar_base = P.bar_count + 1;
+    uint8_t *act_q = sb + o_aq, *act_f = sb + o_af;
+
+    auto fit_rows = [&](int nb, int mats) { // rows per ring slot
+        const int row_bytes = nb * (PB + 2) * mats;
+        int r = kSlotBytes / row_bytes;
+        return r < 1 ? 0 : r;
+    };
+    auto matvec_desc = [&](int kind, int layer, int n, const ggb_weight *const *w, float *const *outs) {
+        PhaseDesc ph{};
+        ph.kind = kind; ph.layer = layer; ph.n_mats = n;
+        ph.nb = (int)w[0]->nb; ph.cols = (int)w[0]->cols;
+        ph.ksegs = (ph.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS;
+        int r = fit_rows(ph.nb, 1);
+        const int rpr = kConsumerWarps / ph.ksegs > 0 ? kConsumerWarps / ph.ksegs : 1;
+        if (r > 24) r = 24;
+        if (r >= rpr) r = r / rpr * rpr; // whole rounds of the consumer warps
+        ph.rows_per_tile = r;
+        ph.n_tiles = 0;
+        for (int i = 0; i < n; i++) {
+            ph.m[i].qs = w[i]->qs; ph.m[i].d = w[i]->d; ph.m[i].rows = (int)w[i]->rows;
+            ph.m[i].n_tiles = r > 0 ? (int)((w[i]->rows + r - 1) / r) : 0;
+            ph.n_tiles += ph.m[i].n_tiles;
+            ph.out[i] = outs[i];
+        }
+        return ph;
+    };
+    bool ok = true;
+    for (int il = 0; il < L && ok; il++) {
+        const ggb_decoder_layer &ly = layers[il];
+        const float *x_in = il == 0 ? nullptr : io->l_out + (size_t)(il - 1) * E;
+        const float *x_res = il == 0 ? P.x0 : x_in;
+        float *sa = io->sa_out + (size_t)il * E, *lo = io->l_out + (size_t)il * E;
+        {   // QKV
+            const ggb_weight *w[3] = {ly.attn_q, ly.attn_k, ly.attn_v};
+            float *o[3] = {P.q, P.k, P.v};
+            PhaseDesc ph = matvec_desc(PH_QKV, il, 3, w, o);
+            ph.x_in = x_in; ph.norm_w = ly.attn_norm;
+            ok = ok && ph.rows_per_tile > 0 && ph.ksegs == 1;
+            D->phases.push_back(ph);
+        }
+        {   // ATTN
+            PhaseDesc ph{};
+            ph.kind = PH_ATTN; ph.layer = il; ph.kcache = (__half *)ly.k_cache; ph.vcache = (__half *)ly.v_cache;
+            D->phases.push_back(ph);
+        }
+        {   // COMBINE
+            PhaseDesc ph{};
+            ph.kind = PH_COMBINE; ph.layer = il; ph.act_out = act_q; ph.f32_out = io->kqv + (size_t)il * QD;
+            D->phases.push_back(ph);
+        }
+        {   // O + residual
+            const ggb_weight *w[1] = {ly.attn_output};
+            float *o[1] = {sa};
+            PhaseDesc ph = matvec_desc(PH_O, il, 1, w, o);
+            ph.act_in = act_q; ph.resid = x_res;
+            ok = ok && ph.rows_per_tile > 0;
+            D->phases.push_back(ph);
+        }
+        {   // GATE_UP
+            PhaseDesc ph{};
+            ph.kind = PH_GATE_UP; ph.layer = il; ph.n_mats = 2;
+            ph.nb = (int)ly.ffn_gate->nb; ph.cols = (int)ly.ffn_gate->cols; ph.ksegs = 1;
+            ph.m[0].qs = ly.ffn_gate->qs; ph.m[0].d = ly.ffn_gate->d; ph.m[0].rows = F;
+            ph.m[1].qs = ly.ffn_up->qs; ph.m[1].d = ly.ffn_up->d; ph.m[1].rows = F;
+            int r = fit_rows(ph.nb, 2);
+            if (r > kConsumerWarps) r = kConsumerWarps;
+            if (r > 8 && r < 12) r = 8;
+            ph.rows_per_tile = r;
+            ph.n_tiles = F / 32;
+            ph.x_in = sa; ph.norm_w = ly.ffn_norm; ph.act_out = act_f;
+            ph.f32_out = io->ffn_act ? io->ffn_act + (size_t)il * F : nullptr;
+            ok = ok && r > 0 && ph.nb <= GGB_DEV_SEG_BLOCKS;
+            D->phases.push_back(ph);
+        }
+        {   // DOWN + residual
+            const ggb_weight *w[1] = {ly.ffn_down};
+            float *o[1] = {lo};
+            PhaseDesc ph = matvec_desc(PH_DOWN, il, 1, w, o);
+            ph.act_in = act_f; ph.resid = sa;
+            ok = ok && ph.rows_per_tile > 0 && ph.ksegs <= kConsumerWarps;
+            D->phases.push_back(ph);
+        }
+    }
+    {   // LOGITS (tied embedding) + SAMPLE
+        const ggb_weight *w[1] = {token_embd};
+        float *o[1] = {io->logits};
+        PhaseDesc ph = matvec_desc(PH_LOGITS, L, 1, w, o);
+        ph.x_in = io->l_out + (size_t)(L - 1) * E; ph.norm_w = output_norm; ph.f32_out = io->result_norm;
+        ok = ok && ph.rows_per_tile > 0 && ph.ksegs == 1;
+        D->phases.push_back(ph);
+        PhaseDesc sp{};
+        sp.kind = PH_SAMPLE; sp.layer = L;
+        D->phases.push_back(sp);
+    }
+    if (!ok) {
+        ggb_set_error("decoder: a weight row does not fit the ring slot (%d B) for this shape", kSlotBytes);
+        cudaFree(D->scratch);
+        delete D;
+        return GGB_ERR_UNSUPPORTED;
+    }
+    for (size_t i = 0; i < D->phases.size(); i++) D->phases[i].rot = (int)((i * 61) % (size_t)sms);
+    D->phases[D->phases.size() - 2].rot = 0; // LOGITS: result_norm dump is written by the CTA owning tile 0
+    D->n_barriers = (int)D->phases.size() - 1;
+    e = cudaMalloc(&D->d_phases, D->phases.size() * sizeof(PhaseDesc));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(D->d_phases, D->phases.data(), D->phases.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice,
+                            ggb_cuda_stream());
+    if (e != cudaSuccess) {
+        ggb_set_error("decoder phase table upload -> %s", cudaGetErrorString(e));
+        cudaFree(D->scratch);
+        delete D;
+        return GGB_ERR_CUDA;
+    }
+    P.phases = D->d_phases;
+    P.n_phases = (int)D->phases.size();
+    D->smem = sizeof(SmemLayout) + 128;
+    const void *fn = type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
+                                           : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem);
+    int occ = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, D->smem);
+    if (e != cudaSuccess || occ < 1) {
+        ggb_set_error("decoder kernel cannot be resident (smem %zu B): %s", D->smem,
+                      e != cudaSuccess ? cudaGetErrorString(e) : "occupancy 0");
+        cudaFree(D->d_phases);
+        cudaFree(D->scratch);
+        delete D;
+        return GGB_ERR_CUDA;
+    }
+    GGB_CUDA(cudaStreamSynchronize(ggb_cuda_stream()));
+    *out = D;
+    return GGB_OK;
+}
+
+int ggb_decoder_step(ggb_decoder *D) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(D != nullptr, "null decoder");
+    void *args[] = {(void *)&D->P};
+    const void *fn = D->P.type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
+                                                : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
+    GGB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)D->grid), dim3(kThreads), args, D->smem, ggb_cuda_stream()));
+    ggb_count_launch();
+    return GGB_OK;
+}
+
+int ggb_decoder_free(ggb_decoder *D) {
+    if (!D) return GGB_OK;
+    cudaStreamSynchronize(ggb_cuda_stream());
+    cudaFree(D->d_phases);
+    cudaFree(D->scratch);
+    delete D;
+    return GGB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,151 @@
+// dot.cuh — the per-block arithmetic shared by the mat-vec kernels (matvec.cu) and the persistent
+// decode kernel (decoder.cu): a lane's Q8_0 activation blocks in registers, one Q4_0 / Q8_0 weight
+// block dotted against them with dp4a, and the scalar reference's per-block term
+//   Q4_0: (float)sumi * d_x * d_y   (left to right)      Q8_0: (float)sumi * (d_x * d_y)
+// ([UPSTREAM] ggml_vec_dot_q4_0_q8_0 / ggml_vec_dot_q8_0_q8_0 scalar branches; called through the
+// vec_dot pointer at ref: src/hpc.cpp:35).
+#pragma once
+
+#include "common.cuh"
+
+constexpr int kTPB = GGB_DEV_SEG_BLOCKS / 32; // blocks per lane per 128-block segment = 4
+
+// activation block held by a lane
+struct ActBlock {
+    int a[8];  // 32 int8
+    float d;   // fp16 scale widened
+    int bias;  // -8 * sum(a): folds Q4_0's "- 8" out of the inner loop
+};
+
+// act: planar Q8_0 row (cols int8, then cols/32 fp16 scales); generic pointer (global or shared)
+__device__ __forceinline__ void load_act(ActBlock &ab, const uint8_t *act, int64_t cols, int64_t b, bool valid) {
+    if (valid) {
+        const uint4 lo = *reinterpret_cast<const uint4 *>(act + b * 32);
+        const uint4 hi = *reinterpret_cast<const uint4 *>(act + b * 32 + 16);
+        ab.a[0] = lo.x; ab.a[1] = lo.y; ab.a[2] = lo.z; ab.a[3] = lo.w;
+        ab.a[4] = hi.x; ab.a[5] = hi.y; ab.a[6] = hi.z; ab.a[7] = hi.w;
+        ab.d = __half2float(reinterpret_cast<const __half *>(act + cols)[b]);
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s = __dp4a(ab.a[i], 0x01010101, s);
+        ab.bias = -8 * s;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) ab.a[i] = 0;
+        ab.d = 0.f;
+        ab.bias = 0;
+    }
+}
+
+// same, reading through L2 (data produced by another CTA of the same kernel)
+__device__ __forceinline__ void load_act_cg(ActBlock &ab, const uint8_t *act, int64_t cols, int64_t b, bool valid) {
+    if (valid) {
+        const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(act + b * 32));
+        const uint4 hi = __ldcg(reinterpret_cast<const uint4 *>(act + b * 32 + 16));
+        ab.a[0] = lo.x; ab.a[1] = lo.y; ab.a[2] = lo.z; ab.a[3] = lo.w;
+        ab.a[4] = hi.x; ab.a[5] = hi.y; ab.a[6] = hi.z; ab.a[7] = hi.w;
+        ab.d = __half2float(__ushort_as_half(__ldcg(reinterpret_cast<const unsigned short *>(act + cols) + b)));
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s = __dp4a(ab.a[i], 0x01010101, s);
+        ab.bias = -8 * s;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) ab.a[i] = 0;
+        ab.d = 0.f;
+        ab.bias = 0;
+    }
+}
+
+__device__ __forceinline__ float q4_term(const uint4 w, float dx, const ActBlock &ab) {
+    int sumi = ab.bias;
+    const uint32_t q[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int lo = (int)(q[i] & 0x0F0F0F0Fu);
+        const int hi = (int)((q[i] >> 4) & 0x0F0F0F0Fu);
+        sumi = __dp4a(lo, ab.a[i], sumi);
+        sumi = __dp4a(hi, ab.a[4 + i], sumi);
+    }
+    return __fmul_rn(__fmul_rn((float)sumi, dx), ab.d);
+}
+
+__device__ __forceinline__ float q8_term(const uint4 w0, const uint4 w1, float dx, const ActBlock &ab) {
+    int sumi = 0;
+    sumi = __dp4a((int)w0.x, ab.a[0], sumi);
+    sumi = __dp4a((int)w0.y, ab.a[1], sumi);
+    sumi = __dp4a((int)w0.z, ab.a[2], sumi);
+    sumi = __dp4a((int)w0.w, ab.a[3], sumi);
+    sumi = __dp4a((int)w1.x, ab.a[4], sumi);
+    sumi = __dp4a((int)w1.y, ab.a[5], sumi);
+    sumi = __dp4a((int)w1.z, ab.a[6], sumi);
+    sumi = __dp4a((int)w1.w, ab.a[7], sumi);
+    return __fmul_rn((float)sumi, __fmul_rn(dx, ab.d));
+}
+
+// weight payload of one block, loaded from global (streaming) or shared memory
+template <int TYPE> struct Payload;
+template <> struct Payload<GGB_TYPE_Q4_0> {
+    uint4 v;
+    __device__ __forceinline__ void load(const uint8_t *qs, int64_t blk) { v = ldg_stream_u4(qs + blk * 16); }
+    __device__ __forceinline__ void load_smem(const uint8_t *qs, int blk) {
+        v = *reinterpret_cast<const uint4 *>(qs + blk * 16);
+    }
+    __device__ __forceinline__ float term(float dx, const ActBlock &ab) const { return q4_term(v, dx, ab); }
+};
+template <> struct Payload<GGB_TYPE_Q8_0> {
+    uint4 v0, v1;
+    __device__ __forceinline__ void load(const uint8_t *qs, int64_t blk) {
+        v0 = ldg_stream_u4(qs + blk * 32);
+        v1 = ldg_stream_u4(qs + blk * 32 + 16);
+    }
+    __device__ __forceinline__ void load_smem(const uint8_t *qs, int blk) {
+        v0 = *reinterpret_cast<const uint4 *>(qs + blk * 32);
+        v1 = *reinterpret_cast<const uint4 *>(qs + blk * 32 + 16);
+    }
+    __device__ __forceinline__ float term(float dx, const ActBlock &ab) const { return q8_term(v0, v1, dx, ab); }
+};
+
+// dot of one 128-block segment of one row, weights in GLOBAL memory: lane partial (blocks in order,
+// from 0.0f) + xor-butterfly.  b0 = first block of this lane (segment start + lane).
+template <int TYPE>
+__device__ __forceinline__ float segment_dot(const uint8_t *qs, const __half *d, int64_t row, int64_t nb, int64_t b0,
+                                             const ActBlock (&ab)[kTPB], const bool (&valid)[kTPB]) {
+    Payload<TYPE> w[kTPB];
+    float dx[kTPB];
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        if (valid[t]) {
+            const int64_t blk = row * nb + b0 + 32 * t;
+            w[t].load(qs, blk);
+            dx[t] = __half2float(d[blk]);
+        }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        if (valid[t]) acc = __fadd_rn(acc, w[t].term(dx[t], ab[t]));
+    }
+    return warp_sum_f32(acc);
+}
+
+// same with the row's payload / scale planes staged in SHARED memory (row-local block index)
+template <int TYPE>
+__device__ __forceinline__ float segment_dot_smem(const uint8_t *qs_row, const __half *d_row, int b0,
+                                                  const ActBlock (&ab)[kTPB], const bool (&valid)[kTPB]) {
+    Payload<TYPE> w[kTPB];
+    float dx[kTPB];
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        if (valid[t]) {
+            w[t].load_smem(qs_row, b0 + 32 * t);
+            dx[t] = __half2float(d_row[b0 + 32 * t]);
+        }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < kTPB; t++) {
+        if (valid[t]) acc = __fadd_rn(acc, w[t].term(dx[t], ab[t]));
+    }
+    return warp_sum_f32(acc);
+}

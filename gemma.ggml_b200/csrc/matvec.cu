@@ -10,12 +10,11 @@
 //     Q4_0 is folded into a per-lane constant (-8 * sum of the activation block);
 //   * per-block terms are the scalar reference's ((float)sumi*dx)*dy, summed in the DEV order
 //     documented in include/ggml_b200.h; reduction is warp shuffles (+ smem across segments).
-#include "common.cuh"
+#include "dot.cuh"
 
 namespace {
 
 constexpr int kMaxMats = 3;
-constexpr int kTPB = GGB_DEV_SEG_BLOCKS / 32; // blocks per lane per segment = 4
 
 struct MatvecMat {
     const uint8_t *qs;
@@ -38,94 +37,6 @@ struct MatvecArgs {
     int rows_per_iter; // warps per CTA / ksegs
     int64_t rows_per_cta;
 };
-
-template <int TYPE> struct Payload;
-template <> struct Payload<GGB_TYPE_Q4_0> {
-    uint4 v;
-    __device__ __forceinline__ void load(const uint8_t *qs, int64_t blk) { v = ldg_stream_u4(qs + blk * 16); }
-};
-template <> struct Payload<GGB_TYPE_Q8_0> {
-    uint4 v0, v1;
-    __device__ __forceinline__ void load(const uint8_t *qs, int64_t blk) {
-        v0 = ldg_stream_u4(qs + blk * 32);
-        v1 = ldg_stream_u4(qs + blk * 32 + 16);
-    }
-};
-
-// activation block held by a lane
-struct ActBlock {
-    int a[8];  // 32 int8
-    float d;   // fp16 scale widened
-    int bias;  // -8 * sum(a) (Q4_0 only)
-};
-
-__device__ __forceinline__ void load_act(ActBlock &ab, const uint8_t *act, int64_t cols, int64_t b, bool valid) {
-    if (valid) {
-        const uint4 lo = *reinterpret_cast<const uint4 *>(act + b * 32);
-        const uint4 hi = *reinterpret_cast<const uint4 *>(act + b * 32 + 16);
-        ab.a[0] = lo.x; ab.a[1] = lo.y; ab.a[2] = lo.z; ab.a[3] = lo.w;
-        ab.a[4] = hi.x; ab.a[5] = hi.y; ab.a[6] = hi.z; ab.a[7] = hi.w;
-        ab.d = __half2float(reinterpret_cast<const __half *>(act + cols)[b]);
-        int s = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) s = __dp4a(ab.a[i], 0x01010101, s);
-        ab.bias = -8 * s;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) ab.a[i] = 0;
-        ab.d = 0.f;
-        ab.bias = 0;
-    }
-}
-
-// one block's contribution, exactly the scalar loops' expression:
-//   Q4_0: sumi * d_x * d_y  (left to right)        Q8_0: sumi * (d_x * d_y)
-__device__ __forceinline__ float block_term(const Payload<GGB_TYPE_Q4_0> &w, float dx, const ActBlock &ab) {
-    int sumi = ab.bias;
-    const uint32_t q[4] = {w.v.x, w.v.y, w.v.z, w.v.w};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int lo = (int)(q[i] & 0x0F0F0F0Fu);
-        const int hi = (int)((q[i] >> 4) & 0x0F0F0F0Fu);
-        sumi = __dp4a(lo, ab.a[i], sumi);
-        sumi = __dp4a(hi, ab.a[4 + i], sumi);
-    }
-    return __fmul_rn(__fmul_rn((float)sumi, dx), ab.d);
-}
-__device__ __forceinline__ float block_term(const Payload<GGB_TYPE_Q8_0> &w, float dx, const ActBlock &ab) {
-    int sumi = 0;
-    sumi = __dp4a((int)w.v0.x, ab.a[0], sumi);
-    sumi = __dp4a((int)w.v0.y, ab.a[1], sumi);
-    sumi = __dp4a((int)w.v0.z, ab.a[2], sumi);
-    sumi = __dp4a((int)w.v0.w, ab.a[3], sumi);
-    sumi = __dp4a((int)w.v1.x, ab.a[4], sumi);
-    sumi = __dp4a((int)w.v1.y, ab.a[5], sumi);
-    sumi = __dp4a((int)w.v1.z, ab.a[6], sumi);
-    sumi = __dp4a((int)w.v1.w, ab.a[7], sumi);
-    return __fmul_rn((float)sumi, __fmul_rn(dx, ab.d));
-}
-
-// dot of one segment of one row: lane partial (blocks in order, from 0.0f) + butterfly
-template <int TYPE>
-__device__ __forceinline__ float segment_dot(const uint8_t *qs, const __half *d, int64_t row, int64_t nb, int64_t b0,
-                                             const ActBlock (&ab)[kTPB], const bool (&valid)[kTPB]) {
-    Payload<TYPE> w[kTPB];
-    float dx[kTPB];
-#pragma unroll
-    for (int t = 0; t < kTPB; t++) {
-        if (valid[t]) {
-            const int64_t blk = row * nb + b0 + 32 * t;
-            w[t].load(qs, blk);
-            dx[t] = __half2float(d[blk]);
-        }
-    }
-    float acc = 0.0f;
-#pragma unroll
-    for (int t = 0; t < kTPB; t++) {
-        if (valid[t]) acc = __fadd_rn(acc, block_term(w[t], dx[t], ab[t]));
-    }
-    return warp_sum_f32(acc);
-}
 
 template <int TYPE>
 __global__ void __launch_bounds__(384) matvec_kernel(const MatvecArgs a) {

@@ -16,7 +16,10 @@ int gm_set_tensor(void *m, int tensor_id, const void *host, int64_t nbytes) {
 }
 int gm_init_kv_cache(void *m) { return ((gemma_model *)m)->init_kv_cache(); }
 int gm_fill_kv_cache_synthetic(void *m, uint64_t seed) { return ((gemma_model *)m)->fill_kv_cache_synthetic(seed); }
-int gm_build_compute_graph(void *m, int capture_acts) { return ((gemma_model *)m)->build_compute_graph(capture_acts != 0); }
+int gm_build_compute_graph(void *m, int capture_acts, int fused) {
+    return ((gemma_model *)m)->build_compute_graph(capture_acts != 0, fused != 0);
+}
+int gm_is_fused(void *m) { return ((gemma_model *)m)->is_fused() ? 1 : 0; }
 int gm_decode_step(void *m, int32_t token, int32_t pos, int32_t *next) {
     return ((gemma_model *)m)->decode_step(token, pos, next);
 }

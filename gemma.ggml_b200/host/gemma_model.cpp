@@ -24,6 +24,8 @@ void gemma_model::free_all() {
     ggb_sync();
     ggb_graph_free(graph_);
     graph_ = nullptr;
+    ggb_decoder_free(decoder_);
+    decoder_ = nullptr;
     ggb_weight_free(token_embd_);
     token_embd_ = nullptr;
     for (auto &l : layers_) {
@@ -231,7 +233,7 @@ int gemma_model::emit_decode_step() {
 
 // eager (un-captured) steps with the cudaEvent probes live: per-op-class device time
 int gemma_model::run_steps_profiled(int steps) {
-    if (!graph_) return GGB_ERR_ARG;
+    if (!built_) return GGB_ERR_ARG;
     ggb_prof_enable(1);
     int rc = 0;
     for (int i = 0; i < steps && !rc; i++) rc = emit_decode_step();
@@ -240,24 +242,56 @@ int gemma_model::run_steps_profiled(int steps) {
     return rc;
 }
 
-int gemma_model::build_compute_graph(bool capture_acts) {
+// ref: build_compute_graph (:665-747).  fused: the whole token step is the persistent decode kernel;
+// otherwise the ggb_op_* sequence of emit_decode_step().  Either way the step is captured into a
+// CUDA graph once and replayed per token (a cooperative launch that cannot be captured is
+// launched directly).
+int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
     if (!token_embd_ || k_cache_.empty()) return GGB_ERR_ARG;
     GM_TRY(alloc_buffers());
     capture_acts_ = capture_acts;
     ggb_graph_free(graph_);
     graph_ = nullptr;
+    ggb_decoder_free(decoder_);
+    decoder_ = nullptr;
+    built_ = false;
     GM_TRY(ggb_sync());
-    GM_TRY(ggb_capture_begin());
-    const int rc = emit_decode_step();
-    ggb_graph *g = nullptr;
-    const int rc2 = ggb_capture_end(&g);
-    if (rc) {
-        ggb_graph_free(g);
-        return rc;
+    if (fused) {
+        const gemma_config &c = cfg_;
+        ggb_decoder_dims dims{c.n_embd, c.n_layer, c.n_head, c.n_head_kv, c.head_dim, c.n_ff, c.n_vocab, c.n_ctx, c.eps, 0};
+        std::vector<ggb_decoder_layer> ls((size_t)c.n_layer);
+        for (int il = 0; il < c.n_layer; il++) {
+            const gemma_layer &l = layers_[(size_t)il];
+            ls[(size_t)il] = ggb_decoder_layer{l.attn_norm, l.ffn_norm, l.attn_q, l.attn_k, l.attn_v, l.attn_output,
+                                               l.ffn_gate, l.ffn_up, l.ffn_down, k_cache_[(size_t)il], v_cache_[(size_t)il]};
+        }
+        ggb_decoder_io io{state_, history_, sa_out_, l_out_, kqv_, capture_acts ? ffn_act_ : nullptr, result_norm_, logits_};
+        const int rc = ggb_decoder_create(&dims, ls.data(), token_embd_, output_norm_, &io, &decoder_);
+        if (rc == GGB_ERR_UNSUPPORTED) {
+            decoder_ = nullptr; // shape outside the fused envelope: lower node by node instead
+        } else if (rc) {
+            return rc;
+        }
     }
-    GM_TRY(rc2);
-    graph_ = g;
+    if (ggb_capture_begin() == 0) {
+        const int rc = decoder_ ? ggb_decoder_step(decoder_) : emit_decode_step();
+        ggb_graph *g = nullptr;
+        const int rc2 = ggb_capture_end(&g);
+        if (rc == 0 && rc2 == 0) {
+            graph_ = g;
+        } else {
+            ggb_graph_free(g);
+            if (!decoder_) return rc ? rc : rc2; // the op sequence must be capturable
+        }
+    }
+    built_ = true;
     return 0;
+}
+
+int gemma_model::launch_step() {
+    if (graph_) return ggb_graph_launch(graph_);
+    if (decoder_) return ggb_decoder_step(decoder_);
+    return GGB_ERR_ARG;
 }
 
 int gemma_model::set_state(token_id token, int32_t pos, int32_t pos_step) {
@@ -270,8 +304,8 @@ int gemma_model::set_state(token_id token, int32_t pos, int32_t pos_step) {
 }
 
 int gemma_model::run_steps(int steps) {
-    if (!graph_) return GGB_ERR_ARG;
-    for (int i = 0; i < steps; i++) GM_TRY(ggb_graph_launch(graph_));
+    if (!built_) return GGB_ERR_ARG;
+    for (int i = 0; i < steps; i++) GM_TRY(launch_step());
     return 0;
 }
 
@@ -286,7 +320,7 @@ int gemma_model::get_state(token_id *token, int32_t *pos) {
 // host-buffer step: the e2e path (pinned H2D of the inputs, graph, D2H of the sampled token)
 int gemma_model::decode_step(token_id token, int32_t pos, token_id *next) {
     GM_TRY(set_state(token, pos, 1));
-    GM_TRY(ggb_graph_launch(graph_));
+    GM_TRY(launch_step());
     GM_TRY(ggb_download(h_state_ + 4, state_, 4)); // pinned: a true async D2H + stream sync
     if (next) *next = h_state_[4];
     return 0;
@@ -296,7 +330,7 @@ int gemma_model::decode_step(token_id token, int32_t pos, token_id *next) {
 // graph (bit-identical to the reference's batched prefill because every column of a ggml mul_mat and
 // every soft-max row is computed independently); the tcgen05 GEMM prefill is a separate path.
 int gemma_model::inference(std::vector<token_id> &input, inference_stage stage) {
-    if (input.empty() || !graph_) return GGB_ERR_ARG;
+    if (input.empty() || !built_) return GGB_ERR_ARG;
     token_id next = -1;
     if (stage == inference_stage::PREFILL) {
         for (size_t t = 0; t < input.size(); t++) GM_TRY(decode_step(input[t], (int32_t)t, &next));

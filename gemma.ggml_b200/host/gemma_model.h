@@ -47,7 +47,10 @@ class gemma_model {
     int set_tensor(int tensor_id, const void *host_data, int64_t nbytes);
     int init_kv_cache();                       // ref: :361-401
     int fill_kv_cache_synthetic(uint64_t seed); // bandwidth sweeps
-    int build_compute_graph(bool capture_acts); // ref: :665-747
+    // ref: :665-747.  fused = true lowers the token step to the persistent decode kernel
+    // (ggb_decoder_*); fused = false emits one ggb_op_* per (fused group of) graph node(s).
+    int build_compute_graph(bool capture_acts, bool fused = true);
+    bool is_fused() const { return decoder_ != nullptr; }
 
     // ref: inference() (:231-286): appends the sampled token to `input`
     int inference(std::vector<token_id> &input, inference_stage stage);
@@ -66,13 +69,14 @@ class gemma_model {
     int get_logits(float *host) const;
     int get_capture(const std::string &name, int layer, float *host, int64_t n) const;
     int get_kv(int layer, void *k_host, void *v_host) const;
-    int kernels_per_step() const { return graph_ ? ggb_graph_kernel_count(graph_) : 0; }
+    int kernels_per_step() const { return graph_ ? ggb_graph_kernel_count(graph_) : (decoder_ ? 1 : 0); }
     size_t weight_bytes() const { return weight_bytes_; }
     const gemma_config &config() const { return cfg_; }
 
   private:
     int alloc_buffers();
     int emit_decode_step(); // the op sequence of one token
+    int launch_step();      // graph replay, or a direct cooperative launch
     void free_all();
 
     gemma_config cfg_;
@@ -92,4 +96,6 @@ class gemma_model {
     void *attn_scratch_ = nullptr, *sample_scratch_ = nullptr;
     bool capture_acts_ = false;
     ggb_graph *graph_ = nullptr;
+    ggb_decoder *decoder_ = nullptr;
+    bool built_ = false;
 };

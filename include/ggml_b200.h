@@ -176,6 +176,36 @@ int ggb_op_embed_token(const ggb_weight *table, const int32_t *state, float scal
 int ggb_op_sample_greedy(const float *logits, int64_t n, int32_t *state, int32_t *history, void *scratch);
 size_t ggb_sample_scratch_bytes(int64_t n);
 
+/* ------------------------------------------------------------------ fused decode step
+ * The whole per-token node list (ref: src/gemma_model.cpp:665-747) as ONE persistent cooperative
+ * kernel: weights and KV stream through a shared-memory ring fed by TMA bulk copies while the
+ * consumers cross phase barriers (csrc/decoder.cu).  Bit-identical to the ggb_op_* sequence. */
+typedef struct {
+    int32_t n_embd, n_layer, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
+    float eps;
+    int32_t pad_;
+} ggb_decoder_dims;
+typedef struct {
+    const float *attn_norm, *ffn_norm;
+    const ggb_weight *attn_q, *attn_k, *attn_v, *attn_output, *ffn_gate, *ffn_up, *ffn_down;
+    void *k_cache, *v_cache; /* fp16, position-major [n_ctx][n_head_kv*head_dim] */
+} ggb_decoder_layer;
+typedef struct {
+    int32_t *state;   /* [token, pos, pos_step] */
+    int32_t *history; /* [n_ctx + 2] or NULL */
+    float *sa_out, *l_out; /* [n_layer][n_embd] */
+    float *kqv;            /* [n_layer][n_head*head_dim] */
+    float *ffn_act;        /* [n_layer][n_ff] or NULL (dump of gelu(gate)*up) */
+    float *result_norm;    /* [n_embd] */
+    float *logits;         /* [n_vocab] */
+} ggb_decoder_io;
+typedef struct ggb_decoder ggb_decoder;
+/* GGB_ERR_UNSUPPORTED when the shape is outside the fused kernel's envelope (callers then use ggb_op_*) */
+int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
+                       const float *output_norm, const ggb_decoder_io *io, ggb_decoder **out);
+int ggb_decoder_step(ggb_decoder *d); /* enqueue one token; capturable into a ggb_graph */
+int ggb_decoder_free(ggb_decoder *d);
+
 /* ------------------------------------------------------------------ multi-GPU (row-sharded TP)
  * one process per GPU; the 128-byte NCCL unique id is created on rank 0 and shipped by the
  * caller (torch.distributed / any transport). */

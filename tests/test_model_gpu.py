@@ -15,25 +15,29 @@ def bits(a):
 SMALL = {
     "mqa": dict(n_embd=256, n_layer=3, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=2048, n_ctx=96),
     # Gemma-7B-like: MHA, n_head*head_dim != n_embd, K > 4096 in the down projection (2 K-segments)
-    "mha": dict(n_embd=384, n_layer=2, n_head=4, n_head_kv=4, head_dim=128, n_ff=4608, n_vocab=1024, n_ctx=64),
+    "mha": dict(n_embd=512, n_layer=2, n_head=4, n_head_kv=4, head_dim=128, n_ff=4608, n_vocab=1024, n_ctx=64),
+    # outside the fused kernel's envelope (n_embd % 256 != 0): exercises the per-operator lowering
+    "odd": dict(n_embd=384, n_layer=2, n_head=4, n_head_kv=2, head_dim=96, n_ff=1056, n_vocab=777, n_ctx=48),
 }
 
 
-def _models(gpu, dims, wtype, capture=True, sigma_embd=0.002):
+def _models(gpu, dims, wtype, capture=True, sigma_embd=0.002, fused=True):
     cfg = gpu.make_config(wtype=wtype, sigma_embd=sigma_embd, **dims)
     m = gpu.GemmaModel(cfg)
     m.init_synthetic_weights()
     m.init_kv_cache()
-    m.build_compute_graph(capture_acts=capture)
+    m.build_compute_graph(capture_acts=capture, fused=fused)
     om = O.Model(wtype=wtype, sigma_embd=sigma_embd, **dims)
     return m, om
 
 
-@pytest.mark.parametrize("name", ["mqa", "mha"])
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "ops"])
+@pytest.mark.parametrize("name", ["mqa", "mha", "odd"])
 @pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
-def test_generate_matches_oracle(gpu, name, wtype):
+def test_generate_matches_oracle(gpu, name, wtype, fused):
     dims = SMALL[name]
-    m, om = _models(gpu, dims, wtype)
+    m, om = _models(gpu, dims, wtype, fused=fused)
+    assert m.is_fused == (fused and name != "odd")
     prompt = ((1 + 7919 * np.arange(12)) % dims["n_vocab"]).astype(np.int32)
     n_decode = 10
     toks, _, _ = m.generate(prompt, n_decode)
