@@ -101,7 +101,7 @@ _CUDA_SIG = {
     "ggb_op_embed_token": (i32, [vp, vp, f32, vp]),
     "ggb_op_sample_greedy": (i32, [vp, i64, vp, vp, vp]), "ggb_sample_scratch_bytes": (sz, [i64]),
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]), "ggb_decoder_step": (i32, [vp]),
-    "ggb_decoder_free": (i32, [vp]),
+    "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),
     "ggb_comm_unique_id": (i32, [vp]), "ggb_comm_init": (i32, [vp, i32, i32]), "ggb_comm_destroy": (i32, []),
     "ggb_comm_rank": (i32, []), "ggb_comm_size": (i32, []), "ggb_op_allgather": (i32, [vp, vp, sz]),
 }
@@ -110,7 +110,7 @@ _HOST_SIG = {
     "gm_create": (vp, [P(Config)]), "gm_free": (None, [vp]),
     "gm_init_synthetic_weights": (i32, [vp]), "gm_set_tensor": (i32, [vp, i32, vp, i64]),
     "gm_init_kv_cache": (i32, [vp]), "gm_fill_kv_cache_synthetic": (i32, [vp, u64]),
-    "gm_build_compute_graph": (i32, [vp, i32, i32]), "gm_is_fused": (i32, [vp]), "gm_decode_step": (i32, [vp, i32, i32, P(i32)]),
+    "gm_build_compute_graph": (i32, [vp, i32, i32]), "gm_decoder": (vp, [vp]), "gm_is_fused": (i32, [vp]), "gm_decode_step": (i32, [vp, i32, i32, P(i32)]),
     "gm_set_state": (i32, [vp, i32, i32, i32]), "gm_run_steps": (i32, [vp, i32]), "gm_run_steps_profiled": (i32, [vp, i32]),
     "gm_get_state": (i32, [vp, P(i32), P(i32)]),
     "gm_generate": (i32, [vp, vp, i32, i32, vp, P(i32), P(C.c_double), P(C.c_double)]),
@@ -358,6 +358,22 @@ class GemmaModel:
         """fused=True: the persistent decode kernel (falls back to the per-operator sequence when the
         shape is outside its envelope; see .is_fused); fused=False: one kernel per (group of) node(s)."""
         check(self.H.gm_build_compute_graph(self.h, int(capture_acts), int(fused)), "gm_build_compute_graph")
+
+    def trace_step(self):
+        """One traced fused step: (stamps[n_phases, grid, 4] in SM clocks, kinds[n_phases])."""
+        dec = self.H.gm_decoder(self.h)
+        if not dec:
+            raise GgbError("trace_step needs the fused decoder")
+        max_ph = 4096
+        grid = cuda_lib().ggb_sm_count()
+        stamps = np.zeros(max_ph * grid * 4, dtype=np.int64)
+        kinds = np.zeros(max_ph, dtype=np.int32)
+        n, g = i32(), i32()
+        check(cuda_lib().ggb_decoder_trace(dec, _ptr(stamps), _ptr(kinds), max_ph, C.byref(n), C.byref(g)),
+              "ggb_decoder_trace")
+        n1 = n.value * g.value * 4
+        self.tile_stamps = stamps[n1:n1 + g.value * 32 * 3].reshape(g.value, 32, 3).copy()
+        return stamps[:n1].reshape(n.value, g.value, 4), kinds[:n.value].copy()
 
     @property
     def is_fused(self):

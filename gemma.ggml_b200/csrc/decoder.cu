@@ -86,6 +86,8 @@ struct DecoderParams {
     unsigned long long *bar_count, *bar_base;
     const uint16_t *exp_table, *gelu_table;
     const float *rope_cos, *rope_sin;
+    long long *trace; // optional [n_phases][grid][4] SM-clock stamps: start, after prologue, after tiles, after barrier
+    long long *trace2; // optional [grid][32][3]: LOGITS tiles: before wait, after wait, after compute
 };
 
 struct SmemLayout {
@@ -97,13 +99,23 @@ struct SmemLayout {
     alignas(16) __half knew[256];
     alignas(16) __half vnew[256];
     float part[2][24][kConsumerWarps];
-    float stage[2][32];
+    float stage_g[2][32], stage_u[2][32];
     double red[kConsumerWarps];
     float cand_v[kConsumerWarps];
     int cand_i[kConsumerWarps];
     alignas(8) unsigned long long full_bar[kSlots];
     alignas(8) unsigned long long empty_bar[kSlots];
+    alignas(16) PhaseDesc ph[2]; // current / next phase descriptor (global reads would re-miss after every fence)
+    alignas(16) PhaseDesc ph_prod; // the producer's own copy (it runs phases ahead of the consumers)
+    alignas(16) DecoderParams P;   // kernel parameters (see decoder_kernel)
 };
+static_assert(sizeof(DecoderParams) % 4 == 0, "DecoderParams is copied word-wise");
+
+// Every function re-derives the layout from the extern __shared__ symbol instead of receiving a reference:
+// an out-of-line function that gets a SmemLayout& only sees a generic pointer and emits LD.E/ST.E.
+extern __shared__ __align__(1024) uint8_t ggb_dec_smem[];
+__device__ __forceinline__ SmemLayout &smem() { return *reinterpret_cast<SmemLayout *>(ggb_dec_smem); }
+static_assert(sizeof(PhaseDesc) % 4 == 0, "PhaseDesc is copied word-wise");
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,15 +155,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
-// grid barrier over the consumer threads of all CTAs
+// grid barrier over the consumer threads of all CTAs: bar.sync orders the CTA's writes before
+// thread 0's release-add (cumulative at gpu scope); the acquire-poll + bar.sync orders every
+// consumer's later reads after the other CTAs' writes.
 __device__ __forceinline__ void grid_barrier(const DecoderParams &P, unsigned long long target) {
     consumer_bar();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(P.bar_count, 1ull);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(P.bar_count), "l"(1ull) : "memory");
         while (ld_acquire_u64(P.bar_count) < target) {
         }
-        __threadfence();
     }
     consumer_bar();
 }
@@ -184,12 +196,23 @@ struct RingPos {
 
 // ---------------------------------------------------------------- producer
 template <int TYPE>
-__device__ void producer_loop(const DecoderParams &P, SmemLayout &S, int cta, int G, int n_pos) {
+__device__ __noinline__ void producer_loop(int cta, int G, int n_pos) {
+    SmemLayout &S = smem();
+    const DecoderParams &P = S.P;
     constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
     RingPos rp{0};
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
     for (int pi = 0; pi < P.n_phases; pi++) {
-        const PhaseDesc &ph = P.phases[pi];
+        // private shared-memory copy of the descriptor: one burst of independent loads per phase
+        // (a by-value struct would live in local memory because ph.m[] is indexed dynamically)
+        {
+            constexpr int kWords = (int)(sizeof(PhaseDesc) / 4);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&P.phases[pi]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&S.ph_prod);
+#pragma unroll 10
+            for (int i = 0; i < kWords; i++) dst[i] = src[i];
+        }
+        const PhaseDesc &ph = S.ph_prod;
         if (ph.kind == PH_QKV || ph.kind == PH_O || ph.kind == PH_DOWN || ph.kind == PH_LOGITS) {
             for (int t = first_unit(ph, cta, G); t < ph.n_tiles; t += G) {
                 const TileInfo ti = locate_tile(ph, t);
@@ -248,48 +271,75 @@ __device__ void producer_loop(const DecoderParams &P, SmemLayout &S, int cta, in
 
 // rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into S.act (every CTA recomputes it).
 // Sum of squares in the DEV order: threads 0..255 hold the strided double partials.
-__device__ void norm_prologue(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int token, bool write_x0,
-                              float *f32_out) {
+__device__ __noinline__ void norm_prologue(int pb, int token, bool write_x0, float *f32_out) {
+    SmemLayout &S = smem();
+    const DecoderParams &P = S.P;
+    const PhaseDesc &ph = S.ph[pb];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = P.E;
-    auto load_x = [&](int i) -> float {
-        if (ph.x_in) return __ldcg(ph.x_in + i);
-        // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
-        const int nb = E / 32, b = i >> 5, j = i & 31;
-        const float dd = __half2float(P.emb_d[(size_t)token * nb + b]);
-        float val;
-        if (P.type == GGB_TYPE_Q4_0) {
-            const uint8_t byte = P.emb_qs[((size_t)token * nb + b) * 16 + (j & 15)];
-            val = __fmul_rn((float)((j < 16 ? (byte & 0x0F) : (byte >> 4)) - 8), dd);
-        } else {
-            val = __fmul_rn((float)((const int8_t *)P.emb_qs)[((size_t)token * nb + b) * 32 + j], dd);
-        }
-        return __fmul_rn(val, P.emb_scale);
-    };
-    double acc = 0.0;
+    // thread t < 256 owns elements t, t+256, ... (E % 256 == 0).  Every load is unconditional (index clamped
+    // to the thread's last element) and issued before anything is consumed, so the prologue costs one L2
+    // round trip; the surplus copies are dropped with selects.
+    constexpr int kPer = kMaxE / GGB_DEV_NORM_THREADS;
+    const int per = E / GGB_DEV_NORM_THREADS;
+    float x[kPer], wv[kPer];
     if (tid < GGB_DEV_NORM_THREADS) {
-        for (int i = tid; i < E; i += GGB_DEV_NORM_THREADS) {
-            const float v = load_x(i);
-            acc = __dadd_rn(acc, (double)__fmul_rn(v, v));
+        const float *x_in = ph.x_in, *norm_w = ph.norm_w;
+        if (x_in) {
+#pragma unroll
+            for (int j = 0; j < kPer; j++) x[j] = __ldcg(x_in + tid + GGB_DEV_NORM_THREADS * min(j, per - 1));
+        } else {
+            // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
+            const int nb = E / 32;
+            const size_t blk0 = (size_t)token * nb;
+            int qv[kPer];
+            float dd[kPer];
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                const int i = tid + GGB_DEV_NORM_THREADS * min(j, per - 1);
+                const int b = i >> 5, e = i & 31;
+                dd[j] = __half2float(P.emb_d[blk0 + b]);
+                if (P.type == GGB_TYPE_Q4_0) {
+                    const int byte = P.emb_qs[(blk0 + b) * 16 + (e & 15)];
+                    qv[j] = (e < 16 ? (byte & 0x0F) : (byte >> 4)) - 8;
+                } else {
+                    qv[j] = ((const int8_t *)P.emb_qs)[(blk0 + b) * 32 + e];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; j++) x[j] = __fmul_rn(__fmul_rn((float)qv[j], dd[j]), P.emb_scale);
+        }
+#pragma unroll
+        for (int j = 0; j < kPer; j++) wv[j] = norm_w[tid + GGB_DEV_NORM_THREADS * min(j, per - 1)];
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const double next = __dadd_rn(acc, (double)__fmul_rn(x[j], x[j]));
+            acc = j < per ? next : acc;
         }
         acc = warp_sum_f64(acc);
         if (lane == 0) S.red[warp] = acc;
     }
     consumer_bar();
-    double sum = S.red[0];
+    if (tid < GGB_DEV_NORM_THREADS) {
+        double sum = S.red[0];
 #pragma unroll
-    for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
-    const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
-    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-    for (int i = tid; i < E; i += kConsumerThreads) { // E % 32 == 0: a warp's 32 elements are one Q8_0 block
-        const float x = load_x(i);
-        if (write_x0) P.x0[i] = x;
-        const float v = __fmul_rn(__fmul_rn(x, scale), ph.norm_w[i]);
-        if (f32_out) f32_out[i] = v;
-        float d;
-        const int q = quantize_q8_lane(v, d);
-        ((int8_t *)S.act)[i] = (int8_t)q;
-        if (lane == 0) reinterpret_cast<__half *>(S.act + E)[i >> 5] = __float2half_rn(d);
+        for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
+        const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
+        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            if (j < per) { // warp-uniform; a warp's 32 consecutive elements are one Q8_0 block
+                const int i = tid + GGB_DEV_NORM_THREADS * j;
+                if (write_x0) P.x0[i] = x[j];
+                const float v = __fmul_rn(__fmul_rn(x[j], scale), wv[j]);
+                if (f32_out) f32_out[i] = v;
+                float d;
+                const int q = quantize_q8_lane(v, d);
+                ((int8_t *)S.act)[i] = (int8_t)q;
+                if (lane == 0) reinterpret_cast<__half *>(S.act + E)[i >> 5] = __float2half_rn(d);
+            }
+        }
     }
     consumer_bar();
 }
@@ -298,6 +348,12 @@ struct Best {
     float v;
     int i;
 };
+// per-thread state crosses the out-of-line phase functions BY VALUE (registers): a reference would live in
+// local memory, be flushed/reloaded around every asm("memory") barrier, and miss the tiny L1 every time
+struct MvRet {
+    uint32_t seq;
+    Best best;
+};
 __device__ __forceinline__ Best better(Best a, Best b) {
     if (b.i < 0) return a;
     if (a.i < 0) return b;
@@ -305,114 +361,143 @@ __device__ __forceinline__ Best better(Best a, Best b) {
     return a;
 }
 
-// mat-vec phases: QKV, O, DOWN, LOGITS
-template <int TYPE>
-__device__ void matvec_phase(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int cta, int G, RingPos &rp,
-                             const uint8_t *act, bool act_in_smem, Best &best) {
+// mat-vec phases: QKV, O, DOWN, LOGITS.  Ring tiles are read with explicit ld.shared through 32-bit shared
+// addresses; the inner loop is branch-free.  Global-latency work of the epilogue is kept off the per-row
+// critical path: lane k of a warp owns the k-th row that warp computes in the tile, its residual is
+// requested BEFORE the tile is waited for, and results leave with one coalesced store per warp.
+template <int TYPE, int BPL>
+__device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
+    SmemLayout &S = smem();
+    const DecoderParams &P = S.P;
+    const PhaseDesc &ph = S.ph[pb];
     constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ksegs = ph.ksegs;
+    const int ksegs = ph.ksegs, nb = ph.nb, n_tiles = ph.n_tiles, kind = ph.kind;
+    const float *resid = ph.resid;
     const int rows_per_round = kConsumerWarps / ksegs;
     const int kseg = warp % ksegs, rsub = warp / ksegs;
     const bool warp_live = rsub < rows_per_round;
     const int b0 = kseg * GGB_DEV_SEG_BLOCKS + lane;
-    if (first_unit(ph, cta, G) >= ph.n_tiles) return;
+    const int unit0 = first_unit(ph, cta, G);
+    if (unit0 >= n_tiles) return MvRet{seq, best};
 
-    ActBlock ab[kTPB];
-    bool valid[kTPB];
+    ActBlock ab[BPL];
+    bool live[BPL];
 #pragma unroll
-    for (int t = 0; t < kTPB; t++) {
-        valid[t] = warp_live && (b0 + 32 * t < ph.nb);
-        if (act_in_smem) load_act(ab[t], act, ph.cols, b0 + 32 * t, valid[t]);
-        else load_act_cg(ab[t], act, ph.cols, b0 + 32 * t, valid[t]);
+    for (int t = 0; t < BPL; t++) {
+        live[t] = warp_live && (b0 + 32 * t < nb);
+        if (act_in_smem) load_act(ab[t], S.act, ph.cols, b0 + 32 * t, live[t]);
+        else load_act_cg(ab[t], ph.act_in, ph.cols, b0 + 32 * t, live[t]);
     }
+    const uint32_t ring0 = smem_u32(&S.ring[0][0]);
+    const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
+    const uint32_t lane_pay = (uint32_t)b0 * PB, lane_scl = (uint32_t)b0 * 2;
     int pbuf = 0;
-    for (int t = first_unit(ph, cta, G); t < ph.n_tiles; t += G) {
+    for (int t = unit0; t < n_tiles; t += G) {
         const TileInfo ti = locate_tile(ph, t);
-        const int s = rp.slot();
-        mbar_wait(&S.full_bar[s], rp.parity());
-        const uint8_t *pay = S.ring[s];
-        const __half *scl = reinterpret_cast<const __half *>(S.ring[s] + (size_t)ti.nrows * ph.nb * PB);
+        const int s = (int)(seq % kSlots);
+        const uint32_t par = (seq / kSlots) & 1u;
         float *out = ph.out[ti.mat];
+        const uint32_t pay = ring0 + (uint32_t)s * kSlotBytes + lane_pay;
+        const uint32_t scl = ring0 + (uint32_t)s * kSlotBytes + (uint32_t)ti.nrows * row_pb + lane_scl;
         if (ksegs == 1) {
-            for (int r = rsub; r < ti.nrows; r += rows_per_round) {
-                const float seg = segment_dot_smem<TYPE>(pay + (size_t)r * ph.nb * PB, scl + (size_t)r * ph.nb, b0, ab, valid);
-                if (lane == 0) {
-                    const int row = ti.row0 + r;
-                    float v = seg;
-                    if (ph.resid) v = __fadd_rn(v, __ldcg(ph.resid + row));
-                    out[row] = v;
-                    if (ph.kind == PH_LOGITS) best = better(best, Best{v, row});
-                }
+            const int myr = rsub + lane * rows_per_round; // the row lane `lane` publishes
+            const bool own = myr < ti.nrows;
+            float rv = 0.0f;
+            if (own && resid) rv = __ldcg(resid + ti.row0 + myr);
+            const int ord = (t - unit0) / G;
+            const bool dbg = P.trace2 && kind == PH_LOGITS && ord < 32 && threadIdx.x == 0;
+            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 0] = clock64();
+            mbar_wait(&S.full_bar[s], par);
+            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 1] = clock64();
+            float mine = 0.0f;
+            int k = 0;
+            for (int r = rsub; r < ti.nrows; r += rows_per_round, k++) {
+                const float seg = row_dot_lds<TYPE, BPL>(pay + (uint32_t)r * row_pb, scl + (uint32_t)r * row_sb, ab, live);
+                mine = lane == k ? seg : mine;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 2] = clock64();
+            if (own) {
+                const float v = resid ? __fadd_rn(mine, rv) : mine;
+                out[ti.row0 + myr] = v;
+                if (kind == PH_LOGITS) best = better(best, Best{v, ti.row0 + myr});
+            }
         } else {
+            float rv = 0.0f;
+            if (warp == 0 && lane < ti.nrows && resid) rv = __ldcg(resid + ti.row0 + lane);
+            mbar_wait(&S.full_bar[s], par);
             for (int r = rsub; r < ti.nrows; r += rows_per_round) {
-                float seg = 0.0f;
-                if (warp_live)
-                    seg = segment_dot_smem<TYPE>(pay + (size_t)r * ph.nb * PB, scl + (size_t)r * ph.nb, b0, ab, valid);
+                const float seg = row_dot_lds<TYPE, BPL>(pay + (uint32_t)r * row_pb, scl + (uint32_t)r * row_sb, ab, live);
                 if (lane == 0 && warp_live) S.part[pbuf][r][kseg] = seg;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty_bar[s]);
             consumer_bar();
-            if (warp_live && kseg == 0 && lane == 0) {
-                for (int r = rsub; r < ti.nrows; r += rows_per_round) {
-                    float total = S.part[pbuf][r][0];
-                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][r][k]);
-                    const int row = ti.row0 + r;
-                    if (ph.resid) total = __fadd_rn(total, __ldcg(ph.resid + row));
-                    out[row] = total;
-                    if (ph.kind == PH_LOGITS) best = better(best, Best{total, row});
-                }
+            if (warp == 0 && lane < ti.nrows) { // lane r: segment totals of row r added in segment order
+                float total = S.part[pbuf][lane][0];
+                for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][lane][k]);
+                if (resid) total = __fadd_rn(total, rv);
+                out[ti.row0 + lane] = total;
+                if (kind == PH_LOGITS) best = better(best, Best{total, ti.row0 + lane});
             }
             pbuf ^= 1;
         }
-        rp.seq++;
+        seq++;
     }
+    return MvRet{seq, best};
 }
 
-// GATE_UP: super-tiles of 32 output rows; gate and up rows of a sub-tile share a ring slot; GeGLU through
-// the fp16 gelu table, then quantize_row_q8_0 of the 32 products ([UPSTREAM] ggml_vec_gelu_f32, ggml_mul;
-// ref: src/gemma_model.cpp:444-452)
-template <int TYPE>
-__device__ void gate_up_phase(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int cta, int G, RingPos &rp) {
+// GATE_UP: super-tiles of 32 output rows; gate and up rows of a sub-tile share a ring slot; the raw dots
+// are staged in shared memory and the GeGLU (fp16 gelu table) + quantize_row_q8_0 of the 32 products
+// runs once per super-tile, lane-parallel ([UPSTREAM] ggml_vec_gelu_f32, ggml_mul; ref: src/gemma_model.cpp:444-452)
+template <int TYPE, int BPL>
+__device__ __noinline__ uint32_t gate_up_phase(int pb, int cta, int G, uint32_t seq) {
+    SmemLayout &S = smem();
+    const DecoderParams &P = S.P;
+    const PhaseDesc &ph = S.ph[pb];
     constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (first_unit(ph, cta, G) >= ph.n_tiles) return;
-    ActBlock ab[kTPB];
-    bool valid[kTPB];
+    const int nb = ph.nb, n_tiles = ph.n_tiles, rpt = ph.rows_per_tile;
+    const int unit0 = first_unit(ph, cta, G);
+    if (unit0 >= n_tiles) return seq;
+    ActBlock ab[BPL];
+    bool live[BPL];
 #pragma unroll
-    for (int t = 0; t < kTPB; t++) {
-        valid[t] = lane + 32 * t < ph.nb;
-        load_act(ab[t], S.act, ph.cols, lane + 32 * t, valid[t]);
+    for (int t = 0; t < BPL; t++) {
+        live[t] = lane + 32 * t < nb;
+        load_act(ab[t], S.act, ph.cols, lane + 32 * t, live[t]);
     }
+    const uint32_t ring0 = smem_u32(&S.ring[0][0]);
+    const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
+    const uint32_t lane_pay = (uint32_t)lane * PB, lane_scl = (uint32_t)lane * 2;
     int sbuf = 0;
-    for (int st = first_unit(ph, cta, G); st < ph.n_tiles; st += G) {
-        for (int r0 = 0; r0 < 32; r0 += ph.rows_per_tile) {
-            const int nrows = min(ph.rows_per_tile, 32 - r0);
-            const int s = rp.slot();
-            mbar_wait(&S.full_bar[s], rp.parity());
-            const size_t pbytes = (size_t)nrows * ph.nb * PB, sbytes = (size_t)nrows * ph.nb * 2;
-            const uint8_t *gp = S.ring[s], *up = S.ring[s] + pbytes + sbytes;
-            const __half *gs = reinterpret_cast<const __half *>(gp + pbytes);
-            const __half *us = reinterpret_cast<const __half *>(up + pbytes);
+    for (int st = unit0; st < n_tiles; st += G) {
+        for (int r0 = 0; r0 < 32; r0 += rpt) {
+            const int nrows = min(rpt, 32 - r0);
+            const int s = (int)(seq % kSlots);
+            mbar_wait(&S.full_bar[s], (seq / kSlots) & 1u);
+            const uint32_t pbytes = (uint32_t)nrows * row_pb, sbytes = (uint32_t)nrows * row_sb;
+            const uint32_t gp = ring0 + (uint32_t)s * kSlotBytes, up = gp + pbytes + sbytes;
             for (int r = warp; r < nrows; r += kConsumerWarps) {
-                const float g = segment_dot_smem<TYPE>(gp + (size_t)r * ph.nb * PB, gs + (size_t)r * ph.nb, lane, ab, valid);
-                const float u = segment_dot_smem<TYPE>(up + (size_t)r * ph.nb * PB, us + (size_t)r * ph.nb, lane, ab, valid);
+                const float g = row_dot_lds<TYPE, BPL>(gp + (uint32_t)r * row_pb + lane_pay,
+                                                       gp + pbytes + (uint32_t)r * row_sb + lane_scl, ab, live);
+                const float u = row_dot_lds<TYPE, BPL>(up + (uint32_t)r * row_pb + lane_pay,
+                                                       up + pbytes + (uint32_t)r * row_sb + lane_scl, ab, live);
                 if (lane == 0) {
-                    const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(g)]);
-                    S.stage[sbuf][r0 + r] = __fmul_rn(gl, u);
+                    S.stage_g[sbuf][r0 + r] = g;
+                    S.stage_u[sbuf][r0 + r] = u;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty_bar[s]);
-            rp.seq++;
+            seq++;
         }
         consumer_bar();
         if (warp == 0) {
-            const float x = S.stage[sbuf][lane];
+            const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(S.stage_g[sbuf][lane])]);
+            const float x = __fmul_rn(gl, S.stage_u[sbuf][lane]);
             const size_t row = (size_t)st * 32 + lane;
             if (ph.f32_out) ph.f32_out[row] = x;
             float d;
@@ -422,13 +507,17 @@ __device__ void gate_up_phase(const DecoderParams &P, SmemLayout &S, const Phase
         }
         sbuf ^= 1;
     }
+    return seq;
 }
 
 // ATTN: items (kv head g, chunk of 32 positions); K chunk and V chunk arrive in two ring slots.
 // Same arithmetic as attention.cu attn_partial_kernel; rope + Q scale are applied to q on load, and the
 // item that owns the newest position ropes K, rounds K/V to fp16, stores them in the cache and uses them.
-__device__ void attn_phase(const DecoderParams &P, SmemLayout &S, const PhaseDesc &ph, int cta, int G, RingPos &rp,
-                           int n_pos) {
+__device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq_in, int n_pos) {
+    SmemLayout &S = smem();
+    const DecoderParams &P = S.P;
+    const PhaseDesc &ph = S.ph[pb];
+    RingPos rp{seq_in};
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, halfd = d / 2, Gq = P.H / P.Hkv;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
@@ -441,15 +530,32 @@ __device__ void attn_phase(const DecoderParams &P, SmemLayout &S, const PhaseDes
         const int h0 = g * Gq;
         const bool owns_new = (pos >= p0 && pos < p0 + np);
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
-        for (int i = tid; i < Gq * halfd; i += kConsumerThreads) {
-            const int jh = i / halfd, e = i % halfd;
-            const float *qh = P.q + (size_t)(h0 + jh) * d;
-            const float x0 = __ldcg(qh + e), x1 = __ldcg(qh + e + halfd);
-            const float cs = cosr[e], sn = sinr[e];
-            const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
-            const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
-            S.q[jh][e] = __half2float(__float2half_rn(r0));
-            S.q[jh][e + halfd] = __half2float(__float2half_rn(r1));
+        {
+            constexpr int kQIter = (kMaxG * 128 + kConsumerThreads - 1) / kConsumerThreads;
+            float x0[kQIter], x1[kQIter], cs[kQIter], sn[kQIter];
+#pragma unroll
+            for (int it = 0; it < kQIter; it++) { // all loads first: one L2 round trip
+                const int i = tid + kConsumerThreads * it;
+                if (i < Gq * halfd) {
+                    const int jh = i / halfd, e = i % halfd;
+                    const float *qh = P.q + (size_t)(h0 + jh) * d;
+                    x0[it] = __ldcg(qh + e);
+                    x1[it] = __ldcg(qh + e + halfd);
+                    cs[it] = cosr[e];
+                    sn[it] = sinr[e];
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < kQIter; it++) {
+                const int i = tid + kConsumerThreads * it;
+                if (i < Gq * halfd) {
+                    const int jh = i / halfd, e = i % halfd;
+                    const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0[it], cs[it]), __fmul_rn(x1[it], sn[it])), P.q_scale);
+                    const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0[it], sn[it]), __fmul_rn(x1[it], cs[it])), P.q_scale);
+                    S.q[jh][e] = __half2float(__float2half_rn(r0));
+                    S.q[jh][e + halfd] = __half2float(__float2half_rn(r1));
+                }
+            }
         }
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
             for (int e = tid; e < halfd; e += kConsumerThreads) {
@@ -491,14 +597,35 @@ __device__ void attn_phase(const DecoderParams &P, SmemLayout &S, const PhaseDes
 #pragma unroll
                     for (int e = 0; e < 8; e++) kf[e] = 0.f;
                 }
-                for (int jh = 0; jh < Gq; jh++) {
-                    float acc = 0.0f;
-                    if (8 * lane < d) {
+                // all heads' lane partials first, then the 8 butterflies interleaved (ILP instead of 8
+                // serial shuffle chains); each head's sum still follows the DEV order
+                float acc[kMaxG];
 #pragma unroll
-                        for (int e = 0; e < 8; e++) acc = __fadd_rn(acc, __fmul_rn(kf[e], S.q[jh][8 * lane + e]));
+                for (int jh = 0; jh < kMaxG; jh++) {
+                    acc[jh] = 0.0f;
+                    if (jh < Gq && 8 * lane < d) {
+                        const float4 qa = *reinterpret_cast<const float4 *>(&S.q[jh][8 * lane]);
+                        const float4 qb = *reinterpret_cast<const float4 *>(&S.q[jh][8 * lane + 4]);
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[0], qa.x));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[1], qa.y));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[2], qa.z));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[3], qa.w));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[4], qb.x));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[5], qb.y));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[6], qb.z));
+                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[7], qb.w));
                     }
-                    acc = warp_sum_f32(acc);
-                    if (lane == 0) S.s[jh][j] = acc;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                    for (int jh = 0; jh < kMaxG; jh++)
+                        acc[jh] = __fadd_rn(acc[jh], __shfl_xor_sync(0xffffffffu, acc[jh], off));
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int jh = 0; jh < kMaxG; jh++)
+                        if (jh < Gq) S.s[jh][j] = acc[jh];
                 }
             }
             __syncwarp();
@@ -529,6 +656,7 @@ __device__ void attn_phase(const DecoderParams &P, SmemLayout &S, const PhaseDes
                 float a0[kMaxG / 2], a1[kMaxG / 2];
 #pragma unroll
                 for (int u = 0; u < kMaxG / 2; u++) a0[u] = a1[u] = 0.0f;
+#pragma unroll 4
                 for (int j = 0; j < np; j++) {
                     const __half *vrow = (owns_new && p0 + j == pos) ? S.vnew : vchunk + (size_t)j * d;
                     const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(vrow + 2 * dp));
@@ -557,11 +685,15 @@ __device__ void attn_phase(const DecoderParams &P, SmemLayout &S, const PhaseDes
         }
         consumer_bar();
     }
+    return rp.seq;
 }
 
 // COMBINE: one warp per (head, 32-dim slice): M = max m_c; w_c = exp_table[f16(m_c - M)];
 // L = sum l_c*w_c; O = sum acc_c*w_c (sequential in c); out = O / L; the slice is one Q8_0 block.
-__device__ void combine_phase(const DecoderParams &P, const PhaseDesc &ph, int cta, int G, int n_pos) {
+__device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
+    SmemLayout &S = smem();
+    const DecoderParams &P = S.P;
+    const PhaseDesc &ph = S.ph[pb];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = P.d, slices = d / 32;
     const int n_tasks = P.H * slices;
@@ -571,25 +703,36 @@ __device__ void combine_phase(const DecoderParams &P, const PhaseDesc &ph, int c
         const float *pm = P.attn_m + (size_t)h * P.max_chunks;
         const float *pl = P.attn_l + (size_t)h * P.max_chunks;
         const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32 + lane;
+        // pass 1: M over all chunks (lane-strided, independent loads)
         float mx = -INFINITY;
-        for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, __ldcg(pm + c));
-        mx = warp_max_f32(mx);
-        float L = 0.0f, O = 0.0f;
-        for (int c0 = 0; c0 < nchunk; c0 += 8) {
-            float a[8], l[8], m[8];
+        for (int c0 = 0; c0 < nchunk; c0 += 128) {
+            float mm[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (c0 + u < nchunk) {
-                    a[u] = __ldcg(pa + (size_t)(c0 + u) * d);
-                    l[u] = __ldcg(pl + c0 + u);
-                    m[u] = __ldcg(pm + c0 + u);
-                }
+            for (int u = 0; u < 4; u++) mm[u] = (c0 + 32 * u + lane < nchunk) ? __ldcg(pm + c0 + 32 * u + lane) : -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 4; u++) mx = fmaxf(mx, mm[u]);
+        }
+        mx = warp_max_f32(mx);
+        // pass 2: 16 chunks at a time — lane c holds (w_c, l_c), every lane prefetches its 32 acc values,
+        // then the sequential chain runs on registers and shuffles only
+        float L = 0.0f, O = 0.0f;
+        for (int c0 = 0; c0 < nchunk; c0 += 16) {
+            const int nc = min(16, nchunk - c0);
+            float a[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (u < nc) a[u] = __ldcg(pa + (size_t)(c0 + u) * d);
+            float wl = 0.0f, ll = 0.0f;
+            if (lane < nc) {
+                wl = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(__ldcg(pm + c0 + lane), mx))]);
+                ll = __ldcg(pl + c0 + lane);
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                if (c0 + u < nchunk) {
-                    const float w = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(m[u], mx))]);
-                    L = __fadd_rn(L, __fmul_rn(l[u], w));
+            for (int u = 0; u < 16; u++) {
+                if (u < nc) { // warp-uniform
+                    const float w = __shfl_sync(0xffffffffu, wl, u);
+                    const float l = __shfl_sync(0xffffffffu, ll, u);
+                    L = __fadd_rn(L, __fmul_rn(l, w));
                     O = __fadd_rn(O, __fmul_rn(a[u], w));
                 }
             }
@@ -604,10 +747,42 @@ __device__ void combine_phase(const DecoderParams &P, const PhaseDesc &ph, int c
     }
 }
 
+// blocks per lane of a 128-block segment -> compile-time BPL (fewer live registers, no predicated dead work)
 template <int TYPE>
-__global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const DecoderParams P) {
-    extern __shared__ uint8_t smem_raw[];
-    SmemLayout &S = *reinterpret_cast<SmemLayout *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+__device__ __forceinline__ MvRet run_matvec(int pb, int nb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
+    const int seg_blocks = nb < GGB_DEV_SEG_BLOCKS ? nb : GGB_DEV_SEG_BLOCKS;
+    switch ((seg_blocks + 31) / 32) {
+    case 1: return matvec_phase<TYPE, 1>(pb, cta, G, seq, act_in_smem, best);
+    case 2: return matvec_phase<TYPE, 2>(pb, cta, G, seq, act_in_smem, best);
+    case 3: return matvec_phase<TYPE, 3>(pb, cta, G, seq, act_in_smem, best);
+    default: return matvec_phase<TYPE, 4>(pb, cta, G, seq, act_in_smem, best);
+    }
+}
+template <int TYPE>
+__device__ __forceinline__ uint32_t run_gate_up(int pb, int nb, int cta, int G, uint32_t seq) {
+    switch ((nb + 31) / 32) {
+    case 1: return gate_up_phase<TYPE, 1>(pb, cta, G, seq);
+    case 2: return gate_up_phase<TYPE, 2>(pb, cta, G, seq);
+    case 3: return gate_up_phase<TYPE, 3>(pb, cta, G, seq);
+    default: return gate_up_phase<TYPE, 4>(pb, cta, G, seq);
+    }
+}
+
+// 13 warps: the register file is allocated in units of 4 warps, so the per-thread budget is 128.  With
+// 212 KB of the SM's 228 KB carved out as shared memory the L1 left for local memory is tiny and a spill
+// is an L2 round trip: the phase functions are kept out of line and templated so none of them spills.
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_constant__ DecoderParams Pk) {
+    SmemLayout &S = smem();
+    // the parameter block is copied to shared memory: the out-of-line phase functions take it by reference,
+    // and a reference to kernel parameters would be a local-memory copy
+    {
+        constexpr int kWords = (int)(sizeof(DecoderParams) / 4);
+        for (int i = threadIdx.x; i < kWords; i += kThreads)
+            reinterpret_cast<uint32_t *>(&S.P)[i] = reinterpret_cast<const uint32_t *>(&Pk)[i];
+    }
+    __syncthreads();
+    const DecoderParams &P = S.P;
     const int cta = blockIdx.x, G = gridDim.x;
     const int tid = threadIdx.x, warp = tid >> 5;
 
@@ -624,16 +799,25 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const DecoderParam
     const unsigned long long base = *P.bar_base;
 
     if (warp == kConsumerWarps) {
-        if (tid == kConsumerThreads) producer_loop<TYPE>(P, S, cta, G, n_pos);
+        if (tid == kConsumerThreads) producer_loop<TYPE>(cta, G, n_pos);
         return;
     }
 
     // ---- consumers
-    RingPos rp{0};
+    uint32_t seq = 0;
     unsigned long long bar_target = base;
     Best best{-INFINITY, -1};
+    constexpr int kPhWords = (int)(sizeof(PhaseDesc) / 4);
+    if (tid < kPhWords) reinterpret_cast<uint32_t *>(&S.ph[0])[tid] = reinterpret_cast<const uint32_t *>(&P.phases[0])[tid];
+    consumer_bar();
     for (int pi = 0; pi < P.n_phases; pi++) {
-        const PhaseDesc &ph = P.phases[pi];
+        const PhaseDesc &ph = S.ph[pi & 1];
+        // prefetch the next descriptor; it is published by the barriers at the end of this phase
+        if (pi + 1 < P.n_phases && tid < kPhWords)
+            reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1])[tid] =
+                reinterpret_cast<const uint32_t *>(&P.phases[pi + 1])[tid];
+        long long tr0 = 0, tr1 = 0;
+        if (P.trace) tr0 = tr1 = clock64();
         switch (ph.kind) {
         case PH_QKV:
         case PH_LOGITS: {
@@ -641,24 +825,34 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const DecoderParam
             const bool write_x0 = (ph.kind == PH_QKV && ph.x_in == nullptr && cta == 0);
             // LOGITS has rot = 0, so CTA 0 owns tile 0 and also writes the result_norm dump
             if (mine || write_x0)
-                norm_prologue(P, S, ph, token, write_x0, (ph.kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
-            matvec_phase<TYPE>(P, S, ph, cta, G, rp, S.act, true, best);
+                norm_prologue(pi & 1, token, write_x0, (ph.kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
+            if (P.trace) tr1 = clock64();
+            {
+                const MvRet r = run_matvec<TYPE>(pi & 1, ph.nb, cta, G, seq, true, best);
+                seq = r.seq;
+                best = r.best;
+            }
             break;
         }
         case PH_GATE_UP: {
-            if (first_unit(ph, cta, G) < ph.n_tiles) norm_prologue(P, S, ph, token, false, nullptr);
-            gate_up_phase<TYPE>(P, S, ph, cta, G, rp);
+            if (first_unit(ph, cta, G) < ph.n_tiles) norm_prologue(pi & 1, token, false, nullptr);
+            if (P.trace) tr1 = clock64();
+            seq = run_gate_up<TYPE>(pi & 1, ph.nb, cta, G, seq);
             break;
         }
         case PH_O:
         case PH_DOWN:
-            matvec_phase<TYPE>(P, S, ph, cta, G, rp, ph.act_in, false, best);
+            {
+                const MvRet r = run_matvec<TYPE>(pi & 1, ph.nb, cta, G, seq, false, best);
+                seq = r.seq;
+                best = r.best;
+            }
             break;
         case PH_ATTN:
-            attn_phase(P, S, ph, cta, G, rp, n_pos);
+            seq = attn_phase(pi & 1, cta, G, seq, n_pos);
             break;
         case PH_COMBINE:
-            combine_phase(P, ph, cta, G, n_pos);
+            combine_phase(pi & 1, cta, G, n_pos);
             break;
         case PH_SAMPLE: {
             // per-CTA candidates were published before the previous barrier; CTA 0 picks the first maximum
@@ -703,9 +897,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const DecoderParam
                 P.cand_i[cta] = b.i;
             }
         }
+        long long tr2 = 0;
+        if (P.trace) tr2 = clock64();
         if (ph.kind != PH_SAMPLE) {
             bar_target += (unsigned long long)G;
             grid_barrier(P, bar_target);
+        }
+        if (P.trace && tid == 0) {
+            long long *t = P.trace + ((size_t)pi * G + cta) * 4;
+            t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = clock64();
         }
     }
     if (cta == 0 && tid == 0) *P.bar_base = bar_target;
@@ -893,7 +1093,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     }
     P.phases = D->d_phases;
     P.n_phases = (int)D->phases.size();
-    D->smem = sizeof(SmemLayout) + 128;
+    D->smem = sizeof(SmemLayout);
     const void *fn = type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
                                            : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem);
@@ -921,6 +1121,40 @@ int ggb_decoder_step(ggb_decoder *D) {
     GGB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)D->grid), dim3(kThreads), args, D->smem, ggb_cuda_stream()));
     ggb_count_launch();
     return GGB_OK;
+}
+
+// one traced step: per phase and CTA four SM-clock stamps (start, after prologue, after tiles, after
+// the grid barrier) plus the phase kinds; the cudaEvent/ncu numbers say how long, this says where.
+int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(D && stamps && kinds && n_phases && grid, "null pointer");
+    const int np = (int)D->phases.size();
+    GGB_CHECK_ARG(max_phases >= np, "trace buffer holds %d phases, need %d", max_phases, np);
+    // stamps: [np][grid][4] phase stamps followed by [grid][32][3] LOGITS tile stamps
+    const size_t bytes1 = (size_t)np * D->grid * 4 * sizeof(long long);
+    const size_t bytes = bytes1 + (size_t)D->grid * 32 * 3 * sizeof(long long);
+    GGB_CHECK_ARG((size_t)max_phases * D->grid * 4 * sizeof(long long) >= bytes, "trace buffer too small");
+    long long *dev = nullptr;
+    GGB_CUDA(cudaMalloc(&dev, bytes));
+    GGB_CUDA(cudaMemsetAsync(dev, 0, bytes, ggb_cuda_stream()));
+    D->P.trace = dev;
+    D->P.trace2 = dev + bytes1 / sizeof(long long);
+    int rc = ggb_decoder_step(D);
+    D->P.trace = nullptr;
+    D->P.trace2 = nullptr;
+    if (rc == GGB_OK) {
+        cudaError_t e = cudaMemcpyAsync(stamps, dev, bytes, cudaMemcpyDeviceToHost, ggb_cuda_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ggb_cuda_stream());
+        if (e != cudaSuccess) {
+            ggb_set_error("decoder trace -> %s", cudaGetErrorString(e));
+            rc = GGB_ERR_CUDA;
+        }
+    }
+    cudaFree(dev);
+    for (int i = 0; i < np; i++) kinds[i] = D->phases[(size_t)i].kind;
+    *n_phases = np;
+    *grid = D->grid;
+    return rc;
 }
 
 int ggb_decoder_free(ggb_decoder *D) {

@@ -129,6 +129,68 @@ __device__ __forceinline__ float segment_dot(const uint8_t *qs, const __half *d,
     return warp_sum_f32(acc);
 }
 
+// ---- explicit shared-space loads (32-bit shared addresses).  Going through generic pointers made nvcc
+// emit LD.E + local-memory bounces in the persistent kernel; these are guaranteed LDS.
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds_half_as_float(uint32_t addr) {
+    unsigned short h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+    return __half2float(__ushort_as_half(h));
+}
+
+// Branch-free dot of one segment of one row staged in shared memory.  pay = shared address of this lane's
+// first block payload, scl = shared address of its first fp16 scale; block t of the lane sits 32 blocks
+// further.  Blocks beyond the row (live[t] false) are still loaded (any in-bounds shared address) and
+// dropped with a select, so the loop has no control flow and every value stays in registers.
+template <int TYPE, int BPL>
+__device__ __forceinline__ float row_dot_lds(uint32_t pay, uint32_t scl, const ActBlock (&ab)[BPL],
+                                             const bool (&live)[BPL]) {
+    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
+    uint4 w0[BPL], w1[BPL];
+    float dx[BPL];
+#pragma unroll
+    for (int t = 0; t < BPL; t++) {
+        w0[t] = lds_u4(pay + t * 32 * PB);
+        if (TYPE == GGB_TYPE_Q8_0) w1[t] = lds_u4(pay + t * 32 * PB + 16);
+        dx[t] = lds_half_as_float(scl + t * 64);
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < BPL; t++) {
+        const float term = TYPE == GGB_TYPE_Q4_0 ? q4_term(w0[t], dx[t], ab[t]) : q8_term(w0[t], w1[t], dx[t], ab[t]);
+        const float next = __fadd_rn(acc, term);
+        acc = live[t] ? next : acc;
+    }
+    return warp_sum_f32(acc);
+}
+
+// shared-memory variant with a compile-time number of blocks per lane (BPL = ceil(segment blocks / 32)):
+// K = 2048 needs 2, so only 2 activation blocks occupy registers and no predicated dead work is issued.
+// `live[t]` masks the ragged tail (block index >= nb) and idle warps.
+template <int TYPE, int BPL>
+__device__ __forceinline__ float segment_dot_smem_n(const uint8_t *qs_row, const __half *d_row, int b0,
+                                                    const ActBlock (&ab)[BPL], const bool (&live)[BPL]) {
+    Payload<TYPE> w[BPL];
+    float dx[BPL];
+#pragma unroll
+    for (int t = 0; t < BPL; t++) {
+        if (live[t]) {
+            w[t].load_smem(qs_row, b0 + 32 * t);
+            dx[t] = __half2float(d_row[b0 + 32 * t]);
+        }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int t = 0; t < BPL; t++) {
+        if (live[t]) acc = __fadd_rn(acc, w[t].term(dx[t], ab[t]));
+    }
+    return warp_sum_f32(acc);
+}
+
 // same with the row's payload / scale planes staged in SHARED memory (row-local block index)
 template <int TYPE>
 __device__ __forceinline__ float segment_dot_smem(const uint8_t *qs_row, const __half *d_row, int b0,

@@ -19,6 +19,7 @@ int gm_fill_kv_cache_synthetic(void *m, uint64_t seed) { return ((gemma_model *)
 int gm_build_compute_graph(void *m, int capture_acts, int fused) {
     return ((gemma_model *)m)->build_compute_graph(capture_acts != 0, fused != 0);
 }
+void *gm_decoder(void *m) { return ((gemma_model *)m)->decoder(); }
 int gm_is_fused(void *m) { return ((gemma_model *)m)->is_fused() ? 1 : 0; }
 int gm_decode_step(void *m, int32_t token, int32_t pos, int32_t *next) {
     return ((gemma_model *)m)->decode_step(token, pos, next);

@@ -51,6 +51,7 @@ class gemma_model {
     // (ggb_decoder_*); fused = false emits one ggb_op_* per (fused group of) graph node(s).
     int build_compute_graph(bool capture_acts, bool fused = true);
     bool is_fused() const { return decoder_ != nullptr; }
+    ggb_decoder *decoder() const { return decoder_; }
 
     // ref: inference() (:231-286): appends the sampled token to `input`
     int inference(std::vector<token_id> &input, inference_stage stage);
