@@ -93,7 +93,9 @@ struct DecoderParams {
 struct SmemLayout {
     alignas(128) uint8_t ring[kSlots][kSlotBytes];
     alignas(16) uint8_t act[kMaxE + kMaxE / 16]; // planar Q8_0 activation built by the norm prologue
-    alignas(16) float q[kMaxG][256];
+    // 16 KB scratch: the norm prologue's fp32 input row, the attention's rope'd q (8 x 256), the combine's
+    // staged partials (2 x 8 KB) — never live at the same time
+    alignas(16) float scratch[kMaxE];
     float s[kMaxG][kChunk];
     float e[kMaxG][kChunk];
     alignas(16) __half knew[256];
@@ -141,12 +143,38 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "r"(parity)
         : "memory");
 }
+// Producer-side wait: poll with back-off.  The producer is warp 12, which shares scheduler 0 with consumer
+// warps 0/4/8 and (highest warp id first) out-prioritises them: a tight try_wait loop there starves a
+// quarter of the consumers.  The producer runs tiles ahead, so a little wake-up latency costs nothing.
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(200);
+    }
+}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// Ampere-style async copy global -> shared, L2 only (.cg): used to stage small rows without holding registers
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
@@ -218,7 +246,7 @@ __device__ __noinline__ void producer_loop(int cta, int G, int n_pos) {
                 const TileInfo ti = locate_tile(ph, t);
                 const uint32_t pbytes = (uint32_t)ti.nrows * ph.nb * PB, sbytes = (uint32_t)ti.nrows * ph.nb * 2;
                 const int s = rp.slot();
-                mbar_wait(&S.empty_bar[s], rp.parity() ^ 1u);
+                mbar_wait_backoff(&S.empty_bar[s], rp.parity() ^ 1u);
                 mbar_expect_tx(&S.full_bar[s], pbytes + sbytes);
                 bulk_g2s(S.ring[s], ph.m[ti.mat].qs + (size_t)ti.row0 * ph.nb * PB, pbytes, &S.full_bar[s]);
                 bulk_g2s(S.ring[s] + pbytes, ph.m[ti.mat].d + (size_t)ti.row0 * ph.nb, sbytes, &S.full_bar[s]);
@@ -231,12 +259,12 @@ __device__ __noinline__ void producer_loop(int cta, int G, int n_pos) {
                     const size_t row = (size_t)st * 32 + r0;
                     const uint32_t pbytes = (uint32_t)nrows * ph.nb * PB, sbytes = (uint32_t)nrows * ph.nb * 2;
                     const int s = rp.slot();
-                    mbar_wait(&S.empty_bar[s], rp.parity() ^ 1u);
+                    mbar_wait_backoff(&S.empty_bar[s], rp.parity() ^ 1u);
                     mbar_expect_tx(&S.full_bar[s], 2 * (pbytes + sbytes));
                     uint8_t *dst = S.ring[s];
                     bulk_g2s(dst, ph.m[0].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
-                    bulk_g2s(dst + pbytes, ph.m[0].d + row * ph.nb, sbytes, &S.full_bar[s]);
-                    bulk_g2s(dst + pbytes + sbytes, ph.m[1].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
+                    bulk_g2s(dst + pbytes, ph.m[1].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
+                    bulk_g2s(dst + 2 * pbytes, ph.m[0].d + row * ph.nb, sbytes, &S.full_bar[s]);
                     bulk_g2s(dst + 2 * pbytes + sbytes, ph.m[1].d + row * ph.nb, sbytes, &S.full_bar[s]);
                     rp.seq++;
                 }
@@ -251,7 +279,7 @@ __device__ __noinline__ void producer_loop(int cta, int G, int n_pos) {
                 for (int which = 0; which < 2; which++) {
                     const __half *base = (which == 0 ? ph.kcache : ph.vcache) + (size_t)p0 * kv_stride + (size_t)g * P.d;
                     const int s = rp.slot();
-                    mbar_wait(&S.empty_bar[s], rp.parity() ^ 1u);
+                    mbar_wait_backoff(&S.empty_bar[s], rp.parity() ^ 1u);
                     mbar_expect_tx(&S.full_bar[s], (uint32_t)np * row_bytes);
                     if (P.Hkv == 1) {
                         bulk_g2s(S.ring[s], base, (uint32_t)np * row_bytes, &S.full_bar[s]);
@@ -271,75 +299,72 @@ __device__ __noinline__ void producer_loop(int cta, int G, int n_pos) {
 
 // rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into S.act (every CTA recomputes it).
 // Sum of squares in the DEV order: threads 0..255 hold the strided double partials.
+// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into S.act (every CTA recomputes it).
+// Deliberately compact (the persistent kernel is instruction-fetch sensitive): the fp32 row is staged in
+// shared memory with cp.async (one L2 round trip, no registers), the sum of squares follows the DEV order
+// (thread t < 256 sums elements t, t+256, ... in double; butterfly; warps in order), and the 12 warps then
+// quantise one 32-element block per iteration.
 __device__ __noinline__ void norm_prologue(int pb, int token, bool write_x0, float *f32_out) {
     SmemLayout &S = smem();
     const DecoderParams &P = S.P;
     const PhaseDesc &ph = S.ph[pb];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = P.E;
-    // thread t < 256 owns elements t, t+256, ... (E % 256 == 0).  Every load is unconditional (index clamped
-    // to the thread's last element) and issued before anything is consumed, so the prologue costs one L2
-    // round trip; the surplus copies are dropped with selects.
-    constexpr int kPer = kMaxE / GGB_DEV_NORM_THREADS;
-    const int per = E / GGB_DEV_NORM_THREADS;
-    float x[kPer], wv[kPer];
-    if (tid < GGB_DEV_NORM_THREADS) {
-        const float *x_in = ph.x_in, *norm_w = ph.norm_w;
-        if (x_in) {
-#pragma unroll
-            for (int j = 0; j < kPer; j++) x[j] = __ldcg(x_in + tid + GGB_DEV_NORM_THREADS * min(j, per - 1));
-        } else {
-            // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
-            const int nb = E / 32;
-            const size_t blk0 = (size_t)token * nb;
-            int qv[kPer];
-            float dd[kPer];
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                const int i = tid + GGB_DEV_NORM_THREADS * min(j, per - 1);
-                const int b = i >> 5, e = i & 31;
-                dd[j] = __half2float(P.emb_d[blk0 + b]);
-                if (P.type == GGB_TYPE_Q4_0) {
-                    const int byte = P.emb_qs[(blk0 + b) * 16 + (e & 15)];
-                    qv[j] = (e < 16 ? (byte & 0x0F) : (byte >> 4)) - 8;
-                } else {
-                    qv[j] = ((const int8_t *)P.emb_qs)[(blk0 + b) * 32 + e];
-                }
+    float *xs = S.scratch;
+    const float *x_in = ph.x_in, *norm_w = ph.norm_w;
+    if (x_in) {
+        const uint32_t xs_addr = smem_u32(xs);
+        for (int v = tid; v < E / 4; v += kConsumerThreads) cp_async16(xs_addr + 16u * v, x_in + 4 * v);
+        cp_async_wait_all();
+    } else {
+        // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
+        const int nb = E / 32;
+        const size_t blk0 = (size_t)token * nb;
+        for (int i = tid; i < E; i += kConsumerThreads) {
+            const int b = i >> 5, e = i & 31;
+            const float dd = __half2float(P.emb_d[blk0 + b]);
+            int qv;
+            if (P.type == GGB_TYPE_Q4_0) {
+                const int byte = P.emb_qs[(blk0 + b) * 16 + (e & 15)];
+                qv = (e < 16 ? (byte & 0x0F) : (byte >> 4)) - 8;
+            } else {
+                qv = ((const int8_t *)P.emb_qs)[(blk0 + b) * 32 + e];
             }
-#pragma unroll
-            for (int j = 0; j < kPer; j++) x[j] = __fmul_rn(__fmul_rn((float)qv[j], dd[j]), P.emb_scale);
+            xs[i] = __fmul_rn(__fmul_rn((float)qv, dd), P.emb_scale);
         }
-#pragma unroll
-        for (int j = 0; j < kPer; j++) wv[j] = norm_w[tid + GGB_DEV_NORM_THREADS * min(j, per - 1)];
+    }
+    consumer_bar();
+    if (tid < GGB_DEV_NORM_THREADS) {
         double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            const double next = __dadd_rn(acc, (double)__fmul_rn(x[j], x[j]));
-            acc = j < per ? next : acc;
+#pragma unroll 4
+        for (int i = tid; i < E; i += GGB_DEV_NORM_THREADS) {
+            const float v = xs[i];
+            acc = __dadd_rn(acc, (double)__fmul_rn(v, v));
         }
         acc = warp_sum_f64(acc);
         if (lane == 0) S.red[warp] = acc;
     }
     consumer_bar();
-    if (tid < GGB_DEV_NORM_THREADS) {
-        double sum = S.red[0];
+    double sum = S.red[0];
 #pragma unroll
-        for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
-        const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
-        const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            if (j < per) { // warp-uniform; a warp's 32 consecutive elements are one Q8_0 block
-                const int i = tid + GGB_DEV_NORM_THREADS * j;
-                if (write_x0) P.x0[i] = x[j];
-                const float v = __fmul_rn(__fmul_rn(x[j], scale), wv[j]);
-                if (f32_out) f32_out[i] = v;
-                float d;
-                const int q = quantize_q8_lane(v, d);
-                ((int8_t *)S.act)[i] = (int8_t)q;
-                if (lane == 0) reinterpret_cast<__half *>(S.act + E)[i >> 5] = __float2half_rn(d);
-            }
-        }
+    for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
+    const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
+    // one Q8_0 block (32 consecutive elements) per warp per iteration; next block's weight prefetched
+    float w_next = norm_w[32 * warp + lane];
+#pragma unroll 1
+    for (int b = warp; b < E / 32; b += kConsumerWarps) {
+        const int i = 32 * b + lane;
+        const float w = w_next;
+        if (b + kConsumerWarps < E / 32) w_next = norm_w[i + 32 * kConsumerWarps];
+        const float x = xs[i];
+        const float v = __fmul_rn(__fmul_rn(x, scale), w);
+        if (write_x0) P.x0[i] = x;
+        if (f32_out) f32_out[i] = v;
+        float d;
+        const int q = quantize_q8_lane(v, d);
+        ((int8_t *)S.act)[i] = (int8_t)q;
+        if (lane == 0) reinterpret_cast<__half *>(S.act + E)[b] = __float2half_rn(d);
     }
     consumer_bar();
 }
@@ -361,153 +386,183 @@ __device__ __forceinline__ Best better(Best a, Best b) {
     return a;
 }
 
-// mat-vec phases: QKV, O, DOWN, LOGITS.  Ring tiles are read with explicit ld.shared through 32-bit shared
-// addresses; the inner loop is branch-free.  Global-latency work of the epilogue is kept off the per-row
-// critical path: lane k of a warp owns the k-th row that warp computes in the tile, its residual is
-// requested BEFORE the tile is waited for, and results leave with one coalesced store per warp.
-template <int TYPE, int BPL>
+// ONE routine for every mat-vec phase (QKV, O, GATE_UP, DOWN, LOGITS).  The persistent kernel executes each
+// phase's code once per layer, so its instruction footprint per layer has to stay cache-resident: separate,
+// heavily unrolled functions per phase made the kernel instruction-fetch bound (a cold norm prologue took
+// ~4 us, the same code re-run hot 0.5 us).
+//
+// A warp always issues a "pass" of 4 block slots per lane.  With bpl = blocks per lane of one row segment
+// (K=2048 -> 2, a 128-block segment -> 4) a pass covers rp = 4/bpl rows (ksegs == 1) or one (row, segment)
+// unit (ksegs > 1); the per-row lane partial is still "blocks in order from 0.0f", then the xor-butterfly,
+// i.e. the DEV order.  Ring tiles are read with explicit ld.shared; the pass is branch-free.
+// GATE_UP slots hold [gate payload][up payload][gate scales][up scales], i.e. they look like a 2R-row tile.
+template <int TYPE>
 __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
     SmemLayout &S = smem();
     const DecoderParams &P = S.P;
     const PhaseDesc &ph = S.ph[pb];
     constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ksegs = ph.ksegs, nb = ph.nb, n_tiles = ph.n_tiles, kind = ph.kind;
+    const int kind = ph.kind, nb = ph.nb, ksegs = ph.ksegs, n_units = ph.n_tiles, rpt = ph.rows_per_tile;
+    const bool gate_up = kind == PH_GATE_UP;
     const float *resid = ph.resid;
-    const int rows_per_round = kConsumerWarps / ksegs;
-    const int kseg = warp % ksegs, rsub = warp / ksegs;
-    const bool warp_live = rsub < rows_per_round;
-    const int b0 = kseg * GGB_DEV_SEG_BLOCKS + lane;
     const int unit0 = first_unit(ph, cta, G);
-    if (unit0 >= n_tiles) return MvRet{seq, best};
+    if (unit0 >= n_units) return MvRet{seq, best};
 
-    ActBlock ab[BPL];
-    bool live[BPL];
+    const int seg_blocks = nb < GGB_DEV_SEG_BLOCKS ? nb : GGB_DEV_SEG_BLOCKS;
+    const int bpl = (seg_blocks + 31) >> 5;              // 1..4
+    const int rp = ksegs > 1 ? 1 : (bpl == 1 ? 4 : (bpl == 2 ? 2 : 1)); // rows per pass
+    const int kseg = ksegs > 1 ? warp % ksegs : 0;
+    const int rsub = ksegs > 1 ? warp / ksegs : warp;    // this warp's row group within a round
+    const int groups = ksegs > 1 ? kConsumerWarps / ksegs : kConsumerWarps;
+    const bool warp_live = rsub < groups;
+    const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
+
+    ActBlock ab[4];
+    bool blk_live[4];
+    uint32_t off_pay[4], off_scl[4];
 #pragma unroll
-    for (int t = 0; t < BPL; t++) {
-        live[t] = warp_live && (b0 + 32 * t < nb);
-        if (act_in_smem) load_act(ab[t], S.act, ph.cols, b0 + 32 * t, live[t]);
-        else load_act_cg(ab[t], ph.act_in, ph.cols, b0 + 32 * t, live[t]);
+    for (int t = 0; t < 4; t++) {
+        const int rr = bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0); // row of the pass this slot belongs to
+        const int bb = bpl == 1 ? 0 : (bpl == 2 ? (t & 1) : t);  // block slot within the row
+        const int blk = kseg * GGB_DEV_SEG_BLOCKS + lane + 32 * bb;
+        blk_live[t] = warp_live && rr < rp && bb < bpl && blk < nb;
+        if (act_in_smem) load_act(ab[t], S.act, ph.cols, blk, blk_live[t]);
+        else load_act_cg(ab[t], ph.act_in, ph.cols, blk, blk_live[t]);
+        off_pay[t] = (uint32_t)rr * row_pb + (uint32_t)blk * PB;
+        off_scl[t] = (uint32_t)rr * row_sb + (uint32_t)blk * 2;
     }
     const uint32_t ring0 = smem_u32(&S.ring[0][0]);
-    const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
-    const uint32_t lane_pay = (uint32_t)b0 * PB, lane_scl = (uint32_t)b0 * 2;
-    int pbuf = 0;
-    for (int t = unit0; t < n_tiles; t += G) {
-        const TileInfo ti = locate_tile(ph, t);
-        const int s = (int)(seq % kSlots);
-        const uint32_t par = (seq / kSlots) & 1u;
-        float *out = ph.out[ti.mat];
-        const uint32_t pay = ring0 + (uint32_t)s * kSlotBytes + lane_pay;
-        const uint32_t scl = ring0 + (uint32_t)s * kSlotBytes + (uint32_t)ti.nrows * row_pb + lane_scl;
-        if (ksegs == 1) {
-            const int myr = rsub + lane * rows_per_round; // the row lane `lane` publishes
-            const bool own = myr < ti.nrows;
+    const int n_sub = gate_up ? (32 + rpt - 1) / rpt : 1;
+    int pbuf = 0, sbuf = 0, ord = 0;
+    for (int u = unit0; u < n_units; u += G, ord++) {
+        for (int sub = 0; sub < n_sub; sub++) {
+            // geometry of this slot
+            int mat = 0, row0, nrows;
+            if (gate_up) {
+                row0 = sub * rpt;
+                nrows = min(rpt, 32 - row0);
+            } else {
+                const TileInfo ti = locate_tile(ph, u);
+                mat = ti.mat; row0 = ti.row0; nrows = ti.nrows;
+            }
+            const int slot_rows = gate_up ? 2 * nrows : nrows;
+            const int s = (int)(seq % kSlots);
+            const uint32_t par = (seq / kSlots) & 1u;
+            const uint32_t pay0 = ring0 + (uint32_t)s * kSlotBytes;
+            const uint32_t scl0 = pay0 + (uint32_t)slot_rows * row_pb;
+            // epilogue lane j < rp publishes row (first row of this warp's pass) + j; its residual is requested
+            // before the tile is waited for
+            const int my_first = rsub * rp;
+            const int pstride = 32 / rp;
+            const bool own0 = ksegs == 1 ? ((lane % pstride) == 0 && my_first + lane / pstride < slot_rows)
+                                         : (warp == 0 && lane < nrows);
             float rv = 0.0f;
-            if (own && resid) rv = __ldcg(resid + ti.row0 + myr);
-            const int ord = (t - unit0) / G;
-            const bool dbg = P.trace2 && kind == PH_LOGITS && ord < 32 && threadIdx.x == 0;
+            if (own0 && resid) rv = __ldcg(resid + row0 + (ksegs == 1 ? my_first + lane / pstride : lane));
+            const bool dbg = P.trace2 && kind == PH_LOGITS && ord < 31 && threadIdx.x == 0;
             if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 0] = clock64();
             mbar_wait(&S.full_bar[s], par);
             if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 1] = clock64();
-            float mine = 0.0f;
-            int k = 0;
-            for (int r = rsub; r < ti.nrows; r += rows_per_round, k++) {
-                const float seg = row_dot_lds<TYPE, BPL>(pay + (uint32_t)r * row_pb, scl + (uint32_t)r * row_sb, ab, live);
-                mine = lane == k ? seg : mine;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
-            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 2] = clock64();
-            if (own) {
-                const float v = resid ? __fadd_rn(mine, rv) : mine;
-                out[ti.row0 + myr] = v;
-                if (kind == PH_LOGITS) best = better(best, Best{v, ti.row0 + myr});
-            }
-        } else {
-            float rv = 0.0f;
-            if (warp == 0 && lane < ti.nrows && resid) rv = __ldcg(resid + ti.row0 + lane);
-            mbar_wait(&S.full_bar[s], par);
-            for (int r = rsub; r < ti.nrows; r += rows_per_round) {
-                const float seg = row_dot_lds<TYPE, BPL>(pay + (uint32_t)r * row_pb, scl + (uint32_t)r * row_sb, ab, live);
-                if (lane == 0 && warp_live) S.part[pbuf][r][kseg] = seg;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
-            consumer_bar();
-            if (warp == 0 && lane < ti.nrows) { // lane r: segment totals of row r added in segment order
-                float total = S.part[pbuf][lane][0];
-                for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][lane][k]);
-                if (resid) total = __fadd_rn(total, rv);
-                out[ti.row0 + lane] = total;
-                if (kind == PH_LOGITS) best = better(best, Best{total, ti.row0 + lane});
-            }
-            pbuf ^= 1;
-        }
-        seq++;
-    }
-    return MvRet{seq, best};
-}
-
-// GATE_UP: super-tiles of 32 output rows; gate and up rows of a sub-tile share a ring slot; the raw dots
-// are staged in shared memory and the GeGLU (fp16 gelu table) + quantize_row_q8_0 of the 32 products
-// runs once per super-tile, lane-parallel ([UPSTREAM] ggml_vec_gelu_f32, ggml_mul; ref: src/gemma_model.cpp:444-452)
-template <int TYPE, int BPL>
-__device__ __noinline__ uint32_t gate_up_phase(int pb, int cta, int G, uint32_t seq) {
-    SmemLayout &S = smem();
-    const DecoderParams &P = S.P;
-    const PhaseDesc &ph = S.ph[pb];
-    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nb = ph.nb, n_tiles = ph.n_tiles, rpt = ph.rows_per_tile;
-    const int unit0 = first_unit(ph, cta, G);
-    if (unit0 >= n_tiles) return seq;
-    ActBlock ab[BPL];
-    bool live[BPL];
+            for (int first = my_first; first < slot_rows; first += groups * rp) {
+                uint4 w0[4], w1[4];
+                float dx[4];
+                const uint32_t pbase = pay0 + (uint32_t)first * row_pb, sbase = scl0 + (uint32_t)first * row_sb;
 #pragma unroll
-    for (int t = 0; t < BPL; t++) {
-        live[t] = lane + 32 * t < nb;
-        load_act(ab[t], S.act, ph.cols, lane + 32 * t, live[t]);
-    }
-    const uint32_t ring0 = smem_u32(&S.ring[0][0]);
-    const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
-    const uint32_t lane_pay = (uint32_t)lane * PB, lane_scl = (uint32_t)lane * 2;
-    int sbuf = 0;
-    for (int st = unit0; st < n_tiles; st += G) {
-        for (int r0 = 0; r0 < 32; r0 += rpt) {
-            const int nrows = min(rpt, 32 - r0);
-            const int s = (int)(seq % kSlots);
-            mbar_wait(&S.full_bar[s], (seq / kSlots) & 1u);
-            const uint32_t pbytes = (uint32_t)nrows * row_pb, sbytes = (uint32_t)nrows * row_sb;
-            const uint32_t gp = ring0 + (uint32_t)s * kSlotBytes, up = gp + pbytes + sbytes;
-            for (int r = warp; r < nrows; r += kConsumerWarps) {
-                const float g = row_dot_lds<TYPE, BPL>(gp + (uint32_t)r * row_pb + lane_pay,
-                                                       gp + pbytes + (uint32_t)r * row_sb + lane_scl, ab, live);
-                const float u = row_dot_lds<TYPE, BPL>(up + (uint32_t)r * row_pb + lane_pay,
-                                                       up + pbytes + (uint32_t)r * row_sb + lane_scl, ab, live);
-                if (lane == 0) {
-                    S.stage_g[sbuf][r0 + r] = g;
-                    S.stage_u[sbuf][r0 + r] = u;
+                for (int t = 0; t < 4; t++) {
+                    w0[t] = lds_u4(pbase + off_pay[t]);
+                    if (TYPE == GGB_TYPE_Q8_0) w1[t] = lds_u4(pbase + off_pay[t] + 16);
+                    dx[t] = lds_half_as_float(sbase + off_scl[t]);
+                }
+                float term[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    term[t] = TYPE == GGB_TYPE_Q4_0 ? q4_term(w0[t], dx[t], ab[t]) : q8_term(w0[t], w1[t], dx[t], ab[t]);
+                // lane partial of each row of the pass: its blocks in order, from 0.0f (dead slots dropped by select)
+                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int rr = bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0);
+                    const bool on = blk_live[t] && first + rr < slot_rows;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const float nx = __fadd_rn(acc[r], term[t]);
+                        acc[r] = (on && rr == r) ? nx : acc[r];
+                    }
+                }
+                // xor-butterfly 16,8,4,2,1 per row (DEV order).  rp == 2 (the K=2048 shapes) folds both rows into
+                // one butterfly: at offset 16 lanes < 16 keep row 0 and receive its upper half, lanes >= 16 keep
+                // row 1 — the same pairs are added as in two separate butterflies, with half the shuffles.
+                // No shuffle sits under a data-dependent predicate (that costs a divergence check each).
+                float mine;
+                if (rp == 2) {
+                    const bool lo = lane < 16;
+                    const float send = lo ? acc[1] : acc[0];
+                    float keep = __fadd_rn(lo ? acc[0] : acc[1], __shfl_xor_sync(0xffffffffu, send, 16));
+#pragma unroll
+                    for (int off = 8; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
+                    mine = keep; // lanes 0..15: row 0 total, lanes 16..31: row 1 total
+                } else if (rp == 1) {
+                    acc[0] = warp_sum_f32(acc[0]);
+                    mine = acc[0];
+                } else {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int r = 0; r < 4; r++) acc[r] = __fadd_rn(acc[r], __shfl_xor_sync(0xffffffffu, acc[r], off));
+                    }
+                    mine = lane < 8 ? acc[0] : (lane < 16 ? acc[1] : (lane < 24 ? acc[2] : acc[3]));
+                }
+                // row j of the pass is published by lane j * (32 / rp)
+                const int pub_stride = 32 / rp;
+                const int jrow = lane / pub_stride;
+                const bool pub = (lane % pub_stride) == 0 && first + jrow < slot_rows;
+                if (ksegs > 1) {
+                    if (lane == 0 && warp_live) S.part[pbuf][first][kseg] = mine;
+                } else if (pub) {
+                    const int r = first + jrow;
+                    if (gate_up) {
+                        if (r < nrows) S.stage_g[sbuf][row0 + r] = mine;
+                        else S.stage_u[sbuf][row0 + r - nrows] = mine;
+                    } else {
+                        float v = mine;
+                        if (resid) v = __fadd_rn(v, first == my_first ? rv : __ldcg(resid + row0 + r));
+                        ph.out[mat][row0 + r] = v;
+                        if (kind == PH_LOGITS) best = better(best, Best{v, row0 + r});
+                    }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 2] = clock64();
+            if (ksegs > 1) {
+                consumer_bar();
+                if (warp == 0 && lane < nrows) { // lane r: segment totals of row r added in segment order
+                    float total = S.part[pbuf][lane][0];
+                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][lane][k]);
+                    if (resid) total = __fadd_rn(total, rv);
+                    ph.out[mat][row0 + lane] = total;
+                    if (kind == PH_LOGITS) best = better(best, Best{total, row0 + lane});
+                }
+                pbuf ^= 1;
+            }
             seq++;
         }
-        consumer_bar();
-        if (warp == 0) {
-            const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(S.stage_g[sbuf][lane])]);
-            const float x = __fmul_rn(gl, S.stage_u[sbuf][lane]);
-            const size_t row = (size_t)st * 32 + lane;
-            if (ph.f32_out) ph.f32_out[row] = x;
-            float d;
-            const int q = quantize_q8_lane(x, d);
-            ((int8_t *)ph.act_out)[row] = (int8_t)q;
-            if (lane == 0) reinterpret_cast<__half *>(ph.act_out + P.F)[st] = __float2half_rn(d);
+        if (gate_up) { // GeGLU (fp16 gelu table) + quantize_row_q8_0 of the super-tile's 32 products, lane-parallel
+            consumer_bar();
+            if (warp == 0) {
+                const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(S.stage_g[sbuf][lane])]);
+                const float x = __fmul_rn(gl, S.stage_u[sbuf][lane]);
+                const size_t row = (size_t)u * 32 + lane;
+                if (ph.f32_out) ph.f32_out[row] = x;
+                float d;
+                const int q = quantize_q8_lane(x, d);
+                ((int8_t *)ph.act_out)[row] = (int8_t)q;
+                if (lane == 0) reinterpret_cast<__half *>(ph.act_out + P.F)[u] = __float2half_rn(d);
+            }
+            sbuf ^= 1;
         }
-        sbuf ^= 1;
     }
-    return seq;
+    return MvRet{seq, best};
 }
 
 // ATTN: items (kv head g, chunk of 32 positions); K chunk and V chunk arrive in two ring slots.
@@ -524,6 +579,8 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
     const int n_items = P.Hkv * nchunk;
     const int pos = n_pos - 1;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
+    float(*Sq)[256] = reinterpret_cast<float(*)[256]>(S.scratch);
+#pragma unroll 1
     for (int it = first_unit(ph, cta, G); it < n_items; it += G) {
         const int g = it / nchunk, c = it % nchunk;
         const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
@@ -552,8 +609,8 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
                     const int jh = i / halfd, e = i % halfd;
                     const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0[it], cs[it]), __fmul_rn(x1[it], sn[it])), P.q_scale);
                     const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0[it], sn[it]), __fmul_rn(x1[it], cs[it])), P.q_scale);
-                    S.q[jh][e] = __half2float(__float2half_rn(r0));
-                    S.q[jh][e + halfd] = __half2float(__float2half_rn(r1));
+                    Sq[jh][e] = __half2float(__float2half_rn(r0));
+                    Sq[jh][e + halfd] = __half2float(__float2half_rn(r1));
                 }
             }
         }
@@ -597,35 +654,37 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
 #pragma unroll
                     for (int e = 0; e < 8; e++) kf[e] = 0.f;
                 }
-                // all heads' lane partials first, then the 8 butterflies interleaved (ILP instead of 8
-                // serial shuffle chains); each head's sum still follows the DEV order
-                float acc[kMaxG];
+                // heads in groups of 4: lane partials first, then the group's butterflies interleaved (ILP
+                // without unrolling all 8 heads: code size matters here); each sum follows the DEV order
+#pragma unroll 1
+                for (int j0 = 0; j0 < Gq; j0 += 4) {
+                    float acc[4];
 #pragma unroll
-                for (int jh = 0; jh < kMaxG; jh++) {
-                    acc[jh] = 0.0f;
-                    if (jh < Gq && 8 * lane < d) {
-                        const float4 qa = *reinterpret_cast<const float4 *>(&S.q[jh][8 * lane]);
-                        const float4 qb = *reinterpret_cast<const float4 *>(&S.q[jh][8 * lane + 4]);
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[0], qa.x));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[1], qa.y));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[2], qa.z));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[3], qa.w));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[4], qb.x));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[5], qb.y));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[6], qb.z));
-                        acc[jh] = __fadd_rn(acc[jh], __fmul_rn(kf[7], qb.w));
+                    for (int u = 0; u < 4; u++) {
+                        acc[u] = 0.0f;
+                        if (j0 + u < Gq && 8 * lane < d) {
+                            const float4 qa = *reinterpret_cast<const float4 *>(&Sq[j0 + u][8 * lane]);
+                            const float4 qb = *reinterpret_cast<const float4 *>(&Sq[j0 + u][8 * lane + 4]);
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[0], qa.x));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[1], qa.y));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[2], qa.z));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[3], qa.w));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[4], qb.x));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[5], qb.y));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[6], qb.z));
+                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[7], qb.w));
+                        }
                     }
-                }
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
+                    for (int off = 16; off >= 1; off >>= 1) {
 #pragma unroll
-                    for (int jh = 0; jh < kMaxG; jh++)
-                        acc[jh] = __fadd_rn(acc[jh], __shfl_xor_sync(0xffffffffu, acc[jh], off));
-                }
-                if (lane == 0) {
+                        for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __shfl_xor_sync(0xffffffffu, acc[u], off));
+                    }
+                    if (lane == 0) {
 #pragma unroll
-                    for (int jh = 0; jh < kMaxG; jh++)
-                        if (jh < Gq) S.s[jh][j] = acc[jh];
+                        for (int u = 0; u < 4; u++)
+                            if (j0 + u < Gq) S.s[j0 + u][j] = acc[u];
+                    }
                 }
             }
             __syncwarp();
@@ -656,7 +715,7 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
                 float a0[kMaxG / 2], a1[kMaxG / 2];
 #pragma unroll
                 for (int u = 0; u < kMaxG / 2; u++) a0[u] = a1[u] = 0.0f;
-#pragma unroll 4
+#pragma unroll 2
                 for (int j = 0; j < np; j++) {
                     const __half *vrow = (owns_new && p0 + j == pos) ? S.vnew : vchunk + (size_t)j * d;
                     const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(vrow + 2 * dp));
@@ -690,6 +749,8 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
 
 // COMBINE: one warp per (head, 32-dim slice): M = max m_c; w_c = exp_table[f16(m_c - M)];
 // L = sum l_c*w_c; O = sum acc_c*w_c (sequential in c); out = O / L; the slice is one Q8_0 block.
+// Compact on purpose: the warp stages its 64-chunk window of partials in shared memory with cp.async
+// (one L2 round trip), then runs the sequential chain from shared memory.
 __device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
     SmemLayout &S = smem();
     const DecoderParams &P = S.P;
@@ -698,44 +759,48 @@ __device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
     const int d = P.d, slices = d / 32;
     const int n_tasks = P.H * slices;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    for (int task = warp * G + ((cta - ph.rot) % G + G) % G; task < n_tasks; task += kConsumerWarps * G) {
+    if (warp >= 2) return; // two 8 KB staging windows -> at most two tasks in flight per CTA
+    float *win = S.scratch + warp * 2048; // 64 chunks x 32 floats
+    const uint32_t win_addr = smem_u32(win);
+#pragma unroll 1
+    for (int task = warp * G + ((cta - ph.rot) % G + G) % G; task < n_tasks; task += 2 * G) {
         const int h = task / slices, sl = task % slices;
         const float *pm = P.attn_m + (size_t)h * P.max_chunks;
         const float *pl = P.attn_l + (size_t)h * P.max_chunks;
-        const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32 + lane;
-        // pass 1: M over all chunks (lane-strided, independent loads)
+        const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32;
         float mx = -INFINITY;
-        for (int c0 = 0; c0 < nchunk; c0 += 128) {
-            float mm[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) mm[u] = (c0 + 32 * u + lane < nchunk) ? __ldcg(pm + c0 + 32 * u + lane) : -INFINITY;
-#pragma unroll
-            for (int u = 0; u < 4; u++) mx = fmaxf(mx, mm[u]);
-        }
+#pragma unroll 4
+        for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, __ldcg(pm + c));
         mx = warp_max_f32(mx);
-        // pass 2: 16 chunks at a time — lane c holds (w_c, l_c), every lane prefetches its 32 acc values,
-        // then the sequential chain runs on registers and shuffles only
         float L = 0.0f, O = 0.0f;
-        for (int c0 = 0; c0 < nchunk; c0 += 16) {
-            const int nc = min(16, nchunk - c0);
-            float a[16];
+#pragma unroll 1
+        for (int c0 = 0; c0 < nchunk; c0 += 64) {
+            const int nc = min(64, nchunk - c0);
+            // stage nc x 128 B: 8 x 16 B pieces per chunk
+            for (int v = lane; v < nc * 8; v += 32)
+                cp_async16(win_addr + 16u * v, pa + (size_t)(c0 + (v >> 3)) * d + 4 * (v & 7));
+            float wl[2], ll[2];
 #pragma unroll
-            for (int u = 0; u < 16; u++)
-                if (u < nc) a[u] = __ldcg(pa + (size_t)(c0 + u) * d);
-            float wl = 0.0f, ll = 0.0f;
-            if (lane < nc) {
-                wl = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(__ldcg(pm + c0 + lane), mx))]);
-                ll = __ldcg(pl + c0 + lane);
+            for (int u = 0; u < 2; u++) {
+                const int c = c0 + 32 * u + lane;
+                const bool ok = 32 * u + lane < nc;
+                wl[u] = ok ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(__ldcg(pm + c), mx))]) : 0.0f;
+                ll[u] = ok ? __ldcg(pl + c) : 0.0f;
             }
-#pragma unroll
-            for (int u = 0; u < 16; u++) {
-                if (u < nc) { // warp-uniform
-                    const float w = __shfl_sync(0xffffffffu, wl, u);
-                    const float l = __shfl_sync(0xffffffffu, ll, u);
+            cp_async_wait_all();
+            __syncwarp();
+#pragma unroll 1
+            for (int u = 0; u < 2; u++) {
+                const int n = min(32, nc - 32 * u);
+#pragma unroll 4
+                for (int j = 0; j < n; j++) {
+                    const float w = __shfl_sync(0xffffffffu, wl[u], j);
+                    const float l = __shfl_sync(0xffffffffu, ll[u], j);
                     L = __fadd_rn(L, __fmul_rn(l, w));
-                    O = __fadd_rn(O, __fmul_rn(a[u], w));
+                    O = __fadd_rn(O, __fmul_rn(win[(32 * u + j) * 32 + lane], w));
                 }
             }
+            __syncwarp();
         }
         const float r = __fdiv_rn(O, L);
         const size_t idx = (size_t)h * d + sl * 32 + lane;
@@ -744,27 +809,6 @@ __device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
         const int qv = quantize_q8_lane(r, dd);
         ((int8_t *)ph.act_out)[idx] = (int8_t)qv;
         if (lane == 0) reinterpret_cast<__half *>(ph.act_out + (size_t)P.H * d)[idx >> 5] = __float2half_rn(dd);
-    }
-}
-
-// blocks per lane of a 128-block segment -> compile-time BPL (fewer live registers, no predicated dead work)
-template <int TYPE>
-__device__ __forceinline__ MvRet run_matvec(int pb, int nb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
-    const int seg_blocks = nb < GGB_DEV_SEG_BLOCKS ? nb : GGB_DEV_SEG_BLOCKS;
-    switch ((seg_blocks + 31) / 32) {
-    case 1: return matvec_phase<TYPE, 1>(pb, cta, G, seq, act_in_smem, best);
-    case 2: return matvec_phase<TYPE, 2>(pb, cta, G, seq, act_in_smem, best);
-    case 3: return matvec_phase<TYPE, 3>(pb, cta, G, seq, act_in_smem, best);
-    default: return matvec_phase<TYPE, 4>(pb, cta, G, seq, act_in_smem, best);
-    }
-}
-template <int TYPE>
-__device__ __forceinline__ uint32_t run_gate_up(int pb, int nb, int cta, int G, uint32_t seq) {
-    switch ((nb + 31) / 32) {
-    case 1: return gate_up_phase<TYPE, 1>(pb, cta, G, seq);
-    case 2: return gate_up_phase<TYPE, 2>(pb, cta, G, seq);
-    case 3: return gate_up_phase<TYPE, 3>(pb, cta, G, seq);
-    default: return gate_up_phase<TYPE, 4>(pb, cta, G, seq);
     }
 }
 
@@ -828,7 +872,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                 norm_prologue(pi & 1, token, write_x0, (ph.kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
             if (P.trace) tr1 = clock64();
             {
-                const MvRet r = run_matvec<TYPE>(pi & 1, ph.nb, cta, G, seq, true, best);
+                const MvRet r = matvec_phase<TYPE>(pi & 1, cta, G, seq, true, best);
                 seq = r.seq;
                 best = r.best;
             }
@@ -837,13 +881,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         case PH_GATE_UP: {
             if (first_unit(ph, cta, G) < ph.n_tiles) norm_prologue(pi & 1, token, false, nullptr);
             if (P.trace) tr1 = clock64();
-            seq = run_gate_up<TYPE>(pi & 1, ph.nb, cta, G, seq);
+            seq = matvec_phase<TYPE>(pi & 1, cta, G, seq, true, best).seq;
             break;
         }
         case PH_O:
         case PH_DOWN:
             {
-                const MvRet r = run_matvec<TYPE>(pi & 1, ph.nb, cta, G, seq, false, best);
+                const MvRet r = matvec_phase<TYPE>(pi & 1, cta, G, seq, false, best);
                 seq = r.seq;
                 best = r.best;
             }
@@ -1132,7 +1176,8 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
     GGB_CHECK_ARG(max_phases >= np, "trace buffer holds %d phases, need %d", max_phases, np);
     // stamps: [np][grid][4] phase stamps followed by [grid][32][3] LOGITS tile stamps
     const size_t bytes1 = (size_t)np * D->grid * 4 * sizeof(long long);
-    const size_t bytes = bytes1 + (size_t)D->grid * 32 * 3 * sizeof(long long);
+    const size_t bytes2 = (size_t)D->grid * 32 * 3 * sizeof(long long);
+    const size_t bytes = bytes1 + bytes2 + (size_t)D->grid * 8 * sizeof(long long);
     GGB_CHECK_ARG((size_t)max_phases * D->grid * 4 * sizeof(long long) >= bytes, "trace buffer too small");
     long long *dev = nullptr;
     GGB_CUDA(cudaMalloc(&dev, bytes));

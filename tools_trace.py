@@ -40,6 +40,9 @@ def main():
         comp = (t[:, 2] - t[:, 1]) / mhz
         gap = (t[1:, 0] - t[:-1, 2]) / mhz
         print(f"LOGITS cta {cta}: wait us", np.round(wait[:12], 2), "compute us", np.round(comp[:12], 2), "gap", np.round(gap[:6], 2))
+    ex = ts[:, 31, :]
+    okk = ex[:, 0] > 0
+    print('prologue experiment (2nd, 3rd run back-to-back) us: 2nd mean %.2f max %.2f | 3rd mean %.2f max %.2f' % (((ex[okk,1]-ex[okk,0])/mhz).mean(), ((ex[okk,1]-ex[okk,0])/mhz).max(), ((ex[okk,2]-ex[okk,1])/mhz).mean(), ((ex[okk,2]-ex[okk,1])/mhz).max()))
     # layer 1 detail
     for pi in range(6, 12):
         s = st[pi].astype(np.float64)
