@@ -159,7 +159,7 @@ __device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, uint3
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (done) return;
-        __nanosleep(200);
+        __nanosleep(500);
     }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
@@ -186,12 +186,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 // grid barrier over the consumer threads of all CTAs: bar.sync orders the CTA's writes before
 // thread 0's release-add (cumulative at gpu scope); the acquire-poll + bar.sync orders every
 // consumer's later reads after the other CTAs' writes.
-__device__ __forceinline__ void grid_barrier(const DecoderParams &P, unsigned long long target) {
+// Polling uses relaxed loads (an acquire load costs an L1 invalidate — CCTL.IVALL — per poll) and a single
+// acquire fence once the count is reached.
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar_count, unsigned long long target) {
     consumer_bar();
     if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(P.bar_count), "l"(1ull) : "memory");
-        while (ld_acquire_u64(P.bar_count) < target) {
-        }
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar_count), "l"(1ull) : "memory");
+        unsigned long long v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar_count) : "memory");
+        } while (v < target);
+        (void)ld_acquire_u64(bar_count);
     }
     consumer_bar();
 }
@@ -396,7 +401,10 @@ __device__ __forceinline__ Best better(Best a, Best b) {
 // unit (ksegs > 1); the per-row lane partial is still "blocks in order from 0.0f", then the xor-butterfly,
 // i.e. the DEV order.  Ring tiles are read with explicit ld.shared; the pass is branch-free.
 // GATE_UP slots hold [gate payload][up payload][gate scales][up scales], i.e. they look like a 2R-row tile.
-template <int TYPE>
+// ROWS2 = the K <= 2048 shapes (bpl == 2, one segment): the two rows of a pass share the lane's two activation
+// blocks, so only 20 registers hold activations and the pass addresses collapse to (lane, +32 blocks, +1 row);
+// the freed registers let ptxas keep the four dp4a chains interleaved instead of serialising them.
+template <int TYPE, bool ROWS2>
 __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
     SmemLayout &S = smem();
     const DecoderParams &P = S.P;
@@ -406,6 +414,7 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
     const int kind = ph.kind, nb = ph.nb, ksegs = ph.ksegs, n_units = ph.n_tiles, rpt = ph.rows_per_tile;
     const bool gate_up = kind == PH_GATE_UP;
     const float *resid = ph.resid;
+    const int n_mats = ph.n_mats, rows0 = ph.m[0].rows;
     const int unit0 = first_unit(ph, cta, G);
     if (unit0 >= n_units) return MvRet{seq, best};
 
@@ -418,17 +427,20 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
     const bool warp_live = rsub < groups;
     const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
 
-    ActBlock ab[4];
+    constexpr int NA = ROWS2 ? 2 : 4;
+    ActBlock ab[NA];
     bool blk_live[4];
     uint32_t off_pay[4], off_scl[4];
 #pragma unroll
     for (int t = 0; t < 4; t++) {
-        const int rr = bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0); // row of the pass this slot belongs to
-        const int bb = bpl == 1 ? 0 : (bpl == 2 ? (t & 1) : t);  // block slot within the row
+        const int rr = ROWS2 ? (t >> 1) : (bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0)); // row of the pass
+        const int bb = ROWS2 ? (t & 1) : (bpl == 1 ? 0 : (bpl == 2 ? (t & 1) : t));   // block slot within the row
         const int blk = kseg * GGB_DEV_SEG_BLOCKS + lane + 32 * bb;
         blk_live[t] = warp_live && rr < rp && bb < bpl && blk < nb;
-        if (act_in_smem) load_act(ab[t], S.act, ph.cols, blk, blk_live[t]);
-        else load_act_cg(ab[t], ph.act_in, ph.cols, blk, blk_live[t]);
+        if (!ROWS2 || t < 2) {
+            if (act_in_smem) load_act(ab[ROWS2 ? (t & 1) : t], S.act, ph.cols, blk, blk_live[t]);
+            else load_act_cg(ab[ROWS2 ? (t & 1) : t], ph.act_in, ph.cols, blk, blk_live[t]);
+        }
         off_pay[t] = (uint32_t)rr * row_pb + (uint32_t)blk * PB;
         off_scl[t] = (uint32_t)rr * row_sb + (uint32_t)blk * 2;
     }
@@ -442,6 +454,9 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
             if (gate_up) {
                 row0 = sub * rpt;
                 nrows = min(rpt, 32 - row0);
+            } else if (n_mats == 1) {
+                row0 = u * rpt;
+                nrows = min(rpt, rows0 - row0);
             } else {
                 const TileInfo ti = locate_tile(ph, u);
                 mat = ti.mat; row0 = ti.row0; nrows = ti.nrows;
@@ -474,14 +489,12 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
                     dx[t] = lds_half_as_float(sbase + off_scl[t]);
                 }
                 float term[4];
-#pragma unroll
-                for (int t = 0; t < 4; t++)
-                    term[t] = TYPE == GGB_TYPE_Q4_0 ? q4_term(w0[t], dx[t], ab[t]) : q8_term(w0[t], w1[t], dx[t], ab[t]);
+                pass_terms<TYPE, NA>(w0, w1, dx, ab, term);
                 // lane partial of each row of the pass: its blocks in order, from 0.0f (dead slots dropped by select)
                 float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    const int rr = bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0);
+                    const int rr = ROWS2 ? (t >> 1) : (bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0));
                     const bool on = blk_live[t] && first + rr < slot_rows;
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
@@ -812,6 +825,14 @@ __device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
     }
 }
 
+template <int TYPE>
+__device__ __forceinline__ MvRet run_matvec(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
+    const PhaseDesc &ph = smem().ph[pb];
+    const bool rows2 = ph.ksegs == 1 && ph.nb > 32 && ph.nb <= 64;
+    return rows2 ? matvec_phase<TYPE, true>(pb, cta, G, seq, act_in_smem, best)
+                 : matvec_phase<TYPE, false>(pb, cta, G, seq, act_in_smem, best);
+}
+
 // 13 warps: the register file is allocated in units of 4 warps, so the per-thread budget is 128.  With
 // 212 KB of the SM's 228 KB carved out as shared memory the L1 left for local memory is tiny and a spill
 // is an L2 round trip: the phase functions are kept out of line and templated so none of them spills.
@@ -841,6 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     const int token = min(max(P.state[0], 0), P.V - 1);
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
     const unsigned long long base = *P.bar_base;
+    unsigned long long *const bar_count = P.bar_count;
 
     if (warp == kConsumerWarps) {
         if (tid == kConsumerThreads) producer_loop<TYPE>(cta, G, n_pos);
@@ -872,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                 norm_prologue(pi & 1, token, write_x0, (ph.kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
             if (P.trace) tr1 = clock64();
             {
-                const MvRet r = matvec_phase<TYPE>(pi & 1, cta, G, seq, true, best);
+                const MvRet r = run_matvec<TYPE>(pi & 1, cta, G, seq, true, best);
                 seq = r.seq;
                 best = r.best;
             }
@@ -881,13 +903,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         case PH_GATE_UP: {
             if (first_unit(ph, cta, G) < ph.n_tiles) norm_prologue(pi & 1, token, false, nullptr);
             if (P.trace) tr1 = clock64();
-            seq = matvec_phase<TYPE>(pi & 1, cta, G, seq, true, best).seq;
+            seq = run_matvec<TYPE>(pi & 1, cta, G, seq, true, best).seq;
             break;
         }
         case PH_O:
         case PH_DOWN:
             {
-                const MvRet r = matvec_phase<TYPE>(pi & 1, cta, G, seq, false, best);
+                const MvRet r = run_matvec<TYPE>(pi & 1, cta, G, seq, false, best);
                 seq = r.seq;
                 best = r.best;
             }
@@ -945,7 +967,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         if (P.trace) tr2 = clock64();
         if (ph.kind != PH_SAMPLE) {
             bar_target += (unsigned long long)G;
-            grid_barrier(P, bar_target);
+            grid_barrier(bar_count, bar_target);
         }
         if (P.trace && tid == 0) {
             long long *t = P.trace + ((size_t)pi * G + cta) * 4;

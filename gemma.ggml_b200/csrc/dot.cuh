@@ -168,6 +168,51 @@ __device__ __forceinline__ float row_dot_lds(uint32_t pay, uint32_t scl, const A
     return warp_sum_f32(acc);
 }
 
+// The four block terms of one pass, with the four dp4a chains advanced in lock step: a warp issues in order
+// and the persistent kernel runs only 3 consumer warps per scheduler, so instruction-level parallelism inside
+// the warp is what hides the 5-cycle dp4a / 4-cycle ALU latencies.  Same per-block arithmetic as q4_term /
+// q8_term (integer dots are exact; the fp32 part is per block).
+// NA = number of distinct activation blocks held: 4 (slot t uses ab[t]) or 2 (two rows share the
+// same two blocks: slot t uses ab[t & 1]).
+template <int TYPE, int NA>
+__device__ __forceinline__ void pass_terms(const uint4 (&w0)[4], const uint4 (&w1)[4], const float (&dx)[4],
+                                           const ActBlock (&abx)[NA], float (&term)[4]) {
+    int sumi[4];
+#define ab(t) abx[NA == 4 ? (t) : ((t) & 1)]
+    if (TYPE == GGB_TYPE_Q4_0) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) sumi[t] = ab(t).bias;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t q[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) q[t] = i == 0 ? w0[t].x : (i == 1 ? w0[t].y : (i == 2 ? w0[t].z : w0[t].w));
+#pragma unroll
+            for (int t = 0; t < 4; t++) sumi[t] = __dp4a((int)(q[t] & 0x0F0F0F0Fu), ab(t).a[i], sumi[t]);
+#pragma unroll
+            for (int t = 0; t < 4; t++) sumi[t] = __dp4a((int)((q[t] >> 4) & 0x0F0F0F0Fu), ab(t).a[4 + i], sumi[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) term[t] = __fmul_rn(__fmul_rn((float)sumi[t], dx[t]), ab(t).d);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; t++) sumi[t] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const uint4 &v = i < 4 ? w0[t] : w1[t];
+                const int k = i & 3;
+                const uint32_t q = k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+                sumi[t] = __dp4a((int)q, ab(t).a[i], sumi[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 4; t++) term[t] = __fmul_rn((float)sumi[t], __fmul_rn(dx[t], ab(t).d));
+    }
+#undef ab
+}
+
 // shared-memory variant with a compile-time number of blocks per lane (BPL = ceil(segment blocks / 32)):
 // K = 2048 needs 2, so only 2 activation blocks occupy registers and no predicated dead work is issued.
 // `live[t]` masks the ragged tail (block index >= nb) and idle warps.
