@@ -87,6 +87,8 @@ _CUDA_SIG = {
     "ggb_op_mul_mat_q8": (i32, [vp, vp, i64, vp, i64, vp]),
     "ggb_op_mul_mat_q8_multi": (i32, [i32, P(vp), vp, P(vp)]),
     "ggb_op_ffn_gate_up": (i32, [vp, vp, vp, vp, vp]),
+    "ggb_op_ffn_gate_up_shard": (i32, [vp, vp, vp, vp, vp, vp]),
+    "ggb_op_argmax_shard": (i32, [vp, i64, i32, vp, vp]), "ggb_op_sample_from_candidates": (i32, [vp, i32, vp, vp]),
     "ggb_op_rms_norm": (i32, [vp, vp, f32, i64, i64, vp, vp]),
     "ggb_op_add": (i32, [vp, vp, i64, vp]), "ggb_op_mul": (i32, [vp, vp, i64, vp]),
     "ggb_op_scale": (i32, [vp, f32, i64, vp]), "ggb_op_gelu": (i32, [vp, i64, vp]),
@@ -108,7 +110,8 @@ _CUDA_SIG = {
 
 _HOST_SIG = {
     "gm_create": (vp, [P(Config)]), "gm_free": (None, [vp]),
-    "gm_init_synthetic_weights": (i32, [vp]), "gm_set_tensor": (i32, [vp, i32, vp, i64]),
+    "gm_init_synthetic_weights": (i32, [vp]), "gm_init_tensor_parallel": (i32, [vp, i32, i32]),
+    "gm_tp_plan": (i32, [P(Config), i32, i32, P(i64)]), "gm_set_tensor": (i32, [vp, i32, vp, i64]),
     "gm_init_kv_cache": (i32, [vp]), "gm_fill_kv_cache_synthetic": (i32, [vp, u64]),
     "gm_build_compute_graph": (i32, [vp, i32, i32]), "gm_decoder": (vp, [vp]), "gm_is_fused": (i32, [vp]), "gm_decode_step": (i32, [vp, i32, i32, P(i32)]),
     "gm_set_state": (i32, [vp, i32, i32, i32]), "gm_run_steps": (i32, [vp, i32]), "gm_run_steps_profiled": (i32, [vp, i32]),
@@ -288,6 +291,20 @@ def prof_reset():
     check(cuda_lib().ggb_prof_reset(), "ggb_prof_reset")
 
 
+TP_PLAN_FIELDS = ("valid", "head0", "heads", "kv_head0", "kv_heads", "kv_replicated", "q_row0", "q_rows", "k_row0",
+                  "k_rows", "o_row0", "o_rows", "gate_up_row0", "gate_up_rows", "down_row0", "down_rows", "logits_row0",
+                  "logits_rows")
+
+
+def tp_plan(cfg, rank, size):
+    """Host-only: the row ranges rank `rank` of `size` owns (host/gemma_model.cpp make_tp_plan); None if the
+    shape does not shard evenly."""
+    out = (i64 * 18)()
+    rc = host_lib().gm_tp_plan(C.byref(cfg), rank, size, out)
+    d = dict(zip(TP_PLAN_FIELDS, [int(v) for v in out]))
+    return d if rc == 0 else None
+
+
 def q8_row_bytes(cols):
     return int(cuda_lib().ggb_q8_row_bytes(cols))
 
@@ -340,6 +357,21 @@ class GemmaModel:
             self.close()
         except Exception:
             pass
+
+    def init_tensor_parallel(self, dist, rank, world):
+        """Row-sharded tensor parallelism over `world` ranks (one process per GPU).  `dist` is an initialised
+        torch.distributed module/backend used only to ship the 128-byte NCCL unique id from rank 0."""
+        import torch
+        L = cuda_lib()
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            check(L.ggb_comm_unique_id(_ptr(ident)), "ggb_comm_unique_id")
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(ident).to(dev)
+        dist.broadcast(t, src=0)
+        ident = t.cpu().numpy().copy()
+        check(L.ggb_comm_init(_ptr(ident), rank, world), "ggb_comm_init")
+        check(self.H.gm_init_tensor_parallel(self.h, rank, world), "gm_init_tensor_parallel")
 
     def init_synthetic_weights(self):
         check(self.H.gm_init_synthetic_weights(self.h), "gm_init_synthetic_weights")

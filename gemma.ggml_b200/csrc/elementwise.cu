@@ -290,6 +290,19 @@ argmax_stage2(const Cand *__restrict__ part, int n_part, int32_t *__restrict__ o
     }
 }
 
+// stage 2 for a row shard: publish (value, global index) so ranks can be compared after an allgather
+__global__ void __launch_bounds__(256)
+argmax_stage2_shard(const Cand *__restrict__ part, int n_part, int index_offset, Cand *__restrict__ out) {
+    __shared__ Cand s_c[8];
+    Cand c{-INFINITY, -1};
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) c = better(c, part[i]);
+    c = block_best(c, s_c);
+    if (threadIdx.x == 0) {
+        if (c.i >= 0) c.i += index_offset;
+        *out = c;
+    }
+}
+
 constexpr int kArgmaxParts = 296;
 
 inline unsigned blocks_for(int64_t n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
@@ -419,6 +432,24 @@ int ggb_op_sample_greedy(const float *logits, int64_t n, int32_t *state, int32_t
     argmax_stage1<<<kArgmaxParts, 256, 0, ggb_cuda_stream()>>>(logits, n, (Cand *)scratch);
     GGB_LAUNCH_CHECK();
     argmax_stage2<<<1, 256, 0, ggb_cuda_stream()>>>((const Cand *)scratch, kArgmaxParts, nullptr, state, history);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_argmax_shard(const float *x, int64_t n, int32_t index_offset, void *cand_out, void *scratch) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(x && cand_out && scratch && n > 0, "bad argmax_shard args");
+    argmax_stage1<<<kArgmaxParts, 256, 0, ggb_cuda_stream()>>>(x, n, (Cand *)scratch);
+    GGB_LAUNCH_CHECK();
+    argmax_stage2_shard<<<1, 256, 0, ggb_cuda_stream()>>>((const Cand *)scratch, kArgmaxParts, index_offset, (Cand *)cand_out);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_sample_from_candidates(const void *cands, int n_cands, int32_t *state, int32_t *history) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(cands && state && n_cands > 0, "bad sample_from_candidates args");
+    argmax_stage2<<<1, 256, 0, ggb_cuda_stream()>>>((const Cand *)cands, n_cands, nullptr, state, history);
     GGB_LAUNCH_CHECK();
     return GGB_OK;
 }

@@ -207,8 +207,14 @@ int ggb_op_mul_mat_q8_multi(int n, const ggb_weight *const *w, const void *q8, f
 }
 
 int ggb_op_ffn_gate_up(const ggb_weight *gate, const ggb_weight *up, const void *q8, void *q8_out, float *act_f32) {
+    GGB_CHECK_ARG(gate && q8_out, "null pointer");
+    return ggb_op_ffn_gate_up_shard(gate, up, q8, q8_out, (uint8_t *)q8_out + gate->rows, act_f32);
+}
+
+int ggb_op_ffn_gate_up_shard(const ggb_weight *gate, const ggb_weight *up, const void *q8, void *out_qs, void *out_d,
+                             float *act_f32) {
     GGB_REQUIRE_INIT();
-    GGB_CHECK_ARG(gate && up && q8 && q8_out, "null pointer");
+    GGB_CHECK_ARG(gate && up && q8 && out_qs && out_d, "null pointer");
     GGB_CHECK_ARG(gate->type == up->type && gate->rows == up->rows && gate->cols == up->cols, "gate/up mismatch");
     GGB_CHECK_ARG(gate->nb <= GGB_DEV_SEG_BLOCKS, "ffn_gate_up needs n_embd <= 4096 (got %lld)", (long long)gate->cols);
     GGB_CHECK_ARG(gate->rows % 32 == 0, "n_ff %lld not a multiple of 32", (long long)gate->rows);
@@ -217,8 +223,8 @@ int ggb_op_ffn_gate_up(const ggb_weight *gate, const ggb_weight *up, const void 
     a.nb = gate->nb; a.cols = gate->cols; a.rows = gate->rows;
     a.act = (const uint8_t *)q8;
     a.gelu_table = ggb_gelu_table_dev();
-    a.out_qs = (int8_t *)q8_out;
-    a.out_d = (__half *)((uint8_t *)q8_out + gate->rows);
+    a.out_qs = (int8_t *)out_qs;
+    a.out_d = (__half *)out_d;
     a.act_f32 = act_f32;
     const unsigned grid = (unsigned)(gate->rows / 32);
     if (gate->type == GGB_TYPE_Q4_0) gate_up_kernel<GGB_TYPE_Q4_0><<<grid, 256, 0, ggb_cuda_stream()>>>(a);

@@ -10,6 +10,17 @@ extern "C" {
 
 void *gm_create(const gemma_config *cfg) { return new gemma_model(*cfg); }
 void gm_free(void *m) { delete (gemma_model *)m; }
+int gm_init_tensor_parallel(void *m, int rank, int size) { return ((gemma_model *)m)->init_tensor_parallel(rank, size); }
+// host-only: fills out[18] = {valid, head0, heads, kv_head0, kv_heads, kv_replicated, q.row0, q.nrows, k.row0, k.nrows,
+// o.row0, o.nrows, gate_up.row0, gate_up.nrows, down.row0, down.nrows, logits.row0, logits.nrows}
+int gm_tp_plan(const gemma_config *cfg, int rank, int size, int64_t *out) {
+    const tp_plan p = make_tp_plan(*cfg, rank, size);
+    const int64_t v[18] = {p.valid, p.head0, p.heads, p.kv_head0, p.kv_heads, p.kv_replicated, p.q.row0, p.q.nrows,
+                           p.k.row0, p.k.nrows, p.o.row0, p.o.nrows, p.gate_up.row0, p.gate_up.nrows, p.down.row0,
+                           p.down.nrows, p.logits.row0, p.logits.nrows};
+    for (int i = 0; i < 18; i++) out[i] = v[i];
+    return p.valid ? 0 : -2;
+}
 int gm_init_synthetic_weights(void *m) { return ((gemma_model *)m)->init_synthetic_weights(); }
 int gm_set_tensor(void *m, int tensor_id, const void *host, int64_t nbytes) {
     return ((gemma_model *)m)->set_tensor(tensor_id, host, nbytes);

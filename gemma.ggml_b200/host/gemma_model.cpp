@@ -16,7 +16,63 @@
 
 static constexpr float kNormSigma = 0.02f; // norm weights: 1 + N(0, 0.02^2)
 
-gemma_model::gemma_model(const gemma_config &cfg) : cfg_(cfg) { layers_.resize((size_t)cfg.n_layer); }
+gemma_model::gemma_model(const gemma_config &cfg) : cfg_(cfg) {
+    layers_.resize((size_t)cfg.n_layer);
+    plan_ = make_tp_plan(cfg, 0, 1);
+}
+
+// ---------------------------------------------------------------- tensor-parallel plan (host logic only)
+tp_plan make_tp_plan(const gemma_config &c, int rank, int size) {
+    tp_plan p{};
+    p.rank = rank;
+    p.size = size;
+    const int64_t d = c.head_dim, E = c.n_embd, F = c.n_ff, V = c.n_vocab;
+    if (size < 1 || rank < 0 || rank >= size) return p;
+    if (c.n_head % size || E % size || V % size || F % (32 * size)) return p; // GeGLU+quantise works on 32-row blocks
+    p.kv_replicated = (c.n_head_kv % size) != 0;
+    if (p.kv_replicated && c.n_head_kv != 1) return p; // only MQA is replicated
+    p.heads = c.n_head / size;
+    p.head0 = rank * p.heads;
+    p.kv_heads = p.kv_replicated ? c.n_head_kv : c.n_head_kv / size;
+    p.kv_head0 = p.kv_replicated ? 0 : rank * p.kv_heads;
+    p.q = {p.head0 * d, p.heads * d};
+    p.k = {p.kv_head0 * d, p.kv_heads * d};
+    p.v = p.k;
+    p.o = {rank * (E / size), E / size};
+    p.gate_up = {rank * (F / size), F / size};
+    p.down = p.o;
+    p.logits = {rank * (V / size), V / size};
+    p.valid = 1;
+    return p;
+}
+
+int gemma_model::init_tensor_parallel(int rank, int size) {
+    if (token_embd_) return GGB_ERR_ARG; // must precede weight creation
+    const tp_plan p = make_tp_plan(cfg_, rank, size);
+    if (!p.valid) return GGB_ERR_ARG;
+    if (size > 1 && (ggb_comm_size() != size || ggb_comm_rank() != rank)) return GGB_ERR_ARG;
+    plan_ = p;
+    return 0;
+}
+
+int gemma_model::make_shards() {
+    if (plan_.size == 1) return 0;
+    auto sl = [&](const ggb_weight *w, const tp_range &r, ggb_weight **out) -> int {
+        ggb_weight_free(*out);
+        *out = nullptr;
+        return ggb_weight_slice(w, r.row0, r.nrows, out);
+    };
+    for (auto &l : layers_) {
+        GM_TRY(sl(l.attn_q, plan_.q, &l.sh_q));
+        GM_TRY(sl(l.attn_k, plan_.k, &l.sh_k));
+        GM_TRY(sl(l.attn_v, plan_.v, &l.sh_v));
+        GM_TRY(sl(l.attn_output, plan_.o, &l.sh_o));
+        GM_TRY(sl(l.ffn_gate, plan_.gate_up, &l.sh_gate));
+        GM_TRY(sl(l.ffn_up, plan_.gate_up, &l.sh_up));
+        GM_TRY(sl(l.ffn_down, plan_.down, &l.sh_down));
+    }
+    return sl(token_embd_, plan_.logits, &sh_logits_);
+}
 
 gemma_model::~gemma_model() { free_all(); }
 
@@ -28,15 +84,20 @@ void gemma_model::free_all() {
     decoder_ = nullptr;
     ggb_weight_free(token_embd_);
     token_embd_ = nullptr;
+    ggb_weight_free(sh_logits_);
+    sh_logits_ = nullptr;
     for (auto &l : layers_) {
-        ggb_weight *ws[] = {l.attn_q, l.attn_k, l.attn_v, l.attn_output, l.ffn_gate, l.ffn_up, l.ffn_down};
+        ggb_weight *ws[] = {l.sh_q, l.sh_k, l.sh_v, l.sh_o, l.sh_gate, l.sh_up, l.sh_down,
+                            l.attn_q, l.attn_k, l.attn_v, l.attn_output, l.ffn_gate, l.ffn_up, l.ffn_down};
         for (auto *w : ws) ggb_weight_free(w);
         if (l.attn_norm) ggb_buffer_free(l.attn_norm);
         if (l.ffn_norm) ggb_buffer_free(l.ffn_norm);
         l = gemma_layer();
     }
     void *bufs[] = {output_norm_, state_, history_, x0_, q_, k_, v_, logits_, result_norm_, sa_out_, l_out_, kqv_,
-                    ffn_act_, act_e_, act_q_, act_f_, attn_scratch_, sample_scratch_};
+                    ffn_act_, act_e_, act_q_, act_f_, attn_scratch_, sample_scratch_, kqv_local_, cand_};
+    kqv_local_ = nullptr;
+    cand_ = nullptr;
     for (void *b : bufs)
         if (b) ggb_buffer_free(b);
     output_norm_ = nullptr; state_ = history_ = nullptr; x0_ = q_ = k_ = v_ = logits_ = result_norm_ = nullptr;
@@ -128,7 +189,7 @@ int gemma_model::set_tensor(int tensor_id, const void *host_data, int64_t nbytes
 // ref: init_kv_cache (:361-401): per layer one F16 K and one F16 V tensor, zeroed.  Device layout is
 // position-major [n_ctx][n_head_kv*head_dim] for both (see csrc/attention.cu).
 int gemma_model::init_kv_cache() {
-    const size_t bytes = (size_t)cfg_.n_ctx * cfg_.n_head_kv * cfg_.head_dim * 2;
+    const size_t bytes = (size_t)cfg_.n_ctx * plan_.kv_heads * cfg_.head_dim * 2;
     for (int il = 0; il < cfg_.n_layer; il++) {
         void *k = nullptr, *v = nullptr;
         if ((int)k_cache_.size() <= il) {
@@ -145,7 +206,7 @@ int gemma_model::init_kv_cache() {
 }
 
 int gemma_model::fill_kv_cache_synthetic(uint64_t seed) {
-    const int64_t n = (int64_t)cfg_.n_ctx * cfg_.n_head_kv * cfg_.head_dim;
+    const int64_t n = (int64_t)cfg_.n_ctx * plan_.kv_heads * cfg_.head_dim;
     float *tmp = nullptr;
     GM_TRY(ggb_buffer_alloc((size_t)n * 4, (void **)&tmp));
     for (int il = 0; il < cfg_.n_layer; il++) {
@@ -181,6 +242,8 @@ int gemma_model::alloc_buffers() {
     GM_TRY(ggb_buffer_alloc(ggb_q8_row_bytes((int64_t)F), &act_f_));
     GM_TRY(ggb_buffer_alloc(ggb_attn_scratch_bytes(c.n_head, c.head_dim, c.n_ctx), &attn_scratch_));
     GM_TRY(ggb_buffer_alloc(ggb_sample_scratch_bytes((int64_t)V), &sample_scratch_));
+    GM_TRY(ggb_buffer_alloc(QD * 4, (void **)&kqv_local_));
+    GM_TRY(ggb_buffer_alloc(8 * (size_t)(plan_.size > 0 ? plan_.size : 1), &cand_));
     GM_TRY(ggb_buffer_memset(state_, 0, 16));
     GM_TRY(ggb_buffer_memset(history_, 0, ((size_t)c.n_ctx + 2) * 4));
     return ggb_sync();
@@ -231,12 +294,63 @@ int gemma_model::emit_decode_step() {
     return 0;
 }
 
+// The same token step, row-sharded over plan_.size ranks.  Every rank keeps the replicated
+// fp32 residual stream; each weight mat-vec computes this rank's rows only and the shards meet in four
+// allgathers per layer: attention output, o-proj (+residual), GeGLU activations (already Q8_0: int8 codes and
+// block scales are gathered, 4.25x fewer bytes than fp32), down-proj (+residual); plus 8 bytes per rank for the
+// arg-max.  Collectives are NCCL on the compute stream, captured in the same CUDA graph.
+int gemma_model::emit_decode_step_tp() {
+    const gemma_config &c = cfg_;
+    const tp_plan &p = plan_;
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab, d = c.head_dim;
+    const int64_t QD = (int64_t)c.n_head * d;
+    const float q_scale = 1.0f / sqrtf((float)d);
+    PROFILE("op_get_rows", ggb_op_embed_token(token_embd_, state_, sqrtf((float)c.n_embd), x0_));
+    const float *x_in = x0_;
+    uint8_t *actf = (uint8_t *)act_f_;
+    for (int il = 0; il < c.n_layer; il++) {
+        const gemma_layer &l = layers_[(size_t)il];
+        float *sa = sa_out_ + (size_t)il * E, *lo = l_out_ + (size_t)il * E, *kqv = kqv_ + (size_t)il * QD;
+        PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, l.attn_norm, c.eps, E, 1, nullptr, act_e_));
+        const ggb_weight *qkv[3] = {l.sh_q, l.sh_k, l.sh_v};
+        float *qkv_dst[3] = {q_, k_, v_};
+        PROFILE("op_mul_mat", ggb_op_mul_mat_q8_multi(3, qkv, act_e_, qkv_dst));
+        PROFILE("op_rope", ggb_op_rope_kv_store(q_, k_, v_, state_ + 1, p.heads, p.kv_heads, c.head_dim, q_scale,
+                                                k_cache_[(size_t)il], v_cache_[(size_t)il]));
+        PROFILE("op_attn", ggb_op_attn_decode(q_, k_cache_[(size_t)il], v_cache_[(size_t)il], state_ + 1, p.heads,
+                                              p.kv_heads, c.head_dim, c.n_ctx, attn_scratch_, kqv + p.q.row0, nullptr));
+        PROFILE("op_allgather", ggb_op_allgather(kqv + p.q.row0, kqv, (size_t)p.q.nrows * 4));
+        PROFILE("op_quantize", ggb_op_quantize_q8_0(kqv, QD, 1, act_q_));
+        PROFILE("op_mul_mat", ggb_op_mul_mat_q8(l.sh_o, act_q_, 1, sa + p.o.row0, E, x_in + p.o.row0));
+        PROFILE("op_allgather", ggb_op_allgather(sa + p.o.row0, sa, (size_t)p.o.nrows * 4));
+        PROFILE("op_rms_norm", ggb_op_rms_norm(sa, l.ffn_norm, c.eps, E, 1, nullptr, act_e_));
+        PROFILE("op_mul_mat", ggb_op_ffn_gate_up_shard(l.sh_gate, l.sh_up, act_e_, actf + p.gate_up.row0,
+                                                       actf + F + p.gate_up.row0 / 32 * 2,
+                                                       capture_acts_ ? ffn_act_ + (size_t)il * F + p.gate_up.row0 : nullptr));
+        PROFILE("op_allgather", ggb_op_allgather(actf + p.gate_up.row0, actf, (size_t)p.gate_up.nrows));
+        PROFILE("op_allgather", ggb_op_allgather(actf + F + p.gate_up.row0 / 32 * 2, actf + F, (size_t)p.gate_up.nrows / 32 * 2));
+        if (capture_acts_)
+            PROFILE("op_allgather", ggb_op_allgather(ffn_act_ + (size_t)il * F + p.gate_up.row0, ffn_act_ + (size_t)il * F,
+                                                     (size_t)p.gate_up.nrows * 4));
+        PROFILE("op_mul_mat", ggb_op_mul_mat_q8(l.sh_down, act_f_, 1, lo + p.down.row0, E, sa + p.down.row0));
+        PROFILE("op_allgather", ggb_op_allgather(lo + p.down.row0, lo, (size_t)p.down.nrows * 4));
+        x_in = lo;
+    }
+    PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, output_norm_, c.eps, E, 1, result_norm_, act_e_));
+    PROFILE("op_mul_mat", ggb_op_mul_mat_q8(sh_logits_, act_e_, 1, logits_ + p.logits.row0, V, nullptr));
+    PROFILE("op_argmax", ggb_op_argmax_shard(logits_ + p.logits.row0, p.logits.nrows, (int32_t)p.logits.row0,
+                                             (uint8_t *)cand_ + 8 * p.rank, sample_scratch_));
+    PROFILE("op_allgather", ggb_op_allgather((uint8_t *)cand_ + 8 * p.rank, cand_, 8));
+    PROFILE("op_argmax", ggb_op_sample_from_candidates(cand_, p.size, state_, history_));
+    return 0;
+}
+
 // eager (un-captured) steps with the cudaEvent probes live: per-op-class device time
 int gemma_model::run_steps_profiled(int steps) {
     if (!built_) return GGB_ERR_ARG;
     ggb_prof_enable(1);
     int rc = 0;
-    for (int i = 0; i < steps && !rc; i++) rc = emit_decode_step();
+    for (int i = 0; i < steps && !rc; i++) rc = plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step();
     ggb_sync();
     ggb_prof_enable(0);
     return rc;
@@ -256,6 +370,8 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
     decoder_ = nullptr;
     built_ = false;
     GM_TRY(ggb_sync());
+    GM_TRY(make_shards());
+    if (plan_.size > 1) fused = false; // the persistent kernel is single-GPU
     if (fused) {
         const gemma_config &c = cfg_;
         ggb_decoder_dims dims{c.n_embd, c.n_layer, c.n_head, c.n_head_kv, c.head_dim, c.n_ff, c.n_vocab, c.n_ctx, c.eps, 0};
@@ -274,7 +390,8 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
         }
     }
     if (ggb_capture_begin() == 0) {
-        const int rc = decoder_ ? ggb_decoder_step(decoder_) : emit_decode_step();
+        const int rc = decoder_ ? ggb_decoder_step(decoder_)
+                                : (plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step());
         ggb_graph *g = nullptr;
         const int rc2 = ggb_capture_end(&g);
         if (rc == 0 && rc2 == 0) {
@@ -359,7 +476,12 @@ int gemma_model::generate(const std::vector<token_id> &prompt, int n_decode, std
     return 0;
 }
 
-int gemma_model::get_logits(float *host) const { return ggb_download(host, logits_, (size_t)cfg_.n_vocab * 4); }
+int gemma_model::get_logits(float *host) const {
+    if (plan_.size > 1) { // the shards live at their own offsets of logits_: gather them (collective: every rank calls)
+        GM_TRY(ggb_op_allgather(logits_ + plan_.logits.row0, logits_, (size_t)plan_.logits.nrows * 4));
+    }
+    return ggb_download(host, logits_, (size_t)cfg_.n_vocab * 4);
+}
 
 // tensor_dump-style access to named intermediates of the last step (ref: src/tensor_dump.cpp:11-27)
 int gemma_model::get_capture(const std::string &name, int layer, float *host, int64_t n) const {
@@ -379,7 +501,7 @@ int gemma_model::get_capture(const std::string &name, int layer, float *host, in
 
 int gemma_model::get_kv(int layer, void *k_host, void *v_host) const {
     if (layer < 0 || layer >= (int)k_cache_.size()) return GGB_ERR_ARG;
-    const size_t bytes = (size_t)cfg_.n_ctx * cfg_.n_head_kv * cfg_.head_dim * 2;
+    const size_t bytes = (size_t)cfg_.n_ctx * plan_.kv_heads * cfg_.head_dim * 2;
     if (k_host) GM_TRY(ggb_download(k_host, k_cache_[(size_t)layer], bytes));
     if (v_host) GM_TRY(ggb_download(v_host, v_cache_[(size_t)layer], bytes));
     return 0;

@@ -35,13 +35,35 @@ struct gemma_layer { // ref: gemma_layer (src/gemma_model.h:42-50 region)
     float *attn_norm = nullptr, *ffn_norm = nullptr;
     ggb_weight *attn_q = nullptr, *attn_k = nullptr, *attn_v = nullptr, *attn_output = nullptr;
     ggb_weight *ffn_gate = nullptr, *ffn_up = nullptr, *ffn_down = nullptr;
+    // tensor-parallel row shards of the above (views, no copy); null when tp_size == 1
+    ggb_weight *sh_q = nullptr, *sh_k = nullptr, *sh_v = nullptr, *sh_o = nullptr;
+    ggb_weight *sh_gate = nullptr, *sh_up = nullptr, *sh_down = nullptr;
 };
+
+// Row-sharded tensor parallelism: every weight mat-vec is split by OUTPUT ROWS — the axis the
+// reference already splits between its CPU threads and the GPU (ref: src/hpc.cpp:245-269) — so each output
+// element is computed by exactly one rank in the same K-order and sharded results are bit-identical to
+// 1-GPU results.  Pure host logic, testable without a GPU.
+struct tp_range {
+    int64_t row0, nrows;
+};
+struct tp_plan {
+    int32_t rank, size, valid;
+    int32_t head0, heads;        // query heads owned
+    int32_t kv_head0, kv_heads;  // KV heads held in this rank's cache
+    int32_t kv_replicated;       // MQA (1 KV head): every rank keeps the whole (tiny) K/V projection and cache
+    tp_range q, k, v, o, gate_up, down, logits;
+};
+tp_plan make_tp_plan(const gemma_config &cfg, int rank, int size);
 
 class gemma_model {
   public:
     explicit gemma_model(const gemma_config &cfg);
     ~gemma_model();
 
+    // call before the weights exist; NCCL (ggb_comm_init) must already be up for size > 1
+    int init_tensor_parallel(int rank, int size);
+    const tp_plan &plan() const { return plan_; }
     // weights: synthetic (generated on the device) or uploaded tensor by tensor
     int init_synthetic_weights();
     int set_tensor(int tensor_id, const void *host_data, int64_t nbytes);
@@ -77,6 +99,8 @@ class gemma_model {
   private:
     int alloc_buffers();
     int emit_decode_step(); // the op sequence of one token
+    int emit_decode_step_tp(); // same, row-sharded over tp_size ranks with allgathers at the layer boundaries
+    int make_shards();
     int launch_step();      // graph replay, or a direct cooperative launch
     void free_all();
 
@@ -99,4 +123,8 @@ class gemma_model {
     ggb_graph *graph_ = nullptr;
     ggb_decoder *decoder_ = nullptr;
     bool built_ = false;
+    tp_plan plan_{};
+    ggb_weight *sh_logits_ = nullptr;
+    float *kqv_local_ = nullptr;
+    void *cand_ = nullptr; // [tp_size] (value, index) candidates of the sharded arg-max
 };

@@ -137,6 +137,11 @@ int ggb_op_mul_mat_q8_multi(int n, const ggb_weight *const *w, const void *q8, f
 int ggb_op_ffn_gate_up(const ggb_weight *gate, const ggb_weight *up, const void *q8, void *q8_out,
                        float *act_f32);
 
+/* row-shard form (tensor parallel): this rank's rows write their int8 codes to out_qs and their fp16 block
+ * scales to out_d — the caller passes pointers already offset into the gathered planar row */
+int ggb_op_ffn_gate_up_shard(const ggb_weight *gate, const ggb_weight *up, const void *q8, void *out_qs, void *out_d,
+                             float *act_f32);
+
 /* K5 — rms_norm (+ weight mul when w != NULL) over T rows of E floats; y and/or q8 may be NULL */
 int ggb_op_rms_norm(const float *x, const float *w, float eps, int64_t E, int64_t T, float *y, void *q8);
 /* element-wise nodes */
@@ -175,6 +180,10 @@ int ggb_op_embed_token(const ggb_weight *table, const int32_t *state, float scal
 /* state[0] <- argmax(logits), state[1] += state[2], history[state[1]] <- token (history may be NULL) */
 int ggb_op_sample_greedy(const float *logits, int64_t n, int32_t *state, int32_t *history, void *scratch);
 size_t ggb_sample_scratch_bytes(int64_t n);
+/* tensor-parallel greedy sampling: each rank publishes (fp32 value, int32 global index) of the first maximum of
+ * its logits shard (8 bytes), the candidates are allgathered, then the first maximum over ranks is taken */
+int ggb_op_argmax_shard(const float *x, int64_t n, int32_t index_offset, void *cand_out, void *scratch);
+int ggb_op_sample_from_candidates(const void *cands, int n_cands, int32_t *state, int32_t *history);
 
 /* ------------------------------------------------------------------ fused decode step
  * The whole per-token node list (ref: src/gemma_model.cpp:665-747) as ONE persistent cooperative
