@@ -27,11 +27,11 @@
 
 namespace {
 
-constexpr int kConsumerWarps = 12;
+constexpr int kConsumerWarps = 16;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;
-constexpr int kSlotBytes = 27648; // 24 rows of K=2048 Q4_0 (1152 B/row); 16 of K=3072; 3 of K=16384; 2 of K=24576
-constexpr int kSlots = 7;
+constexpr int kSlotBytes = 36864; // 32 rows of K=2048 Q4_0 (1152 B/row); 21 of K=3072; 4 of K=16384; 2 of K=24576
+constexpr int kSlots = 5;
 constexpr int kChunk = GGB_DEV_ATTN_CHUNK;
 constexpr int kMaxG = 8;
 constexpr int kMaxE = 4096; // n_embd limit of the fused path (one K segment for the norm-fed mat-vecs)
@@ -100,7 +100,7 @@ struct SmemLayout {
     float e[kMaxG][kChunk];
     alignas(16) __half knew[256];
     alignas(16) __half vnew[256];
-    float part[2][24][kConsumerWarps];
+    float part[2][2 * kConsumerWarps][kConsumerWarps];
     float stage_g[2][32], stage_u[2][32];
     double red[kConsumerWarps];
     float cand_v[kConsumerWarps];
@@ -396,21 +396,21 @@ __device__ __forceinline__ Best better(Best a, Best b) {
 // heavily unrolled functions per phase made the kernel instruction-fetch bound (a cold norm prologue took
 // ~4 us, the same code re-run hot 0.5 us).
 //
-// A warp always issues a "pass" of 4 block slots per lane.  With bpl = blocks per lane of one row segment
-// (K=2048 -> 2, a 128-block segment -> 4) a pass covers rp = 4/bpl rows (ksegs == 1) or one (row, segment)
-// unit (ksegs > 1); the per-row lane partial is still "blocks in order from 0.0f", then the xor-butterfly,
-// i.e. the DEV order.  Ring tiles are read with explicit ld.shared; the pass is branch-free.
+// K is cut into segments of 64 blocks (GGB_DEV_SEG_BLOCKS): lane l owns blocks l and l+32 of its warp's
+// segment, for EVERY row — 20 registers of activations, loaded once per phase.  A "pass" covers two rows of
+// that segment (4 block slots per lane): the four dp4a chains advance in lock step, the two lane partials
+// ("blocks in order from 0.0f") go through ONE folded xor-butterfly (lanes < 16 end with row 0's sum, lanes
+// >= 16 with row 1's; same additions as two separate butterflies), i.e. the DEV order.  With more than one
+// segment (K > 2048) the per-segment sums meet in shared memory and are added in segment order.
+// Ring tiles are read with explicit ld.shared; the pass is branch-free.
 // GATE_UP slots hold [gate payload][up payload][gate scales][up scales], i.e. they look like a 2R-row tile.
-// ROWS2 = the K <= 2048 shapes (bpl == 2, one segment): the two rows of a pass share the lane's two activation
-// blocks, so only 20 registers hold activations and the pass addresses collapse to (lane, +32 blocks, +1 row);
-// the freed registers let ptxas keep the four dp4a chains interleaved instead of serialising them.
-template <int TYPE, bool ROWS2>
+template <int TYPE>
 __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
     SmemLayout &S = smem();
     const DecoderParams &P = S.P;
     const PhaseDesc &ph = S.ph[pb];
     constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int kind = ph.kind, nb = ph.nb, ksegs = ph.ksegs, n_units = ph.n_tiles, rpt = ph.rows_per_tile;
     const bool gate_up = kind == PH_GATE_UP;
     const float *resid = ph.resid;
@@ -418,38 +418,39 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
     const int unit0 = first_unit(ph, cta, G);
     if (unit0 >= n_units) return MvRet{seq, best};
 
-    const int seg_blocks = nb < GGB_DEV_SEG_BLOCKS ? nb : GGB_DEV_SEG_BLOCKS;
-    const int bpl = (seg_blocks + 31) >> 5;              // 1..4
-    const int rp = ksegs > 1 ? 1 : (bpl == 1 ? 4 : (bpl == 2 ? 2 : 1)); // rows per pass
-    const int kseg = ksegs > 1 ? warp % ksegs : 0;
-    const int rsub = ksegs > 1 ? warp / ksegs : warp;    // this warp's row group within a round
-    const int groups = ksegs > 1 ? kConsumerWarps / ksegs : kConsumerWarps;
-    const bool warp_live = rsub < groups;
+    const int kseg = warp % ksegs, group = warp / ksegs; // this warp's segment and row-pair group
+    const int groups = kConsumerWarps / ksegs;
+    const bool warp_live = group < groups;
     const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
-
-    constexpr int NA = ROWS2 ? 2 : 4;
-    ActBlock ab[NA];
-    bool blk_live[4];
-    uint32_t off_pay[4], off_scl[4];
+    const int blk0 = kseg * GGB_DEV_SEG_BLOCKS + lane;
+    ActBlock ab[2];
+    bool blk_live[2];
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int rr = ROWS2 ? (t >> 1) : (bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0)); // row of the pass
-        const int bb = ROWS2 ? (t & 1) : (bpl == 1 ? 0 : (bpl == 2 ? (t & 1) : t));   // block slot within the row
-        const int blk = kseg * GGB_DEV_SEG_BLOCKS + lane + 32 * bb;
-        blk_live[t] = warp_live && rr < rp && bb < bpl && blk < nb;
-        if (!ROWS2 || t < 2) {
-            if (act_in_smem) load_act(ab[ROWS2 ? (t & 1) : t], S.act, ph.cols, blk, blk_live[t]);
-            else load_act_cg(ab[ROWS2 ? (t & 1) : t], ph.act_in, ph.cols, blk, blk_live[t]);
-        }
-        off_pay[t] = (uint32_t)rr * row_pb + (uint32_t)blk * PB;
-        off_scl[t] = (uint32_t)rr * row_sb + (uint32_t)blk * 2;
+    for (int b = 0; b < 2; b++) {
+        blk_live[b] = warp_live && blk0 + 32 * b < nb;
+        if (act_in_smem) load_act(ab[b], S.act, ph.cols, blk0 + 32 * b, blk_live[b]);
+        else load_act_cg(ab[b], ph.act_in, ph.cols, blk0 + 32 * b, blk_live[b]);
     }
     const uint32_t ring0 = smem_u32(&S.ring[0][0]);
+    const uint32_t lane_pay = (uint32_t)blk0 * PB, lane_scl = (uint32_t)blk0 * 2;
+    const int half = lane >> 4; // which row of a pass this lane publishes
     const int n_sub = gate_up ? (32 + rpt - 1) / rpt : 1;
     int pbuf = 0, sbuf = 0, ord = 0;
+
+    // hand one finished row (index r of the slot) to its consumer: residual add + store, or the GeGLU staging
+    auto publish = [&](int r, float v, float rv, int mat, int row0, int nrows) {
+        if (gate_up) {
+            if (r < nrows) S.stage_g[sbuf][row0 + r] = v;
+            else S.stage_u[sbuf][row0 + r - nrows] = v;
+        } else {
+            if (resid) v = __fadd_rn(v, rv);
+            ph.out[mat][row0 + r] = v;
+            if (kind == PH_LOGITS) best = better(best, Best{v, row0 + r});
+        }
+    };
+
     for (int u = unit0; u < n_units; u += G, ord++) {
         for (int sub = 0; sub < n_sub; sub++) {
-            // geometry of this slot
             int mat = 0, row0, nrows;
             if (gate_up) {
                 row0 = sub * rpt;
@@ -464,84 +465,48 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
             const int slot_rows = gate_up ? 2 * nrows : nrows;
             const int s = (int)(seq % kSlots);
             const uint32_t par = (seq / kSlots) & 1u;
-            const uint32_t pay0 = ring0 + (uint32_t)s * kSlotBytes;
-            const uint32_t scl0 = pay0 + (uint32_t)slot_rows * row_pb;
-            // epilogue lane j < rp publishes row (first row of this warp's pass) + j; its residual is requested
-            // before the tile is waited for
-            const int my_first = rsub * rp;
-            const int pstride = 32 / rp;
-            const bool own0 = ksegs == 1 ? ((lane % pstride) == 0 && my_first + lane / pstride < slot_rows)
-                                         : (warp == 0 && lane < nrows);
+            const uint32_t pay0 = ring0 + (uint32_t)s * kSlotBytes + lane_pay;
+            const uint32_t scl0 = ring0 + (uint32_t)s * kSlotBytes + (uint32_t)slot_rows * row_pb + lane_scl;
+            // residual of the row this lane will publish, requested before the tile is waited for
+            const int my_first = 2 * group;
+            const int my_row = ksegs == 1 ? my_first + half : tid; // ksegs > 1: thread t < slot_rows finishes row t
+            const bool my_pub = ksegs == 1 ? ((lane & 15) == 0 && my_row < slot_rows) : (tid < slot_rows);
             float rv = 0.0f;
-            if (own0 && resid) rv = __ldcg(resid + row0 + (ksegs == 1 ? my_first + lane / pstride : lane));
-            const bool dbg = P.trace2 && kind == PH_LOGITS && ord < 31 && threadIdx.x == 0;
+            if (my_pub && resid) rv = __ldcg(resid + row0 + my_row);
+            const bool dbg = P.trace2 && kind == PH_LOGITS && ord < 31 && tid == 0;
             if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 0] = clock64();
             mbar_wait(&S.full_bar[s], par);
             if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 1] = clock64();
-            for (int first = my_first; first < slot_rows; first += groups * rp) {
+#pragma unroll 1
+            for (int first = my_first; first < slot_rows; first += 2 * groups) {
                 uint4 w0[4], w1[4];
                 float dx[4];
                 const uint32_t pbase = pay0 + (uint32_t)first * row_pb, sbase = scl0 + (uint32_t)first * row_sb;
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    w0[t] = lds_u4(pbase + off_pay[t]);
-                    if (TYPE == GGB_TYPE_Q8_0) w1[t] = lds_u4(pbase + off_pay[t] + 16);
-                    dx[t] = lds_half_as_float(sbase + off_scl[t]);
+                    const uint32_t po = (uint32_t)(t >> 1) * row_pb + (uint32_t)(t & 1) * 32 * PB;
+                    w0[t] = lds_u4(pbase + po);
+                    if (TYPE == GGB_TYPE_Q8_0) w1[t] = lds_u4(pbase + po + 16);
+                    dx[t] = lds_half_as_float(sbase + (uint32_t)(t >> 1) * row_sb + (uint32_t)(t & 1) * 64);
                 }
                 float term[4];
-                pass_terms<TYPE, NA>(w0, w1, dx, ab, term);
-                // lane partial of each row of the pass: its blocks in order, from 0.0f (dead slots dropped by select)
-                float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                pass_terms<TYPE, 2>(w0, w1, dx, ab, term);
+                const bool row1 = first + 1 < slot_rows;
+                // lane partials: blocks in order from 0.0f, dead blocks dropped
+                float a0 = 0.0f, a1 = 0.0f;
+                a0 = blk_live[0] ? __fadd_rn(a0, term[0]) : a0;
+                a0 = blk_live[1] ? __fadd_rn(a0, term[1]) : a0;
+                a1 = (blk_live[0] && row1) ? __fadd_rn(a1, term[2]) : a1;
+                a1 = (blk_live[1] && row1) ? __fadd_rn(a1, term[3]) : a1;
+                // folded xor-butterfly 16,8,4,2,1
+                const float send = half ? a0 : a1;
+                float keep = __fadd_rn(half ? a1 : a0, __shfl_xor_sync(0xffffffffu, send, 16));
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const int rr = ROWS2 ? (t >> 1) : (bpl == 1 ? t : (bpl == 2 ? (t >> 1) : 0));
-                    const bool on = blk_live[t] && first + rr < slot_rows;
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const float nx = __fadd_rn(acc[r], term[t]);
-                        acc[r] = (on && rr == r) ? nx : acc[r];
-                    }
-                }
-                // xor-butterfly 16,8,4,2,1 per row (DEV order).  rp == 2 (the K=2048 shapes) folds both rows into
-                // one butterfly: at offset 16 lanes < 16 keep row 0 and receive its upper half, lanes >= 16 keep
-                // row 1 — the same pairs are added as in two separate butterflies, with half the shuffles.
-                // No shuffle sits under a data-dependent predicate (that costs a divergence check each).
-                float mine;
-                if (rp == 2) {
-                    const bool lo = lane < 16;
-                    const float send = lo ? acc[1] : acc[0];
-                    float keep = __fadd_rn(lo ? acc[0] : acc[1], __shfl_xor_sync(0xffffffffu, send, 16));
-#pragma unroll
-                    for (int off = 8; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
-                    mine = keep; // lanes 0..15: row 0 total, lanes 16..31: row 1 total
-                } else if (rp == 1) {
-                    acc[0] = warp_sum_f32(acc[0]);
-                    mine = acc[0];
-                } else {
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                        for (int r = 0; r < 4; r++) acc[r] = __fadd_rn(acc[r], __shfl_xor_sync(0xffffffffu, acc[r], off));
-                    }
-                    mine = lane < 8 ? acc[0] : (lane < 16 ? acc[1] : (lane < 24 ? acc[2] : acc[3]));
-                }
-                // row j of the pass is published by lane j * (32 / rp)
-                const int pub_stride = 32 / rp;
-                const int jrow = lane / pub_stride;
-                const bool pub = (lane % pub_stride) == 0 && first + jrow < slot_rows;
-                if (ksegs > 1) {
-                    if (lane == 0 && warp_live) S.part[pbuf][first][kseg] = mine;
-                } else if (pub) {
-                    const int r = first + jrow;
-                    if (gate_up) {
-                        if (r < nrows) S.stage_g[sbuf][row0 + r] = mine;
-                        else S.stage_u[sbuf][row0 + r - nrows] = mine;
-                    } else {
-                        float v = mine;
-                        if (resid) v = __fadd_rn(v, first == my_first ? rv : __ldcg(resid + row0 + r));
-                        ph.out[mat][row0 + r] = v;
-                        if (kind == PH_LOGITS) best = better(best, Best{v, row0 + r});
-                    }
+                for (int off = 8; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
+                const int r = first + half;
+                if ((lane & 15) == 0 && r < slot_rows && warp_live) {
+                    if (ksegs > 1) S.part[pbuf][r][kseg] = keep;
+                    else publish(r, keep, first == my_first ? rv : (resid ? __ldcg(resid + row0 + r) : 0.0f), mat, row0, nrows);
                 }
             }
             __syncwarp();
@@ -549,12 +514,10 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
             if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 2] = clock64();
             if (ksegs > 1) {
                 consumer_bar();
-                if (warp == 0 && lane < nrows) { // lane r: segment totals of row r added in segment order
-                    float total = S.part[pbuf][lane][0];
-                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][lane][k]);
-                    if (resid) total = __fadd_rn(total, rv);
-                    ph.out[mat][row0 + lane] = total;
-                    if (kind == PH_LOGITS) best = better(best, Best{total, row0 + lane});
+                if (tid < slot_rows) { // thread r: segment sums of row r added in segment order
+                    float total = S.part[pbuf][tid][0];
+                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][tid][k]);
+                    publish(tid, total, rv, mat, row0, nrows);
                 }
                 pbuf ^= 1;
             }
@@ -827,13 +790,10 @@ __device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
 
 template <int TYPE>
 __device__ __forceinline__ MvRet run_matvec(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
-    const PhaseDesc &ph = smem().ph[pb];
-    const bool rows2 = ph.ksegs == 1 && ph.nb > 32 && ph.nb <= 64;
-    return rows2 ? matvec_phase<TYPE, true>(pb, cta, G, seq, act_in_smem, best)
-                 : matvec_phase<TYPE, false>(pb, cta, G, seq, act_in_smem, best);
+    return matvec_phase<TYPE>(pb, cta, G, seq, act_in_smem, best);
 }
 
-// 13 warps: the register file is allocated in units of 4 warps, so the per-thread budget is 128.  With
+// 17 warps: the register file is allocated in units of 4 warps (20 here), so the per-thread budget is 96.  With
 // 212 KB of the SM's 228 KB carved out as shared memory the L1 left for local memory is tiny and a spill
 // is an L2 round trip: the phase functions are kept out of line and templated so none of them spills.
 template <int TYPE>
@@ -1058,7 +1018,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         ph.ksegs = (ph.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS;
         int r = fit_rows(ph.nb, 1);
         const int rpr = kConsumerWarps / ph.ksegs > 0 ? kConsumerWarps / ph.ksegs : 1;
-        if (r > 24) r = 24;
+        if (r > 2 * kConsumerWarps) r = 2 * kConsumerWarps;
         if (r >= rpr) r = r / rpr * rpr; // whole rounds of the consumer warps
         ph.rows_per_tile = r;
         ph.n_tiles = 0;
@@ -1081,7 +1041,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
             float *o[3] = {P.q, P.k, P.v};
             PhaseDesc ph = matvec_desc(PH_QKV, il, 3, w, o);
             ph.x_in = x_in; ph.norm_w = ly.attn_norm;
-            ok = ok && ph.rows_per_tile > 0 && ph.ksegs == 1;
+            ok = ok && ph.rows_per_tile > 0 && ph.ksegs <= kConsumerWarps;
             D->phases.push_back(ph);
         }
         {   // ATTN
@@ -1105,17 +1065,18 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         {   // GATE_UP
             PhaseDesc ph{};
             ph.kind = PH_GATE_UP; ph.layer = il; ph.n_mats = 2;
-            ph.nb = (int)ly.ffn_gate->nb; ph.cols = (int)ly.ffn_gate->cols; ph.ksegs = 1;
+            ph.nb = (int)ly.ffn_gate->nb; ph.cols = (int)ly.ffn_gate->cols;
+            ph.ksegs = (ph.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS;
             ph.m[0].qs = ly.ffn_gate->qs; ph.m[0].d = ly.ffn_gate->d; ph.m[0].rows = F;
             ph.m[1].qs = ly.ffn_up->qs; ph.m[1].d = ly.ffn_up->d; ph.m[1].rows = F;
             int r = fit_rows(ph.nb, 2);
             if (r > kConsumerWarps) r = kConsumerWarps;
-            if (r > 8 && r < 12) r = 8;
+            if (r > 8 && r < kConsumerWarps) r = 8;
             ph.rows_per_tile = r;
             ph.n_tiles = F / 32;
             ph.x_in = sa; ph.norm_w = ly.ffn_norm; ph.act_out = act_f;
             ph.f32_out = io->ffn_act ? io->ffn_act + (size_t)il * F : nullptr;
-            ok = ok && r > 0 && ph.nb <= GGB_DEV_SEG_BLOCKS;
+            ok = ok && r > 0 && ph.ksegs <= kConsumerWarps;
             D->phases.push_back(ph);
         }
         {   // DOWN + residual
@@ -1132,7 +1093,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         float *o[1] = {io->logits};
         PhaseDesc ph = matvec_desc(PH_LOGITS, L, 1, w, o);
         ph.x_in = io->l_out + (size_t)(L - 1) * E; ph.norm_w = output_norm; ph.f32_out = io->result_norm;
-        ok = ok && ph.rows_per_tile > 0 && ph.ksegs == 1;
+        ok = ok && ph.rows_per_tile > 0 && ph.ksegs <= kConsumerWarps;
         D->phases.push_back(ph);
         PhaseDesc sp{};
         sp.kind = PH_SAMPLE; sp.layer = L;

@@ -8,7 +8,7 @@
 
 #include "common.cuh"
 
-constexpr int kTPB = GGB_DEV_SEG_BLOCKS / 32; // blocks per lane per 128-block segment = 4
+constexpr int kTPB = GGB_DEV_SEG_BLOCKS / 32; // blocks per lane per 64-block segment = 2
 
 // activation block held by a lane
 struct ActBlock {

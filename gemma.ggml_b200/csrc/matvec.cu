@@ -2,8 +2,8 @@
 // of the reference (ref: src/hpc.cpp:15-41 mul_mat_sub -> vec_dot, 99.98 % of mul_mat time,
 // notes.md:87).  Not a port of src/kernals.cl (one work-item per output, serial K loop):
 //
-//   * a warp owns a row (or, for K > 4096, one 128-block segment of a row); lane l owns blocks
-//     l, l+32, l+64, l+96 of the segment, so the activation blocks a lane needs never change
+//   * a warp owns a row (or, for K > 2048, one 64-block segment of a row); lane l owns blocks
+//     l, l+32 of the segment, so the activation blocks a lane needs never change
 //     from row to row and live in REGISTERS for the whole kernel;
 //   * weight payloads stream with one coalesced 128-bit load per lane per block (SoA planes,
 //     L1 no-allocate), nibbles are unpacked in registers and dotted with dp4a; the "-8" of
@@ -114,28 +114,39 @@ __global__ void __launch_bounds__(256) gate_up_kernel(const GateUpArgs a) {
     __shared__ float s_g[32], s_u[32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    ActBlock ab[kTPB];
-    bool valid[kTPB];
-#pragma unroll
-    for (int t = 0; t < kTPB; t++) {
-        valid[t] = lane + 32 * t < a.nb;
-        load_act(ab[t], a.act, a.cols, lane + 32 * t, valid[t]);
-    }
     const int64_t tile_row0 = (int64_t)blockIdx.x * 32;
+    const int ksegs = (int)((a.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS);
+    float g[4], u[4];
+    // segments in order (DEV): the lane's activation blocks are reloaded per segment
+    for (int seg = 0; seg < ksegs; seg++) {
+        ActBlock ab[kTPB];
+        bool valid[kTPB];
+        const int64_t b0 = (int64_t)seg * GGB_DEV_SEG_BLOCKS + lane;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int64_t r = tile_row0 + warp * 4 + i;
-        const float g = segment_dot<TYPE>(a.gate_qs, a.gate_d, r, a.nb, lane, ab, valid);
-        const float u = segment_dot<TYPE>(a.up_qs, a.up_d, r, a.nb, lane, ab, valid);
-        if (lane == 0) {
-            s_g[warp * 4 + i] = g;
-            s_u[warp * 4 + i] = u;
+        for (int t = 0; t < kTPB; t++) {
+            valid[t] = b0 + 32 * t < a.nb;
+            load_act(ab[t], a.act, a.cols, b0 + 32 * t, valid[t]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t r = tile_row0 + warp * 4 + i;
+            const float gs = segment_dot<TYPE>(a.gate_qs, a.gate_d, r, a.nb, b0, ab, valid);
+            const float us = segment_dot<TYPE>(a.up_qs, a.up_d, r, a.nb, b0, ab, valid);
+            g[i] = seg == 0 ? gs : __fadd_rn(g[i], gs);
+            u[i] = seg == 0 ? us : __fadd_rn(u[i], us);
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            s_g[warp * 4 + i] = g[i];
+            s_u[warp * 4 + i] = u[i];
         }
     }
     __syncthreads();
     if (warp == 0) {
-        const float g = s_g[lane];
-        const float gl = half_bits_to_float(a.gelu_table[float_to_half_bits(g)]);
+        const float gv = s_g[lane];
+        const float gl = half_bits_to_float(a.gelu_table[float_to_half_bits(gv)]);
         const float x = __fmul_rn(gl, s_u[lane]);
         if (a.act_f32) a.act_f32[tile_row0 + lane] = x;
         float d;
@@ -169,7 +180,7 @@ int launch_matvec(int n, const ggb_weight *const *w, const void *q8, int64_t T, 
     a.act_stride = (int64_t)ggb_q8_row_bytes(a.cols);
     a.dst_stride = dst_stride;
     a.ksegs = (int)((a.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS);
-    GGB_CHECK_ARG(a.ksegs <= 12, "K = %lld too large for one CTA (max 49152)", (long long)a.cols);
+    GGB_CHECK_ARG(a.ksegs <= 12, "K = %lld too large for one CTA (max 24576)", (long long)a.cols);
     a.rows_per_iter = a.ksegs >= 8 ? 1 : 8 / a.ksegs;
     const int warps = a.rows_per_iter * a.ksegs;
     const int64_t target_ctas = (int64_t)ggb_sm_count() * 8;
@@ -216,7 +227,6 @@ int ggb_op_ffn_gate_up_shard(const ggb_weight *gate, const ggb_weight *up, const
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(gate && up && q8 && out_qs && out_d, "null pointer");
     GGB_CHECK_ARG(gate->type == up->type && gate->rows == up->rows && gate->cols == up->cols, "gate/up mismatch");
-    GGB_CHECK_ARG(gate->nb <= GGB_DEV_SEG_BLOCKS, "ffn_gate_up needs n_embd <= 4096 (got %lld)", (long long)gate->cols);
     GGB_CHECK_ARG(gate->rows % 32 == 0, "n_ff %lld not a multiple of 32", (long long)gate->rows);
     GateUpArgs a{};
     a.gate_qs = gate->qs; a.up_qs = up->qs; a.gate_d = gate->d; a.up_d = up->d;

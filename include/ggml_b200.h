@@ -38,7 +38,7 @@ enum { GGB_TYPE_F32 = 0, GGB_TYPE_F16 = 1, GGB_TYPE_Q4_0 = 2, GGB_TYPE_Q8_0 = 8 
  * mat-vec: K cut into segments of GGB_DEV_SEG_BLOCKS blocks, 32 lane-strided partials per
  * segment, xor-butterfly, segments added in order.  rms_norm: GGB_DEV_NORM_THREADS strided
  * double partials.  attention: split-K chunks of GGB_DEV_ATTN_CHUNK positions. */
-#define GGB_DEV_SEG_BLOCKS 128
+#define GGB_DEV_SEG_BLOCKS 64
 #define GGB_DEV_NORM_THREADS 256
 #define GGB_DEV_ATTN_CHUNK 32
 

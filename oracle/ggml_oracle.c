@@ -233,8 +233,8 @@ static double butterfly32d(double lane[32]) {
 }
 
 /* DEV order of the sm_100a mat-vec kernels (gemma.ggml_b200/csrc/matvec.cuh): same per-block
- * terms as the scalar loops, summed as: segments of 128 blocks; lane l of a warp sums blocks
- * seg+l, seg+l+32, seg+l+64, seg+l+96 (those < nb) sequentially from 0.0f; xor-butterfly;
+ * terms as the scalar loops, summed as: segments of 64 blocks; lane l of a warp sums blocks
+ * seg+l, seg+l+32 (those < nb) sequentially from 0.0f; xor-butterfly;
  * segment totals added in order. */
 #define ORC_DEV_DOT(NAME, XT, TERM)                                                         \
     void NAME(int n, float *s, const void *vx, const void *vy) {                           \

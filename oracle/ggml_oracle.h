@@ -46,7 +46,7 @@ typedef struct { uint16_t d; int8_t qs[ORC_QK]; } orc_block_q8_0;      /* 34 B *
 #pragma pack(pop)
 
 /* DEV-order parameters (must match include/ggml_b200.h GGB_DEV_*) */
-#define ORC_DEV_SEG_BLOCKS 128 /* mat-vec: K is cut into segments of 128 blocks */
+#define ORC_DEV_SEG_BLOCKS 64 /* mat-vec: K is cut into segments of 64 blocks (2048 elements) */
 #define ORC_DEV_NORM_THREADS 256 /* rms_norm: 256 strided partials */
 #define ORC_DEV_ATTN_CHUNK 32 /* attention: positions per split-K chunk */
 
@@ -66,8 +66,8 @@ void orc_dequantize_row(int type, const void *x, float *y, int64_t k);
 /* REF: scalar ggml order (blocks in order, one fp32 accumulator). */
 void orc_vec_dot_q4_0_q8_0(int n, float *s, const void *vx, const void *vy);
 void orc_vec_dot_q8_0_q8_0(int n, float *s, const void *vx, const void *vy);
-/* DEV: segments of 128 blocks; inside a segment 32 lane partials (lane l sums
- * blocks l, l+32, l+64, l+96 in that order from 0.0f), xor-butterfly 16,8,4,2,1,
+/* DEV: segments of 64 blocks; inside a segment 32 lane partials (lane l sums
+ * blocks l, l+32 in that order from 0.0f), xor-butterfly 16,8,4,2,1,
  * segment sums added in segment order. */
 void orc_vec_dot_q4_0_q8_0_dev(int n, float *s, const void *vx, const void *vy);
 void orc_vec_dot_q8_0_q8_0_dev(int n, float *s, const void *vx, const void *vy);
