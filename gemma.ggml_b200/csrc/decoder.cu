@@ -196,7 +196,8 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *bar_count, unsi
         do {
             asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar_count) : "memory");
         } while (v < target);
-        (void)ld_acquire_u64(bar_count);
+        // no acquire needed here: every read of another CTA's data after a barrier is an L2 access
+        // (__ldcg / cp.async.cg / TMA), never an L1-cached load, and the writers released at gpu scope
     }
     consumer_bar();
 }
@@ -436,6 +437,8 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
     const int half = lane >> 4; // which row of a pass this lane publishes
     const int n_sub = gate_up ? (32 + rpt - 1) / rpt : 1;
     int pbuf = 0, sbuf = 0, ord = 0;
+    int slot = (int)(seq % kSlots);
+    uint32_t parity = (seq / kSlots) & 1u;
 
     // hand one finished row (index r of the slot) to its consumer: residual add + store, or the GeGLU staging
     auto publish = [&](int r, float v, float rv, int mat, int row0, int nrows) {
@@ -463,8 +466,8 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
                 mat = ti.mat; row0 = ti.row0; nrows = ti.nrows;
             }
             const int slot_rows = gate_up ? 2 * nrows : nrows;
-            const int s = (int)(seq % kSlots);
-            const uint32_t par = (seq / kSlots) & 1u;
+            const int s = slot;
+            const uint32_t par = parity;
             const uint32_t pay0 = ring0 + (uint32_t)s * kSlotBytes + lane_pay;
             const uint32_t scl0 = ring0 + (uint32_t)s * kSlotBytes + (uint32_t)slot_rows * row_pb + lane_scl;
             // residual of the row this lane will publish, requested before the tile is waited for
@@ -522,6 +525,10 @@ __device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq,
                 pbuf ^= 1;
             }
             seq++;
+            if (++slot == kSlots) {
+                slot = 0;
+                parity ^= 1u;
+            }
         }
         if (gate_up) { // GeGLU (fp16 gelu table) + quantize_row_q8_0 of the super-tile's 32 products, lane-parallel
             consumer_bar();
@@ -630,6 +637,7 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
 #pragma unroll
                     for (int e = 0; e < 8; e++) kf[e] = 0.f;
                 }
+                // (fp16 x fp16 products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once: same bits)
                 // heads in groups of 4: lane partials first, then the group's butterflies interleaved (ILP
                 // without unrolling all 8 heads: code size matters here); each sum follows the DEV order
 #pragma unroll 1
@@ -641,14 +649,14 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
                         if (j0 + u < Gq && 8 * lane < d) {
                             const float4 qa = *reinterpret_cast<const float4 *>(&Sq[j0 + u][8 * lane]);
                             const float4 qb = *reinterpret_cast<const float4 *>(&Sq[j0 + u][8 * lane + 4]);
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[0], qa.x));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[1], qa.y));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[2], qa.z));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[3], qa.w));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[4], qb.x));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[5], qb.y));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[6], qb.z));
-                            acc[u] = __fadd_rn(acc[u], __fmul_rn(kf[7], qb.w));
+                            acc[u] = __fmaf_rn(kf[0], qa.x, acc[u]);
+                            acc[u] = __fmaf_rn(kf[1], qa.y, acc[u]);
+                            acc[u] = __fmaf_rn(kf[2], qa.z, acc[u]);
+                            acc[u] = __fmaf_rn(kf[3], qa.w, acc[u]);
+                            acc[u] = __fmaf_rn(kf[4], qb.x, acc[u]);
+                            acc[u] = __fmaf_rn(kf[5], qb.y, acc[u]);
+                            acc[u] = __fmaf_rn(kf[6], qb.z, acc[u]);
+                            acc[u] = __fmaf_rn(kf[7], qb.w, acc[u]);
                         }
                     }
 #pragma unroll
@@ -686,28 +694,30 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
             const int s = rp.slot();
             mbar_wait(&S.full_bar[s], rp.parity());
             const __half *vchunk = reinterpret_cast<const __half *>(S.ring[s]);
+            // 4 thread groups of 128: group hs takes heads hs, hs+4; thread -> one pair of dims
+            constexpr int kHG = kConsumerThreads / 128; // 4
             const int dp = tid % 128, hs = tid / 128;
-            if (tid < 256 && dp < halfd) {
-                float a0[kMaxG / 2], a1[kMaxG / 2];
+            if (dp < halfd) {
+                float a0[kMaxG / kHG], a1[kMaxG / kHG];
 #pragma unroll
-                for (int u = 0; u < kMaxG / 2; u++) a0[u] = a1[u] = 0.0f;
+                for (int u = 0; u < kMaxG / kHG; u++) a0[u] = a1[u] = 0.0f;
 #pragma unroll 2
                 for (int j = 0; j < np; j++) {
                     const __half *vrow = (owns_new && p0 + j == pos) ? S.vnew : vchunk + (size_t)j * d;
                     const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(vrow + 2 * dp));
 #pragma unroll
-                    for (int u = 0; u < kMaxG / 2; u++) {
-                        const int jh = 2 * u + hs;
-                        if (jh < Gq) {
+                    for (int u = 0; u < kMaxG / kHG; u++) {
+                        const int jh = kHG * u + hs;
+                        if (jh < Gq) { // e is an fp16 value: e*v is exact, fmaf == mul + add
                             const float e = S.e[jh][j];
-                            a0[u] = __fadd_rn(a0[u], __fmul_rn(e, vf.x));
-                            a1[u] = __fadd_rn(a1[u], __fmul_rn(e, vf.y));
+                            a0[u] = __fmaf_rn(e, vf.x, a0[u]);
+                            a1[u] = __fmaf_rn(e, vf.y, a1[u]);
                         }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < kMaxG / 2; u++) {
-                    const int jh = 2 * u + hs;
+                for (int u = 0; u < kMaxG / kHG; u++) {
+                    const int jh = kHG * u + hs;
                     if (jh < Gq) {
                         float *out = P.attn_acc + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
                         *reinterpret_cast<float2 *>(out) = make_float2(a0[u], a1[u]);
