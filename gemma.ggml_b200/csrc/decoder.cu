@@ -1,84 +1,92 @@
-// decoder.cu — the persistent decode kernel: ONE cooperative launch per token.
+// decoder.cu — the persistent decode kernel: ONE cooperative launch per token (v2: pass-stream design).
 //
-// Why: a Gemma-2B Q4_0 token is 1.41 GB of weights + 38 MB of KV = ~220 us of HBM time on a B200,
-// spread over 163 mat-vecs and ~450 small nodes (ref: src/gemma_model.cpp:688-740).  Launched as
-// separate kernels the HBM pipe drains and refills ~170 times per token and the step takes 1.6 ms.
-// Here one CTA per SM stays resident for the whole token:
+// Why: a Gemma-2B Q4_0 token is 1.41 GB of weights + 38 MB of KV = ~220 us of HBM time on a B200, spread
+// over 163 mat-vecs and ~450 small nodes (ref: src/gemma_model.cpp:688-740).  One CTA per SM stays resident
+// for the whole token; what limits it is (a) how cleanly the weights stream and (b) what every phase change
+// costs.  Design rules, each measured (tools/ubench_stream.cu, tools_trace.py):
 //
-//   * warp 12 lane 0 is the PRODUCER: it walks the static per-CTA tile schedule of the whole token
-//     and streams every weight tile (and KV chunk) into a 7 x 27 KiB shared-memory ring with
-//     cp.async.bulk (TMA, SASS UBLKCP) completing on mbarriers.  Weights do not depend on
-//     activations, so the producer runs AHEAD across phase boundaries: while the consumers sit in a
-//     grid barrier or a norm prologue, HBM keeps streaming the next phase's tiles.
-//   * warps 0-11 are CONSUMERS: per phase they build their activation registers (rms_norm + Q8_0
-//     quantisation is recomputed by every CTA, 8 KB from L2, instead of being a phase of its own),
-//     then dot ring tiles exactly like matvec.cu (same lane->block map, same DEV summation order).
+//   * PASS STREAM.  At create time every weight matrix is re-laid out as a stream of PASSES: one pass =
+//     two rows x one 64-block K segment (2304 B Q4_0 / 4352 B Q8_0), payloads then scales, i.e. exactly what
+//     one consumer warp dots in one go.  A phase's passes are contiguous in HBM in schedule order, so a CTA's
+//     share of a phase is ONE contiguous byte range and the producer is a trivial loop of bulk copies.
+//   * PRODUCER = lane 0 of warp 16: cp.async.bulk (TMA, SASS UBLKCP) of up to 16 passes (36 KB) per ring slot,
+//     5 slots, completion on mbarriers.  Weights do not depend on activations, so it runs AHEAD across phase
+//     boundaries: while consumers sit in a grid barrier or a prologue, HBM keeps streaming.
+//   * CONSUMERS = 16 warps.  Warp w owns pass w of every slot: 4 x LDS.128 weights + the two activation
+//     blocks of its segment from shared memory, dp4a, the scalar reference's per-block fp32 term, a folded
+//     xor-butterfly for the two rows.  Segment sums go to a shared-memory partial table; ONE block barrier per
+//     phase, then an epilogue finishes rows (segments in order, residual, GeGLU + Q8_0, arg-max).
+//     The stand-alone loop sustains 6.0-6.2 TB/s of 6.6 TB/s read peak (tools/ubench_stream.cu).
+//   * SMALL CODE.  The 32 KB instruction cache holds ~2000 SASS instructions and a persistent kernel runs
+//     each phase's code once per layer: every mat-vec phase shares one pass loop, prologues and epilogues are
+//     short and not unrolled.
 //   * phases are separated by a grid barrier (monotonic 64-bit counter in global memory).
 //
-// Phases per layer: QKV | ATTN (split-K partials; rope, Q scale and the KV-cache store of the new
-// position are folded in) | COMBINE (+ Q8_0 quantise) | O (+ residual) | GATE_UP (+ GeGLU + quantise)
-// | DOWN (+ residual); then LOGITS (+ per-CTA argmax) | SAMPLE.
-// Numerics are bit-identical to the per-operator kernels (same DEV order; tests compare both).
-#include <cooperative_groups.h>
-
+// Phases per layer: QKV | ATTN (split-K partials; rope, Q scale and the KV-cache store of the new position
+// folded in) | COMBINE (+ Q8_0 quantise) | O (+ residual) | GATE_UP (+ GeGLU + quantise) | DOWN (+ residual);
+// then LOGITS (+ per-CTA arg-max) | SAMPLE.
+// Numerics are bit-identical to the per-operator kernels (same DEV order; tests compare both and the oracle).
 #include <vector>
 
-#include "dot.cuh"
+#include "common.cuh"
 
 namespace {
 
-constexpr int kConsumerWarps = 16;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;
-constexpr int kSlotBytes = 36864; // 32 rows of K=2048 Q4_0 (1152 B/row); 21 of K=3072; 4 of K=16384; 2 of K=24576
+constexpr int kCW = 16;             // consumer warps
+constexpr int kCT = kCW * 32;       // consumer threads
+constexpr int kThreads = kCT + 32;  // + producer warp
 constexpr int kSlots = 5;
 constexpr int kChunk = GGB_DEV_ATTN_CHUNK;
+constexpr int kSeg = GGB_DEV_SEG_BLOCKS; // 64 blocks per K segment
 constexpr int kMaxG = 8;
-constexpr int kMaxE = 4096; // n_embd limit of the fused path (one K segment for the norm-fed mat-vecs)
+constexpr int kMaxE = 4096;         // longest norm-fed activation row
+constexpr int kMaxK = 24576;        // longest activation row kept in shared memory
+constexpr int kPartFloats = 2048;   // partial table: (rows of this CTA in a phase) x (K segments)
 
 enum PhaseKind { PH_QKV = 0, PH_ATTN, PH_COMBINE, PH_O, PH_GATE_UP, PH_DOWN, PH_LOGITS, PH_SAMPLE };
 
-struct Mat {
-    const uint8_t *qs;
-    const __half *d;
-    int rows;
-    int n_tiles;
+template <int TYPE> struct Fmt {
+    static constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;        // payload bytes per block
+    static constexpr int ROW_PB = kSeg * PB;                           // payload bytes per row segment
+    static constexpr int PASS_BYTES = 2 * kSeg * (PB + 2);             // 2304 / 4352
+    static constexpr int PPS = TYPE == GGB_TYPE_Q4_0 ? 16 : 8;         // passes per ring slot
+    static constexpr int SLOT_BYTES = PPS * PASS_BYTES;                // 36864 / 34816
 };
 
-struct PhaseDesc {
+struct Phase {
     int kind, layer;
-    Mat m[3];
-    int n_mats;
-    int nb;            // blocks per weight row
-    int cols;          // nb * 32
-    int rows_per_tile; // weight rows per ring slot (GATE_UP: gate rows per sub-tile; the slot also holds the up rows)
-    int ksegs;         // ceil(nb / 128)
-    int n_tiles;       // schedulable units: tiles (mat-vec), super-tiles of 32 rows (GATE_UP)
-    int rot;           // CTA rotation so small phases do not always land on the same SMs
-    const float *x_in;    // fp32 input of a norm-fed phase (null in layer 0: embedding row)
+    int n_units;     // schedulable units (row pairs; GATE_UP: 32-row groups of gate + up)
+    int unit_passes; // passes per unit
+    int unit_rows;   // logical rows per unit
+    int ksegs;       // K segments per row
+    int K;           // activation length
+    int n_rows;      // logical rows of the phase
+    int rot;         // CTA rotation so remainders do not always land on the same SMs
+    int pad_;
+    const uint8_t *stream;  // pass stream of the phase
+    const float *x_in;      // fp32 input of a norm-fed phase (null in layer 0: embedding row)
     const float *norm_w;
-    const uint8_t *act_in; // planar Q8_0 input (O, DOWN)
-    float *out[3];
+    const uint8_t *act_in;  // planar Q8_0 input (O, DOWN)
+    float *out;
     const float *resid;
-    uint8_t *act_out; // planar Q8_0 output (COMBINE, GATE_UP)
-    float *f32_out;   // COMBINE: kqv; GATE_UP: optional ffn_act dump; LOGITS: result_norm
+    uint8_t *act_out;       // planar Q8_0 output (COMBINE, GATE_UP)
+    float *f32_out;         // COMBINE: kqv; GATE_UP: optional ffn_act dump; LOGITS: result_norm
     __half *kcache, *vcache;
 };
+static_assert(sizeof(Phase) % 4 == 0, "Phase is copied word-wise");
+constexpr int kPhWords = (int)(sizeof(Phase) / 4);
 
 struct DecoderParams {
-    const PhaseDesc *phases;
+    const Phase *phases;
     int n_phases;
-    int type; // weight type
+    int type;
     int E, H, Hkv, d, F, V, n_ctx;
     float eps, q_scale, emb_scale;
-    // embedding
-    const uint8_t *emb_qs;
+    const uint8_t *emb_qs; // planar embedding table (layer-0 get_rows)
     const __half *emb_d;
     float *x0;
-    // decode state
     int32_t *state, *history;
-    // scratch
-    float *q, *k, *v; // fp32 Q/K/V of the current token
+    float *qkv; // fp32 Q | K | V of the current token
     float *attn_m, *attn_l, *attn_acc;
     int max_chunks;
     float *cand_v;
@@ -86,251 +94,184 @@ struct DecoderParams {
     unsigned long long *bar_count, *bar_base;
     const uint16_t *exp_table, *gelu_table;
     const float *rope_cos, *rope_sin;
-    long long *trace; // optional [n_phases][grid][4] SM-clock stamps: start, after prologue, after tiles, after barrier
-    long long *trace2; // optional [grid][32][3]: LOGITS tiles: before wait, after wait, after compute
+    long long *trace; // optional [n_phases][grid][4] SM-clock stamps: start, after prologue, after work, after barrier
 };
 
-struct SmemLayout {
-    alignas(128) uint8_t ring[kSlots][kSlotBytes];
-    alignas(16) uint8_t act[kMaxE + kMaxE / 16]; // planar Q8_0 activation built by the norm prologue
-    // 16 KB scratch: the norm prologue's fp32 input row, the attention's rope'd q (8 x 256), the combine's
-    // staged partials (2 x 8 KB) — never live at the same time
-    alignas(16) float scratch[kMaxE];
-    float s[kMaxG][kChunk];
-    float e[kMaxG][kChunk];
-    alignas(16) __half knew[256];
-    alignas(16) __half vnew[256];
-    float part[2][2 * kConsumerWarps][kConsumerWarps];
-    float stage_g[2][32], stage_u[2][32];
-    double red[kConsumerWarps];
-    float cand_v[kConsumerWarps];
-    int cand_i[kConsumerWarps];
+// union region: the views are never live at the same time
+//   mat-vec : act_q [kMaxK] | act_d half[kMaxK/32] | bias int[kMaxK/32] | part float[kPartFloats]
+//   norm    : xs float[kMaxE] at +8192 (act_q only uses [0, kMaxE) in a norm-fed phase)
+//   attn    : Kc half[32][256] | Vc half[32][256] | Sq half[8][256] | s float[8][32] | e float[8][32]
+constexpr int U_ACT_D = kMaxK;
+constexpr int U_BIAS = U_ACT_D + kMaxK / 32 * 2;
+constexpr int U_PART = U_BIAS + kMaxK / 32 * 4;
+constexpr int U_XS = 8192;
+constexpr int U_KC = 0, U_VC = 16384, U_SQ = 32768, U_S = 36864, U_E = 37888;
+constexpr int U_BYTES = 38912;
+static_assert(U_PART + kPartFloats * 4 <= U_BYTES, "union region too small");
+static_assert(U_XS + kMaxE * 4 <= U_ACT_D && kMaxE <= U_XS, "xs overlaps the activation row");
+
+template <int TYPE> struct Smem {
+    alignas(1024) uint8_t ring[kSlots][Fmt<TYPE>::SLOT_BYTES];
+    alignas(128) uint8_t u[U_BYTES];
+    double red[kCW];
+    float cand_v[kCW];
+    int cand_i[kCW];
     alignas(8) unsigned long long full_bar[kSlots];
     alignas(8) unsigned long long empty_bar[kSlots];
-    alignas(16) PhaseDesc ph[2]; // current / next phase descriptor (global reads would re-miss after every fence)
-    alignas(16) PhaseDesc ph_prod; // the producer's own copy (it runs phases ahead of the consumers)
-    alignas(16) DecoderParams P;   // kernel parameters (see decoder_kernel)
+    alignas(16) Phase ph[2];
 };
-static_assert(sizeof(DecoderParams) % 4 == 0, "DecoderParams is copied word-wise");
 
-// Every function re-derives the layout from the extern __shared__ symbol instead of receiving a reference:
-// an out-of-line function that gets a SmemLayout& only sees a generic pointer and emits LD.E/ST.E.
 extern __shared__ __align__(1024) uint8_t ggb_dec_smem[];
-__device__ __forceinline__ SmemLayout &smem() { return *reinterpret_cast<SmemLayout *>(ggb_dec_smem); }
-static_assert(sizeof(PhaseDesc) % 4 == 0, "PhaseDesc is copied word-wise");
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
+        "{\n.reg .pred p;\nWAIT_LOOP:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// Producer-side wait: poll with back-off.  The producer is warp 12, which shares scheduler 0 with consumer
-// warps 0/4/8 and (highest warp id first) out-prioritises them: a tight try_wait loop there starves a
-// quarter of the consumers.  The producer runs tiles ahead, so a little wake-up latency costs nothing.
-__device__ __forceinline__ void mbar_wait_backoff(unsigned long long *bar, uint32_t parity) {
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (done) return;
-        __nanosleep(500);
-    }
+        "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// Ampere-style async copy global -> shared, L2 only (.cg): used to stage small rows without holding registers
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+// async copy global -> shared through L2 only (.cg): data written by other CTAs of this kernel
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds_half(uint32_t addr) {
+    unsigned short h;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+    return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int r;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) { // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 
-// grid barrier over the consumer threads of all CTAs: bar.sync orders the CTA's writes before
-// thread 0's release-add (cumulative at gpu scope); the acquire-poll + bar.sync orders every
-// consumer's later reads after the other CTAs' writes.
-// Polling uses relaxed loads (an acquire load costs an L1 invalidate — CCTL.IVALL — per poll) and a single
-// acquire fence once the count is reached.
-__device__ __forceinline__ void grid_barrier(unsigned long long *bar_count, unsigned long long target) {
+// Grid barrier over the consumer threads of all CTAs: bar.sync orders the CTA's writes before thread 0's
+// release-add on ONE monotonic counter; thread 0 polls it (relaxed: an acquire load costs an L1 invalidate per
+// poll).  Every read of another CTA's data after a barrier is an L2 access (__ldcg / cp.async.cg / TMA), never
+// an L1-cached load, and the writers released at gpu scope.  Measured (tools/ubench_bar.cu): 1.4 us, of which
+// 0.6 us is the release fence; per-CTA flag arrays (3.7 us packed, 1.5 us padded) and counter trees (2.5 us)
+// are slower on B200.
+__device__ __forceinline__ void grid_barrier(unsigned long long *count, unsigned long long target) {
     consumer_bar();
     if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar_count), "l"(1ull) : "memory");
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(count), "l"(1ull) : "memory");
         unsigned long long v;
         do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar_count) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(count) : "memory");
         } while (v < target);
-        // no acquire needed here: every read of another CTA's data after a barrier is an L2 access
-        // (__ldcg / cp.async.cg / TMA), never an L1-cached load, and the writers released at gpu scope
     }
     consumer_bar();
 }
 
-// ---------------------------------------------------------------- schedule helpers (producer and consumers agree)
-struct TileInfo {
-    int mat, row0, nrows;
+struct Best {
+    float v;
+    int i;
 };
-__device__ __forceinline__ TileInfo locate_tile(const PhaseDesc &ph, int t) {
-    TileInfo ti;
-    int m = 0;
-    while (m + 1 < ph.n_mats && t >= ph.m[m].n_tiles) {
-        t -= ph.m[m].n_tiles;
-        m++;
-    }
-    ti.mat = m;
-    ti.row0 = t * ph.rows_per_tile;
-    ti.nrows = min(ph.rows_per_tile, ph.m[m].rows - ti.row0);
-    return ti;
-}
-__device__ __forceinline__ int first_unit(const PhaseDesc &ph, int cta, int G) {
-    return ((cta - ph.rot) % G + G) % G;
+__device__ __forceinline__ Best better(Best a, Best b) { // first maximum (ref: src/gemma_model.cpp:538-543)
+    if (b.i < 0) return a;
+    if (a.i < 0) return b;
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
 }
 
-struct RingPos {
-    uint32_t seq;
-    __device__ __forceinline__ int slot() const { return (int)(seq % kSlots); }
-    __device__ __forceinline__ uint32_t parity() const { return (seq / kSlots) & 1u; }
-};
+// CTA c's share [u0, u1) of n units: contiguous and balanced
+__device__ __forceinline__ void unit_range(int cta, int G, int rot, int n_units, int &u0, int &u1) {
+    const int c = (cta + rot) % G;
+    u0 = (int)(((long long)c * n_units) / G);
+    u1 = (int)(((long long)(c + 1) * n_units) / G);
+}
+
+__device__ __forceinline__ bool is_matvec(int kind) {
+    return kind == PH_QKV || kind == PH_O || kind == PH_GATE_UP || kind == PH_DOWN || kind == PH_LOGITS;
+}
 
 // ---------------------------------------------------------------- producer
 template <int TYPE>
-__device__ __noinline__ void producer_loop(int cta, int G, int n_pos) {
-    SmemLayout &S = smem();
-    const DecoderParams &P = S.P;
-    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
-    RingPos rp{0};
-    const int nchunk = (n_pos + kChunk - 1) / kChunk;
+__device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE> &S, int cta, int G) {
+    using F = Fmt<TYPE>;
+    const uint32_t ring = smem_u32(&S.ring[0][0]);
+    const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
+    int slot = 0;
+    uint32_t parity = 0;
+#pragma unroll 1
     for (int pi = 0; pi < P.n_phases; pi++) {
-        // private shared-memory copy of the descriptor: one burst of independent loads per phase
-        // (a by-value struct would live in local memory because ph.m[] is indexed dynamically)
-        {
-            constexpr int kWords = (int)(sizeof(PhaseDesc) / 4);
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(&P.phases[pi]);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(&S.ph_prod);
-#pragma unroll 10
-            for (int i = 0; i < kWords; i++) dst[i] = src[i];
-        }
-        const PhaseDesc &ph = S.ph_prod;
-        if (ph.kind == PH_QKV || ph.kind == PH_O || ph.kind == PH_DOWN || ph.kind == PH_LOGITS) {
-            for (int t = first_unit(ph, cta, G); t < ph.n_tiles; t += G) {
-                const TileInfo ti = locate_tile(ph, t);
-                const uint32_t pbytes = (uint32_t)ti.nrows * ph.nb * PB, sbytes = (uint32_t)ti.nrows * ph.nb * 2;
-                const int s = rp.slot();
-                mbar_wait_backoff(&S.empty_bar[s], rp.parity() ^ 1u);
-                mbar_expect_tx(&S.full_bar[s], pbytes + sbytes);
-                bulk_g2s(S.ring[s], ph.m[ti.mat].qs + (size_t)ti.row0 * ph.nb * PB, pbytes, &S.full_bar[s]);
-                bulk_g2s(S.ring[s] + pbytes, ph.m[ti.mat].d + (size_t)ti.row0 * ph.nb, sbytes, &S.full_bar[s]);
-                rp.seq++;
-            }
-        } else if (ph.kind == PH_GATE_UP) {
-            for (int st = first_unit(ph, cta, G); st < ph.n_tiles; st += G) {
-                for (int r0 = 0; r0 < 32; r0 += ph.rows_per_tile) {
-                    const int nrows = min(ph.rows_per_tile, 32 - r0);
-                    const size_t row = (size_t)st * 32 + r0;
-                    const uint32_t pbytes = (uint32_t)nrows * ph.nb * PB, sbytes = (uint32_t)nrows * ph.nb * 2;
-                    const int s = rp.slot();
-                    mbar_wait_backoff(&S.empty_bar[s], rp.parity() ^ 1u);
-                    mbar_expect_tx(&S.full_bar[s], 2 * (pbytes + sbytes));
-                    uint8_t *dst = S.ring[s];
-                    bulk_g2s(dst, ph.m[0].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
-                    bulk_g2s(dst + pbytes, ph.m[1].qs + row * ph.nb * PB, pbytes, &S.full_bar[s]);
-                    bulk_g2s(dst + 2 * pbytes, ph.m[0].d + row * ph.nb, sbytes, &S.full_bar[s]);
-                    bulk_g2s(dst + 2 * pbytes + sbytes, ph.m[1].d + row * ph.nb, sbytes, &S.full_bar[s]);
-                    rp.seq++;
-                }
-            }
-        } else if (ph.kind == PH_ATTN) {
-            const int n_items = P.Hkv * nchunk;
-            const uint32_t row_bytes = (uint32_t)P.d * 2;
-            const size_t kv_stride = (size_t)P.Hkv * P.d;
-            for (int it = first_unit(ph, cta, G); it < n_items; it += G) {
-                const int g = it / nchunk, c = it % nchunk;
-                const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
-                for (int which = 0; which < 2; which++) {
-                    const __half *base = (which == 0 ? ph.kcache : ph.vcache) + (size_t)p0 * kv_stride + (size_t)g * P.d;
-                    const int s = rp.slot();
-                    mbar_wait_backoff(&S.empty_bar[s], rp.parity() ^ 1u);
-                    mbar_expect_tx(&S.full_bar[s], (uint32_t)np * row_bytes);
-                    if (P.Hkv == 1) {
-                        bulk_g2s(S.ring[s], base, (uint32_t)np * row_bytes, &S.full_bar[s]);
-                    } else {
-                        for (int j = 0; j < np; j++)
-                            bulk_g2s(S.ring[s] + (size_t)j * row_bytes, base + (size_t)j * kv_stride, row_bytes,
-                                     &S.full_bar[s]);
-                    }
-                    rp.seq++;
-                }
+        const Phase *ph = P.phases + pi;
+        if (!is_matvec(ph->kind)) continue;
+        int u0, u1;
+        unit_range(cta, G, ph->rot, ph->n_units, u0, u1);
+        const int up = ph->unit_passes;
+        int n = (u1 - u0) * up;
+        const uint8_t *src = ph->stream + (size_t)u0 * up * F::PASS_BYTES;
+#pragma unroll 1
+        while (n > 0) {
+            const int cnt = min(n, F::PPS);
+            const uint32_t bytes = (uint32_t)cnt * F::PASS_BYTES;
+            mbar_wait(empty0 + 8 * slot, parity ^ 1u);
+            mbar_expect_tx(full0 + 8 * slot, bytes);
+            bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot);
+            src += bytes;
+            n -= cnt;
+            if (++slot == kSlots) {
+                slot = 0;
+                parity ^= 1u;
             }
         }
     }
 }
 
-// ---------------------------------------------------------------- consumer pieces
-
-// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into S.act (every CTA recomputes it).
-// Sum of squares in the DEV order: threads 0..255 hold the strided double partials.
-// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into S.act (every CTA recomputes it).
-// Deliberately compact (the persistent kernel is instruction-fetch sensitive): the fp32 row is staged in
-// shared memory with cp.async (one L2 round trip, no registers), the sum of squares follows the DEV order
-// (thread t < 256 sums elements t, t+256, ... in double; butterfly; warps in order), and the 12 warps then
-// quantise one 32-element block per iteration.
-__device__ __noinline__ void norm_prologue(int pb, int token, bool write_x0, float *f32_out) {
-    SmemLayout &S = smem();
-    const DecoderParams &P = S.P;
-    const PhaseDesc &ph = S.ph[pb];
+// ---------------------------------------------------------------- prologues
+// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into the shared activation row; every CTA
+// recomputes it (8 KB from L2) instead of making it a phase of its own.  Sum of squares in the DEV order:
+// threads 0..255 hold the strided double partials, butterfly, warps in order.
+template <int TYPE>
+__device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
+                                              bool write_x0, float *f32_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = P.E;
-    float *xs = S.scratch;
+    float *xs = reinterpret_cast<float *>(S.u + U_XS);
     const float *x_in = ph.x_in, *norm_w = ph.norm_w;
     if (x_in) {
         const uint32_t xs_addr = smem_u32(xs);
-        for (int v = tid; v < E / 4; v += kConsumerThreads) cp_async16(xs_addr + 16u * v, x_in + 4 * v);
+        for (int v = tid; v < E / 4; v += kCT) cp_async16(xs_addr + 16u * v, x_in + 4 * v);
         cp_async_wait_all();
     } else {
         // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
         const int nb = E / 32;
         const size_t blk0 = (size_t)token * nb;
-        for (int i = tid; i < E; i += kConsumerThreads) {
+        for (int i = tid; i < E; i += kCT) {
             const int b = i >> 5, e = i & 31;
             const float dd = __half2float(P.emb_d[blk0 + b]);
             int qv;
-            if (P.type == GGB_TYPE_Q4_0) {
+            if (TYPE == GGB_TYPE_Q4_0) {
                 const int byte = P.emb_qs[(blk0 + b) * 16 + (e & 15)];
                 qv = (e < 16 ? (byte & 0x0F) : (byte >> 4)) - 8;
             } else {
@@ -356,360 +297,258 @@ __device__ __noinline__ void norm_prologue(int pb, int token, bool write_x0, flo
     for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
     const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-    // one Q8_0 block (32 consecutive elements) per warp per iteration; next block's weight prefetched
-    float w_next = norm_w[32 * warp + lane];
-#pragma unroll 1
-    for (int b = warp; b < E / 32; b += kConsumerWarps) {
+    int8_t *act_q = reinterpret_cast<int8_t *>(S.u);
+    __half *act_d = reinterpret_cast<__half *>(S.u + U_ACT_D);
+    int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
+#pragma unroll 2
+    for (int b = warp; b < E / 32; b += kCW) { // one Q8_0 block (32 consecutive elements) per warp per iteration
         const int i = 32 * b + lane;
-        const float w = w_next;
-        if (b + kConsumerWarps < E / 32) w_next = norm_w[i + 32 * kConsumerWarps];
         const float x = xs[i];
-        const float v = __fmul_rn(__fmul_rn(x, scale), w);
+        const float v = __fmul_rn(__fmul_rn(x, scale), norm_w[i]);
         if (write_x0) P.x0[i] = x;
         if (f32_out) f32_out[i] = v;
         float d;
         const int q = quantize_q8_lane(v, d);
-        ((int8_t *)S.act)[i] = (int8_t)q;
-        if (lane == 0) reinterpret_cast<__half *>(S.act + E)[b] = __float2half_rn(d);
+        act_q[i] = (int8_t)q;
+        const int qs = __reduce_add_sync(0xffffffffu, q);
+        if (lane == 0) {
+            act_d[b] = __float2half_rn(d);
+            bias[b] = -8 * qs;
+        }
     }
     consumer_bar();
 }
 
-struct Best {
-    float v;
-    int i;
-};
-// per-thread state crosses the out-of-line phase functions BY VALUE (registers): a reference would live in
-// local memory, be flushed/reloaded around every asm("memory") barrier, and miss the tiny L1 every time
-struct MvRet {
-    uint32_t seq;
-    Best best;
-};
-__device__ __forceinline__ Best better(Best a, Best b) {
-    if (b.i < 0) return a;
-    if (a.i < 0) return b;
-    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
-    return a;
-}
-
-// ONE routine for every mat-vec phase (QKV, O, GATE_UP, DOWN, LOGITS).  The persistent kernel executes each
-// phase's code once per layer, so its instruction footprint per layer has to stay cache-resident: separate,
-// heavily unrolled functions per phase made the kernel instruction-fetch bound (a cold norm prologue took
-// ~4 us, the same code re-run hot 0.5 us).
-//
-// K is cut into segments of 64 blocks (GGB_DEV_SEG_BLOCKS): lane l owns blocks l and l+32 of its warp's
-// segment, for EVERY row — 20 registers of activations, loaded once per phase.  A "pass" covers two rows of
-// that segment (4 block slots per lane): the four dp4a chains advance in lock step, the two lane partials
-// ("blocks in order from 0.0f") go through ONE folded xor-butterfly (lanes < 16 end with row 0's sum, lanes
-// >= 16 with row 1's; same additions as two separate butterflies), i.e. the DEV order.  With more than one
-// segment (K > 2048) the per-segment sums meet in shared memory and are added in segment order.
-// Ring tiles are read with explicit ld.shared; the pass is branch-free.
-// GATE_UP slots hold [gate payload][up payload][gate scales][up scales], i.e. they look like a 2R-row tile.
+// planar Q8_0 row produced by other CTAs (COMBINE, GATE_UP) -> shared activation row + per-block bias
 template <int TYPE>
-__device__ __noinline__ MvRet matvec_phase(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
-    SmemLayout &S = smem();
-    const DecoderParams &P = S.P;
-    const PhaseDesc &ph = S.ph[pb];
-    constexpr int PB = TYPE == GGB_TYPE_Q4_0 ? 16 : 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int kind = ph.kind, nb = ph.nb, ksegs = ph.ksegs, n_units = ph.n_tiles, rpt = ph.rows_per_tile;
-    const bool gate_up = kind == PH_GATE_UP;
-    const float *resid = ph.resid;
-    const int n_mats = ph.n_mats, rows0 = ph.m[0].rows;
-    const int unit0 = first_unit(ph, cta, G);
-    if (unit0 >= n_units) return MvRet{seq, best};
-
-    const int kseg = warp % ksegs, group = warp / ksegs; // this warp's segment and row-pair group
-    const int groups = kConsumerWarps / ksegs;
-    const bool warp_live = group < groups;
-    const uint32_t row_pb = (uint32_t)nb * PB, row_sb = (uint32_t)nb * 2;
-    const int blk0 = kseg * GGB_DEV_SEG_BLOCKS + lane;
-    ActBlock ab[2];
-    bool blk_live[2];
+__device__ __forceinline__ void copy_prologue(Smem<TYPE> &S, const uint8_t *act_in, int K) {
+    const int tid = threadIdx.x;
+    const uint32_t q_addr = smem_u32(S.u), d_addr = smem_u32(S.u + U_ACT_D);
+    for (int v = tid; v < K / 16; v += kCT) cp_async16(q_addr + 16u * v, act_in + 16 * v);
+    for (int v = tid; v < K / 256; v += kCT) cp_async16(d_addr + 16u * v, act_in + K + 16 * v);
+    cp_async_wait_all();
+    consumer_bar();
+    if (TYPE == GGB_TYPE_Q4_0) {
+        const int *aq = reinterpret_cast<const int *>(S.u);
+        int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
+        for (int b = tid; b < K / 32; b += kCT) {
+            int s = 0;
 #pragma unroll
-    for (int b = 0; b < 2; b++) {
-        blk_live[b] = warp_live && blk0 + 32 * b < nb;
-        if (act_in_smem) load_act(ab[b], S.act, ph.cols, blk0 + 32 * b, blk_live[b]);
-        else load_act_cg(ab[b], ph.act_in, ph.cols, blk0 + 32 * b, blk_live[b]);
+            for (int i = 0; i < 8; i++) s = __dp4a(aq[8 * b + i], 0x01010101, s);
+            bias[b] = -8 * s;
+        }
+        consumer_bar();
     }
-    const uint32_t ring0 = smem_u32(&S.ring[0][0]);
-    const uint32_t lane_pay = (uint32_t)blk0 * PB, lane_scl = (uint32_t)blk0 * 2;
-    const int half = lane >> 4; // which row of a pass this lane publishes
-    const int n_sub = gate_up ? (32 + rpt - 1) / rpt : 1;
-    int pbuf = 0, sbuf = 0, ord = 0;
-    int slot = (int)(seq % kSlots);
-    uint32_t parity = (seq / kSlots) & 1u;
-
-    // hand one finished row (index r of the slot) to its consumer: residual add + store, or the GeGLU staging
-    auto publish = [&](int r, float v, float rv, int mat, int row0, int nrows) {
-        if (gate_up) {
-            if (r < nrows) S.stage_g[sbuf][row0 + r] = v;
-            else S.stage_u[sbuf][row0 + r - nrows] = v;
-        } else {
-            if (resid) v = __fadd_rn(v, rv);
-            ph.out[mat][row0 + r] = v;
-            if (kind == PH_LOGITS) best = better(best, Best{v, row0 + r});
-        }
-    };
-
-    for (int u = unit0; u < n_units; u += G, ord++) {
-        for (int sub = 0; sub < n_sub; sub++) {
-            int mat = 0, row0, nrows;
-            if (gate_up) {
-                row0 = sub * rpt;
-                nrows = min(rpt, 32 - row0);
-            } else if (n_mats == 1) {
-                row0 = u * rpt;
-                nrows = min(rpt, rows0 - row0);
-            } else {
-                const TileInfo ti = locate_tile(ph, u);
-                mat = ti.mat; row0 = ti.row0; nrows = ti.nrows;
-            }
-            const int slot_rows = gate_up ? 2 * nrows : nrows;
-            const int s = slot;
-            const uint32_t par = parity;
-            const uint32_t pay0 = ring0 + (uint32_t)s * kSlotBytes + lane_pay;
-            const uint32_t scl0 = ring0 + (uint32_t)s * kSlotBytes + (uint32_t)slot_rows * row_pb + lane_scl;
-            // residual of the row this lane will publish, requested before the tile is waited for
-            const int my_first = 2 * group;
-            const int my_row = ksegs == 1 ? my_first + half : tid; // ksegs > 1: thread t < slot_rows finishes row t
-            const bool my_pub = ksegs == 1 ? ((lane & 15) == 0 && my_row < slot_rows) : (tid < slot_rows);
-            float rv = 0.0f;
-            if (my_pub && resid) rv = __ldcg(resid + row0 + my_row);
-            const bool dbg = P.trace2 && kind == PH_LOGITS && ord < 31 && tid == 0;
-            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 0] = clock64();
-            mbar_wait(&S.full_bar[s], par);
-            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 1] = clock64();
-#pragma unroll 1
-            for (int first = my_first; first < slot_rows; first += 2 * groups) {
-                uint4 w0[4], w1[4];
-                float dx[4];
-                const uint32_t pbase = pay0 + (uint32_t)first * row_pb, sbase = scl0 + (uint32_t)first * row_sb;
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    const uint32_t po = (uint32_t)(t >> 1) * row_pb + (uint32_t)(t & 1) * 32 * PB;
-                    w0[t] = lds_u4(pbase + po);
-                    if (TYPE == GGB_TYPE_Q8_0) w1[t] = lds_u4(pbase + po + 16);
-                    dx[t] = lds_half_as_float(sbase + (uint32_t)(t >> 1) * row_sb + (uint32_t)(t & 1) * 64);
-                }
-                float term[4];
-                pass_terms<TYPE, 2>(w0, w1, dx, ab, term);
-                const bool row1 = first + 1 < slot_rows;
-                // lane partials: blocks in order from 0.0f, dead blocks dropped
-                float a0 = 0.0f, a1 = 0.0f;
-                a0 = blk_live[0] ? __fadd_rn(a0, term[0]) : a0;
-                a0 = blk_live[1] ? __fadd_rn(a0, term[1]) : a0;
-                a1 = (blk_live[0] && row1) ? __fadd_rn(a1, term[2]) : a1;
-                a1 = (blk_live[1] && row1) ? __fadd_rn(a1, term[3]) : a1;
-                // folded xor-butterfly 16,8,4,2,1
-                const float send = half ? a0 : a1;
-                float keep = __fadd_rn(half ? a1 : a0, __shfl_xor_sync(0xffffffffu, send, 16));
-#pragma unroll
-                for (int off = 8; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
-                const int r = first + half;
-                if ((lane & 15) == 0 && r < slot_rows && warp_live) {
-                    if (ksegs > 1) S.part[pbuf][r][kseg] = keep;
-                    else publish(r, keep, first == my_first ? rv : (resid ? __ldcg(resid + row0 + r) : 0.0f), mat, row0, nrows);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
-            if (dbg) P.trace2[((size_t)cta * 32 + ord) * 3 + 2] = clock64();
-            if (ksegs > 1) {
-                consumer_bar();
-                if (tid < slot_rows) { // thread r: segment sums of row r added in segment order
-                    float total = S.part[pbuf][tid][0];
-                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, S.part[pbuf][tid][k]);
-                    publish(tid, total, rv, mat, row0, nrows);
-                }
-                pbuf ^= 1;
-            }
-            seq++;
-            if (++slot == kSlots) {
-                slot = 0;
-                parity ^= 1u;
-            }
-        }
-        if (gate_up) { // GeGLU (fp16 gelu table) + quantize_row_q8_0 of the super-tile's 32 products, lane-parallel
-            consumer_bar();
-            if (warp == 0) {
-                const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(S.stage_g[sbuf][lane])]);
-                const float x = __fmul_rn(gl, S.stage_u[sbuf][lane]);
-                const size_t row = (size_t)u * 32 + lane;
-                if (ph.f32_out) ph.f32_out[row] = x;
-                float d;
-                const int q = quantize_q8_lane(x, d);
-                ((int8_t *)ph.act_out)[row] = (int8_t)q;
-                if (lane == 0) reinterpret_cast<__half *>(ph.act_out + P.F)[u] = __float2half_rn(d);
-            }
-            sbuf ^= 1;
-        }
-    }
-    return MvRet{seq, best};
 }
 
-// ATTN: items (kv head g, chunk of 32 positions); K chunk and V chunk arrive in two ring slots.
-// Same arithmetic as attention.cu attn_partial_kernel; rope + Q scale are applied to q on load, and the
-// item that owns the newest position ropes K, rounds K/V to fp16, stores them in the cache and uses them.
-__device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq_in, int n_pos) {
-    SmemLayout &S = smem();
-    const DecoderParams &P = S.P;
-    const PhaseDesc &ph = S.ph[pb];
-    RingPos rp{seq_in};
+// ---------------------------------------------------------------- one pass: 2 rows x one K segment
+// Lane l owns blocks l and l + 32 of the segment for both rows.  Per-block term = the scalar reference's
+//   Q4_0: ((float)sumi * d_x) * d_y      Q8_0: (float)sumi * (d_x * d_y)
+// lane partial = blocks in order from 0.0f; the two rows' butterflies (xor 16,8,4,2,1) are folded into one:
+// lanes < 16 end with row A's sum, lanes >= 16 with row B's (same additions, DEV order).
+template <int TYPE>
+__device__ __forceinline__ float pass_dot(uint32_t base, uint32_t act, int seg, int nb, int lane) {
+    using F = Fmt<TYPE>;
+    int a[2][8];
+    float dy[2];
+    int bias[2];
+    bool live[2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int b = seg * kSeg + lane + 32 * t;
+        live[t] = b < nb;
+        const int bc = live[t] ? b : 0;
+        const uint4 lo = lds_u4(act + bc * 32), hi = lds_u4(act + bc * 32 + 16);
+        a[t][0] = lo.x; a[t][1] = lo.y; a[t][2] = lo.z; a[t][3] = lo.w;
+        a[t][4] = hi.x; a[t][5] = hi.y; a[t][6] = hi.z; a[t][7] = hi.w;
+        dy[t] = lds_half(act + U_ACT_D + bc * 2);
+        bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + bc * 4) : 0;
+    }
+    float term[4]; // [row][block]
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int r = k >> 1, t = k & 1;
+        const uint32_t pay = base + r * F::ROW_PB + (lane + 32 * t) * F::PB;
+        const float dx = lds_half(base + 2 * F::ROW_PB + r * (kSeg * 2) + (lane + 32 * t) * 2);
+        if (TYPE == GGB_TYPE_Q4_0) {
+            const uint4 w = lds_u4(pay);
+            const uint32_t q[4] = {w.x, w.y, w.z, w.w};
+            int lo = bias[t], hi = 0; // high nibbles stay in place (x16) and are divided out once: exact
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                lo = __dp4a((int)(q[i] & 0x0F0F0F0Fu), a[t][i], lo);
+                hi = dp4a_us(q[i] & 0xF0F0F0F0u, a[t][4 + i], hi);
+            }
+            const int sumi = lo + (hi >> 4);
+            term[k] = __fmul_rn(__fmul_rn((float)sumi, dx), dy[t]);
+        } else {
+            const uint4 w0 = lds_u4(pay), w1 = lds_u4(pay + 16);
+            int s0 = 0, s1 = 0;
+            s0 = __dp4a((int)w0.x, a[t][0], s0); s1 = __dp4a((int)w1.x, a[t][4], s1);
+            s0 = __dp4a((int)w0.y, a[t][1], s0); s1 = __dp4a((int)w1.y, a[t][5], s1);
+            s0 = __dp4a((int)w0.z, a[t][2], s0); s1 = __dp4a((int)w1.z, a[t][6], s1);
+            s0 = __dp4a((int)w0.w, a[t][3], s0); s1 = __dp4a((int)w1.w, a[t][7], s1);
+            term[k] = __fmul_rn((float)(s0 + s1), __fmul_rn(dx, dy[t]));
+        }
+    }
+    float a0 = 0.0f, a1 = 0.0f;
+    a0 = live[0] ? __fadd_rn(a0, term[0]) : a0;
+    a0 = live[1] ? __fadd_rn(a0, term[1]) : a0;
+    a1 = live[0] ? __fadd_rn(a1, term[2]) : a1;
+    a1 = live[1] ? __fadd_rn(a1, term[3]) : a1;
+    const int half = lane >> 4;
+    const float send = half ? a0 : a1;
+    float keep = __fadd_rn(half ? a1 : a0, __shfl_xor_sync(0xffffffffu, send, 16));
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
+    return keep;
+}
+
+// ---------------------------------------------------------------- ATTN
+// items (kv head g, chunk of 32 positions).  Same arithmetic as attention.cu attn_partial_kernel; rope + Q
+// scale are applied to q on load, and the item that owns the newest position ropes K, rounds K/V to fp16,
+// stores them in the cache and uses them.
+template <int TYPE>
+__device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
+                                           int n_pos) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = P.d, halfd = d / 2, Gq = P.H / P.Hkv;
+    const int d = P.d, halfd = d / 2, Hkv = P.Hkv, Gq = P.H / Hkv;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    const int n_items = P.Hkv * nchunk;
+    const int n_items = Hkv * nchunk;
     const int pos = n_pos - 1;
+    const size_t kv_stride = (size_t)Hkv * d;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
-    float(*Sq)[256] = reinterpret_cast<float(*)[256]>(S.scratch);
+    const float *q_all = P.qkv, *k_all = P.qkv + (size_t)P.H * d, *v_all = k_all + (size_t)Hkv * d;
+    __half *Kc = reinterpret_cast<__half *>(S.u + U_KC), *Vc = reinterpret_cast<__half *>(S.u + U_VC);
+    __half *Sq = reinterpret_cast<__half *>(S.u + U_SQ);
+    float(*Ss)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_S);
+    float(*Se)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_E);
+    const uint32_t kc_addr = smem_u32(Kc), vc_addr = smem_u32(Vc);
+    const int pieces = d / 8; // 16-byte pieces per row
 #pragma unroll 1
-    for (int it = first_unit(ph, cta, G); it < n_items; it += G) {
+    for (int it = (cta + ph.rot) % G; it < n_items; it += G) {
         const int g = it / nchunk, c = it % nchunk;
         const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
         const int h0 = g * Gq;
-        const bool owns_new = (pos >= p0 && pos < p0 + np);
+        const int jnew = pos - p0; // row of the new position inside this chunk (if 0 <= jnew < np)
+        const bool owns_new = jnew >= 0 && jnew < np;
+        // K / V chunk rows (the new position's row is computed below, not loaded)
+        for (int v = tid; v < np * pieces; v += kCT) {
+            const int j = v / pieces, qd = v % pieces;
+            if (j == jnew) continue;
+            const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d + 8 * qd;
+            cp_async16(kc_addr + (uint32_t)(j * d + 8 * qd) * 2, ph.kcache + src);
+            cp_async16(vc_addr + (uint32_t)(j * d + 8 * qd) * 2, ph.vcache + src);
+        }
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
-        {
-            constexpr int kQIter = (kMaxG * 128 + kConsumerThreads - 1) / kConsumerThreads;
-            float x0[kQIter], x1[kQIter], cs[kQIter], sn[kQIter];
-#pragma unroll
-            for (int it = 0; it < kQIter; it++) { // all loads first: one L2 round trip
-                const int i = tid + kConsumerThreads * it;
-                if (i < Gq * halfd) {
-                    const int jh = i / halfd, e = i % halfd;
-                    const float *qh = P.q + (size_t)(h0 + jh) * d;
-                    x0[it] = __ldcg(qh + e);
-                    x1[it] = __ldcg(qh + e + halfd);
-                    cs[it] = cosr[e];
-                    sn[it] = sinr[e];
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < kQIter; it++) {
-                const int i = tid + kConsumerThreads * it;
-                if (i < Gq * halfd) {
-                    const int jh = i / halfd, e = i % halfd;
-                    const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0[it], cs[it]), __fmul_rn(x1[it], sn[it])), P.q_scale);
-                    const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0[it], sn[it]), __fmul_rn(x1[it], cs[it])), P.q_scale);
-                    Sq[jh][e] = __half2float(__float2half_rn(r0));
-                    Sq[jh][e + halfd] = __half2float(__float2half_rn(r1));
-                }
-            }
+        for (int i = tid; i < Gq * halfd; i += kCT) {
+            const int jh = i / halfd, e = i % halfd;
+            const float *qh = q_all + (size_t)(h0 + jh) * d;
+            const float x0 = __ldcg(qh + e), x1 = __ldcg(qh + e + halfd);
+            const float cs = cosr[e], sn = sinr[e];
+            const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
+            const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
+            Sq[jh * d + e] = __float2half_rn(r0);
+            Sq[jh * d + e + halfd] = __float2half_rn(r1);
         }
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
-            for (int e = tid; e < halfd; e += kConsumerThreads) {
-                const float x0 = __ldcg(P.k + (size_t)g * d + e), x1 = __ldcg(P.k + (size_t)g * d + e + halfd);
+            for (int e = tid; e < halfd; e += kCT) {
+                const float x0 = __ldcg(k_all + (size_t)g * d + e), x1 = __ldcg(k_all + (size_t)g * d + e + halfd);
                 const float cs = cosr[e], sn = sinr[e];
                 const __half k0 = __float2half_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)));
                 const __half k1 = __float2half_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)));
-                S.knew[e] = k0;
-                S.knew[e + halfd] = k1;
-                __half *krow = ph.kcache + ((size_t)pos * P.Hkv + g) * d;
+                Kc[jnew * d + e] = k0;
+                Kc[jnew * d + e + halfd] = k1;
+                __half *krow = ph.kcache + ((size_t)pos * Hkv + g) * d;
                 krow[e] = k0;
                 krow[e + halfd] = k1;
             }
-            for (int e = tid; e < d; e += kConsumerThreads) {
-                const __half vv = __float2half_rn(__ldcg(P.v + (size_t)g * d + e));
-                S.vnew[e] = vv;
-                ph.vcache[((size_t)pos * P.Hkv + g) * d + e] = vv;
+            for (int e = tid; e < d; e += kCT) {
+                const __half vv = __float2half_rn(__ldcg(v_all + (size_t)g * d + e));
+                Vc[jnew * d + e] = vv;
+                ph.vcache[((size_t)pos * Hkv + g) * d + e] = vv;
             }
         }
+        cp_async_wait_all();
         consumer_bar();
-        // scores: warp w takes positions w, w+12, w+24
-        {
-            const int s = rp.slot();
-            mbar_wait(&S.full_bar[s], rp.parity());
-            const __half *kchunk = reinterpret_cast<const __half *>(S.ring[s]);
-            for (int j = warp; j < np; j += kConsumerWarps) {
-                float kf[8];
-                if (8 * lane < d) {
-                    const __half *krow = (owns_new && p0 + j == pos) ? S.knew : kchunk + (size_t)j * d;
-                    const uint4 raw = *reinterpret_cast<const uint4 *>(krow + 8 * lane);
-                    const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const float2 f = __half22float2(h2[e]);
-                        kf[2 * e] = f.x;
-                        kf[2 * e + 1] = f.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) kf[e] = 0.f;
-                }
-                // (fp16 x fp16 products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once: same bits)
-                // heads in groups of 4: lane partials first, then the group's butterflies interleaved (ILP
-                // without unrolling all 8 heads: code size matters here); each sum follows the DEV order
+        // scores: warp w takes positions w, w + 16
 #pragma unroll 1
-                for (int j0 = 0; j0 < Gq; j0 += 4) {
-                    float acc[4];
+        for (int j = warp; j < np; j += kCW) {
+            float kf[8];
+            const bool in = 8 * lane < d;
+            {
+                uint4 raw = make_uint4(0, 0, 0, 0);
+                if (in) raw = *reinterpret_cast<const uint4 *>(Kc + j * d + 8 * lane);
+                const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        acc[u] = 0.0f;
-                        if (j0 + u < Gq && 8 * lane < d) {
-                            const float4 qa = *reinterpret_cast<const float4 *>(&Sq[j0 + u][8 * lane]);
-                            const float4 qb = *reinterpret_cast<const float4 *>(&Sq[j0 + u][8 * lane + 4]);
-                            acc[u] = __fmaf_rn(kf[0], qa.x, acc[u]);
-                            acc[u] = __fmaf_rn(kf[1], qa.y, acc[u]);
-                            acc[u] = __fmaf_rn(kf[2], qa.z, acc[u]);
-                            acc[u] = __fmaf_rn(kf[3], qa.w, acc[u]);
-                            acc[u] = __fmaf_rn(kf[4], qb.x, acc[u]);
-                            acc[u] = __fmaf_rn(kf[5], qb.y, acc[u]);
-                            acc[u] = __fmaf_rn(kf[6], qb.z, acc[u]);
-                            acc[u] = __fmaf_rn(kf[7], qb.w, acc[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __shfl_xor_sync(0xffffffffu, acc[u], off));
-                    }
-                    if (lane == 0) {
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (j0 + u < Gq) S.s[j0 + u][j] = acc[u];
-                    }
+                for (int e = 0; e < 4; e++) {
+                    const float2 f = __half22float2(h2[e]);
+                    kf[2 * e] = f.x;
+                    kf[2 * e + 1] = f.y;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
-            rp.seq++;
+            // fp16 x fp16 products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once.  Heads in
+            // groups of 4: lane partials first, then the group's butterflies interleaved; each sum in DEV order
+#pragma unroll 1
+            for (int j0 = 0; j0 < Gq; j0 += 4) {
+                float acc[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    acc[u] = 0.0f;
+                    if (j0 + u < Gq && in) {
+                        const uint4 raw = *reinterpret_cast<const uint4 *>(Sq + (j0 + u) * d + 8 * lane);
+                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float2 f = __half22float2(h2[e]);
+                            acc[u] = __fmaf_rn(kf[2 * e], f.x, acc[u]);
+                            acc[u] = __fmaf_rn(kf[2 * e + 1], f.y, acc[u]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __shfl_xor_sync(0xffffffffu, acc[u], off));
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j0 + u < Gq) Ss[j0 + u][j] = acc[u];
+                }
+            }
         }
         consumer_bar();
         // per-head chunk soft-max through the fp16 exp table
         if (warp < Gq) {
-            const float sv = lane < np ? S.s[warp][lane] : -INFINITY;
+            const float sv = lane < np ? Ss[warp][lane] : -INFINITY;
             const float m = warp_max_f32(sv);
             const float e = lane < np ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sv, m))]) : 0.0f;
             const float l = warp_sum_f32(e);
-            S.e[warp][lane] = e;
+            Se[warp][lane] = e;
             if (lane == 0) {
                 P.attn_m[(size_t)(h0 + warp) * P.max_chunks + c] = m;
                 P.attn_l[(size_t)(h0 + warp) * P.max_chunks + c] = l;
             }
         }
         consumer_bar();
-        // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p
+        // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p.  4 thread groups of 128: group hs takes heads
+        // hs, hs + 4; thread -> one pair of dims
         {
-            const int s = rp.slot();
-            mbar_wait(&S.full_bar[s], rp.parity());
-            const __half *vchunk = reinterpret_cast<const __half *>(S.ring[s]);
-            // 4 thread groups of 128: group hs takes heads hs, hs+4; thread -> one pair of dims
-            constexpr int kHG = kConsumerThreads / 128; // 4
+            constexpr int kHG = kCT / 128; // 4
             const int dp = tid % 128, hs = tid / 128;
             if (dp < halfd) {
                 float a0[kMaxG / kHG], a1[kMaxG / kHG];
 #pragma unroll
                 for (int u = 0; u < kMaxG / kHG; u++) a0[u] = a1[u] = 0.0f;
-#pragma unroll 2
+#pragma unroll 4
                 for (int j = 0; j < np; j++) {
-                    const __half *vrow = (owns_new && p0 + j == pos) ? S.vnew : vchunk + (size_t)j * d;
-                    const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(vrow + 2 * dp));
+                    const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(Vc + j * d + 2 * dp));
 #pragma unroll
                     for (int u = 0; u < kMaxG / kHG; u++) {
                         const int jh = kHG * u + hs;
                         if (jh < Gq) { // e is an fp16 value: e*v is exact, fmaf == mul + add
-                            const float e = S.e[jh][j];
+                            const float e = Se[jh][j];
                             a0[u] = __fmaf_rn(e, vf.x, a0[u]);
                             a1[u] = __fmaf_rn(e, vf.y, a1[u]);
                         }
@@ -724,69 +563,50 @@ __device__ __noinline__ uint32_t attn_phase(int pb, int cta, int G, uint32_t seq
                     }
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
-            rp.seq++;
         }
         consumer_bar();
     }
-    return rp.seq;
 }
 
-// COMBINE: one warp per (head, 32-dim slice): M = max m_c; w_c = exp_table[f16(m_c - M)];
+// COMBINE: one warp per (head, 32-dim slice), lane = dim: M = max m_c; w_c = exp_table[f16(m_c - M)];
 // L = sum l_c*w_c; O = sum acc_c*w_c (sequential in c); out = O / L; the slice is one Q8_0 block.
-// Compact on purpose: the warp stages its 64-chunk window of partials in shared memory with cp.async
-// (one L2 round trip), then runs the sequential chain from shared memory.
-__device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
-    SmemLayout &S = smem();
-    const DecoderParams &P = S.P;
-    const PhaseDesc &ph = S.ph[pb];
+template <int TYPE>
+__device__ __forceinline__ void combine_phase(const DecoderParams &P, const Phase &ph, int cta, int G, int n_pos) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = P.d, slices = d / 32;
     const int n_tasks = P.H * slices;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    if (warp >= 2) return; // two 8 KB staging windows -> at most two tasks in flight per CTA
-    float *win = S.scratch + warp * 2048; // 64 chunks x 32 floats
-    const uint32_t win_addr = smem_u32(win);
 #pragma unroll 1
-    for (int task = warp * G + ((cta - ph.rot) % G + G) % G; task < n_tasks; task += 2 * G) {
+    for (int task = (cta + ph.rot) % G + G * warp; task < n_tasks; task += G * kCW) {
         const int h = task / slices, sl = task % slices;
         const float *pm = P.attn_m + (size_t)h * P.max_chunks;
         const float *pl = P.attn_l + (size_t)h * P.max_chunks;
-        const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32;
+        const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32 + lane;
         float mx = -INFINITY;
-#pragma unroll 4
         for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, __ldcg(pm + c));
         mx = warp_max_f32(mx);
         float L = 0.0f, O = 0.0f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < nchunk; c0 += 64) {
-            const int nc = min(64, nchunk - c0);
-            // stage nc x 128 B: 8 x 16 B pieces per chunk
-            for (int v = lane; v < nc * 8; v += 32)
-                cp_async16(win_addr + 16u * v, pa + (size_t)(c0 + (v >> 3)) * d + 4 * (v & 7));
-            float wl[2], ll[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int c = c0 + 32 * u + lane;
-                const bool ok = 32 * u + lane < nc;
-                wl[u] = ok ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(__ldcg(pm + c), mx))]) : 0.0f;
-                ll[u] = ok ? __ldcg(pl + c) : 0.0f;
-            }
-            cp_async_wait_all();
-            __syncwarp();
+        for (int c0 = 0; c0 < nchunk; c0 += 32) {
+            const int nc = min(32, nchunk - c0);
+            const bool ok = lane < nc;
+            const float wl = ok ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(__ldcg(pm + c0 + lane), mx))]) : 0.0f;
+            const float ll = ok ? __ldcg(pl + c0 + lane) : 0.0f;
 #pragma unroll 1
-            for (int u = 0; u < 2; u++) {
-                const int n = min(32, nc - 32 * u);
-#pragma unroll 4
-                for (int j = 0; j < n; j++) {
-                    const float w = __shfl_sync(0xffffffffu, wl[u], j);
-                    const float l = __shfl_sync(0xffffffffu, ll[u], j);
-                    L = __fadd_rn(L, __fmul_rn(l, w));
-                    O = __fadd_rn(O, __fmul_rn(win[(32 * u + j) * 32 + lane], w));
+            for (int j0 = 0; j0 < nc; j0 += 8) {
+                float a[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) a[u] = j0 + u < nc ? __ldcg(pa + (size_t)(c0 + j0 + u) * d) : 0.0f;
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float w = __shfl_sync(0xffffffffu, wl, j0 + u);
+                    const float l = __shfl_sync(0xffffffffu, ll, j0 + u);
+                    if (j0 + u < nc) {
+                        L = __fadd_rn(L, __fmul_rn(l, w));
+                        O = __fadd_rn(O, __fmul_rn(a[u], w));
+                    }
                 }
             }
-            __syncwarp();
         }
         const float r = __fdiv_rn(O, L);
         const size_t idx = (size_t)h * d + sl * 32 + lane;
@@ -798,102 +618,148 @@ __device__ __noinline__ void combine_phase(int pb, int cta, int G, int n_pos) {
     }
 }
 
+// ---------------------------------------------------------------- the kernel
 template <int TYPE>
-__device__ __forceinline__ MvRet run_matvec(int pb, int cta, int G, uint32_t seq, bool act_in_smem, Best best) {
-    return matvec_phase<TYPE>(pb, cta, G, seq, act_in_smem, best);
-}
-
-// 17 warps: the register file is allocated in units of 4 warps (20 here), so the per-thread budget is 96.  With
-// 212 KB of the SM's 228 KB carved out as shared memory the L1 left for local memory is tiny and a spill
-// is an L2 round trip: the phase functions are kept out of line and templated so none of them spills.
-template <int TYPE>
-__global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_constant__ DecoderParams Pk) {
-    SmemLayout &S = smem();
-    // the parameter block is copied to shared memory: the out-of-line phase functions take it by reference,
-    // and a reference to kernel parameters would be a local-memory copy
-    {
-        constexpr int kWords = (int)(sizeof(DecoderParams) / 4);
-        for (int i = threadIdx.x; i < kWords; i += kThreads)
-            reinterpret_cast<uint32_t *>(&S.P)[i] = reinterpret_cast<const uint32_t *>(&Pk)[i];
-    }
-    __syncthreads();
-    const DecoderParams &P = S.P;
+__global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_constant__ DecoderParams P) {
+    using F = Fmt<TYPE>;
+    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
     const int cta = blockIdx.x, G = gridDim.x;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
         for (int i = 0; i < kSlots; i++) {
-            mbar_init(&S.full_bar[i], 1);
-            mbar_init(&S.empty_bar[i], kConsumerWarps);
+            mbar_init(smem_u32(&S.full_bar[i]), 1);
+            mbar_init(smem_u32(&S.empty_bar[i]), kCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int token = min(max(P.state[0], 0), P.V - 1);
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
-    const unsigned long long base = *P.bar_base;
-    unsigned long long *const bar_count = P.bar_count;
+    unsigned long long bar_target = *P.bar_base;
 
-    if (warp == kConsumerWarps) {
-        if (tid == kConsumerThreads) producer_loop<TYPE>(cta, G, n_pos);
+    if (warp == kCW) {
+        if (lane == 0) producer_loop<TYPE>(P, S, cta, G);
         return;
     }
 
     // ---- consumers
-    uint32_t seq = 0;
-    unsigned long long bar_target = base;
-    Best best{-INFINITY, -1};
-    constexpr int kPhWords = (int)(sizeof(PhaseDesc) / 4);
+    const uint32_t ring = smem_u32(&S.ring[0][0]);
+    const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
+    const uint32_t act = smem_u32(S.u);
+    float *part = reinterpret_cast<float *>(S.u + U_PART);
+    int slot = 0;
+    uint32_t parity = 0;
     if (tid < kPhWords) reinterpret_cast<uint32_t *>(&S.ph[0])[tid] = reinterpret_cast<const uint32_t *>(&P.phases[0])[tid];
     consumer_bar();
+#pragma unroll 1
     for (int pi = 0; pi < P.n_phases; pi++) {
-        const PhaseDesc &ph = S.ph[pi & 1];
+        const Phase &ph = S.ph[pi & 1];
         // prefetch the next descriptor; it is published by the barriers at the end of this phase
         if (pi + 1 < P.n_phases && tid < kPhWords)
             reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1])[tid] =
                 reinterpret_cast<const uint32_t *>(&P.phases[pi + 1])[tid];
         long long tr0 = 0, tr1 = 0;
         if (P.trace) tr0 = tr1 = clock64();
-        switch (ph.kind) {
-        case PH_QKV:
-        case PH_LOGITS: {
-            const bool mine = first_unit(ph, cta, G) < ph.n_tiles;
-            const bool write_x0 = (ph.kind == PH_QKV && ph.x_in == nullptr && cta == 0);
-            // LOGITS has rot = 0, so CTA 0 owns tile 0 and also writes the result_norm dump
-            if (mine || write_x0)
-                norm_prologue(pi & 1, token, write_x0, (ph.kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
-            if (P.trace) tr1 = clock64();
-            {
-                const MvRet r = run_matvec<TYPE>(pi & 1, cta, G, seq, true, best);
-                seq = r.seq;
-                best = r.best;
+        const int kind = ph.kind;
+        if (is_matvec(kind)) {
+            int u0, u1;
+            unit_range(cta, G, ph.rot, ph.n_units, u0, u1);
+            const int n_passes = (u1 - u0) * ph.unit_passes;
+            const int ksegs = ph.ksegs, nb = ph.K >> 5;
+            // CTA 0 also writes the x0 (layer-0 embedding row) and result_norm dumps
+            const bool dump0 = cta == 0 && (kind == PH_LOGITS || (kind == PH_QKV && ph.x_in == nullptr));
+            if (n_passes > 0 || dump0) {
+                if (kind == PH_O || kind == PH_DOWN) copy_prologue<TYPE>(S, ph.act_in, ph.K);
+                else
+                    norm_prologue<TYPE>(P, S, ph, token, kind == PH_QKV && ph.x_in == nullptr && cta == 0,
+                                        (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
             }
-            break;
-        }
-        case PH_GATE_UP: {
-            if (first_unit(ph, cta, G) < ph.n_tiles) norm_prologue(pi & 1, token, false, nullptr);
             if (P.trace) tr1 = clock64();
-            seq = run_matvec<TYPE>(pi & 1, cta, G, seq, true, best).seq;
-            break;
-        }
-        case PH_O:
-        case PH_DOWN:
-            {
-                const MvRet r = run_matvec<TYPE>(pi & 1, cta, G, seq, false, best);
-                seq = r.seq;
-                best = r.best;
+            // ---- passes: warp w owns pass w of every slot (Q8_0: 8 passes per slot, warps alternate slots)
+#pragma unroll 1
+            for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
+                const int cnt = min(F::PPS, n_passes - p0);
+                const int j = F::PPS == kCW ? warp : (((warp >> 3) == (i & 1)) ? (warp & 7) : F::PPS);
+                mbar_wait(full0 + 8 * slot, parity);
+                if (j < cnt) {
+                    const int p = p0 + j;
+                    const int pair = p / ksegs, seg = p - pair * ksegs;
+                    const float keep = pass_dot<TYPE>(ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES, act, seg, nb, lane);
+                    if ((lane & 15) == 0) part[(2 * pair + (lane >> 4)) * ksegs + seg] = keep;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+                if (++slot == kSlots) {
+                    slot = 0;
+                    parity ^= 1u;
+                }
             }
-            break;
-        case PH_ATTN:
-            seq = attn_phase(pi & 1, cta, G, seq, n_pos);
-            break;
-        case PH_COMBINE:
-            combine_phase(pi & 1, cta, G, n_pos);
-            break;
-        case PH_SAMPLE: {
-            // per-CTA candidates were published before the previous barrier; CTA 0 picks the first maximum
+            consumer_bar();
+            // ---- epilogue: finish this CTA's rows (segments added in order)
+            const int row0 = u0 * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows;
+            if (kind == PH_GATE_UP) {
+                // GeGLU (fp16 gelu table) + quantize_row_q8_0: one 32-row group per warp, lane = row
+#pragma unroll 1
+                for (int u = warp; u < u1 - u0; u += kCW) {
+                    const float *pg = part + (u * 64 + lane) * ksegs, *pu = pg + 32 * ksegs;
+                    float gsum = pg[0], usum = pu[0];
+                    for (int k = 1; k < ksegs; k++) {
+                        gsum = __fadd_rn(gsum, pg[k]);
+                        usum = __fadd_rn(usum, pu[k]);
+                    }
+                    const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(gsum)]);
+                    const float x = __fmul_rn(gl, usum);
+                    const size_t row = (size_t)(u0 + u) * 32 + lane;
+                    if (ph.f32_out) ph.f32_out[row] = x;
+                    float dd;
+                    const int q = quantize_q8_lane(x, dd);
+                    ((int8_t *)ph.act_out)[row] = (int8_t)q;
+                    if (lane == 0) reinterpret_cast<__half *>(ph.act_out + P.F)[u0 + u] = __float2half_rn(dd);
+                }
+            } else {
+                Best best{-INFINITY, -1};
+                const float *resid = ph.resid;
+#pragma unroll 1
+                for (int r = tid; r < nrows; r += kCT) {
+                    const int grow = row0 + r;
+                    if (grow >= ph.n_rows) break;
+                    float rv = 0.0f;
+                    if (resid) rv = __ldcg(resid + grow);
+                    const float *pp = part + r * ksegs;
+                    float total = pp[0];
+                    for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, pp[k]);
+                    if (resid) total = __fadd_rn(total, rv);
+                    ph.out[grow] = total;
+                    if (total > best.v || best.i < 0) best = Best{total, grow};
+                }
+                if (kind == PH_LOGITS) { // this CTA's arg-max candidate (strict '>' / lowest index, ref: :538-543)
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        Best o;
+                        o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
+                        o.i = __shfl_xor_sync(0xffffffffu, best.i, off);
+                        best = better(best, o);
+                    }
+                    if (lane == 0) {
+                        S.cand_v[warp] = best.v;
+                        S.cand_i[warp] = best.i;
+                    }
+                    consumer_bar();
+                    if (tid == 0) {
+                        Best b{S.cand_v[0], S.cand_i[0]};
+                        for (int w = 1; w < kCW; w++) b = better(b, Best{S.cand_v[w], S.cand_i[w]});
+                        P.cand_v[cta] = b.v;
+                        P.cand_i[cta] = b.i;
+                    }
+                }
+            }
+        } else if (kind == PH_ATTN) {
+            attn_phase<TYPE>(P, S, ph, cta, G, n_pos);
+        } else if (kind == PH_COMBINE) {
+            combine_phase<TYPE>(P, ph, cta, G, n_pos);
+        } else { // PH_SAMPLE: per-CTA candidates were published before the previous barrier
             if (cta == 0 && warp == 0) {
-                const int lane = tid & 31;
                 Best b{-INFINITY, -1};
                 for (int i = lane; i < G; i += 32) b = better(b, Best{__ldcg(P.cand_v + i), __ldcg(P.cand_i + i)});
 #pragma unroll
@@ -909,35 +775,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     if (P.history) P.history[P.state[1]] = b.i;
                 }
             }
-            break;
-        }
-        }
-        if (ph.kind == PH_LOGITS) { // publish this CTA's arg-max candidate (strict '>' / lowest index, ref: :538-543)
-            const int lane = tid & 31;
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                Best o;
-                o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
-                o.i = __shfl_xor_sync(0xffffffffu, best.i, off);
-                best = better(best, o);
-            }
-            if (lane == 0) {
-                S.cand_v[warp] = best.v;
-                S.cand_i[warp] = best.i;
-            }
-            consumer_bar();
-            if (tid == 0) {
-                Best b{S.cand_v[0], S.cand_i[0]};
-                for (int w = 1; w < kConsumerWarps; w++) b = better(b, Best{S.cand_v[w], S.cand_i[w]});
-                P.cand_v[cta] = b.v;
-                P.cand_i[cta] = b.i;
-            }
         }
         long long tr2 = 0;
         if (P.trace) tr2 = clock64();
-        if (ph.kind != PH_SAMPLE) {
+        if (kind != PH_SAMPLE) {
             bar_target += (unsigned long long)G;
-            grid_barrier(bar_count, bar_target);
+            grid_barrier(P.bar_count, bar_target);
         }
         if (P.trace && tid == 0) {
             long long *t = P.trace + ((size_t)pi * G + cta) * 4;
@@ -947,18 +790,78 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     if (cta == 0 && tid == 0) *P.bar_base = bar_target;
 }
 
+// ---------------------------------------------------------------- pass-stream builder
+struct RepackSrc {
+    const uint8_t *qs;
+    const __half *d;
+    int rows;
+};
+struct RepackArgs {
+    RepackSrc m[3];
+    int n_mats;
+    int gate_up; // logical row r: group r / 64, j = r % 64: j < 32 -> m[0] row 32*group + j, else m[1] row 32*group + j - 32
+    int n_rows;  // logical rows
+    int nb, ksegs;
+    uint8_t *dst;
+};
+// one block per pass; thread t < 128 copies block (t & 63) of row (t >> 6)
+template <int TYPE> __global__ void repack_kernel(RepackArgs A) {
+    using F = Fmt<TYPE>;
+    const long long p = blockIdx.x;
+    const int pair = (int)(p / A.ksegs), seg = (int)(p % A.ksegs);
+    const int t = threadIdx.x;
+    if (t >= 128) return;
+    const int r = t >> 6, i = t & 63;
+    const int lr = 2 * pair + r;
+    const int blk = seg * kSeg + i;
+    int mat = 0, row = lr;
+    bool valid = lr < A.n_rows && blk < A.nb;
+    if (A.gate_up) {
+        const int grp = lr / 64, j = lr % 64;
+        mat = j < 32 ? 0 : 1;
+        row = 32 * grp + (j & 31);
+    } else {
+        while (mat + 1 < A.n_mats && row >= A.m[mat].rows) {
+            row -= A.m[mat].rows;
+            mat++;
+        }
+    }
+    uint8_t *pass = A.dst + (size_t)p * F::PASS_BYTES;
+    uint4 *pay = reinterpret_cast<uint4 *>(pass + r * F::ROW_PB + i * F::PB);
+    __half *scl = reinterpret_cast<__half *>(pass + 2 * F::ROW_PB + r * (kSeg * 2)) + i;
+    if (valid) {
+        const size_t b = (size_t)row * A.nb + blk;
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.m[mat].qs + b * F::PB);
+        pay[0] = src[0];
+        if (F::PB == 32) pay[1] = src[1];
+        *scl = A.m[mat].d[b];
+    } else {
+        pay[0] = make_uint4(0, 0, 0, 0);
+        if (F::PB == 32) pay[1] = make_uint4(0, 0, 0, 0);
+        *scl = __float2half(0.0f);
+    }
+}
+
 } // namespace
 
 // ---------------------------------------------------------------- host side
 struct ggb_decoder {
     DecoderParams P{};
-    std::vector<PhaseDesc> phases;
-    PhaseDesc *d_phases = nullptr;
+    std::vector<Phase> phases;
+    std::vector<void *> streams;
+    Phase *d_phases = nullptr;
     void *scratch = nullptr;
     int grid = 0;
     size_t smem = 0;
-    int n_barriers = 0;
+    size_t stream_bytes = 0;
 };
+
+static void decoder_release(ggb_decoder *D) {
+    for (void *s : D->streams) cudaFree(s);
+    cudaFree(D->d_phases);
+    cudaFree(D->scratch);
+    delete D;
+}
 
 extern "C" {
 
@@ -969,9 +872,9 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     const int E = dims->n_embd, L = dims->n_layer, H = dims->n_head, Hkv = dims->n_head_kv, d = dims->head_dim;
     const int F = dims->n_ff, V = dims->n_vocab;
     const int type = token_embd->type;
-    const int PB = ggb_payload_bytes(type);
-    if (!(E % 256 == 0 && E <= kMaxE && (H * d) % 256 == 0 && H * d <= kMaxE && F % 256 == 0 && d % 32 == 0 &&
-          d <= 256 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= kMaxG && F % 32 == 0 && F / 32 * 2 % 16 == 0)) {
+    if (!(E % 256 == 0 && E <= kMaxE && (H * d) % 256 == 0 && H * d <= kMaxE && F % 256 == 0 && F <= kMaxK &&
+          d % 32 == 0 && d <= 256 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= kMaxG &&
+          (type == GGB_TYPE_Q4_0 || type == GGB_TYPE_Q8_0))) {
         ggb_set_error("decoder: shape outside the fused kernel's envelope (E=%d H=%d Hkv=%d d=%d F=%d)", E, H, Hkv, d, F);
         return GGB_ERR_UNSUPPORTED;
     }
@@ -992,12 +895,12 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     D->grid = sms;
-    // scratch: x0 | q | k | v | attn m,l,acc | cand | barrier words | planar activations
+    // scratch: x0 | qkv | attn m,l,acc | cand | barrier words | planar activations
     const size_t QD = (size_t)H * d, KD = (size_t)Hkv * d;
     const size_t act_q_bytes = ggb_q8_row_bytes((int64_t)QD), act_f_bytes = ggb_q8_row_bytes((int64_t)F);
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_x0 = carve((size_t)E * 4), o_q = carve(QD * 4), o_k = carve(KD * 4), o_v = carve(KD * 4);
+    const size_t o_x0 = carve((size_t)E * 4), o_qkv = carve((QD + 2 * KD) * 4);
     const size_t o_m = carve((size_t)H * P.max_chunks * 4), o_l = carve((size_t)H * P.max_chunks * 4);
     const size_t o_acc = carve((size_t)H * P.max_chunks * d * 4);
     const size_t o_cv = carve((size_t)sms * 4), o_ci = carve((size_t)sms * 4), o_bar = carve(16);
@@ -1010,37 +913,55 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     }
     cudaMemsetAsync(D->scratch, 0, off, ggb_cuda_stream());
     uint8_t *sb = (uint8_t *)D->scratch;
-    P.x0 = (float *)(sb + o_x0); P.q = (float *)(sb + o_q); P.k = (float *)(sb + o_k); P.v = (float *)(sb + o_v);
+    P.x0 = (float *)(sb + o_x0); P.qkv = (float *)(sb + o_qkv);
     P.attn_m = (float *)(sb + o_m); P.attn_l = (float *)(sb + o_l); P.attn_acc = (float *)(sb + o_acc);
     P.cand_v = (float *)(sb + o_cv); P.cand_i = (int *)(sb + o_ci);
     P.bar_count = (unsigned long long *)(sb + o_bar); P.bar_base = P.bar_count + 1;
     uint8_t *act_q = sb + o_aq, *act_f = sb + o_af;
 
-    auto fit_rows = [&](int nb, int mats) { // rows per ring slot
-        const int row_bytes = nb * (PB + 2) * mats;
-        int r = kSlotBytes / row_bytes;
-        return r < 1 ? 0 : r;
-    };
-    auto matvec_desc = [&](int kind, int layer, int n, const ggb_weight *const *w, float *const *outs) {
-        PhaseDesc ph{};
-        ph.kind = kind; ph.layer = layer; ph.n_mats = n;
-        ph.nb = (int)w[0]->nb; ph.cols = (int)w[0]->cols;
-        ph.ksegs = (ph.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS;
-        int r = fit_rows(ph.nb, 1);
-        const int rpr = kConsumerWarps / ph.ksegs > 0 ? kConsumerWarps / ph.ksegs : 1;
-        if (r > 2 * kConsumerWarps) r = 2 * kConsumerWarps;
-        if (r >= rpr) r = r / rpr * rpr; // whole rounds of the consumer warps
-        ph.rows_per_tile = r;
-        ph.n_tiles = 0;
+    const int pass_bytes = type == GGB_TYPE_Q4_0 ? Fmt<GGB_TYPE_Q4_0>::PASS_BYTES : Fmt<GGB_TYPE_Q8_0>::PASS_BYTES;
+    bool ok = true;
+    const char *why = "";
+    // builds the pass stream of one mat-vec phase and fills the schedule fields
+    auto matvec_phase = [&](int kind, int layer, int n, const ggb_weight *const *w, bool gate_up) -> Phase {
+        Phase ph{};
+        ph.kind = kind; ph.layer = layer;
+        const int nb = (int)w[0]->nb;
+        ph.K = (int)w[0]->cols;
+        ph.ksegs = (nb + kSeg - 1) / kSeg;
+        RepackArgs A{};
+        A.n_mats = n; A.gate_up = gate_up ? 1 : 0; A.nb = nb; A.ksegs = ph.ksegs;
+        int rows = 0;
         for (int i = 0; i < n; i++) {
-            ph.m[i].qs = w[i]->qs; ph.m[i].d = w[i]->d; ph.m[i].rows = (int)w[i]->rows;
-            ph.m[i].n_tiles = r > 0 ? (int)((w[i]->rows + r - 1) / r) : 0;
-            ph.n_tiles += ph.m[i].n_tiles;
-            ph.out[i] = outs[i];
+            A.m[i].qs = w[i]->qs; A.m[i].d = w[i]->d; A.m[i].rows = (int)w[i]->rows;
+            rows += (int)w[i]->rows;
+            if (w[i]->nb != nb || w[i]->type != type) { ok = false; why = "mixed shapes/types in one phase"; }
+            if (i + 1 < n && !gate_up && (w[i]->rows & 1)) { ok = false; why = "odd row count inside a fused phase"; }
         }
+        ph.n_rows = rows; A.n_rows = rows;
+        const int n_pairs = (rows + 1) / 2;
+        if (gate_up) {
+            ph.n_units = rows / 64; ph.unit_passes = 32 * ph.ksegs; ph.unit_rows = 64;
+            if (rows % 64) { ok = false; why = "n_ff not a multiple of 32"; }
+        } else {
+            ph.n_units = n_pairs; ph.unit_passes = ph.ksegs; ph.unit_rows = 2;
+        }
+        const long long max_units = (ph.n_units + sms - 1) / sms;
+        if (max_units * ph.unit_rows * ph.ksegs > kPartFloats) { ok = false; why = "phase does not fit the partial table"; }
+        if (ph.K > kMaxK) { ok = false; why = "activation row too long"; }
+        if (!ok) return ph;
+        const size_t n_passes = (size_t)n_pairs * ph.ksegs;
+        void *stream = nullptr;
+        cudaError_t ce = cudaMalloc(&stream, n_passes * pass_bytes);
+        if (ce != cudaSuccess) { ok = false; why = "pass stream cudaMalloc failed"; return ph; }
+        D->streams.push_back(stream);
+        D->stream_bytes += n_passes * pass_bytes;
+        A.dst = (uint8_t *)stream;
+        if (type == GGB_TYPE_Q4_0) repack_kernel<GGB_TYPE_Q4_0><<<(unsigned)n_passes, 128, 0, ggb_cuda_stream()>>>(A);
+        else repack_kernel<GGB_TYPE_Q8_0><<<(unsigned)n_passes, 128, 0, ggb_cuda_stream()>>>(A);
+        ph.stream = (const uint8_t *)stream;
         return ph;
     };
-    bool ok = true;
     for (int il = 0; il < L && ok; il++) {
         const ggb_decoder_layer &ly = layers[il];
         const float *x_in = il == 0 ? nullptr : io->l_out + (size_t)(il - 1) * E;
@@ -1048,89 +969,70 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         float *sa = io->sa_out + (size_t)il * E, *lo = io->l_out + (size_t)il * E;
         {   // QKV
             const ggb_weight *w[3] = {ly.attn_q, ly.attn_k, ly.attn_v};
-            float *o[3] = {P.q, P.k, P.v};
-            PhaseDesc ph = matvec_desc(PH_QKV, il, 3, w, o);
-            ph.x_in = x_in; ph.norm_w = ly.attn_norm;
-            ok = ok && ph.rows_per_tile > 0 && ph.ksegs <= kConsumerWarps;
+            Phase ph = matvec_phase(PH_QKV, il, 3, w, false);
+            ph.x_in = x_in; ph.norm_w = ly.attn_norm; ph.out = P.qkv;
+            if (ph.K != E) { ok = false; why = "attn_q input width != n_embd"; }
             D->phases.push_back(ph);
         }
         {   // ATTN
-            PhaseDesc ph{};
+            Phase ph{};
             ph.kind = PH_ATTN; ph.layer = il; ph.kcache = (__half *)ly.k_cache; ph.vcache = (__half *)ly.v_cache;
             D->phases.push_back(ph);
         }
         {   // COMBINE
-            PhaseDesc ph{};
+            Phase ph{};
             ph.kind = PH_COMBINE; ph.layer = il; ph.act_out = act_q; ph.f32_out = io->kqv + (size_t)il * QD;
             D->phases.push_back(ph);
         }
         {   // O + residual
             const ggb_weight *w[1] = {ly.attn_output};
-            float *o[1] = {sa};
-            PhaseDesc ph = matvec_desc(PH_O, il, 1, w, o);
-            ph.act_in = act_q; ph.resid = x_res;
-            ok = ok && ph.rows_per_tile > 0;
+            Phase ph = matvec_phase(PH_O, il, 1, w, false);
+            ph.act_in = act_q; ph.resid = x_res; ph.out = sa;
             D->phases.push_back(ph);
         }
         {   // GATE_UP
-            PhaseDesc ph{};
-            ph.kind = PH_GATE_UP; ph.layer = il; ph.n_mats = 2;
-            ph.nb = (int)ly.ffn_gate->nb; ph.cols = (int)ly.ffn_gate->cols;
-            ph.ksegs = (ph.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS;
-            ph.m[0].qs = ly.ffn_gate->qs; ph.m[0].d = ly.ffn_gate->d; ph.m[0].rows = F;
-            ph.m[1].qs = ly.ffn_up->qs; ph.m[1].d = ly.ffn_up->d; ph.m[1].rows = F;
-            int r = fit_rows(ph.nb, 2);
-            if (r > kConsumerWarps) r = kConsumerWarps;
-            if (r > 8 && r < kConsumerWarps) r = 8;
-            ph.rows_per_tile = r;
-            ph.n_tiles = F / 32;
+            const ggb_weight *w[2] = {ly.ffn_gate, ly.ffn_up};
+            Phase ph = matvec_phase(PH_GATE_UP, il, 2, w, true);
             ph.x_in = sa; ph.norm_w = ly.ffn_norm; ph.act_out = act_f;
             ph.f32_out = io->ffn_act ? io->ffn_act + (size_t)il * F : nullptr;
-            ok = ok && r > 0 && ph.ksegs <= kConsumerWarps;
             D->phases.push_back(ph);
         }
         {   // DOWN + residual
             const ggb_weight *w[1] = {ly.ffn_down};
-            float *o[1] = {lo};
-            PhaseDesc ph = matvec_desc(PH_DOWN, il, 1, w, o);
-            ph.act_in = act_f; ph.resid = sa;
-            ok = ok && ph.rows_per_tile > 0 && ph.ksegs <= kConsumerWarps;
+            Phase ph = matvec_phase(PH_DOWN, il, 1, w, false);
+            ph.act_in = act_f; ph.resid = sa; ph.out = lo;
             D->phases.push_back(ph);
         }
     }
-    {   // LOGITS (tied embedding) + SAMPLE
+    if (ok) {   // LOGITS (tied embedding) + SAMPLE
         const ggb_weight *w[1] = {token_embd};
-        float *o[1] = {io->logits};
-        PhaseDesc ph = matvec_desc(PH_LOGITS, L, 1, w, o);
+        Phase ph = matvec_phase(PH_LOGITS, L, 1, w, false);
         ph.x_in = io->l_out + (size_t)(L - 1) * E; ph.norm_w = output_norm; ph.f32_out = io->result_norm;
-        ok = ok && ph.rows_per_tile > 0 && ph.ksegs <= kConsumerWarps;
+        ph.out = io->logits;
         D->phases.push_back(ph);
-        PhaseDesc sp{};
+        Phase sp{};
         sp.kind = PH_SAMPLE; sp.layer = L;
         D->phases.push_back(sp);
     }
     if (!ok) {
-        ggb_set_error("decoder: a weight row does not fit the ring slot (%d B) for this shape", kSlotBytes);
-        cudaFree(D->scratch);
-        delete D;
+        ggb_set_error("decoder: %s", why);
+        cudaStreamSynchronize(ggb_cuda_stream());
+        decoder_release(D);
         return GGB_ERR_UNSUPPORTED;
     }
     for (size_t i = 0; i < D->phases.size(); i++) D->phases[i].rot = (int)((i * 61) % (size_t)sms);
-    D->phases[D->phases.size() - 2].rot = 0; // LOGITS: result_norm dump is written by the CTA owning tile 0
-    D->n_barriers = (int)D->phases.size() - 1;
-    e = cudaMalloc(&D->d_phases, D->phases.size() * sizeof(PhaseDesc));
+    e = cudaMalloc(&D->d_phases, D->phases.size() * sizeof(Phase));
     if (e == cudaSuccess)
-        e = cudaMemcpyAsync(D->d_phases, D->phases.data(), D->phases.size() * sizeof(PhaseDesc), cudaMemcpyHostToDevice,
+        e = cudaMemcpyAsync(D->d_phases, D->phases.data(), D->phases.size() * sizeof(Phase), cudaMemcpyHostToDevice,
                             ggb_cuda_stream());
     if (e != cudaSuccess) {
         ggb_set_error("decoder phase table upload -> %s", cudaGetErrorString(e));
-        cudaFree(D->scratch);
-        delete D;
+        decoder_release(D);
         return GGB_ERR_CUDA;
     }
     P.phases = D->d_phases;
     P.n_phases = (int)D->phases.size();
-    D->smem = sizeof(SmemLayout);
+    D->smem = type == GGB_TYPE_Q4_0 ? sizeof(Smem<GGB_TYPE_Q4_0>) : sizeof(Smem<GGB_TYPE_Q8_0>);
     const void *fn = type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
                                            : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem);
@@ -1139,12 +1041,16 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     if (e != cudaSuccess || occ < 1) {
         ggb_set_error("decoder kernel cannot be resident (smem %zu B): %s", D->smem,
                       e != cudaSuccess ? cudaGetErrorString(e) : "occupancy 0");
-        cudaFree(D->d_phases);
-        cudaFree(D->scratch);
-        delete D;
+        decoder_release(D);
         return GGB_ERR_CUDA;
     }
-    GGB_CUDA(cudaStreamSynchronize(ggb_cuda_stream()));
+    e = cudaStreamSynchronize(ggb_cuda_stream());
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ggb_set_error("decoder pass-stream build -> %s", cudaGetErrorString(e));
+        decoder_release(D);
+        return GGB_ERR_CUDA;
+    }
     *out = D;
     return GGB_OK;
 }
@@ -1160,26 +1066,20 @@ int ggb_decoder_step(ggb_decoder *D) {
     return GGB_OK;
 }
 
-// one traced step: per phase and CTA four SM-clock stamps (start, after prologue, after tiles, after
+// one traced step: per phase and CTA four SM-clock stamps (start, after prologue, after the work, after
 // the grid barrier) plus the phase kinds; the cudaEvent/ncu numbers say how long, this says where.
 int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(D && stamps && kinds && n_phases && grid, "null pointer");
     const int np = (int)D->phases.size();
     GGB_CHECK_ARG(max_phases >= np, "trace buffer holds %d phases, need %d", max_phases, np);
-    // stamps: [np][grid][4] phase stamps followed by [grid][32][3] LOGITS tile stamps
-    const size_t bytes1 = (size_t)np * D->grid * 4 * sizeof(long long);
-    const size_t bytes2 = (size_t)D->grid * 32 * 3 * sizeof(long long);
-    const size_t bytes = bytes1 + bytes2 + (size_t)D->grid * 8 * sizeof(long long);
-    GGB_CHECK_ARG((size_t)max_phases * D->grid * 4 * sizeof(long long) >= bytes, "trace buffer too small");
+    const size_t bytes = (size_t)np * D->grid * 4 * sizeof(long long);
     long long *dev = nullptr;
     GGB_CUDA(cudaMalloc(&dev, bytes));
     GGB_CUDA(cudaMemsetAsync(dev, 0, bytes, ggb_cuda_stream()));
     D->P.trace = dev;
-    D->P.trace2 = dev + bytes1 / sizeof(long long);
     int rc = ggb_decoder_step(D);
     D->P.trace = nullptr;
-    D->P.trace2 = nullptr;
     if (rc == GGB_OK) {
         cudaError_t e = cudaMemcpyAsync(stamps, dev, bytes, cudaMemcpyDeviceToHost, ggb_cuda_stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(ggb_cuda_stream());
@@ -1198,9 +1098,7 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
 int ggb_decoder_free(ggb_decoder *D) {
     if (!D) return GGB_OK;
     cudaStreamSynchronize(ggb_cuda_stream());
-    cudaFree(D->d_phases);
-    cudaFree(D->scratch);
-    delete D;
+    decoder_release(D);
     return GGB_OK;
 }
 
