@@ -1,9 +1,9 @@
-// decoder.cu — the persistent decode kernel: ONE cooperative launch per token (v2: pass-stream design).
+// decoder.cu — the persistent decode kernel: ONE cooperative launch per token (v3: pass stream + flagged data flow).
 //
 // Why: a Gemma-2B Q4_0 token is 1.41 GB of weights + 38 MB of KV = ~220 us of HBM time on a B200, spread
 // over 163 mat-vecs and ~450 small nodes (ref: src/gemma_model.cpp:688-740).  One CTA per SM stays resident
 // for the whole token; what limits it is (a) how cleanly the weights stream and (b) what every phase change
-// costs.  Design rules, each measured (tools/ubench_stream.cu, tools_trace.py):
+// costs.  Design rules, each measured (tools/ubench_stream.cu, tools/ubench_bar.cu, tools_trace.py):
 //
 //   * PASS STREAM.  At create time every weight matrix is re-laid out as a stream of PASSES: one pass =
 //     two rows x one 64-block K segment (2304 B Q4_0 / 4352 B Q8_0), payloads then scales, i.e. exactly what
@@ -11,19 +11,24 @@
 //     share of a phase is ONE contiguous byte range and the producer is a trivial loop of bulk copies.
 //   * PRODUCER = lane 0 of warp 16: cp.async.bulk (TMA, SASS UBLKCP) of up to 16 passes (36 KB) per ring slot,
 //     5 slots, completion on mbarriers.  Weights do not depend on activations, so it runs AHEAD across phase
-//     boundaries: while consumers sit in a grid barrier or a prologue, HBM keeps streaming.
+//     boundaries: while consumers wait for their inputs, HBM keeps streaming.
 //   * CONSUMERS = 16 warps.  Warp w owns pass w of every slot: 4 x LDS.128 weights + the two activation
 //     blocks of its segment from shared memory, dp4a, the scalar reference's per-block fp32 term, a folded
 //     xor-butterfly for the two rows.  Segment sums go to a shared-memory partial table; ONE block barrier per
 //     phase, then an epilogue finishes rows (segments in order, residual, GeGLU + Q8_0, arg-max).
 //     The stand-alone loop sustains 6.0-6.2 TB/s of 6.6 TB/s read peak (tools/ubench_stream.cu).
+//   * NO GRID BARRIERS.  A grid barrier costs 1.4 us on B200 (0.6 us of it the release fence,
+//     tools/ubench_bar.cu) and a token has 108 phase changes.  Instead every value that crosses CTAs travels
+//     as an 8-byte word {payload, tag} written with one store (the NCCL "LL" idea): tag = the token's sequence
+//     number, the buffers are per layer, and a consumer simply re-reads a word until its tag matches.  Data
+//     and flag arrive together, so no fence and no separate wait: a phase change costs one L2 write + one L2
+//     read.  Each phase's prologue polls exactly the inputs it needs.
 //   * SMALL CODE.  The 32 KB instruction cache holds ~2000 SASS instructions and a persistent kernel runs
 //     each phase's code once per layer: every mat-vec phase shares one pass loop, prologues and epilogues are
 //     short and not unrolled.
-//   * phases are separated by a grid barrier (monotonic 64-bit counter in global memory).
 //
 // Phases per layer: QKV | ATTN (split-K partials; rope, Q scale and the KV-cache store of the new position
-// folded in) | COMBINE (+ Q8_0 quantise) | O (+ residual) | GATE_UP (+ GeGLU + quantise) | DOWN (+ residual);
+// folded in) | COMBINE | O (+ residual) | GATE_UP (+ GeGLU + Q8_0 quantise) | DOWN (+ residual);
 // then LOGITS (+ per-CTA arg-max) | SAMPLE.
 // Numerics are bit-identical to the per-operator kernels (same DEV order; tests compare both and the oracle).
 #include <vector>
@@ -42,6 +47,7 @@ constexpr int kMaxG = 8;
 constexpr int kMaxE = 4096;         // longest norm-fed activation row
 constexpr int kMaxK = 24576;        // longest activation row kept in shared memory
 constexpr int kPartFloats = 2048;   // partial table: (rows of this CTA in a phase) x (K segments)
+constexpr int kMaxChunks = 256;     // split-K chunks per head the COMBINE staging holds (n_ctx <= 8192)
 
 enum PhaseKind { PH_QKV = 0, PH_ATTN, PH_COMBINE, PH_O, PH_GATE_UP, PH_DOWN, PH_LOGITS, PH_SAMPLE };
 
@@ -53,6 +59,8 @@ template <int TYPE> struct Fmt {
     static constexpr int SLOT_BYTES = PPS * PASS_BYTES;                // 36864 / 34816
 };
 
+typedef unsigned long long ll_t; // flagged word: low 32 bits payload, high 32 bits tag
+
 struct Phase {
     int kind, layer;
     int n_units;     // schedulable units (row pairs; GATE_UP: 32-row groups of gate + up)
@@ -62,16 +70,18 @@ struct Phase {
     int K;           // activation length
     int n_rows;      // logical rows of the phase
     int rot;         // CTA rotation so remainders do not always land on the same SMs
-    int pad_;
-    const uint8_t *stream;  // pass stream of the phase
-    const float *x_in;      // fp32 input of a norm-fed phase (null in layer 0: embedding row)
+    int resid_embed; // residual = embedding row of the token (layer 0, O phase)
+    const uint8_t *stream; // pass stream of the phase
+    // flagged inputs: QKV / GATE_UP / LOGITS: fp32 x [E] (null in layer 0: embedding row); O: fp32 kqv [H*d];
+    // DOWN: packed Q8_0 (4 codes per word) [F/4] then fp16 scales [F/32]; ATTN: fp32 q | k | v
+    const ll_t *in_ll;
     const float *norm_w;
-    const uint8_t *act_in;  // planar Q8_0 input (O, DOWN)
-    float *out;
-    const float *resid;
-    uint8_t *act_out;       // planar Q8_0 output (COMBINE, GATE_UP)
-    float *f32_out;         // COMBINE: kqv; GATE_UP: optional ffn_act dump; LOGITS: result_norm
+    ll_t *out_ll;          // flagged output (QKV: qkv; O: sa; DOWN: next layer's x; GATE_UP: packed Q8_0; COMBINE: kqv)
+    float *out;            // plain fp32 copy for tensor_dump-style captures / logits (may be null)
+    const ll_t *resid_ll;  // flagged residual
+    float *f32_out;        // COMBINE: kqv dump; GATE_UP: optional ffn_act dump; LOGITS: result_norm
     __half *kcache, *vcache;
+    ll_t *acc_ll, *m_ll, *l_ll; // ATTN -> COMBINE split-K partials of this layer
 };
 static_assert(sizeof(Phase) % 4 == 0, "Phase is copied word-wise");
 constexpr int kPhWords = (int)(sizeof(Phase) / 4);
@@ -84,31 +94,30 @@ struct DecoderParams {
     float eps, q_scale, emb_scale;
     const uint8_t *emb_qs; // planar embedding table (layer-0 get_rows)
     const __half *emb_d;
-    float *x0;
     int32_t *state, *history;
-    float *qkv; // fp32 Q | K | V of the current token
-    float *attn_m, *attn_l, *attn_acc;
     int max_chunks;
-    float *cand_v;
-    int *cand_i;
-    unsigned long long *bar_count, *bar_base;
+    ll_t *cand_ll;         // [2][grid]: per-CTA arg-max candidates (value, index)
+    uint32_t *seq;         // token sequence number = tag of the previous launch
     const uint16_t *exp_table, *gelu_table;
     const float *rope_cos, *rope_sin;
-    long long *trace; // optional [n_phases][grid][4] SM-clock stamps: start, after prologue, after work, after barrier
+    long long *trace; // optional [n_phases][grid][4] SM-clock stamps: start, after prologue (inputs arrived), after work, end
 };
 
 // union region: the views are never live at the same time
 //   mat-vec : act_q [kMaxK] | act_d half[kMaxK/32] | bias int[kMaxK/32] | part float[kPartFloats]
 //   norm    : xs float[kMaxE] at +8192 (act_q only uses [0, kMaxE) in a norm-fed phase)
 //   attn    : Kc half[32][256] | Vc half[32][256] | Sq half[8][256] | s float[8][32] | e float[8][32]
+//   combine : stage float[kMaxChunks][32] | m float[kMaxChunks] | l float[kMaxChunks] | w float[kMaxChunks]
 constexpr int U_ACT_D = kMaxK;
 constexpr int U_BIAS = U_ACT_D + kMaxK / 32 * 2;
 constexpr int U_PART = U_BIAS + kMaxK / 32 * 4;
 constexpr int U_XS = 8192;
 constexpr int U_KC = 0, U_VC = 16384, U_SQ = 32768, U_S = 36864, U_E = 37888;
+constexpr int U_CM = kMaxChunks * 128, U_CL = U_CM + kMaxChunks * 4, U_CW = U_CL + kMaxChunks * 4;
 constexpr int U_BYTES = 38912;
 static_assert(U_PART + kPartFloats * 4 <= U_BYTES, "union region too small");
 static_assert(U_XS + kMaxE * 4 <= U_ACT_D && kMaxE <= U_XS, "xs overlaps the activation row");
+static_assert(U_CW + kMaxChunks * 4 <= U_BYTES, "combine staging too large");
 
 template <int TYPE> struct Smem {
     alignas(1024) uint8_t ring[kSlots][Fmt<TYPE>::SLOT_BYTES];
@@ -145,7 +154,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// async copy global -> shared through L2 only (.cg): data written by other CTAs of this kernel
+// async copy global -> shared through L2 only (.cg)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -174,23 +183,23 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) { // unsigned b
     return d;
 }
 
-// Grid barrier over the consumer threads of all CTAs: bar.sync orders the CTA's writes before thread 0's
-// release-add on ONE monotonic counter; thread 0 polls it (relaxed: an acquire load costs an L1 invalidate per
-// poll).  Every read of another CTA's data after a barrier is an L2 access (__ldcg / cp.async.cg / TMA), never
-// an L1-cached load, and the writers released at gpu scope.  Measured (tools/ubench_bar.cu): 1.4 us, of which
-// 0.6 us is the release fence; per-CTA flag arrays (3.7 us packed, 1.5 us padded) and counter trees (2.5 us)
-// are slower on B200.
-__device__ __forceinline__ void grid_barrier(unsigned long long *count, unsigned long long target) {
-    consumer_bar();
-    if (threadIdx.x == 0) {
-        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(count), "l"(1ull) : "memory");
-        unsigned long long v;
-        do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(count) : "memory");
-        } while (v < target);
-    }
-    consumer_bar();
+// ---- flagged words.  An aligned 8-byte access is single-copy atomic, so payload and tag are seen together;
+// relaxed gpu-scope accesses go to L2 (never a stale L1 line).  ll_get = the word if its tag matches, else poll.
+__device__ __forceinline__ void ll_put(ll_t *p, uint32_t payload, uint32_t tag) {
+    const ll_t v = ((ll_t)tag << 32) | payload;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void ll_put_f(ll_t *p, float x, uint32_t tag) { ll_put(p, __float_as_uint(x), tag); }
+__device__ __forceinline__ ll_t ll_peek(const ll_t *p) {
+    ll_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ll_get(ll_t v, const ll_t *p, uint32_t tag) {
+    while ((uint32_t)(v >> 32) != tag) v = ll_peek(p);
+    return (uint32_t)v;
+}
+__device__ __forceinline__ float ll_get_f(ll_t v, const ll_t *p, uint32_t tag) { return __uint_as_float(ll_get(v, p, tag)); }
 
 struct Best {
     float v;
@@ -212,6 +221,21 @@ __device__ __forceinline__ void unit_range(int cta, int G, int rot, int n_units,
 
 __device__ __forceinline__ bool is_matvec(int kind) {
     return kind == PH_QKV || kind == PH_O || kind == PH_GATE_UP || kind == PH_DOWN || kind == PH_LOGITS;
+}
+
+// get_rows(token_embd, token)[i] * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
+template <int TYPE> __device__ __forceinline__ float embed_value(const DecoderParams &P, int token, int i) {
+    const size_t blk = (size_t)token * (P.E / 32) + (i >> 5);
+    const int e = i & 31;
+    const float dd = __half2float(P.emb_d[blk]);
+    int qv;
+    if (TYPE == GGB_TYPE_Q4_0) {
+        const int byte = P.emb_qs[blk * 16 + (e & 15)];
+        qv = (e < 16 ? (byte & 0x0F) : (byte >> 4)) - 8;
+    } else {
+        qv = ((const int8_t *)P.emb_qs)[blk * 32 + e];
+    }
+    return __fmul_rn(__fmul_rn((float)qv, dd), P.emb_scale);
 }
 
 // ---------------------------------------------------------------- producer
@@ -248,93 +272,120 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
     }
 }
 
-// ---------------------------------------------------------------- prologues
-// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input into the shared activation row; every CTA
-// recomputes it (8 KB from L2) instead of making it a phase of its own.  Sum of squares in the DEV order:
-// threads 0..255 hold the strided double partials, butterfly, warps in order.
+// ---------------------------------------------------------------- prologues (each ends with the activation row in
+// shared memory: act_q int8[K], act_d fp16[K/32], bias int[K/32] = -8 * sum of the block's codes)
+
+// quantize_row_q8_0 of one 32-element block spread over a warp (lane = element) into the shared row
+__device__ __forceinline__ void quant_block_to_smem(uint8_t *u, int b, int lane, float v) {
+    float d;
+    const int q = quantize_q8_lane(v, d);
+    reinterpret_cast<int8_t *>(u)[32 * b + lane] = (int8_t)q;
+    const int qs = __reduce_add_sync(0xffffffffu, q);
+    if (lane == 0) {
+        reinterpret_cast<__half *>(u + U_ACT_D)[b] = __float2half_rn(d);
+        reinterpret_cast<int *>(u + U_BIAS)[b] = -8 * qs;
+    }
+}
+
+// rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input; every CTA recomputes it (16 KB of flagged
+// words from L2) instead of making it a phase of its own.  Sum of squares in the DEV order: 256 strided double
+// partials (partial t = elements t, t + 256, ...), butterfly per warp, the 8 warp sums in order.  Thread
+// (warp w, lane l) loads exactly the elements of partial 32 * (w & 7) + l, so both warp halves hold the
+// partials in registers and no staging pass is needed; the halves then split the quantisation by blocks.
 template <int TYPE>
 __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
-                                              bool write_x0, float *f32_out) {
+                                              uint32_t tag, float *f32_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int E = P.E;
+    const int E = P.E, nk = E / GGB_DEV_NORM_THREADS;
+    const int base = 32 * (warp & 7) + lane;
     float *xs = reinterpret_cast<float *>(S.u + U_XS);
-    const float *x_in = ph.x_in, *norm_w = ph.norm_w;
-    if (x_in) {
-        const uint32_t xs_addr = smem_u32(xs);
-        for (int v = tid; v < E / 4; v += kCT) cp_async16(xs_addr + 16u * v, x_in + 4 * v);
-        cp_async_wait_all();
-    } else {
-        // layer 0: get_rows(token_embd, token) * sqrt(n_embd)   (ref: src/gemma_model.cpp:675-679)
-        const int nb = E / 32;
-        const size_t blk0 = (size_t)token * nb;
-        for (int i = tid; i < E; i += kCT) {
-            const int b = i >> 5, e = i & 31;
-            const float dd = __half2float(P.emb_d[blk0 + b]);
-            int qv;
-            if (TYPE == GGB_TYPE_Q4_0) {
-                const int byte = P.emb_qs[(blk0 + b) * 16 + (e & 15)];
-                qv = (e < 16 ? (byte & 0x0F) : (byte >> 4)) - 8;
-            } else {
-                qv = ((const int8_t *)P.emb_qs)[(blk0 + b) * 32 + e];
+    const ll_t *in = ph.in_ll;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < nk; k0 += 4) {
+        ll_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (in && k0 + u < nk) v[u] = ll_peek(in + GGB_DEV_NORM_THREADS * (k0 + u) + base);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (k0 + u < nk) {
+                const int i = GGB_DEV_NORM_THREADS * (k0 + u) + base;
+                const float x = in ? ll_get_f(v[u], in + i, tag) : embed_value<TYPE>(P, token, i);
+                xs[i] = x;
+                acc = __dadd_rn(acc, (double)__fmul_rn(x, x));
             }
-            xs[i] = __fmul_rn(__fmul_rn((float)qv, dd), P.emb_scale);
         }
     }
-    consumer_bar();
-    if (tid < GGB_DEV_NORM_THREADS) {
-        double acc = 0.0;
-#pragma unroll 4
-        for (int i = tid; i < E; i += GGB_DEV_NORM_THREADS) {
-            const float v = xs[i];
-            acc = __dadd_rn(acc, (double)__fmul_rn(v, v));
-        }
-        acc = warp_sum_f64(acc);
-        if (lane == 0) S.red[warp] = acc;
-    }
+    acc = warp_sum_f64(acc);
+    if (warp < 8 && lane == 0) S.red[warp] = acc;
     consumer_bar();
     double sum = S.red[0];
 #pragma unroll
     for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
     const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-    int8_t *act_q = reinterpret_cast<int8_t *>(S.u);
-    __half *act_d = reinterpret_cast<__half *>(S.u + U_ACT_D);
-    int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
+    const float *norm_w = ph.norm_w;
 #pragma unroll 2
-    for (int b = warp; b < E / 32; b += kCW) { // one Q8_0 block (32 consecutive elements) per warp per iteration
-        const int i = 32 * b + lane;
-        const float x = xs[i];
-        const float v = __fmul_rn(__fmul_rn(x, scale), norm_w[i]);
-        if (write_x0) P.x0[i] = x;
+    for (int k = warp >> 3; k < nk; k += 2) { // block 8k + (w & 7): elements written by this very thread above
+        const int i = GGB_DEV_NORM_THREADS * k + base;
+        const float v = __fmul_rn(__fmul_rn(xs[i], scale), norm_w[i]);
         if (f32_out) f32_out[i] = v;
-        float d;
-        const int q = quantize_q8_lane(v, d);
-        act_q[i] = (int8_t)q;
-        const int qs = __reduce_add_sync(0xffffffffu, q);
-        if (lane == 0) {
-            act_d[b] = __float2half_rn(d);
-            bias[b] = -8 * qs;
+        quant_block_to_smem(S.u, i >> 5, lane, v);
+    }
+    consumer_bar();
+}
+
+// O: the flagged fp32 row written by COMBINE -> quantize_row_q8_0 (ggml mul_mat INIT stage)
+template <int TYPE>
+__device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbk = K / 32;
+#pragma unroll 1
+    for (int b0 = warp; b0 < nbk; b0 += 4 * kCW) {
+        ll_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (b0 + kCW * u < nbk) v[u] = ll_peek(in + 32 * (b0 + kCW * u) + lane);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int b = b0 + kCW * u;
+            if (b < nbk) quant_block_to_smem(S.u, b, lane, ll_get_f(v[u], in + 32 * b + lane, tag));
         }
     }
     consumer_bar();
 }
 
-// planar Q8_0 row produced by other CTAs (COMBINE, GATE_UP) -> shared activation row + per-block bias
+// DOWN: packed Q8_0 row written by GATE_UP (4 codes per flagged word, then the fp16 scales)
 template <int TYPE>
-__device__ __forceinline__ void copy_prologue(Smem<TYPE> &S, const uint8_t *act_in, int K) {
+__device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
     const int tid = threadIdx.x;
-    const uint32_t q_addr = smem_u32(S.u), d_addr = smem_u32(S.u + U_ACT_D);
-    for (int v = tid; v < K / 16; v += kCT) cp_async16(q_addr + 16u * v, act_in + 16 * v);
-    for (int v = tid; v < K / 256; v += kCT) cp_async16(d_addr + 16u * v, act_in + K + 16 * v);
-    cp_async_wait_all();
+    const int nw = K / 4, ns = K / 32;
+    uint32_t *aq = reinterpret_cast<uint32_t *>(S.u);
+    __half *ad = reinterpret_cast<__half *>(S.u + U_ACT_D);
+#pragma unroll 1
+    for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) {
+        ll_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i0 + kCT * u < nw + ns) v[u] = ll_peek(in + i0 + kCT * u);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + kCT * u;
+            if (i < nw + ns) {
+                const uint32_t w = ll_get(v[u], in + i, tag);
+                if (i < nw) aq[i] = w;
+                else ad[i - nw] = __ushort_as_half((unsigned short)w);
+            }
+        }
+    }
     consumer_bar();
     if (TYPE == GGB_TYPE_Q4_0) {
-        const int *aq = reinterpret_cast<const int *>(S.u);
         int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
-        for (int b = tid; b < K / 32; b += kCT) {
+        for (int b = tid; b < ns; b += kCT) {
             int s = 0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) s = __dp4a(aq[8 * b + i], 0x01010101, s);
+            for (int i = 0; i < 8; i++) s = __dp4a((int)aq[8 * b + i], 0x01010101, s);
             bias[b] = -8 * s;
         }
         consumer_bar();
@@ -407,10 +458,11 @@ __device__ __forceinline__ float pass_dot(uint32_t base, uint32_t act, int seg, 
 // ---------------------------------------------------------------- ATTN
 // items (kv head g, chunk of 32 positions).  Same arithmetic as attention.cu attn_partial_kernel; rope + Q
 // scale are applied to q on load, and the item that owns the newest position ropes K, rounds K/V to fp16,
-// stores them in the cache and uses them.
+// stores them in the cache and uses them.  The K/V rows of older positions do not depend on this token: their
+// copies are in flight while the CTA still waits for q.
 template <int TYPE>
 __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                           int n_pos) {
+                                           int n_pos, uint32_t tag) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, halfd = d / 2, Hkv = P.Hkv, Gq = P.H / Hkv;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
@@ -418,7 +470,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     const int pos = n_pos - 1;
     const size_t kv_stride = (size_t)Hkv * d;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
-    const float *q_all = P.qkv, *k_all = P.qkv + (size_t)P.H * d, *v_all = k_all + (size_t)Hkv * d;
+    const ll_t *q_all = ph.in_ll, *k_all = q_all + (size_t)P.H * d, *v_all = k_all + (size_t)Hkv * d;
     __half *Kc = reinterpret_cast<__half *>(S.u + U_KC), *Vc = reinterpret_cast<__half *>(S.u + U_VC);
     __half *Sq = reinterpret_cast<__half *>(S.u + U_SQ);
     float(*Ss)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_S);
@@ -443,9 +495,10 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
         for (int i = tid; i < Gq * halfd; i += kCT) {
             const int jh = i / halfd, e = i % halfd;
-            const float *qh = q_all + (size_t)(h0 + jh) * d;
-            const float x0 = __ldcg(qh + e), x1 = __ldcg(qh + e + halfd);
+            const ll_t *qh = q_all + (size_t)(h0 + jh) * d;
+            const ll_t w0 = ll_peek(qh + e), w1 = ll_peek(qh + e + halfd);
             const float cs = cosr[e], sn = sinr[e];
+            const float x0 = ll_get_f(w0, qh + e, tag), x1 = ll_get_f(w1, qh + e + halfd, tag);
             const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
             const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
             Sq[jh * d + e] = __float2half_rn(r0);
@@ -453,8 +506,10 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         }
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
             for (int e = tid; e < halfd; e += kCT) {
-                const float x0 = __ldcg(k_all + (size_t)g * d + e), x1 = __ldcg(k_all + (size_t)g * d + e + halfd);
+                const ll_t *kp = k_all + (size_t)g * d + e;
+                const ll_t w0 = ll_peek(kp), w1 = ll_peek(kp + halfd);
                 const float cs = cosr[e], sn = sinr[e];
+                const float x0 = ll_get_f(w0, kp, tag), x1 = ll_get_f(w1, kp + halfd, tag);
                 const __half k0 = __float2half_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)));
                 const __half k1 = __float2half_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)));
                 Kc[jnew * d + e] = k0;
@@ -464,7 +519,8 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                 krow[e + halfd] = k1;
             }
             for (int e = tid; e < d; e += kCT) {
-                const __half vv = __float2half_rn(__ldcg(v_all + (size_t)g * d + e));
+                const ll_t *vp = v_all + (size_t)g * d + e;
+                const __half vv = __float2half_rn(ll_get_f(ll_peek(vp), vp, tag));
                 Vc[jnew * d + e] = vv;
                 ph.vcache[((size_t)pos * Hkv + g) * d + e] = vv;
             }
@@ -527,8 +583,8 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             const float l = warp_sum_f32(e);
             Se[warp][lane] = e;
             if (lane == 0) {
-                P.attn_m[(size_t)(h0 + warp) * P.max_chunks + c] = m;
-                P.attn_l[(size_t)(h0 + warp) * P.max_chunks + c] = l;
+                ll_put_f(ph.m_ll + (size_t)(h0 + warp) * P.max_chunks + c, m, tag);
+                ll_put_f(ph.l_ll + (size_t)(h0 + warp) * P.max_chunks + c, l, tag);
             }
         }
         consumer_bar();
@@ -558,8 +614,9 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                 for (int u = 0; u < kMaxG / kHG; u++) {
                     const int jh = kHG * u + hs;
                     if (jh < Gq) {
-                        float *out = P.attn_acc + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
-                        *reinterpret_cast<float2 *>(out) = make_float2(a0[u], a1[u]);
+                        ll_t *out = ph.acc_ll + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
+                        ll_put_f(out, a0[u], tag);
+                        ll_put_f(out + 1, a1[u], tag);
                     }
                 }
             }
@@ -568,53 +625,64 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     }
 }
 
-// COMBINE: one warp per (head, 32-dim slice), lane = dim: M = max m_c; w_c = exp_table[f16(m_c - M)];
-// L = sum l_c*w_c; O = sum acc_c*w_c (sequential in c); out = O / L; the slice is one Q8_0 block.
+// COMBINE: one CTA per (head, 32-dim slice): M = max m_c; w_c = exp_table[f16(m_c - M)]; L = sum l_c*w_c;
+// O = sum acc_c*w_c (sequential in c); out = O / L.  All 16 warps stage the flagged partials (one L2 round
+// trip), warp 0 runs the sequential chain from shared memory (lane = dim).  Tasks start on the CTAs after the
+// ones that own ATTN items, which are free earlier.
 template <int TYPE>
-__device__ __forceinline__ void combine_phase(const DecoderParams &P, const Phase &ph, int cta, int G, int n_pos) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
+                                              int n_pos, uint32_t tag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, slices = d / 32;
     const int n_tasks = P.H * slices;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
+    const int n_items = P.Hkv * nchunk;
+    float *stage = reinterpret_cast<float *>(S.u);
+    float *sm = reinterpret_cast<float *>(S.u + U_CM), *sl = reinterpret_cast<float *>(S.u + U_CL);
+    float *sw = reinterpret_cast<float *>(S.u + U_CW);
 #pragma unroll 1
-    for (int task = (cta + ph.rot) % G + G * warp; task < n_tasks; task += G * kCW) {
-        const int h = task / slices, sl = task % slices;
-        const float *pm = P.attn_m + (size_t)h * P.max_chunks;
-        const float *pl = P.attn_l + (size_t)h * P.max_chunks;
-        const float *pa = P.attn_acc + (size_t)h * P.max_chunks * d + sl * 32 + lane;
-        float mx = -INFINITY;
-        for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, __ldcg(pm + c));
-        mx = warp_max_f32(mx);
-        float L = 0.0f, O = 0.0f;
+    for (int task = ((cta + ph.rot) % G + G - n_items % G) % G; task < n_tasks; task += G) {
+        const int h = task / slices, sli = task % slices;
+        const ll_t *pa = ph.acc_ll + (size_t)h * P.max_chunks * d + sli * 32 + lane;
+        const ll_t *pm = ph.m_ll + (size_t)h * P.max_chunks, *pl = ph.l_ll + (size_t)h * P.max_chunks;
 #pragma unroll 1
-        for (int c0 = 0; c0 < nchunk; c0 += 32) {
-            const int nc = min(32, nchunk - c0);
-            const bool ok = lane < nc;
-            const float wl = ok ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(__ldcg(pm + c0 + lane), mx))]) : 0.0f;
-            const float ll = ok ? __ldcg(pl + c0 + lane) : 0.0f;
-#pragma unroll 1
-            for (int j0 = 0; j0 < nc; j0 += 8) {
-                float a[8];
+        for (int c0 = warp; c0 < nchunk; c0 += 4 * kCW) {
+            ll_t v[4];
 #pragma unroll
-                for (int u = 0; u < 8; u++) a[u] = j0 + u < nc ? __ldcg(pa + (size_t)(c0 + j0 + u) * d) : 0.0f;
+            for (int u = 0; u < 4; u++)
+                if (c0 + kCW * u < nchunk) v[u] = ll_peek(pa + (size_t)(c0 + kCW * u) * d);
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const float w = __shfl_sync(0xffffffffu, wl, j0 + u);
-                    const float l = __shfl_sync(0xffffffffu, ll, j0 + u);
-                    if (j0 + u < nc) {
-                        L = __fadd_rn(L, __fmul_rn(l, w));
-                        O = __fadd_rn(O, __fmul_rn(a[u], w));
-                    }
-                }
+            for (int u = 0; u < 4; u++) {
+                const int c = c0 + kCW * u;
+                if (c < nchunk) stage[c * 32 + lane] = ll_get_f(v[u], pa + (size_t)c * d, tag);
             }
         }
-        const float r = __fdiv_rn(O, L);
-        const size_t idx = (size_t)h * d + sl * 32 + lane;
-        ph.f32_out[idx] = r;
-        float dd;
-        const int qv = quantize_q8_lane(r, dd);
-        ((int8_t *)ph.act_out)[idx] = (int8_t)qv;
-        if (lane == 0) reinterpret_cast<__half *>(ph.act_out + (size_t)P.H * d)[idx >> 5] = __float2half_rn(dd);
+        for (int c = tid; c < nchunk; c += kCT) {
+            const ll_t vm = ll_peek(pm + c), vl = ll_peek(pl + c);
+            sm[c] = ll_get_f(vm, pm + c, tag);
+            sl[c] = ll_get_f(vl, pl + c, tag);
+        }
+        consumer_bar();
+        if (warp == 0) {
+            float mx = -INFINITY;
+            for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, sm[c]);
+            mx = warp_max_f32(mx);
+            for (int c = lane; c < nchunk; c += 32)
+                sw[c] = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sm[c], mx))]);
+            __syncwarp();
+            float L = 0.0f, O = 0.0f;
+#pragma unroll 4
+            for (int c = 0; c < nchunk; c++) {
+                const float w = sw[c];
+                L = __fadd_rn(L, __fmul_rn(sl[c], w));
+                O = __fadd_rn(O, __fmul_rn(stage[c * 32 + lane], w));
+            }
+            const float r = __fdiv_rn(O, L);
+            const size_t idx = (size_t)h * d + sli * 32 + lane;
+            ph.f32_out[idx] = r;
+            ll_put_f(ph.out_ll + idx, r, tag);
+        }
+        consumer_bar();
     }
 }
 
@@ -636,7 +704,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     __syncthreads();
     const int token = min(max(P.state[0], 0), P.V - 1);
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
-    unsigned long long bar_target = *P.bar_base;
+    const uint32_t tag = *P.seq + 1u;
 
     if (warp == kCW) {
         if (lane == 0) producer_loop<TYPE>(P, S, cta, G);
@@ -655,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
 #pragma unroll 1
     for (int pi = 0; pi < P.n_phases; pi++) {
         const Phase &ph = S.ph[pi & 1];
-        // prefetch the next descriptor; it is published by the barriers at the end of this phase
+        // prefetch the next descriptor; it is published by the block barriers inside this phase / at its end
         if (pi + 1 < P.n_phases && tid < kPhWords)
             reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1])[tid] =
                 reinterpret_cast<const uint32_t *>(&P.phases[pi + 1])[tid];
@@ -667,13 +735,10 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             unit_range(cta, G, ph.rot, ph.n_units, u0, u1);
             const int n_passes = (u1 - u0) * ph.unit_passes;
             const int ksegs = ph.ksegs, nb = ph.K >> 5;
-            // CTA 0 also writes the x0 (layer-0 embedding row) and result_norm dumps
-            const bool dump0 = cta == 0 && (kind == PH_LOGITS || (kind == PH_QKV && ph.x_in == nullptr));
-            if (n_passes > 0 || dump0) {
-                if (kind == PH_O || kind == PH_DOWN) copy_prologue<TYPE>(S, ph.act_in, ph.K);
-                else
-                    norm_prologue<TYPE>(P, S, ph, token, kind == PH_QKV && ph.x_in == nullptr && cta == 0,
-                                        (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
+            if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
+                if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
+                else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
+                else norm_prologue<TYPE>(P, S, ph, token, tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
             }
             if (P.trace) tr1 = clock64();
             // ---- passes: warp w owns pass w of every slot (Q8_0: 8 passes per slot, warps alternate slots)
@@ -699,7 +764,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             // ---- epilogue: finish this CTA's rows (segments added in order)
             const int row0 = u0 * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows;
             if (kind == PH_GATE_UP) {
-                // GeGLU (fp16 gelu table) + quantize_row_q8_0: one 32-row group per warp, lane = row
+                // GeGLU (fp16 gelu table) + quantize_row_q8_0: one 32-row group per warp, lane = row; the codes
+                // leave as flagged words of 4, the block scale as one more
+                ll_t *oq = ph.out_ll, *od = ph.out_ll + P.F / 4;
 #pragma unroll 1
                 for (int u = warp; u < u1 - u0; u += kCW) {
                     const float *pg = part + (u * 64 + lane) * ksegs, *pu = pg + 32 * ksegs;
@@ -713,24 +780,28 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     const size_t row = (size_t)(u0 + u) * 32 + lane;
                     if (ph.f32_out) ph.f32_out[row] = x;
                     float dd;
-                    const int q = quantize_q8_lane(x, dd);
-                    ((int8_t *)ph.act_out)[row] = (int8_t)q;
-                    if (lane == 0) reinterpret_cast<__half *>(ph.act_out + P.F)[u0 + u] = __float2half_rn(dd);
+                    const uint32_t q = (uint32_t)quantize_q8_lane(x, dd) & 0xFFu;
+                    uint32_t w = q;
+                    w |= __shfl_down_sync(0xffffffffu, q, 1) << 8;
+                    w |= __shfl_down_sync(0xffffffffu, q, 2) << 16;
+                    w |= __shfl_down_sync(0xffffffffu, q, 3) << 24;
+                    if ((lane & 3) == 0) ll_put(oq + (row >> 2), w, tag);
+                    if (lane == 0) ll_put(od + (u0 + u), (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
                 }
             } else {
                 Best best{-INFINITY, -1};
-                const float *resid = ph.resid;
+                const ll_t *resid = ph.resid_ll;
 #pragma unroll 1
                 for (int r = tid; r < nrows; r += kCT) {
                     const int grow = row0 + r;
                     if (grow >= ph.n_rows) break;
-                    float rv = 0.0f;
-                    if (resid) rv = __ldcg(resid + grow);
                     const float *pp = part + r * ksegs;
                     float total = pp[0];
                     for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, pp[k]);
-                    if (resid) total = __fadd_rn(total, rv);
-                    ph.out[grow] = total;
+                    if (resid) total = __fadd_rn(total, ll_get_f(ll_peek(resid + grow), resid + grow, tag));
+                    else if (ph.resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, token, grow));
+                    if (ph.out) ph.out[grow] = total;
+                    if (ph.out_ll) ll_put_f(ph.out_ll + grow, total, tag);
                     if (total > best.v || best.i < 0) best = Best{total, grow};
                 }
                 if (kind == PH_LOGITS) { // this CTA's arg-max candidate (strict '>' / lowest index, ref: :538-543)
@@ -749,19 +820,23 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     if (tid == 0) {
                         Best b{S.cand_v[0], S.cand_i[0]};
                         for (int w = 1; w < kCW; w++) b = better(b, Best{S.cand_v[w], S.cand_i[w]});
-                        P.cand_v[cta] = b.v;
-                        P.cand_i[cta] = b.i;
+                        ll_put_f(P.cand_ll + cta, b.v, tag);
+                        ll_put(P.cand_ll + G + cta, (uint32_t)b.i, tag);
                     }
                 }
             }
         } else if (kind == PH_ATTN) {
-            attn_phase<TYPE>(P, S, ph, cta, G, n_pos);
+            attn_phase<TYPE>(P, S, ph, cta, G, n_pos, tag);
         } else if (kind == PH_COMBINE) {
-            combine_phase<TYPE>(P, ph, cta, G, n_pos);
-        } else { // PH_SAMPLE: per-CTA candidates were published before the previous barrier
+            combine_phase<TYPE>(P, S, ph, cta, G, n_pos, tag);
+        } else { // PH_SAMPLE: CTA 0 picks the first maximum of the per-CTA candidates
             if (cta == 0 && warp == 0) {
                 Best b{-INFINITY, -1};
-                for (int i = lane; i < G; i += 32) b = better(b, Best{__ldcg(P.cand_v + i), __ldcg(P.cand_i + i)});
+                for (int i = lane; i < G; i += 32) {
+                    const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + G + i;
+                    const ll_t wv = ll_peek(pv), wi = ll_peek(pi2);
+                    b = better(b, Best{ll_get_f(wv, pv, tag), (int)ll_get(wi, pi2, tag)});
+                }
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     Best o;
@@ -770,24 +845,22 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     b = better(b, o);
                 }
                 if (lane == 0) {
+                    // every CTA has published its candidate, i.e. has long read state and seq
                     P.state[0] = b.i;
                     P.state[1] += P.state[2];
                     if (P.history) P.history[P.state[1]] = b.i;
+                    *P.seq = tag;
                 }
             }
         }
-        long long tr2 = 0;
-        if (P.trace) tr2 = clock64();
-        if (kind != PH_SAMPLE) {
-            bar_target += (unsigned long long)G;
-            grid_barrier(P.bar_count, bar_target);
-        }
+        // the union region is rewritten by the next phase's prologue, and the prefetched descriptor is read
+        consumer_bar();
         if (P.trace && tid == 0) {
             long long *t = P.trace + ((size_t)pi * G + cta) * 4;
-            t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = clock64();
+            const long long tr2 = clock64();
+            t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = tr2;
         }
     }
-    if (cta == 0 && tid == 0) *P.bar_base = bar_target;
 }
 
 // ---------------------------------------------------------------- pass-stream builder
@@ -872,10 +945,12 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     const int E = dims->n_embd, L = dims->n_layer, H = dims->n_head, Hkv = dims->n_head_kv, d = dims->head_dim;
     const int F = dims->n_ff, V = dims->n_vocab;
     const int type = token_embd->type;
+    const int max_chunks = (dims->n_ctx + kChunk - 1) / kChunk;
     if (!(E % 256 == 0 && E <= kMaxE && (H * d) % 256 == 0 && H * d <= kMaxE && F % 256 == 0 && F <= kMaxK &&
-          d % 32 == 0 && d <= 256 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= kMaxG &&
+          d % 32 == 0 && d <= 256 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= kMaxG && max_chunks <= kMaxChunks &&
           (type == GGB_TYPE_Q4_0 || type == GGB_TYPE_Q8_0))) {
-        ggb_set_error("decoder: shape outside the fused kernel's envelope (E=%d H=%d Hkv=%d d=%d F=%d)", E, H, Hkv, d, F);
+        ggb_set_error("decoder: shape outside the fused kernel's envelope (E=%d H=%d Hkv=%d d=%d F=%d ctx=%d)", E, H, Hkv,
+                      d, F, dims->n_ctx);
         return GGB_ERR_UNSUPPORTED;
     }
     GGB_CHECK_ARG(ggb_rope_cos_dev() && ggb_rope_n_dims() == d && ggb_rope_n_ctx() >= dims->n_ctx,
@@ -890,21 +965,23 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     P.state = io->state; P.history = io->history;
     P.exp_table = ggb_exp_table_dev(); P.gelu_table = ggb_gelu_table_dev();
     P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
-    P.max_chunks = (dims->n_ctx + kChunk - 1) / kChunk;
+    P.max_chunks = max_chunks;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     D->grid = sms;
-    // scratch: x0 | qkv | attn m,l,acc | cand | barrier words | planar activations
+    // scratch: flagged buffers, one set per layer (tag = token sequence number, so a word of the previous
+    // token never matches and nothing is rewritten while another CTA may still read it)
     const size_t QD = (size_t)H * d, KD = (size_t)Hkv * d;
-    const size_t act_q_bytes = ggb_q8_row_bytes((int64_t)QD), act_f_bytes = ggb_q8_row_bytes((int64_t)F);
     size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_x0 = carve((size_t)E * 4), o_qkv = carve((QD + 2 * KD) * 4);
-    const size_t o_m = carve((size_t)H * P.max_chunks * 4), o_l = carve((size_t)H * P.max_chunks * 4);
-    const size_t o_acc = carve((size_t)H * P.max_chunks * d * 4);
-    const size_t o_cv = carve((size_t)sms * 4), o_ci = carve((size_t)sms * 4), o_bar = carve(16);
-    const size_t o_aq = carve(act_q_bytes), o_af = carve(act_f_bytes);
+    auto carve = [&](size_t words) { size_t o = off; off = (off + words * 8 + 255) & ~(size_t)255; return o; };
+    const size_t o_x = carve((size_t)L * E);                       // slot il = output of layer il
+    const size_t o_qkv = carve((size_t)L * (QD + 2 * KD));
+    const size_t o_m = carve((size_t)L * H * max_chunks), o_l = carve((size_t)L * H * max_chunks);
+    const size_t o_acc = carve((size_t)L * H * max_chunks * d);
+    const size_t o_kqv = carve((size_t)L * QD), o_sa = carve((size_t)L * E);
+    const size_t o_ff = carve((size_t)L * (F / 4 + F / 32));
+    const size_t o_cand = carve((size_t)2 * sms), o_seq = carve(1);
     cudaError_t e = cudaMalloc(&D->scratch, off);
     if (e != cudaSuccess) {
         ggb_set_error("decoder scratch cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e));
@@ -913,11 +990,11 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     }
     cudaMemsetAsync(D->scratch, 0, off, ggb_cuda_stream());
     uint8_t *sb = (uint8_t *)D->scratch;
-    P.x0 = (float *)(sb + o_x0); P.qkv = (float *)(sb + o_qkv);
-    P.attn_m = (float *)(sb + o_m); P.attn_l = (float *)(sb + o_l); P.attn_acc = (float *)(sb + o_acc);
-    P.cand_v = (float *)(sb + o_cv); P.cand_i = (int *)(sb + o_ci);
-    P.bar_count = (unsigned long long *)(sb + o_bar); P.bar_base = P.bar_count + 1;
-    uint8_t *act_q = sb + o_aq, *act_f = sb + o_af;
+    ll_t *x_ll = (ll_t *)(sb + o_x), *qkv_ll = (ll_t *)(sb + o_qkv), *m_ll = (ll_t *)(sb + o_m), *l_ll = (ll_t *)(sb + o_l);
+    ll_t *acc_ll = (ll_t *)(sb + o_acc), *kqv_ll = (ll_t *)(sb + o_kqv), *sa_ll = (ll_t *)(sb + o_sa);
+    ll_t *ff_ll = (ll_t *)(sb + o_ff);
+    P.cand_ll = (ll_t *)(sb + o_cand);
+    P.seq = (uint32_t *)(sb + o_seq);
 
     const int pass_bytes = type == GGB_TYPE_Q4_0 ? Fmt<GGB_TYPE_Q4_0>::PASS_BYTES : Fmt<GGB_TYPE_Q8_0>::PASS_BYTES;
     bool ok = true;
@@ -964,50 +1041,59 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     };
     for (int il = 0; il < L && ok; il++) {
         const ggb_decoder_layer &ly = layers[il];
-        const float *x_in = il == 0 ? nullptr : io->l_out + (size_t)(il - 1) * E;
-        const float *x_res = il == 0 ? P.x0 : x_in;
+        const ll_t *x_in = il == 0 ? nullptr : x_ll + (size_t)(il - 1) * E;
         float *sa = io->sa_out + (size_t)il * E, *lo = io->l_out + (size_t)il * E;
+        ll_t *qkv_l = qkv_ll + (size_t)il * (QD + 2 * KD);
+        ll_t *m_l = m_ll + (size_t)il * H * max_chunks, *l_l = l_ll + (size_t)il * H * max_chunks;
+        ll_t *acc_l = acc_ll + (size_t)il * H * max_chunks * d;
+        ll_t *kqv_l = kqv_ll + (size_t)il * QD, *sa_l = sa_ll + (size_t)il * E;
+        ll_t *ff_l = ff_ll + (size_t)il * (F / 4 + F / 32);
         {   // QKV
             const ggb_weight *w[3] = {ly.attn_q, ly.attn_k, ly.attn_v};
             Phase ph = matvec_phase(PH_QKV, il, 3, w, false);
-            ph.x_in = x_in; ph.norm_w = ly.attn_norm; ph.out = P.qkv;
+            ph.in_ll = x_in; ph.norm_w = ly.attn_norm; ph.out_ll = qkv_l;
             if (ph.K != E) { ok = false; why = "attn_q input width != n_embd"; }
             D->phases.push_back(ph);
         }
         {   // ATTN
             Phase ph{};
             ph.kind = PH_ATTN; ph.layer = il; ph.kcache = (__half *)ly.k_cache; ph.vcache = (__half *)ly.v_cache;
+            ph.in_ll = qkv_l; ph.acc_ll = acc_l; ph.m_ll = m_l; ph.l_ll = l_l;
             D->phases.push_back(ph);
         }
         {   // COMBINE
             Phase ph{};
-            ph.kind = PH_COMBINE; ph.layer = il; ph.act_out = act_q; ph.f32_out = io->kqv + (size_t)il * QD;
+            ph.kind = PH_COMBINE; ph.layer = il; ph.f32_out = io->kqv + (size_t)il * QD; ph.out_ll = kqv_l;
+            ph.acc_ll = acc_l; ph.m_ll = m_l; ph.l_ll = l_l;
             D->phases.push_back(ph);
         }
         {   // O + residual
             const ggb_weight *w[1] = {ly.attn_output};
             Phase ph = matvec_phase(PH_O, il, 1, w, false);
-            ph.act_in = act_q; ph.resid = x_res; ph.out = sa;
+            ph.in_ll = kqv_l; ph.resid_ll = x_in; ph.resid_embed = il == 0 ? 1 : 0; ph.out = sa; ph.out_ll = sa_l;
+            if (ph.K != (int)QD) { ok = false; why = "attn_output input width != n_head*head_dim"; }
             D->phases.push_back(ph);
         }
         {   // GATE_UP
             const ggb_weight *w[2] = {ly.ffn_gate, ly.ffn_up};
             Phase ph = matvec_phase(PH_GATE_UP, il, 2, w, true);
-            ph.x_in = sa; ph.norm_w = ly.ffn_norm; ph.act_out = act_f;
+            ph.in_ll = sa_l; ph.norm_w = ly.ffn_norm; ph.out_ll = ff_l;
             ph.f32_out = io->ffn_act ? io->ffn_act + (size_t)il * F : nullptr;
+            if (ph.K != E) { ok = false; why = "ffn_gate input width != n_embd"; }
             D->phases.push_back(ph);
         }
         {   // DOWN + residual
             const ggb_weight *w[1] = {ly.ffn_down};
             Phase ph = matvec_phase(PH_DOWN, il, 1, w, false);
-            ph.act_in = act_f; ph.resid = sa; ph.out = lo;
+            ph.in_ll = ff_l; ph.resid_ll = sa_l; ph.out = lo; ph.out_ll = x_ll + (size_t)il * E;
+            if (ph.K != F) { ok = false; why = "ffn_down input width != n_ff"; }
             D->phases.push_back(ph);
         }
     }
     if (ok) {   // LOGITS (tied embedding) + SAMPLE
         const ggb_weight *w[1] = {token_embd};
         Phase ph = matvec_phase(PH_LOGITS, L, 1, w, false);
-        ph.x_in = io->l_out + (size_t)(L - 1) * E; ph.norm_w = output_norm; ph.f32_out = io->result_norm;
+        ph.in_ll = x_ll + (size_t)(L - 1) * E; ph.norm_w = output_norm; ph.f32_out = io->result_norm;
         ph.out = io->logits;
         D->phases.push_back(ph);
         Phase sp{};
@@ -1061,13 +1147,14 @@ int ggb_decoder_step(ggb_decoder *D) {
     void *args[] = {(void *)&D->P};
     const void *fn = D->P.type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
                                                 : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
+    // cooperative launch: the flagged data flow needs every CTA resident (a waiting CTA spins)
     GGB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)D->grid), dim3(kThreads), args, D->smem, ggb_cuda_stream()));
     ggb_count_launch();
     return GGB_OK;
 }
 
-// one traced step: per phase and CTA four SM-clock stamps (start, after prologue, after the work, after
-// the grid barrier) plus the phase kinds; the cudaEvent/ncu numbers say how long, this says where.
+// one traced step: per phase and CTA four SM-clock stamps (start, after the prologue = inputs arrived, after
+// the work, end) plus the phase kinds; the cudaEvent/ncu numbers say how long, this says where.
 int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(D && stamps && kinds && n_phases && grid, "null pointer");
