@@ -404,9 +404,7 @@ class GemmaModel:
         check(cuda_lib().ggb_decoder_trace(dec, _ptr(stamps), _ptr(kinds), max_ph, C.byref(n), C.byref(g)),
               "ggb_decoder_trace")
         n1 = n.value * g.value * 4
-        self.tile_stamps = stamps[n1:n1 + g.value * 32 * 3].reshape(g.value, 32, 3).copy()
-        n2 = n1 + g.value * 32 * 3
-        self.prologue_stamps = stamps[n2:n2 + g.value * 8].reshape(g.value, 8).copy()
+        self.dbg_stamps = stamps[n1:n1 + g.value * 16].reshape(g.value, 16).copy()
         return stamps[:n1].reshape(n.value, g.value, 4), kinds[:n.value].copy()
 
     @property

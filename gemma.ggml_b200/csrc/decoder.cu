@@ -31,6 +31,7 @@
 // folded in) | COMBINE | O (+ residual) | GATE_UP (+ GeGLU + Q8_0 quantise) | DOWN (+ residual);
 // then LOGITS (+ per-CTA arg-max) | SAMPLE.
 // Numerics are bit-identical to the per-operator kernels (same DEV order; tests compare both and the oracle).
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -70,6 +71,7 @@ struct Phase {
     int K;           // activation length
     int n_rows;      // logical rows of the phase
     int rot;         // CTA rotation so remainders do not always land on the same SMs
+    int uq, ur;      // n_units / grid, n_units % grid
     int resid_embed; // residual = embedding row of the token (layer 0, O phase)
     const uint8_t *stream; // pass stream of the phase
     // flagged inputs: QKV / GATE_UP / LOGITS: fp32 x [E] (null in layer 0: embedding row); O: fp32 kqv [H*d];
@@ -100,7 +102,9 @@ struct DecoderParams {
     uint32_t *seq;         // token sequence number = tag of the previous launch
     const uint16_t *exp_table, *gelu_table;
     const float *rope_cos, *rope_sin;
-    long long *trace; // optional [n_phases][grid][4] SM-clock stamps: start, after prologue (inputs arrived), after work, end
+    long long *trace; // optional [n_phases][grid][4] %globaltimer stamps (ns): start, after prologue (inputs arrived), end, end
+    long long *dbg;   // optional [grid][16] SM-clock stamps inside phase dbg_phase
+    int dbg_phase;
 };
 
 // union region: the views are never live at the same time
@@ -201,6 +205,14 @@ __device__ __forceinline__ uint32_t ll_get(ll_t v, const ll_t *p, uint32_t tag) 
 }
 __device__ __forceinline__ float ll_get_f(ll_t v, const ll_t *p, uint32_t tag) { return __uint_as_float(ll_get(v, p, tag)); }
 
+__device__ __forceinline__ unsigned long long gtime() { // ns, one clock for the whole GPU (SM clocks are not aligned)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// fine-grained SM-clock stamps of ONE phase (debug builds of the trace): thread 0 of every CTA
+#define DBG_STAMP(i) do { if (dbg && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+
 struct Best {
     float v;
     int i;
@@ -212,11 +224,13 @@ __device__ __forceinline__ Best better(Best a, Best b) { // first maximum (ref: 
     return a;
 }
 
-// CTA c's share [u0, u1) of n units: contiguous and balanced
-__device__ __forceinline__ void unit_range(int cta, int G, int rot, int n_units, int &u0, int &u1) {
-    const int c = (cta + rot) % G;
-    u0 = (int)(((long long)c * n_units) / G);
-    u1 = (int)(((long long)(c + 1) * n_units) / G);
+// CTA c's share [u0, u1) of n units: contiguous and balanced (q = n / G, r = n % G come from the host and
+// rot < G: no division here, a 64-bit one costs 0.2 us on the critical path of every phase)
+__device__ __forceinline__ void unit_range(int cta, int G, int rot, int q, int r, int &u0, int &u1) {
+    int c = cta + rot;
+    if (c >= G) c -= G;
+    u0 = c * q + min(c, r);
+    u1 = u0 + q + (c < r ? 1 : 0);
 }
 
 __device__ __forceinline__ bool is_matvec(int kind) {
@@ -251,7 +265,7 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
         const Phase *ph = P.phases + pi;
         if (!is_matvec(ph->kind)) continue;
         int u0, u1;
-        unit_range(cta, G, ph->rot, ph->n_units, u0, u1);
+        unit_range(cta, G, ph->rot, ph->uq, ph->ur, u0, u1);
         const int up = ph->unit_passes;
         int n = (u1 - u0) * up;
         const uint8_t *src = ph->stream + (size_t)u0 * up * F::PASS_BYTES;
@@ -275,15 +289,29 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
 // ---------------------------------------------------------------- prologues (each ends with the activation row in
 // shared memory: act_q int8[K], act_d fp16[K/32], bias int[K/32] = -8 * sum of the block's codes)
 
-// quantize_row_q8_0 of one 32-element block spread over a warp (lane = element) into the shared row
-__device__ __forceinline__ void quant_block_to_smem(uint8_t *u, int b, int lane, float v) {
-    float d;
-    const int q = quantize_q8_lane(v, d);
-    reinterpret_cast<int8_t *>(u)[32 * b + lane] = (int8_t)q;
-    const int qs = __reduce_add_sync(0xffffffffu, q);
-    if (lane == 0) {
-        reinterpret_cast<__half *>(u + U_ACT_D)[b] = __float2half_rn(d);
-        reinterpret_cast<int *>(u + U_BIAS)[b] = -8 * qs;
+// quantize_row_q8_0 of FOUR consecutive 32-element blocks per warp: lane l holds elements 4l .. 4l+3 of the
+// 128, so 8 lanes share a block.  The serial instruction chain (two IEEE divisions, roundf) is what a block
+// costs (~0.3 us at 4 warps per scheduler), so a warp runs it once per four blocks instead of once per block.
+// amax / code sum: three xor-shuffles inside each 8-lane group (a sub-warp REDUX serialises the four groups
+// behind WARPSYNC.EXCLUSIVE and costs ~0.5 us).  max is exact: same value as the reference's scan.
+__device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lane, const float (&v)[4]) {
+    float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+    for (int off = 1; off <= 4; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off)); // 8-lane groups
+    const float d = __fdiv_rn(amax, 127.0f);
+    const float id = d != 0.0f ? __fdiv_rn(1.0f, d) : 0.0f;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) packed |= ((uint32_t)(int)roundf(__fmul_rn(v[e], id)) & 0xFFu) << (8 * e);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(u + 128 * quad + 4 * lane), "r"(packed) : "memory");
+    int qs = __dp4a((int)packed, 0x01010101, 0);
+#pragma unroll
+    for (int off = 1; off <= 4; off <<= 1) qs += __shfl_xor_sync(0xffffffffu, qs, off);
+    if ((lane & 7) == 0) {
+        const int b = 4 * quad + (lane >> 3);
+        const unsigned short hd = __half_as_ushort(__float2half_rn(d));
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(u + U_ACT_D + 2 * b), "h"(hd) : "memory");
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(u + U_BIAS + 4 * b), "r"(-8 * qs) : "memory");
     }
 }
 
@@ -294,12 +322,18 @@ __device__ __forceinline__ void quant_block_to_smem(uint8_t *u, int b, int lane,
 // partials in registers and no staging pass is needed; the halves then split the quantisation by blocks.
 template <int TYPE>
 __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
-                                              uint32_t tag, float *f32_out) {
+                                              uint32_t tag, float *f32_out, long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = P.E, nk = E / GGB_DEV_NORM_THREADS;
+    DBG_STAMP(1);
     const int base = 32 * (warp & 7) + lane;
     float *xs = reinterpret_cast<float *>(S.u + U_XS);
     const ll_t *in = ph.in_ll;
+    // the norm weights of this warp's first quad of blocks: requested before the (long) wait for x
+    const float *norm_w = ph.norm_w;
+    const int nquad = E / 128;
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp < nquad) w4 = *reinterpret_cast<const float4 *>(norm_w + 128 * warp + 4 * lane);
     double acc = 0.0;
 #pragma unroll 1
     for (int k0 = 0; k0 < nk; k0 += 4) {
@@ -317,41 +351,53 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
             }
         }
     }
+    DBG_STAMP(2);
     acc = warp_sum_f64(acc);
     if (warp < 8 && lane == 0) S.red[warp] = acc;
+    DBG_STAMP(3);
     consumer_bar();
+    DBG_STAMP(4);
     double sum = S.red[0];
 #pragma unroll
     for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
-    const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
+    // sum / E: a power-of-two E scales exactly (same bits as the division, which is a ~600-cycle routine)
+    const float mean = __double2float_rn((E & (E - 1)) == 0 ? __dmul_rn(sum, 1.0 / (double)E) : __ddiv_rn(sum, (double)E));
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
-    const float *norm_w = ph.norm_w;
-#pragma unroll 2
-    for (int k = warp >> 3; k < nk; k += 2) { // block 8k + (w & 7): elements written by this very thread above
-        const int i = GGB_DEV_NORM_THREADS * k + base;
-        const float v = __fmul_rn(__fmul_rn(xs[i], scale), norm_w[i]);
-        if (f32_out) f32_out[i] = v;
-        quant_block_to_smem(S.u, i >> 5, lane, v);
+    DBG_STAMP(5);
+    const uint32_t ua = smem_u32(S.u);
+#pragma unroll 1
+    for (int quad = warp; quad < nquad; quad += kCW) { // elements 128 quad + 4 lane .. + 3 (staged by other threads: bar above)
+        const int i = 128 * quad + 4 * lane;
+        const float4 x4 = *reinterpret_cast<const float4 *>(xs + i);
+        if (quad != warp) w4 = *reinterpret_cast<const float4 *>(norm_w + i);
+        float v[4];
+        v[0] = __fmul_rn(__fmul_rn(x4.x, scale), w4.x);
+        v[1] = __fmul_rn(__fmul_rn(x4.y, scale), w4.y);
+        v[2] = __fmul_rn(__fmul_rn(x4.z, scale), w4.z);
+        v[3] = __fmul_rn(__fmul_rn(x4.w, scale), w4.w);
+        if (f32_out) *reinterpret_cast<float4 *>(f32_out + i) = make_float4(v[0], v[1], v[2], v[3]);
+        quant_quad_to_smem(ua, quad, lane, v);
     }
+    DBG_STAMP(6);
     consumer_bar();
+    DBG_STAMP(7);
 }
 
 // O: the flagged fp32 row written by COMBINE -> quantize_row_q8_0 (ggml mul_mat INIT stage)
 template <int TYPE>
 __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nbk = K / 32;
+    const uint32_t ua = smem_u32(S.u);
 #pragma unroll 1
-    for (int b0 = warp; b0 < nbk; b0 += 4 * kCW) {
-        ll_t v[4];
+    for (int quad = warp; quad < K / 128; quad += kCW) {
+        const ll_t *p = in + 128 * quad + 4 * lane;
+        ll_t w[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (b0 + kCW * u < nbk) v[u] = ll_peek(in + 32 * (b0 + kCW * u) + lane);
+        for (int e = 0; e < 4; e++) w[e] = ll_peek(p + e);
+        float v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int b = b0 + kCW * u;
-            if (b < nbk) quant_block_to_smem(S.u, b, lane, ll_get_f(v[u], in + 32 * b + lane, tag));
-        }
+        for (int e = 0; e < 4; e++) v[e] = ll_get_f(w[e], p + e, tag);
+        quant_quad_to_smem(ua, quad, lane, v);
     }
     consumer_bar();
 }
@@ -397,24 +443,33 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
 //   Q4_0: ((float)sumi * d_x) * d_y      Q8_0: (float)sumi * (d_x * d_y)
 // lane partial = blocks in order from 0.0f; the two rows' butterflies (xor 16,8,4,2,1) are folded into one:
 // lanes < 16 end with row A's sum, lanes >= 16 with row B's (same additions, DEV order).
-template <int TYPE>
-__device__ __forceinline__ float pass_dot(uint32_t base, uint32_t act, int seg, int nb, int lane) {
-    using F = Fmt<TYPE>;
+struct ActRegs { // the lane's two activation blocks of one K segment
     int a[2][8];
     float dy[2];
     int bias[2];
     bool live[2];
+};
+template <int TYPE>
+__device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg, int nb, int lane) {
 #pragma unroll
     for (int t = 0; t < 2; t++) {
         const int b = seg * kSeg + lane + 32 * t;
-        live[t] = b < nb;
-        const int bc = live[t] ? b : 0;
+        A.live[t] = b < nb;
+        const int bc = A.live[t] ? b : 0;
         const uint4 lo = lds_u4(act + bc * 32), hi = lds_u4(act + bc * 32 + 16);
-        a[t][0] = lo.x; a[t][1] = lo.y; a[t][2] = lo.z; a[t][3] = lo.w;
-        a[t][4] = hi.x; a[t][5] = hi.y; a[t][6] = hi.z; a[t][7] = hi.w;
-        dy[t] = lds_half(act + U_ACT_D + bc * 2);
-        bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + bc * 4) : 0;
+        A.a[t][0] = lo.x; A.a[t][1] = lo.y; A.a[t][2] = lo.z; A.a[t][3] = lo.w;
+        A.a[t][4] = hi.x; A.a[t][5] = hi.y; A.a[t][6] = hi.z; A.a[t][7] = hi.w;
+        A.dy[t] = lds_half(act + U_ACT_D + bc * 2);
+        A.bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + bc * 4) : 0;
     }
+}
+template <int TYPE>
+__device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int lane) {
+    using F = Fmt<TYPE>;
+    const int(&a)[2][8] = A.a;
+    const float(&dy)[2] = A.dy;
+    const int(&bias)[2] = A.bias;
+    const bool(&live)[2] = A.live;
     float term[4]; // [row][block]
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -456,17 +511,20 @@ __device__ __forceinline__ float pass_dot(uint32_t base, uint32_t act, int seg, 
 }
 
 // ---------------------------------------------------------------- ATTN
-// items (kv head g, chunk of 32 positions).  Same arithmetic as attention.cu attn_partial_kernel; rope + Q
+// items (kv head g, chunk of 32 positions, half of the query heads).  Same arithmetic as attention.cu attn_partial_kernel; rope + Q
 // scale are applied to q on load, and the item that owns the newest position ropes K, rounds K/V to fp16,
 // stores them in the cache and uses them.  The K/V rows of older positions do not depend on this token: their
 // copies are in flight while the CTA still waits for q.
 template <int TYPE>
 __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                           int n_pos, uint32_t tag) {
+                                           int n_pos, uint32_t tag, long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, halfd = d / 2, Hkv = P.Hkv, Gq = P.H / Hkv;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    const int n_items = Hkv * nchunk;
+    // with more than 4 query heads per KV head an item is split in two (heads 0..Gq/2-1 | the rest): the K/V
+    // chunk is read twice (L2), the score / PV work per CTA halves and twice as many SMs take part
+    const int hsplit = Gq > 4 ? 2 : 1, Gh = Gq / hsplit;
+    const int n_items = Hkv * nchunk * hsplit;
     const int pos = n_pos - 1;
     const size_t kv_stride = (size_t)Hkv * d;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
@@ -478,22 +536,24 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     const uint32_t kc_addr = smem_u32(Kc), vc_addr = smem_u32(Vc);
     const int pieces = d / 8; // 16-byte pieces per row
 #pragma unroll 1
-    for (int it = (cta + ph.rot) % G; it < n_items; it += G) {
-        const int g = it / nchunk, c = it % nchunk;
+    for (int it = cta + ph.rot >= G ? cta + ph.rot - G : cta + ph.rot; it < n_items; it += G) {
+        const int hh = it % hsplit, gc = it / hsplit;
+        const int g = gc / nchunk, c = gc % nchunk;
         const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
-        const int h0 = g * Gq;
+        const int h0 = g * Gq + hh * Gh;
         const int jnew = pos - p0; // row of the new position inside this chunk (if 0 <= jnew < np)
         const bool owns_new = jnew >= 0 && jnew < np;
-        // K / V chunk rows (the new position's row is computed below, not loaded)
-        for (int v = tid; v < np * pieces; v += kCT) {
-            const int j = v / pieces, qd = v % pieces;
-            if (j == jnew) continue;
-            const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d + 8 * qd;
-            cp_async16(kc_addr + (uint32_t)(j * d + 8 * qd) * 2, ph.kcache + src);
-            cp_async16(vc_addr + (uint32_t)(j * d + 8 * qd) * 2, ph.vcache + src);
+        // K / V chunk rows: warp w copies rows w, w + 16, lane = 16-byte piece (the new position's row is
+        // computed below, not loaded)
+        for (int j = warp; j < np; j += kCW) {
+            if (j == jnew || lane >= pieces) continue;
+            const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d + 8 * lane;
+            cp_async16(kc_addr + (uint32_t)(j * d + 8 * lane) * 2, ph.kcache + src);
+            cp_async16(vc_addr + (uint32_t)(j * d + 8 * lane) * 2, ph.vcache + src);
         }
+        DBG_STAMP(1);
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
-        for (int i = tid; i < Gq * halfd; i += kCT) {
+        for (int i = tid; i < Gh * halfd; i += kCT) {
             const int jh = i / halfd, e = i % halfd;
             const ll_t *qh = q_all + (size_t)(h0 + jh) * d;
             const ll_t w0 = ll_peek(qh + e), w1 = ll_peek(qh + e + halfd);
@@ -504,6 +564,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             Sq[jh * d + e] = __float2half_rn(r0);
             Sq[jh * d + e + halfd] = __float2half_rn(r1);
         }
+        DBG_STAMP(2);
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
             for (int e = tid; e < halfd; e += kCT) {
                 const ll_t *kp = k_all + (size_t)g * d + e;
@@ -514,19 +575,23 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                 const __half k1 = __float2half_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)));
                 Kc[jnew * d + e] = k0;
                 Kc[jnew * d + e + halfd] = k1;
-                __half *krow = ph.kcache + ((size_t)pos * Hkv + g) * d;
-                krow[e] = k0;
-                krow[e + halfd] = k1;
+                if (hh == 0) {
+                    __half *krow = ph.kcache + ((size_t)pos * Hkv + g) * d;
+                    krow[e] = k0;
+                    krow[e + halfd] = k1;
+                }
             }
             for (int e = tid; e < d; e += kCT) {
                 const ll_t *vp = v_all + (size_t)g * d + e;
                 const __half vv = __float2half_rn(ll_get_f(ll_peek(vp), vp, tag));
                 Vc[jnew * d + e] = vv;
-                ph.vcache[((size_t)pos * Hkv + g) * d + e] = vv;
+                if (hh == 0) ph.vcache[((size_t)pos * Hkv + g) * d + e] = vv;
             }
         }
+        DBG_STAMP(3);
         cp_async_wait_all();
         consumer_bar();
+        DBG_STAMP(4);
         // scores: warp w takes positions w, w + 16
 #pragma unroll 1
         for (int j = warp; j < np; j += kCW) {
@@ -546,12 +611,12 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             // fp16 x fp16 products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once.  Heads in
             // groups of 4: lane partials first, then the group's butterflies interleaved; each sum in DEV order
 #pragma unroll 1
-            for (int j0 = 0; j0 < Gq; j0 += 4) {
+            for (int j0 = 0; j0 < Gh; j0 += 4) {
                 float acc[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     acc[u] = 0.0f;
-                    if (j0 + u < Gq && in) {
+                    if (j0 + u < Gh && in) {
                         const uint4 raw = *reinterpret_cast<const uint4 *>(Sq + (j0 + u) * d + 8 * lane);
                         const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
@@ -570,13 +635,14 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                 if (lane == 0) {
 #pragma unroll
                     for (int u = 0; u < 4; u++)
-                        if (j0 + u < Gq) Ss[j0 + u][j] = acc[u];
+                        if (j0 + u < Gh) Ss[j0 + u][j] = acc[u];
                 }
             }
         }
+        DBG_STAMP(5);
         consumer_bar();
         // per-head chunk soft-max through the fp16 exp table
-        if (warp < Gq) {
+        if (warp < Gh) {
             const float sv = lane < np ? Ss[warp][lane] : -INFINITY;
             const float m = warp_max_f32(sv);
             const float e = lane < np ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sv, m))]) : 0.0f;
@@ -587,7 +653,9 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                 ll_put_f(ph.l_ll + (size_t)(h0 + warp) * P.max_chunks + c, l, tag);
             }
         }
+        DBG_STAMP(6);
         consumer_bar();
+        DBG_STAMP(7);
         // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p.  4 thread groups of 128: group hs takes heads
         // hs, hs + 4; thread -> one pair of dims
         {
@@ -603,7 +671,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
 #pragma unroll
                     for (int u = 0; u < kMaxG / kHG; u++) {
                         const int jh = kHG * u + hs;
-                        if (jh < Gq) { // e is an fp16 value: e*v is exact, fmaf == mul + add
+                        if (jh < Gh) { // e is an fp16 value: e*v is exact, fmaf == mul + add
                             const float e = Se[jh][j];
                             a0[u] = __fmaf_rn(e, vf.x, a0[u]);
                             a1[u] = __fmaf_rn(e, vf.y, a1[u]);
@@ -613,7 +681,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
 #pragma unroll
                 for (int u = 0; u < kMaxG / kHG; u++) {
                     const int jh = kHG * u + hs;
-                    if (jh < Gq) {
+                    if (jh < Gh) {
                         ll_t *out = ph.acc_ll + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
                         ll_put_f(out, a0[u], tag);
                         ll_put_f(out + 1, a1[u], tag);
@@ -631,12 +699,12 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
 // ones that own ATTN items, which are free earlier.
 template <int TYPE>
 __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                              int n_pos, uint32_t tag) {
+                                              int n_pos, uint32_t tag, long long *dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, slices = d / 32;
     const int n_tasks = P.H * slices;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    const int n_items = P.Hkv * nchunk;
+    const int n_items = P.Hkv * nchunk * (P.H / P.Hkv > 4 ? 2 : 1);
     float *stage = reinterpret_cast<float *>(S.u);
     float *sm = reinterpret_cast<float *>(S.u + U_CM), *sl = reinterpret_cast<float *>(S.u + U_CL);
     float *sw = reinterpret_cast<float *>(S.u + U_CW);
@@ -662,7 +730,9 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
             sm[c] = ll_get_f(vm, pm + c, tag);
             sl[c] = ll_get_f(vl, pl + c, tag);
         }
+        DBG_STAMP(1);
         consumer_bar();
+        DBG_STAMP(2);
         if (warp == 0) {
             float mx = -INFINITY;
             for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, sm[c]);
@@ -670,17 +740,31 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
             for (int c = lane; c < nchunk; c += 32)
                 sw[c] = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sm[c], mx))]);
             __syncwarp();
+            DBG_STAMP(3);
             float L = 0.0f, O = 0.0f;
-#pragma unroll 4
-            for (int c = 0; c < nchunk; c++) {
-                const float w = sw[c];
-                L = __fadd_rn(L, __fmul_rn(sl[c], w));
-                O = __fadd_rn(O, __fmul_rn(stage[c * 32 + lane], w));
+#pragma unroll 1
+            for (int c0 = 0; c0 < nchunk; c0 += 16) { // products of 16 chunks first (independent), then the chain
+                float pl[16], po[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const int c = min(c0 + u, nchunk - 1);
+                    const float w = sw[c];
+                    pl[u] = __fmul_rn(sl[c], w);
+                    po[u] = __fmul_rn(stage[c * 32 + lane], w);
+                }
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    if (c0 + u < nchunk) {
+                        L = __fadd_rn(L, pl[u]);
+                        O = __fadd_rn(O, po[u]);
+                    }
+                }
             }
             const float r = __fdiv_rn(O, L);
             const size_t idx = (size_t)h * d + sli * 32 + lane;
             ph.f32_out[idx] = r;
             ll_put_f(ph.out_ll + idx, r, tag);
+            DBG_STAMP(4);
         }
         consumer_bar();
     }
@@ -728,48 +812,75 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1])[tid] =
                 reinterpret_cast<const uint32_t *>(&P.phases[pi + 1])[tid];
         long long tr0 = 0, tr1 = 0;
-        if (P.trace) tr0 = tr1 = clock64();
+        if (P.trace) tr0 = tr1 = (long long)gtime();
         const int kind = ph.kind;
+        long long *dbg = (P.dbg && pi == P.dbg_phase) ? P.dbg + 16 * cta : nullptr;
+        DBG_STAMP(0);
         if (is_matvec(kind)) {
             int u0, u1;
-            unit_range(cta, G, ph.rot, ph.n_units, u0, u1);
+            unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
             const int n_passes = (u1 - u0) * ph.unit_passes;
             const int ksegs = ph.ksegs, nb = ph.K >> 5;
             if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
                 if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
                 else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
-                else norm_prologue<TYPE>(P, S, ph, token, tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
+                else norm_prologue<TYPE>(P, S, ph, token, tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr, dbg);
             }
-            if (P.trace) tr1 = clock64();
-            // ---- passes: warp w owns pass w of every slot (Q8_0: 8 passes per slot, warps alternate slots)
-#pragma unroll 1
-            for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
-                const int cnt = min(F::PPS, n_passes - p0);
-                const int j = F::PPS == kCW ? warp : (((warp >> 3) == (i & 1)) ? (warp & 7) : F::PPS);
-                mbar_wait(full0 + 8 * slot, parity);
-                if (j < cnt) {
-                    const int p = p0 + j;
-                    const int pair = p / ksegs, seg = p - pair * ksegs;
-                    const float keep = pass_dot<TYPE>(ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES, act, seg, nb, lane);
-                    if ((lane & 15) == 0) part[(2 * pair + (lane >> 4)) * ksegs + seg] = keep;
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-                if (++slot == kSlots) {
-                    slot = 0;
-                    parity ^= 1u;
-                }
-            }
-            consumer_bar();
-            // ---- epilogue: finish this CTA's rows (segments added in order)
+            if (P.trace) tr1 = (long long)gtime();
+            // the residual of this thread's first row: requested before the passes, consumed in the epilogue
             const int row0 = u0 * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows;
-            if (kind == PH_GATE_UP) {
-                // GeGLU (fp16 gelu table) + quantize_row_q8_0: one 32-row group per warp, lane = row; the codes
-                // leave as flagged words of 4, the block scale as one more
-                ll_t *oq = ph.out_ll, *od = ph.out_ll + P.F / 4;
+            ll_t resid_w = 0;
+            if (ph.resid_ll && kind != PH_GATE_UP && tid < nrows && row0 + tid < ph.n_rows) resid_w = ll_peek(ph.resid_ll + row0 + tid);
+            // ---- passes: warp w owns passes w, w + 16, ... (Q4_0: one per slot; Q8_0: 8 passes per slot, so the
+            // two warp halves alternate slots).  Every warp waits for and releases every slot.  The activation
+            // blocks live in registers and are reloaded only when the warp's K segment changes (never for
+            // K <= 2048, and never when 16 % ksegs == 0).
+            {
+                const int pstep = kCW / ksegs, sstep = kCW % ksegs; // one division per phase, not per pass
+                int pair = warp / ksegs, seg = warp % ksegs, cur_seg = -1;
+                ActRegs A;
 #pragma unroll 1
-                for (int u = warp; u < u1 - u0; u += kCW) {
-                    const float *pg = part + (u * 64 + lane) * ksegs, *pu = pg + 32 * ksegs;
+                for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
+                    const int cnt = min(F::PPS, n_passes - p0);
+                    const int j = F::PPS == kCW ? warp : (((warp >> 3) == (i & 1)) ? (warp & 7) : F::PPS);
+                    if (j < cnt && seg != cur_seg) {
+                        load_act_regs<TYPE>(A, act, seg, nb, lane);
+                        cur_seg = seg;
+                    }
+                    mbar_wait(full0 + 8 * slot, parity);
+                    if (j < cnt) {
+                        const float keep = pass_dot<TYPE>(ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES, A, lane);
+                        if ((lane & 15) == 0) part[(2 * pair + (lane >> 4)) * ksegs + seg] = keep;
+                        pair += pstep;
+                        seg += sstep;
+                        if (seg >= ksegs) {
+                            seg -= ksegs;
+                            pair++;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty0 + 8 * slot);
+                    if (++slot == kSlots) {
+                        slot = 0;
+                        parity ^= 1u;
+                    }
+                }
+            }
+            DBG_STAMP(8);
+            consumer_bar();
+            DBG_STAMP(9);
+            // ---- epilogue: finish this CTA's rows (segments added in order)
+            if (kind == PH_GATE_UP) {
+                // GeGLU (fp16 gelu table) for every row in parallel (one table round trip), then
+                // quantize_row_q8_0 with 8 lanes per 32-row group (4 groups per warp pass); a lane's four codes are
+                // exactly one flagged word of the packed row, the block scale is one more
+                ll_t *oq = ph.out_ll, *od = ph.out_ll + P.F / 4;
+                float *xb = reinterpret_cast<float *>(S.u + U_XS); // GeGLU products (the activation row is dead)
+                const int nu = u1 - u0;
+#pragma unroll 1
+                for (int r = tid; r < nu * 32; r += kCT) {
+                    const int u = r >> 5, i = r & 31;
+                    const float *pg = part + (u * 64 + i) * ksegs, *pu = pg + 32 * ksegs;
                     float gsum = pg[0], usum = pu[0];
                     for (int k = 1; k < ksegs; k++) {
                         gsum = __fadd_rn(gsum, pg[k]);
@@ -777,16 +888,29 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     }
                     const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(gsum)]);
                     const float x = __fmul_rn(gl, usum);
-                    const size_t row = (size_t)(u0 + u) * 32 + lane;
-                    if (ph.f32_out) ph.f32_out[row] = x;
-                    float dd;
-                    const uint32_t q = (uint32_t)quantize_q8_lane(x, dd) & 0xFFu;
-                    uint32_t w = q;
-                    w |= __shfl_down_sync(0xffffffffu, q, 1) << 8;
-                    w |= __shfl_down_sync(0xffffffffu, q, 2) << 16;
-                    w |= __shfl_down_sync(0xffffffffu, q, 3) << 24;
-                    if ((lane & 3) == 0) ll_put(oq + (row >> 2), w, tag);
-                    if (lane == 0) ll_put(od + (u0 + u), (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
+                    xb[r] = x;
+                    if (ph.f32_out) ph.f32_out[(size_t)u0 * 32 + r] = x;
+                }
+                consumer_bar();
+#pragma unroll 1
+                for (int q0 = 4 * warp; q0 < nu; q0 += 4 * kCW) {
+                    const int u = q0 + (lane >> 3);
+                    const bool ok = u < nu;
+                    const float4 x4 = ok ? *reinterpret_cast<const float4 *>(xb + 32 * u + 4 * (lane & 7))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float amax = fmaxf(fmaxf(fabsf(x4.x), fabsf(x4.y)), fmaxf(fabsf(x4.z), fabsf(x4.w)));
+#pragma unroll
+                    for (int off = 1; off <= 4; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+                    const float dd = __fdiv_rn(amax, 127.0f);
+                    const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
+                    const uint32_t w = ((uint32_t)(int)roundf(__fmul_rn(x4.x, id)) & 0xFFu) |
+                                       (((uint32_t)(int)roundf(__fmul_rn(x4.y, id)) & 0xFFu) << 8) |
+                                       (((uint32_t)(int)roundf(__fmul_rn(x4.z, id)) & 0xFFu) << 16) |
+                                       (((uint32_t)(int)roundf(__fmul_rn(x4.w, id)) & 0xFFu) << 24);
+                    if (ok) {
+                        ll_put(oq + (size_t)(u0 + u) * 8 + (lane & 7), w, tag);
+                        if ((lane & 7) == 0) ll_put(od + (u0 + u), (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
+                    }
                 }
             } else {
                 Best best{-INFINITY, -1};
@@ -798,7 +922,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     const float *pp = part + r * ksegs;
                     float total = pp[0];
                     for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, pp[k]);
-                    if (resid) total = __fadd_rn(total, ll_get_f(ll_peek(resid + grow), resid + grow, tag));
+                    if (resid) total = __fadd_rn(total, ll_get_f(r == tid ? resid_w : ll_peek(resid + grow), resid + grow, tag));
                     else if (ph.resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, token, grow));
                     if (ph.out) ph.out[grow] = total;
                     if (ph.out_ll) ll_put_f(ph.out_ll + grow, total, tag);
@@ -826,9 +950,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                 }
             }
         } else if (kind == PH_ATTN) {
-            attn_phase<TYPE>(P, S, ph, cta, G, n_pos, tag);
+            attn_phase<TYPE>(P, S, ph, cta, G, n_pos, tag, dbg);
         } else if (kind == PH_COMBINE) {
-            combine_phase<TYPE>(P, S, ph, cta, G, n_pos, tag);
+            combine_phase<TYPE>(P, S, ph, cta, G, n_pos, tag, dbg);
         } else { // PH_SAMPLE: CTA 0 picks the first maximum of the per-CTA candidates
             if (cta == 0 && warp == 0) {
                 Best b{-INFINITY, -1};
@@ -853,11 +977,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                 }
             }
         }
+        DBG_STAMP(10);
         // the union region is rewritten by the next phase's prologue, and the prefetched descriptor is read
         consumer_bar();
+        DBG_STAMP(11);
         if (P.trace && tid == 0) {
             long long *t = P.trace + ((size_t)pi * G + cta) * 4;
-            const long long tr2 = clock64();
+            const long long tr2 = (long long)gtime();
             t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = tr2;
         }
     }
@@ -1023,6 +1149,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         } else {
             ph.n_units = n_pairs; ph.unit_passes = ph.ksegs; ph.unit_rows = 2;
         }
+        ph.uq = ph.n_units / sms; ph.ur = ph.n_units % sms;
         const long long max_units = (ph.n_units + sms - 1) / sms;
         if (max_units * ph.unit_rows * ph.ksegs > kPartFloats) { ok = false; why = "phase does not fit the partial table"; }
         if (ph.K > kMaxK) { ok = false; why = "activation row too long"; }
@@ -1153,20 +1280,26 @@ int ggb_decoder_step(ggb_decoder *D) {
     return GGB_OK;
 }
 
-// one traced step: per phase and CTA four SM-clock stamps (start, after the prologue = inputs arrived, after
-// the work, end) plus the phase kinds; the cudaEvent/ncu numbers say how long, this says where.
+// one traced step: per phase and CTA four %globaltimer stamps in ns (start, after the prologue = inputs
+// arrived, end, end) plus the phase kinds; the cudaEvent/ncu numbers say how long, this says where.
 int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(D && stamps && kinds && n_phases && grid, "null pointer");
     const int np = (int)D->phases.size();
     GGB_CHECK_ARG(max_phases >= np, "trace buffer holds %d phases, need %d", max_phases, np);
-    const size_t bytes = (size_t)np * D->grid * 4 * sizeof(long long);
+    const size_t bytes1 = (size_t)np * D->grid * 4 * sizeof(long long);
+    const size_t bytes = bytes1 + (size_t)D->grid * 16 * sizeof(long long); // + [grid][16] stamps inside one phase
+    GGB_CHECK_ARG((size_t)max_phases * D->grid * 4 * sizeof(long long) >= bytes, "trace buffer too small");
     long long *dev = nullptr;
     GGB_CUDA(cudaMalloc(&dev, bytes));
     GGB_CUDA(cudaMemsetAsync(dev, 0, bytes, ggb_cuda_stream()));
     D->P.trace = dev;
+    D->P.dbg = dev + bytes1 / sizeof(long long);
+    if (const char *env = getenv("GGB_DBG_PHASE")) D->P.dbg_phase = atoi(env);
+    else D->P.dbg_phase = 30;
     int rc = ggb_decoder_step(D);
     D->P.trace = nullptr;
+    D->P.dbg = nullptr;
     if (rc == GGB_OK) {
         cudaError_t e = cudaMemcpyAsync(stamps, dev, bytes, cudaMemcpyDeviceToHost, ggb_cuda_stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(ggb_cuda_stream());

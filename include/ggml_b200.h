@@ -214,8 +214,8 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
                        const float *output_norm, const ggb_decoder_io *io, ggb_decoder **out);
 int ggb_decoder_step(ggb_decoder *d); /* enqueue one token; capturable into a ggb_graph */
 int ggb_decoder_free(ggb_decoder *d);
-/* run ONE traced step: stamps[n_phases][grid][4] SM-clock values (phase start, after prologue, after
- * the tiles, after the grid barrier), kinds[n_phases] phase kinds (0 QKV, 1 ATTN, 2 COMBINE, 3 O,
+/* run ONE traced step: stamps[n_phases][grid][4] %globaltimer values in ns (phase start, after the
+ * prologue = inputs arrived, end, end), kinds[n_phases] phase kinds (0 QKV, 1 ATTN, 2 COMBINE, 3 O,
  * 4 GATE_UP, 5 DOWN, 6 LOGITS, 7 SAMPLE) */
 int ggb_decoder_trace(ggb_decoder *d, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid);
 

@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(64, 1) tma_only_kernel(const uint8_t *p, size_
     }
 }
 
+static int g_grid = 148;
 template <typename F> float time_ms(F f, int iters) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -236,7 +237,7 @@ void run_stream(const uint8_t *qs, const __half *d, const uint8_t *act, float *y
     auto fn = stream_kernel<NW, PPW, SLOTS, MODE>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaMemset(y, 0, rows * 4));
-    const float ms = time_ms([&] { fn<<<148, NW * 32 + 32, smem>>>(qs, d, act, y, n_tiles); }, 10);
+    const float ms = time_ms([&] { fn<<<g_grid, NW * 32 + 32, smem>>>(qs, d, act, y, n_tiles); }, 10);
     CK(cudaGetLastError());
     const double bytes = (double)n_tiles * SLOT_BYTES;
     std::vector<float> h((size_t)n_tiles * ROWS);
@@ -244,8 +245,9 @@ void run_stream(const uint8_t *qs, const __half *d, const uint8_t *act, float *y
     int bad = -1;
     if (keep->empty()) *keep = h;
     else for (size_t i = 0; i < h.size() && i < keep->size(); i++) if (h[i] != (*keep)[i]) { bad = (int)i; break; }
-    printf("stream NW=%2d PPW=%d SLOTS=%d MODE=%d tile=%6d B smem=%6d: %.1f us  %.2f TB/s  %s\n", NW, PPW, SLOTS, MODE,
+    printf("grid %3d stream NW=%2d PPW=%d SLOTS=%d MODE=%d tile=%6d B smem=%6d: %.1f us  %.2f TB/s  %s\n", g_grid, NW, PPW, SLOTS, MODE,
            SLOT_BYTES, smem, ms * 1e3, bytes / ms / 1e9, bad < 0 ? "same" : "DIFF");
+    printf("     -> %.1f GB/s per CTA\n", bytes / ms / 1e6 / g_grid);
 }
 
 int main() {
@@ -293,16 +295,19 @@ int main() {
         const float ms = time_ms([&] { fn<<<148, 64, SL * SB + 16 * SL>>>(qs, per, out); }, 10);
         printf("tma_only 24 x 8 KB: %.1f us  %.2f TB/s\n", ms * 1e3, (double)per * 148 / ms / 1e9);
     }
-    std::vector<float> keep;
-    run_stream<16, 1, 5, 0>(qs, d, act, y, rows, &keep);
-    run_stream<16, 1, 5, 1>(qs, d, act, y, rows, &keep);
-    run_stream<16, 1, 6, 1>(qs, d, act, y, rows, &keep);
-    run_stream<8, 1, 10, 1>(qs, d, act, y, rows, &keep);
-    run_stream<8, 2, 5, 1>(qs, d, act, y, rows, &keep);
-    run_stream<24, 1, 4, 1>(qs, d, act, y, rows, &keep);
-    run_stream<28, 1, 3, 1>(qs, d, act, y, rows, &keep);
-    run_stream<16, 2, 3, 1>(qs, d, act, y, rows, &keep);
-    run_stream<12, 1, 8, 1>(qs, d, act, y, rows, &keep);
-    run_stream<4, 1, 20, 1>(qs, d, act, y, rows, &keep);
+    for (int g : {37, 148}) {
+        g_grid = g;
+        std::vector<float> keep;
+        run_stream<16, 1, 5, 1>(qs, d, act, y, rows, &keep);
+        run_stream<16, 2, 3, 1>(qs, d, act, y, rows, &keep);
+        run_stream<8, 2, 5, 1>(qs, d, act, y, rows, &keep);
+        run_stream<8, 4, 3, 1>(qs, d, act, y, rows, &keep);
+        run_stream<12, 2, 4, 1>(qs, d, act, y, rows, &keep);
+        run_stream<24, 1, 4, 1>(qs, d, act, y, rows, &keep);
+        run_stream<28, 1, 3, 1>(qs, d, act, y, rows, &keep);
+        run_stream<20, 1, 4, 1>(qs, d, act, y, rows, &keep);
+        run_stream<4, 4, 5, 1>(qs, d, act, y, rows, &keep);
+        run_stream<4, 8, 3, 1>(qs, d, act, y, rows, &keep);
+    }
     return 0;
 }
