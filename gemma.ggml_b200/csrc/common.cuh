@@ -138,6 +138,7 @@ static inline float ggb_synth_unit(float sigma) {
 // tables shared by several translation units (runtime.cu owns them)
 const uint16_t *ggb_exp_table_dev();  // 64 Ki fp16: exp(f16)
 const uint16_t *ggb_gelu_table_dev(); // 64 Ki fp16: gelu(f16)
+size_t ggb_tables_bytes();            // both tables are one allocation starting at ggb_exp_table_dev()
 const float *ggb_rope_cos_dev();      // [n_ctx][n_dims/2]
 const float *ggb_rope_sin_dev();
 int ggb_rope_n_ctx();

@@ -72,6 +72,7 @@ struct Phase {
     int n_rows;      // logical rows of the phase
     int rot;         // CTA rotation so remainders do not always land on the same SMs
     int uq, ur;      // n_units / grid, n_units % grid
+    int pstep, sstep; // 16 / ksegs, 16 % ksegs: how a warp's (row pair, segment) advances from pass to pass
     int resid_embed; // residual = embedding row of the token (layer 0, O phase)
     const uint8_t *stream; // pass stream of the phase
     // flagged inputs: QKV / GATE_UP / LOGITS: fp32 x [E] (null in layer 0: embedding row); O: fp32 kqv [H*d];
@@ -153,10 +154,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar) : "memory");
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.  The weight stream is read once
+// per token and is 11x the L2: it carries an evict-first policy so that it does not push the small hot data
+// (exp / gelu tables, flagged buffers, norm weights, KV cache) out of L2 between two layers.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
 }
 // async copy global -> shared through L2 only (.cg)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
@@ -185,6 +195,12 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) { // unsigned b
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+}
+
+// fp16 table lookup (exp / gelu).  The tables are pinned in L2 by the launch's access-policy window: under the
+// weight stream a demand miss to HBM costs ~1 us of queueing, and these lookups sit on every layer's critical path
+__device__ __forceinline__ float table_f16(const uint16_t *table, float x) {
+    return half_bits_to_float(__ldg(table + float_to_half_bits(x)));
 }
 
 // ---- flagged words.  An aligned 8-byte access is single-copy atomic, so payload and tag are seen together;
@@ -260,6 +276,7 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
     const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
     int slot = 0;
     uint32_t parity = 0;
+    const uint64_t pol = l2_evict_first_policy();
 #pragma unroll 1
     for (int pi = 0; pi < P.n_phases; pi++) {
         const Phase *ph = P.phases + pi;
@@ -275,7 +292,7 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
             const uint32_t bytes = (uint32_t)cnt * F::PASS_BYTES;
             mbar_wait(empty0 + 8 * slot, parity ^ 1u);
             mbar_expect_tx(full0 + 8 * slot, bytes);
-            bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot);
+            bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot, pol);
             src += bytes;
             n -= cnt;
             if (++slot == kSlots) {
@@ -537,8 +554,8 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     const int pieces = d / 8; // 16-byte pieces per row
 #pragma unroll 1
     for (int it = cta + ph.rot >= G ? cta + ph.rot - G : cta + ph.rot; it < n_items; it += G) {
-        const int hh = it % hsplit, gc = it / hsplit;
-        const int g = gc / nchunk, c = gc % nchunk;
+        const int hh = hsplit == 2 ? (it & 1) : 0, gc = hsplit == 2 ? (it >> 1) : it;
+        const int g = Hkv == 1 ? 0 : gc / nchunk, c = Hkv == 1 ? gc : gc % nchunk;
         const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
         const int h0 = g * Gq + hh * Gh;
         const int jnew = pos - p0; // row of the new position inside this chunk (if 0 <= jnew < np)
@@ -645,7 +662,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         if (warp < Gh) {
             const float sv = lane < np ? Ss[warp][lane] : -INFINITY;
             const float m = warp_max_f32(sv);
-            const float e = lane < np ? half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sv, m))]) : 0.0f;
+            const float e = lane < np ? table_f16(P.exp_table, __fsub_rn(sv, m)) : 0.0f;
             const float l = warp_sum_f32(e);
             Se[warp][lane] = e;
             if (lane == 0) {
@@ -738,7 +755,7 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
             for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, sm[c]);
             mx = warp_max_f32(mx);
             for (int c = lane; c < nchunk; c += 32)
-                sw[c] = half_bits_to_float(P.exp_table[float_to_half_bits(__fsub_rn(sm[c], mx))]);
+                sw[c] = table_f16(P.exp_table, __fsub_rn(sm[c], mx));
             __syncwarp();
             DBG_STAMP(3);
             float L = 0.0f, O = 0.0f;
@@ -836,8 +853,16 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             // blocks live in registers and are reloaded only when the warp's K segment changes (never for
             // K <= 2048, and never when 16 % ksegs == 0).
             {
-                const int pstep = kCW / ksegs, sstep = kCW % ksegs; // one division per phase, not per pass
-                int pair = warp / ksegs, seg = warp % ksegs, cur_seg = -1;
+                const int pstep = ph.pstep, sstep = ph.sstep; // from the host: no division on the critical path
+                int pair = warp, seg = 0, cur_seg = -1;
+                if (ksegs > 1) { // warp / ksegs, warp % ksegs by subtraction (at most 7 steps)
+                    pair = 0;
+                    seg = warp;
+                    while (seg >= ksegs) {
+                        seg -= ksegs;
+                        pair++;
+                    }
+                }
                 ActRegs A;
 #pragma unroll 1
                 for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
@@ -851,6 +876,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     if (j < cnt) {
                         const float keep = pass_dot<TYPE>(ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES, A, lane);
                         if ((lane & 15) == 0) part[(2 * pair + (lane >> 4)) * ksegs + seg] = keep;
+
                         pair += pstep;
                         seg += sstep;
                         if (seg >= ksegs) {
@@ -886,12 +912,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                         gsum = __fadd_rn(gsum, pg[k]);
                         usum = __fadd_rn(usum, pu[k]);
                     }
-                    const float gl = half_bits_to_float(P.gelu_table[float_to_half_bits(gsum)]);
+                    const float gl = table_f16(P.gelu_table, gsum);
                     const float x = __fmul_rn(gl, usum);
                     xb[r] = x;
                     if (ph.f32_out) ph.f32_out[(size_t)u0 * 32 + r] = x;
                 }
+                DBG_STAMP(12);
                 consumer_bar();
+                DBG_STAMP(13);
 #pragma unroll 1
                 for (int q0 = 4 * warp; q0 < nu; q0 += 4 * kCW) {
                     const int u = q0 + (lane >> 3);
@@ -1150,6 +1178,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
             ph.n_units = n_pairs; ph.unit_passes = ph.ksegs; ph.unit_rows = 2;
         }
         ph.uq = ph.n_units / sms; ph.ur = ph.n_units % sms;
+        ph.pstep = kCW / ph.ksegs; ph.sstep = kCW % ph.ksegs;
         const long long max_units = (ph.n_units + sms - 1) / sms;
         if (max_units * ph.unit_rows * ph.ksegs > kPartFloats) { ok = false; why = "phase does not fit the partial table"; }
         if (ph.K > kMaxK) { ok = false; why = "activation row too long"; }
@@ -1274,8 +1303,25 @@ int ggb_decoder_step(ggb_decoder *D) {
     void *args[] = {(void *)&D->P};
     const void *fn = D->P.type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
                                                 : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
-    // cooperative launch: the flagged data flow needs every CTA resident (a waiting CTA spins)
-    GGB_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)D->grid), dim3(kThreads), args, D->smem, ggb_cuda_stream()));
+    // cooperative launch: the flagged data flow needs every CTA resident (a waiting CTA spins).  The fp16
+    // exp / gelu tables are pinned in the persisting part of L2 for this kernel.
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)D->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = D->smem;
+    cfg.stream = ggb_cuda_stream();
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[1].val.accessPolicyWindow.base_ptr = (void *)ggb_exp_table_dev();
+    at[1].val.accessPolicyWindow.num_bytes = ggb_tables_bytes();
+    at[1].val.accessPolicyWindow.hitRatio = 1.0f;
+    at[1].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[1].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cfg.attrs = at;
+    cfg.numAttrs = 2;
+    GGB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
     ggb_count_launch();
     return GGB_OK;
 }

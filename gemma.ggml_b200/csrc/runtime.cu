@@ -65,6 +65,7 @@ void ggb_count_launch(int n) {
 }
 const uint16_t *ggb_exp_table_dev() { return g_ctx.exp_table; }
 const uint16_t *ggb_gelu_table_dev() { return g_ctx.gelu_table; }
+size_t ggb_tables_bytes() { return 2 * 65536 * 2; } // exp then gelu, contiguous from ggb_exp_table_dev()
 const float *ggb_rope_cos_dev() { return g_ctx.rope_cos; }
 const float *ggb_rope_sin_dev() { return g_ctx.rope_sin; }
 int ggb_rope_n_ctx() { return g_ctx.rope_n_ctx; }
@@ -91,8 +92,12 @@ static int build_tables() {
         e[i] = __half_as_ushort(__float2half_rn(expf(f)));
         g[i] = __half_as_ushort(__float2half_rn(host_gelu_f32(f)));
     }
-    GGB_CUDA(cudaMalloc(&g_ctx.exp_table, 65536 * 2));
-    GGB_CUDA(cudaMalloc(&g_ctx.gelu_table, 65536 * 2));
+    // one allocation for both tables: the decode kernel pins it in L2 with an access-policy window
+    GGB_CUDA(cudaMalloc(&g_ctx.exp_table, 2 * 65536 * 2));
+    g_ctx.gelu_table = g_ctx.exp_table + 65536;
+    // set-aside L2 for persisting lines (the tables; a lookup that misses under the weight stream costs ~1 us)
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 4u << 20);
+    cudaGetLastError();
     GGB_CUDA(cudaMemcpy(g_ctx.exp_table, e.data(), 65536 * 2, cudaMemcpyHostToDevice));
     GGB_CUDA(cudaMemcpy(g_ctx.gelu_table, g.data(), 65536 * 2, cudaMemcpyHostToDevice));
     return GGB_OK;
@@ -130,7 +135,6 @@ int ggb_shutdown(void) {
     cudaStreamSynchronize(g_ctx.stream);
     ggb_comm_destroy();
     cudaFree(g_ctx.exp_table);
-    cudaFree(g_ctx.gelu_table);
     cudaFree(g_ctx.rope_cos);
     cudaFree(g_ctx.rope_sin);
     for (auto &kv : g_ctx.prof) {

@@ -53,8 +53,8 @@ def main():
     rel = (db[ok] - db[ok, 0:1]) / 1965.0
     rel[db[ok] == 0] = np.nan
     print("inside phase %s (us since phase start, SM clock): median / max over CTAs per stamp" % os.environ.get("GGB_DBG_PHASE", "30"))
-    print("   median", np.round(np.nanmedian(rel, axis=0)[:13], 2))
-    print("   max   ", np.round(np.nanmax(rel, axis=0)[:13], 2))
+    print("   median", np.round(np.nanmedian(rel, axis=0)[:16], 2))
+    print("   max   ", np.round(np.nanmax(rel, axis=0)[:16], 2))
     print("last phases:")
     for r in rows[-2:]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
