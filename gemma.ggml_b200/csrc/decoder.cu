@@ -47,7 +47,7 @@ constexpr int kSeg = GGB_DEV_SEG_BLOCKS; // 64 blocks per K segment
 constexpr int kMaxG = 8;
 constexpr int kMaxE = 4096;         // longest norm-fed activation row
 constexpr int kMaxK = 24576;        // longest activation row kept in shared memory
-constexpr int kPartFloats = 2048;   // partial table: (rows of this CTA in a phase) x (K segments)
+constexpr int kPartFloats = 4096;   // partial table: (rows of this CTA in a phase) x (K segments)
 constexpr int kMaxChunks = 256;     // split-K chunks per head the COMBINE staging holds (n_ctx <= 8192)
 
 enum PhaseKind { PH_QKV = 0, PH_ATTN, PH_COMBINE, PH_O, PH_GATE_UP, PH_DOWN, PH_LOGITS, PH_SAMPLE };
@@ -119,8 +119,8 @@ constexpr int U_PART = U_BIAS + kMaxK / 32 * 4;
 constexpr int U_XS = 8192;
 constexpr int U_KC = 0, U_VC = 16384, U_SQ = 32768, U_S = 36864, U_E = 37888;
 constexpr int U_CM = kMaxChunks * 128, U_CL = U_CM + kMaxChunks * 4, U_CW = U_CL + kMaxChunks * 4;
-constexpr int U_BYTES = 38912;
-static_assert(U_PART + kPartFloats * 4 <= U_BYTES, "union region too small");
+constexpr int U_BYTES = U_PART + kPartFloats * 4;
+static_assert(U_E + 1024 <= U_BYTES, "union region too small for the attention view");
 static_assert(U_XS + kMaxE * 4 <= U_ACT_D && kMaxE <= U_XS, "xs overlaps the activation row");
 static_assert(U_CW + kMaxChunks * 4 <= U_BYTES, "combine staging too large");
 
