@@ -102,6 +102,10 @@ _CUDA_SIG = {
     "ggb_op_attn_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "ggb_op_embed_token": (i32, [vp, vp, f32, vp]),
     "ggb_op_sample_greedy": (i32, [vp, i64, vp, vp, vp]), "ggb_sample_scratch_bytes": (sz, [i64]),
+    "ggb_gemm_workspace_bytes": (sz, [i64, i64, i64]),
+    "ggb_op_gemm_bf16": (i32, [vp, vp, i64, vp, i64, vp, vp, sz]),
+    "ggb_op_cvt_f32_bf16": (i32, [vp, i64, vp]),
+    "ggb_op_attn_prefill": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]), "ggb_decoder_step": (i32, [vp]),
     "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),
     "ggb_comm_unique_id": (i32, [vp]), "ggb_comm_init": (i32, [vp, i32, i32]), "ggb_comm_destroy": (i32, []),

@@ -1,0 +1,459 @@
+// prefill.cu — the one genuinely dense contraction of the path: mul_mat with col_num = T > 1
+// (ref: src/hpc.cpp:216-277 called with ne11 = T; graph nodes at src/gemma_model.cpp:692-696, 493, 446-450,
+// 740).  Decode (T = 1) is 2 flop per weight byte and HBM-bound; prefill re-uses every weight T times, so it
+// belongs on the 5th-generation tensor cores:
+//
+//   C[T][N] (fp32) = A[T][K] (bf16 activations) x dequant(W[N][K] Q4_0 | Q8_0)^T       (+ residual)
+//
+// One CTA computes a 256 x 256 tile of C.  Per 64-wide K block
+//   * warps 0-3 (PRODUCERS) copy the A tile (bf16, L2) and DEQUANTISE the W tile (int8/int4 codes x fp16 block
+//     scale -> bf16, exact product rounded once) into shared memory in the canonical K-major 128-byte-swizzled
+//     UMMA layout, fence the async proxy and arrive on the stage's mbarrier;
+//   * one lane of warp 4 (MMA ISSUER) waits for the stage and issues 2 x 4 tcgen05.mma (M = 128, N = 256,
+//     K = 16, kind::f16, bf16 x bf16 -> fp32) whose accumulators live in TENSOR MEMORY (2 x 256 columns =
+//     all 512), then tcgen05.commit releases the stage;
+//   * after the last K block the producer warps become the EPILOGUE: tcgen05.ld 32 lanes x 32 columns at a
+//     time, add the residual, store fp32.
+// Small-N matrices (o-proj, down-proj: 16 tiles) are split along K so that every SM has a tile; the partial
+// tiles go to a workspace and are reduced in split order by a second kernel (deterministic).
+//
+// Numerics: weights q*d are exact in fp32 (8 x 11 bits) and rounded once to bf16; activations are rounded
+// to bf16 instead of being re-quantised to Q8_0 per 32 (the reference's INIT stage), so prefill agrees with
+// the reference within a tolerance (tests/test_prefill_gpu.py), not bit for bit — the decode path is the
+// bit-exact one.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 256, BN = 256, BK = 64;
+constexpr int kStages = 3;
+constexpr int kAStage = BM * BK * 2, kBStage = BN * BK * 2; // 32 KB each
+constexpr int kStageBytes = kAStage + kBStage;
+constexpr int kProducerWarps = 4, kProducerThreads = 128;
+constexpr int kGemmThreads = kProducerThreads + 32;
+constexpr int kTmemCols = 512;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// UMMA shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row
+// atoms of 1024 B (stride-dimension byte offset), descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);       // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                          // leading-dimension byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024u >> 4) << 32;               // stride-dimension byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, M = 128, N = 256
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) { // arrives on the mbarrier when all prior MMAs are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmArgs {
+    const uint8_t *qs; // weight payload plane [N][nb][16|32]
+    const __half *d;   // weight scale plane [N][nb]
+    int N, K, nb;      // nb = K / 32
+    const __nv_bfloat16 *a; // [T][K]
+    int T;
+    float *c;          // [T][ldc] (ksplit == 1) or workspace [ksplit][T][N]
+    int ldc;
+    const float *resid; // [T][ldc] or null (only with ksplit == 1)
+    int kblocks_per_split; // 64-wide K blocks per split
+};
+
+// int8 / int4 code -> fp32 without the conversion pipe: the (biased) code is dropped into the mantissa of
+// 2^23 with one PRMT, the bias is removed with one exact FADD, and one FMUL applies the block scale
+// (code * d is exact in fp32: 8 x 11 significant bits); the product is then rounded once to bf16.
+template <int SEL> __device__ __forceinline__ float code_to_f32(uint32_t biased_word, float bias, float d) {
+    return __fmul_rn(__fadd_rn(__uint_as_float(__byte_perm(biased_word, 0x4B000000u, SEL)), bias), d);
+}
+__device__ __forceinline__ void word_to_bf16x4(uint32_t biased_word, float bias, float d, uint32_t &o0, uint32_t &o1) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(code_to_f32<0x7540>(biased_word, bias, d), code_to_f32<0x7541>(biased_word, bias, d));
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(code_to_f32<0x7542>(biased_word, bias, d), code_to_f32<0x7543>(biased_word, bias, d));
+    o0 = *reinterpret_cast<uint32_t *>(&p0);
+    o1 = *reinterpret_cast<uint32_t *>(&p1);
+}
+// 16 bf16 of dequantised weights (two 16-byte chunks of the swizzled row) from 16 int8 codes
+__device__ __forceinline__ void dequant16_q8(const uint4 w, float d, uint4 &lo, uint4 &hi) {
+    const float bias = -8388736.0f; // -(2^23 + 128): code ^ 0x80 = code + 128
+    uint32_t out[8];
+    word_to_bf16x4(w.x ^ 0x80808080u, bias, d, out[0], out[1]);
+    word_to_bf16x4(w.y ^ 0x80808080u, bias, d, out[2], out[3]);
+    word_to_bf16x4(w.z ^ 0x80808080u, bias, d, out[4], out[5]);
+    word_to_bf16x4(w.w ^ 0x80808080u, bias, d, out[6], out[7]);
+    lo = make_uint4(out[0], out[1], out[2], out[3]);
+    hi = make_uint4(out[4], out[5], out[6], out[7]);
+}
+// one Q4_0 block (16 payload bytes -> 32 weights): elements 0..15 are the low nibbles, 16..31 the high ones
+__device__ __forceinline__ void dequant32_q4(const uint4 w, float d, uint4 (&o)[4]) {
+    const float bias = -8388616.0f; // -(2^23 + 8): value = nibble - 8
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        word_to_bf16x4(ws[i] & 0x0F0F0F0Fu, bias, d, lo[2 * i], lo[2 * i + 1]);
+        word_to_bf16x4((ws[i] >> 4) & 0x0F0F0F0Fu, bias, d, hi[2 * i], hi[2 * i + 1]);
+    }
+    o[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    o[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    o[2] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    o[3] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+}
+
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmArgs A) {
+    extern __shared__ uint8_t gemm_smem_raw[];
+    const uint32_t smem0 = (smem_u32(gemm_smem_raw) + 1023u) & ~1023u; // SWIZZLE_128B atoms need 1024-byte alignment
+    const uint32_t bars = smem0 + kStages * kStageBytes;                // full[kStages], empty[kStages], tmem_full
+    const uint32_t tmem_slot = bars + 8 * (2 * kStages + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, split = blockIdx.z;
+    const int kb0 = split * A.kblocks_per_split;
+    const int kb1 = min(kb0 + A.kblocks_per_split, (A.K + BK - 1) / BK);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(bars + 8 * s, kProducerWarps);        // full: one arrive per producer warp
+            mbar_init(bars + 8 * (kStages + s), 1);          // empty: tcgen05.commit
+        }
+        mbar_init(bars + 8 * 2 * kStages, 1);                // accumulators complete
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarps) { // the MMA warp owns tensor memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp < kProducerWarps) {
+        // ================= producers
+        int stage = 0;
+        uint32_t parity = 0;
+        for (int kb = kb0; kb < kb1; kb++) {
+            mbar_wait(bars + 8 * (kStages + stage), parity ^ 1u);
+            const uint32_t sa = smem0 + stage * kStageBytes, sb = sa + kAStage;
+            // A tile: 256 rows x 128 B; 8 threads per row (16-byte chunks), 16 rows per sweep
+            {
+                const int ch = tid & 7;
+#pragma unroll 4
+                for (int r = tid >> 3; r < BM; r += kProducerThreads / 8) {
+                    const int row = m0 + r;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (row < A.T) v = __ldg(reinterpret_cast<const uint4 *>(A.a + (size_t)row * A.K + (size_t)kb * BK) + ch);
+                    sts_u4(sa + r * 128 + ((ch ^ (r & 7)) << 4), v);
+                }
+            }
+            // W tile: 256 rows (output features) x 64 weights = 2 quant blocks per row
+            for (int r = tid; r < BN; r += kProducerThreads) {
+                const int row = n0 + r;
+                const uint32_t dst = sb + r * 128;
+                const int sw = r & 7;
+                if (row < A.N) {
+                    const size_t blk = (size_t)row * A.nb + (size_t)kb * 2;
+                    const __half2 dd = *reinterpret_cast<const __half2 *>(A.d + blk);
+                    const float d0 = __low2float(dd), d1 = __high2float(dd);
+                    if (TYPE == GGB_TYPE_Q8_0) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(A.qs + blk * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { // 16 codes -> chunks 2j, 2j+1
+                            uint4 lo, hi;
+                            dequant16_q8(__ldg(src + j), j < 2 ? d0 : d1, lo, hi);
+                            sts_u4(dst + (((2 * j) ^ sw) << 4), lo);
+                            sts_u4(dst + (((2 * j + 1) ^ sw) << 4), hi);
+                        }
+                    } else {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(A.qs + blk * 16);
+#pragma unroll
+                        for (int j = 0; j < 2; j++) { // one block -> chunks 4j .. 4j+3
+                            uint4 o[4];
+                            dequant32_q4(__ldg(src + j), j == 0 ? d0 : d1, o);
+#pragma unroll
+                            for (int u = 0; u < 4; u++) sts_u4(dst + (((4 * j + u) ^ sw) << 4), o[u]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) sts_u4(dst + (u << 4), make_uint4(0, 0, 0, 0));
+                }
+            }
+            // generic-proxy stores -> visible to the tensor core (async proxy), then hand the stage over
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * stage);
+            if (++stage == kStages) {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+        // ================= epilogue: warp w reads TMEM lanes 32w .. 32w+31 (accumulator rows)
+        mbar_wait(bars + 8 * 2 * kStages, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float *cbase = A.c + (size_t)split * A.T * A.ldc; // split > 0 only with the workspace (ldc == N)
+#pragma unroll 1
+        for (int mt = 0; mt < BM / 128; mt++) {
+            const int row = m0 + mt * 128 + warp * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * BN + c0), v);
+                const int col = n0 + c0;
+                if (row < A.T && col < A.N) { // N % 32 == 0
+                    float *dst = cbase + (size_t)row * A.ldc + col;
+                    const float *rs = A.resid ? A.resid + (size_t)row * A.ldc + col : nullptr;
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) {
+                        float4 o = make_float4(__uint_as_float(v[u]), __uint_as_float(v[u + 1]), __uint_as_float(v[u + 2]),
+                                               __uint_as_float(v[u + 3]));
+                        if (rs) {
+                            const float4 r4 = *reinterpret_cast<const float4 *>(rs + u);
+                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                        }
+                        *reinterpret_cast<float4 *>(dst + u) = o;
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= MMA issuer (one lane)
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, BN);
+            int stage = 0;
+            uint32_t parity = 0;
+            for (int kb = kb0; kb < kb1; kb++) {
+                mbar_wait(bars + 8 * stage, parity);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem0 + stage * kStageBytes, sb = sa + kAStage;
+                const uint64_t bdesc = umma_desc_sw128(sb);
+#pragma unroll
+                for (int mt = 0; mt < BM / 128; mt++) {
+                    const uint64_t adesc = umma_desc_sw128(sa + mt * 128 * 128);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++) // 16 bf16 = 32 B = 2 descriptor units along K
+                        umma_bf16(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                  (kb > kb0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(bars + 8 * (kStages + stage)); // frees the stage when these MMAs have read it
+                if (++stage == kStages) {
+                    stage = 0;
+                    parity ^= 1u;
+                }
+            }
+            umma_commit(bars + 8 * 2 * kStages); // accumulators final
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == kProducerWarps) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// partial tiles of a K-split GEMM summed in split order (+ residual)
+__global__ void splitk_reduce_kernel(const float *ws, int splits, int64_t T, int64_t N, float *c, int64_t ldc,
+                                     const float *resid) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * N) return;
+    const int64_t t = i / N, n = i % N;
+    float acc = ws[i];
+    for (int s = 1; s < splits; s++) acc += ws[(int64_t)s * T * N + i];
+    if (resid) acc += resid[t * ldc + n];
+    c[t * ldc + n] = acc;
+}
+
+__global__ void cvt_f32_bf16_kernel(const float *x, int64_t n, __nv_bfloat16 *y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// Causal attention of T query tokens at positions pos0 .. pos0+T-1 over the fp16 KV cache (position-major
+// [n_ctx][Hkv*d]).  One warp per (token, head), the reference's node order (ref: src/gemma_model.cpp:454-489):
+// kq = K . f16(q) (fp32 accumulate), soft_max_ext with the fp16 exp table and a double sum, P rounded to fp16,
+// kqv = V^T . P.  q is already roped and scaled.  CUDA cores: 4 % of the prefill flops.
+constexpr int kAttnWarps = 4;
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_prefill_kernel(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, int T,
+                    int pos0, int H, int Hkv, int d, const uint16_t *__restrict__ exp_table, float *__restrict__ out,
+                    int n_kv_max) {
+    extern __shared__ float attn_s[]; // [kAttnWarps][n_kv_max]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * kAttnWarps + warp;
+    if (item >= T * H) return;
+    const int t = item / H, h = item % H, g = h / (H / Hkv);
+    const int n_kv = pos0 + t + 1;
+    float *s = attn_s + (size_t)warp * n_kv_max;
+    const size_t stride = (size_t)Hkv * d;
+    const bool in = 8 * lane < d;
+    float qf[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) qf[e] = in ? __half2float(__float2half_rn(q[((size_t)t * H + h) * d + 8 * lane + e])) : 0.f;
+    float mx = -INFINITY;
+    for (int j = 0; j < n_kv; j++) {
+        float acc = 0.f;
+        if (in) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(kc + (size_t)j * stride + (size_t)g * d + 8 * lane);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __half22float2(h2[e]);
+                acc = fmaf(f.x, qf[2 * e], acc);
+                acc = fmaf(f.y, qf[2 * e + 1], acc);
+            }
+        }
+        acc = warp_sum_f32(acc);
+        if (lane == 0) s[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    __syncwarp();
+    double sum = 0.0;
+    for (int j = lane; j < n_kv; j += 32) {
+        const float e = half_bits_to_float(exp_table[float_to_half_bits(s[j] - mx)]);
+        s[j] = e;
+        sum += (double)e;
+    }
+    sum = warp_sum_f64(sum);
+    const float inv = (float)(1.0 / sum);
+    __syncwarp();
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) o[e] = 0.f;
+    for (int j = 0; j < n_kv; j++) {
+        const float p = __half2float(__float2half_rn(s[j] * inv)); // ggml converts P to fp16 for the V mat-mul
+        if (in) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(vc + (size_t)j * stride + (size_t)g * d + 8 * lane);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __half22float2(h2[e]);
+                o[2 * e] = fmaf(f.x, p, o[2 * e]);
+                o[2 * e + 1] = fmaf(f.y, p, o[2 * e + 1]);
+            }
+        }
+    }
+    if (in) {
+        float *dst = out + ((size_t)t * H + h) * d + 8 * lane;
+#pragma unroll
+        for (int e = 0; e < 8; e++) dst[e] = o[e];
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+size_t ggb_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K) {
+    (void)K;
+    return (size_t)8 * (size_t)T * (size_t)N * 4; // up to 8 K-splits
+}
+
+int ggb_op_cvt_f32_bf16(const float *x, int64_t n, void *y_bf16) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(x && y_bf16 && n > 0, "bad cvt args");
+    cvt_f32_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>(x, n, (__nv_bfloat16 *)y_bf16);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *c, int64_t ldc, const float *resid,
+                     void *workspace, size_t workspace_bytes) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(w && a_bf16 && c && T > 0, "bad gemm args");
+    const int64_t N = w->rows, K = w->cols;
+    GGB_CHECK_ARG(K % 64 == 0 && N % 32 == 0 && ldc >= N && ldc % 4 == 0, "gemm needs K %% 64 == 0, N %% 32 == 0 (N=%lld K=%lld)",
+                  (long long)N, (long long)K);
+    GGB_CHECK_ARG(w->type == GGB_TYPE_Q4_0 || w->type == GGB_TYPE_Q8_0, "gemm: weight type %d", w->type);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GGB_CUDA(cudaFuncSetAttribute(gemm_bf16w_kernel<GGB_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        GGB_CUDA(cudaFuncSetAttribute(gemm_bf16w_kernel<GGB_TYPE_Q8_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+        attr_done = true;
+    }
+    const int n_tiles = (int)((N + BN - 1) / BN), m_tiles = (int)((T + BM - 1) / BM), kblocks = (int)(K / BK);
+    // split K until every SM has a tile (partials are reduced in split order: deterministic)
+    int splits = 1;
+    const int sms = ggb_sm_count();
+    while (splits < 8 && n_tiles * m_tiles * splits * 2 <= sms && kblocks / (splits * 2) >= 4) splits *= 2;
+    if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * T * N * 4)) splits = 1;
+    GemmArgs A{};
+    A.qs = w->qs; A.d = w->d; A.N = (int)N; A.K = (int)K; A.nb = (int)w->nb;
+    A.a = (const __nv_bfloat16 *)a_bf16; A.T = (int)T;
+    A.kblocks_per_split = (kblocks + splits - 1) / splits;
+    if (splits == 1) { A.c = c; A.ldc = (int)ldc; A.resid = resid; }
+    else { A.c = (float *)workspace; A.ldc = (int)N; A.resid = nullptr; }
+    const dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)splits);
+    if (w->type == GGB_TYPE_Q4_0) gemm_bf16w_kernel<GGB_TYPE_Q4_0><<<grid, kGemmThreads, kGemmSmem, ggb_cuda_stream()>>>(A);
+    else gemm_bf16w_kernel<GGB_TYPE_Q8_0><<<grid, kGemmThreads, kGemmSmem, ggb_cuda_stream()>>>(A);
+    GGB_LAUNCH_CHECK();
+    if (splits > 1) {
+        const int64_t n = T * N;
+        splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>((const float *)workspace, splits, T, N, c, ldc, resid);
+        GGB_LAUNCH_CHECK();
+    }
+    return GGB_OK;
+}
+
+int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, int64_t T, int pos0, int H, int Hkv, int d,
+                        float *out) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(q && kcache && vcache && out && T > 0 && d % 8 == 0 && d <= 256 && H % Hkv == 0, "bad attn_prefill args");
+    const int n_kv_max = pos0 + (int)T;
+    const size_t smem = (size_t)kAttnWarps * n_kv_max * 4;
+    GGB_CHECK_ARG(smem <= 200 * 1024, "attn_prefill: context %d too long for the score buffer", n_kv_max);
+    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)((T * H + kAttnWarps - 1) / kAttnWarps);
+    attn_prefill_kernel<<<blocks, kAttnWarps * 32, smem, ggb_cuda_stream()>>>(q, (const __half *)kcache, (const __half *)vcache,
+                                                                             (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out,
+                                                                             n_kv_max);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+} // extern "C"

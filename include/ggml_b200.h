@@ -185,6 +185,20 @@ size_t ggb_sample_scratch_bytes(int64_t n);
 int ggb_op_argmax_shard(const float *x, int64_t n, int32_t index_offset, void *cand_out, void *scratch);
 int ggb_op_sample_from_candidates(const void *cands, int n_cands, int32_t *state, int32_t *history);
 
+/* ------------------------------------------------------------------ prefill (mul_mat with col_num = T > 1)
+ * K10 — C[T][N] = A[T][K] (bf16) x dequant(W[N][K])^T (+ residual): dequant -> bf16 tcgen05 GEMM with TMEM
+ * accumulators (csrc/prefill.cu).  replaces: mul_mat with ne11 = T (src/hpc.cpp:216-277) for the graph nodes
+ * at src/gemma_model.cpp:692-696, 493, 446-450, 740.  K %% 64 == 0, N %% 32 == 0; workspace (optional,
+ * ggb_gemm_workspace_bytes) enables the K-split used for small N. */
+size_t ggb_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K);
+int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *c, int64_t ldc, const float *resid,
+                     void *workspace, size_t workspace_bytes);
+int ggb_op_cvt_f32_bf16(const float *x, int64_t n, void *y_bf16);
+/* causal attention of T query tokens at positions pos0..pos0+T-1 over the fp16 KV cache (q already roped and
+ * scaled, fp32 [T][H*d]); reference node order kq -> soft_max_ext -> kqv (src/gemma_model.cpp:454-489) */
+int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, int64_t T, int pos0, int H, int Hkv, int d,
+                        float *out);
+
 /* ------------------------------------------------------------------ fused decode step
  * The whole per-token node list (ref: src/gemma_model.cpp:665-747) as ONE persistent cooperative
  * kernel: weights and KV stream through a shared-memory ring fed by TMA bulk copies while the
