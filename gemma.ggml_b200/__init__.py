@@ -121,6 +121,8 @@ _HOST_SIG = {
     "gm_set_state": (i32, [vp, i32, i32, i32]), "gm_run_steps": (i32, [vp, i32]), "gm_run_steps_profiled": (i32, [vp, i32]),
     "gm_get_state": (i32, [vp, P(i32), P(i32)]),
     "gm_generate": (i32, [vp, vp, i32, i32, vp, P(i32), P(C.c_double), P(C.c_double)]),
+    "gm_prefill": (i32, [vp, vp, i32, i32, P(i32)]), "gm_get_prefill_logits": (i32, [vp, i32, vp]),
+    "gm_last_prefill_gemm_flops": (C.c_double, [vp]),
     "gm_get_logits": (i32, [vp, vp]), "gm_get_capture": (i32, [vp, C.c_char_p, i32, vp, i64]),
     "gm_get_kv": (i32, [vp, i32, vp, vp]), "gm_kernels_per_step": (i32, [vp]), "gm_weight_bytes": (u64, [vp]),
     "mul_mat": (None, [i64, i64, i64, i64, i64, i64, i64, sz, i64, vp, vp, vp, vp, i32, vp]),
@@ -414,6 +416,22 @@ class GemmaModel:
     @property
     def is_fused(self):
         return bool(self.H.gm_is_fused(self.h))
+
+    def prefill(self, tokens, pos0=0):
+        """Batched prefill through the tcgen05 GEMM path; returns the greedy token of the last position."""
+        tokens = np.ascontiguousarray(tokens, dtype=np.int32)
+        nxt = i32()
+        check(self.H.gm_prefill(self.h, _ptr(tokens), tokens.size, int(pos0), C.byref(nxt)), "gm_prefill")
+        return nxt.value
+
+    def prefill_logits(self, row):
+        out = np.empty(self.cfg.n_vocab, dtype=np.float32)
+        check(self.H.gm_get_prefill_logits(self.h, int(row), _ptr(out)), "gm_get_prefill_logits")
+        return out
+
+    @property
+    def prefill_gemm_flops(self):
+        return float(self.H.gm_last_prefill_gemm_flops(self.h))
 
     def decode_step(self, token, pos):
         nxt = i32()

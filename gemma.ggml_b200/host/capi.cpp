@@ -50,6 +50,11 @@ int gm_generate(void *m, const int32_t *prompt, int n_prompt, int n_decode, int3
     memcpy(out, o.data(), o.size() * sizeof(int32_t));
     return 0;
 }
+int gm_prefill(void *m, const int32_t *tokens, int T, int32_t pos0, int32_t *next) {
+    return ((gemma_model *)m)->prefill(tokens, T, pos0, next);
+}
+int gm_get_prefill_logits(void *m, int row, float *host) { return ((gemma_model *)m)->get_prefill_logits(row, host); }
+double gm_last_prefill_gemm_flops(void *m) { return ((gemma_model *)m)->last_prefill_gemm_flops(); }
 int gm_get_logits(void *m, float *host) { return ((gemma_model *)m)->get_logits(host); }
 int gm_get_capture(void *m, const char *name, int layer, float *host, int64_t n) {
     return ((gemma_model *)m)->get_capture(name, layer, host, n);

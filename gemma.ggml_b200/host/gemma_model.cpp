@@ -78,6 +78,7 @@ gemma_model::~gemma_model() { free_all(); }
 
 void gemma_model::free_all() {
     ggb_sync();
+    free_prefill();
     ggb_graph_free(graph_);
     graph_ = nullptr;
     ggb_decoder_free(decoder_);
@@ -474,6 +475,108 @@ int gemma_model::generate(const std::vector<token_id> &prompt, int n_decode, std
     if (prefill_ms) *prefill_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     if (decode_ms) *decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
     return 0;
+}
+
+// ---------------------------------------------------------------- batched prefill (tcgen05 GEMMs)
+void gemma_model::free_prefill() {
+    void *bufs[] = {pf_ids_, pf_pos_, pf_x_, pf_xn_, pf_q_, pf_k_, pf_v_, pf_attn_, pf_sa_, pf_g_, pf_u_, pf_logits_, pf_a_, pf_ws_};
+    for (void *b : bufs)
+        if (b) ggb_buffer_free(b);
+    pf_ids_ = pf_pos_ = nullptr;
+    pf_x_ = pf_xn_ = pf_q_ = pf_k_ = pf_v_ = pf_attn_ = pf_sa_ = pf_g_ = pf_u_ = pf_logits_ = nullptr;
+    pf_a_ = pf_ws_ = nullptr;
+    pf_T_ = 0;
+}
+
+int gemma_model::alloc_prefill(int T) {
+    if (T <= pf_T_) return 0;
+    free_prefill();
+    const gemma_config &c = cfg_;
+    const size_t E = (size_t)c.n_embd, F = (size_t)c.n_ff, V = (size_t)c.n_vocab, t = (size_t)T;
+    const size_t QD = (size_t)c.n_head * c.head_dim, KD = (size_t)c.n_head_kv * c.head_dim;
+    size_t widest = E > QD ? E : QD;
+    if (F > widest) widest = F;
+    GM_TRY(ggb_buffer_alloc(t * 4, (void **)&pf_ids_));
+    GM_TRY(ggb_buffer_alloc(t * 4, (void **)&pf_pos_));
+    GM_TRY(ggb_buffer_alloc(t * E * 4, (void **)&pf_x_));
+    GM_TRY(ggb_buffer_alloc(t * E * 4, (void **)&pf_xn_));
+    GM_TRY(ggb_buffer_alloc(t * QD * 4, (void **)&pf_q_));
+    GM_TRY(ggb_buffer_alloc(t * KD * 4, (void **)&pf_k_));
+    GM_TRY(ggb_buffer_alloc(t * KD * 4, (void **)&pf_v_));
+    GM_TRY(ggb_buffer_alloc(t * QD * 4, (void **)&pf_attn_));
+    GM_TRY(ggb_buffer_alloc(t * E * 4, (void **)&pf_sa_));
+    GM_TRY(ggb_buffer_alloc(t * F * 4, (void **)&pf_g_));
+    GM_TRY(ggb_buffer_alloc(t * F * 4, (void **)&pf_u_));
+    GM_TRY(ggb_buffer_alloc(t * V * 4, (void **)&pf_logits_));
+    GM_TRY(ggb_buffer_alloc(t * widest * 2, &pf_a_));
+    // the K-split is only taken for small N (o-proj, down-proj, q/k/v): N <= max(E, QD)
+    pf_ws_bytes_ = ggb_gemm_workspace_bytes((int64_t)t, (int64_t)(E > QD ? E : QD), 0);
+    GM_TRY(ggb_buffer_alloc(pf_ws_bytes_, &pf_ws_));
+    pf_T_ = T;
+    return 0;
+}
+
+int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *next) {
+    const gemma_config &c = cfg_;
+    if (!tokens || T <= 0 || pos0 < 0 || pos0 + T > c.n_ctx || !built_ || plan_.size > 1) return GGB_ERR_ARG;
+    GM_TRY(alloc_prefill(T));
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab, t = T;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
+    const float q_scale = 1.0f / sqrtf((float)c.head_dim);
+    std::vector<int32_t> pos((size_t)T);
+    for (int i = 0; i < T; i++) pos[(size_t)i] = pos0 + i;
+    GM_TRY(ggb_upload(pf_ids_, tokens, (size_t)T * 4));
+    GM_TRY(ggb_upload(pf_pos_, pos.data(), (size_t)T * 4));
+    auto gemm = [&](const ggb_weight *w, int64_t K, float *out, const float *resid) -> int {
+        pf_flops_ += 2.0 * (double)t * (double)K * (double)ggb_weight_rows(w);
+        const int64_t N = ggb_weight_rows(w);
+        const bool small = N <= (E > QD ? E : QD);
+        return ggb_op_gemm_bf16(w, pf_a_, t, out, N, resid, small ? pf_ws_ : nullptr, small ? pf_ws_bytes_ : 0);
+    };
+    pf_flops_ = 0.0;
+    PROFILE("op_get_rows", ggb_op_get_rows(token_embd_, pf_ids_, t, sqrtf((float)c.n_embd), pf_x_));   // :675-679
+    for (int il = 0; il < c.n_layer; il++) {
+        const gemma_layer &l = layers_[(size_t)il];
+        void *kc = k_cache_[(size_t)il], *vc = v_cache_[(size_t)il];
+        PROFILE("op_rms_norm", ggb_op_rms_norm(pf_x_, l.attn_norm, c.eps, E, t, pf_xn_, nullptr));      // :690
+        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_xn_, t * E, pf_a_));
+        PROFILE("op_mul_mat", gemm(l.attn_q, E, pf_q_, nullptr));                                        // :692-696
+        PROFILE("op_mul_mat", gemm(l.attn_k, E, pf_k_, nullptr));
+        PROFILE("op_mul_mat", gemm(l.attn_v, E, pf_v_, nullptr));
+        PROFILE("op_rope", ggb_op_rope_neox(pf_q_, pf_pos_, c.head_dim, c.n_head, t, pf_q_));            // :698-716
+        PROFILE("op_rope", ggb_op_scale(pf_q_, q_scale, t * QD, pf_q_));                                 // :708
+        PROFILE("op_rope", ggb_op_rope_neox(pf_k_, pf_pos_, c.head_dim, c.n_head_kv, t, pf_k_));
+        // KV store (ref :499-518): rows pos0 .. pos0+T-1 of the position-major fp16 cache are contiguous
+        PROFILE("op_cpy", ggb_op_cpy_f32_f16(pf_k_, t * KD, (char *)kc + (size_t)pos0 * (size_t)KD * 2));
+        PROFILE("op_cpy", ggb_op_cpy_f32_f16(pf_v_, t * KD, (char *)vc + (size_t)pos0 * (size_t)KD * 2));
+        PROFILE("op_attn", ggb_op_attn_prefill(pf_q_, kc, vc, t, pos0, c.n_head, c.n_head_kv, c.head_dim, pf_attn_)); // :454-489
+        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_attn_, t * QD, pf_a_));
+        PROFILE("op_mul_mat", gemm(l.attn_output, QD, pf_sa_, pf_x_));                                   // :493 + :723
+        PROFILE("op_rms_norm", ggb_op_rms_norm(pf_sa_, l.ffn_norm, c.eps, E, t, pf_xn_, nullptr));       // :727
+        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_xn_, t * E, pf_a_));
+        PROFILE("op_mul_mat", gemm(l.ffn_gate, E, pf_g_, nullptr));                                      // :446-447
+        PROFILE("op_mul_mat", gemm(l.ffn_up, E, pf_u_, nullptr));
+        PROFILE("op_gelu", ggb_op_gelu(pf_g_, t * F, pf_g_));                                            // :448
+        PROFILE("op_gelu", ggb_op_mul(pf_g_, pf_u_, t * F, pf_g_));                                      // :449
+        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_g_, t * F, pf_a_));
+        PROFILE("op_mul_mat", gemm(l.ffn_down, F, pf_x_, pf_sa_));                                       // :450 + :731
+    }
+    PROFILE("op_rms_norm", ggb_op_rms_norm(pf_x_, output_norm_, c.eps, E, t, pf_xn_, nullptr));          // :735
+    PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_xn_, t * E, pf_a_));
+    PROFILE("op_mul_mat", gemm(token_embd_, E, pf_logits_, nullptr));                                    // :740 (all T rows)
+    // greedy token of the last position; decode continues at pos0 + T
+    h_state_[0] = 0; h_state_[1] = pos0 + T - 1; h_state_[2] = 1; h_state_[3] = 0;
+    GM_TRY(ggb_upload(state_, h_state_, 16));
+    PROFILE("op_argmax", ggb_op_sample_greedy(pf_logits_ + (size_t)(T - 1) * (size_t)V, V, state_, history_, sample_scratch_));
+    GM_TRY(ggb_download(h_state_ + 4, state_, 16));
+    if (next) *next = h_state_[4];
+    pf_last_T_ = T;
+    return 0;
+}
+
+int gemma_model::get_prefill_logits(int row, float *host) const {
+    if (!pf_logits_ || row < 0 || row >= pf_last_T_) return GGB_ERR_ARG;
+    return ggb_download(host, pf_logits_ + (size_t)row * (size_t)cfg_.n_vocab, (size_t)cfg_.n_vocab * 4);
 }
 
 int gemma_model::get_logits(float *host) const {

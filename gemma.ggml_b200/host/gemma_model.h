@@ -81,6 +81,15 @@ class gemma_model {
     int generate(const std::vector<token_id> &prompt, int n_decode, std::vector<token_id> &out, double *prefill_ms,
                  double *decode_ms);
 
+    // Batched prefill of T tokens at positions pos0 .. pos0+T-1 through the dequant -> bf16 tcgen05 GEMMs
+    // (ggb_op_gemm_bf16): the reference's PREFILL stage evaluates the same graph with col_num = T
+    // (ref: inference(), src/gemma_model.cpp:231-286; logits for all T rows, :740).  Fills the KV cache, leaves
+    // the decode state at (next token, pos0 + T) and returns the greedy token of the last position.
+    // Tolerance-exact (bf16 activations), unlike the token-by-token PREFILL above which is bit-exact.
+    int prefill(const token_id *tokens, int T, int32_t pos0, token_id *next);
+    int get_prefill_logits(int row, float *host) const; // row in [0, T) of the last prefill
+    double last_prefill_gemm_flops() const { return pf_flops_; }
+
     // one decode step through host buffers: H2D (token,pos), graph, D2H next token
     int decode_step(token_id token, int32_t pos, token_id *next);
     // device-resident loop: `steps` graph launches, no host round trip; pos_step 0 pins n_kv
@@ -127,4 +136,14 @@ class gemma_model {
     ggb_weight *sh_logits_ = nullptr;
     float *kqv_local_ = nullptr;
     void *cand_ = nullptr; // [tp_size] (value, index) candidates of the sharded arg-max
+    // prefill buffers, sized for pf_T_ tokens
+    int alloc_prefill(int T);
+    void free_prefill();
+    int pf_T_ = 0, pf_last_T_ = 0;
+    double pf_flops_ = 0.0;
+    int32_t *pf_ids_ = nullptr, *pf_pos_ = nullptr;
+    float *pf_x_ = nullptr, *pf_xn_ = nullptr, *pf_q_ = nullptr, *pf_k_ = nullptr, *pf_v_ = nullptr, *pf_attn_ = nullptr;
+    float *pf_sa_ = nullptr, *pf_g_ = nullptr, *pf_u_ = nullptr, *pf_logits_ = nullptr;
+    void *pf_a_ = nullptr, *pf_ws_ = nullptr; // bf16 A operand, K-split workspace
+    size_t pf_ws_bytes_ = 0;
 };

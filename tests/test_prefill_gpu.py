@@ -47,3 +47,66 @@ def test_gemm_bf16_matches_dequantised_model(gpu, wtype, T, N, K):
     gpu.sync()
     got2 = Cb.download(np.float32).reshape(T, N)
     assert np.all(np.abs(got2 - (ref - resid)) <= 1e-5 * scale + 1e-6)
+
+
+SMALL = {
+    "mqa": dict(n_embd=256, n_layer=3, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=2048, n_ctx=160),
+    "mha": dict(n_embd=512, n_layer=2, n_head=4, n_head_kv=4, head_dim=128, n_ff=4608, n_vocab=1024, n_ctx=96),
+}
+# Prefill rounds activations to bf16 (8 significant bits) where the reference re-quantises them to Q8_0 per
+# block of 32 (7 bits + sign relative to the block maximum), and weights q*d are rounded once to bf16.  Both
+# are ~0.4 % relative perturbations per mat-mul input; PREFILL_TOL bounds the resulting difference of the
+# logits / layer outputs relative to the tensor's maximum magnitude.
+PREFILL_TOL = 3e-2
+
+
+@pytest.mark.parametrize("name,T", [("mqa", 128), ("mqa", 37), ("mha", 64)])
+@pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
+def test_prefill_matches_oracle_ref_forward(gpu, name, wtype, T):
+    dims = SMALL[name]
+    cfg = gpu.make_config(wtype=wtype, sigma_embd=0.002, **dims)
+    m = gpu.GemmaModel(cfg)
+    m.init_synthetic_weights(); m.init_kv_cache(); m.build_compute_graph(capture_acts=False, fused=True)
+    om = O.Model(wtype=wtype, sigma_embd=0.002, **dims)
+    prompt = ((1 + 7919 * np.arange(T)) % dims["n_vocab"]).astype(np.int32)
+    nxt = m.prefill(prompt, 0)
+    rlog = om.forward(prompt, 0, O.REF)
+    glog = m.prefill_logits(T - 1)
+    tol = PREFILL_TOL * max(1.0, float(np.abs(rlog).max()))
+    assert np.abs(glog - rlog).max() < tol, float(np.abs(glog - rlog).max())
+    top = np.sort(rlog)[-2:]
+    if top[1] - top[0] > 2 * tol:  # the greedy token is only pinned when the reference's margin exceeds the tolerance
+        assert nxt == O.argmax(rlog)
+    # KV cache written by the prefill agrees with the reference's (fp16 values)
+    for il in range(dims["n_layer"]):
+        gk, gv = m.kv(il)
+        ok, ov = om.kv(il)
+        for g_, o_ in ((gk, ok), (gv, ov)):
+            gf, of = g_[:T].view(np.float16).astype(np.float32), o_[:T].view(np.float16).astype(np.float32)
+            assert np.abs(gf - of).max() < PREFILL_TOL * max(1.0, float(np.abs(of).max())), il
+    # decode continues from the prefilled cache: the next decode step runs and yields a valid token
+    tok2 = m.decode_step(nxt, T)
+    assert 0 <= tok2 < dims["n_vocab"]
+    m.close(); om.close()
+
+
+def test_prefill_agrees_with_token_by_token_decode_path(gpu):
+    """Same prompt through the bit-exact decode kernel (one token at a time) and through the GEMM prefill:
+    last-position logits agree within the tolerance, at a size the oracle would need minutes for."""
+    dims = dict(n_embd=1024, n_layer=4, n_head=8, n_head_kv=1, head_dim=128, n_ff=4096, n_vocab=8192, n_ctx=320)
+    T = 256
+    cfg = gpu.make_config(wtype=O.TYPE_Q8_0, sigma_embd=0.002, **dims)
+    prompt = ((1 + 7919 * np.arange(T)) % dims["n_vocab"]).astype(np.int32)
+    m = gpu.GemmaModel(cfg)
+    m.init_synthetic_weights(); m.init_kv_cache(); m.build_compute_graph(capture_acts=False, fused=True)
+    toks, _, _ = m.generate(prompt, 1)
+    dlog = m.logits()
+    m.init_kv_cache()
+    nxt = m.prefill(prompt, 0)
+    glog = m.prefill_logits(T - 1)
+    tol = PREFILL_TOL * max(1.0, float(np.abs(dlog).max()))
+    assert np.abs(glog - dlog).max() < tol
+    top = np.sort(dlog)[-2:]
+    if top[1] - top[0] > 2 * tol:
+        assert nxt == int(toks[0])
+    m.close()
