@@ -309,6 +309,61 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+def run_prefill(args):
+    """Secondary workload (BASELINE.json config 3): batched prefill of T tokens through the dequant -> bf16
+    tcgen05 GEMMs.  value = prompt tokens/s; roofline = tensor pipe (GEMM flops / cudaEvent time of the GEMM
+    launches vs the measured dense bf16 peak)."""
+    import gemma_ggml_b200 as G
+    G.init(0)
+    L = G.cuda_lib()
+    T = args.prefill_tokens
+    dims = dict(getattr(G, MODELS[args.model]), n_ctx=max(args.ctx, T))
+    m = G.GemmaModel(G.make_config(wtype=WTYPES[args.wtype], **dims))
+    m.init_synthetic_weights(); m.init_kv_cache(); m.build_compute_graph(capture_acts=False, fused=True)
+    prompt = ((1 + 7919 * np.arange(T)) % dims["n_vocab"]).astype(np.int32)
+    for _ in range(max(3, args.warmup if args.warmup < 8 else 3)):
+        m.prefill(prompt, 0)
+    G.sync()
+    steps = max(1, min(args.steps, 20))
+    L.ggb_prof_enable(1)
+    G.prof_reset()
+    with ClockSampler(0) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m.prefill(prompt, 0)
+        G.sync()
+        wall = time.perf_counter() - t0
+    gemm_ms, gemm_calls = G.prof_get("op_mul_mat")
+    classes = {}
+    for name in ("op_mul_mat", "op_attn", "op_rms_norm", "op_rope", "op_cvt", "op_gelu", "op_cpy", "op_get_rows", "op_argmax"):
+        tms, calls = G.prof_get(name)
+        classes[name] = {"ms_per_step": tms / steps, "launches_per_step": calls / steps}
+    L.ggb_prof_enable(0)
+    flops = m.prefill_gemm_flops
+    peak_tf = 1396.9
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    ach = flops / (gemm_ms / steps / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    line = {
+        "metric": "prefill tokens/s", "value": T * steps / wall, "unit": "tokens/s", "n_gpus": 1, "steps": steps,
+        "warmup": 3, "ms_per_step": 1000.0 * wall / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16 x bf16 -> fp32 (weights dequantised from " + args.wtype + ")",
+        "data": "synthetic (seeded random-init Gemma-architecture weights in ggml quant format)",
+        "config": {"workload": f"gemma-{args.model} {args.wtype} prefill of {T} tokens (host call: H2D ids, per-op launches, D2H token)",
+                   "timing": "eager per-op launches with cudaEvent probes per op class (the probes add launch gaps)"},
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                     "traffic": None, "kernel": "gemm_bf16w_kernel (tcgen05.mma kind::f16, TMEM accumulators)",
+                     "algorithmic_flops_per_step": flops, "gemm_ms_per_step": gemm_ms / steps,
+                     "launches_per_step": gemm_calls / steps, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+        "op_classes": classes,
+    }
+    m.close()
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -318,7 +373,8 @@ def main():
     ap.add_argument("--model", default="2b", choices=list(MODELS))
     ap.add_argument("--wtype", default="q4_0", choices=list(WTYPES))
     ap.add_argument("--ctx", type=int, default=2048)
-    ap.add_argument("--mode", default="fused", choices=["fused", "ops"])
+    ap.add_argument("--mode", default="fused", choices=["fused", "ops", "prefill"])
+    ap.add_argument("--prefill-tokens", type=int, default=512)
     ap.add_argument("--cpu-tokens", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -326,6 +382,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "prefill":
+        run_prefill(args)
     else:
         run_ours(args)
 

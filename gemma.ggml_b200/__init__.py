@@ -105,6 +105,7 @@ _CUDA_SIG = {
     "ggb_gemm_workspace_bytes": (sz, [i64, i64, i64]),
     "ggb_op_gemm_bf16": (i32, [vp, vp, i64, vp, i64, vp, vp, sz]),
     "ggb_op_cvt_f32_bf16": (i32, [vp, i64, vp]),
+    "ggb_op_rms_norm_bf16": (i32, [vp, vp, f32, i64, i64, vp]), "ggb_op_geglu_bf16": (i32, [vp, vp, i64, vp]),
     "ggb_op_attn_prefill": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]), "ggb_decoder_step": (i32, [vp]),
     "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),

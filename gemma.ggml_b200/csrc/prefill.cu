@@ -6,10 +6,10 @@
 //   C[T][N] (fp32) = A[T][K] (bf16 activations) x dequant(W[N][K] Q4_0 | Q8_0)^T       (+ residual)
 //
 // One CTA computes a 256 x 256 tile of C.  Per 64-wide K block
-//   * warps 0-3 (PRODUCERS) copy the A tile (bf16, L2) and DEQUANTISE the W tile (int8/int4 codes x fp16 block
+//   * warps 0-15 (PRODUCERS) copy the A tile (bf16, L2) and DEQUANTISE the W tile (int8/int4 codes x fp16 block
 //     scale -> bf16, exact product rounded once) into shared memory in the canonical K-major 128-byte-swizzled
 //     UMMA layout, fence the async proxy and arrive on the stage's mbarrier;
-//   * one lane of warp 4 (MMA ISSUER) waits for the stage and issues 2 x 4 tcgen05.mma (M = 128, N = 256,
+//   * one lane of warp 16 (MMA ISSUER) waits for the stage and issues 2 x 4 tcgen05.mma (M = 128, N = 256,
 //     K = 16, kind::f16, bf16 x bf16 -> fp32) whose accumulators live in TENSOR MEMORY (2 x 256 columns =
 //     all 512), then tcgen05.commit releases the stage;
 //   * after the last K block the producer warps become the EPILOGUE: tcgen05.ld 32 lanes x 32 columns at a
@@ -31,7 +31,7 @@ constexpr int BM = 256, BN = 256, BK = 64;
 constexpr int kStages = 3;
 constexpr int kAStage = BM * BK * 2, kBStage = BN * BK * 2; // 32 KB each
 constexpr int kStageBytes = kAStage + kBStage;
-constexpr int kProducerWarps = 4, kProducerThreads = 128;
+constexpr int kProducerWarps = 16, kProducerThreads = 512;
 constexpr int kGemmThreads = kProducerThreads + 32;
 constexpr int kTmemCols = 512;
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -173,64 +173,98 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp < kProducerWarps) {
-        // ================= producers
-        int stage = 0;
+        // ================= producers: thread t owns weight row n0 + t of the tile (64 weights per K block) and
+        // 8 of the 2048 16-byte chunks of the A tile.  The raw codes of the NEXT K block are requested before the
+        // current one is converted (register double buffer), and the A tile travels with cp.async, so the
+        // memory latency of both operands overlaps the dequantisation arithmetic.
+        // thread t owns ONE quant block (32 weights) per K block: row n0 + (t >> 1), block 2 kb + (t & 1)
+        const int wr = tid >> 1, whalf = tid & 1;
+        const int wrow = n0 + wr;
+        const bool wlive = wrow < A.N;
+        constexpr int PBW = TYPE == GGB_TYPE_Q8_0 ? 2 : 1; // 16-byte payload words per quant block
+        // register ring of raw codes, kStages K blocks deep: HBM latency under load (~2000 cycles) is longer
+        // than one K block of MMA time, so the codes are requested kStages blocks before they are converted
+        uint4 raw[kStages][PBW];
+        __half dd[kStages];
+        auto fetch = [&](int kb, uint4 (&r)[PBW], __half &d1) {
+            if (!wlive || kb >= kb1) return;
+            const size_t blk = (size_t)wrow * A.nb + (size_t)kb * 2 + whalf;
+            d1 = A.d[blk];
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.qs + blk * (TYPE == GGB_TYPE_Q8_0 ? 32 : 16));
+#pragma unroll
+            for (int j = 0; j < PBW; j++) r[j] = __ldg(src + j);
+        };
+#pragma unroll
+        for (int u = 0; u < kStages; u++) {
+            dd[u] = __float2half(0.f);
+#pragma unroll
+            for (int j = 0; j < PBW; j++) raw[u][j] = make_uint4(0, 0, 0, 0);
+            fetch(kb0 + u, raw[u], dd[u]);
+        }
         uint32_t parity = 0;
-        for (int kb = kb0; kb < kb1; kb++) {
-            mbar_wait(bars + 8 * (kStages + stage), parity ^ 1u);
-            const uint32_t sa = smem0 + stage * kStageBytes, sb = sa + kAStage;
-            // A tile: 256 rows x 128 B; 8 threads per row (16-byte chunks), 16 rows per sweep
-            {
-                const int ch = tid & 7;
-#pragma unroll 4
-                for (int r = tid >> 3; r < BM; r += kProducerThreads / 8) {
-                    const int row = m0 + r;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (row < A.T) v = __ldg(reinterpret_cast<const uint4 *>(A.a + (size_t)row * A.K + (size_t)kb * BK) + ch);
-                    sts_u4(sa + r * 128 + ((ch ^ (r & 7)) << 4), v);
-                }
-            }
-            // W tile: 256 rows (output features) x 64 weights = 2 quant blocks per row
-            for (int r = tid; r < BN; r += kProducerThreads) {
-                const int row = n0 + r;
-                const uint32_t dst = sb + r * 128;
-                const int sw = r & 7;
-                if (row < A.N) {
-                    const size_t blk = (size_t)row * A.nb + (size_t)kb * 2;
-                    const __half2 dd = *reinterpret_cast<const __half2 *>(A.d + blk);
-                    const float d0 = __low2float(dd), d1 = __high2float(dd);
-                    if (TYPE == GGB_TYPE_Q8_0) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(A.qs + blk * 32);
+        for (int kbase = kb0; kbase < kb1; kbase += kStages, parity ^= 1u) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) { // 16 codes -> chunks 2j, 2j+1
-                            uint4 lo, hi;
-                            dequant16_q8(__ldg(src + j), j < 2 ? d0 : d1, lo, hi);
-                            sts_u4(dst + (((2 * j) ^ sw) << 4), lo);
-                            sts_u4(dst + (((2 * j + 1) ^ sw) << 4), hi);
-                        }
-                    } else {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(A.qs + blk * 16);
+            for (int u = 0; u < kStages; u++) { // stage == u: the K loop is unrolled by the ring depth
+                const int kb = kbase + u;
+                if (kb >= kb1) break;
+                const int stage = u;
+                mbar_wait(bars + 8 * (kStages + stage), parity ^ 1u);
+                const uint32_t sa = smem0 + stage * kStageBytes, sb = sa + kAStage;
+                // A tile: 256 rows x 128 B; 8 threads per row (16-byte chunks), 64 rows per sweep
+                {
+                    const int ch = tid & 7;
 #pragma unroll
-                        for (int j = 0; j < 2; j++) { // one block -> chunks 4j .. 4j+3
-                            uint4 o[4];
-                            dequant32_q4(__ldg(src + j), j == 0 ? d0 : d1, o);
-#pragma unroll
-                            for (int u = 0; u < 4; u++) sts_u4(dst + (((4 * j + u) ^ sw) << 4), o[u]);
+                    for (int r = tid >> 3; r < BM; r += kProducerThreads / 8) {
+                        const int row = m0 + r;
+                        const uint32_t dst = sa + r * 128 + ((ch ^ (r & 7)) << 4);
+                        if (row < A.T) {
+                            const void *src = reinterpret_cast<const uint4 *>(A.a + (size_t)row * A.K + (size_t)kb * BK) + ch;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        } else {
+                            sts_u4(dst, make_uint4(0, 0, 0, 0));
                         }
                     }
-                } else {
+                }
+                // W tile: convert the block requested kStages K blocks ago, then request block kb + kStages
+                {
+                    uint4 cur[PBW];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) sts_u4(dst + (u << 4), make_uint4(0, 0, 0, 0));
+                    for (int j = 0; j < PBW; j++) cur[j] = raw[u][j];
+                    const float d0 = __half2float(dd[u]);
+                    fetch(kb + kStages, raw[u], dd[u]);
+                    const uint32_t dst = sb + wr * 128;
+                    const int sw = wr & 7, c0 = 4 * whalf; // this block's four 16-byte chunks of the 128-byte row
+                    uint4 o[4];
+                    if (wlive) {
+                        if (TYPE == GGB_TYPE_Q8_0) {
+                            dequant16_q8(cur[0], d0, o[0], o[1]);
+                            dequant16_q8(cur[PBW - 1], d0, o[2], o[3]);
+                        } else {
+                            dequant32_q4(cur[0], d0, o);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) o[q] = make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) sts_u4(dst + (((c0 + q) ^ sw) << 4), o[q]);
+                }
+                // The A copies of THIS block stay in flight (one L2 round trip) while the next block is converted:
+                // wait only for the previous block's group, then hand the PREVIOUS stage over.  generic-proxy /
+                // cp.async writes -> visible to the tensor core (async proxy) -> arrive.
+                asm volatile("cp.async.commit_group;\ncp.async.wait_group 1;" ::: "memory");
+                if (kb > kb0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bars + 8 * (stage == 0 ? kStages - 1 : stage - 1));
                 }
             }
-            // generic-proxy stores -> visible to the tensor core (async proxy), then hand the stage over
+        }
+        if (kb0 < kb1) { // last stage
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + 8 * stage);
-            if (++stage == kStages) {
-                stage = 0;
-                parity ^= 1u;
-            }
+            if (lane == 0) mbar_arrive(bars + 8 * ((kb1 - kb0 - 1) % kStages));
         }
         // ================= epilogue: warp w reads TMEM lanes 32w .. 32w+31 (accumulator rows)
         mbar_wait(bars + 8 * 2 * kStages, 0);
@@ -238,11 +272,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
         float *cbase = A.c + (size_t)split * A.T * A.ldc; // split > 0 only with the workspace (ldc == N)
 #pragma unroll 1
         for (int mt = 0; mt < BM / 128; mt++) {
-            const int row = m0 + mt * 128 + warp * 32 + lane;
+            const int lq = warp & 3, chalf = warp >> 2; // TMEM lane quarter of this warp, column quarter it drains
+            const int row = m0 + mt * 128 + lq * 32 + lane;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = chalf * (BN / 4); c0 < (chalf + 1) * (BN / 4); c0 += 32) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * BN + c0), v);
+                tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(mt * BN + c0), v);
                 const int col = n0 + c0;
                 if (row < A.T && col < A.N) { // N % 32 == 0
                     float *dst = cbase + (size_t)row * A.ldc + col;
@@ -307,6 +342,35 @@ __global__ void splitk_reduce_kernel(const float *ws, int splits, int64_t T, int
     for (int s = 1; s < splits; s++) acc += ws[(int64_t)s * T * N + i];
     if (resid) acc += resid[t * ldc + n];
     c[t * ldc + n] = acc;
+}
+
+// rms_norm * w -> bf16 (the A operand of the next GEMM): same double-sum order as rms_norm_kernel (elementwise.cu)
+__global__ void __launch_bounds__(GGB_DEV_NORM_THREADS)
+rms_norm_bf16_kernel(const float *__restrict__ x, const float *__restrict__ w, float eps, int64_t E, __nv_bfloat16 *__restrict__ y) {
+    __shared__ double s_w[GGB_DEV_NORM_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *xr = x + (int64_t)blockIdx.x * E;
+    double acc = 0.0;
+    for (int64_t i = tid; i < E; i += GGB_DEV_NORM_THREADS) {
+        const float v = xr[i];
+        acc = __dadd_rn(acc, (double)__fmul_rn(v, v));
+    }
+    acc = warp_sum_f64(acc);
+    if (lane == 0) s_w[warp] = acc;
+    __syncthreads();
+    double sum = s_w[0];
+#pragma unroll
+    for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, s_w[i]);
+    const float mean = __double2float_rn(__ddiv_rn(sum, (double)E));
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+    for (int64_t i = tid; i < E; i += GGB_DEV_NORM_THREADS)
+        y[(int64_t)blockIdx.x * E + i] = __float2bfloat16_rn(__fmul_rn(__fmul_rn(xr[i], scale), w[i]));
+}
+// gelu(gate) * up -> bf16 (fp16 gelu table like the reference's ggml_gelu; ref: src/gemma_model.cpp:448-449)
+__global__ void geglu_bf16_kernel(const float *gate, const float *up, int64_t n, const uint16_t *__restrict__ table,
+                                  __nv_bfloat16 *y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16_rn(__fmul_rn(half_bits_to_float(table[float_to_half_bits(gate[i])]), up[i]));
 }
 
 __global__ void cvt_f32_bf16_kernel(const float *x, int64_t n, __nv_bfloat16 *y) {
@@ -398,6 +462,22 @@ int ggb_op_cvt_f32_bf16(const float *x, int64_t n, void *y_bf16) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(x && y_bf16 && n > 0, "bad cvt args");
     cvt_f32_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>(x, n, (__nv_bfloat16 *)y_bf16);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_rms_norm_bf16(const float *x, const float *w, float eps, int64_t E, int64_t T, void *y_bf16) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(x && w && y_bf16 && E > 0 && T > 0, "bad rms_norm_bf16 args");
+    rms_norm_bf16_kernel<<<(unsigned)T, GGB_DEV_NORM_THREADS, 0, ggb_cuda_stream()>>>(x, w, eps, E, (__nv_bfloat16 *)y_bf16);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_geglu_bf16(const float *gate, const float *up, int64_t n, void *y_bf16) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(gate && up && y_bf16 && n > 0, "bad geglu_bf16 args");
+    geglu_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>(gate, up, n, ggb_gelu_table_dev(), (__nv_bfloat16 *)y_bf16);
     GGB_LAUNCH_CHECK();
     return GGB_OK;
 }

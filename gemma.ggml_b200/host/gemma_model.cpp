@@ -538,8 +538,7 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
     for (int il = 0; il < c.n_layer; il++) {
         const gemma_layer &l = layers_[(size_t)il];
         void *kc = k_cache_[(size_t)il], *vc = v_cache_[(size_t)il];
-        PROFILE("op_rms_norm", ggb_op_rms_norm(pf_x_, l.attn_norm, c.eps, E, t, pf_xn_, nullptr));      // :690
-        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_xn_, t * E, pf_a_));
+        PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_x_, l.attn_norm, c.eps, E, t, pf_a_));           // :690
         PROFILE("op_mul_mat", gemm(l.attn_q, E, pf_q_, nullptr));                                        // :692-696
         PROFILE("op_mul_mat", gemm(l.attn_k, E, pf_k_, nullptr));
         PROFILE("op_mul_mat", gemm(l.attn_v, E, pf_v_, nullptr));
@@ -552,17 +551,13 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
         PROFILE("op_attn", ggb_op_attn_prefill(pf_q_, kc, vc, t, pos0, c.n_head, c.n_head_kv, c.head_dim, pf_attn_)); // :454-489
         PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_attn_, t * QD, pf_a_));
         PROFILE("op_mul_mat", gemm(l.attn_output, QD, pf_sa_, pf_x_));                                   // :493 + :723
-        PROFILE("op_rms_norm", ggb_op_rms_norm(pf_sa_, l.ffn_norm, c.eps, E, t, pf_xn_, nullptr));       // :727
-        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_xn_, t * E, pf_a_));
+        PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_sa_, l.ffn_norm, c.eps, E, t, pf_a_));            // :727
         PROFILE("op_mul_mat", gemm(l.ffn_gate, E, pf_g_, nullptr));                                      // :446-447
         PROFILE("op_mul_mat", gemm(l.ffn_up, E, pf_u_, nullptr));
-        PROFILE("op_gelu", ggb_op_gelu(pf_g_, t * F, pf_g_));                                            // :448
-        PROFILE("op_gelu", ggb_op_mul(pf_g_, pf_u_, t * F, pf_g_));                                      // :449
-        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_g_, t * F, pf_a_));
+        PROFILE("op_gelu", ggb_op_geglu_bf16(pf_g_, pf_u_, t * F, pf_a_));                               // :448-449
         PROFILE("op_mul_mat", gemm(l.ffn_down, F, pf_x_, pf_sa_));                                       // :450 + :731
     }
-    PROFILE("op_rms_norm", ggb_op_rms_norm(pf_x_, output_norm_, c.eps, E, t, pf_xn_, nullptr));          // :735
-    PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_xn_, t * E, pf_a_));
+    PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_x_, output_norm_, c.eps, E, t, pf_a_));               // :735
     PROFILE("op_mul_mat", gemm(token_embd_, E, pf_logits_, nullptr));                                    // :740 (all T rows)
     // greedy token of the last position; decode continues at pos0 + T
     h_state_[0] = 0; h_state_[1] = pos0 + T - 1; h_state_[2] = 1; h_state_[3] = 0;

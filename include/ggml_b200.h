@@ -194,6 +194,10 @@ size_t ggb_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K);
 int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *c, int64_t ldc, const float *resid,
                      void *workspace, size_t workspace_bytes);
 int ggb_op_cvt_f32_bf16(const float *x, int64_t n, void *y_bf16);
+/* fused producers of the GEMM's bf16 A operand: rms_norm(x) * w, and gelu(gate) * up (graph_build_norm /
+ * graph_build_ffn, src/gemma_model.cpp:438-452) */
+int ggb_op_rms_norm_bf16(const float *x, const float *w, float eps, int64_t E, int64_t T, void *y_bf16);
+int ggb_op_geglu_bf16(const float *gate, const float *up, int64_t n, void *y_bf16);
 /* causal attention of T query tokens at positions pos0..pos0+T-1 over the fp16 KV cache (q already roped and
  * scaled, fp32 [T][H*d]); reference node order kq -> soft_max_ext -> kqv (src/gemma_model.cpp:454-489) */
 int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, int64_t T, int pos0, int H, int Hkv, int d,
