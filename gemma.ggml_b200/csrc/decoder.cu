@@ -73,6 +73,8 @@ struct Phase {
     int rot;         // CTA rotation so remainders do not always land on the same SMs
     int uq, ur;      // n_units / grid, n_units % grid
     int pstep, sstep; // 16 / ksegs, 16 % ksegs: how a warp's (row pair, segment) advances from pass to pass
+    int u_off;       // first unit of this rank (tensor parallel: units are split by rank, then by CTA)
+    int pad2_;
     int resid_embed; // residual = embedding row of the token (layer 0, O phase)
     const uint8_t *stream; // pass stream of the phase
     // flagged inputs: QKV / GATE_UP / LOGITS: fp32 x [E] (null in layer 0: embedding row); O: fp32 kqv [H*d];
@@ -99,7 +101,9 @@ struct DecoderParams {
     const __half *emb_d;
     int32_t *state, *history;
     int max_chunks;
-    ll_t *cand_ll;         // [2][grid]: per-CTA arg-max candidates (value, index)
+    ll_t *cand_ll;         // [2][R * grid]: per-CTA arg-max candidates (value, index) of every rank
+    int rank, R;           // tensor parallel: this GPU's rank and the number of GPUs (1 = single GPU)
+    long long peer_delta[8]; // byte offset from a local flagged word to the same word in rank r's memory (0 for self)
     uint32_t *seq;         // token sequence number = tag of the previous launch
     const uint16_t *exp_table, *gelu_table;
     const float *rope_cos, *rope_sin;
@@ -205,14 +209,21 @@ __device__ __forceinline__ float table_f16(const uint16_t *table, float x) {
 
 // ---- flagged words.  An aligned 8-byte access is single-copy atomic, so payload and tag are seen together;
 // relaxed gpu-scope accesses go to L2 (never a stale L1 line).  ll_get = the word if its tag matches, else poll.
-__device__ __forceinline__ void ll_put(ll_t *p, uint32_t payload, uint32_t tag) {
+// A flagged word is written to EVERY rank's copy of the buffer (tensor parallel: one-shot push all-gather over
+// NVLink peer stores, the consumer polls its local memory); with one GPU this is a single local store.
+__device__ __forceinline__ void ll_put(const DecoderParams &pe, ll_t *p, uint32_t payload, uint32_t tag) {
     const ll_t v = ((ll_t)tag << 32) | payload;
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#pragma unroll 1
+    for (int r = 1; r < pe.R; r++) { // peer_delta[0] is this rank (0); entries 1 .. R-1 are the peer mappings
+        const char *q = reinterpret_cast<const char *>(p) + pe.peer_delta[r];
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+    }
 }
-__device__ __forceinline__ void ll_put_f(ll_t *p, float x, uint32_t tag) { ll_put(p, __float_as_uint(x), tag); }
+__device__ __forceinline__ void ll_put_f(const DecoderParams &pe, ll_t *p, float x, uint32_t tag) { ll_put(pe, p, __float_as_uint(x), tag); }
 __device__ __forceinline__ ll_t ll_peek(const ll_t *p) {
     ll_t v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ uint32_t ll_get(ll_t v, const ll_t *p, uint32_t tag) {
@@ -541,7 +552,10 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     // with more than 4 query heads per KV head an item is split in two (heads 0..Gq/2-1 | the rest): the K/V
     // chunk is read twice (L2), the score / PV work per CTA halves and twice as many SMs take part
     const int hsplit = Gq > 4 ? 2 : 1, Gh = Gq / hsplit;
-    const int n_items = Hkv * nchunk * hsplit;
+    // (kv head, chunk) pairs are dealt round-robin to the ranks (pair gc belongs to rank gc % R: its K/V rows,
+    // including the new position's, live only there); a rank's items go round-robin to its CTAs
+    const int n_gc = Hkv * nchunk;
+    const int n_items = ((n_gc - P.rank + P.R - 1) / P.R) * hsplit; // this rank's items
     const int pos = n_pos - 1;
     const size_t kv_stride = (size_t)Hkv * d;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
@@ -554,7 +568,8 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     const int pieces = d / 8; // 16-byte pieces per row
 #pragma unroll 1
     for (int it = cta + ph.rot >= G ? cta + ph.rot - G : cta + ph.rot; it < n_items; it += G) {
-        const int hh = hsplit == 2 ? (it & 1) : 0, gc = hsplit == 2 ? (it >> 1) : it;
+        const int hh = hsplit == 2 ? (it & 1) : 0;
+        const int gc = (hsplit == 2 ? (it >> 1) : it) * P.R + P.rank;
         const int g = Hkv == 1 ? 0 : gc / nchunk, c = Hkv == 1 ? gc : gc % nchunk;
         const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
         const int h0 = g * Gq + hh * Gh;
@@ -666,8 +681,8 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             const float l = warp_sum_f32(e);
             Se[warp][lane] = e;
             if (lane == 0) {
-                ll_put_f(ph.m_ll + (size_t)(h0 + warp) * P.max_chunks + c, m, tag);
-                ll_put_f(ph.l_ll + (size_t)(h0 + warp) * P.max_chunks + c, l, tag);
+                ll_put_f(P, ph.m_ll + (size_t)(h0 + warp) * P.max_chunks + c, m, tag);
+                ll_put_f(P, ph.l_ll + (size_t)(h0 + warp) * P.max_chunks + c, l, tag);
             }
         }
         DBG_STAMP(6);
@@ -700,8 +715,8 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                     const int jh = kHG * u + hs;
                     if (jh < Gh) {
                         ll_t *out = ph.acc_ll + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
-                        ll_put_f(out, a0[u], tag);
-                        ll_put_f(out + 1, a1[u], tag);
+                        ll_put_f(P, out, a0[u], tag);
+                        ll_put_f(P, out + 1, a1[u], tag);
                     }
                 }
             }
@@ -721,12 +736,13 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
     const int d = P.d, slices = d / 32;
     const int n_tasks = P.H * slices;
     const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    const int n_items = P.Hkv * nchunk * (P.H / P.Hkv > 4 ? 2 : 1);
+    const int n_items = ((P.Hkv * nchunk - P.rank + P.R - 1) / P.R) * (P.H / P.Hkv > 4 ? 2 : 1); // this rank's ATTN items
     float *stage = reinterpret_cast<float *>(S.u);
     float *sm = reinterpret_cast<float *>(S.u + U_CM), *sl = reinterpret_cast<float *>(S.u + U_CL);
     float *sw = reinterpret_cast<float *>(S.u + U_CW);
 #pragma unroll 1
-    for (int task = ((cta + ph.rot) % G + G - n_items % G) % G; task < n_tasks; task += G) {
+    for (int tl = ((cta + ph.rot) % G + G - n_items % G) % G; tl * P.R + P.rank < n_tasks; tl += G) {
+        const int task = tl * P.R + P.rank; // tasks are dealt round-robin to the ranks
         const int h = task / slices, sli = task % slices;
         const ll_t *pa = ph.acc_ll + (size_t)h * P.max_chunks * d + sli * 32 + lane;
         const ll_t *pm = ph.m_ll + (size_t)h * P.max_chunks, *pl = ph.l_ll + (size_t)h * P.max_chunks;
@@ -780,7 +796,7 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
             const float r = __fdiv_rn(O, L);
             const size_t idx = (size_t)h * d + sli * 32 + lane;
             ph.f32_out[idx] = r;
-            ll_put_f(ph.out_ll + idx, r, tag);
+            ll_put_f(P, ph.out_ll + idx, r, tag);
             DBG_STAMP(4);
         }
         consumer_bar();
@@ -845,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             }
             if (P.trace) tr1 = (long long)gtime();
             // the residual of this thread's first row: requested before the passes, consumed in the epilogue
-            const int row0 = u0 * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows;
+            const int row0 = (ph.u_off + u0) * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows; // global rows of this CTA
             ll_t resid_w = 0;
             if (ph.resid_ll && kind != PH_GATE_UP && tid < nrows && row0 + tid < ph.n_rows) resid_w = ll_peek(ph.resid_ll + row0 + tid);
             // ---- passes: warp w owns passes w, w + 16, ... (Q4_0: one per slot; Q8_0: 8 passes per slot, so the
@@ -915,7 +931,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     const float gl = table_f16(P.gelu_table, gsum);
                     const float x = __fmul_rn(gl, usum);
                     xb[r] = x;
-                    if (ph.f32_out) ph.f32_out[(size_t)u0 * 32 + r] = x;
+                    if (ph.f32_out) ph.f32_out[(size_t)(ph.u_off + u0) * 32 + r] = x;
                 }
                 DBG_STAMP(12);
                 consumer_bar();
@@ -936,8 +952,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                                        (((uint32_t)(int)roundf(__fmul_rn(x4.z, id)) & 0xFFu) << 16) |
                                        (((uint32_t)(int)roundf(__fmul_rn(x4.w, id)) & 0xFFu) << 24);
                     if (ok) {
-                        ll_put(oq + (size_t)(u0 + u) * 8 + (lane & 7), w, tag);
-                        if ((lane & 7) == 0) ll_put(od + (u0 + u), (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
+                        ll_put(P, oq + (size_t)(ph.u_off + u0 + u) * 8 + (lane & 7), w, tag);
+                        if ((lane & 7) == 0) ll_put(P, od + (ph.u_off + u0 + u), (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
                     }
                 }
             } else {
@@ -953,7 +969,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     if (resid) total = __fadd_rn(total, ll_get_f(r == tid ? resid_w : ll_peek(resid + grow), resid + grow, tag));
                     else if (ph.resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, token, grow));
                     if (ph.out) ph.out[grow] = total;
-                    if (ph.out_ll) ll_put_f(ph.out_ll + grow, total, tag);
+                    if (ph.out_ll) ll_put_f(P, ph.out_ll + grow, total, tag);
                     if (total > best.v || best.i < 0) best = Best{total, grow};
                 }
                 if (kind == PH_LOGITS) { // this CTA's arg-max candidate (strict '>' / lowest index, ref: :538-543)
@@ -972,8 +988,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     if (tid == 0) {
                         Best b{S.cand_v[0], S.cand_i[0]};
                         for (int w = 1; w < kCW; w++) b = better(b, Best{S.cand_v[w], S.cand_i[w]});
-                        ll_put_f(P.cand_ll + cta, b.v, tag);
-                        ll_put(P.cand_ll + G + cta, (uint32_t)b.i, tag);
+                        ll_put_f(P, P.cand_ll + P.rank * G + cta, b.v, tag);
+                        ll_put(P, P.cand_ll + P.R * G + P.rank * G + cta, (uint32_t)b.i, tag);
                     }
                 }
             }
@@ -981,11 +997,11 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             attn_phase<TYPE>(P, S, ph, cta, G, n_pos, tag, dbg);
         } else if (kind == PH_COMBINE) {
             combine_phase<TYPE>(P, S, ph, cta, G, n_pos, tag, dbg);
-        } else { // PH_SAMPLE: CTA 0 picks the first maximum of the per-CTA candidates
+        } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
             if (cta == 0 && warp == 0) {
                 Best b{-INFINITY, -1};
-                for (int i = lane; i < G; i += 32) {
-                    const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + G + i;
+                for (int i = lane; i < P.R * G; i += 32) {
+                    const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + P.R * G + i;
                     const ll_t wv = ll_peek(pv), wi = ll_peek(pi2);
                     b = better(b, Best{ll_get_f(wv, pv, tag), (int)ll_get(wi, pi2, tag)});
                 }
@@ -1029,13 +1045,14 @@ struct RepackArgs {
     int gate_up; // logical row r: group r / 64, j = r % 64: j < 32 -> m[0] row 32*group + j, else m[1] row 32*group + j - 32
     int n_rows;  // logical rows
     int nb, ksegs;
+    int pair_off; // first row pair of the stream (tensor parallel: a rank streams only its own rows)
     uint8_t *dst;
 };
 // one block per pass; thread t < 128 copies block (t & 63) of row (t >> 6)
 template <int TYPE> __global__ void repack_kernel(RepackArgs A) {
     using F = Fmt<TYPE>;
     const long long p = blockIdx.x;
-    const int pair = (int)(p / A.ksegs), seg = (int)(p % A.ksegs);
+    const int pair = A.pair_off + (int)(p / A.ksegs), seg = (int)(p % A.ksegs);
     const int t = threadIdx.x;
     if (t >= 128) return;
     const int r = t >> 6, i = t & 63;
@@ -1081,9 +1098,11 @@ struct ggb_decoder {
     int grid = 0;
     size_t smem = 0;
     size_t stream_bytes = 0;
+    std::vector<void *> peer_maps; // cudaIpcOpenMemHandle mappings of the other ranks' scratch
 };
 
 static void decoder_release(ggb_decoder *D) {
+    for (void *pm : D->peer_maps) cudaIpcCloseMemHandle(pm);
     for (void *s : D->streams) cudaFree(s);
     cudaFree(D->d_phases);
     cudaFree(D->scratch);
@@ -1094,7 +1113,13 @@ extern "C" {
 
 int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
                        const float *output_norm, const ggb_decoder_io *io, ggb_decoder **out) {
+    return ggb_decoder_create_tp(dims, layers, token_embd, output_norm, io, 0, 1, out);
+}
+
+int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
+                          const float *output_norm, const ggb_decoder_io *io, int rank, int size, ggb_decoder **out) {
     GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(size >= 1 && size <= 8 && rank >= 0 && rank < size, "bad tensor-parallel rank %d / size %d", rank, size);
     GGB_CHECK_ARG(dims && layers && token_embd && output_norm && io && out, "null pointer");
     const int E = dims->n_embd, L = dims->n_layer, H = dims->n_head, Hkv = dims->n_head_kv, d = dims->head_dim;
     const int F = dims->n_ff, V = dims->n_vocab;
@@ -1120,6 +1145,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     P.exp_table = ggb_exp_table_dev(); P.gelu_table = ggb_gelu_table_dev();
     P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
     P.max_chunks = max_chunks;
+    P.rank = rank; P.R = size;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1135,7 +1161,7 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
     const size_t o_acc = carve((size_t)L * H * max_chunks * d);
     const size_t o_kqv = carve((size_t)L * QD), o_sa = carve((size_t)L * E);
     const size_t o_ff = carve((size_t)L * (F / 4 + F / 32));
-    const size_t o_cand = carve((size_t)2 * sms), o_seq = carve(1);
+    const size_t o_cand = carve((size_t)2 * sms * size), o_seq = carve(1);
     cudaError_t e = cudaMalloc(&D->scratch, off);
     if (e != cudaSuccess) {
         ggb_set_error("decoder scratch cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e));
@@ -1143,6 +1169,37 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         return GGB_ERR_CUDA;
     }
     cudaMemsetAsync(D->scratch, 0, off, ggb_cuda_stream());
+    for (int r = 0; r < 8; r++) P.peer_delta[r] = 0;
+    if (size > 1) {
+        // every rank maps every other rank's flagged buffers (cudaIpc over NVLink peer access); the 64-byte handles
+        // travel through the NCCL communicator, which also orders the memset above before any peer store
+        cudaIpcMemHandle_t mine;
+        GGB_CUDA(cudaIpcGetMemHandle(&mine, D->scratch));
+        void *d_h = nullptr;
+        GGB_CUDA(cudaMalloc(&d_h, sizeof(mine) * (size_t)size));
+        GGB_CUDA(cudaMemcpyAsync((char *)d_h + sizeof(mine) * (size_t)rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, ggb_cuda_stream()));
+        int rc = ggb_op_allgather((char *)d_h + sizeof(mine) * (size_t)rank, d_h, sizeof(mine));
+        std::vector<cudaIpcMemHandle_t> all((size_t)size);
+        if (rc == GGB_OK) {
+            GGB_CUDA(cudaMemcpyAsync(all.data(), d_h, sizeof(mine) * (size_t)size, cudaMemcpyDeviceToHost, ggb_cuda_stream()));
+            GGB_CUDA(cudaStreamSynchronize(ggb_cuda_stream()));
+        }
+        cudaFree(d_h);
+        if (rc != GGB_OK) { decoder_release(D); return rc; }
+        int slot = 1; // peer_delta[0] = self; the others in rank order
+        for (int r = 0; r < size; r++) {
+            if (r == rank) continue;
+            void *pm = nullptr;
+            cudaError_t ie = cudaIpcOpenMemHandle(&pm, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+            if (ie != cudaSuccess) {
+                ggb_set_error("decoder: cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(ie));
+                decoder_release(D);
+                return GGB_ERR_CUDA;
+            }
+            D->peer_maps.push_back(pm);
+            P.peer_delta[slot++] = (long long)((char *)pm - (char *)D->scratch);
+        }
+    }
     uint8_t *sb = (uint8_t *)D->scratch;
     ll_t *x_ll = (ll_t *)(sb + o_x), *qkv_ll = (ll_t *)(sb + o_qkv), *m_ll = (ll_t *)(sb + o_m), *l_ll = (ll_t *)(sb + o_l);
     ll_t *acc_ll = (ll_t *)(sb + o_acc), *kqv_ll = (ll_t *)(sb + o_kqv), *sa_ll = (ll_t *)(sb + o_sa);
@@ -1177,13 +1234,20 @@ int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *la
         } else {
             ph.n_units = n_pairs; ph.unit_passes = ph.ksegs; ph.unit_rows = 2;
         }
+        // tensor parallel: units are split by rank first (contiguous, balanced), then by CTA
+        const int u_total = ph.n_units;
+        ph.u_off = (int)(((long long)rank * u_total) / size);
+        ph.n_units = (int)(((long long)(rank + 1) * u_total) / size) - ph.u_off;
         ph.uq = ph.n_units / sms; ph.ur = ph.n_units % sms;
         ph.pstep = kCW / ph.ksegs; ph.sstep = kCW % ph.ksegs;
         const long long max_units = (ph.n_units + sms - 1) / sms;
         if (max_units * ph.unit_rows * ph.ksegs > kPartFloats) { ok = false; why = "phase does not fit the partial table"; }
         if (ph.K > kMaxK) { ok = false; why = "activation row too long"; }
         if (!ok) return ph;
-        const size_t n_passes = (size_t)n_pairs * ph.ksegs;
+        (void)n_pairs;
+        const size_t n_passes = (size_t)ph.n_units * ph.unit_passes; // this rank's passes only
+        A.pair_off = ph.u_off * (ph.unit_rows / 2);
+        if (n_passes == 0) return ph;
         void *stream = nullptr;
         cudaError_t ce = cudaMalloc(&stream, n_passes * pass_bytes);
         if (ce != cudaSuccess) { ok = false; why = "pass stream cudaMalloc failed"; return ph; }

@@ -2,6 +2,7 @@
 // (tensor binding :159-194, KV cache :361-401 / :428-436, graph builder :438-530 / :665-747,
 // inference :231-286, greedy round :548-575) with every node lowered to the C-ABI CUDA layer.
 #include "gemma_model.h"
+#include <cstdlib>
 
 #include <chrono>
 #include <cmath>
@@ -52,6 +53,7 @@ int gemma_model::init_tensor_parallel(int rank, int size) {
     if (!p.valid) return GGB_ERR_ARG;
     if (size > 1 && (ggb_comm_size() != size || ggb_comm_rank() != rank)) return GGB_ERR_ARG;
     plan_ = p;
+    if (const char *e = getenv("GGB_TP_FUSED")) tp_fused_ = atoi(e) != 0;
     return 0;
 }
 
@@ -190,7 +192,7 @@ int gemma_model::set_tensor(int tensor_id, const void *host_data, int64_t nbytes
 // ref: init_kv_cache (:361-401): per layer one F16 K and one F16 V tensor, zeroed.  Device layout is
 // position-major [n_ctx][n_head_kv*head_dim] for both (see csrc/attention.cu).
 int gemma_model::init_kv_cache() {
-    const size_t bytes = (size_t)cfg_.n_ctx * plan_.kv_heads * cfg_.head_dim * 2;
+    const size_t bytes = (size_t)cfg_.n_ctx * kv_heads_alloc() * cfg_.head_dim * 2;
     for (int il = 0; il < cfg_.n_layer; il++) {
         void *k = nullptr, *v = nullptr;
         if ((int)k_cache_.size() <= il) {
@@ -207,7 +209,7 @@ int gemma_model::init_kv_cache() {
 }
 
 int gemma_model::fill_kv_cache_synthetic(uint64_t seed) {
-    const int64_t n = (int64_t)cfg_.n_ctx * plan_.kv_heads * cfg_.head_dim;
+    const int64_t n = (int64_t)cfg_.n_ctx * kv_heads_alloc() * cfg_.head_dim;
     float *tmp = nullptr;
     GM_TRY(ggb_buffer_alloc((size_t)n * 4, (void **)&tmp));
     for (int il = 0; il < cfg_.n_layer; il++) {
@@ -372,7 +374,7 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
     built_ = false;
     GM_TRY(ggb_sync());
     GM_TRY(make_shards());
-    if (plan_.size > 1) fused = false; // the persistent kernel is single-GPU
+    if (plan_.size > 1) fused = tp_fused_; // multi-GPU: persistent kernel with peer stores, or ops + NCCL
     if (fused) {
         const gemma_config &c = cfg_;
         ggb_decoder_dims dims{c.n_embd, c.n_layer, c.n_head, c.n_head_kv, c.head_dim, c.n_ff, c.n_vocab, c.n_ctx, c.eps, 0};
@@ -383,7 +385,9 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
                                                l.ffn_gate, l.ffn_up, l.ffn_down, k_cache_[(size_t)il], v_cache_[(size_t)il]};
         }
         ggb_decoder_io io{state_, history_, sa_out_, l_out_, kqv_, capture_acts ? ffn_act_ : nullptr, result_norm_, logits_};
-        const int rc = ggb_decoder_create(&dims, ls.data(), token_embd_, output_norm_, &io, &decoder_);
+        const int rc = ggb_decoder_create_tp(&dims, ls.data(), token_embd_, output_norm_, &io, plan_.size > 1 ? plan_.rank : 0,
+                                             plan_.size > 1 ? plan_.size : 1, &decoder_);
+        if (rc == GGB_ERR_UNSUPPORTED && plan_.size > 1) return rc; // the KV cache is already in the fused layout
         if (rc == GGB_ERR_UNSUPPORTED) {
             decoder_ = nullptr; // shape outside the fused envelope: lower node by node instead
         } else if (rc) {
@@ -599,7 +603,7 @@ int gemma_model::get_capture(const std::string &name, int layer, float *host, in
 
 int gemma_model::get_kv(int layer, void *k_host, void *v_host) const {
     if (layer < 0 || layer >= (int)k_cache_.size()) return GGB_ERR_ARG;
-    const size_t bytes = (size_t)cfg_.n_ctx * plan_.kv_heads * cfg_.head_dim * 2;
+    const size_t bytes = (size_t)cfg_.n_ctx * kv_heads_alloc() * cfg_.head_dim * 2;
     if (k_host) GM_TRY(ggb_download(k_host, k_cache_[(size_t)layer], bytes));
     if (v_host) GM_TRY(ggb_download(v_host, v_cache_[(size_t)layer], bytes));
     return 0;

@@ -133,6 +133,11 @@ class gemma_model {
     ggb_decoder *decoder_ = nullptr;
     bool built_ = false;
     tp_plan plan_{};
+    // multi-GPU lowering: true = the persistent kernel with flagged peer stores over NVLink (ggb_decoder_create_tp;
+    // KV cache in the full [n_ctx][Hkv*d] layout, each rank fills the chunks it owns); false = per-operator
+    // kernels + NCCL allgathers (KV cache sharded by head).  GGB_TP_FUSED=0 selects the latter.
+    bool tp_fused_ = true;
+    int kv_heads_alloc() const { return (plan_.size > 1 && tp_fused_) ? cfg_.n_head_kv : plan_.kv_heads; }
     ggb_weight *sh_logits_ = nullptr;
     float *kqv_local_ = nullptr;
     void *cand_ = nullptr; // [tp_size] (value, index) candidates of the sharded arg-max

@@ -230,6 +230,12 @@ typedef struct ggb_decoder ggb_decoder;
 /* GGB_ERR_UNSUPPORTED when the shape is outside the fused kernel's envelope (callers then use ggb_op_*) */
 int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
                        const float *output_norm, const ggb_decoder_io *io, ggb_decoder **out);
+/* tensor-parallel form (one process per GPU, ggb_comm_init done): every mat-vec phase is split by output rows
+ * over `size` ranks, and every value that crosses CTAs is pushed as a flagged 8-byte word into EVERY rank's
+ * buffers with peer stores over NVLink (cudaIpc mappings exchanged at create time) — the all-gather is fused into
+ * the producing epilogue, no NCCL call on the token path.  Bit-identical to the single-GPU kernel. */
+int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
+                          const float *output_norm, const ggb_decoder_io *io, int rank, int size, ggb_decoder **out);
 int ggb_decoder_step(ggb_decoder *d); /* enqueue one token; capturable into a ggb_graph */
 int ggb_decoder_free(ggb_decoder *d);
 /* run ONE traced step: stamps[n_phases][grid][4] %globaltimer values in ns (phase start, after the

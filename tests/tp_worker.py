@@ -27,35 +27,40 @@ def main():
         "mqa": dict(n_embd=256, n_layer=3, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=2048, n_ctx=96),
     }
     first = True
-    for name, dims in configs.items():
-        for wtype in (G.TYPE_Q4_0, G.TYPE_Q8_0):
-            cfg = G.make_config(wtype=wtype, sigma_embd=0.002, **dims)
-            m = G.GemmaModel(cfg)
-            if first:
-                m.init_tensor_parallel(dist, rank, world)
-                first = False
-            else:
-                G.check(m.H.gm_init_tensor_parallel(m.h, rank, world), "gm_init_tensor_parallel")
-            m.init_synthetic_weights()
-            m.init_kv_cache()
-            m.build_compute_graph(capture_acts=True)
-            assert not m.is_fused
-            prompt = ((1 + 7919 * np.arange(9)) % dims["n_vocab"]).astype(np.int32)
-            toks, _, _ = m.generate(prompt, 7)
-            logits = m.logits()  # collective (gathers the shards)
-            if rank == 0:
-                om = O.Model(wtype=wtype, sigma_embd=0.002, **dims)
-                otoks, _, _ = om.generate(prompt, 7, O.DEV)
-                assert np.array_equal(toks, otoks), (name, wtype, toks, otoks)
-                ol = om.capture("result_output")
-                assert np.array_equal(logits.view(np.uint32), ol.view(np.uint32)), (name, wtype, np.abs(logits - ol).max())
-                for il in range(dims["n_layer"]):
-                    for cap in ("kqv_out", "sa_out", "ffn_act", "l_out"):
-                        a, b = m.capture(cap, il), om.capture(cap, il)
-                        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, wtype, cap, il)
-                om.close()
-            dist.barrier()
-            m.close()
+    # fused = the persistent kernel with flagged peer stores over NVLink (no NCCL on the token path);
+    # not fused = per-operator kernels + NCCL allgathers at the layer boundaries
+    for fused in (True, False):
+        os.environ["GGB_TP_FUSED"] = "1" if fused else "0"
+        for name, dims in configs.items():
+            for wtype in (G.TYPE_Q4_0, G.TYPE_Q8_0):
+                cfg = G.make_config(wtype=wtype, sigma_embd=0.002, **dims)
+                m = G.GemmaModel(cfg)
+                if first:
+                    m.init_tensor_parallel(dist, rank, world)
+                    first = False
+                else:
+                    G.check(m.H.gm_init_tensor_parallel(m.h, rank, world), "gm_init_tensor_parallel")
+                m.init_synthetic_weights()
+                m.init_kv_cache()
+                m.build_compute_graph(capture_acts=True)
+                assert m.is_fused == fused
+                prompt = ((1 + 7919 * np.arange(9)) % dims["n_vocab"]).astype(np.int32)
+                toks, _, _ = m.generate(prompt, 7)
+                logits = m.logits()  # collective (gathers the shards)
+                if rank == 0:
+                    om = O.Model(wtype=wtype, sigma_embd=0.002, **dims)
+                    otoks, _, _ = om.generate(prompt, 7, O.DEV)
+                    assert np.array_equal(toks, otoks), (fused, name, wtype, toks, otoks)
+                    ol = om.capture("result_output")
+                    assert np.array_equal(logits.view(np.uint32), ol.view(np.uint32)), (fused, name, wtype, np.abs(logits - ol).max())
+                    if not fused:  # the fused kernel dumps only the rows a rank computes itself
+                        for il in range(dims["n_layer"]):
+                            for cap in ("kqv_out", "sa_out", "ffn_act", "l_out"):
+                                a, b = m.capture(cap, il), om.capture(cap, il)
+                                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, wtype, cap, il)
+                    om.close()
+                dist.barrier()
+                m.close()
     dist.destroy_process_group()
     print(f"rank {rank} ok")
 
