@@ -42,6 +42,10 @@ constexpr int kCW = 16;             // consumer warps
 constexpr int kCT = kCW * 32;       // consumer threads
 constexpr int kThreads = kCT + 32;  // + producer warp
 constexpr int kSlots = 5;
+#ifndef GGB_MAX_OUTSTANDING
+#define GGB_MAX_OUTSTANDING 2
+#endif
+constexpr int kMaxOutstanding = GGB_MAX_OUTSTANDING; // TMA copies in flight per SM (of the kSlots ring slots)
 constexpr int kChunk = GGB_DEV_ATTN_CHUNK;
 constexpr int kSeg = GGB_DEV_SEG_BLOCKS; // 64 blocks per K segment
 constexpr int kMaxG = 8;
@@ -285,7 +289,7 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
     using F = Fmt<TYPE>;
     const uint32_t ring = smem_u32(&S.ring[0][0]);
     const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
-    int slot = 0;
+    int slot = 0, issued = 0;
     uint32_t parity = 0;
     const uint64_t pol = l2_evict_first_policy();
 #pragma unroll 1
@@ -302,8 +306,15 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
             const int cnt = min(n, F::PPS);
             const uint32_t bytes = (uint32_t)cnt * F::PASS_BYTES;
             mbar_wait(empty0 + 8 * slot, parity ^ 1u);
+            // at most kMaxOutstanding copies in flight per SM: enough to cover the HBM latency at full rate, and
+            // it bounds the queueing delay every small latency-critical access (flag polls, table lookups) sees
+            if (issued >= kMaxOutstanding) {
+                const int old = issued - kMaxOutstanding;
+                mbar_wait(full0 + 8 * (old % kSlots), (uint32_t)((old / kSlots) & 1));
+            }
             mbar_expect_tx(full0 + 8 * slot, bytes);
             bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot, pol);
+            issued++;
             src += bytes;
             n -= cnt;
             if (++slot == kSlots) {

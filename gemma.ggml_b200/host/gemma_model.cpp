@@ -49,11 +49,18 @@ tp_plan make_tp_plan(const gemma_config &c, int rank, int size) {
 
 int gemma_model::init_tensor_parallel(int rank, int size) {
     if (token_embd_) return GGB_ERR_ARG; // must precede weight creation
-    const tp_plan p = make_tp_plan(cfg_, rank, size);
+    tp_plan p = make_tp_plan(cfg_, rank, size);
+    if (const char *e = getenv("GGB_TP_FUSED")) tp_fused_ = atoi(e) != 0;
+    if (!p.valid && tp_fused_ && size >= 1 && rank >= 0 && rank < size && cfg_.n_vocab % (2 * size) == 0) {
+        // the persistent kernel splits every phase by row pairs / 32-row groups, whatever the head count: only
+        // the logits shard boundaries (V / size rows per rank, used by get_logits) come from the plan
+        p.kv_heads = cfg_.n_head_kv;
+        p.logits = {(int64_t)rank * (cfg_.n_vocab / size), cfg_.n_vocab / size};
+        p.valid = 1;
+    }
     if (!p.valid) return GGB_ERR_ARG;
     if (size > 1 && (ggb_comm_size() != size || ggb_comm_rank() != rank)) return GGB_ERR_ARG;
     plan_ = p;
-    if (const char *e = getenv("GGB_TP_FUSED")) tp_fused_ = atoi(e) != 0;
     return 0;
 }
 
