@@ -42,10 +42,8 @@ constexpr int kCW = 16;             // consumer warps
 constexpr int kCT = kCW * 32;       // consumer threads
 constexpr int kThreads = kCT + 32;  // + producer warp
 constexpr int kSlots = 5;
-#ifndef GGB_MAX_OUTSTANDING
-#define GGB_MAX_OUTSTANDING 2
-#endif
-constexpr int kMaxOutstanding = GGB_MAX_OUTSTANDING; // TMA copies in flight per SM (of the kSlots ring slots)
+constexpr int kMaxOutstanding = 2;  // ring copies in flight per SM (default; GGB_MAX_OUTSTANDING overrides)
+constexpr int kPrefetchChunks = 0;  // L2 look-ahead of the weight stream in ring chunks (GGB_PREFETCH_CHUNKS overrides)
 constexpr int kChunk = GGB_DEV_ATTN_CHUNK;
 constexpr int kSeg = GGB_DEV_SEG_BLOCKS; // 64 blocks per K segment
 constexpr int kMaxG = 8;
@@ -100,12 +98,16 @@ struct DecoderParams {
     int n_phases;
     int type;
     int E, H, Hkv, d, F, V, n_ctx;
+    // host-precomputed so that no phase starts with a chain of integer divisions (each ~100 cycles of dependent
+    // MUFU / I2F / uniform-register round trips): query heads per KV head, the ATTN head split, log2 of d/2, d/32, Hkv
+    int Gq, hsplit, Gh, hd_shift, sl_shift, kvh_shift;
     float eps, q_scale, emb_scale;
     const uint8_t *emb_qs; // planar embedding table (layer-0 get_rows)
     const __half *emb_d;
     int32_t *state, *history;
     int max_chunks;
     ll_t *cand_ll;         // [2][R * grid]: per-CTA arg-max candidates (value, index) of every rank
+    int max_outstanding, prefetch_chunks; // producer tuning (see producer_loop)
     int rank, R;           // tensor parallel: this GPU's rank and the number of GPUs (1 = single GPU)
     long long peer_delta[8]; // byte offset from a local flagged word to the same word in rank r's memory (0 for self)
     uint32_t *seq;         // token sequence number = tag of the previous launch
@@ -114,12 +116,13 @@ struct DecoderParams {
     long long *trace; // optional [n_phases][grid][4] %globaltimer stamps (ns): start, after prologue (inputs arrived), end, end
     long long *dbg;   // optional [grid][16] SM-clock stamps inside phase dbg_phase
     int dbg_phase;
+    int dbg_repeat; // debug: run ATTN / COMBINE this many times (idempotent), stamps from the last run (warm caches)
 };
 
 // union region: the views are never live at the same time
 //   mat-vec : act_q [kMaxK] | act_d half[kMaxK/32] | bias int[kMaxK/32] | part float[kPartFloats]
 //   norm    : xs float[kMaxE] at +8192 (act_q only uses [0, kMaxE) in a norm-fed phase)
-//   attn    : Kc half[32][256] | Vc half[32][256] | Sq half[8][256] | s float[8][32] | e float[8][32]
+//   attn    : Kc half[32][256] | Vc half[32][256] | Sq float[4][256] | s float[4][32] | e float[32][4]
 //   combine : stage float[kMaxChunks][32] | m float[kMaxChunks] | l float[kMaxChunks] | w float[kMaxChunks]
 constexpr int U_ACT_D = kMaxK;
 constexpr int U_BIAS = U_ACT_D + kMaxK / 32 * 2;
@@ -140,6 +143,10 @@ template <int TYPE> struct Smem {
     int cand_i[kCW];
     alignas(8) unsigned long long full_bar[kSlots];
     alignas(8) unsigned long long empty_bar[kSlots];
+    alignas(8) unsigned long long kv_bar; // ATTN: K / V chunk rows have landed (kCW arrivals + bytes)
+    long long tr[2]; // trace stamps of the current phase (thread 0)
+    int sched[4]; // the token's attention schedule: chunks, this rank's ATTN items, items % grid (kept out of registers:
+                  // the kernel runs at the 96-register limit of 17 warps per SM and a spill costs an L2 round trip)
     alignas(16) Phase ph[2];
 };
 
@@ -176,13 +183,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
         "l"(src), "r"(bytes), "r"(bar), "l"(pol)
         : "memory");
 }
-// async copy global -> shared through L2 only (.cg)
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// small async copy global -> shared (the issuing warp does not wait for the data)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
+// orders this thread's (and, through a preceding barrier, the CTA's) generic-proxy accesses before later async-proxy ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
     uint4 r;
@@ -242,7 +259,8 @@ __device__ __forceinline__ unsigned long long gtime() { // ns, one clock for the
     return t;
 }
 // fine-grained SM-clock stamps of ONE phase (debug builds of the trace): thread 0 of every CTA
-#define DBG_STAMP(i) do { if (dbg && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
+// (dbg is a flag, not a pointer, and the trace stamps live in shared memory: the kernel has no registers to spare)
+#define DBG_STAMP(i) do { if (dbg && threadIdx.x == 0) P.dbg[16 * blockIdx.x + (i)] = clock64(); } while (0)
 
 struct Best {
     float v;
@@ -284,6 +302,40 @@ template <int TYPE> __device__ __forceinline__ float embed_value(const DecoderPa
 }
 
 // ---------------------------------------------------------------- producer
+// The weight stream of this CTA, flattened over the token: chunk after chunk of <= PPS passes, never across a phase.
+template <int TYPE> struct ChunkWalk {
+    const DecoderParams &P;
+    int cta, G, pi, n;
+    const uint8_t *src;
+    __device__ __forceinline__ ChunkWalk(const DecoderParams &P_, int cta_, int G_) : P(P_), cta(cta_), G(G_), pi(-1), n(0), src(nullptr) {}
+    // next chunk: false when the token's stream is exhausted
+    __device__ __forceinline__ bool next(const uint8_t *&p, uint32_t &bytes) {
+        using F = Fmt<TYPE>;
+        while (n <= 0) {
+            if (++pi >= P.n_phases) return false;
+            const Phase *ph = P.phases + pi;
+            if (!is_matvec(ph->kind)) continue;
+            int u0, u1;
+            unit_range(cta, G, ph->rot, ph->uq, ph->ur, u0, u1);
+            const int up = ph->unit_passes;
+            n = (u1 - u0) * up;
+            src = ph->stream + (size_t)u0 * up * F::PASS_BYTES;
+        }
+        const int cnt = min(n, F::PPS);
+        bytes = (uint32_t)cnt * F::PASS_BYTES;
+        p = src;
+        src += bytes;
+        n -= cnt;
+        return true;
+    }
+};
+
+// Two walkers over the same chunk sequence.  The LOADER fills the shared-memory ring (cp.async.bulk, completion
+// on the slot's mbarrier).  The PREFETCHER runs P.prefetch_chunks chunks ahead of it and only asks L2 to fetch
+// (cp.async.bulk.prefetch.L2): the ring (180 KB per SM) is full during the latency-bound phases (ATTN, COMBINE,
+// prologues) and HBM would idle; with the look-ahead in L2 the stream keeps flowing and GATE_UP / DOWN find their
+// tail in L2 instead of waiting for HBM.  The look-ahead is bounded (chunks x 36 KB x 148 SMs, well inside the
+// 126 MB L2), and the later ring load marks the lines evict-first, so a consumed chunk is the first to leave.
 template <int TYPE>
 __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE> &S, int cta, int G) {
     using F = Fmt<TYPE>;
@@ -292,35 +344,34 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
     int slot = 0, issued = 0;
     uint32_t parity = 0;
     const uint64_t pol = l2_evict_first_policy();
+    const int max_out = P.max_outstanding;
+    ChunkWalk<TYPE> load(P, cta, G), pre(P, cta, G);
+    const uint8_t *src, *psrc;
+    uint32_t bytes, pbytes;
+    bool more = P.prefetch_chunks > 0;
+    for (int i = 0; i < P.prefetch_chunks && more; i++) {
+        more = pre.next(psrc, pbytes);
+        if (more && i >= kSlots) bulk_prefetch_l2(psrc, pbytes); // the first kSlots chunks go straight to the ring
+    }
 #pragma unroll 1
-    for (int pi = 0; pi < P.n_phases; pi++) {
-        const Phase *ph = P.phases + pi;
-        if (!is_matvec(ph->kind)) continue;
-        int u0, u1;
-        unit_range(cta, G, ph->rot, ph->uq, ph->ur, u0, u1);
-        const int up = ph->unit_passes;
-        int n = (u1 - u0) * up;
-        const uint8_t *src = ph->stream + (size_t)u0 * up * F::PASS_BYTES;
-#pragma unroll 1
-        while (n > 0) {
-            const int cnt = min(n, F::PPS);
-            const uint32_t bytes = (uint32_t)cnt * F::PASS_BYTES;
-            mbar_wait(empty0 + 8 * slot, parity ^ 1u);
-            // at most kMaxOutstanding copies in flight per SM: enough to cover the HBM latency at full rate, and
-            // it bounds the queueing delay every small latency-critical access (flag polls, table lookups) sees
-            if (issued >= kMaxOutstanding) {
-                const int old = issued - kMaxOutstanding;
-                mbar_wait(full0 + 8 * (old % kSlots), (uint32_t)((old / kSlots) & 1));
-            }
-            mbar_expect_tx(full0 + 8 * slot, bytes);
-            bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot, pol);
-            issued++;
-            src += bytes;
-            n -= cnt;
-            if (++slot == kSlots) {
-                slot = 0;
-                parity ^= 1u;
-            }
+    while (load.next(src, bytes)) {
+        if (more) {
+            more = pre.next(psrc, pbytes);
+            if (more) bulk_prefetch_l2(psrc, pbytes);
+        }
+        mbar_wait(empty0 + 8 * slot, parity ^ 1u);
+        // at most max_out copies in flight per SM: enough to cover the HBM latency at full rate, and it bounds the
+        // queueing delay every small latency-critical access (flag polls, table lookups) sees
+        if (issued >= max_out) {
+            const int old = issued - max_out;
+            mbar_wait(full0 + 8 * (old % kSlots), (uint32_t)((old / kSlots) & 1));
+        }
+        mbar_expect_tx(full0 + 8 * slot, bytes);
+        bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot, pol);
+        issued++;
+        if (++slot == kSlots) {
+            slot = 0;
+            parity ^= 1u;
         }
     }
 }
@@ -361,7 +412,7 @@ __device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lan
 // partials in registers and no staging pass is needed; the halves then split the quantisation by blocks.
 template <int TYPE>
 __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
-                                              uint32_t tag, float *f32_out, long long *dbg) {
+                                              uint32_t tag, float *f32_out, bool dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = P.E, nk = E / GGB_DEV_NORM_THREADS;
     DBG_STAMP(1);
@@ -550,62 +601,70 @@ __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int l
 }
 
 // ---------------------------------------------------------------- ATTN
-// items (kv head g, chunk of 32 positions, half of the query heads).  Same arithmetic as attention.cu attn_partial_kernel; rope + Q
-// scale are applied to q on load, and the item that owns the newest position ropes K, rounds K/V to fp16,
-// stores them in the cache and uses them.  The K/V rows of older positions do not depend on this token: their
-// copies are in flight while the CTA still waits for q.
+// items (kv head g, chunk of 32 positions, half of the query heads).  Same arithmetic as attention.cu
+// attn_partial_kernel; rope + Q scale are applied to q on load, and the item that owns the newest position ropes K,
+// rounds K/V to fp16, stores them in the cache and uses them.  The K/V rows of older positions do not depend on
+// this token: they travel as bulk copies (TMA, one per row, issued by lane 0 of the warp that will score the row;
+// completion on S.kv_bar) while the CTA still waits for q.  Everything here is issue-bound, so the instruction
+// count is what was minimised: q is staged as fp32 (converted once), a warp scores its two positions against all
+// heads of the item at once and reduces the 8 lane partials with ONE folded butterfly (9 shuffles instead of 40;
+// every sum adds the same pairs in the same order as the plain xor-butterfly), and P.V runs with one thread per
+// pair of dims for all heads (V converted once, the heads' weights in one LDS.128).
 template <int TYPE>
 __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                           int n_pos, uint32_t tag, long long *dbg) {
+                                           int n_pos, int n_items, uint32_t tag, uint32_t &kv_parity, bool dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = P.d, halfd = d / 2, Hkv = P.Hkv, Gq = P.H / Hkv;
-    const int nchunk = (n_pos + kChunk - 1) / kChunk;
+    const int d = P.d, halfd = d >> 1, Hkv = P.Hkv, Gq = P.Gq;
     // with more than 4 query heads per KV head an item is split in two (heads 0..Gq/2-1 | the rest): the K/V
     // chunk is read twice (L2), the score / PV work per CTA halves and twice as many SMs take part
-    const int hsplit = Gq > 4 ? 2 : 1, Gh = Gq / hsplit;
-    // (kv head, chunk) pairs are dealt round-robin to the ranks (pair gc belongs to rank gc % R: its K/V rows,
-    // including the new position's, live only there); a rank's items go round-robin to its CTAs
-    const int n_gc = Hkv * nchunk;
-    const int n_items = ((n_gc - P.rank + P.R - 1) / P.R) * hsplit; // this rank's items
+    const int hsplit = P.hsplit, Gh = P.Gh;
+    // (chunk, kv head) pairs gc = chunk * Hkv + g are dealt round-robin to the ranks (pair gc belongs to rank
+    // gc % R for every later token as well: its K/V rows, including the new position's, live only there); a rank's
+    // n_items items go round-robin to its CTAs
     const int pos = n_pos - 1;
     const size_t kv_stride = (size_t)Hkv * d;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
     const ll_t *q_all = ph.in_ll, *k_all = q_all + (size_t)P.H * d, *v_all = k_all + (size_t)Hkv * d;
     __half *Kc = reinterpret_cast<__half *>(S.u + U_KC), *Vc = reinterpret_cast<__half *>(S.u + U_VC);
-    __half *Sq = reinterpret_cast<__half *>(S.u + U_SQ);
-    float(*Ss)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_S);
-    float(*Se)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_E);
-    const uint32_t kc_addr = smem_u32(Kc), vc_addr = smem_u32(Vc);
-    const int pieces = d / 8; // 16-byte pieces per row
+    float *Sq = reinterpret_cast<float *>(S.u + U_SQ);              // [4][d] fp16-rounded q, widened
+    float(*Ss)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_S); // [4][32] scores
+    float *Se = reinterpret_cast<float *>(S.u + U_E);               // [32][4] soft-max numerators, heads innermost
+    const uint32_t kc_addr = smem_u32(Kc), vc_addr = smem_u32(Vc), kvbar = smem_u32(&S.kv_bar);
+    const uint32_t row_bytes = (uint32_t)d * 2;
 #pragma unroll 1
     for (int it = cta + ph.rot >= G ? cta + ph.rot - G : cta + ph.rot; it < n_items; it += G) {
         const int hh = hsplit == 2 ? (it & 1) : 0;
         const int gc = (hsplit == 2 ? (it >> 1) : it) * P.R + P.rank;
-        const int g = Hkv == 1 ? 0 : gc / nchunk, c = Hkv == 1 ? gc : gc % nchunk;
+        const int g = gc & (Hkv - 1), c = gc >> P.kvh_shift;
         const int p0 = c * kChunk, np = min(kChunk, n_pos - p0);
         const int h0 = g * Gq + hh * Gh;
         const int jnew = pos - p0; // row of the new position inside this chunk (if 0 <= jnew < np)
         const bool owns_new = jnew >= 0 && jnew < np;
-        // K / V chunk rows: warp w copies rows w, w + 16, lane = 16-byte piece (the new position's row is
-        // computed below, not loaded)
-        for (int j = warp; j < np; j += kCW) {
-            if (j == jnew || lane >= pieces) continue;
-            const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d + 8 * lane;
-            cp_async16(kc_addr + (uint32_t)(j * d + 8 * lane) * 2, ph.kcache + src);
-            cp_async16(vc_addr + (uint32_t)(j * d + 8 * lane) * 2, ph.vcache + src);
+        // K / V chunk rows w, w + 16 (the new position's row is computed below, not loaded)
+        if (lane == 0) {
+            fence_proxy_async(); // the union region was last touched through the generic proxy (ordered by the phase barrier)
+            uint32_t bytes = 0;
+            for (int j = warp; j < np; j += kCW) bytes += j == jnew ? 0u : 2u * row_bytes;
+            mbar_expect_tx(kvbar, bytes); // arrive (+ expected bytes, possibly 0): the barrier counts the kCW warps
+            for (int j = warp; j < np; j += kCW) {
+                if (j == jnew) continue;
+                const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d;
+                bulk_g2s_plain(kc_addr + (uint32_t)j * row_bytes, ph.kcache + src, row_bytes, kvbar);
+                bulk_g2s_plain(vc_addr + (uint32_t)j * row_bytes, ph.vcache + src, row_bytes, kvbar);
+            }
         }
         DBG_STAMP(1);
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
         for (int i = tid; i < Gh * halfd; i += kCT) {
-            const int jh = i / halfd, e = i % halfd;
+            const int jh = i >> P.hd_shift, e = i & (halfd - 1);
             const ll_t *qh = q_all + (size_t)(h0 + jh) * d;
             const ll_t w0 = ll_peek(qh + e), w1 = ll_peek(qh + e + halfd);
             const float cs = cosr[e], sn = sinr[e];
             const float x0 = ll_get_f(w0, qh + e, tag), x1 = ll_get_f(w1, qh + e + halfd, tag);
             const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
             const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
-            Sq[jh * d + e] = __float2half_rn(r0);
-            Sq[jh * d + e + halfd] = __float2half_rn(r1);
+            Sq[jh * d + e] = __half2float(__float2half_rn(r0));
+            Sq[jh * d + e + halfd] = __half2float(__float2half_rn(r1));
         }
         DBG_STAMP(2);
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
@@ -632,106 +691,114 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             }
         }
         DBG_STAMP(3);
-        cp_async_wait_all();
+        mbar_wait(kvbar, kv_parity);
+        kv_parity ^= 1u;
         consumer_bar();
         DBG_STAMP(4);
-        // scores: warp w takes positions w, w + 16
-#pragma unroll 1
-        for (int j = warp; j < np; j += kCW) {
-            float kf[8];
+        // scores: warp w takes positions w and w + 16 against the item's (<= 4) heads; lane = 8 dims.  fp16 x fp16
+        // products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once
+        {
             const bool in = 8 * lane < d;
-            {
+            const int j0 = warp, j1 = warp + kCW;
+            float kf[2][8];
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const int j = p ? j1 : j0;
                 uint4 raw = make_uint4(0, 0, 0, 0);
-                if (in) raw = *reinterpret_cast<const uint4 *>(Kc + j * d + 8 * lane);
+                if (in && j < np) raw = *reinterpret_cast<const uint4 *>(Kc + j * d + 8 * lane);
                 const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const float2 f = __half22float2(h2[e]);
-                    kf[2 * e] = f.x;
-                    kf[2 * e + 1] = f.y;
+                    kf[p][2 * e] = f.x;
+                    kf[p][2 * e + 1] = f.y;
                 }
             }
-            // fp16 x fp16 products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once.  Heads in
-            // groups of 4: lane partials first, then the group's butterflies interleaved; each sum in DEV order
-#pragma unroll 1
-            for (int j0 = 0; j0 < Gh; j0 += 4) {
-                float acc[4];
+            float acc[2][4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    acc[u] = 0.0f;
-                    if (j0 + u < Gh && in) {
-                        const uint4 raw = *reinterpret_cast<const uint4 *>(Sq + (j0 + u) * d + 8 * lane);
-                        const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const float2 f = __half22float2(h2[e]);
-                            acc[u] = __fmaf_rn(kf[2 * e], f.x, acc[u]);
-                            acc[u] = __fmaf_rn(kf[2 * e + 1], f.y, acc[u]);
-                        }
-                    }
+            for (int u = 0; u < 4; u++) {
+                float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+                if (u < Gh && in) {
+                    qa = *reinterpret_cast<const float4 *>(Sq + u * d + 8 * lane);
+                    qb = *reinterpret_cast<const float4 *>(Sq + u * d + 8 * lane + 4);
                 }
+                const float qf[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
+                for (int p = 0; p < 2; p++) {
+                    float a = 0.0f;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __shfl_xor_sync(0xffffffffu, acc[u], off));
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (j0 + u < Gh) Ss[j0 + u][j] = acc[u];
+                    for (int e = 0; e < 8; e++) a = __fmaf_rn(kf[p][e], qf[e], a);
+                    acc[p][u] = a;
                 }
             }
+            // folded butterfly: xor 16 keeps one position per half-warp, xor 8 two heads, xor 4 one head
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            float k4[4], k2[2];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const float send = b4 ? acc[0][u] : acc[1][u], keep = b4 ? acc[1][u] : acc[0][u];
+                k4[u] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                const float send = b3 ? k4[v] : k4[2 + v], keep = b3 ? k4[2 + v] : k4[v];
+                k2[v] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            float k1;
+            {
+                const float send = b2 ? k2[0] : k2[1], keep = b2 ? k2[1] : k2[0];
+                k1 = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+            }
+            k1 = __fadd_rn(k1, __shfl_xor_sync(0xffffffffu, k1, 2));
+            k1 = __fadd_rn(k1, __shfl_xor_sync(0xffffffffu, k1, 1));
+            const int js = b4 ? j1 : j0, us = (b3 ? 2 : 0) + (b2 ? 1 : 0);
+            if ((lane & 3) == 0 && js < np && us < Gh) Ss[us][js] = k1;
         }
         DBG_STAMP(5);
         consumer_bar();
-        // per-head chunk soft-max through the fp16 exp table
-        if (warp < Gh) {
-            const float sv = lane < np ? Ss[warp][lane] : -INFINITY;
-            const float m = warp_max_f32(sv);
-            const float e = lane < np ? table_f16(P.exp_table, __fsub_rn(sv, m)) : 0.0f;
-            const float l = warp_sum_f32(e);
-            Se[warp][lane] = e;
-            if (lane == 0) {
-                ll_put_f(P, ph.m_ll + (size_t)(h0 + warp) * P.max_chunks + c, m, tag);
-                ll_put_f(P, ph.l_ll + (size_t)(h0 + warp) * P.max_chunks + c, l, tag);
+        // per-head chunk soft-max through the fp16 exp table (heads the item does not have get weight 0)
+        if (warp < 4) {
+            float e = 0.0f;
+            if (warp < Gh) {
+                const float sv = lane < np ? Ss[warp][lane] : -INFINITY;
+                const float m = warp_max_f32(sv);
+                e = lane < np ? table_f16(P.exp_table, __fsub_rn(sv, m)) : 0.0f;
+                const float l = warp_sum_f32(e);
+                if (lane == 0) {
+                    ll_put_f(P, ph.m_ll + (size_t)(h0 + warp) * P.max_chunks + c, m, tag);
+                    ll_put_f(P, ph.l_ll + (size_t)(h0 + warp) * P.max_chunks + c, l, tag);
+                }
             }
+            Se[lane * 4 + warp] = e;
         }
         DBG_STAMP(6);
         consumer_bar();
         DBG_STAMP(7);
-        // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p.  4 thread groups of 128: group hs takes heads
-        // hs, hs + 4; thread -> one pair of dims
-        {
-            constexpr int kHG = kCT / 128; // 4
-            const int dp = tid % 128, hs = tid / 128;
-            if (dp < halfd) {
-                float a0[kMaxG / kHG], a1[kMaxG / kHG];
+        // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p; thread -> dims 2 tid, 2 tid + 1 for every head
+        // (e is an fp16 value: e*v is exact, fmaf == mul + add)
+        if (tid < halfd) {
+            float a0[4], a1[4];
 #pragma unroll
-                for (int u = 0; u < kMaxG / kHG; u++) a0[u] = a1[u] = 0.0f;
+            for (int u = 0; u < 4; u++) a0[u] = a1[u] = 0.0f;
 #pragma unroll 4
-                for (int j = 0; j < np; j++) {
-                    const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(Vc + j * d + 2 * dp));
+            for (int j = 0; j < np; j++) {
+                const float2 vf = __half22float2(*reinterpret_cast<const __half2 *>(Vc + j * d + 2 * tid));
+                const float4 e4 = *reinterpret_cast<const float4 *>(Se + 4 * j);
+                a0[0] = __fmaf_rn(e4.x, vf.x, a0[0]); a1[0] = __fmaf_rn(e4.x, vf.y, a1[0]);
+                a0[1] = __fmaf_rn(e4.y, vf.x, a0[1]); a1[1] = __fmaf_rn(e4.y, vf.y, a1[1]);
+                a0[2] = __fmaf_rn(e4.z, vf.x, a0[2]); a1[2] = __fmaf_rn(e4.z, vf.y, a1[2]);
+                a0[3] = __fmaf_rn(e4.w, vf.x, a0[3]); a1[3] = __fmaf_rn(e4.w, vf.y, a1[3]);
+            }
 #pragma unroll
-                    for (int u = 0; u < kMaxG / kHG; u++) {
-                        const int jh = kHG * u + hs;
-                        if (jh < Gh) { // e is an fp16 value: e*v is exact, fmaf == mul + add
-                            const float e = Se[jh][j];
-                            a0[u] = __fmaf_rn(e, vf.x, a0[u]);
-                            a1[u] = __fmaf_rn(e, vf.y, a1[u]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kMaxG / kHG; u++) {
-                    const int jh = kHG * u + hs;
-                    if (jh < Gh) {
-                        ll_t *out = ph.acc_ll + ((size_t)(h0 + jh) * P.max_chunks + c) * d + 2 * dp;
-                        ll_put_f(P, out, a0[u], tag);
-                        ll_put_f(P, out + 1, a1[u], tag);
-                    }
+            for (int u = 0; u < 4; u++) {
+                if (u < Gh) {
+                    ll_t *out = ph.acc_ll + ((size_t)(h0 + u) * P.max_chunks + c) * d + 2 * tid;
+                    ll_put_f(P, out, a0[u], tag);
+                    ll_put_f(P, out + 1, a1[u], tag);
                 }
             }
         }
+        DBG_STAMP(8);
         consumer_bar();
     }
 }
@@ -742,19 +809,21 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
 // ones that own ATTN items, which are free earlier.
 template <int TYPE>
 __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                              int n_pos, uint32_t tag, long long *dbg) {
+                                              int nchunk, int items_rem, uint32_t tag, bool dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = P.d, slices = d / 32;
+    const int d = P.d, slices = d >> 5;
     const int n_tasks = P.H * slices;
-    const int nchunk = (n_pos + kChunk - 1) / kChunk;
-    const int n_items = ((P.Hkv * nchunk - P.rank + P.R - 1) / P.R) * (P.H / P.Hkv > 4 ? 2 : 1); // this rank's ATTN items
     float *stage = reinterpret_cast<float *>(S.u);
     float *sm = reinterpret_cast<float *>(S.u + U_CM), *sl = reinterpret_cast<float *>(S.u + U_CL);
     float *sw = reinterpret_cast<float *>(S.u + U_CW);
+    int tl = cta + ph.rot; // tasks start on the CTAs after the ones that own this rank's ATTN items (items_rem = items % G)
+    if (tl >= G) tl -= G;
+    tl -= items_rem;
+    if (tl < 0) tl += G;
 #pragma unroll 1
-    for (int tl = ((cta + ph.rot) % G + G - n_items % G) % G; tl * P.R + P.rank < n_tasks; tl += G) {
+    for (; tl * P.R + P.rank < n_tasks; tl += G) {
         const int task = tl * P.R + P.rank; // tasks are dealt round-robin to the ranks
-        const int h = task / slices, sli = task % slices;
+        const int h = task >> P.sl_shift, sli = task & (slices - 1);
         const ll_t *pa = ph.acc_ll + (size_t)h * P.max_chunks * d + sli * 32 + lane;
         const ll_t *pm = ph.m_ll + (size_t)h * P.max_chunks, *pl = ph.l_ll + (size_t)h * P.max_chunks;
 #pragma unroll 1
@@ -827,12 +896,20 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             mbar_init(smem_u32(&S.full_bar[i]), 1);
             mbar_init(smem_u32(&S.empty_bar[i]), kCW);
         }
+        mbar_init(smem_u32(&S.kv_bar), kCW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int token = min(max(P.state[0], 0), P.V - 1);
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
     const uint32_t tag = *P.seq + 1u;
+    if (tid == 0) { // the token's attention schedule (the same for every layer)
+        const int nchunk = (n_pos + kChunk - 1) / kChunk;
+        const int items = (P.R == 1 ? P.Hkv * nchunk : (P.Hkv * nchunk - P.rank + P.R - 1) / P.R) * P.hsplit;
+        S.sched[0] = nchunk;
+        S.sched[1] = items;
+        S.sched[2] = items % G;
+    }
 
     if (warp == kCW) {
         if (lane == 0) producer_loop<TYPE>(P, S, cta, G);
@@ -845,20 +922,20 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     const uint32_t act = smem_u32(S.u);
     float *part = reinterpret_cast<float *>(S.u + U_PART);
     int slot = 0;
-    uint32_t parity = 0;
+    uint32_t parity = 0, kv_parity = 0;
     if (tid < kPhWords) reinterpret_cast<uint32_t *>(&S.ph[0])[tid] = reinterpret_cast<const uint32_t *>(&P.phases[0])[tid];
     consumer_bar();
 #pragma unroll 1
     for (int pi = 0; pi < P.n_phases; pi++) {
         const Phase &ph = S.ph[pi & 1];
-        // prefetch the next descriptor; it is published by the block barriers inside this phase / at its end
+        // prefetch the next descriptor with an ASYNC copy (a plain load + store would stall warps 0-1 in order for one
+        // L2 round trip, ~0.8 us under the weight stream, at the start of every phase); waited for at the phase's end
         if (pi + 1 < P.n_phases && tid < kPhWords)
-            reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1])[tid] =
-                reinterpret_cast<const uint32_t *>(&P.phases[pi + 1])[tid];
-        long long tr0 = 0, tr1 = 0;
-        if (P.trace) tr0 = tr1 = (long long)gtime();
+            cp_async4(smem_u32(reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1]) + tid),
+                      reinterpret_cast<const uint32_t *>(&P.phases[pi + 1]) + tid);
+        if (P.trace && tid == 0) S.tr[0] = S.tr[1] = (long long)gtime();
         const int kind = ph.kind;
-        long long *dbg = (P.dbg && pi == P.dbg_phase) ? P.dbg + 16 * cta : nullptr;
+        const bool dbg = P.dbg && pi == P.dbg_phase;
         DBG_STAMP(0);
         if (is_matvec(kind)) {
             int u0, u1;
@@ -870,7 +947,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                 else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
                 else norm_prologue<TYPE>(P, S, ph, token, tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr, dbg);
             }
-            if (P.trace) tr1 = (long long)gtime();
+            if (P.trace && tid == 0) S.tr[1] = (long long)gtime();
             // the residual of this thread's first row: requested before the passes, consumed in the epilogue
             const int row0 = (ph.u_off + u0) * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows; // global rows of this CTA
             ll_t resid_w = 0;
@@ -1005,9 +1082,19 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                 }
             }
         } else if (kind == PH_ATTN) {
-            attn_phase<TYPE>(P, S, ph, cta, G, n_pos, tag, dbg);
+#pragma unroll 1
+            for (int rep = P.dbg_repeat; rep >= 1; rep--) {
+                const bool dbg_r = dbg && rep == 1;
+                if (dbg_r && threadIdx.x == 0) P.dbg[16 * cta] = clock64();
+                attn_phase<TYPE>(P, S, ph, cta, G, n_pos, S.sched[1], tag, kv_parity, dbg_r);
+            }
         } else if (kind == PH_COMBINE) {
-            combine_phase<TYPE>(P, S, ph, cta, G, n_pos, tag, dbg);
+#pragma unroll 1
+            for (int rep = P.dbg_repeat; rep >= 1; rep--) {
+                const bool dbg_r = dbg && rep == 1;
+                if (dbg_r && threadIdx.x == 0) P.dbg[16 * cta] = clock64();
+                combine_phase<TYPE>(P, S, ph, cta, G, S.sched[0], S.sched[2], tag, dbg_r);
+            }
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
             if (cta == 0 && warp == 0) {
                 Best b{-INFINITY, -1};
@@ -1034,12 +1121,13 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         }
         DBG_STAMP(10);
         // the union region is rewritten by the next phase's prologue, and the prefetched descriptor is read
+        cp_async_wait_all();
         consumer_bar();
         DBG_STAMP(11);
         if (P.trace && tid == 0) {
             long long *t = P.trace + ((size_t)pi * G + cta) * 4;
             const long long tr2 = (long long)gtime();
-            t[0] = tr0; t[1] = tr1; t[2] = tr2; t[3] = tr2;
+            t[0] = S.tr[0]; t[1] = S.tr[1]; t[2] = tr2; t[3] = tr2;
         }
     }
 }
@@ -1137,7 +1225,8 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     const int type = token_embd->type;
     const int max_chunks = (dims->n_ctx + kChunk - 1) / kChunk;
     if (!(E % 256 == 0 && E <= kMaxE && (H * d) % 256 == 0 && H * d <= kMaxE && F % 256 == 0 && F <= kMaxK &&
-          d % 32 == 0 && d <= 256 && Hkv > 0 && H % Hkv == 0 && H / Hkv <= kMaxG && max_chunks <= kMaxChunks &&
+          d >= 32 && d <= 256 && (d & (d - 1)) == 0 && Hkv > 0 && (Hkv & (Hkv - 1)) == 0 && H % Hkv == 0 &&
+          H / Hkv <= kMaxG && max_chunks <= kMaxChunks &&
           (type == GGB_TYPE_Q4_0 || type == GGB_TYPE_Q8_0))) {
         ggb_set_error("decoder: shape outside the fused kernel's envelope (E=%d H=%d Hkv=%d d=%d F=%d ctx=%d)", E, H, Hkv,
                       d, F, dims->n_ctx);
@@ -1157,6 +1246,12 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
     P.max_chunks = max_chunks;
     P.rank = rank; P.R = size;
+    auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) s++; return s; };
+    P.Gq = H / Hkv; P.hsplit = P.Gq > 4 ? 2 : 1; P.Gh = P.Gq / P.hsplit;
+    P.hd_shift = ilog2(d / 2); P.sl_shift = ilog2(d / 32); P.kvh_shift = ilog2(Hkv);
+    P.max_outstanding = kMaxOutstanding; P.prefetch_chunks = kPrefetchChunks; P.dbg_repeat = 1;
+    if (const char *e = getenv("GGB_MAX_OUTSTANDING")) P.max_outstanding = std::min(std::max(atoi(e), 1), kSlots);
+    if (const char *e = getenv("GGB_PREFETCH_CHUNKS")) P.prefetch_chunks = std::min(std::max(atoi(e), 0), 64);
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1418,9 +1513,11 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
     D->P.dbg = dev + bytes1 / sizeof(long long);
     if (const char *env = getenv("GGB_DBG_PHASE")) D->P.dbg_phase = atoi(env);
     else D->P.dbg_phase = 30;
+    D->P.dbg_repeat = getenv("GGB_DBG_REPEAT") ? atoi(getenv("GGB_DBG_REPEAT")) : 1;
     int rc = ggb_decoder_step(D);
     D->P.trace = nullptr;
     D->P.dbg = nullptr;
+    D->P.dbg_repeat = 1;
     if (rc == GGB_OK) {
         cudaError_t e = cudaMemcpyAsync(stamps, dev, bytes, cudaMemcpyDeviceToHost, ggb_cuda_stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(ggb_cuda_stream());

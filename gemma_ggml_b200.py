@@ -4,7 +4,8 @@ import importlib.util
 import os
 import sys
 
-_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemma.ggml_b200")
+# GGB_PKG_DIR: load another build of the package (A/B runs of kernel variants on one GPU box, tools/ab.sh)
+_dir = os.environ.get("GGB_PKG_DIR") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemma.ggml_b200")
 _spec = importlib.util.spec_from_file_location("gemma_ggml_b200", os.path.join(_dir, "__init__.py"),
                                                submodule_search_locations=[_dir])
 _mod = importlib.util.module_from_spec(_spec)

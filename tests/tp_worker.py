@@ -47,7 +47,7 @@ def main():
                 m.init_kv_cache()
                 m.build_compute_graph(capture_acts=True)
                 assert m.is_fused == fused
-                prompt = ((1 + 7919 * np.arange(9)) % dims["n_vocab"]).astype(np.int32)
+                prompt = ((1 + 7919 * np.arange(29)) % dims["n_vocab"]).astype(np.int32)
                 toks, _, _ = m.generate(prompt, 7)
                 logits = m.logits()  # collective (gathers the shards)
                 if rank == 0:

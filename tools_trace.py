@@ -52,9 +52,14 @@ def main():
     ok = db[:, 0] > 0
     rel = (db[ok] - db[ok, 0:1]) / 1965.0
     rel[db[ok] == 0] = np.nan
+    rel[:, 14:] = np.nan
     print("inside phase %s (us since phase start, SM clock): median / max over CTAs per stamp" % os.environ.get("GGB_DBG_PHASE", "30"))
     print("   median", np.round(np.nanmedian(rel, axis=0)[:16], 2))
     print("   max   ", np.round(np.nanmax(rel, axis=0)[:16], 2))
+    if (db[:, 15] > 0).any():
+        okw = db[:, 15] > 0
+        print("   weight wait inside the pass loop (warp 0): median %.2f us, max %.2f us over %d..%d slots" % (
+            np.median(db[okw, 14]) / 1965.0, db[okw, 14].max() / 1965.0, db[okw, 15].min(), db[okw, 15].max()))
     print("last phases:")
     for r in rows[-2:]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
