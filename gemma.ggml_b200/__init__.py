@@ -110,6 +110,7 @@ _CUDA_SIG = {
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]),
     "ggb_decoder_create_tp": (i32, [vp, vp, vp, vp, vp, i32, i32, P(vp)]), "ggb_decoder_step": (i32, [vp]),
     "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),
+    "ggb_decoder_exp_computed": (i32, [vp]),
     "ggb_comm_unique_id": (i32, [vp]), "ggb_comm_init": (i32, [vp, i32, i32]), "ggb_comm_destroy": (i32, []),
     "ggb_comm_rank": (i32, []), "ggb_comm_size": (i32, []), "ggb_op_allgather": (i32, [vp, vp, sz]),
 }
@@ -414,6 +415,12 @@ class GemmaModel:
         n1 = n.value * g.value * 4
         self.dbg_stamps = stamps[n1:n1 + g.value * 16].reshape(g.value, 16).copy()
         return stamps[:n1].reshape(n.value, g.value, 4), kinds[:n.value].copy()
+
+    @property
+    def exp_computed(self):
+        """True if the fused kernel computes exp (proved identical to the fp16 table at create time)."""
+        dec = self.H.gm_decoder(self.h)
+        return bool(dec and cuda_lib().ggb_decoder_exp_computed(dec))
 
     @property
     def is_fused(self):

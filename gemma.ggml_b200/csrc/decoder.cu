@@ -112,6 +112,7 @@ struct DecoderParams {
     long long peer_delta[8]; // byte offset from a local flagged word to the same word in rank r's memory (0 for self)
     uint32_t *seq;         // token sequence number = tag of the previous launch
     const uint16_t *exp_table, *gelu_table;
+    int exp_compute;       // 1: exp_f16_computed reproduces exp_table bit for bit (checked at create)
     const float *rope_cos, *rope_sin;
     long long *trace; // optional [n_phases][grid][4] %globaltimer stamps (ns): start, after prologue (inputs arrived), end, end
     long long *dbg;   // optional [grid][16] SM-clock stamps inside phase dbg_phase
@@ -226,6 +227,25 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) { // unsigned b
 // weight stream a demand miss to HBM costs ~1 us of queueing, and these lookups sit on every layer's critical path
 __device__ __forceinline__ float table_f16(const uint16_t *table, float x) {
     return half_bits_to_float(__ldg(table + float_to_half_bits(x)));
+}
+
+// exp with the reference's fp16-table semantics, table[h] = fp16(expf(fp32(h))), COMPUTED: exp() in double, rounded
+// to fp32, then to fp16.  ggb_decoder_create checks this against the uploaded table for every non-NaN fp16 input
+// and only then sets P.exp_compute; the lookup it replaces is an L2 round trip on the critical path of ATTN and
+// COMBINE in every layer.
+__device__ __forceinline__ float exp_f16_computed(float x_f16_valued) {
+    return half_bits_to_float(float_to_half_bits(__double2float_rn(exp((double)x_f16_valued))));
+}
+__device__ __forceinline__ float exp_f16(const DecoderParams &P, float x) {
+    const uint16_t hb = float_to_half_bits(x);
+    if (!P.exp_compute || (hb & 0x7FFFu) > 0x7C00u) return half_bits_to_float(__ldg(P.exp_table + hb)); // no proof / NaN
+    return exp_f16_computed(half_bits_to_float(hb));
+}
+__global__ void exp_check_kernel(const uint16_t *table, int *mismatches) {
+    const uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hb >= 65536u || (hb & 0x7FFFu) > 0x7C00u) return;
+    const float got = exp_f16_computed(half_bits_to_float((uint16_t)hb));
+    if (float_to_half_bits(got) != table[hb]) atomicAdd(mismatches, 1);
 }
 
 // ---- flagged words.  An aligned 8-byte access is single-copy atomic, so payload and tag are seen together;
@@ -640,17 +660,32 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         const int h0 = g * Gq + hh * Gh;
         const int jnew = pos - p0; // row of the new position inside this chunk (if 0 <= jnew < np)
         const bool owns_new = jnew >= 0 && jnew < np;
-        // K / V chunk rows w, w + 16 (the new position's row is computed below, not loaded)
+        // K / V chunk rows (the new position's row is computed below, not loaded).  MQA (one KV head): the rows of a
+        // chunk are contiguous in the cache, so warps 0..3 issue one copy each (K | V) x (rows before | after the new
+        // one); otherwise the warp that scores rows w, w + 16 copies them.  Every warp arrives once on kv_bar.
         if (lane == 0) {
+#ifndef GGB_EXP_NOFENCE
             fence_proxy_async(); // the union region was last touched through the generic proxy (ordered by the phase barrier)
-            uint32_t bytes = 0;
-            for (int j = warp; j < np; j += kCW) bytes += j == jnew ? 0u : 2u * row_bytes;
-            mbar_expect_tx(kvbar, bytes); // arrive (+ expected bytes, possibly 0): the barrier counts the kCW warps
-            for (int j = warp; j < np; j += kCW) {
-                if (j == jnew) continue;
-                const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d;
-                bulk_g2s_plain(kc_addr + (uint32_t)j * row_bytes, ph.kcache + src, row_bytes, kvbar);
-                bulk_g2s_plain(vc_addr + (uint32_t)j * row_bytes, ph.vcache + src, row_bytes, kvbar);
+#endif
+            if (Hkv == 1) {
+                const int lo = (warp & 1) ? (owns_new ? jnew + 1 : np) : 0;
+                const int hi = (warp & 1) ? np : (owns_new ? jnew : np);
+                const uint32_t bytes = warp < 4 && hi > lo ? (uint32_t)(hi - lo) * row_bytes : 0u;
+                mbar_expect_tx(kvbar, bytes);
+                if (bytes) {
+                    const __half *cache = warp < 2 ? ph.kcache : ph.vcache;
+                    bulk_g2s_plain((warp < 2 ? kc_addr : vc_addr) + (uint32_t)lo * row_bytes, cache + (size_t)(p0 + lo) * d, bytes, kvbar);
+                }
+            } else {
+                uint32_t bytes = 0;
+                for (int j = warp; j < np; j += kCW) bytes += j == jnew ? 0u : 2u * row_bytes;
+                mbar_expect_tx(kvbar, bytes); // arrive (+ expected bytes, possibly 0): the barrier counts the kCW warps
+                for (int j = warp; j < np; j += kCW) {
+                    if (j == jnew) continue;
+                    const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d;
+                    bulk_g2s_plain(kc_addr + (uint32_t)j * row_bytes, ph.kcache + src, row_bytes, kvbar);
+                    bulk_g2s_plain(vc_addr + (uint32_t)j * row_bytes, ph.vcache + src, row_bytes, kvbar);
+                }
             }
         }
         DBG_STAMP(1);
@@ -762,7 +797,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             if (warp < Gh) {
                 const float sv = lane < np ? Ss[warp][lane] : -INFINITY;
                 const float m = warp_max_f32(sv);
-                e = lane < np ? table_f16(P.exp_table, __fsub_rn(sv, m)) : 0.0f;
+                e = lane < np ? exp_f16(P, __fsub_rn(sv, m)) : 0.0f;
                 const float l = warp_sum_f32(e);
                 if (lane == 0) {
                     ll_put_f(P, ph.m_ll + (size_t)(h0 + warp) * P.max_chunks + c, m, tag);
@@ -851,7 +886,7 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
             for (int c = lane; c < nchunk; c += 32) mx = fmaxf(mx, sm[c]);
             mx = warp_max_f32(mx);
             for (int c = lane; c < nchunk; c += 32)
-                sw[c] = table_f16(P.exp_table, __fsub_rn(sm[c], mx));
+                sw[c] = exp_f16(P, __fsub_rn(sm[c], mx));
             __syncwarp();
             DBG_STAMP(3);
             float L = 0.0f, O = 0.0f;
@@ -1245,6 +1280,19 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     P.exp_table = ggb_exp_table_dev(); P.gelu_table = ggb_gelu_table_dev();
     P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
     P.max_chunks = max_chunks;
+    {   // does the computed exp reproduce the table?  (GGB_EXP_TABLE=1 forces the lookup)
+        int *d_mis = nullptr, h_mis = -1;
+        const char *force = getenv("GGB_EXP_TABLE");
+        if (!(force && atoi(force)) && cudaMalloc(&d_mis, sizeof(int)) == cudaSuccess) {
+            cudaMemsetAsync(d_mis, 0, sizeof(int), ggb_cuda_stream());
+            exp_check_kernel<<<256, 256, 0, ggb_cuda_stream()>>>(P.exp_table, d_mis);
+            if (cudaMemcpyAsync(&h_mis, d_mis, sizeof(int), cudaMemcpyDeviceToHost, ggb_cuda_stream()) != cudaSuccess ||
+                cudaStreamSynchronize(ggb_cuda_stream()) != cudaSuccess)
+                h_mis = -1;
+            cudaFree(d_mis);
+        }
+        P.exp_compute = h_mis == 0 ? 1 : 0;
+    }
     P.rank = rank; P.R = size;
     auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) s++; return s; };
     P.Gq = H / Hkv; P.hsplit = P.Gq > 4 ? 2 : 1; P.Gh = P.Gq / P.hsplit;
@@ -1532,6 +1580,8 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
     *grid = D->grid;
     return rc;
 }
+
+int ggb_decoder_exp_computed(const ggb_decoder *D) { return D ? D->P.exp_compute : 0; }
 
 int ggb_decoder_free(ggb_decoder *D) {
     if (!D) return GGB_OK;

@@ -242,6 +242,9 @@ int ggb_decoder_free(ggb_decoder *d);
  * prologue = inputs arrived, end, end), kinds[n_phases] phase kinds (0 QKV, 1 ATTN, 2 COMBINE, 3 O,
  * 4 GATE_UP, 5 DOWN, 6 LOGITS, 7 SAMPLE) */
 int ggb_decoder_trace(ggb_decoder *d, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid);
+/* 1 if the kernel computes the soft-max exp (double exp -> fp32 -> fp16) instead of reading the reference's fp16 table:
+ * enabled only when an exhaustive check at create time found the two identical for every non-NaN fp16 input */
+int ggb_decoder_exp_computed(const ggb_decoder *d);
 
 /* ------------------------------------------------------------------ multi-GPU (row-sharded TP)
  * one process per GPU; the 128-byte NCCL unique id is created on rank 0 and shipped by the

@@ -38,6 +38,8 @@ def test_generate_matches_oracle(gpu, name, wtype, fused):
     dims = SMALL[name]
     m, om = _models(gpu, dims, wtype, fused=fused)
     assert m.is_fused == (fused and name != "odd")
+    if m.is_fused:  # the computed soft-max exp must have been proved identical to the fp16 table on this GPU
+        assert m.exp_computed
     prompt = ((1 + 7919 * np.arange(12)) % dims["n_vocab"]).astype(np.int32)
     n_decode = 10
     toks, _, _ = m.generate(prompt, n_decode)
