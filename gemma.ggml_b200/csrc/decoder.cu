@@ -146,7 +146,8 @@ template <int TYPE> struct Smem {
     alignas(8) unsigned long long empty_bar[kSlots];
     alignas(8) unsigned long long kv_bar; // ATTN: K / V chunk rows have landed (kCW arrivals + bytes)
     long long tr[2]; // trace stamps of the current phase (thread 0)
-    int sched[4]; // the token's attention schedule: chunks, this rank's ATTN items, items % grid (kept out of registers:
+    alignas(8) ll_t resid[32]; // residual words of this CTA's first 32 rows, fetched asynchronously before the passes
+    int sched[6]; // [3] = token, [4] = number of positions; the token's attention schedule: chunks, this rank's ATTN items, items % grid (kept out of registers:
                   // the kernel runs at the 96-register limit of 17 warps per SM and a spill costs an L2 round trip)
     alignas(16) Phase ph[2];
 };
@@ -195,6 +196,9 @@ __device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void *src, ui
 // small async copy global -> shared (the issuing warp does not wait for the data)
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
@@ -445,14 +449,15 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp < nquad) w4 = *reinterpret_cast<const float4 *>(norm_w + 128 * warp + 4 * lane);
     double acc = 0.0;
+    // a thread's words are requested 8 at a time (all of them for E <= 2048): ONE L2 round trip when x is there
 #pragma unroll 1
-    for (int k0 = 0; k0 < nk; k0 += 4) {
-        ll_t v[4];
+    for (int k0 = 0; k0 < nk; k0 += 8) {
+        ll_t v[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
+        for (int u = 0; u < 8; u++)
             if (in && k0 + u < nk) v[u] = ll_peek(in + GGB_DEV_NORM_THREADS * (k0 + u) + base);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             if (k0 + u < nk) {
                 const int i = GGB_DEV_NORM_THREADS * (k0 + u) + base;
                 const float x = in ? ll_get_f(v[u], in + i, tag) : embed_value<TYPE>(P, token, i);
@@ -512,15 +517,17 @@ __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, in
     consumer_bar();
 }
 
-// DOWN: packed Q8_0 row written by GATE_UP (4 codes per flagged word, then the fp16 scales)
+// DOWN: packed Q8_0 row written by GATE_UP: 4 codes per flagged word, then one word per block with the fp16 scale
+// (low half) and the sum of the block's codes (high half, int16: |sum| <= 32 * 127), from which the Q4_0 bias follows
 template <int TYPE>
 __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
     const int tid = threadIdx.x;
     const int nw = K / 4, ns = K / 32;
     uint32_t *aq = reinterpret_cast<uint32_t *>(S.u);
     __half *ad = reinterpret_cast<__half *>(S.u + U_ACT_D);
+    int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
 #pragma unroll 1
-    for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) {
+    for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 9 words in flight per thread: one L2 round trip for F <= 16384
         ll_t v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
@@ -531,21 +538,14 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
             if (i < nw + ns) {
                 const uint32_t w = ll_get(v[u], in + i, tag);
                 if (i < nw) aq[i] = w;
-                else ad[i - nw] = __ushort_as_half((unsigned short)w);
+                else {
+                    ad[i - nw] = __ushort_as_half((unsigned short)w);
+                    if (TYPE == GGB_TYPE_Q4_0) bias[i - nw] = -8 * ((int)w >> 16);
+                }
             }
         }
     }
     consumer_bar();
-    if (TYPE == GGB_TYPE_Q4_0) {
-        int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
-        for (int b = tid; b < ns; b += kCT) {
-            int s = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) s = __dp4a((int)aq[8 * b + i], 0x01010101, s);
-            bias[b] = -8 * s;
-        }
-        consumer_bar();
-    }
 }
 
 // ---------------------------------------------------------------- one pass: 2 rows x one K segment
@@ -555,7 +555,7 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
 // lanes < 16 end with row A's sum, lanes >= 16 with row B's (same additions, DEV order).
 struct ActRegs { // the lane's two activation blocks of one K segment
     int a[2][8];
-    float dy[2];
+    uint32_t dy2; // the two fp16 activation scales in one register (the kernel runs at its register limit)
     int bias[2];
     bool live[2];
 };
@@ -569,7 +569,9 @@ __device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg,
         const uint4 lo = lds_u4(act + bc * 32), hi = lds_u4(act + bc * 32 + 16);
         A.a[t][0] = lo.x; A.a[t][1] = lo.y; A.a[t][2] = lo.z; A.a[t][3] = lo.w;
         A.a[t][4] = hi.x; A.a[t][5] = hi.y; A.a[t][6] = hi.z; A.a[t][7] = hi.w;
-        A.dy[t] = lds_half(act + U_ACT_D + bc * 2);
+        unsigned short hd;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hd) : "r"(act + U_ACT_D + bc * 2));
+        A.dy2 = t == 0 ? (uint32_t)hd : (A.dy2 | ((uint32_t)hd << 16));
         A.bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + bc * 4) : 0;
     }
 }
@@ -577,7 +579,8 @@ template <int TYPE>
 __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int lane) {
     using F = Fmt<TYPE>;
     const int(&a)[2][8] = A.a;
-    const float(&dy)[2] = A.dy;
+    const float dy[2] = {__half2float(__ushort_as_half((unsigned short)(A.dy2 & 0xFFFFu))),
+                         __half2float(__ushort_as_half((unsigned short)(A.dy2 >> 16)))};
     const int(&bias)[2] = A.bias;
     const bool(&live)[2] = A.live;
     float term[4]; // [row][block]
@@ -944,6 +947,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         S.sched[0] = nchunk;
         S.sched[1] = items;
         S.sched[2] = items % G;
+        S.sched[3] = token;
+        S.sched[4] = n_pos;
     }
 
     if (warp == kCW) {
@@ -980,28 +985,35 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
                 if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
                 else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
-                else norm_prologue<TYPE>(P, S, ph, token, tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr, dbg);
+                else norm_prologue<TYPE>(P, S, ph, S.sched[3], tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr, dbg);
             }
             if (P.trace && tid == 0) S.tr[1] = (long long)gtime();
             // the residual of this thread's first row: requested before the passes, consumed in the epilogue
-            const int row0 = (ph.u_off + u0) * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows; // global rows of this CTA
-            ll_t resid_w = 0;
-            if (ph.resid_ll && kind != PH_GATE_UP && tid < nrows && row0 + tid < ph.n_rows) resid_w = ll_peek(ph.resid_ll + row0 + tid);
+            // (an async 8-byte copy into shared memory: no register is held across the pass loop, no warp waits; a
+            // word that had not arrived yet, or a stale L1 line, simply fails the tag check later and is polled then)
+            {
+                const int row0 = (ph.u_off + u0) * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows;
+                if (ph.resid_ll && kind != PH_GATE_UP && tid < 32 && tid < nrows && row0 + tid < ph.n_rows)
+                    cp_async8(smem_u32(&S.resid[tid]), ph.resid_ll + row0 + tid);
+            }
             // ---- passes: warp w owns passes w, w + 16, ... (Q4_0: one per slot; Q8_0: 8 passes per slot, so the
             // two warp halves alternate slots).  Every warp waits for and releases every slot.  The activation
             // blocks live in registers and are reloaded only when the warp's K segment changes (never for
             // K <= 2048, and never when 16 % ksegs == 0).
             {
                 const int pstep = ph.pstep, sstep = ph.sstep; // from the host: no division on the critical path
-                int pair = warp, seg = 0, cur_seg = -1;
+                // pidx = 2 * pair * ksegs + seg: where this warp's (row pair, segment) lands in the partial table
+                int pidx = 2 * warp, seg = 0, cur_seg = -1;
                 if (ksegs > 1) { // warp / ksegs, warp % ksegs by subtraction (at most 7 steps)
-                    pair = 0;
+                    pidx = 0;
                     seg = warp;
                     while (seg >= ksegs) {
                         seg -= ksegs;
-                        pair++;
+                        pidx += 2 * ksegs;
                     }
+                    pidx += seg;
                 }
+                const int dstep = 2 * pstep * ksegs + sstep;
                 ActRegs A;
 #pragma unroll 1
                 for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
@@ -1014,13 +1026,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     mbar_wait(full0 + 8 * slot, parity);
                     if (j < cnt) {
                         const float keep = pass_dot<TYPE>(ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES, A, lane);
-                        if ((lane & 15) == 0) part[(2 * pair + (lane >> 4)) * ksegs + seg] = keep;
-
-                        pair += pstep;
+                        if ((lane & 15) == 0) part[pidx + ((lane >> 4) ? ksegs : 0)] = keep;
+                        pidx += dstep;
                         seg += sstep;
-                        if (seg >= ksegs) {
+                        if (seg >= ksegs) { // next row pair: + 2 * ksegs for the pair, - ksegs for the segment
                             seg -= ksegs;
-                            pair++;
+                            pidx += ksegs;
                         }
                     }
                     __syncwarp();
@@ -1036,52 +1047,58 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             DBG_STAMP(9);
             // ---- epilogue: finish this CTA's rows (segments added in order)
             if (kind == PH_GATE_UP) {
-                // GeGLU (fp16 gelu table) for every row in parallel (one table round trip), then
-                // quantize_row_q8_0 with 8 lanes per 32-row group (4 groups per warp pass); a lane's four codes are
-                // exactly one flagged word of the packed row, the block scale is one more
+                // GeGLU (fp16 gelu table) + quantize_row_q8_0 in one go: 8 lanes per 32-row group (a lane owns 4 rows:
+                // four table lookups in flight at once = one L2 round trip), 4 groups per warp.  A lane's four codes
+                // are exactly one flagged word of the packed row; the block's fp16 scale and the sum of its codes
+                // (the Q4_0 bias of DOWN's dot products) share one more.
                 ll_t *oq = ph.out_ll, *od = ph.out_ll + P.F / 4;
-                float *xb = reinterpret_cast<float *>(S.u + U_XS); // GeGLU products (the activation row is dead)
                 const int nu = u1 - u0;
 #pragma unroll 1
-                for (int r = tid; r < nu * 32; r += kCT) {
-                    const int u = r >> 5, i = r & 31;
-                    const float *pg = part + (u * 64 + i) * ksegs, *pu = pg + 32 * ksegs;
-                    float gsum = pg[0], usum = pu[0];
-                    for (int k = 1; k < ksegs; k++) {
-                        gsum = __fadd_rn(gsum, pg[k]);
-                        usum = __fadd_rn(usum, pu[k]);
-                    }
-                    const float gl = table_f16(P.gelu_table, gsum);
-                    const float x = __fmul_rn(gl, usum);
-                    xb[r] = x;
-                    if (ph.f32_out) ph.f32_out[(size_t)(ph.u_off + u0) * 32 + r] = x;
-                }
-                DBG_STAMP(12);
-                consumer_bar();
-                DBG_STAMP(13);
-#pragma unroll 1
                 for (int q0 = 4 * warp; q0 < nu; q0 += 4 * kCW) {
-                    const int u = q0 + (lane >> 3);
+                    const int u = q0 + (lane >> 3), i0 = 4 * (lane & 7);
                     const bool ok = u < nu;
-                    const float4 x4 = ok ? *reinterpret_cast<const float4 *>(xb + 32 * u + 4 * (lane & 7))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float amax = fmaxf(fmaxf(fabsf(x4.x), fabsf(x4.y)), fmaxf(fabsf(x4.z), fabsf(x4.w)));
+                    float x[4];
+                    {
+                        float gs[4], us[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float *pg = part + ((ok ? u : 0) * 64 + i0 + e) * ksegs, *pu = pg + 32 * ksegs;
+                            gs[e] = pg[0];
+                            us[e] = pu[0];
+                            for (int k = 1; k < ksegs; k++) {
+                                gs[e] = __fadd_rn(gs[e], pg[k]);
+                                us[e] = __fadd_rn(us[e], pu[k]);
+                            }
+                        }
+                        uint16_t gl[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) gl[e] = __ldg(P.gelu_table + float_to_half_bits(gs[e]));
+#pragma unroll
+                        for (int e = 0; e < 4; e++) x[e] = ok ? __fmul_rn(half_bits_to_float(gl[e]), us[e]) : 0.0f;
+                    }
+                    if (ph.f32_out && ok)
+                        *reinterpret_cast<float4 *>(ph.f32_out + (size_t)(ph.u_off + u0 + u) * 32 + i0) = make_float4(x[0], x[1], x[2], x[3]);
+                    float amax = fmaxf(fmaxf(fabsf(x[0]), fabsf(x[1])), fmaxf(fabsf(x[2]), fabsf(x[3])));
 #pragma unroll
                     for (int off = 1; off <= 4; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
                     const float dd = __fdiv_rn(amax, 127.0f);
                     const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
-                    const uint32_t w = ((uint32_t)(int)roundf(__fmul_rn(x4.x, id)) & 0xFFu) |
-                                       (((uint32_t)(int)roundf(__fmul_rn(x4.y, id)) & 0xFFu) << 8) |
-                                       (((uint32_t)(int)roundf(__fmul_rn(x4.z, id)) & 0xFFu) << 16) |
-                                       (((uint32_t)(int)roundf(__fmul_rn(x4.w, id)) & 0xFFu) << 24);
-                    if (ok) {
-                        ll_put(P, oq + (size_t)(ph.u_off + u0 + u) * 8 + (lane & 7), w, tag);
-                        if ((lane & 7) == 0) ll_put(P, od + (ph.u_off + u0 + u), (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
-                    }
+                    const uint32_t w = ((uint32_t)(int)roundf(__fmul_rn(x[0], id)) & 0xFFu) |
+                                       (((uint32_t)(int)roundf(__fmul_rn(x[1], id)) & 0xFFu) << 8) |
+                                       (((uint32_t)(int)roundf(__fmul_rn(x[2], id)) & 0xFFu) << 16) |
+                                       (((uint32_t)(int)roundf(__fmul_rn(x[3], id)) & 0xFFu) << 24);
+                    if (ok) ll_put(P, oq + (size_t)(ph.u_off + u0 + u) * 8 + (lane & 7), w, tag);
+                    int qs = __dp4a((int)w, 0x01010101, 0);
+#pragma unroll
+                    for (int off = 1; off <= 4; off <<= 1) qs += __shfl_xor_sync(0xffffffffu, qs, off);
+                    if (ok && (lane & 7) == 0)
+                        ll_put(P, od + (ph.u_off + u0 + u), ((uint32_t)qs << 16) | (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
                 }
             } else {
                 Best best{-INFINITY, -1};
                 const ll_t *resid = ph.resid_ll;
+                const int row0 = (ph.u_off + u0) * ph.unit_rows, nrows = (u1 - u0) * ph.unit_rows; // global rows of this CTA
+                if (resid) cp_async_wait_all();
 #pragma unroll 1
                 for (int r = tid; r < nrows; r += kCT) {
                     const int grow = row0 + r;
@@ -1089,8 +1106,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     const float *pp = part + r * ksegs;
                     float total = pp[0];
                     for (int k = 1; k < ksegs; k++) total = __fadd_rn(total, pp[k]);
-                    if (resid) total = __fadd_rn(total, ll_get_f(r == tid ? resid_w : ll_peek(resid + grow), resid + grow, tag));
-                    else if (ph.resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, token, grow));
+                    if (resid) total = __fadd_rn(total, ll_get_f(r < 32 ? S.resid[r] : ll_peek(resid + grow), resid + grow, tag));
+                    else if (ph.resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, S.sched[3], grow));
                     if (ph.out) ph.out[grow] = total;
                     if (ph.out_ll) ll_put_f(P, ph.out_ll + grow, total, tag);
                     if (total > best.v || best.i < 0) best = Best{total, grow};
@@ -1121,7 +1138,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             for (int rep = P.dbg_repeat; rep >= 1; rep--) {
                 const bool dbg_r = dbg && rep == 1;
                 if (dbg_r && threadIdx.x == 0) P.dbg[16 * cta] = clock64();
-                attn_phase<TYPE>(P, S, ph, cta, G, n_pos, S.sched[1], tag, kv_parity, dbg_r);
+                attn_phase<TYPE>(P, S, ph, cta, G, S.sched[4], S.sched[1], tag, kv_parity, dbg_r);
             }
         } else if (kind == PH_COMBINE) {
 #pragma unroll 1
