@@ -74,7 +74,15 @@ struct Phase {
     int n_rows;      // logical rows of the phase
     int rot;         // CTA rotation so remainders do not always land on the same SMs
     int uq, ur;      // n_units / grid, n_units % grid
-    int pstep, sstep; // 16 / ksegs, 16 % ksegs: how a warp's (row pair, segment) advances from pass to pass
+    // how a warp's position advances from pass to pass (it takes every 16th pass of the CTA's share), all from the
+    // host so that no division runs on the critical path.  Position = (seg, pidx): index inside the unit of `wrapn`
+    // passes, and the unit's base in the partial table.  Per pass: pidx += dstep, seg += sstep, and on seg >= wrapn:
+    // seg -= wrapn, pidx += winc.  Plain phases: unit = row pair (wrapn = ksegs passes, pidx includes seg).
+    // QUAD phases (K % 2048 in (0, 1024]: the last K segment has <= 32 blocks): unit = 4 rows =
+    // kf passes of rows 0-1 | kf passes of rows 2-3 | ONE pass holding the short segment of all 4 rows, so the
+    // short segment costs half a pass per row pair instead of a zero-padded full one (Gemma-7B: K = 3072).
+    int sstep, dstep, wrapn, winc, winit;
+    int quad, kf;    // quad layout; number of full 64-block segments per row
     int u_off;       // first unit of this rank (tensor parallel: units are split by rank, then by CTA)
     int pad2_;
     int resid_embed; // residual = embedding row of the token (layer 0, O phase)
@@ -527,7 +535,7 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
     __half *ad = reinterpret_cast<__half *>(S.u + U_ACT_D);
     int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
 #pragma unroll 1
-    for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 9 words in flight per thread: one L2 round trip for F <= 16384
+    for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 4 words in flight per thread (more spills at the 96-register limit)
         ll_t v[4];
 #pragma unroll
         for (int u = 0; u < 4; u++)
@@ -575,7 +583,12 @@ __device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg,
         A.bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + bc * 4) : 0;
     }
 }
-template <int TYPE>
+// QUAD = true: the pass holds the short last segment (<= 32 blocks) of FOUR rows; lane l owns block l of each row
+// (its "l + 32" is past the end of the row), lane partial = 0.0f + term, and the four rows' butterflies are folded
+// into one (xor 16 keeps two rows per half-warp, xor 8 one row per quarter): the same additions as the plain
+// butterfly of each row.  Returns row 2 * (lane bit 4) + (lane bit 3)'s segment sum.  The byte layout of a pass is
+// the same in both cases: four groups of 32 blocks, payloads then scales.
+template <int TYPE, bool QUAD>
 __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int lane) {
     using F = Fmt<TYPE>;
     const int(&a)[2][8] = A.a;
@@ -583,12 +596,12 @@ __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int l
                          __half2float(__ushort_as_half((unsigned short)(A.dy2 >> 16)))};
     const int(&bias)[2] = A.bias;
     const bool(&live)[2] = A.live;
-    float term[4]; // [row][block]
+    float term[4]; // plain: [row][block]; quad: [row]
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int r = k >> 1, t = k & 1;
-        const uint32_t pay = base + r * F::ROW_PB + (lane + 32 * t) * F::PB;
-        const float dx = lds_half(base + 2 * F::ROW_PB + r * (kSeg * 2) + (lane + 32 * t) * 2);
+        const int t = QUAD ? 0 : (k & 1);
+        const uint32_t pay = base + k * (32 * F::PB) + lane * F::PB;
+        const float dx = lds_half(base + 2 * F::ROW_PB + k * 64 + lane * 2);
         if (TYPE == GGB_TYPE_Q4_0) {
             const uint4 w = lds_u4(pay);
             const uint32_t q[4] = {w.x, w.y, w.z, w.w};
@@ -610,14 +623,26 @@ __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int l
             term[k] = __fmul_rn((float)(s0 + s1), __fmul_rn(dx, dy[t]));
         }
     }
+    const bool b4 = lane & 16;
+    if (QUAD) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = live[0] ? __fadd_rn(0.0f, term[k]) : 0.0f;
+        const bool b3 = lane & 8;
+        const float k20 = __fadd_rn(b4 ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16));
+        const float k21 = __fadd_rn(b4 ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16));
+        float keep = __fadd_rn(b3 ? k21 : k20, __shfl_xor_sync(0xffffffffu, b3 ? k20 : k21, 8));
+#pragma unroll
+        for (int off = 4; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
+        return keep;
+    }
     float a0 = 0.0f, a1 = 0.0f;
     a0 = live[0] ? __fadd_rn(a0, term[0]) : a0;
     a0 = live[1] ? __fadd_rn(a0, term[1]) : a0;
     a1 = live[0] ? __fadd_rn(a1, term[2]) : a1;
     a1 = live[1] ? __fadd_rn(a1, term[3]) : a1;
-    const int half = lane >> 4;
-    const float send = half ? a0 : a1;
-    float keep = __fadd_rn(half ? a1 : a0, __shfl_xor_sync(0xffffffffu, send, 16));
+    const float send = b4 ? a0 : a1;
+    float keep = __fadd_rn(b4 ? a1 : a0, __shfl_xor_sync(0xffffffffu, send, 16));
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) keep = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, keep, off));
     return keep;
@@ -922,7 +947,9 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int TYPE>
+// QUAD: the model has phases in the quad layout (a short last K segment).  A compile-time switch, because the pass loop
+// is issue-bound: the two extra branches of the quad layout cost a model without such phases (Gemma-2B) 1.5 %.
+template <int TYPE, bool QUAD>
 __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_constant__ DecoderParams P) {
     using F = Fmt<TYPE>;
     Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
@@ -1001,37 +1028,45 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             // blocks live in registers and are reloaded only when the warp's K segment changes (never for
             // K <= 2048, and never when 16 % ksegs == 0).
             {
-                const int pstep = ph.pstep, sstep = ph.sstep; // from the host: no division on the critical path
-                // pidx = 2 * pair * ksegs + seg: where this warp's (row pair, segment) lands in the partial table
-                int pidx = 2 * warp, seg = 0, cur_seg = -1;
-                if (ksegs > 1) { // warp / ksegs, warp % ksegs by subtraction (at most 7 steps)
-                    pidx = 0;
-                    seg = warp;
-                    while (seg >= ksegs) {
-                        seg -= ksegs;
-                        pidx += 2 * ksegs;
-                    }
-                    pidx += seg;
+                const int sstep = ph.sstep, dstep = ph.dstep, wrapn = ph.wrapn, winc = ph.winc;
+                const int kf = ph.kf;
+                const bool quad = QUAD && ph.quad != 0;
+                // this warp's first pass is number `warp` of the CTA's share (by subtraction: at most 15 steps)
+                int seg = warp, pidx = 0, cur_seg = -1;
+                while (seg >= wrapn) {
+                    seg -= wrapn;
+                    pidx += ph.winit;
                 }
-                const int dstep = 2 * pstep * ksegs + sstep;
+                if (!quad) pidx += seg;
                 ActRegs A;
 #pragma unroll 1
                 for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
                     const int cnt = min(F::PPS, n_passes - p0);
                     const int j = F::PPS == kCW ? warp : (((warp >> 3) == (i & 1)) ? (warp & 7) : F::PPS);
-                    if (j < cnt && seg != cur_seg) {
-                        load_act_regs<TYPE>(A, act, seg, nb, lane);
-                        cur_seg = seg;
+                    // activation segment of this pass (quad units: rows 0-1 | rows 2-3 | the short segment of all four)
+                    int aseg = seg;
+                    if (quad) aseg = seg < kf ? seg : (seg >= 2 * kf ? kf : seg - kf);
+                    if (j < cnt && aseg != cur_seg) {
+                        load_act_regs<TYPE>(A, act, aseg, nb, lane);
+                        cur_seg = aseg;
                     }
                     mbar_wait(full0 + 8 * slot, parity);
                     if (j < cnt) {
-                        const float keep = pass_dot<TYPE>(ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES, A, lane);
-                        if ((lane & 15) == 0) part[pidx + ((lane >> 4) ? ksegs : 0)] = keep;
+                        const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;
+                        if (quad && seg >= 2 * kf) {
+                            const float keep = pass_dot<TYPE, true>(pass, A, lane);
+                            if ((lane & 7) == 0) part[pidx + kf + (lane >> 3) * ksegs] = keep;
+                        } else {
+                            const float keep = pass_dot<TYPE, false>(pass, A, lane);
+                            int out = pidx;
+                            if (quad) out += seg < kf ? seg : 2 * ksegs + seg - kf;
+                            if ((lane & 15) == 0) part[out + ((lane >> 4) ? ksegs : 0)] = keep;
+                        }
                         pidx += dstep;
                         seg += sstep;
-                        if (seg >= ksegs) { // next row pair: + 2 * ksegs for the pair, - ksegs for the segment
-                            seg -= ksegs;
-                            pidx += ksegs;
+                        if (seg >= wrapn) { // next unit
+                            seg -= wrapn;
+                            pidx += winc;
                         }
                     }
                     __syncwarp();
@@ -1196,21 +1231,37 @@ struct RepackArgs {
     int gate_up; // logical row r: group r / 64, j = r % 64: j < 32 -> m[0] row 32*group + j, else m[1] row 32*group + j - 32
     int n_rows;  // logical rows
     int nb, ksegs;
-    int pair_off; // first row pair of the stream (tensor parallel: a rank streams only its own rows)
+    int quad, kf; // quad layout (see Phase): unit = 4 rows = 2 * kf + 1 passes
+    int row_off;  // first logical row of the stream (tensor parallel: a rank streams only its own rows)
     uint8_t *dst;
 };
-// one block per pass; thread t < 128 copies block (t & 63) of row (t >> 6)
+// one block per pass; a pass is four groups of 32 blocks: thread t < 128 copies block (t & 31) of group (t >> 5).
+// Plain pass: groups = (row 0 | row 1) x (blocks 0-31 | 32-63) of one 64-block segment; quad pass: groups = rows 0..3,
+// blocks = the short last segment.
 template <int TYPE> __global__ void repack_kernel(RepackArgs A) {
     using F = Fmt<TYPE>;
     const long long p = blockIdx.x;
-    const int pair = A.pair_off + (int)(p / A.ksegs), seg = (int)(p % A.ksegs);
     const int t = threadIdx.x;
     if (t >= 128) return;
-    const int r = t >> 6, i = t & 63;
-    const int lr = 2 * pair + r;
-    const int blk = seg * kSeg + i;
+    const int k = t >> 5, i = t & 31;
+    int lr, blk;
+    if (!A.quad) {
+        const int pair = (int)(p / A.ksegs), seg = (int)(p % A.ksegs);
+        lr = A.row_off + 2 * pair + (k >> 1);
+        blk = seg * kSeg + (k & 1) * 32 + i;
+    } else {
+        const int upq = 2 * A.kf + 1;
+        const int q = (int)(p / upq), m = (int)(p % upq);
+        if (m < 2 * A.kf) {
+            lr = A.row_off + 4 * q + (m < A.kf ? 0 : 2) + (k >> 1);
+            blk = (m < A.kf ? m : m - A.kf) * kSeg + (k & 1) * 32 + i;
+        } else {
+            lr = A.row_off + 4 * q + k;
+            blk = A.kf * kSeg + i;
+        }
+    }
     int mat = 0, row = lr;
-    bool valid = lr < A.n_rows && blk < A.nb;
+    const bool valid = lr < A.n_rows && blk < A.nb;
     if (A.gate_up) {
         const int grp = lr / 64, j = lr % 64;
         mat = j < 32 ? 0 : 1;
@@ -1222,8 +1273,8 @@ template <int TYPE> __global__ void repack_kernel(RepackArgs A) {
         }
     }
     uint8_t *pass = A.dst + (size_t)p * F::PASS_BYTES;
-    uint4 *pay = reinterpret_cast<uint4 *>(pass + r * F::ROW_PB + i * F::PB);
-    __half *scl = reinterpret_cast<__half *>(pass + 2 * F::ROW_PB + r * (kSeg * 2)) + i;
+    uint4 *pay = reinterpret_cast<uint4 *>(pass + k * (32 * F::PB) + i * F::PB);
+    __half *scl = reinterpret_cast<__half *>(pass + 2 * F::ROW_PB + k * 64) + i;
     if (valid) {
         const size_t b = (size_t)row * A.nb + blk;
         const uint4 *src = reinterpret_cast<const uint4 *>(A.m[mat].qs + b * F::PB);
@@ -1250,7 +1301,13 @@ struct ggb_decoder {
     size_t smem = 0;
     size_t stream_bytes = 0;
     std::vector<void *> peer_maps; // cudaIpcOpenMemHandle mappings of the other ranks' scratch
+    bool any_quad = false;         // some phase uses the quad layout -> the QUAD instantiation of the kernel
 };
+
+static const void *decoder_fn(int type, bool quad) {
+    if (type == GGB_TYPE_Q4_0) return quad ? (const void *)decoder_kernel<GGB_TYPE_Q4_0, true> : (const void *)decoder_kernel<GGB_TYPE_Q4_0, false>;
+    return quad ? (const void *)decoder_kernel<GGB_TYPE_Q8_0, true> : (const void *)decoder_kernel<GGB_TYPE_Q8_0, false>;
+}
 
 static void decoder_release(ggb_decoder *D) {
     for (void *pm : D->peer_maps) cudaIpcCloseMemHandle(pm);
@@ -1387,37 +1444,49 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
         ph.kind = kind; ph.layer = layer;
         const int nb = (int)w[0]->nb;
         ph.K = (int)w[0]->cols;
+        const int nbp = nb % kSeg;                       // blocks of the short last segment (0: none)
+        ph.quad = (nbp > 0 && nbp <= 32) ? 1 : 0;        // it fits one group of a pass: quad layout
+        ph.kf = nb / kSeg;
         ph.ksegs = (nb + kSeg - 1) / kSeg;
+        const int upq = 2 * ph.kf + 1;                   // passes per 4 rows (quad layout)
         RepackArgs A{};
-        A.n_mats = n; A.gate_up = gate_up ? 1 : 0; A.nb = nb; A.ksegs = ph.ksegs;
+        A.n_mats = n; A.gate_up = gate_up ? 1 : 0; A.nb = nb; A.ksegs = ph.ksegs; A.quad = ph.quad; A.kf = ph.kf;
         int rows = 0;
+        const int row_mult = ph.quad ? 4 : 2;
         for (int i = 0; i < n; i++) {
             A.m[i].qs = w[i]->qs; A.m[i].d = w[i]->d; A.m[i].rows = (int)w[i]->rows;
             rows += (int)w[i]->rows;
             if (w[i]->nb != nb || w[i]->type != type) { ok = false; why = "mixed shapes/types in one phase"; }
-            if (i + 1 < n && !gate_up && (w[i]->rows & 1)) { ok = false; why = "odd row count inside a fused phase"; }
+            if (i + 1 < n && !gate_up && (w[i]->rows % row_mult)) { ok = false; why = "row count inside a fused phase not a multiple of the unit"; }
         }
         ph.n_rows = rows; A.n_rows = rows;
-        const int n_pairs = (rows + 1) / 2;
         if (gate_up) {
-            ph.n_units = rows / 64; ph.unit_passes = 32 * ph.ksegs; ph.unit_rows = 64;
+            ph.n_units = rows / 64; ph.unit_rows = 64;
+            ph.unit_passes = ph.quad ? 16 * upq : 32 * ph.ksegs;
             if (rows % 64) { ok = false; why = "n_ff not a multiple of 32"; }
+        } else if (ph.quad) {
+            ph.n_units = (rows + 3) / 4; ph.unit_passes = upq; ph.unit_rows = 4;
         } else {
-            ph.n_units = n_pairs; ph.unit_passes = ph.ksegs; ph.unit_rows = 2;
+            ph.n_units = (rows + 1) / 2; ph.unit_passes = ph.ksegs; ph.unit_rows = 2;
+        }
+        if (ph.quad) {
+            ph.wrapn = upq; ph.sstep = kCW % upq; ph.dstep = 4 * ph.ksegs * (kCW / upq); ph.winc = 4 * ph.ksegs;
+            ph.winit = 4 * ph.ksegs;
+        } else {
+            ph.wrapn = ph.ksegs; ph.sstep = kCW % ph.ksegs; ph.dstep = 2 * (kCW / ph.ksegs) * ph.ksegs + ph.sstep;
+            ph.winc = ph.ksegs; ph.winit = 2 * ph.ksegs;
         }
         // tensor parallel: units are split by rank first (contiguous, balanced), then by CTA
         const int u_total = ph.n_units;
         ph.u_off = (int)(((long long)rank * u_total) / size);
         ph.n_units = (int)(((long long)(rank + 1) * u_total) / size) - ph.u_off;
         ph.uq = ph.n_units / sms; ph.ur = ph.n_units % sms;
-        ph.pstep = kCW / ph.ksegs; ph.sstep = kCW % ph.ksegs;
         const long long max_units = (ph.n_units + sms - 1) / sms;
         if (max_units * ph.unit_rows * ph.ksegs > kPartFloats) { ok = false; why = "phase does not fit the partial table"; }
         if (ph.K > kMaxK) { ok = false; why = "activation row too long"; }
         if (!ok) return ph;
-        (void)n_pairs;
         const size_t n_passes = (size_t)ph.n_units * ph.unit_passes; // this rank's passes only
-        A.pair_off = ph.u_off * (ph.unit_rows / 2);
+        A.row_off = ph.u_off * ph.unit_rows;
         if (n_passes == 0) return ph;
         void *stream = nullptr;
         cudaError_t ce = cudaMalloc(&stream, n_passes * pass_bytes);
@@ -1510,8 +1579,8 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     P.phases = D->d_phases;
     P.n_phases = (int)D->phases.size();
     D->smem = type == GGB_TYPE_Q4_0 ? sizeof(Smem<GGB_TYPE_Q4_0>) : sizeof(Smem<GGB_TYPE_Q8_0>);
-    const void *fn = type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
-                                           : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
+    for (const Phase &ph : D->phases) D->any_quad = D->any_quad || ph.quad;
+    const void *fn = decoder_fn(type, D->any_quad);
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem);
     int occ = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, D->smem);
@@ -1536,8 +1605,7 @@ int ggb_decoder_step(ggb_decoder *D) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(D != nullptr, "null decoder");
     void *args[] = {(void *)&D->P};
-    const void *fn = D->P.type == GGB_TYPE_Q4_0 ? (const void *)decoder_kernel<GGB_TYPE_Q4_0>
-                                                : (const void *)decoder_kernel<GGB_TYPE_Q8_0>;
+    const void *fn = decoder_fn(D->P.type, D->any_quad);
     // cooperative launch: the flagged data flow needs every CTA resident (a waiting CTA spins).  The fp16
     // exp / gelu tables are pinned in the persisting part of L2 for this kernel.
     cudaLaunchConfig_t cfg{};

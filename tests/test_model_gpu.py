@@ -16,6 +16,10 @@ SMALL = {
     "mqa": dict(n_embd=256, n_layer=3, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=2048, n_ctx=96),
     # Gemma-7B-like: MHA, n_head*head_dim != n_embd, K > 4096 in the down projection (2 K-segments)
     "mha": dict(n_embd=512, n_layer=2, n_head=4, n_head_kv=4, head_dim=128, n_ff=4608, n_vocab=1024, n_ctx=64),
+    # K = 3072 as in Gemma-7B: 96 blocks = one full 64-block segment + a short one (quad passes, kf = 1); n_ff = 1280:
+    # 40 blocks, a short segment too long for a quad pass (zero-padded plain pass).  The configs above cover kf = 0
+    # (K <= 1024) and kf = 2 (n_ff 4608)
+    "k96": dict(n_embd=3072, n_layer=1, n_head=2, n_head_kv=2, head_dim=128, n_ff=1280, n_vocab=512, n_ctx=48),
     # outside the fused kernel's envelope (n_embd % 256 != 0): exercises the per-operator lowering
     "odd": dict(n_embd=384, n_layer=2, n_head=4, n_head_kv=2, head_dim=96, n_ff=1056, n_vocab=777, n_ctx=48),
 }
@@ -32,7 +36,7 @@ def _models(gpu, dims, wtype, capture=True, sigma_embd=0.002, fused=True):
 
 
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "ops"])
-@pytest.mark.parametrize("name", ["mqa", "mha", "odd"])
+@pytest.mark.parametrize("name", ["mqa", "mha", "k96", "odd"])
 @pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
 def test_generate_matches_oracle(gpu, name, wtype, fused):
     dims = SMALL[name]
