@@ -69,6 +69,9 @@ int gemma_model::make_shards() {
     auto sl = [&](const ggb_weight *w, const tp_range &r, ggb_weight **out) -> int {
         ggb_weight_free(*out);
         *out = nullptr;
+        // a plan made for the persistent kernel only (head count not divisible by the world size) has no
+        // per-operator ranges: that lowering is not built, the kernel slices its own pass streams
+        if (r.nrows == 0) return 0;
         return ggb_weight_slice(w, r.row0, r.nrows, out);
     };
     for (auto &l : layers_) {
