@@ -144,15 +144,21 @@ static_assert(U_E + 1024 <= U_BYTES, "union region too small for the attention v
 static_assert(U_XS + kMaxE * 4 <= U_ACT_D && kMaxE <= U_XS, "xs overlaps the activation row");
 static_assert(U_CW + kMaxChunks * 4 <= U_BYTES, "combine staging too large");
 
-template <int TYPE> struct Smem {
-    alignas(1024) uint8_t ring[kSlots][Fmt<TYPE>::SLOT_BYTES];
-    alignas(128) uint8_t u[U_BYTES];
+// GROUPS: how many ATTN items a CTA works on at once.  1 (MQA models): all 16 warps on one item, weight ring of 5 slots.
+// 2 (MHA models: many one-head items per CTA, each a ~3 us latency chain): two groups of 8 warps, each with its own K/V
+// buffers, barrier and item; the ring gives up one slot for the second attention view.
+constexpr int kAttnView = U_E + 1024; // bytes of one group's attention view
+template <int TYPE, int GROUPS> struct Smem {
+    static constexpr int SLOTS = GROUPS == 2 ? kSlots - 1 : kSlots;
+    static constexpr int U_SIZE = GROUPS * kAttnView > U_BYTES ? GROUPS * kAttnView : U_BYTES;
+    alignas(1024) uint8_t ring[SLOTS][Fmt<TYPE>::SLOT_BYTES];
+    alignas(128) uint8_t u[U_SIZE];
     double red[kCW];
     float cand_v[kCW];
     int cand_i[kCW];
     alignas(8) unsigned long long full_bar[kSlots];
     alignas(8) unsigned long long empty_bar[kSlots];
-    alignas(8) unsigned long long kv_bar; // ATTN: K / V chunk rows have landed (kCW arrivals + bytes)
+    alignas(8) unsigned long long kv_bar[2]; // ATTN: a group's K / V chunk rows have landed (its warps' arrivals + bytes)
     long long tr[2]; // trace stamps of the current phase (thread 0)
     alignas(8) ll_t resid[32]; // residual words of this CTA's first 32 rows, fetched asynchronously before the passes
     int sched[6]; // [3] = token, [4] = number of positions; the token's attention schedule: chunks, this rank's ATTN items, items % grid (kept out of registers:
@@ -368,9 +374,10 @@ template <int TYPE> struct ChunkWalk {
 // prologues) and HBM would idle; with the look-ahead in L2 the stream keeps flowing and GATE_UP / DOWN find their
 // tail in L2 instead of waiting for HBM.  The look-ahead is bounded (chunks x 36 KB x 148 SMs, well inside the
 // 126 MB L2), and the later ring load marks the lines evict-first, so a consumed chunk is the first to leave.
-template <int TYPE>
-__device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE> &S, int cta, int G) {
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE, GROUPS> &S, int cta, int G) {
     using F = Fmt<TYPE>;
+    constexpr int SLOTS = Smem<TYPE, GROUPS>::SLOTS;
     const uint32_t ring = smem_u32(&S.ring[0][0]);
     const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
     int slot = 0, issued = 0;
@@ -383,7 +390,7 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
     bool more = P.prefetch_chunks > 0;
     for (int i = 0; i < P.prefetch_chunks && more; i++) {
         more = pre.next(psrc, pbytes);
-        if (more && i >= kSlots) bulk_prefetch_l2(psrc, pbytes); // the first kSlots chunks go straight to the ring
+        if (more && i >= SLOTS) bulk_prefetch_l2(psrc, pbytes); // the first kSlots chunks go straight to the ring
     }
 #pragma unroll 1
     while (load.next(src, bytes)) {
@@ -396,12 +403,12 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
         // queueing delay every small latency-critical access (flag polls, table lookups) sees
         if (issued >= max_out) {
             const int old = issued - max_out;
-            mbar_wait(full0 + 8 * (old % kSlots), (uint32_t)((old / kSlots) & 1));
+            mbar_wait(full0 + 8 * (old % SLOTS), (uint32_t)((old / SLOTS) & 1));
         }
         mbar_expect_tx(full0 + 8 * slot, bytes);
         bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot, pol);
         issued++;
-        if (++slot == kSlots) {
+        if (++slot == SLOTS) {
             slot = 0;
             parity ^= 1u;
         }
@@ -442,8 +449,8 @@ __device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lan
 // partials (partial t = elements t, t + 256, ...), butterfly per warp, the 8 warp sums in order.  Thread
 // (warp w, lane l) loads exactly the elements of partial 32 * (w & 7) + l, so both warp halves hold the
 // partials in registers and no staging pass is needed; the halves then split the quantisation by blocks.
-template <int TYPE>
-__device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE, GROUPS> &S, const Phase &ph, int token,
                                               uint32_t tag, float *f32_out, bool dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = P.E, nk = E / GGB_DEV_NORM_THREADS;
@@ -459,13 +466,14 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
     double acc = 0.0;
     // a thread's words are requested 8 at a time (all of them for E <= 2048): ONE L2 round trip when x is there
 #pragma unroll 1
-    for (int k0 = 0; k0 < nk; k0 += 8) {
-        ll_t v[8];
+    constexpr int NV = GROUPS == 2 ? 4 : 8; // (the two-group kernel has fewer registers to spare)
+    for (int k0 = 0; k0 < nk; k0 += NV) {
+        ll_t v[NV];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < NV; u++)
             if (in && k0 + u < nk) v[u] = ll_peek(in + GGB_DEV_NORM_THREADS * (k0 + u) + base);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < NV; u++) {
             if (k0 + u < nk) {
                 const int i = GGB_DEV_NORM_THREADS * (k0 + u) + base;
                 const float x = in ? ll_get_f(v[u], in + i, tag) : embed_value<TYPE>(P, token, i);
@@ -507,8 +515,8 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
 }
 
 // O: the flagged fp32 row written by COMBINE -> quantize_row_q8_0 (ggml mul_mat INIT stage)
-template <int TYPE>
-__device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void quant_prologue(Smem<TYPE, GROUPS> &S, const ll_t *in, int K, uint32_t tag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ua = smem_u32(S.u);
 #pragma unroll 1
@@ -527,8 +535,8 @@ __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, in
 
 // DOWN: packed Q8_0 row written by GATE_UP: 4 codes per flagged word, then one word per block with the fp16 scale
 // (low half) and the sum of the block's codes (high half, int16: |sum| <= 32 * 127), from which the Q4_0 bias follows
-template <int TYPE>
-__device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void packed_prologue(Smem<TYPE, GROUPS> &S, const ll_t *in, int K, uint32_t tag) {
     const int tid = threadIdx.x;
     const int nw = K / 4, ns = K / 32;
     uint32_t *aq = reinterpret_cast<uint32_t *>(S.u);
@@ -658,10 +666,20 @@ __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int l
 // heads of the item at once and reduces the 8 lane partials with ONE folded butterfly (9 shuffles instead of 40;
 // every sum adds the same pairs in the same order as the plain xor-butterfly), and P.V runs with one thread per
 // pair of dims for all heads (V converted once, the heads' weights in one LDS.128).
-template <int TYPE>
-__device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
+// (the group index is a run-time value: making it a template parameter - two inlined copies - or calling the groups'
+// code as real functions both measured slower on Gemma-7B; the two-group kernel has ~50 bytes of spills either way)
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void attn_group(const DecoderParams &P, Smem<TYPE, GROUPS> &S, const Phase &ph, int cta, int G,
                                            int n_pos, int n_items, uint32_t tag, uint32_t &kv_parity, bool dbg) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // a group = kCW / GROUPS warps working on one item: thread / warp index inside the group, the group's view
+    constexpr int NW = kCW / GROUPS, NT = kCT / GROUPS;
+    const int lane = threadIdx.x & 31, grp = GROUPS == 2 ? (threadIdx.x >> 5) / NW : 0;
+    const int warp = (threadIdx.x >> 5) - grp * NW, tid = threadIdx.x - grp * NT;
+    uint8_t *const view = S.u + grp * kAttnView;
+    auto group_bar = [&]() {
+        if (GROUPS == 1) consumer_bar();
+        else asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(NT) : "memory");
+    };
     const int d = P.d, halfd = d >> 1, Hkv = P.Hkv, Gq = P.Gq;
     // with more than 4 query heads per KV head an item is split in two (heads 0..Gq/2-1 | the rest): the K/V
     // chunk is read twice (L2), the score / PV work per CTA halves and twice as many SMs take part
@@ -673,14 +691,14 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
     const size_t kv_stride = (size_t)Hkv * d;
     const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
     const ll_t *q_all = ph.in_ll, *k_all = q_all + (size_t)P.H * d, *v_all = k_all + (size_t)Hkv * d;
-    __half *Kc = reinterpret_cast<__half *>(S.u + U_KC), *Vc = reinterpret_cast<__half *>(S.u + U_VC);
-    float *Sq = reinterpret_cast<float *>(S.u + U_SQ);              // [4][d] fp16-rounded q, widened
-    float(*Ss)[kChunk] = reinterpret_cast<float(*)[kChunk]>(S.u + U_S); // [4][32] scores
-    float *Se = reinterpret_cast<float *>(S.u + U_E);               // [32][4] soft-max numerators, heads innermost
-    const uint32_t kc_addr = smem_u32(Kc), vc_addr = smem_u32(Vc), kvbar = smem_u32(&S.kv_bar);
+    __half *Kc = reinterpret_cast<__half *>(view + U_KC), *Vc = reinterpret_cast<__half *>(view + U_VC);
+    float *Sq = reinterpret_cast<float *>(view + U_SQ);              // [4][d] fp16-rounded q, widened
+    float(*Ss)[kChunk] = reinterpret_cast<float(*)[kChunk]>(view + U_S); // [4][32] scores
+    float *Se = reinterpret_cast<float *>(view + U_E);               // [32][4] soft-max numerators, heads innermost
+    const uint32_t kc_addr = smem_u32(Kc), vc_addr = smem_u32(Vc), kvbar = smem_u32(&S.kv_bar[grp]);
     const uint32_t row_bytes = (uint32_t)d * 2;
 #pragma unroll 1
-    for (int it = cta + ph.rot >= G ? cta + ph.rot - G : cta + ph.rot; it < n_items; it += G) {
+    for (int it = (cta + ph.rot >= G ? cta + ph.rot - G : cta + ph.rot) + grp * G; it < n_items; it += GROUPS * G) {
         const int hh = hsplit == 2 ? (it & 1) : 0;
         const int gc = (hsplit == 2 ? (it >> 1) : it) * P.R + P.rank;
         const int g = gc & (Hkv - 1), c = gc >> P.kvh_shift;
@@ -706,9 +724,9 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                 }
             } else {
                 uint32_t bytes = 0;
-                for (int j = warp; j < np; j += kCW) bytes += j == jnew ? 0u : 2u * row_bytes;
+                for (int j = warp; j < np; j += NW) bytes += j == jnew ? 0u : 2u * row_bytes;
                 mbar_expect_tx(kvbar, bytes); // arrive (+ expected bytes, possibly 0): the barrier counts the kCW warps
-                for (int j = warp; j < np; j += kCW) {
+                for (int j = warp; j < np; j += NW) {
                     if (j == jnew) continue;
                     const size_t src = (size_t)(p0 + j) * kv_stride + (size_t)g * d;
                     bulk_g2s_plain(kc_addr + (uint32_t)j * row_bytes, ph.kcache + src, row_bytes, kvbar);
@@ -718,7 +736,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         }
         DBG_STAMP(1);
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16)
-        for (int i = tid; i < Gh * halfd; i += kCT) {
+        for (int i = tid; i < Gh * halfd; i += NT) {
             const int jh = i >> P.hd_shift, e = i & (halfd - 1);
             const ll_t *qh = q_all + (size_t)(h0 + jh) * d;
             const ll_t w0 = ll_peek(qh + e), w1 = ll_peek(qh + e + halfd);
@@ -731,7 +749,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         }
         DBG_STAMP(2);
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
-            for (int e = tid; e < halfd; e += kCT) {
+            for (int e = tid; e < halfd; e += NT) {
                 const ll_t *kp = k_all + (size_t)g * d + e;
                 const ll_t w0 = ll_peek(kp), w1 = ll_peek(kp + halfd);
                 const float cs = cosr[e], sn = sinr[e];
@@ -746,7 +764,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
                     krow[e + halfd] = k1;
                 }
             }
-            for (int e = tid; e < d; e += kCT) {
+            for (int e = tid; e < d; e += NT) {
                 const ll_t *vp = v_all + (size_t)g * d + e;
                 const __half vv = __float2half_rn(ll_get_f(ll_peek(vp), vp, tag));
                 Vc[jnew * d + e] = vv;
@@ -756,13 +774,14 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
         DBG_STAMP(3);
         mbar_wait(kvbar, kv_parity);
         kv_parity ^= 1u;
-        consumer_bar();
+        group_bar();
         DBG_STAMP(4);
-        // scores: warp w takes positions w and w + 16 against the item's (<= 4) heads; lane = 8 dims.  fp16 x fp16
+        // scores: warp w takes positions w and w + NW (and, with two groups, w + 2 NW and w + 3 NW) against the item's (<= 4) heads; lane = 8 dims.  fp16 x fp16
         // products are exact in fp32, so fmaf(k, q, acc) == acc + k*q rounded once
-        {
+#pragma unroll 1
+        for (int rp = 0; rp < GROUPS; rp++) { // a warp takes kChunk / NW positions, two at a time
             const bool in = 8 * lane < d;
-            const int j0 = warp, j1 = warp + kCW;
+            const int j0 = warp + 2 * rp * NW, j1 = j0 + NW;
             float kf[2][8];
 #pragma unroll
             for (int p = 0; p < 2; p++) {
@@ -818,7 +837,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             if ((lane & 3) == 0 && js < np && us < Gh) Ss[us][js] = k1;
         }
         DBG_STAMP(5);
-        consumer_bar();
+        group_bar();
         // per-head chunk soft-max through the fp16 exp table (heads the item does not have get weight 0)
         if (warp < 4) {
             float e = 0.0f;
@@ -835,7 +854,7 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             Se[lane * 4 + warp] = e;
         }
         DBG_STAMP(6);
-        consumer_bar();
+        group_bar();
         DBG_STAMP(7);
         // acc[h][i] = sum_p e[h][p] * V[p][i], sequential in p; thread -> dims 2 tid, 2 tid + 1 for every head
         // (e is an fp16 value: e*v is exact, fmaf == mul + add)
@@ -862,16 +881,22 @@ __device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE> &S
             }
         }
         DBG_STAMP(8);
-        consumer_bar();
+        group_bar();
     }
+}
+
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void attn_phase(const DecoderParams &P, Smem<TYPE, GROUPS> &S, const Phase &ph, int cta, int G,
+                                           int n_pos, int n_items, uint32_t tag, uint32_t &kv_parity, bool dbg) {
+    attn_group<TYPE, GROUPS>(P, S, ph, cta, G, n_pos, n_items, tag, kv_parity, dbg);
 }
 
 // COMBINE: one CTA per (head, 32-dim slice): M = max m_c; w_c = exp_table[f16(m_c - M)]; L = sum l_c*w_c;
 // O = sum acc_c*w_c (sequential in c); out = O / L.  All 16 warps stage the flagged partials (one L2 round
 // trip), warp 0 runs the sequential chain from shared memory (lane = dim).  Tasks start on the CTAs after the
 // ones that own ATTN items, which are free earlier.
-template <int TYPE>
-__device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
+template <int TYPE, int GROUPS>
+__device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE, GROUPS> &S, const Phase &ph, int cta, int G,
                                               int nchunk, int items_rem, uint32_t tag, bool dbg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, slices = d >> 5;
@@ -949,19 +974,21 @@ __device__ __forceinline__ void combine_phase(const DecoderParams &P, Smem<TYPE>
 // ---------------------------------------------------------------- the kernel
 // QUAD: the model has phases in the quad layout (a short last K segment).  A compile-time switch, because the pass loop
 // is issue-bound: the two extra branches of the quad layout cost a model without such phases (Gemma-2B) 1.5 %.
-template <int TYPE, bool QUAD>
+template <int TYPE, bool QUAD, int GROUPS>
 __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_constant__ DecoderParams P) {
     using F = Fmt<TYPE>;
-    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
+    using SM = Smem<TYPE, GROUPS>;
+    SM &S = *reinterpret_cast<SM *>(ggb_dec_smem);
     const int cta = blockIdx.x, G = gridDim.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < kSlots; i++) {
+        for (int i = 0; i < SM::SLOTS; i++) {
             mbar_init(smem_u32(&S.full_bar[i]), 1);
             mbar_init(smem_u32(&S.empty_bar[i]), kCW);
         }
-        mbar_init(smem_u32(&S.kv_bar), kCW);
+        mbar_init(smem_u32(&S.kv_bar[0]), kCW / GROUPS);
+        mbar_init(smem_u32(&S.kv_bar[1]), kCW / GROUPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -979,7 +1006,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     }
 
     if (warp == kCW) {
-        if (lane == 0) producer_loop<TYPE>(P, S, cta, G);
+        if (lane == 0) producer_loop<TYPE, GROUPS>(P, S, cta, G);
         return;
     }
 
@@ -1010,9 +1037,9 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             const int n_passes = (u1 - u0) * ph.unit_passes;
             const int ksegs = ph.ksegs, nb = ph.K >> 5;
             if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
-                if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
-                else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
-                else norm_prologue<TYPE>(P, S, ph, S.sched[3], tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr, dbg);
+                if (kind == PH_O) quant_prologue<TYPE, GROUPS>(S, ph.in_ll, ph.K, tag);
+                else if (kind == PH_DOWN) packed_prologue<TYPE, GROUPS>(S, ph.in_ll, ph.K, tag);
+                else norm_prologue<TYPE, GROUPS>(P, S, ph, S.sched[3], tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr, dbg);
             }
             if (P.trace && tid == 0) S.tr[1] = (long long)gtime();
             // the residual of this thread's first row: requested before the passes, consumed in the epilogue
@@ -1071,7 +1098,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-                    if (++slot == kSlots) {
+                    if (++slot == SM::SLOTS) {
                         slot = 0;
                         parity ^= 1u;
                     }
@@ -1173,14 +1200,14 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             for (int rep = P.dbg_repeat; rep >= 1; rep--) {
                 const bool dbg_r = dbg && rep == 1;
                 if (dbg_r && threadIdx.x == 0) P.dbg[16 * cta] = clock64();
-                attn_phase<TYPE>(P, S, ph, cta, G, S.sched[4], S.sched[1], tag, kv_parity, dbg_r);
+                attn_phase<TYPE, GROUPS>(P, S, ph, cta, G, S.sched[4], S.sched[1], tag, kv_parity, dbg_r);
             }
         } else if (kind == PH_COMBINE) {
 #pragma unroll 1
             for (int rep = P.dbg_repeat; rep >= 1; rep--) {
                 const bool dbg_r = dbg && rep == 1;
                 if (dbg_r && threadIdx.x == 0) P.dbg[16 * cta] = clock64();
-                combine_phase<TYPE>(P, S, ph, cta, G, S.sched[0], S.sched[2], tag, dbg_r);
+                combine_phase<TYPE, GROUPS>(P, S, ph, cta, G, S.sched[0], S.sched[2], tag, dbg_r);
             }
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
             if (cta == 0 && warp == 0) {
@@ -1302,11 +1329,21 @@ struct ggb_decoder {
     size_t stream_bytes = 0;
     std::vector<void *> peer_maps; // cudaIpcOpenMemHandle mappings of the other ranks' scratch
     bool any_quad = false;         // some phase uses the quad layout -> the QUAD instantiation of the kernel
+    int groups = 1;                // ATTN items a CTA works on at once (2 for MHA models)
 };
 
-static const void *decoder_fn(int type, bool quad) {
-    if (type == GGB_TYPE_Q4_0) return quad ? (const void *)decoder_kernel<GGB_TYPE_Q4_0, true> : (const void *)decoder_kernel<GGB_TYPE_Q4_0, false>;
-    return quad ? (const void *)decoder_kernel<GGB_TYPE_Q8_0, true> : (const void *)decoder_kernel<GGB_TYPE_Q8_0, false>;
+// instantiations: (plain, 1 group) | (quad, 1 group) | (quad, 2 groups: also serves MHA models without quad phases)
+static const void *decoder_fn(int type, bool quad, int groups) {
+    if (type == GGB_TYPE_Q4_0) {
+        if (groups == 2) return (const void *)decoder_kernel<GGB_TYPE_Q4_0, true, 2>;
+        return quad ? (const void *)decoder_kernel<GGB_TYPE_Q4_0, true, 1> : (const void *)decoder_kernel<GGB_TYPE_Q4_0, false, 1>;
+    }
+    if (groups == 2) return (const void *)decoder_kernel<GGB_TYPE_Q8_0, true, 2>;
+    return quad ? (const void *)decoder_kernel<GGB_TYPE_Q8_0, true, 1> : (const void *)decoder_kernel<GGB_TYPE_Q8_0, false, 1>;
+}
+static size_t decoder_smem(int type, int groups) {
+    if (type == GGB_TYPE_Q4_0) return groups == 2 ? sizeof(Smem<GGB_TYPE_Q4_0, 2>) : sizeof(Smem<GGB_TYPE_Q4_0, 1>);
+    return groups == 2 ? sizeof(Smem<GGB_TYPE_Q8_0, 2>) : sizeof(Smem<GGB_TYPE_Q8_0, 1>);
 }
 
 static void decoder_release(ggb_decoder *D) {
@@ -1580,9 +1617,14 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     }
     P.phases = D->d_phases;
     P.n_phases = (int)D->phases.size();
-    D->smem = type == GGB_TYPE_Q4_0 ? sizeof(Smem<GGB_TYPE_Q4_0>) : sizeof(Smem<GGB_TYPE_Q8_0>);
+    // two ATTN groups pay off when a CTA has many items per layer (MHA at long context: Gemma-7B Q8_0 n_kv 8192
+    // 4.67 -> 4.03 ms/token); at n_kv <= 2048 the one-group kernel with its 5-slot ring is as fast or faster
+    D->groups = (Hkv > 1 && dims->n_ctx >= 4096) ? 2 : 1;
+    if (const char *e = getenv("GGB_ATTN_GROUPS")) D->groups = atoi(e) == 2 ? 2 : 1;
+    D->smem = decoder_smem(type, D->groups);
+    P.max_outstanding = std::min(P.max_outstanding, D->groups == 2 ? kSlots - 1 : kSlots);
     for (const Phase &ph : D->phases) D->any_quad = D->any_quad || ph.quad;
-    const void *fn = decoder_fn(type, D->any_quad);
+    const void *fn = decoder_fn(type, D->any_quad, D->groups);
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem);
     int occ = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, kThreads, D->smem);
@@ -1607,7 +1649,7 @@ int ggb_decoder_step(ggb_decoder *D) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(D != nullptr, "null decoder");
     void *args[] = {(void *)&D->P};
-    const void *fn = decoder_fn(D->P.type, D->any_quad);
+    const void *fn = decoder_fn(D->P.type, D->any_quad, D->groups);
     // cooperative launch: the flagged data flow needs every CTA resident (a waiting CTA spins).  The fp16
     // exp / gelu tables are pinned in the persisting part of L2 for this kernel.
     cudaLaunchConfig_t cfg{};

@@ -35,6 +35,27 @@ def _models(gpu, dims, wtype, capture=True, sigma_embd=0.002, fused=True):
     return m, om
 
 
+@pytest.mark.parametrize("name", ["mha", "k96", "mqa"])
+@pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
+def test_two_attention_groups_match_oracle(gpu, monkeypatch, name, wtype):
+    """The long-context MHA form of the persistent kernel (two 8-warp groups, each on its own ATTN item, 4-slot
+    weight ring; chosen automatically for MHA models with n_ctx >= 4096) forced onto the small configs: bit-exact."""
+    monkeypatch.setenv("GGB_ATTN_GROUPS", "2")
+    dims = SMALL[name]
+    m, om = _models(gpu, dims, wtype, fused=True)
+    assert m.is_fused
+    prompt = ((1 + 7919 * np.arange(35)) % dims["n_vocab"]).astype(np.int32)  # crosses a 32-position chunk boundary
+    toks, _, _ = m.generate(prompt, 6)
+    dtoks, _, _ = om.generate(prompt, 6, O.DEV)
+    assert np.array_equal(toks, dtoks)
+    assert np.array_equal(bits(m.logits()), bits(om.capture("result_output")))
+    for il in range(dims["n_layer"]):
+        for cap in ("kqv_out", "l_out"):
+            assert np.array_equal(bits(m.capture(cap, il)), bits(om.capture(cap, il))), (cap, il)
+    m.close()
+    om.close()
+
+
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "ops"])
 @pytest.mark.parametrize("name", ["mqa", "mha", "k96", "odd"])
 @pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
