@@ -465,8 +465,8 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE,
     if (warp < nquad) w4 = *reinterpret_cast<const float4 *>(norm_w + 128 * warp + 4 * lane);
     double acc = 0.0;
     // a thread's words are requested 8 at a time (all of them for E <= 2048): ONE L2 round trip when x is there
-#pragma unroll 1
     constexpr int NV = GROUPS == 2 ? 4 : 8; // (the two-group kernel has fewer registers to spare)
+#pragma unroll 1
     for (int k0 = 0; k0 < nk; k0 += NV) {
         ll_t v[NV];
 #pragma unroll
