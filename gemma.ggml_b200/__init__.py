@@ -104,6 +104,7 @@ _CUDA_SIG = {
     "ggb_op_sample_greedy": (i32, [vp, i64, vp, vp, vp]), "ggb_sample_scratch_bytes": (sz, [i64]),
     "ggb_gemm_workspace_bytes": (sz, [i64, i64, i64]),
     "ggb_op_gemm_bf16": (i32, [vp, vp, i64, vp, i64, vp, vp, sz]),
+    "ggb_op_gemm_bf16_multi": (i32, [i32, vp, vp, i64, vp, vp, vp, sz]),
     "ggb_op_cvt_f32_bf16": (i32, [vp, i64, vp]),
     "ggb_op_rms_norm_bf16": (i32, [vp, vp, f32, i64, i64, vp]), "ggb_op_geglu_bf16": (i32, [vp, vp, i64, vp]),
     "ggb_op_attn_prefill": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),

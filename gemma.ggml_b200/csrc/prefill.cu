@@ -88,15 +88,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// up to 3 weight matrices that share the A operand run as ONE launch (Q | K | V, gate | up): a segment = one matrix,
+// its first row is a multiple of the tile height, so a tile belongs to exactly one segment
+constexpr int kMaxSegs = 3;
+struct GemmSeg {
+    const uint8_t *qs; // weight payload plane [rows][nb][16|32]
+    const __half *d;   // weight scale plane [rows][nb]
+    float *c;          // [T][ldc] output of this matrix
+    int ldc;
+    int n_begin, rows; // first row of the segment in the concatenated N, its row count
+};
 struct GemmArgs {
-    const uint8_t *qs; // weight payload plane [N][nb][16|32]
-    const __half *d;   // weight scale plane [N][nb]
-    int N, K, nb;      // nb = K / 32
+    GemmSeg seg[kMaxSegs];
+    int n_seg;
+    int N, K, nb;      // N = concatenated rows (tile-padded between segments), nb = K / 32
     const __nv_bfloat16 *a; // [T][K]
     int T;
-    float *c;          // [T][ldc] (ksplit == 1) or workspace [ksplit][T][N]
-    int ldc;
-    const float *resid; // [T][ldc] or null (only with ksplit == 1)
+    float *ws;         // K-split workspace [ksplit][T][N] or null (ksplit == 1: tiles go straight to seg.c)
+    const float *resid; // [T][seg[0].ldc] or null (single segment, ksplit == 1)
     int kblocks_per_split; // 64-wide K blocks per split
 };
 
@@ -151,6 +160,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
     const uint32_t tmem_slot = bars + 8 * (2 * kStages + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, split = blockIdx.z;
+    int si = 0;
+    if (A.n_seg > 1 && n0 >= A.seg[1].n_begin) si = (A.n_seg > 2 && n0 >= A.seg[2].n_begin) ? 2 : 1;
+    const GemmSeg &sg = A.seg[si];
+    const int sn0 = n0 - sg.n_begin; // first row of this tile inside its matrix
     const int kb0 = split * A.kblocks_per_split;
     const int kb1 = min(kb0 + A.kblocks_per_split, (A.K + BK - 1) / BK);
 
@@ -179,8 +192,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
         // memory latency of both operands overlaps the dequantisation arithmetic.
         // thread t owns ONE quant block (32 weights) per K block: row n0 + (t >> 1), block 2 kb + (t & 1)
         const int wr = tid >> 1, whalf = tid & 1;
-        const int wrow = n0 + wr;
-        const bool wlive = wrow < A.N;
+        const int wrow = sn0 + wr;
+        const bool wlive = wrow < sg.rows;
         constexpr int PBW = TYPE == GGB_TYPE_Q8_0 ? 2 : 1; // 16-byte payload words per quant block
         // register ring of raw codes, kStages K blocks deep: HBM latency under load (~2000 cycles) is longer
         // than one K block of MMA time, so the codes are requested kStages blocks before they are converted
@@ -189,8 +202,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
         auto fetch = [&](int kb, uint4 (&r)[PBW], __half &d1) {
             if (!wlive || kb >= kb1) return;
             const size_t blk = (size_t)wrow * A.nb + (size_t)kb * 2 + whalf;
-            d1 = A.d[blk];
-            const uint4 *src = reinterpret_cast<const uint4 *>(A.qs + blk * (TYPE == GGB_TYPE_Q8_0 ? 32 : 16));
+            d1 = sg.d[blk];
+            const uint4 *src = reinterpret_cast<const uint4 *>(sg.qs + blk * (TYPE == GGB_TYPE_Q8_0 ? 32 : 16));
 #pragma unroll
             for (int j = 0; j < PBW; j++) r[j] = __ldg(src + j);
         };
@@ -269,7 +282,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
         // ================= epilogue: warp w reads TMEM lanes 32w .. 32w+31 (accumulator rows)
         mbar_wait(bars + 8 * 2 * kStages, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float *cbase = A.c + (size_t)split * A.T * A.ldc; // split > 0 only with the workspace (ldc == N)
+        // straight to the matrix's output, or (K-split) into this split's [T][N] plane of the workspace
+        float *cbase = A.ws ? A.ws + (size_t)split * A.T * A.N + n0 : sg.c + sn0;
+        const int cld = A.ws ? A.N : sg.ldc;
 #pragma unroll 1
         for (int mt = 0; mt < BM / 128; mt++) {
             const int lq = warp & 3, chalf = warp >> 2; // TMEM lane quarter of this warp, column quarter it drains
@@ -278,10 +293,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
             for (int c0 = chalf * (BN / 4); c0 < (chalf + 1) * (BN / 4); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(mt * BN + c0), v);
-                const int col = n0 + c0;
-                if (row < A.T && col < A.N) { // N % 32 == 0
-                    float *dst = cbase + (size_t)row * A.ldc + col;
-                    const float *rs = A.resid ? A.resid + (size_t)row * A.ldc + col : nullptr;
+                if (row < A.T && sn0 + c0 < sg.rows) { // rows % 32 == 0
+                    float *dst = cbase + (size_t)row * cld + c0;
+                    const float *rs = A.resid ? A.resid + (size_t)row * sg.ldc + sn0 + c0 : nullptr;
 #pragma unroll
                     for (int u = 0; u < 32; u += 4) {
                         float4 o = make_float4(__uint_as_float(v[u]), __uint_as_float(v[u + 1]), __uint_as_float(v[u + 2]),
@@ -333,15 +347,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16w_kernel(const GemmA
 }
 
 // partial tiles of a K-split GEMM summed in split order (+ residual)
-__global__ void splitk_reduce_kernel(const float *ws, int splits, int64_t T, int64_t N, float *c, int64_t ldc,
-                                     const float *resid) {
+__global__ void splitk_reduce_kernel(const GemmArgs A, int splits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t T = A.T, N = A.N;
     if (i >= T * N) return;
-    const int64_t t = i / N, n = i % N;
-    float acc = ws[i];
-    for (int s = 1; s < splits; s++) acc += ws[(int64_t)s * T * N + i];
-    if (resid) acc += resid[t * ldc + n];
-    c[t * ldc + n] = acc;
+    const int64_t t = i / N;
+    const int n = (int)(i % N);
+    int si = 0;
+    if (A.n_seg > 1 && n >= A.seg[1].n_begin) si = (A.n_seg > 2 && n >= A.seg[2].n_begin) ? 2 : 1;
+    const GemmSeg &sg = A.seg[si];
+    const int col = n - sg.n_begin;
+    if (col >= sg.rows) return; // tile padding between segments
+    float acc = A.ws[i];
+    for (int s = 1; s < splits; s++) acc += A.ws[(int64_t)s * T * N + i];
+    if (A.resid) acc += A.resid[t * sg.ldc + col];
+    sg.c[t * sg.ldc + col] = acc;
 }
 
 // rms_norm * w -> bf16 (the A operand of the next GEMM): same double-sum order as rms_norm_kernel (elementwise.cu)
@@ -482,14 +502,25 @@ int ggb_op_geglu_bf16(const float *gate, const float *up, int64_t n, void *y_bf1
     return GGB_OK;
 }
 
-int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *c, int64_t ldc, const float *resid,
-                     void *workspace, size_t workspace_bytes) {
+static int gemm_launch(int n, const ggb_weight *const *w, const void *a_bf16, int64_t T, float *const *c, const int64_t *ldc,
+                       const float *resid, void *workspace, size_t workspace_bytes) {
     GGB_REQUIRE_INIT();
-    GGB_CHECK_ARG(w && a_bf16 && c && T > 0, "bad gemm args");
-    const int64_t N = w->rows, K = w->cols;
-    GGB_CHECK_ARG(K % 64 == 0 && N % 32 == 0 && ldc >= N && ldc % 4 == 0, "gemm needs K %% 64 == 0, N %% 32 == 0 (N=%lld K=%lld)",
-                  (long long)N, (long long)K);
-    GGB_CHECK_ARG(w->type == GGB_TYPE_Q4_0 || w->type == GGB_TYPE_Q8_0, "gemm: weight type %d", w->type);
+    GGB_CHECK_ARG(n >= 1 && n <= kMaxSegs && w && a_bf16 && c && ldc && T > 0, "bad gemm args");
+    GGB_CHECK_ARG(n == 1 || !resid, "gemm: a residual needs a single matrix");
+    const int64_t K = w[0]->cols;
+    const int type = w[0]->type;
+    GGB_CHECK_ARG(type == GGB_TYPE_Q4_0 || type == GGB_TYPE_Q8_0, "gemm: weight type %d", type);
+    GemmArgs A{};
+    int64_t N = 0;
+    for (int i = 0; i < n; i++) {
+        GGB_CHECK_ARG(w[i] && c[i] && w[i]->cols == K && w[i]->type == type, "gemm: matrices of one launch share K and the type");
+        const int64_t rows = w[i]->rows;
+        GGB_CHECK_ARG(K % 64 == 0 && rows % 32 == 0 && ldc[i] >= rows && ldc[i] % 4 == 0,
+                      "gemm needs K %% 64 == 0, N %% 32 == 0 (N=%lld K=%lld)", (long long)rows, (long long)K);
+        A.seg[i] = GemmSeg{w[i]->qs, w[i]->d, c[i], (int)ldc[i], (int)N, (int)rows};
+        N += i + 1 < n ? (rows + BN - 1) / BN * BN : rows; // the next matrix starts on a tile boundary
+    }
+    A.n_seg = n;
     static bool attr_done = false;
     if (!attr_done) {
         GGB_CUDA(cudaFuncSetAttribute(gemm_bf16w_kernel<GGB_TYPE_Q4_0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
@@ -502,22 +533,37 @@ int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *
     const int sms = ggb_sm_count();
     while (splits < 8 && n_tiles * m_tiles * splits * 2 <= sms && kblocks / (splits * 2) >= 4) splits *= 2;
     if (splits > 1 && (!workspace || workspace_bytes < (size_t)splits * T * N * 4)) splits = 1;
-    GemmArgs A{};
-    A.qs = w->qs; A.d = w->d; A.N = (int)N; A.K = (int)K; A.nb = (int)w->nb;
+    A.N = (int)N; A.K = (int)K; A.nb = (int)w[0]->nb;
     A.a = (const __nv_bfloat16 *)a_bf16; A.T = (int)T;
     A.kblocks_per_split = (kblocks + splits - 1) / splits;
-    if (splits == 1) { A.c = c; A.ldc = (int)ldc; A.resid = resid; }
-    else { A.c = (float *)workspace; A.ldc = (int)N; A.resid = nullptr; }
+    A.ws = splits > 1 ? (float *)workspace : nullptr;
+    A.resid = resid;
     const dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)splits);
-    if (w->type == GGB_TYPE_Q4_0) gemm_bf16w_kernel<GGB_TYPE_Q4_0><<<grid, kGemmThreads, kGemmSmem, ggb_cuda_stream()>>>(A);
+    if (splits > 1) A.resid = nullptr; // added by the reducer
+    if (type == GGB_TYPE_Q4_0) gemm_bf16w_kernel<GGB_TYPE_Q4_0><<<grid, kGemmThreads, kGemmSmem, ggb_cuda_stream()>>>(A);
     else gemm_bf16w_kernel<GGB_TYPE_Q8_0><<<grid, kGemmThreads, kGemmSmem, ggb_cuda_stream()>>>(A);
     GGB_LAUNCH_CHECK();
     if (splits > 1) {
-        const int64_t n = T * N;
-        splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>((const float *)workspace, splits, T, N, c, ldc, resid);
+        A.resid = resid;
+        const int64_t cnt = T * N;
+        splitk_reduce_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ggb_cuda_stream()>>>(A, splits);
         GGB_LAUNCH_CHECK();
     }
     return GGB_OK;
+}
+
+int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *c, int64_t ldc, const float *resid,
+                     void *workspace, size_t workspace_bytes) {
+    const ggb_weight *ws[1] = {w};
+    float *cs[1] = {c};
+    const int64_t ls[1] = {ldc};
+    GGB_CHECK_ARG(w != nullptr, "bad gemm args");
+    return gemm_launch(1, ws, a_bf16, T, cs, ls, resid, workspace, workspace_bytes);
+}
+
+int ggb_op_gemm_bf16_multi(int n, const ggb_weight *const *w, const void *a_bf16, int64_t T, float *const *c, const int64_t *ldc,
+                           void *workspace, size_t workspace_bytes) {
+    return gemm_launch(n, w, a_bf16, T, c, ldc, nullptr, workspace, workspace_bytes);
 }
 
 int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, int64_t T, int pos0, int H, int Hkv, int d,

@@ -523,8 +523,11 @@ int gemma_model::alloc_prefill(int T) {
     GM_TRY(ggb_buffer_alloc(t * F * 4, (void **)&pf_u_));
     GM_TRY(ggb_buffer_alloc(t * V * 4, (void **)&pf_logits_));
     GM_TRY(ggb_buffer_alloc(t * widest * 2, &pf_a_));
-    // the K-split is only taken for small N (o-proj, down-proj, q/k/v): N <= max(E, QD)
-    pf_ws_bytes_ = ggb_gemm_workspace_bytes((int64_t)t, (int64_t)(E > QD ? E : QD), 0);
+    // the K-split is only taken for small N (o-proj, down-proj, the fused q | k | v launch)
+    const size_t KDp = (size_t)cfg_.n_head_kv * cfg_.head_dim;
+    const size_t qkv_n = (QD + 255) / 256 * 256 + (KDp + 255) / 256 * 256 + KDp;
+    pf_ws_n_ = (int64_t)std::max(std::max(E, QD), qkv_n);
+    pf_ws_bytes_ = ggb_gemm_workspace_bytes((int64_t)t, pf_ws_n_, 0);
     GM_TRY(ggb_buffer_alloc(pf_ws_bytes_, &pf_ws_));
     pf_T_ = T;
     return 0;
@@ -544,8 +547,19 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
     auto gemm = [&](const ggb_weight *w, int64_t K, float *out, const float *resid) -> int {
         pf_flops_ += 2.0 * (double)t * (double)K * (double)ggb_weight_rows(w);
         const int64_t N = ggb_weight_rows(w);
-        const bool small = N <= (E > QD ? E : QD);
+        const bool small = N <= pf_ws_n_;
         return ggb_op_gemm_bf16(w, pf_a_, t, out, N, resid, small ? pf_ws_ : nullptr, small ? pf_ws_bytes_ : 0);
+    };
+    // matrices that share the A operand go out as ONE launch (more tiles per launch, one pass over A)
+    auto gemm_multi = [&](int n, const ggb_weight *const *w, int64_t K, float *const *outs) -> int {
+        int64_t ld[3], total = 0;
+        for (int i = 0; i < n; i++) {
+            ld[i] = ggb_weight_rows(w[i]);
+            pf_flops_ += 2.0 * (double)t * (double)K * (double)ld[i];
+            total += i + 1 < n ? (ld[i] + 255) / 256 * 256 : ld[i];
+        }
+        const bool small = total <= pf_ws_n_;
+        return ggb_op_gemm_bf16_multi(n, w, pf_a_, t, outs, ld, small ? pf_ws_ : nullptr, small ? pf_ws_bytes_ : 0);
     };
     pf_flops_ = 0.0;
     PROFILE("op_get_rows", ggb_op_get_rows(token_embd_, pf_ids_, t, sqrtf((float)c.n_embd), pf_x_));   // :675-679
@@ -553,9 +567,11 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
         const gemma_layer &l = layers_[(size_t)il];
         void *kc = k_cache_[(size_t)il], *vc = v_cache_[(size_t)il];
         PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_x_, l.attn_norm, c.eps, E, t, pf_a_));           // :690
-        PROFILE("op_mul_mat", gemm(l.attn_q, E, pf_q_, nullptr));                                        // :692-696
-        PROFILE("op_mul_mat", gemm(l.attn_k, E, pf_k_, nullptr));
-        PROFILE("op_mul_mat", gemm(l.attn_v, E, pf_v_, nullptr));
+        {
+            const ggb_weight *w3[3] = {l.attn_q, l.attn_k, l.attn_v};
+            float *o3[3] = {pf_q_, pf_k_, pf_v_};
+            PROFILE("op_mul_mat", gemm_multi(3, w3, E, o3));                                             // :692-696
+        }
         PROFILE("op_rope", ggb_op_rope_neox(pf_q_, pf_pos_, c.head_dim, c.n_head, t, pf_q_));            // :698-716
         PROFILE("op_rope", ggb_op_scale(pf_q_, q_scale, t * QD, pf_q_));                                 // :708
         PROFILE("op_rope", ggb_op_rope_neox(pf_k_, pf_pos_, c.head_dim, c.n_head_kv, t, pf_k_));
@@ -566,8 +582,11 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
         PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_attn_, t * QD, pf_a_));
         PROFILE("op_mul_mat", gemm(l.attn_output, QD, pf_sa_, pf_x_));                                   // :493 + :723
         PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_sa_, l.ffn_norm, c.eps, E, t, pf_a_));            // :727
-        PROFILE("op_mul_mat", gemm(l.ffn_gate, E, pf_g_, nullptr));                                      // :446-447
-        PROFILE("op_mul_mat", gemm(l.ffn_up, E, pf_u_, nullptr));
+        {
+            const ggb_weight *w2[2] = {l.ffn_gate, l.ffn_up};
+            float *o2[2] = {pf_g_, pf_u_};
+            PROFILE("op_mul_mat", gemm_multi(2, w2, E, o2));                                             // :446-447
+        }
         PROFILE("op_gelu", ggb_op_geglu_bf16(pf_g_, pf_u_, t * F, pf_a_));                               // :448-449
         PROFILE("op_mul_mat", gemm(l.ffn_down, F, pf_x_, pf_sa_));                                       // :450 + :731
     }

@@ -151,4 +151,5 @@ class gemma_model {
     float *pf_sa_ = nullptr, *pf_g_ = nullptr, *pf_u_ = nullptr, *pf_logits_ = nullptr;
     void *pf_a_ = nullptr, *pf_ws_ = nullptr; // bf16 A operand, K-split workspace
     size_t pf_ws_bytes_ = 0;
+    int64_t pf_ws_n_ = 0; // widest N the K-split workspace covers
 };

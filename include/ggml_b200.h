@@ -193,6 +193,11 @@ int ggb_op_sample_from_candidates(const void *cands, int n_cands, int32_t *state
 size_t ggb_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K);
 int ggb_op_gemm_bf16(const ggb_weight *w, const void *a_bf16, int64_t T, float *c, int64_t ldc, const float *resid,
                      void *workspace, size_t workspace_bytes);
+/* the same for up to 3 matrices that share the A operand (Q | K | V of src/gemma_model.cpp:692-696, gate | up of
+ * :446-447) in ONE launch: c[i] / ldc[i] are the outputs of w[i].  workspace: ggb_gemm_workspace_bytes(T, sum of the
+ * row counts rounded up to 256 each, K). */
+int ggb_op_gemm_bf16_multi(int n, const ggb_weight *const *w, const void *a_bf16, int64_t T, float *const *c,
+                           const int64_t *ldc, void *workspace, size_t workspace_bytes);
 int ggb_op_cvt_f32_bf16(const float *x, int64_t n, void *y_bf16);
 /* fused producers of the GEMM's bf16 A operand: rms_norm(x) * w, and gelu(gate) * up (graph_build_norm /
  * graph_build_ffn, src/gemma_model.cpp:438-452) */

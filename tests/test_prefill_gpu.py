@@ -49,6 +49,47 @@ def test_gemm_bf16_matches_dequantised_model(gpu, wtype, T, N, K):
     assert np.all(np.abs(got2 - (ref - resid)) <= 1e-5 * scale + 1e-6)
 
 
+@pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
+@pytest.mark.parametrize("T,rows,K", [(512, (2048, 256, 256), 2048), (70, (64, 32, 96), 256), (300, (1024, 1024), 512)])
+def test_gemm_multi_equals_separate_launches(gpu, wtype, T, rows, K):
+    """Q | K | V (gate | up) in one launch: bit-identical to one launch per matrix (same tiles, same K-split rule
+    is NOT guaranteed - more tiles per launch can mean fewer splits - so the comparison is against the same model,
+    and bitwise against the single launches whenever neither form splits K)."""
+    import ctypes as C
+    rng = np.random.default_rng(T + K + sum(rows))
+    L = gpu.cuda_lib()
+    a_bf, a_bits = to_bf16(rng.standard_normal((T, K)).astype(np.float32))
+    A = gpu.DeviceBuffer.from_numpy(a_bits)
+    ws, outs, refs, scales = [], [], [], []
+    for n in rows:
+        wq = O.quantize(wtype, rng.standard_normal((n, K)).astype(np.float32) * 0.02)
+        ws.append(gpu.Weight.upload(wtype, wq, K))
+        w_bf, _ = to_bf16(O.dequantize(wtype, wq, K))
+        refs.append(a_bf.astype(np.float64) @ w_bf.astype(np.float64).T)
+        scales.append(np.abs(a_bf).astype(np.float64) @ np.abs(w_bf).astype(np.float64).T)
+        outs.append(gpu.DeviceBuffer(4 * T * n))
+    n_total = sum((n + 255) // 256 * 256 for n in rows)
+    ws_bytes = L.ggb_gemm_workspace_bytes(T, n_total, K)
+    WS = gpu.DeviceBuffer(ws_bytes)
+    wp = (C.c_void_p * len(rows))(*[w.h for w in ws])
+    cp = (C.c_void_p * len(rows))(*[o.ptr for o in outs])
+    ld = (C.c_int64 * len(rows))(*rows)
+    for use_ws in (True, False):
+        gpu.check(L.ggb_op_gemm_bf16_multi(len(rows), wp, A.ptr, T, cp, ld, WS.ptr if use_ws else None, ws_bytes if use_ws else 0))
+        gpu.sync()
+        for i, n in enumerate(rows):
+            got = outs[i].download(np.float32).reshape(T, n)
+            assert np.all(np.abs(got - refs[i]) <= 1e-5 * scales[i] + 1e-6), (use_ws, i)
+    # without a workspace nothing splits K: bitwise equal to the single launches
+    single = gpu.DeviceBuffer(4 * T * max(rows))
+    for i, n in enumerate(rows):
+        gpu.check(L.ggb_op_gemm_bf16(ws[i].h, A.ptr, T, single.ptr, n, None, None, 0))
+        gpu.sync()
+        a = single.download(np.float32)[:T * n]
+        b = outs[i].download(np.float32)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), i
+
+
 SMALL = {
     "mqa": dict(n_embd=256, n_layer=3, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=2048, n_ctx=160),
     "mha": dict(n_embd=512, n_layer=2, n_head=4, n_head_kv=4, head_dim=128, n_ff=4608, n_vocab=1024, n_ctx=96),
