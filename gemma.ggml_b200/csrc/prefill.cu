@@ -399,73 +399,126 @@ __global__ void cvt_f32_bf16_kernel(const float *x, int64_t n, __nv_bfloat16 *y)
 }
 
 // Causal attention of T query tokens at positions pos0 .. pos0+T-1 over the fp16 KV cache (position-major
-// [n_ctx][Hkv*d]).  One warp per (token, head), the reference's node order (ref: src/gemma_model.cpp:454-489):
-// kq = K . f16(q) (fp32 accumulate), soft_max_ext with the fp16 exp table and a double sum, P rounded to fp16,
-// kqv = V^T . P.  q is already roped and scaled.  CUDA cores: 4 % of the prefill flops.
+// [n_ctx][Hkv*d]).  One warp per (token, GH query heads that share a KV head), the reference's node order
+// (ref: src/gemma_model.cpp:454-489): kq = K . f16(q) (fp32 accumulate), soft_max_ext with the fp16 exp table and
+// a double sum, P rounded to fp16, kqv = V^T . P.  q is already roped and scaled.  A K / V row is loaded once for
+// the GH heads, and the 8 lane partials of a step (8 / GH positions x GH heads) are reduced with ONE folded
+// butterfly (9 shuffles instead of 40; the same additions as the plain xor-butterfly).  CUDA cores.
 constexpr int kAttnWarps = 4;
+template <int GH>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_prefill_kernel(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, int T,
                     int pos0, int H, int Hkv, int d, const uint16_t *__restrict__ exp_table, float *__restrict__ out,
                     int n_kv_max) {
-    extern __shared__ float attn_s[]; // [kAttnWarps][n_kv_max]
+    constexpr int NP = 8 / GH; // positions per step
+    extern __shared__ float attn_s[]; // [kAttnWarps][GH][n_kv_max]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HG = H / GH; // head groups per token
     const int item = blockIdx.x * kAttnWarps + warp;
-    if (item >= T * H) return;
-    const int t = item / H, h = item % H, g = h / (H / Hkv);
+    if (item >= T * HG) return;
+    const int t = item / HG, h0 = (item % HG) * GH, g = h0 / (H / Hkv);
     const int n_kv = pos0 + t + 1;
-    float *s = attn_s + (size_t)warp * n_kv_max;
+    float *s = attn_s + (size_t)warp * GH * n_kv_max;
     const size_t stride = (size_t)Hkv * d;
     const bool in = 8 * lane < d;
-    float qf[8];
+    float qf[GH][8];
 #pragma unroll
-    for (int e = 0; e < 8; e++) qf[e] = in ? __half2float(__float2half_rn(q[((size_t)t * H + h) * d + 8 * lane + e])) : 0.f;
-    float mx = -INFINITY;
-    for (int j = 0; j < n_kv; j++) {
-        float acc = 0.f;
-        if (in) {
-            const uint4 raw = *reinterpret_cast<const uint4 *>(kc + (size_t)j * stride + (size_t)g * d + 8 * lane);
+    for (int u = 0; u < GH; u++)
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            qf[u][e] = in ? __half2float(__float2half_rn(q[((size_t)t * H + h0 + u) * d + 8 * lane + e])) : 0.f;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    // after the fold a lane holds value index 4 b4 + 2 b3 + b2 of the step: value = position * GH + head
+    const int vi = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+    const int my_p = vi / GH, my_u = vi % GH;
+    float mx = -INFINITY; // of head my_u over the positions this lane sees
+    for (int j0 = 0; j0 < n_kv; j0 += NP) {
+        float v[8];
+#pragma unroll
+        for (int p = 0; p < NP; p++) {
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (in && j0 + p < n_kv) raw = *reinterpret_cast<const uint4 *>(kc + (size_t)(j0 + p) * stride + (size_t)g * d + 8 * lane);
             const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+            float kf[8];
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const float2 f = __half22float2(h2[e]);
-                acc = fmaf(f.x, qf[2 * e], acc);
-                acc = fmaf(f.y, qf[2 * e + 1], acc);
+                kf[2 * e] = f.x;
+                kf[2 * e + 1] = f.y;
+            }
+#pragma unroll
+            for (int u = 0; u < GH; u++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc = fmaf(kf[e], qf[u][e], acc);
+                v[p * GH + u] = acc;
             }
         }
-        acc = warp_sum_f32(acc);
-        if (lane == 0) s[j] = acc;
-        mx = fmaxf(mx, acc);
-    }
-    __syncwarp();
-    double sum = 0.0;
-    for (int j = lane; j < n_kv; j += 32) {
-        const float e = half_bits_to_float(exp_table[float_to_half_bits(s[j] - mx)]);
-        s[j] = e;
-        sum += (double)e;
-    }
-    sum = warp_sum_f64(sum);
-    const float inv = (float)(1.0 / sum);
-    __syncwarp();
-    float o[8];
+        float k4[4], k2[2];
 #pragma unroll
-    for (int e = 0; e < 8; e++) o[e] = 0.f;
-    for (int j = 0; j < n_kv; j++) {
-        const float p = __half2float(__float2half_rn(s[j] * inv)); // ggml converts P to fp16 for the V mat-mul
+        for (int i = 0; i < 4; i++) k4[i] = (b4 ? v[4 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[4 + i], 16);
+#pragma unroll
+        for (int i = 0; i < 2; i++) k2[i] = (b3 ? k4[2 + i] : k4[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k4[i] : k4[2 + i], 8);
+        float k1 = (b2 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? k2[0] : k2[1], 4);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+        if (j0 + my_p < n_kv) {
+            if ((lane & 3) == 0) s[(size_t)my_u * n_kv_max + j0 + my_p] = k1;
+            mx = fmaxf(mx, k1);
+        }
+    }
+    // the maximum of every head: lanes with the same head index hold its positions' maxima
+    float mxu[GH];
+#pragma unroll
+    for (int u = 0; u < GH; u++) mxu[u] = warp_max_f32(my_u == u ? mx : -INFINITY);
+    __syncwarp();
+    float inv[GH];
+#pragma unroll
+    for (int u = 0; u < GH; u++) {
+        float *su = s + (size_t)u * n_kv_max;
+        double sum = 0.0;
+        for (int j = lane; j < n_kv; j += 32) {
+            const float e = half_bits_to_float(exp_table[float_to_half_bits(su[j] - mxu[u])]);
+            su[j] = e;
+            sum += (double)e;
+        }
+        sum = warp_sum_f64(sum);
+        inv[u] = (float)(1.0 / sum);
+    }
+    __syncwarp();
+    float o[GH][8];
+#pragma unroll
+    for (int u = 0; u < GH; u++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[u][e] = 0.f;
+    for (int j = 0; j < n_kv; j++) { // (unrolling this loop by 8 measured slower: 3.1 vs 2.5 ms per prefill)
+        float vf[8];
         if (in) {
             const uint4 raw = *reinterpret_cast<const uint4 *>(vc + (size_t)j * stride + (size_t)g * d + 8 * lane);
             const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const float2 f = __half22float2(h2[e]);
-                o[2 * e] = fmaf(f.x, p, o[2 * e]);
-                o[2 * e + 1] = fmaf(f.y, p, o[2 * e + 1]);
+                vf[2 * e] = f.x;
+                vf[2 * e + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < GH; u++) {
+            const float p = __half2float(__float2half_rn(s[(size_t)u * n_kv_max + j] * inv[u])); // ggml converts P to fp16 for the V mat-mul
+            if (in) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) o[u][e] = fmaf(vf[e], p, o[u][e]);
             }
         }
     }
     if (in) {
-        float *dst = out + ((size_t)t * H + h) * d + 8 * lane;
 #pragma unroll
-        for (int e = 0; e < 8; e++) dst[e] = o[e];
+        for (int u = 0; u < GH; u++) {
+            float *dst = out + ((size_t)t * H + h0 + u) * d + 8 * lane;
+#pragma unroll
+            for (int e = 0; e < 8; e++) dst[e] = o[u][e];
+        }
     }
 }
 
@@ -571,13 +624,21 @@ int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, 
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(q && kcache && vcache && out && T > 0 && d % 8 == 0 && d <= 256 && H % Hkv == 0, "bad attn_prefill args");
     const int n_kv_max = pos0 + (int)T;
-    const size_t smem = (size_t)kAttnWarps * n_kv_max * 4;
+    // query heads per warp: sharing the K/V loads between 4 heads (gh = 4) measured SLOWER for Gemma-2B at T = 512 (3.9 vs
+    // 3.3 ms per prefill: a quarter of the warps, each with 4x the serial work), so one head per warp it is
+    const int gh = getenv("GGB_PREFILL_ATTN_GH4") && (H / Hkv) % 4 == 0 ? 4 : 1;
+    const size_t smem = (size_t)kAttnWarps * gh * n_kv_max * 4;
     GGB_CHECK_ARG(smem <= 200 * 1024, "attn_prefill: context %d too long for the score buffer", n_kv_max);
-    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned blocks = (unsigned)((T * H + kAttnWarps - 1) / kAttnWarps);
-    attn_prefill_kernel<<<blocks, kAttnWarps * 32, smem, ggb_cuda_stream()>>>(q, (const __half *)kcache, (const __half *)vcache,
-                                                                             (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out,
-                                                                             n_kv_max);
+    const unsigned blocks = (unsigned)((T * (H / gh) + kAttnWarps - 1) / kAttnWarps);
+    if (gh == 4) {
+        if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_prefill_kernel<4><<<blocks, kAttnWarps * 32, smem, ggb_cuda_stream()>>>(q, (const __half *)kcache, (const __half *)vcache,
+                                                                                    (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out, n_kv_max);
+    } else {
+        if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attn_prefill_kernel<1><<<blocks, kAttnWarps * 32, smem, ggb_cuda_stream()>>>(q, (const __half *)kcache, (const __half *)vcache,
+                                                                                    (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out, n_kv_max);
+    }
     GGB_LAUNCH_CHECK();
     return GGB_OK;
 }
