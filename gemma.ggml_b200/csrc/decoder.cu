@@ -241,11 +241,8 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) { // unsigned b
     return d;
 }
 
-// fp16 table lookup (exp / gelu).  The tables are pinned in L2 by the launch's access-policy window: under the
-// weight stream a demand miss to HBM costs ~1 us of queueing, and these lookups sit on every layer's critical path
-__device__ __forceinline__ float table_f16(const uint16_t *table, float x) {
-    return half_bits_to_float(__ldg(table + float_to_half_bits(x)));
-}
+// (the fp16 exp / gelu tables are pinned in L2 by the launch's access-policy window: under the weight stream a demand
+// miss to HBM costs ~1 us of queueing, and the lookups sit on every layer's critical path)
 
 // exp with the reference's fp16-table semantics, table[h] = fp16(expf(fp32(h))), COMPUTED: exp() in double, rounded
 // to fp32, then to fp16.  ggb_decoder_create checks this against the uploaded table for every non-NaN fp16 input
