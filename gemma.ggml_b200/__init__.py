@@ -98,6 +98,7 @@ _CUDA_SIG = {
     "ggb_op_cpy_f32_f16": (i32, [vp, i64, vp]),
     "ggb_rope_table_init": (i32, [i32, i32, f32]),
     "ggb_op_rope_kv_store": (i32, [vp, vp, vp, vp, i32, i32, i32, f32, vp, vp]),
+    "ggb_op_rope_kv_store_batch": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, f32, vp, vp]),
     "ggb_attn_scratch_bytes": (sz, [i32, i32, i32]),
     "ggb_op_attn_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "ggb_op_embed_token": (i32, [vp, vp, f32, vp]),

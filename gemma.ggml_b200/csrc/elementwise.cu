@@ -205,6 +205,42 @@ __global__ void rope_kv_store_kernel(float *__restrict__ q, const float *__restr
     }
 }
 
+// the same for T tokens (prefill): token t = blockIdx.y, its position pos[t]; q / k / v are [T][H*d] / [T][Hkv*d]
+__global__ void rope_kv_store_batch_kernel(float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
+                                           const int32_t *__restrict__ pos_p, int H, int Hkv, int d, float q_scale,
+                                           const float *__restrict__ cosT, const float *__restrict__ sinT, int table_ctx,
+                                           __half *__restrict__ kcache, __half *__restrict__ vcache) {
+    const int half = d / 2;
+    const int64_t t = blockIdx.y;
+    int pos = pos_p[t];
+    pos = pos < 0 ? 0 : (pos >= table_ctx ? table_ctx - 1 : pos);
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nq = H * half, nk = Hkv * half, nv = Hkv * d;
+    float *qt = q + t * (int64_t)H * d;
+    const float *kt = k + t * (int64_t)Hkv * d, *vt = v + t * (int64_t)Hkv * d;
+    if (idx < nq + nk) {
+        const bool is_q = idx < nq;
+        const int j = is_q ? idx : idx - nq;
+        const int h = j / half, i = j % half;
+        const float c = cosT[(int64_t)pos * half + i], s = sinT[(int64_t)pos * half + i];
+        const float *src = is_q ? qt : kt;
+        const float x0 = src[h * d + i], x1 = src[h * d + i + half];
+        const float r0 = __fsub_rn(__fmul_rn(x0, c), __fmul_rn(x1, s));
+        const float r1 = __fadd_rn(__fmul_rn(x0, s), __fmul_rn(x1, c));
+        if (is_q) {
+            qt[h * d + i] = __fmul_rn(r0, q_scale);
+            qt[h * d + i + half] = __fmul_rn(r1, q_scale);
+        } else {
+            __half *row = kcache + (int64_t)pos * Hkv * d;
+            row[h * d + i] = __float2half_rn(r0);
+            row[h * d + i + half] = __float2half_rn(r1);
+        }
+    } else if (idx < nq + nk + nv) {
+        const int j = idx - nq - nk;
+        vcache[(int64_t)pos * Hkv * d + j] = __float2half_rn(vt[j]);
+    }
+}
+
 // ---------------------------------------------------------------- K8 get_rows + scale
 // [UPSTREAM] dequantize_row_q4_0 / q8_0 of the selected row, then ggml_scale (ref: :675-679).
 __global__ void get_rows_kernel(const uint8_t *__restrict__ qs, const __half *__restrict__ d, int type, int64_t nb,
@@ -403,6 +439,20 @@ int ggb_op_rope_kv_store(float *q, const float *k, const float *v, const int32_t
     const int total = (H + Hkv) * (d / 2) + Hkv * d;
     rope_kv_store_kernel<<<blocks_for(total), 256, 0, ggb_cuda_stream()>>>(
         q, k, v, pos, H, Hkv, d, q_scale, ggb_rope_cos_dev(), ggb_rope_sin_dev(), (__half *)kcache, (__half *)vcache);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_rope_kv_store_batch(float *q, const float *k, const float *v, const int32_t *pos, int64_t T, int H, int Hkv, int d,
+                               float q_scale, void *kcache, void *vcache) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(q && k && v && pos && kcache && vcache && T > 0 && T <= 65535, "bad rope_kv_store_batch args");
+    GGB_CHECK_ARG(ggb_rope_cos_dev() && ggb_rope_n_dims() == d, "rope table not initialised for head_dim %d", d);
+    const int total = (H + Hkv) * (d / 2) + Hkv * d;
+    const dim3 grid((unsigned)((total + 255) / 256), (unsigned)T);
+    rope_kv_store_batch_kernel<<<grid, 256, 0, ggb_cuda_stream()>>>(q, k, v, pos, H, Hkv, d, q_scale, ggb_rope_cos_dev(),
+                                                                     ggb_rope_sin_dev(), ggb_rope_n_ctx(), (__half *)kcache,
+                                                                     (__half *)vcache);
     GGB_LAUNCH_CHECK();
     return GGB_OK;
 }

@@ -389,8 +389,21 @@ rms_norm_bf16_kernel(const float *__restrict__ x, const float *__restrict__ w, f
 // gelu(gate) * up -> bf16 (fp16 gelu table like the reference's ggml_gelu; ref: src/gemma_model.cpp:448-449)
 __global__ void geglu_bf16_kernel(const float *gate, const float *up, int64_t n, const uint16_t *__restrict__ table,
                                   __nv_bfloat16 *y) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = __float2bfloat16_rn(__fmul_rn(half_bits_to_float(table[float_to_half_bits(gate[i])]), up[i]));
+    // four elements per thread: 128-bit loads of gate / up, four table lookups in flight, one 64-bit store
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        const float4 g = *reinterpret_cast<const float4 *>(gate + i), u = *reinterpret_cast<const float4 *>(up + i);
+        const uint16_t t0 = table[float_to_half_bits(g.x)], t1 = table[float_to_half_bits(g.y)];
+        const uint16_t t2 = table[float_to_half_bits(g.z)], t3 = table[float_to_half_bits(g.w)];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(__fmul_rn(half_bits_to_float(t0), u.x), __fmul_rn(half_bits_to_float(t1), u.y));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(__fmul_rn(half_bits_to_float(t2), u.z), __fmul_rn(half_bits_to_float(t3), u.w));
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t *>(&lo);
+        o.y = *reinterpret_cast<uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(y + i) = o;
+    } else {
+        for (int64_t j = i; j < n; j++) y[j] = __float2bfloat16_rn(__fmul_rn(half_bits_to_float(table[float_to_half_bits(gate[j])]), up[j]));
+    }
 }
 
 __global__ void cvt_f32_bf16_kernel(const float *x, int64_t n, __nv_bfloat16 *y) {
@@ -550,7 +563,7 @@ int ggb_op_rms_norm_bf16(const float *x, const float *w, float eps, int64_t E, i
 int ggb_op_geglu_bf16(const float *gate, const float *up, int64_t n, void *y_bf16) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(gate && up && y_bf16 && n > 0, "bad geglu_bf16 args");
-    geglu_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>(gate, up, n, ggb_gelu_table_dev(), (__nv_bfloat16 *)y_bf16);
+    geglu_bf16_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, ggb_cuda_stream()>>>(gate, up, n, ggb_gelu_table_dev(), (__nv_bfloat16 *)y_bf16);
     GGB_LAUNCH_CHECK();
     return GGB_OK;
 }

@@ -572,12 +572,10 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
             float *o3[3] = {pf_q_, pf_k_, pf_v_};
             PROFILE("op_mul_mat", gemm_multi(3, w3, E, o3));                                             // :692-696
         }
-        PROFILE("op_rope", ggb_op_rope_neox(pf_q_, pf_pos_, c.head_dim, c.n_head, t, pf_q_));            // :698-716
-        PROFILE("op_rope", ggb_op_scale(pf_q_, q_scale, t * QD, pf_q_));                                 // :708
-        PROFILE("op_rope", ggb_op_rope_neox(pf_k_, pf_pos_, c.head_dim, c.n_head_kv, t, pf_k_));
-        // KV store (ref :499-518): rows pos0 .. pos0+T-1 of the position-major fp16 cache are contiguous
-        PROFILE("op_cpy", ggb_op_cpy_f32_f16(pf_k_, t * KD, (char *)kc + (size_t)pos0 * (size_t)KD * 2));
-        PROFILE("op_cpy", ggb_op_cpy_f32_f16(pf_v_, t * KD, (char *)vc + (size_t)pos0 * (size_t)KD * 2));
+        // rope(q) * q_scale in place, rope(k) and v straight into the position-major fp16 cache rows pos0 .. pos0+T-1
+        // (ref :698-716 rope + scale, :499-518 KV store): one launch
+        PROFILE("op_rope", ggb_op_rope_kv_store_batch(pf_q_, pf_k_, pf_v_, pf_pos_, t, c.n_head, c.n_head_kv, c.head_dim,
+                                                       q_scale, kc, vc));
         PROFILE("op_attn", ggb_op_attn_prefill(pf_q_, kc, vc, t, pos0, c.n_head, c.n_head_kv, c.head_dim, pf_attn_)); // :454-489
         PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_attn_, t * QD, pf_a_));
         PROFILE("op_mul_mat", gemm(l.attn_output, QD, pf_sa_, pf_x_));                                   // :493 + :723

@@ -167,6 +167,10 @@ int ggb_rope_table_init(int n_ctx, int n_dims, float freq_base);
  * caches are position-major fp16 [n_ctx][Hkv*d]; *pos is a device int32 */
 int ggb_op_rope_kv_store(float *q, const float *k, const float *v, const int32_t *pos, int H, int Hkv, int d,
                          float q_scale, void *kcache, void *vcache);
+/* the same for T tokens (prefill): q [T][H*d], k / v [T][Hkv*d], pos[T] (device int32); one launch instead of
+ * rope(q), scale(q), rope(k) and the two F32->F16 copies */
+int ggb_op_rope_kv_store_batch(float *q, const float *k, const float *v, const int32_t *pos, int64_t T, int H, int Hkv,
+                               int d, float q_scale, void *kcache, void *vcache);
 /* K4 — split-K decode attention over positions [0, *pos]; scratch from ggb_attn_scratch_bytes.
  * out f32 [H*d] and/or q8 (planar, cols = H*d) */
 size_t ggb_attn_scratch_bytes(int H, int d, int n_ctx);
