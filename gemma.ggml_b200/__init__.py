@@ -108,7 +108,7 @@ _CUDA_SIG = {
     "ggb_op_gemm_bf16_multi": (i32, [i32, vp, vp, i64, vp, vp, vp, sz]),
     "ggb_op_cvt_f32_bf16": (i32, [vp, i64, vp]),
     "ggb_op_rms_norm_bf16": (i32, [vp, vp, f32, i64, i64, vp]), "ggb_op_geglu_bf16": (i32, [vp, vp, i64, vp]),
-    "ggb_op_attn_prefill": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "ggb_op_attn_prefill": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]),
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]),
     "ggb_decoder_create_tp": (i32, [vp, vp, vp, vp, vp, i32, i32, P(vp)]), "ggb_decoder_step": (i32, [vp]),
     "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),

@@ -422,7 +422,7 @@ template <int GH>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_prefill_kernel(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, int T,
                     int pos0, int H, int Hkv, int d, const uint16_t *__restrict__ exp_table, float *__restrict__ out,
-                    int n_kv_max) {
+                    __nv_bfloat16 *__restrict__ out_bf16, int n_kv_max) {
     constexpr int NP = 8 / GH; // positions per step
     extern __shared__ float attn_s[]; // [kAttnWarps][GH][n_kv_max]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -528,9 +528,19 @@ attn_prefill_kernel(const float *__restrict__ q, const __half *__restrict__ kc, 
     if (in) {
 #pragma unroll
         for (int u = 0; u < GH; u++) {
-            float *dst = out + ((size_t)t * H + h0 + u) * d + 8 * lane;
+            const size_t at = ((size_t)t * H + h0 + u) * d + 8 * lane;
+            if (out) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) dst[e] = o[u][e];
+                for (int e = 0; e < 8; e++) out[at + e] = o[u][e];
+            }
+            if (out_bf16) { // the o-projection's A operand, rounded exactly as ggb_op_cvt_f32_bf16 would
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(o[u][0], o[u][1]), p1 = __floats2bfloat162_rn(o[u][2], o[u][3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(o[u][4], o[u][5]), p3 = __floats2bfloat162_rn(o[u][6], o[u][7]);
+                pk.x = *reinterpret_cast<uint32_t *>(&p0); pk.y = *reinterpret_cast<uint32_t *>(&p1);
+                pk.z = *reinterpret_cast<uint32_t *>(&p2); pk.w = *reinterpret_cast<uint32_t *>(&p3);
+                *reinterpret_cast<uint4 *>(out_bf16 + at) = pk;
+            }
         }
     }
 }
@@ -633,9 +643,9 @@ int ggb_op_gemm_bf16_multi(int n, const ggb_weight *const *w, const void *a_bf16
 }
 
 int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, int64_t T, int pos0, int H, int Hkv, int d,
-                        float *out) {
+                        float *out, void *out_bf16) {
     GGB_REQUIRE_INIT();
-    GGB_CHECK_ARG(q && kcache && vcache && out && T > 0 && d % 8 == 0 && d <= 256 && H % Hkv == 0, "bad attn_prefill args");
+    GGB_CHECK_ARG(q && kcache && vcache && (out || out_bf16) && T > 0 && d % 8 == 0 && d <= 256 && H % Hkv == 0, "bad attn_prefill args");
     const int n_kv_max = pos0 + (int)T;
     // query heads per warp: sharing the K/V loads between 4 heads (gh = 4) measured SLOWER for Gemma-2B at T = 512 (3.9 vs
     // 3.3 ms per prefill: a quarter of the warps, each with 4x the serial work), so one head per warp it is
@@ -646,11 +656,11 @@ int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, 
     if (gh == 4) {
         if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_prefill_kernel<4><<<blocks, kAttnWarps * 32, smem, ggb_cuda_stream()>>>(q, (const __half *)kcache, (const __half *)vcache,
-                                                                                    (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out, n_kv_max);
+                                                                                    (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out, (__nv_bfloat16 *)out_bf16, n_kv_max);
     } else {
         if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attn_prefill_kernel<1><<<blocks, kAttnWarps * 32, smem, ggb_cuda_stream()>>>(q, (const __half *)kcache, (const __half *)vcache,
-                                                                                    (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out, n_kv_max);
+                                                                                    (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out, (__nv_bfloat16 *)out_bf16, n_kv_max);
     }
     GGB_LAUNCH_CHECK();
     return GGB_OK;

@@ -576,8 +576,9 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
         // (ref :698-716 rope + scale, :499-518 KV store): one launch
         PROFILE("op_rope", ggb_op_rope_kv_store_batch(pf_q_, pf_k_, pf_v_, pf_pos_, t, c.n_head, c.n_head_kv, c.head_dim,
                                                        q_scale, kc, vc));
-        PROFILE("op_attn", ggb_op_attn_prefill(pf_q_, kc, vc, t, pos0, c.n_head, c.n_head_kv, c.head_dim, pf_attn_)); // :454-489
-        PROFILE("op_cvt", ggb_op_cvt_f32_bf16(pf_attn_, t * QD, pf_a_));
+        // kqv goes straight out as the bf16 A operand of the o-projection (the fp32 copy only for captures)
+        PROFILE("op_attn", ggb_op_attn_prefill(pf_q_, kc, vc, t, pos0, c.n_head, c.n_head_kv, c.head_dim,
+                                               capture_acts_ ? pf_attn_ : nullptr, pf_a_)); // :454-489
         PROFILE("op_mul_mat", gemm(l.attn_output, QD, pf_sa_, pf_x_));                                   // :493 + :723
         PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_sa_, l.ffn_norm, c.eps, E, t, pf_a_));            // :727
         {

@@ -209,8 +209,9 @@ int ggb_op_rms_norm_bf16(const float *x, const float *w, float eps, int64_t E, i
 int ggb_op_geglu_bf16(const float *gate, const float *up, int64_t n, void *y_bf16);
 /* causal attention of T query tokens at positions pos0..pos0+T-1 over the fp16 KV cache (q already roped and
  * scaled, fp32 [T][H*d]); reference node order kq -> soft_max_ext -> kqv (src/gemma_model.cpp:454-489) */
+/* out (fp32) and / or out_bf16 (the o-projection's A operand, same rounding as ggb_op_cvt_f32_bf16) may be NULL */
 int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, int64_t T, int pos0, int H, int Hkv, int d,
-                        float *out);
+                        float *out, void *out_bf16);
 
 /* ------------------------------------------------------------------ fused decode step
  * The whole per-token node list (ref: src/gemma_model.cpp:665-747) as ONE persistent cooperative
