@@ -547,6 +547,150 @@ attn_prefill_kernel(const float *__restrict__ q, const __half *__restrict__ kc, 
 
 } // namespace
 
+// The MQA / GQA form: ONE CTA (4 warps) per (token, 4 query heads of one KV head).  The attention above is bound by
+// L2 bandwidth (every warp re-reads the K / V rows: 1 GB per layer at T = 512); here a K / V row is loaded once for the
+// 4 heads and the positions are dealt to the 4 warps, so the traffic drops 4x at the same number of warps.  Scores:
+// 2 positions x 4 heads per folded butterfly; max / sum / P.V partials are combined across the warps in shared memory.
+__global__ void __launch_bounds__(128)
+attn_prefill_gqa_kernel(const float *__restrict__ q, const __half *__restrict__ kc, const __half *__restrict__ vc, int T,
+                        int pos0, int H, int Hkv, int d, const uint16_t *__restrict__ exp_table, float *__restrict__ out,
+                        __nv_bfloat16 *__restrict__ out_bf16, int n_kv_max) {
+    constexpr int GH = 4, NW = 4;
+    extern __shared__ float attn_s[]; // s[GH][n_kv_max] | red[NW][GH][256] | wmax[NW][GH] | wsum double[NW][GH]
+    float *s = attn_s;
+    float *red = attn_s + (size_t)GH * n_kv_max;
+    float *wmax = red + NW * GH * 256;
+    double *wsum = reinterpret_cast<double *>(wmax + NW * GH);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int HG = H / GH;
+    const int t = blockIdx.x / HG, h0 = (blockIdx.x % HG) * GH, g = h0 / (H / Hkv);
+    const int n_kv = pos0 + t + 1;
+    const size_t stride = (size_t)Hkv * d;
+    const bool in = 8 * lane < d;
+    float qf[GH][8];
+#pragma unroll
+    for (int u = 0; u < GH; u++)
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            qf[u][e] = in ? __half2float(__float2half_rn(q[((size_t)t * H + h0 + u) * d + 8 * lane + e])) : 0.f;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const int my_p = b4 ? 1 : 0, my_u = (b3 ? 2 : 0) + (b2 ? 1 : 0); // value index = position * GH + head
+    float mx = -INFINITY;
+    for (int j0 = 2 * warp; j0 < n_kv; j0 += 2 * NW) {
+        float v[8];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            uint4 raw = make_uint4(0, 0, 0, 0);
+            if (in && j0 + p < n_kv) raw = *reinterpret_cast<const uint4 *>(kc + (size_t)(j0 + p) * stride + (size_t)g * d + 8 * lane);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+            float kf[8];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __half22float2(h2[e]);
+                kf[2 * e] = f.x;
+                kf[2 * e + 1] = f.y;
+            }
+#pragma unroll
+            for (int u = 0; u < GH; u++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; e++) acc = fmaf(kf[e], qf[u][e], acc);
+                v[p * GH + u] = acc;
+            }
+        }
+        float k4[4], k2[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) k4[i] = (b4 ? v[4 + i] : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[4 + i], 16);
+#pragma unroll
+        for (int i = 0; i < 2; i++) k2[i] = (b3 ? k4[2 + i] : k4[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k4[i] : k4[2 + i], 8);
+        float k1 = (b2 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? k2[0] : k2[1], 4);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+        if (j0 + my_p < n_kv) {
+            if ((lane & 3) == 0) s[(size_t)my_u * n_kv_max + j0 + my_p] = k1;
+            mx = fmaxf(mx, k1);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < GH; u++) {
+        const float m = warp_max_f32(my_u == u ? mx : -INFINITY);
+        if (lane == 0) wmax[warp * GH + u] = m;
+    }
+    __syncthreads();
+    float inv[GH];
+#pragma unroll
+    for (int u = 0; u < GH; u++) {
+        const float m = fmaxf(fmaxf(wmax[u], wmax[GH + u]), fmaxf(wmax[2 * GH + u], wmax[3 * GH + u]));
+        float *su = s + (size_t)u * n_kv_max;
+        double sum = 0.0;
+        for (int j = tid; j < n_kv; j += 128) {
+            const float e = half_bits_to_float(exp_table[float_to_half_bits(su[j] - m)]);
+            su[j] = e;
+            sum += (double)e;
+        }
+        sum = warp_sum_f64(sum);
+        if (lane == 0) wsum[warp * GH + u] = sum;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < GH; u++) inv[u] = (float)(1.0 / (wsum[u] + wsum[GH + u] + wsum[2 * GH + u] + wsum[3 * GH + u]));
+    float o[GH][8];
+#pragma unroll
+    for (int u = 0; u < GH; u++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[u][e] = 0.f;
+    for (int j = warp; j < n_kv; j += NW) {
+        float vf[8];
+        if (in) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(vc + (size_t)j * stride + (size_t)g * d + 8 * lane);
+            const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __half22float2(h2[e]);
+                vf[2 * e] = f.x;
+                vf[2 * e + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < GH; u++) {
+            const float p = __half2float(__float2half_rn(s[(size_t)u * n_kv_max + j] * inv[u])); // P as fp16, like ggml
+            if (in) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) o[u][e] = fmaf(vf[e], p, o[u][e]);
+            }
+        }
+    }
+    if (in) {
+#pragma unroll
+        for (int u = 0; u < GH; u++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) red[(warp * GH + u) * 256 + 8 * lane + e] = o[u][e];
+    }
+    __syncthreads();
+    if (in) { // warp w finishes head h0 + w: the four warps' partial rows in warp order
+        float r[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int c = 8 * lane + e;
+            r[e] = ((red[(0 * GH + warp) * 256 + c] + red[(1 * GH + warp) * 256 + c]) + red[(2 * GH + warp) * 256 + c]) +
+                   red[(3 * GH + warp) * 256 + c];
+        }
+        const size_t at = ((size_t)t * H + h0 + warp) * d + 8 * lane;
+        if (out) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) out[at + e] = r[e];
+        }
+        if (out_bf16) {
+            uint4 pk;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(r[0], r[1]), p1 = __floats2bfloat162_rn(r[2], r[3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(r[4], r[5]), p3 = __floats2bfloat162_rn(r[6], r[7]);
+            pk.x = *reinterpret_cast<uint32_t *>(&p0); pk.y = *reinterpret_cast<uint32_t *>(&p1);
+            pk.z = *reinterpret_cast<uint32_t *>(&p2); pk.w = *reinterpret_cast<uint32_t *>(&p3);
+            *reinterpret_cast<uint4 *>(out_bf16 + at) = pk;
+        }
+    }
+}
+
 extern "C" {
 
 size_t ggb_gemm_workspace_bytes(int64_t T, int64_t N, int64_t K) {
@@ -647,6 +791,16 @@ int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, 
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(q && kcache && vcache && (out || out_bf16) && T > 0 && d % 8 == 0 && d <= 256 && H % Hkv == 0, "bad attn_prefill args");
     const int n_kv_max = pos0 + (int)T;
+    if ((H / Hkv) % 4 == 0 && !getenv("GGB_PREFILL_ATTN_SIMPLE")) { // MQA / GQA: one CTA per (token, 4 heads of one KV head)
+        const size_t smem4 = ((size_t)4 * n_kv_max + 4 * 4 * 256 + 16) * 4 + 16 * 8;
+        GGB_CHECK_ARG(smem4 <= 200 * 1024, "attn_prefill: context %d too long for the score buffer", n_kv_max);
+        if (smem4 > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(attn_prefill_gqa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        attn_prefill_gqa_kernel<<<(unsigned)(T * (H / 4)), 128, smem4, ggb_cuda_stream()>>>(
+            q, (const __half *)kcache, (const __half *)vcache, (int)T, pos0, H, Hkv, d, ggb_exp_table_dev(), out,
+            (__nv_bfloat16 *)out_bf16, n_kv_max);
+        GGB_LAUNCH_CHECK();
+        return GGB_OK;
+    }
     // query heads per warp: sharing the K/V loads between 4 heads (gh = 4) measured SLOWER for Gemma-2B at T = 512 (3.9 vs
     // 3.3 ms per prefill: a quarter of the warps, each with 4x the serial work), so one head per warp it is
     const int gh = getenv("GGB_PREFILL_ATTN_GH4") && (H / Hkv) % 4 == 0 ? 4 : 1;
