@@ -129,6 +129,9 @@ _HOST_SIG = {
     "gm_prefill": (i32, [vp, vp, i32, i32, P(i32)]), "gm_get_prefill_logits": (i32, [vp, i32, vp]),
     "gm_last_prefill_gemm_flops": (C.c_double, [vp]),
     "gm_get_logits": (i32, [vp, vp]), "gm_get_capture": (i32, [vp, C.c_char_p, i32, vp, i64]),
+    "td_set_dir": (None, [C.c_char_p]), "td_dump_ptr_data": (i32, [C.c_char_p, vp, C.c_uint64, i32]),
+    "td_dump_capture": (i32, [vp, C.c_char_p, i32, i64, i32]), "td_compare_tensors": (i32, [C.c_char_p]),
+    "td_compare_tensors_report": (i32, [C.c_char_p, P(C.c_double)]),
     "gm_get_kv": (i32, [vp, i32, vp, vp]), "gm_kernels_per_step": (i32, [vp]), "gm_weight_bytes": (u64, [vp]),
     "mul_mat": (None, [i64, i64, i64, i64, i64, i64, i64, sz, i64, vp, vp, vp, vp, i32, vp]),
     "init_cuda_offload": (i32, [i32]),

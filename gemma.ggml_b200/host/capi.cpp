@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "gemma_model.h"
+#include "tensor_dump.h"
 
 extern "C" {
 
@@ -62,5 +63,27 @@ int gm_get_capture(void *m, const char *name, int layer, float *host, int64_t n)
 int gm_get_kv(void *m, int layer, void *k_host, void *v_host) { return ((gemma_model *)m)->get_kv(layer, k_host, v_host); }
 int gm_kernels_per_step(void *m) { return ((gemma_model *)m)->kernels_per_step(); }
 uint64_t gm_weight_bytes(void *m) { return (uint64_t)((gemma_model *)m)->weight_bytes(); }
+
+// ---- tensor_dump (ref: src/tensor_dump.h): host-side parity harness
+void td_set_dir(const char *dir) { set_tensor_dump_dir(dir); }
+int td_dump_ptr_data(const char *name, const void *ptr, uint64_t size, int target) {
+    return dump_ptr_data(name, ptr, (size_t)size, target ? tensor_dump_mode::target : tensor_dump_mode::source) ? 0 : -1;
+}
+// a named intermediate of the model's last step, fetched from the device and dumped as "<name>-<layer>_source|_target"
+int td_dump_capture(void *m, const char *name, int layer, int64_t n, int target) {
+    std::vector<float> h((size_t)n);
+    const int rc = ((gemma_model *)m)->get_capture(name, layer, h.data(), n);
+    if (rc) return rc;
+    const std::string file = std::string(name) + "-" + std::to_string(layer);
+    return dump_ptr_data(file.c_str(), h.data(), h.size() * 4, target ? tensor_dump_mode::target : tensor_dump_mode::source) ? 0 : -1;
+}
+int td_compare_tensors(const char *name) { return compare_tensors(name) ? 1 : 0; }
+// out[5] = {n, n_diff, max_abs, max_rel, max_target}; returns 0 if both files exist with equal fp32 sizes
+int td_compare_tensors_report(const char *name, double *out) {
+    tensor_compare_report r;
+    if (!compare_tensors_report(name, &r)) return -1;
+    out[0] = (double)r.n; out[1] = (double)r.n_diff; out[2] = r.max_abs; out[3] = r.max_rel; out[4] = r.max_target;
+    return 0;
+}
 
 } // extern "C"
