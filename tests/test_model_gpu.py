@@ -20,6 +20,9 @@ SMALL = {
     # 40 blocks, a short segment too long for a quad pass (zero-padded plain pass).  The configs above cover kf = 0
     # (K <= 1024) and kf = 2 (n_ff 4608)
     "k96": dict(n_embd=3072, n_layer=1, n_head=2, n_head_kv=2, head_dim=128, n_ff=1280, n_vocab=512, n_ctx=48),
+    # every K a multiple of 2048 (64-block segments only), as in Gemma-2B: the plain (non-quad) instantiation of the
+    # persistent kernel, which the configs above never reach (their short K rows all take the quad layout)
+    "plain": dict(n_embd=2048, n_layer=1, n_head=8, n_head_kv=1, head_dim=256, n_ff=4096, n_vocab=512, n_ctx=48),
     # outside the fused kernel's envelope (n_embd % 256 != 0): exercises the per-operator lowering
     "odd": dict(n_embd=384, n_layer=2, n_head=4, n_head_kv=2, head_dim=96, n_ff=1056, n_vocab=777, n_ctx=48),
 }
@@ -57,7 +60,7 @@ def test_two_attention_groups_match_oracle(gpu, monkeypatch, name, wtype):
 
 
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "ops"])
-@pytest.mark.parametrize("name", ["mqa", "mha", "k96", "odd"])
+@pytest.mark.parametrize("name", ["mqa", "mha", "k96", "plain", "odd"])
 @pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
 def test_generate_matches_oracle(gpu, name, wtype, fused):
     dims = SMALL[name]
