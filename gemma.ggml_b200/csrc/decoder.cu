@@ -741,8 +741,11 @@ __device__ __forceinline__ void attn_group(const DecoderParams &P, Smem<TYPE, GR
             const float x0 = ll_get_f(w0, qh + e, tag), x1 = ll_get_f(w1, qh + e + halfd, tag);
             const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
             const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
-            Sq[jh * d + e] = __half2float(__float2half_rn(r0));
-            Sq[jh * d + e + halfd] = __half2float(__float2half_rn(r1));
+            // two planes per head so that the score loop's LDS.128 are conflict-free (a lane's dims 8l..8l+3 at 16 l of
+            // plane 0, dims 8l+4..8l+7 at 16 l of plane 1; one 32-byte-strided row would take two wavefronts per load)
+            const int e1 = e + halfd;
+            Sq[jh * d + ((e >> 2) & 1) * halfd + (e >> 3) * 4 + (e & 3)] = __half2float(__float2half_rn(r0));
+            Sq[jh * d + ((e1 >> 2) & 1) * halfd + (e1 >> 3) * 4 + (e1 & 3)] = __half2float(__float2half_rn(r1));
         }
         DBG_STAMP(2);
         if (owns_new) { // KV store of the new position (ref: src/gemma_model.cpp:499-518)
@@ -798,8 +801,8 @@ __device__ __forceinline__ void attn_group(const DecoderParams &P, Smem<TYPE, GR
             for (int u = 0; u < 4; u++) {
                 float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
                 if (u < Gh && in) {
-                    qa = *reinterpret_cast<const float4 *>(Sq + u * d + 8 * lane);
-                    qb = *reinterpret_cast<const float4 *>(Sq + u * d + 8 * lane + 4);
+                    qa = *reinterpret_cast<const float4 *>(Sq + u * d + 4 * lane);
+                    qb = *reinterpret_cast<const float4 *>(Sq + u * d + halfd + 4 * lane);
                 }
                 const float qf[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
