@@ -605,7 +605,9 @@ __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int l
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int t = QUAD ? 0 : (k & 1);
-        const uint32_t pay = base + k * (32 * F::PB) + lane * F::PB;
+        // Q8_0 groups hold the first 16 codes of their 32 blocks, then the second 16 (two planes of 512 B): both
+        // LDS.128 of a lane are then 16-byte-strided across the warp, i.e. conflict-free
+        const uint32_t pay = base + k * (32 * F::PB) + lane * 16;
         const float dx = lds_half(base + 2 * F::ROW_PB + k * 64 + lane * 2);
         if (TYPE == GGB_TYPE_Q4_0) {
             const uint4 w = lds_u4(pay);
@@ -619,7 +621,7 @@ __device__ __forceinline__ float pass_dot(uint32_t base, const ActRegs &A, int l
             const int sumi = lo + (hi >> 4);
             term[k] = __fmul_rn(__fmul_rn((float)sumi, dx), dy[t]);
         } else {
-            const uint4 w0 = lds_u4(pay), w1 = lds_u4(pay + 16);
+            const uint4 w0 = lds_u4(pay), w1 = lds_u4(pay + 512);
             int s0 = 0, s1 = 0;
             s0 = __dp4a((int)w0.x, a[t][0], s0); s1 = __dp4a((int)w1.x, a[t][4], s1);
             s0 = __dp4a((int)w0.y, a[t][1], s0); s1 = __dp4a((int)w1.y, a[t][5], s1);
@@ -1300,17 +1302,17 @@ template <int TYPE> __global__ void repack_kernel(RepackArgs A) {
         }
     }
     uint8_t *pass = A.dst + (size_t)p * F::PASS_BYTES;
-    uint4 *pay = reinterpret_cast<uint4 *>(pass + k * (32 * F::PB) + i * F::PB);
+    uint4 *pay = reinterpret_cast<uint4 *>(pass + k * (32 * F::PB) + i * 16); // Q8_0: second half of the block at + 512 B
     __half *scl = reinterpret_cast<__half *>(pass + 2 * F::ROW_PB + k * 64) + i;
     if (valid) {
         const size_t b = (size_t)row * A.nb + blk;
         const uint4 *src = reinterpret_cast<const uint4 *>(A.m[mat].qs + b * F::PB);
         pay[0] = src[0];
-        if (F::PB == 32) pay[1] = src[1];
+        if (F::PB == 32) pay[32] = src[1];
         *scl = A.m[mat].d[b];
     } else {
         pay[0] = make_uint4(0, 0, 0, 0);
-        if (F::PB == 32) pay[1] = make_uint4(0, 0, 0, 0);
+        if (F::PB == 32) pay[32] = make_uint4(0, 0, 0, 0);
         *scl = __float2half(0.0f);
     }
 }
