@@ -420,7 +420,9 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE,
 // costs (~0.3 us at 4 warps per scheduler), so a warp runs it once per four blocks instead of once per block.
 // amax / code sum: three xor-shuffles inside each 8-lane group (a sub-warp REDUX serialises the four groups
 // behind WARPSYNC.EXCLUSIVE and costs ~0.5 us).  max is exact: same value as the reference's scan.
-__device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lane, const float (&v)[4]) {
+// (activation codes live in TWO planes - bytes 0..15 of every block, then bytes 16..31 at + hi_off = K / 2 - so that
+// load_act_regs' LDS.128 are 16-byte-strided across the warp: conflict-free)
+__device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lane, const float (&v)[4], int hi_off) {
     float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
 #pragma unroll
     for (int off = 1; off <= 4; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off)); // 8-lane groups
@@ -429,7 +431,8 @@ __device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lan
     uint32_t packed = 0;
 #pragma unroll
     for (int e = 0; e < 4; e++) packed |= ((uint32_t)(int)roundf(__fmul_rn(v[e], id)) & 0xFFu) << (8 * e);
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(u + 128 * quad + 4 * lane), "r"(packed) : "memory");
+    // word j = lane & 7 of block b = 4 quad + (lane >> 3): plane j >> 2, offset 16 b + 4 (j & 3)
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(u + ((lane & 4) ? hi_off : 0) + 64 * quad + 16 * (lane >> 3) + 4 * (lane & 3)), "r"(packed) : "memory");
     int qs = __dp4a((int)packed, 0x01010101, 0);
 #pragma unroll
     for (int off = 1; off <= 4; off <<= 1) qs += __shfl_xor_sync(0xffffffffu, qs, off);
@@ -504,7 +507,7 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE,
         v[2] = __fmul_rn(__fmul_rn(x4.z, scale), w4.z);
         v[3] = __fmul_rn(__fmul_rn(x4.w, scale), w4.w);
         if (f32_out) *reinterpret_cast<float4 *>(f32_out + i) = make_float4(v[0], v[1], v[2], v[3]);
-        quant_quad_to_smem(ua, quad, lane, v);
+        quant_quad_to_smem(ua, quad, lane, v, E / 2);
     }
     DBG_STAMP(6);
     consumer_bar();
@@ -525,7 +528,7 @@ __device__ __forceinline__ void quant_prologue(Smem<TYPE, GROUPS> &S, const ll_t
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) v[e] = ll_get_f(w[e], p + e, tag);
-        quant_quad_to_smem(ua, quad, lane, v);
+        quant_quad_to_smem(ua, quad, lane, v, K / 2);
     }
     consumer_bar();
 }
@@ -550,7 +553,7 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE, GROUPS> &S, const ll_
             const int i = i0 + kCT * u;
             if (i < nw + ns) {
                 const uint32_t w = ll_get(v[u], in + i, tag);
-                if (i < nw) aq[i] = w;
+                if (i < nw) aq[((i & 4) ? nw / 2 : 0) + 4 * (i >> 3) + (i & 3)] = w; // two planes (see quant_quad_to_smem)
                 else {
                     ad[i - nw] = __ushort_as_half((unsigned short)w);
                     if (TYPE == GGB_TYPE_Q4_0) bias[i - nw] = -8 * ((int)w >> 16);
@@ -579,7 +582,7 @@ __device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg,
         const int b = seg * kSeg + lane + 32 * t;
         A.live[t] = b < nb;
         const int bc = A.live[t] ? b : 0;
-        const uint4 lo = lds_u4(act + bc * 32), hi = lds_u4(act + bc * 32 + 16);
+        const uint4 lo = lds_u4(act + bc * 16), hi = lds_u4(act + nb * 16 + bc * 16); // planes: bytes 0..15 | 16..31
         A.a[t][0] = lo.x; A.a[t][1] = lo.y; A.a[t][2] = lo.z; A.a[t][3] = lo.w;
         A.a[t][4] = hi.x; A.a[t][5] = hi.y; A.a[t][6] = hi.z; A.a[t][7] = hi.w;
         unsigned short hd;
