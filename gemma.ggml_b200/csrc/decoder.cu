@@ -1,9 +1,9 @@
-// decoder.cu — the persistent decode kernel: ONE cooperative launch per token (v3: pass stream + flagged data flow).
+// decoder.cu — the persistent decode kernel: ONE cooperative launch per token (v4: pass stream + flagged data flow).
 //
 // Why: a Gemma-2B Q4_0 token is 1.41 GB of weights + 38 MB of KV = ~220 us of HBM time on a B200, spread
 // over 163 mat-vecs and ~450 small nodes (ref: src/gemma_model.cpp:688-740).  One CTA per SM stays resident
 // for the whole token; what limits it is (a) how cleanly the weights stream and (b) what every phase change
-// costs.  Design rules, each measured (tools/ubench_stream.cu, tools/ubench_bar.cu, tools_trace.py):
+// costs.  Design rules, each measured (tools/ubench_stream.cu, ubench_bar.cu, ubench_dp4a.cu, tools_trace.py, tools/ab.sh):
 //
 //   * PASS STREAM.  At create time every weight matrix is re-laid out as a stream of PASSES: one pass =
 //     two rows x one 64-block K segment (2304 B Q4_0 / 4352 B Q8_0), payloads then scales, i.e. exactly what
@@ -23,9 +23,15 @@
 //     number, the buffers are per layer, and a consumer simply re-reads a word until its tag matches.  Data
 //     and flag arrive together, so no fence and no separate wait: a phase change costs one L2 write + one L2
 //     read.  Each phase's prologue polls exactly the inputs it needs.
-//   * SMALL CODE.  The 32 KB instruction cache holds ~2000 SASS instructions and a persistent kernel runs
-//     each phase's code once per layer: every mat-vec phase shares one pass loop, prologues and epilogues are
-//     short and not unrolled.
+//   * ISSUE-BOUND, AT THE REGISTER LIMIT.  The pass loop is bound by instruction issue (IDP.4A every 2 cycles per SM
+//     sub-partition, ~185 instructions per pass: ~85 GB/s per SM against the 44 GB/s HBM delivers), the phases
+//     between the mat-vecs by chains of ~30-cycle steps.  17 warps per SM cap the kernel at 96 registers, shared
+//     memory leaves no L1, so a spill is an L2 round trip: token-constant scalars live in shared memory, every hot
+//     LDS.128 is conflict-free (two-plane layouts), no integer division at a phase start, the soft-max exp is
+//     computed (proved equal to the reference's fp16 table at create time).  Instruction-cache warmth is NOT a
+//     factor (a warm second run of a phase takes the same time).
+//   * TEMPLATE SWITCHES.  QUAD: models with a short last K segment (Gemma-7B, K = 3072) share one pass between four
+//     rows for it; GROUPS = 2: MHA models at long context run two ATTN items per CTA in two 8-warp groups.
 //
 // Phases per layer: QKV | ATTN (split-K partials; rope, Q scale and the KV-cache store of the new position
 // folded in) | COMBINE | O (+ residual) | GATE_UP (+ GeGLU + Q8_0 quantise) | DOWN (+ residual);
