@@ -486,6 +486,7 @@ void orc_attn_decode_ref(int H, int Hkv, int d, int64_t n_pos, int64_t n_ctx, co
  * 32 positions (absent positions contribute 0.0f); acc[i] = sum_p e_p * V[p][i] sequential in p.
  * Combine (per head): M = max m_c; w_c = exp_table[f16(m_c - M)]; L = sum l_c*w_c and
  * O[i] = sum acc_c[i]*w_c sequential in c (mul then add); out = O / L. */
+int orc_x_attn_variant = 0; /* EXPERIMENT: 0 = DEV as built, 2 = w_c in fp32, 3 = global max first */
 void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
                          const uint16_t *kcache, const uint16_t *vcache, int64_t kv_stride, float *out) {
     const uint16_t *t = orc_exp_table();
@@ -499,6 +500,20 @@ void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
     for (int h = 0; h < H; h++) {
         const int g = h / G;
         for (int i = 0; i < d; i++) q16f[i] = orc_fp16_to_fp32(orc_fp32_to_fp16(q[(size_t)h * d + i]));
+        float GM = -INFINITY;
+        if (orc_x_attn_variant == 3) {
+            for (int64_t pz = 0; pz < n_pos; pz++) {
+                const uint16_t *krow = kcache + pz * kv_stride + (size_t)g * d;
+                float lane[32];
+                for (int l = 0; l < 32; l++) {
+                    float acc = 0.0f;
+                    for (int i = 8 * l; i < 8 * l + 8 && i < d; i++) acc += orc_fp16_to_fp32(krow[i]) * q16f[i];
+                    lane[l] = acc;
+                }
+                const float sc = butterfly32f(lane);
+                GM = sc > GM ? sc : GM;
+            }
+        }
         for (int64_t c = 0; c < nchunk; c++) {
             const int64_t p0 = c * C;
             const int np = (int)((n_pos - p0) < C ? (n_pos - p0) : C);
@@ -516,6 +531,7 @@ void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
                 m = s[j] > m ? s[j] : m;
             }
             float lane[32];
+            if (orc_x_attn_variant == 3) m = GM;
             for (int j = 0; j < 32; j++) {
                 if (j < np) {
                     e[j] = orc_fp16_to_fp32(t[orc_fp32_to_fp16(s[j] - m)]);
@@ -538,7 +554,8 @@ void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
         float L = 0.0f;
         for (int i = 0; i < d; i++) out[(size_t)h * d + i] = 0.0f;
         for (int64_t c = 0; c < nchunk; c++) {
-            const float w = orc_fp16_to_fp32(t[orc_fp32_to_fp16(pm[c] - M)]);
+            float w = orc_fp16_to_fp32(t[orc_fp32_to_fp16(pm[c] - M)]);
+            if (orc_x_attn_variant >= 2) w = (float)exp((double)(pm[c] - M));
             L += pl[c] * w;
             for (int i = 0; i < d; i++) out[(size_t)h * d + i] += pacc[(size_t)c * d + i] * w;
         }
