@@ -176,10 +176,11 @@ __global__ void rope_kernel(const float *__restrict__ x, const int32_t *__restri
 // (ref: src/gemma_model.cpp:698-716 rope+scale, :499-518 KV store as two ggml_cpy F32->F16).
 __global__ void rope_kv_store_kernel(float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
                                      const int32_t *__restrict__ pos_p, int H, int Hkv, int d, float q_scale,
-                                     const float *__restrict__ cosT, const float *__restrict__ sinT,
+                                     const float *__restrict__ cosT, const float *__restrict__ sinT, int table_ctx,
                                      __half *__restrict__ kcache, __half *__restrict__ vcache) {
     const int half = d / 2;
-    const int pos = *pos_p;
+    int pos = *pos_p; // clamped like the batch form: a position outside the rope table / cache must not address memory
+    pos = pos < 0 ? 0 : (pos >= table_ctx ? table_ctx - 1 : pos);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int nq = H * half, nk = Hkv * half, nv = Hkv * d;
     if (idx < nq + nk) {
@@ -319,9 +320,13 @@ argmax_stage2(const Cand *__restrict__ part, int n_part, int32_t *__restrict__ o
     if (threadIdx.x == 0) {
         if (out) *out = c.i;
         if (state) {
+            // state = [token, pos, pos_step, n_ctx]: the position stops at n_ctx - 1 (history holds n_ctx + 2 ids)
+            int np = state[1] + state[2];
+            if (state[3] > 0 && np > state[3] - 1) np = state[3] - 1;
+            if (np < 0) np = 0;
             state[0] = c.i;
-            state[1] += state[2];
-            if (history) history[state[1]] = c.i;
+            state[1] = np;
+            if (history) history[np] = c.i;
         }
     }
 }
@@ -438,7 +443,8 @@ int ggb_op_rope_kv_store(float *q, const float *k, const float *v, const int32_t
     GGB_CHECK_ARG(ggb_rope_cos_dev() && ggb_rope_n_dims() == d, "rope table not initialised for head_dim %d", d);
     const int total = (H + Hkv) * (d / 2) + Hkv * d;
     rope_kv_store_kernel<<<blocks_for(total), 256, 0, ggb_cuda_stream()>>>(
-        q, k, v, pos, H, Hkv, d, q_scale, ggb_rope_cos_dev(), ggb_rope_sin_dev(), (__half *)kcache, (__half *)vcache);
+        q, k, v, pos, H, Hkv, d, q_scale, ggb_rope_cos_dev(), ggb_rope_sin_dev(), ggb_rope_n_ctx(), (__half *)kcache,
+        (__half *)vcache);
     GGB_LAUNCH_CHECK();
     return GGB_OK;
 }

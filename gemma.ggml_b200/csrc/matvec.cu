@@ -2,14 +2,14 @@
 // of the reference (ref: src/hpc.cpp:15-41 mul_mat_sub -> vec_dot, 99.98 % of mul_mat time,
 // notes.md:87).  Not a port of src/kernals.cl (one work-item per output, serial K loop):
 //
-//   * a warp owns a row (or, for K > 2048, one 64-block segment of a row); lane l owns blocks
-//     l, l+32 of the segment, so the activation blocks a lane needs never change
-//     from row to row and live in REGISTERS for the whole kernel;
-//   * weight payloads stream with one coalesced 128-bit load per lane per block (SoA planes,
-//     L1 no-allocate), nibbles are unpacked in registers and dotted with dp4a; the "-8" of
-//     Q4_0 is folded into a per-lane constant (-8 * sum of the activation block);
-//   * per-block terms are the scalar reference's ((float)sumi*dx)*dy, summed in the DEV order
-//     documented in include/ggml_b200.h; reduction is warp shuffles (+ smem across segments).
+//   * a warp owns a row; lane l computes the per-block term of blocks l, l + 32, ... with dp4a
+//     (one coalesced 128-bit payload load per lane per block, nibbles unpacked in registers, the
+//     "-8" of Q4_0 folded into -8 * sum of the activation block);
+//   * the per-block terms are the scalar reference's ((float)sumi*dx)*dy and are ADDED IN THE
+//     REFERENCE'S ORDER: one fp32 accumulator, blocks 0, 1, 2, ... (the warp passes the 32 terms of a
+//     round through a shuffle chain), so every output is bit-identical to ggml's scalar vec_dot.
+//     This per-operator form is the fallback / T > 1 lowering; the persistent decode kernel
+//     (decoder.cu) produces the same bits with a dedicated chain warp.
 #include "dot.cuh"
 
 namespace {
@@ -33,65 +33,28 @@ struct MatvecArgs {
     int64_t act_stride; // bytes between activation rows (T > 1)
     int64_t dst_stride; // floats between dst rows
     int64_t cols;
-    int ksegs;         // ceil(nb / 128)
-    int rows_per_iter; // warps per CTA / ksegs
-    int64_t rows_per_cta;
 };
 
+constexpr int kMvWarps = 8;
+
 template <int TYPE>
-__global__ void __launch_bounds__(384) matvec_kernel(const MatvecArgs a) {
-    extern __shared__ float s_part[]; // [rows_per_iter][ksegs]
+__global__ void __launch_bounds__(kMvWarps * 32) matvec_kernel(const MatvecArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int kseg = warp % a.ksegs;
-    const int rsub = warp / a.ksegs;
     const uint8_t *act = a.act + (int64_t)blockIdx.y * a.act_stride;
-
-    ActBlock ab[kTPB];
-    bool valid[kTPB];
-    const int64_t b0 = (int64_t)kseg * GGB_DEV_SEG_BLOCKS + lane;
-#pragma unroll
-    for (int t = 0; t < kTPB; t++) {
-        valid[t] = b0 + 32 * t < a.nb;
-        load_act(ab[t], act, a.cols, b0 + 32 * t, valid[t]);
+    const int64_t gr = (int64_t)blockIdx.x * kMvWarps + warp;
+    if (gr >= a.total_rows) return;
+    int mi = 0;
+    int64_t r = gr;
+    while (mi + 1 < a.n_mats && r >= a.m[mi].rows) {
+        r -= a.m[mi].rows;
+        mi++;
     }
-
-    const int64_t row_begin = (int64_t)blockIdx.x * a.rows_per_cta;
-    int64_t row_end = row_begin + a.rows_per_cta;
-    if (row_end > a.total_rows) row_end = a.total_rows;
-    for (int64_t base = row_begin; base < row_end; base += a.rows_per_iter) {
-        const int64_t gr = base + rsub;
-        const bool live = gr < row_end;
-        // locate the matrix this global row belongs to
-        int mi = 0;
-        int64_t r = gr;
-        if (live) {
-            while (mi + 1 < a.n_mats && r >= a.m[mi].rows) {
-                r -= a.m[mi].rows;
-                mi++;
-            }
-        }
-        float seg = 0.0f;
-        if (live) seg = segment_dot<TYPE>(a.m[mi].qs, a.m[mi].d, r, a.nb, b0, ab, valid);
-        if (a.ksegs == 1) {
-            if (live && lane == 0) {
-                float *dst = a.m[mi].dst + (int64_t)blockIdx.y * a.dst_stride;
-                float v = seg;
-                if (a.m[mi].resid) v = __fadd_rn(v, a.m[mi].resid[(int64_t)blockIdx.y * a.dst_stride + r]);
-                dst[r] = v;
-            }
-        } else {
-            if (lane == 0) s_part[rsub * a.ksegs + kseg] = seg;
-            __syncthreads();
-            if (live && kseg == 0 && lane == 0) {
-                float total = s_part[rsub * a.ksegs];
-                for (int s = 1; s < a.ksegs; s++) total = __fadd_rn(total, s_part[rsub * a.ksegs + s]);
-                float *dst = a.m[mi].dst + (int64_t)blockIdx.y * a.dst_stride;
-                if (a.m[mi].resid) total = __fadd_rn(total, a.m[mi].resid[(int64_t)blockIdx.y * a.dst_stride + r]);
-                dst[r] = total;
-            }
-            __syncthreads();
-        }
+    float v = row_dot_ref<TYPE>(a.m[mi].qs, a.m[mi].d, r, a.nb, act, a.cols, lane);
+    if (lane == 0) {
+        float *dst = a.m[mi].dst + (int64_t)blockIdx.y * a.dst_stride;
+        if (a.m[mi].resid) v = __fadd_rn(v, a.m[mi].resid[(int64_t)blockIdx.y * a.dst_stride + r]);
+        dst[r] = v;
     }
 }
 
@@ -115,32 +78,14 @@ __global__ void __launch_bounds__(256) gate_up_kernel(const GateUpArgs a) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t tile_row0 = (int64_t)blockIdx.x * 32;
-    const int ksegs = (int)((a.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS);
-    float g[4], u[4];
-    // segments in order (DEV): the lane's activation blocks are reloaded per segment
-    for (int seg = 0; seg < ksegs; seg++) {
-        ActBlock ab[kTPB];
-        bool valid[kTPB];
-        const int64_t b0 = (int64_t)seg * GGB_DEV_SEG_BLOCKS + lane;
-#pragma unroll
-        for (int t = 0; t < kTPB; t++) {
-            valid[t] = b0 + 32 * t < a.nb;
-            load_act(ab[t], a.act, a.cols, b0 + 32 * t, valid[t]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int64_t r = tile_row0 + warp * 4 + i;
-            const float gs = segment_dot<TYPE>(a.gate_qs, a.gate_d, r, a.nb, b0, ab, valid);
-            const float us = segment_dot<TYPE>(a.up_qs, a.up_d, r, a.nb, b0, ab, valid);
-            g[i] = seg == 0 ? gs : __fadd_rn(g[i], gs);
-            u[i] = seg == 0 ? us : __fadd_rn(u[i], us);
-        }
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            s_g[warp * 4 + i] = g[i];
-            s_u[warp * 4 + i] = u[i];
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        const int64_t r = tile_row0 + warp * 4 + i;
+        const float gs = row_dot_ref<TYPE>(a.gate_qs, a.gate_d, r, a.nb, a.act, a.cols, lane);
+        const float us = row_dot_ref<TYPE>(a.up_qs, a.up_d, r, a.nb, a.act, a.cols, lane);
+        if (lane == 0) {
+            s_g[warp * 4 + i] = gs;
+            s_u[warp * 4 + i] = us;
         }
     }
     __syncthreads();
@@ -179,18 +124,9 @@ int launch_matvec(int n, const ggb_weight *const *w, const void *q8, int64_t T, 
     a.act = (const uint8_t *)q8;
     a.act_stride = (int64_t)ggb_q8_row_bytes(a.cols);
     a.dst_stride = dst_stride;
-    a.ksegs = (int)((a.nb + GGB_DEV_SEG_BLOCKS - 1) / GGB_DEV_SEG_BLOCKS);
-    GGB_CHECK_ARG(a.ksegs <= 12, "K = %lld too large for one CTA (max 24576)", (long long)a.cols);
-    a.rows_per_iter = a.ksegs >= 8 ? 1 : 8 / a.ksegs;
-    const int warps = a.rows_per_iter * a.ksegs;
-    const int64_t target_ctas = (int64_t)ggb_sm_count() * 8;
-    int64_t rpc = (a.total_rows + target_ctas - 1) / target_ctas;
-    rpc = ((rpc + a.rows_per_iter - 1) / a.rows_per_iter) * a.rows_per_iter;
-    if (rpc < a.rows_per_iter) rpc = a.rows_per_iter;
-    a.rows_per_cta = rpc;
-    const unsigned grid_x = (unsigned)((a.total_rows + rpc - 1) / rpc);
-    const dim3 grid(grid_x, (unsigned)T);
-    const size_t smem = sizeof(float) * (size_t)warps;
+    const dim3 grid((unsigned)((a.total_rows + kMvWarps - 1) / kMvWarps), (unsigned)T);
+    const int warps = kMvWarps;
+    const size_t smem = 0;
     if (w[0]->type == GGB_TYPE_Q4_0)
         matvec_kernel<GGB_TYPE_Q4_0><<<grid, warps * 32, smem, ggb_cuda_stream()>>>(a);
     else

@@ -431,13 +431,18 @@ int gemma_model::set_state(token_id token, int32_t pos, int32_t pos_step) {
     h_state_[0] = token;
     h_state_[1] = pos;
     h_state_[2] = pos_step;
-    h_state_[3] = 0;
+    h_state_[3] = cfg_.n_ctx; // the device stops advancing the position at n_ctx - 1
+    pos_hint_ = pos;
+    pos_step_hint_ = pos_step;
     return ggb_upload(state_, h_state_, 16);
 }
 
 int gemma_model::run_steps(int steps) {
-    if (!built_) return GGB_ERR_ARG;
+    if (!built_ || steps < 0) return GGB_ERR_ARG;
+    // stepping past the context would address the KV cache / rope table / history out of bounds: refuse
+    if (pos_step_hint_ > 0 && pos_hint_ + (int64_t)(steps - 1) * pos_step_hint_ > (int64_t)cfg_.n_ctx - 1) return GGB_ERR_ARG;
     for (int i = 0; i < steps; i++) GM_TRY(launch_step());
+    pos_hint_ += (int64_t)steps * pos_step_hint_;
     return 0;
 }
 
@@ -592,7 +597,8 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
     PROFILE("op_rms_norm", ggb_op_rms_norm_bf16(pf_x_, output_norm_, c.eps, E, t, pf_a_));               // :735
     PROFILE("op_mul_mat", gemm(token_embd_, E, pf_logits_, nullptr));                                    // :740 (all T rows)
     // greedy token of the last position; decode continues at pos0 + T
-    h_state_[0] = 0; h_state_[1] = pos0 + T - 1; h_state_[2] = 1; h_state_[3] = 0;
+    h_state_[0] = 0; h_state_[1] = pos0 + T - 1; h_state_[2] = 1; h_state_[3] = c.n_ctx;
+    pos_hint_ = pos0 + T; pos_step_hint_ = 1;
     GM_TRY(ggb_upload(state_, h_state_, 16));
     PROFILE("op_argmax", ggb_op_sample_greedy(pf_logits_ + (size_t)(T - 1) * (size_t)V, V, state_, history_, sample_scratch_));
     GM_TRY(ggb_download(h_state_ + 4, state_, 16));

@@ -123,6 +123,8 @@ class gemma_model {
     // device-resident step state: [token, pos, pos_step]
     int32_t *state_ = nullptr, *history_ = nullptr;
     int32_t *h_state_ = nullptr; // pinned
+    int64_t pos_hint_ = 0;       // host mirror of the device position / step (run_steps refuses to leave the context)
+    int32_t pos_step_hint_ = 0;
     // activations
     float *x0_ = nullptr, *q_ = nullptr, *k_ = nullptr, *v_ = nullptr, *logits_ = nullptr, *result_norm_ = nullptr;
     float *sa_out_ = nullptr, *l_out_ = nullptr, *kqv_ = nullptr, *ffn_act_ = nullptr; // per layer slots
