@@ -406,7 +406,7 @@ class GemmaModel:
         check(self.H.gm_build_compute_graph(self.h, int(capture_acts), int(fused)), "gm_build_compute_graph")
 
     def trace_step(self):
-        """One traced fused step: (stamps[n_phases, grid, 4] in SM clocks, kinds[n_phases])."""
+        """One traced fused step: (stamps[n_phases, grid, 4] in %globaltimer ns, kinds[n_phases])."""
         dec = self.H.gm_decoder(self.h)
         if not dec:
             raise GgbError("trace_step needs the fused decoder")
@@ -418,7 +418,6 @@ class GemmaModel:
         check(cuda_lib().ggb_decoder_trace(dec, _ptr(stamps), _ptr(kinds), max_ph, C.byref(n), C.byref(g)),
               "ggb_decoder_trace")
         n1 = n.value * g.value * 4
-        self.dbg_stamps = stamps[n1:n1 + g.value * 16].reshape(g.value, 16).copy()
         return stamps[:n1].reshape(n.value, g.value, 4), kinds[:n.value].copy()
 
     @property

@@ -139,7 +139,11 @@ class gemma_model {
     // KV cache in the full [n_ctx][Hkv*d] layout, each rank fills the chunks it owns); false = per-operator
     // kernels + NCCL allgathers (KV cache sharded by head).  GGB_TP_FUSED=0 selects the latter.
     bool tp_fused_ = true;
-    int kv_heads_alloc() const { return (plan_.size > 1 && tp_fused_) ? cfg_.n_head_kv : plan_.kv_heads; }
+    // KV heads this rank's cache holds: its own heads when attention is sharded by head, all of them when the attention
+    // block is replicated (MQA under the fused lowering)
+    int kv_heads_alloc() const {
+        return (plan_.size > 1 && tp_fused_) ? ggb_decoder_kv_heads_local(cfg_.n_head, cfg_.n_head_kv, plan_.size) : plan_.kv_heads;
+    }
     ggb_weight *sh_logits_ = nullptr;
     float *kqv_local_ = nullptr;
     void *cand_ = nullptr; // [tp_size] (value, index) candidates of the sharded arg-max

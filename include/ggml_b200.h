@@ -215,8 +215,8 @@ int ggb_op_attn_prefill(const float *q, const void *kcache, const void *vcache, 
 
 /* ------------------------------------------------------------------ fused decode step
  * The whole per-token node list (ref: src/gemma_model.cpp:665-747) as ONE persistent cooperative
- * kernel: weights and KV stream through a shared-memory ring fed by TMA bulk copies while the
- * consumers cross phase barriers (csrc/decoder.cu).  Bit-identical to the ggb_op_* sequence. */
+ * kernel: weights and KV stream through a shared-memory ring fed by TMA bulk copies (csrc/decoder.cu).
+ * Bit-identical to the ggb_op_* sequence and to the scalar ggml order of the reference's CPU path. */
 typedef struct {
     int32_t n_embd, n_layer, n_head, n_head_kv, head_dim, n_ff, n_vocab, n_ctx;
     float eps;
@@ -240,16 +240,19 @@ typedef struct ggb_decoder ggb_decoder;
 /* GGB_ERR_UNSUPPORTED when the shape is outside the fused kernel's envelope (callers then use ggb_op_*) */
 int ggb_decoder_create(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
                        const float *output_norm, const ggb_decoder_io *io, ggb_decoder **out);
-/* tensor-parallel form (one process per GPU, ggb_comm_init done): every mat-vec phase is split by output rows
- * over `size` ranks, and every value that crosses CTAs is pushed as a flagged 8-byte word into EVERY rank's
+/* tensor-parallel form (one process per GPU, ggb_comm_init done): the phases that carry the bytes (GATE_UP, DOWN,
+ * LOGITS) are split by output rows over `size` ranks and push their flagged 8-byte output words into EVERY rank's
  * buffers with peer stores over NVLink (cudaIpc mappings exchanged at create time) — the all-gather is fused into
- * the producing epilogue, no NCCL call on the token path.  Bit-identical to the single-GPU kernel. */
+ * the producing epilogue, no NCCL call on the token path.  The attention block (QKV, scores, soft-max * V, O) is
+ * sharded by KV head when n_head and n_head_kv divide by `size` (each rank's cache then holds only its heads:
+ * [n_ctx][ggb_decoder_kv_heads_local * head_dim]) and replicated otherwise.  Bit-identical to the single-GPU kernel. */
+int ggb_decoder_kv_heads_local(int n_head, int n_head_kv, int size);
 int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer *layers, const ggb_weight *token_embd,
                           const float *output_norm, const ggb_decoder_io *io, int rank, int size, ggb_decoder **out);
 int ggb_decoder_step(ggb_decoder *d); /* enqueue one token; capturable into a ggb_graph */
 int ggb_decoder_free(ggb_decoder *d);
 /* run ONE traced step: stamps[n_phases][grid][4] %globaltimer values in ns (phase start, after the
- * prologue = inputs arrived, end, end), kinds[n_phases] phase kinds (0 QKV, 1 ATTN, 2 COMBINE, 3 O,
+ * prologue = inputs arrived, end, end), kinds[n_phases] phase kinds (0 QKV, 1 SCORE, 2 PV, 3 O,
  * 4 GATE_UP, 5 DOWN, 6 LOGITS, 7 SAMPLE) */
 int ggb_decoder_trace(ggb_decoder *d, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid);
 /* 1 if the kernel computes the soft-max exp (double exp -> fp32 -> fp16) instead of reading the reference's fp16 table:

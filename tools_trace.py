@@ -7,7 +7,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import gemma_ggml_b200 as G
 
-NAMES = ["QKV", "ATTN", "COMBINE", "O", "GATE_UP", "DOWN", "LOGITS", "SAMPLE"]
+NAMES = ["QKV", "SCORE", "PV", "O", "GATE_UP", "DOWN", "LOGITS", "SAMPLE"]
 
 
 def main():
@@ -40,26 +40,12 @@ def main():
         rows.append((pi, NAMES[k], crit, wait[busy].min() if busy.any() else 0.0, wait.max(), work.max(), int(busy.sum())))
         prev_end = end
     print("phase      n   critical-path  prologue(min)  prologue(max)  work(max)  work(mean)   [us, summed over the token]")
-    total = 0.0
     for k, d in tot.items():
         print(f"{k:9s} {d['n']:3d}  {d['crit']:12.1f}  {d['wait_min']:12.1f}  {d['wait_max']:12.1f}  {d['work_max']:9.1f}  {d['work_mean']:9.1f}")
-        total += d["crit"]
     print("token (first start -> last end): %.1f us" % (prev_end - t_begin))
     print("layer 5 detail: phase, critical us, prologue min/max us, work max us, busy CTAs")
     for r in rows[30:36]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
-    db = m.dbg_stamps.astype(np.float64)
-    ok = db[:, 0] > 0
-    rel = (db[ok] - db[ok, 0:1]) / 1965.0
-    rel[db[ok] == 0] = np.nan
-    rel[:, 14:] = np.nan
-    print("inside phase %s (us since phase start, SM clock): median / max over CTAs per stamp" % os.environ.get("GGB_DBG_PHASE", "30"))
-    print("   median", np.round(np.nanmedian(rel, axis=0)[:16], 2))
-    print("   max   ", np.round(np.nanmax(rel, axis=0)[:16], 2))
-    if (db[:, 15] > 0).any():
-        okw = db[:, 15] > 0
-        print("   weight wait inside the pass loop (warp 0): median %.2f us, max %.2f us over %d..%d slots" % (
-            np.median(db[okw, 14]) / 1965.0, db[okw, 14].max() / 1965.0, db[okw, 15].min(), db[okw, 15].max()))
     print("last phases:")
     for r in rows[-2:]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
