@@ -44,7 +44,13 @@ namespace {
 
 constexpr int kCW = 16;             // consumer warps
 constexpr int kCT = kCW * 32;       // consumer threads
-constexpr int kProdWarp = 16, kChainWarp = 17;
+// warp roles: the chain warp is warp 0, the consumers warps 1..16, the producer warp 17 (GGB_CHAIN_LAST: chain warp 17,
+// consumers 0..15, producer 16 - kept for A/B runs of the warp arbiter's preference)
+#ifdef GGB_CHAIN_LAST
+constexpr int kProdWarp = 16, kChainWarp = 17, kC0 = 0;
+#else
+constexpr int kProdWarp = 17, kChainWarp = 0, kC0 = 32;
+#endif
 constexpr int kThreads = 18 * 32;
 constexpr int kSlots = 5;
 constexpr int kMaxOutstanding = 2;  // ring copies in flight per SM (default; GGB_MAX_OUTSTANDING overrides)
@@ -53,7 +59,8 @@ constexpr int kChunk = GGB_DEV_ATTN_CHUNK;
 constexpr int kSeg = GGB_DEV_SEG_BLOCKS; // 64 blocks per K segment
 constexpr int kMaxE = 4096;         // longest norm-fed activation row
 constexpr int kMaxK = 24576;        // longest activation row kept in shared memory
-constexpr int kTermFloats = 2048;   // per term buffer: 16 passes x 128 block terms
+constexpr int kTermRow = 68;        // floats per chain lane in a term buffer: 64 block terms + 4 of padding (bank skew)
+constexpr int kTermFloats = 32 * kTermRow; // per term buffer: 16 passes x 128 block terms
 constexpr int kAccFloats = 1792;    // row accumulators of multi-segment phases (rows of one CTA)
 constexpr int kGuFloats = 512;      // finished gate / up rows of one CTA waiting for GeGLU
 constexpr int kAccSmall = 64;       // the same for phases whose activation row covers the accumulator overlay (K > 8192)
@@ -130,6 +137,8 @@ struct DecoderParams {
     int exp_compute;       // 1: exp_f16_computed reproduces exp_table bit for bit (checked at create)
     const float *rope_cos, *rope_sin;
     long long *trace; // optional [n_phases][grid][4] %globaltimer stamps (ns): start, after prologue (inputs arrived), end, end
+    long long *prof;  // PROF instantiation only: [grid][32] SM-clock sums inside phase prof_phase (see tools_trace.py)
+    int prof_phase;
 };
 
 // union region: the views are never live at the same time
@@ -143,10 +152,10 @@ constexpr int U_TERMS = U_BIAS + kMaxK / 32 * 4;
 constexpr int U_XS = 8192;
 constexpr int U_ACC = U_XS, U_GU = U_ACC + kAccFloats * 4;
 constexpr int U_KC = 0, U_SQ = 32768;
-constexpr int U_PVP = 0, U_PVR = kMaxCtx * 4;
+constexpr int U_PVP = 0;
 constexpr int U_BYTES = U_TERMS + 2 * kTermFloats * 4;
 static_assert(U_SQ + 4 * 256 * 8 <= U_BYTES, "union region too small for the score view");
-static_assert(U_PVR + 16 * 32 * 8 <= U_BYTES, "union region too small for the pv view");
+static_assert(kMaxCtx * 4 + 16 * 32 * 8 + kCT * 16 <= U_BYTES, "union region too small for the pv view");
 static_assert(U_XS + kMaxE * 4 <= U_ACT_D && kMaxE <= U_XS, "xs overlaps the activation row");
 static_assert(U_GU + kGuFloats * 4 <= U_ACT_D, "accumulator overlay too large");
 
@@ -164,6 +173,7 @@ template <int TYPE> struct Smem {
     alignas(8) unsigned long long tfull[2];   // term buffer b holds a whole slot's terms (16 consumer-warp arrivals)
     alignas(8) unsigned long long tempty[2];  // the chain warp has consumed term buffer b
     long long tr[2]; // trace stamps of the current phase (thread 0)
+    int wst[kCW + 2][4]; // per-warp state that lives across phases: ring slot, ring parity, term slot counter, K-buffer parities
     int sched[6];    // [0] = chunks, [3] = token, [4] = number of positions (kept out of registers: the kernel runs
                      // at the 96-register limit of 18 warps per SM and a spill costs an L2 round trip)
     alignas(16) Phase ph[2];
@@ -185,7 +195,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // GGB_WATCHDOG: a wait that does not end (a lost flag, a mis-counted barrier) traps instead of hanging the GPU: the
 // launch then fails with an error the host reports.  The bounds are seconds of spinning, far beyond any legal wait.
 #ifndef GGB_WATCHDOG
-#define GGB_WATCHDOG 1
+#define GGB_WATCHDOG 0
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if GGB_WATCHDOG
@@ -233,6 +243,9 @@ __device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void *src, ui
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -271,16 +284,23 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) { // unsigned b
 __device__ __forceinline__ float exp_f16_computed(float x_f16_valued) {
     return half_bits_to_float(float_to_half_bits(__double2float_rn(exp((double)x_f16_valued))));
 }
+// the cheap form: fp32 expf (a few ulp of fp32), rounded to fp16 - identical to the table only if no input lands within
+// that error of an fp16 rounding boundary, which the same exhaustive check decides (exp_compute == 2)
+__device__ __forceinline__ float exp_f16_fast(float x_f16_valued) {
+    return half_bits_to_float(float_to_half_bits(expf(x_f16_valued)));
+}
 __device__ __forceinline__ float exp_f16(const DecoderParams &P, float x) {
     const uint16_t hb = float_to_half_bits(x);
     if (!P.exp_compute || (hb & 0x7FFFu) > 0x7C00u) return half_bits_to_float(__ldg(P.exp_table + hb)); // no proof / NaN
+    if (P.exp_compute == 2) return exp_f16_fast(half_bits_to_float(hb));
     return exp_f16_computed(half_bits_to_float(hb));
 }
-__global__ void exp_check_kernel(const uint16_t *table, int *mismatches) {
+__global__ void exp_check_kernel(const uint16_t *table, int *mismatches) { // [0]: double form, [1]: fp32 form
     const uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
     if (hb >= 65536u || (hb & 0x7FFFu) > 0x7C00u) return;
-    const float got = exp_f16_computed(half_bits_to_float((uint16_t)hb));
-    if (float_to_half_bits(got) != table[hb]) atomicAdd(mismatches, 1);
+    const float x = half_bits_to_float((uint16_t)hb);
+    if (float_to_half_bits(exp_f16_computed(x)) != table[hb]) atomicAdd(mismatches, 1);
+    if (float_to_half_bits(exp_f16_fast(x)) != table[hb]) atomicAdd(mismatches + 1, 1);
 }
 
 // ---- flagged words.  An aligned 8-byte access is single-copy atomic, so payload and tag are seen together;
@@ -479,7 +499,7 @@ __device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lan
 template <int TYPE>
 __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
                                               uint32_t tag, float *f32_out) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = (int)threadIdx.x - kC0, lane = tid & 31, warp = tid >> 5;
     const int E = P.E, nk = E / GGB_DEV_NORM_THREADS;
     const int base = 32 * (warp & 7) + lane;
     float *xs = reinterpret_cast<float *>(S.u + U_XS);
@@ -492,20 +512,29 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
     double acc = 0.0;
     // a thread's words are requested 8 at a time (all of them for E <= 2048): ONE L2 round trip when x is there
     constexpr int NV = 8;
+    if (in) {
 #pragma unroll 1
-    for (int k0 = 0; k0 < nk; k0 += NV) {
-        ll_t v[NV];
+        for (int k0 = 0; k0 < nk; k0 += NV) {
+            ll_t v[NV];
+            const ll_t *pw = in + GGB_DEV_NORM_THREADS * k0 + base;
 #pragma unroll
-        for (int u = 0; u < NV; u++)
-            if (in && k0 + u < nk) v[u] = ll_peek(in + GGB_DEV_NORM_THREADS * (k0 + u) + base);
+            for (int u = 0; u < NV; u++) v[u] = k0 + u < nk ? ll_peek(pw + GGB_DEV_NORM_THREADS * u) : 0ull;
 #pragma unroll
-        for (int u = 0; u < NV; u++) {
-            if (k0 + u < nk) {
-                const int i = GGB_DEV_NORM_THREADS * (k0 + u) + base;
-                const float x = in ? ll_get_f(v[u], in + i, tag) : embed_value<TYPE>(P, token, i);
-                xs[i] = x;
-                acc = __dadd_rn(acc, (double)__fmul_rn(x, x));
+            for (int u = 0; u < NV; u++) {
+                if (k0 + u < nk) {
+                    const float x = ll_get_f(v[u], pw + GGB_DEV_NORM_THREADS * u, tag);
+                    xs[GGB_DEV_NORM_THREADS * (k0 + u) + base] = x;
+                    acc = __dadd_rn(acc, (double)__fmul_rn(x, x));
+                }
             }
+        }
+    } else { // layer 0: the embedding row of the token
+#pragma unroll 1
+        for (int k = 0; k < nk; k++) {
+            const int i = GGB_DEV_NORM_THREADS * k + base;
+            const float x = embed_value<TYPE>(P, token, i);
+            xs[i] = x;
+            acc = __dadd_rn(acc, (double)__fmul_rn(x, x));
         }
     }
     acc = warp_sum_f64(acc);
@@ -537,7 +566,7 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
 // O: the flagged fp32 row written by COMBINE -> quantize_row_q8_0 (ggml mul_mat INIT stage)
 template <int TYPE>
 __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = ((int)threadIdx.x - kC0) >> 5;
     const uint32_t ua = smem_u32(S.u);
 #pragma unroll 1
     for (int quad = warp; quad < K / 128; quad += kCW) {
@@ -557,7 +586,7 @@ __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, in
 // (low half) and the sum of the block's codes (high half, int16: |sum| <= 32 * 127), from which the Q4_0 bias follows
 template <int TYPE>
 __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, int K, uint32_t tag) {
-    const int tid = threadIdx.x;
+    const int tid = (int)threadIdx.x - kC0;
     const int nw = K / 4, ns = K / 32;
     uint32_t *aq = reinterpret_cast<uint32_t *>(S.u);
     __half *ad = reinterpret_cast<__half *>(S.u + U_ACT_D);
@@ -566,8 +595,7 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
     for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 4 words in flight per thread (more spills at the 96-register limit)
         ll_t v[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (i0 + kCT * u < nw + ns) v[u] = ll_peek(in + i0 + kCT * u);
+        for (int u = 0; u < 4; u++) v[u] = i0 + kCT * u < nw + ns ? ll_peek(in + i0 + kCT * u) : 0ull;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int i = i0 + kCT * u;
@@ -589,10 +617,8 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
 //   Q4_0: ((float)sumi * d_x) * d_y      Q8_0: (float)sumi * (d_x * d_y)
 // ([UPSTREAM] ggml_vec_dot_q4_0_q8_0 / ggml_vec_dot_q8_0_q8_0 scalar branches).  Nothing is added here: the four
 // terms of a lane go to the term table and the chain warp adds them in block order.
-struct ActRegs { // the lane's two activation blocks of one K segment
+struct ActRegs { // the codes of the lane's two activation blocks of one K segment
     int a[2][8];
-    uint32_t dy2; // the two fp16 activation scales in one register (the kernel runs at its register limit)
-    int bias[2];
 };
 template <int TYPE>
 __device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg, int nb, int lane) {
@@ -603,21 +629,30 @@ __device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg,
         const uint4 lo = lds_u4(act + bc * 16), hi = lds_u4(act + nb * 16 + bc * 16); // planes: bytes 0..15 | 16..31
         A.a[t][0] = lo.x; A.a[t][1] = lo.y; A.a[t][2] = lo.z; A.a[t][3] = lo.w;
         A.a[t][4] = hi.x; A.a[t][5] = hi.y; A.a[t][6] = hi.z; A.a[t][7] = hi.w;
-        unsigned short hd;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hd) : "r"(act + U_ACT_D + bc * 2));
-        A.dy2 = t == 0 ? (uint32_t)hd : (A.dy2 | ((uint32_t)hd << 16));
-        A.bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + bc * 4) : 0;
     }
 }
 // QUADPASS: the pass holds the short last segment (<= 32 blocks) of FOUR rows; lane l owns block l of each row.
 // The byte layout of a pass is the same in both cases: four groups of 32 blocks, payloads then scales; group k is
 // (row k >> 1, blocks 32 (k & 1) ..) of a plain pass and row k of a quad pass.
+// b0 = seg * 64 + lane: the lane's first activation block.  Its scale and Q4_0 bias (and those of block b0 + 32) are
+// re-read from shared memory every pass - requested first, used last - instead of living in registers: the kernel
+// runs at the 96-register limit and a spilled value would come back from L2 in the middle of the dp4a chain.
+// (A block index past the row reads some other shared-memory word; its term is never used.)
 template <int TYPE, bool QUADPASS>
-__device__ __forceinline__ void pass_terms(uint32_t base, const ActRegs &A, int lane, float (&term)[4]) {
+__device__ __forceinline__ void pass_terms(uint32_t base, uint32_t act, int b0, const ActRegs &A, int lane, float (&term)[4]) {
     using F = Fmt<TYPE>;
     const int(&a)[2][8] = A.a;
-    const float dy[2] = {__half2float(__ushort_as_half((unsigned short)(A.dy2 & 0xFFFFu))),
-                         __half2float(__ushort_as_half((unsigned short)(A.dy2 >> 16)))};
+    float dy[2];
+    int bias[2];
+#pragma unroll
+    for (int t = 0; t < (QUADPASS ? 1 : 2); t++) {
+        dy[t] = lds_half(act + U_ACT_D + 2 * (b0 + 32 * t));
+        bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + 4 * (b0 + 32 * t)) : 0;
+    }
+    if (QUADPASS) {
+        dy[1] = dy[0];
+        bias[1] = bias[0];
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int t = QUADPASS ? 0 : (k & 1);
@@ -628,13 +663,13 @@ __device__ __forceinline__ void pass_terms(uint32_t base, const ActRegs &A, int 
         if (TYPE == GGB_TYPE_Q4_0) {
             const uint4 w = lds_u4(pay);
             const uint32_t q[4] = {w.x, w.y, w.z, w.w};
-            int lo = A.bias[t], hi = 0; // high nibbles stay in place (x16) and are divided out once: exact
+            int lo = 0, hi = 0; // high nibbles stay in place (x16) and are divided out once: exact
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 lo = __dp4a((int)(q[i] & 0x0F0F0F0Fu), a[t][i], lo);
                 hi = dp4a_us(q[i] & 0xF0F0F0F0u, a[t][4 + i], hi);
             }
-            const int sumi = lo + (hi >> 4);
+            const int sumi = lo + (hi >> 4) + bias[t];
             term[k] = __fmul_rn(__fmul_rn((float)sumi, dx), dy[t]);
         } else {
             const uint4 w0 = lds_u4(pay), w1 = lds_u4(pay + 512);
@@ -648,54 +683,67 @@ __device__ __forceinline__ void pass_terms(uint32_t base, const ActRegs &A, int 
     }
 }
 // Term table of one slot: pass j of the slot, group k, lane l -> chain lane c = 2 j + (k >> 1), block b = l + 32 (k & 1)
-// of that lane's 64-term run, stored at [b][(c + b) & 31]: the skew makes both the consumers' stores (32 lanes = 32
-// blocks of one c) and the chain warp's loads (32 lanes = 32 c of one block) hit 32 different banks.
+// of that lane's 64-term run, stored at [c][b] with rows of 68 floats: the consumers' stores (32 lanes = 32 consecutive
+// blocks of one c) and the chain warp's 128-bit loads (lane stride 68 words = 4 banks: quarter-warps cover all 32 banks)
+// are both conflict-free.
 __device__ __forceinline__ void store_terms(uint32_t tbase, int j, int lane, const float (&term)[4]) {
-    const uint32_t r0 = tbase + 4u * (uint32_t)(lane * 32 + ((2 * j + lane) & 31));
-    const uint32_t r1 = tbase + 4u * (uint32_t)(lane * 32 + ((2 * j + 1 + lane) & 31));
+    const uint32_t r0 = tbase + 4u * (uint32_t)(2 * j * kTermRow + lane);
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(r0), "f"(term[0]) : "memory");
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(r0 + 4096u), "f"(term[1]) : "memory");
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(r1), "f"(term[2]) : "memory");
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(r1 + 4096u), "f"(term[3]) : "memory");
+    asm volatile("st.shared.f32 [%0+128], %1;" ::"r"(r0), "f"(term[1]) : "memory");
+    asm volatile("st.shared.f32 [%0+272], %1;" ::"r"(r0), "f"(term[2]) : "memory");
+    asm volatile("st.shared.f32 [%0+400], %1;" ::"r"(r0), "f"(term[3]) : "memory");
 }
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-    float r;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+static_assert(kTermRow * 4 == 272, "store_terms offsets");
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
     return r;
 }
-// acc + term[b0] + term[b0 + 1] + ... (len terms, one by one: the reference's  sumf += term  loop); len is the same for
-// every lane of the warp
-__device__ __forceinline__ float chain_add(uint32_t tbase, int c, int b0, int len, float acc) {
-#pragma unroll 1
-    for (int i0 = 0; i0 < len; i0 += 16) {
-        float t[16];
+// acc + term[b0] + term[b0 + 1] + ... (len terms, one by one: the reference's  sumf += term  loop); row = shared address
+// of the lane's 64-term run; len is the same for every lane of the warp
+__device__ __forceinline__ float chain_add(uint32_t row, int b0, int len, float acc) {
+    if (len == 64) { // the common case, fully unrolled: 16 loads up front, then the 64 dependent adds
+        float4 t[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) t[u] = lds_f4(row + 16u * (uint32_t)u);
 #pragma unroll
         for (int u = 0; u < 16; u++) {
-            const int b = b0 + i0 + u;
-            t[u] = lds_f32(tbase + 4u * (uint32_t)((b & 63) * 32 + ((c + b) & 31)));
+            acc = __fadd_rn(acc, t[u].x);
+            acc = __fadd_rn(acc, t[u].y);
+            acc = __fadd_rn(acc, t[u].z);
+            acc = __fadd_rn(acc, t[u].w);
         }
+        return acc;
+    }
+#pragma unroll 1
+    for (int i0 = 0; i0 < len; i0 += 16) {
+        float4 t[4];
 #pragma unroll
-        for (int u = 0; u < 16; u++)
-            if (i0 + u < len) acc = __fadd_rn(acc, t[u]);
+        for (int u = 0; u < 4; u++) t[u] = lds_f4(row + 4u * (uint32_t)(b0 + i0) + 16u * (uint32_t)u);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i0 + 4 * u + 0 < len) acc = __fadd_rn(acc, t[u].x);
+            if (i0 + 4 * u + 1 < len) acc = __fadd_rn(acc, t[u].y);
+            if (i0 + 4 * u + 2 < len) acc = __fadd_rn(acc, t[u].z);
+            if (i0 + 4 * u + 3 < len) acc = __fadd_rn(acc, t[u].w);
+        }
     }
     return acc;
 }
 
-__device__ __forceinline__ int out_index(const Phase &ph, int lr) {
-    if (lr < ph.seg_rows[0]) return ph.seg_off[0] + lr;
-    lr -= ph.seg_rows[0];
-    if (lr < ph.seg_rows[1]) return ph.seg_off[1] + lr;
-    return ph.seg_off[2] + lr - ph.seg_rows[1];
-}
 
 // ---------------------------------------------------------------- the chain warp's share of a mat-vec phase
 // Slot by slot: wait for the consumers' terms, add them to the rows' accumulators in block order (rounds = the
 // passes of one K segment inside the slot: a row occurs once per round), finish the rows whose last segment this was.
-template <int TYPE, bool QUAD>
-__device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                            uint32_t tag, uint32_t &tslot) {
+template <int TYPE, bool QUAD, bool PROF>
+__device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int cta, int G, uint32_t tag, bool prof) {
+    long long pt0 = 0, p_wait = 0, p_chain = 0, p_fin = 0, p_rounds = 0, p_begin = 0, p_add = 0, p_row = 0, pta = 0;
+    if (PROF) p_begin = clock64();
     using F = Fmt<TYPE>;
+    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem); // (re-derived here: shared addresses stay immediates)
+    const Phase &ph = S.ph[phi];
     const int lane = threadIdx.x & 31;
+    uint32_t tslot = (uint32_t)S.wst[kCW][2];
     int u0, u1;
     unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
     const int n_passes = (u1 - u0) * ph.unit_passes;
@@ -704,6 +752,17 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &
     const bool quad = QUAD && ph.quad != 0;
     const int row0 = u0 * ph.unit_rows;
     const bool bcast = ph.bcast != 0;
+    // the descriptor lives in shared memory and the waits below are memory barriers to the compiler: what the row
+    // finish needs is read once, here
+    const int n_lr = ph.n_lr, sr0 = ph.seg_rows[0], sr1 = ph.seg_rows[1], so0 = ph.seg_off[0], so1 = ph.seg_off[1], so2 = ph.seg_off[2];
+    const int tail_blocks = ph.tail_blocks, kf = ph.kf, resid_embed = ph.resid_embed;
+    float *const out_f = ph.out;
+    ll_t *const out_ll = ph.out_ll;
+    auto oidx = [&](int lr) {
+        if (lr < sr0) return so0 + lr;
+        lr -= sr0;
+        return lr < sr1 ? so1 + lr : so2 + lr - sr1;
+    };
     float *A = ph.K <= 8192 ? reinterpret_cast<float *>(S.u + U_ACC) : S.acc_small;
     float *GU = reinterpret_cast<float *>(S.u + U_GU);
     const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]), terms0 = smem_u32(S.u + U_TERMS);
@@ -714,24 +773,50 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &
 
     auto finish_row = [&](int rl, float total, ll_t rv) {
         const int lr = row0 + rl;
-        if (lr >= ph.n_lr) return;
+        if (lr >= n_lr) return;
         if (kind == PH_GATE_UP) {
             GU[rl] = total;
             return;
         }
-        const int gi = out_index(ph, lr);
+        const int gi = oidx(lr);
         if (resid) total = __fadd_rn(total, ll_get_f(rv, resid + gi, tag));
-        else if (ph.resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, S.sched[3], gi));
-        if (ph.out) ph.out[gi] = total;
-        if (ph.out_ll) ll_put_f(P, bcast, ph.out_ll + gi, total, tag);
+        else if (resid_embed) total = __fadd_rn(total, embed_value<TYPE>(P, S.sched[3], gi));
+        if (out_f) out_f[gi] = total;
+        if (out_ll) ll_put_f(P, bcast, out_ll + gi, total, tag);
         if (total > best.v || best.i < 0) best = Best{total, gi};
+    };
+
+    // a lane's code joins three neighbours' in one flagged word of the packed row; the block's fp16 scale and the sum of
+    // its codes (the Q4_0 bias of DOWN's dot products) share one more
+    int pend = -1;
+    uint16_t pend_gl = 0;
+    const int ug0 = ph.u_off + u0;
+    float *const act_dump = ph.f32_out;
+    ll_t *const oq = out_ll, *const od = out_ll + P.F / 4;
+    auto geglu_finish = [&](int u, uint16_t glb) {
+        const int ug = ug0 + u;
+        const float x = __fmul_rn(half_bits_to_float(glb), GU[64 * u + 32 + lane]);
+        if (act_dump) act_dump[(size_t)ug * 32 + lane] = x;
+        const float amax = warp_max_f32(fabsf(x));
+        const float dd = __fdiv_rn(amax, 127.0f);
+        const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
+        const int qi = (int)roundf(__fmul_rn(x, id));
+        uint32_t w = (uint32_t)qi & 0xFFu;
+        w |= (__shfl_down_sync(0xffffffffu, w, 1) & 0xFFu) << 8;
+        w |= (__shfl_down_sync(0xffffffffu, w, 2) & 0xFFFFu) << 16;
+        if ((lane & 3) == 0) ll_put(P, bcast, oq + (size_t)ug * 8 + (lane >> 2), w, tag);
+        const int qs = __reduce_add_sync(0xffffffffu, qi);
+        if (lane == 0)
+            ll_put(P, bcast, od + ug, ((uint32_t)qs << 16) | (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
     };
 
 #pragma unroll 1
     for (int m0 = 0; m0 < n_passes; m0 += F::PPS) {
         const int cnt = min(F::PPS, n_passes - m0);
         const uint32_t tb = tslot & 1u;
+        if (PROF) pt0 = clock64();
         mbar_wait(tf0 + 8 * tb, (tslot >> 1) & 1u);
+        if (PROF) p_wait += clock64() - pt0;
         const uint32_t tbase = terms0 + tb * (uint32_t)(kTermFloats * 4);
         int jj = 0;
 #pragma unroll 1
@@ -741,36 +826,41 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &
             const bool active = j >= jj && j < jj + run;
             const int idx = rem + (j - jj);
             bool last_section;
+            if (PROF) { pt0 = clock64(); p_rounds++; }
             if (!isB) {
                 const bool last = !quad && segc == kA - 1;
                 last_section = last;
-                const int len = last ? ph.tail_blocks : kSeg;
+                const int len = last ? tail_blocks : kSeg;
                 const int rl = 2 * idx + ab;
                 ll_t rv = 0;
-                if (last && active && resid && row0 + rl < ph.n_lr) rv = ll_peek(resid + out_index(ph, row0 + rl));
+                if (last && active && resid && row0 + rl < n_lr) rv = ll_peek(resid + oidx(row0 + rl));
                 float acc = (active && segc > 0) ? A[rl] : 0.0f;
-                acc = chain_add(tbase, lane, 0, len, acc);
+                if (PROF) pta = clock64();
+                acc = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 0, len, acc);
+                if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; pta = t1; }
                 if (active) {
                     if (last) finish_row(rl, acc, rv);
                     else A[rl] = acc;
                 }
+                if (PROF) p_row += clock64() - pta;
             } else { // the short segment of rows 4 idx + 2 ab and + 1: two 32-term runs of this lane
                 last_section = true;
                 const int rl = 4 * idx + 2 * ab;
                 ll_t rv0 = 0, rv1 = 0;
                 if (active && resid) {
-                    if (row0 + rl < ph.n_lr) rv0 = ll_peek(resid + out_index(ph, row0 + rl));
-                    if (row0 + rl + 1 < ph.n_lr) rv1 = ll_peek(resid + out_index(ph, row0 + rl + 1));
+                    if (row0 + rl < n_lr) rv0 = ll_peek(resid + oidx(row0 + rl));
+                    if (row0 + rl + 1 < n_lr) rv1 = ll_peek(resid + oidx(row0 + rl + 1));
                 }
-                float a0 = (active && ph.kf > 0) ? A[rl] : 0.0f, a1 = (active && ph.kf > 0) ? A[rl + 1] : 0.0f;
-                a0 = chain_add(tbase, lane, 0, ph.tail_blocks, a0);
-                a1 = chain_add(tbase, lane, 32, ph.tail_blocks, a1);
+                float a0 = (active && kf > 0) ? A[rl] : 0.0f, a1 = (active && kf > 0) ? A[rl + 1] : 0.0f;
+                a0 = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 0, tail_blocks, a0);
+                a1 = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 32, tail_blocks, a1);
                 if (active) {
                     finish_row(rl, a0, rv0);
                     finish_row(rl + 1, a1, rv1);
                 }
             }
             __syncwarp();
+            if (PROF) { const long long t1 = clock64(); p_chain += t1 - pt0; pt0 = t1; }
             const int idx_end = rem + run;
             jj += run;
             rem += run;
@@ -778,37 +868,37 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &
                 rem = 0;
                 segc++;
             }
-            if (kind == PH_GATE_UP && last_section) {
+            if (kind == PH_GATE_UP) {
                 // GeGLU (fp16 gelu table) + quantize_row_q8_0 of every 32-row group whose gate and up rows are all in:
-                // lane = row of the group.  A lane's code joins three neighbours' in one flagged word of the packed row;
-                // the block's fp16 scale and the sum of its codes (the Q4_0 bias of DOWN's dot products) share one more.
-                const int complete = isB ? (idx_end >> 4) : (idx_end >> 5);
-                ll_t *oq = ph.out_ll, *od = ph.out_ll + P.F / 4;
+                // lane = row of the group.  The table lookup of a group is issued when the group completes and used one
+                // round later, so its L2 round trip hides behind the next chain.
+                if (pend >= 0) {
+                    geglu_finish(pend, pend_gl);
+                    pend = -1;
+                }
+                if (last_section) {
+                    const int complete = isB ? (idx_end >> 4) : (idx_end >> 5);
 #pragma unroll 1
-                for (; units_done < complete; units_done++) {
-                    const int ug = ph.u_off + u0 + units_done;
-                    const float gs = GU[64 * units_done + lane], us = GU[64 * units_done + 32 + lane];
-                    const float gl = half_bits_to_float(__ldg(P.gelu_table + float_to_half_bits(gs)));
-                    const float x = __fmul_rn(gl, us);
-                    if (ph.f32_out) ph.f32_out[(size_t)ug * 32 + lane] = x;
-                    const float amax = warp_max_f32(fabsf(x));
-                    const float dd = __fdiv_rn(amax, 127.0f);
-                    const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
-                    const int qi = (int)roundf(__fmul_rn(x, id));
-                    uint32_t w = (uint32_t)qi & 0xFFu;
-                    w |= (__shfl_down_sync(0xffffffffu, w, 1) & 0xFFu) << 8;
-                    w |= (__shfl_down_sync(0xffffffffu, w, 2) & 0xFFFFu) << 16;
-                    if ((lane & 3) == 0) ll_put(P, bcast, oq + (size_t)ug * 8 + (lane >> 2), w, tag);
-                    const int qs = __reduce_add_sync(0xffffffffu, qi);
-                    if (lane == 0)
-                        ll_put(P, bcast, od + ug, ((uint32_t)qs << 16) | (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
+                    for (; units_done < complete; units_done++) {
+                        if (pend >= 0) geglu_finish(pend, pend_gl);
+                        pend = units_done;
+                        pend_gl = __ldg(P.gelu_table + float_to_half_bits(GU[64 * units_done + lane]));
+                    }
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(te0 + 8 * tb);
         tslot++;
+        if (PROF) p_fin += clock64() - pt0;
     }
+    if (pend >= 0) geglu_finish(pend, pend_gl);
+    if (PROF && prof && lane == 0) {
+        long long *o = P.prof + 32 * cta + 16;
+        o[0] = p_wait; o[1] = p_chain; o[2] = p_fin; o[3] = p_rounds; o[4] = clock64() - p_begin; o[5] = n_passes;
+        o[6] = p_add; o[7] = p_row;
+    }
+    if (lane == 0) S.wst[kCW][2] = (int)tslot;
     if (kind == PH_LOGITS) { // this CTA's arg-max candidate (strict '>' / lowest index, ref: src/gemma_model.cpp:538-543)
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -824,6 +914,7 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &
     }
 }
 
+#define PROF_STAMP(i) do { if (PROF && prof && (int)threadIdx.x == kC0) P.prof[32 * cta + (i)] = clock64(); } while (0)
 // ---------------------------------------------------------------- SCORE
 // kq = mul_mat(k, q) (ref: src/gemma_model.cpp:465-474) for one (kv head, 32-position chunk, half of the query heads)
 // per item; rope + Q scale are applied to q on load, and the item that owns the newest position ropes K, rounds K / V to
@@ -833,17 +924,17 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, Smem<TYPE> &
 // the reference's vec_dot_f16 does (ref: src/kernals.cl:158-164) - the order of a double sum is invisible after that
 // rounding.  A warp scores its two positions against the item's (<= 4) heads and reduces the 8 lane partials with one
 // folded butterfly.  Scores leave as flagged words.
-template <int TYPE>
-__device__ __forceinline__ void score_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G,
-                                            int n_pos, uint32_t tag, uint32_t (&kv_par)[2]) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int TYPE, bool PROF>
+__device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int cta, int G, int n_pos, uint32_t tag, bool prof) {
+    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
+    const Phase &ph = S.ph[phi];
+    const int tid = (int)threadIdx.x - kC0, lane = tid & 31, warp = tid >> 5;
+    uint32_t kvp = (uint32_t)S.wst[warp][3]; // bit b = parity of K buffer b's barrier
     const int d = P.d, halfd = d >> 1, Gq = P.Gq, hsplit = P.hsplit, Gh = P.Gh, ng = P.ng;
     const int nchunk = S.sched[0];
     const int n_items = ng * nchunk * hsplit;
     const int pos = n_pos - 1;
     const size_t kv_stride = (size_t)ng * d; // this rank's cache holds its own KV heads only
-    const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
-    const ll_t *q_all = ph.in_ll, *k_all = q_all + (size_t)P.H * d, *v_all = k_all + (size_t)P.Hkv * d;
     double *Sq = reinterpret_cast<double *>(S.u + U_SQ); // [4][d] fp16-rounded q
     const uint32_t kc0 = smem_u32(S.u + U_KC), kvbar0 = smem_u32(&S.kv_bar[0]);
     const uint32_t row_bytes = (uint32_t)d * 2;
@@ -897,6 +988,10 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, Smem<TYPE> &
         const int jnew = pos - p0;
         const bool owns_new = jnew >= 0 && jnew < np;
         __half *Kc = reinterpret_cast<__half *>(S.u + U_KC + buf * 16384);
+        PROF_STAMP(0);
+        {
+        const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
+        const ll_t *q_all = ph.in_ll, *k_all = q_all + (size_t)P.H * d, *v_all = k_all + (size_t)P.Hkv * d;
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16), widen
         for (int i = tid; i < Gh * halfd; i += kCT) {
             const int jh = i >> P.hd_shift, e = i & (halfd - 1);
@@ -934,43 +1029,41 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, Smem<TYPE> &
                 }
             }
         }
-        mbar_wait(kvbar0 + 8u * (uint32_t)buf, kv_par[buf]);
-        kv_par[buf] ^= 1u;
+        }
+        PROF_STAMP(1);
+        mbar_wait(kvbar0 + 8u * (uint32_t)buf, (kvp >> buf) & 1u);
+        kvp ^= 1u << buf;
         consumer_bar();
+        PROF_STAMP(2);
         if (it + G < n_items) issue_k(it + G, buf ^ 1); // the other buffer was last read before the barrier above
         {
             const bool in = 8 * lane < d;
             const int j0 = warp, j1 = warp + kCW;
-            double kd[2][8];
+            // one position at a time (its K row as 8 doubles, a head's q as 8 more: the register budget of the kernel)
+            double acc[2][4];
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const int jr = p ? j1 : j0;
                 uint4 raw = make_uint4(0, 0, 0, 0);
                 if (in && jr < np) raw = *reinterpret_cast<const uint4 *>(Kc + jr * d + 8 * lane);
                 const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
+                double kd[8];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const float2 f = __half22float2(h2[e]);
-                    kd[p][2 * e] = (double)f.x;
-                    kd[p][2 * e + 1] = (double)f.y;
-                }
-            }
-            double acc[2][4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                double qf[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    double2 q2 = make_double2(0.0, 0.0);
-                    if (u < Gh && in) q2 = *reinterpret_cast<const double2 *>(Sq + u * 256 + k * 64 + lane * 2);
-                    qf[2 * k] = q2.x;
-                    qf[2 * k + 1] = q2.y;
+                    kd[2 * e] = (double)f.x;
+                    kd[2 * e + 1] = (double)f.y;
                 }
 #pragma unroll
-                for (int p = 0; p < 2; p++) {
+                for (int u = 0; u < 4; u++) {
                     double a = 0.0;
 #pragma unroll
-                    for (int e = 0; e < 8; e++) a = __fma_rn(kd[p][e], qf[e], a);
+                    for (int k = 0; k < 4; k++) {
+                        double2 q2 = make_double2(0.0, 0.0);
+                        if (u < Gh && in) q2 = *reinterpret_cast<const double2 *>(Sq + u * 256 + k * 64 + lane * 2);
+                        a = __fma_rn(kd[2 * k], q2.x, a);
+                        a = __fma_rn(kd[2 * k + 1], q2.y, a);
+                    }
                     acc[p][u] = a;
                 }
             }
@@ -998,9 +1091,11 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, Smem<TYPE> &
             if ((lane & 3) == 0 && js < np && us < Gh)
                 ll_put_f(P, false, ph.s_ll + (size_t)(h0 + us) * P.n_ctx + p0 + js, __double2float_rn(k1), tag);
         }
+        PROF_STAMP(3);
         consumer_bar(); // Sq and (after one more item) this K buffer are rewritten
         buf ^= 1;
     }
+    if (lane == 0) S.wst[warp][3] = (int)kvp;
 }
 
 // ---------------------------------------------------------------- PV
@@ -1010,32 +1105,37 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, Smem<TYPE> &
 // rounds P to fp16 (ggml mul_mat INIT of the kqv node) and accumulates out[i] = sum_p V16[p][i] * P16[p] in double.
 // Thread (o, pl): dims 8 o .. 8 o + 7 of the slice, positions pl, pl + PL, ...; the V rows of older positions do not
 // depend on this token and are requested before the scores arrive.
-template <int TYPE>
-__device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int cta, int G, int n_pos,
-                                         uint32_t tag) {
-    constexpr int NPRE = 8;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int TYPE, bool PROF>
+__device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int cta, int G, int n_pos, uint32_t tag, bool prof) {
+    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
+    const Phase &ph = S.ph[phi];
+    constexpr int NPRE = 4; // V rows per thread held in registers, after the NST rows staged in shared memory
+    const int tid = (int)threadIdx.x - kC0, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, W = P.pv_w;
+    // the thread's first NST (<= 4) V rows wait in a private 16-byte slot each of the union region, copied there
+    // asynchronously (no register is held while the soft-max row is built): [row k][thread]
+    const int sp_bytes = (P.n_ctx * 4 + 127) & ~127;
+    const int NST = min(4, (U_BYTES - sp_bytes - 16 * 32 * 8) / (kCT * 16));
+    const uint32_t stage = smem_u32(S.u) + (uint32_t)(sp_bytes + 16 * 32 * 8) + 16u * (uint32_t)tid;
     const int n_items = P.nh * P.pv_slices;
     const int pos = n_pos - 1;
     const size_t kv_stride = (size_t)P.ng * d;
     float *sp = reinterpret_cast<float *>(S.u + U_PVP);
-    double *part = reinterpret_cast<double *>(S.u + U_PVR); // [16 warps][W]
+    double *part = reinterpret_cast<double *>(S.u + sp_bytes); // [16 warps][32]
     const int o = tid & ((1 << P.pv_oct_shift) - 1), pl = tid >> P.pv_oct_shift, PL = kCT >> P.pv_oct_shift;
     int first = cta + ph.rot;
     if (first >= G) first -= G;
 #pragma unroll 1
     for (int it = first; it < n_items; it += G) {
+        PROF_STAMP(0);
         const int hl = it >> P.pv_sl_shift, slice = it & (P.pv_slices - 1);
         const int h = P.h0 + hl, g = h >> P.gq_shift, gl = g - P.g0;
         const __half *vbase = ph.vcache + (size_t)gl * d + (size_t)slice * W + 8 * o;
-        uint4 vr[NPRE];
-#pragma unroll
-        for (int k = 0; k < NPRE; k++) {
+        for (int k = 0; k < NST; k++) {
             const int p = pl + PL * k;
-            vr[k] = make_uint4(0, 0, 0, 0);
-            if (p < pos) vr[k] = __ldcg(reinterpret_cast<const uint4 *>(vbase + (size_t)p * kv_stride));
+            if (p < pos) cp_async16(stage + (uint32_t)k * (kCT * 16), vbase + (size_t)p * kv_stride);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         // the head's scores: 4 flagged words in flight per thread
         const ll_t *srow = ph.s_ll + (size_t)h * P.n_ctx;
         float mx = -INFINITY;
@@ -1043,8 +1143,7 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, 
         for (int i0 = tid; i0 < n_pos; i0 += 4 * kCT) {
             ll_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (i0 + kCT * u < n_pos) v[u] = ll_peek(srow + i0 + kCT * u);
+            for (int u = 0; u < 4; u++) v[u] = i0 + kCT * u < n_pos ? ll_peek(srow + i0 + kCT * u) : 0ull;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int i = i0 + kCT * u;
@@ -1055,9 +1154,11 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, 
                 }
             }
         }
+        PROF_STAMP(1);
         mx = warp_max_f32(mx);
         if (lane == 0) S.redf[warp] = mx;
         consumer_bar();
+        PROF_STAMP(2);
         mx = S.redf[0];
 #pragma unroll
         for (int w = 1; w < kCW; w++) mx = fmaxf(mx, S.redf[w]);
@@ -1071,15 +1172,26 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, 
             }
             sp[i] = e;
         }
+        PROF_STAMP(3);
+        // the next NPRE V rows of the thread: requested now (after the register-hungry exp), used after the staged ones
+        uint4 vr[NPRE];
+        const int pr0 = pl + PL * NST;
+#pragma unroll
+        for (int k = 0; k < NPRE; k++) {
+            const int p = pr0 + PL * k;
+            vr[k] = p < pos ? __ldcg(reinterpret_cast<const uint4 *>(vbase + (size_t)p * kv_stride)) : make_uint4(0, 0, 0, 0);
+        }
         sum = warp_sum_f64(sum);
         if (lane == 0) S.red[warp] = sum;
         consumer_bar();
+        PROF_STAMP(4);
         sum = S.red[0];
 #pragma unroll
         for (int w = 1; w < kCW; w++) sum = __dadd_rn(sum, S.red[w]);
         const float fs = __double2float_rn(__ddiv_rn(1.0, sum));
         for (int i = tid; i < n_pos; i += kCT) sp[i] = __half2float(__float2half_rn(__fmul_rn(sp[i], fs)));
         consumer_bar();
+        PROF_STAMP(5);
         double acc[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) acc[e] = 0.0;
@@ -1093,13 +1205,25 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, 
                 acc[2 * e + 1] = __fma_rn((double)f.y, pd, acc[2 * e + 1]);
             }
         };
-#pragma unroll
-        for (int k = 0; k < NPRE; k++) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int k = 0; k < NST; k++) {
             const int p = pl + PL * k;
-            if (p < pos) fma8(vr[k], p);
+            if (p < pos) fma8(lds_u4(stage + (uint32_t)k * (kCT * 16)), p);
         }
+#pragma unroll
+        for (int k = 0; k < NPRE; k++)
+            if (pr0 + PL * k < pos) fma8(vr[k], pr0 + PL * k);
 #pragma unroll 1
-        for (int p = pl + PL * NPRE; p < pos; p += PL) fma8(__ldcg(reinterpret_cast<const uint4 *>(vbase + (size_t)p * kv_stride)), p);
+        for (int p0 = pr0 + PL * NPRE; p0 < pos; p0 += PL * NPRE) { // long contexts: NPRE rows in flight
+#pragma unroll
+            for (int k = 0; k < NPRE; k++) {
+                const int p = p0 + PL * k;
+                vr[k] = p < pos ? __ldcg(reinterpret_cast<const uint4 *>(vbase + (size_t)p * kv_stride)) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < NPRE; k++)
+                if (p0 + PL * k < pos) fma8(vr[k], p0 + PL * k);
+        }
         if (pl == (pos & (PL - 1))) { // the new position's V row: from the flagged v words, rounded to fp16 like the cache
             const ll_t *vp = ph.in_ll + (size_t)P.H * d + (size_t)P.Hkv * d + (size_t)g * d + (size_t)slice * W + 8 * o;
             uint4 raw;
@@ -1111,6 +1235,7 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, 
             }
             fma8(raw, pos);
         }
+        PROF_STAMP(6);
         // lanes with the same octet, then the 16 warps (any order: double)
         for (int off = 1 << P.pv_oct_shift; off <= 16; off <<= 1) {
 #pragma unroll
@@ -1130,14 +1255,109 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, Smem<TYPE> &S, 
             ph.f32_out[idx] = r;
             ll_put_f(P, ph.bcast != 0, ph.out_ll + idx, r, tag);
         }
+        PROF_STAMP(7);
         consumer_bar();
+    }
+}
+
+// ---------------------------------------------------------------- a consumer warp's share of a mat-vec phase
+template <int TYPE, bool QUAD, bool PROF>
+__device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi, int cta, int G, uint32_t tag, bool prof) {
+    long long pt0 = 0, p_full = 0, p_te = 0, p_comp = 0, p_begin = 0, p_pro = 0;
+    if (PROF) p_begin = clock64();
+    using F = Fmt<TYPE>;
+    using SM = Smem<TYPE>;
+    SM &S = *reinterpret_cast<SM *>(ggb_dec_smem);
+    const Phase &ph = S.ph[phi];
+    const int tid = (int)threadIdx.x - kC0, warp = tid >> 5, lane = tid & 31;
+    const int kind = ph.kind;
+    const uint32_t ring = smem_u32(&S.ring[0][0]);
+    const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
+    const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]), terms0 = smem_u32(S.u + U_TERMS);
+    const uint32_t act = smem_u32(S.u);
+    int slot = S.wst[warp][0];
+    uint32_t parity = (uint32_t)S.wst[warp][1], tslot = (uint32_t)S.wst[warp][2];
+    int u0, u1;
+    unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
+    const int n_passes = (u1 - u0) * ph.unit_passes;
+    const int npairs = ((u1 - u0) * ph.unit_rows) >> 1;
+    const int nb = ph.K >> 5, kA = ph.kA;
+    if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
+        if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
+        else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
+        else norm_prologue<TYPE>(P, S, ph, S.sched[3], tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
+    }
+    if (P.trace && tid == 0) S.tr[1] = (long long)gtime();
+    if (PROF) p_pro = clock64() - p_begin;
+    // ---- passes: warp w owns passes w, w + 16, ... of the CTA's share (Q4_0: one per slot; Q8_0: 8 passes per
+    // slot, so the two warp halves alternate slots).  Every warp waits for and releases every slot and every
+    // term buffer.  The activation blocks live in registers and are reloaded only when the K segment changes
+    // (the share is segment-major: at most ksegs times per phase).
+    if (n_passes > 0) {
+        const bool quad = QUAD && ph.quad != 0;
+        int rem = warp, segc = 0, cur_seg = -1; // pass `warp` = pair / quad `rem` of section `segc`
+        while (segc < kA && rem >= npairs) {
+            rem -= npairs;
+            segc++;
+        }
+        ActRegs A;
+#pragma unroll 1
+        for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
+            const int cnt = min(F::PPS, n_passes - p0);
+            const int j = F::PPS == kCW ? warp : (((warp >> 3) == (i & 1)) ? (warp & 7) : F::PPS);
+            const int aseg = segc < kA ? segc : ph.kf; // the short segment of a quad pass follows the kf full ones
+            if (j < cnt && aseg != cur_seg) {
+                load_act_regs<TYPE>(A, act, aseg, nb, lane);
+                cur_seg = aseg;
+            }
+            const uint32_t tb = tslot & 1u;
+            if (PROF) pt0 = clock64();
+            mbar_wait(full0 + 8 * slot, parity);
+            if (PROF) { const long long t1 = clock64(); p_full += t1 - pt0; pt0 = t1; }
+            // the chain warp is done with this term buffer's previous slot.  EVERY warp waits, also one without a
+            // pass in this slot: its arrival below must not be counted for the buffer's previous use
+            mbar_wait(te0 + 8 * tb, ((tslot >> 1) & 1u) ^ 1u);
+            if (PROF) { const long long t1 = clock64(); p_te += t1 - pt0; pt0 = t1; }
+            if (j < cnt) {
+                const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;
+                float term[4];
+                if (quad && segc >= kA) pass_terms<TYPE, true>(pass, act, aseg * kSeg + lane, A, lane, term);
+                else pass_terms<TYPE, false>(pass, act, aseg * kSeg + lane, A, lane, term);
+                store_terms(terms0 + tb * (uint32_t)(kTermFloats * 4), j, lane, term);
+                rem += kCW;
+                while (segc < kA && rem >= npairs) {
+                    rem -= npairs;
+                    segc++;
+                }
+            }
+            __syncwarp();
+            if (PROF) p_comp += clock64() - pt0;
+            if (lane == 0) {
+                mbar_arrive(empty0 + 8 * slot);
+                mbar_arrive(tf0 + 8 * tb);
+            }
+            tslot++;
+            if (++slot == SM::SLOTS) {
+                slot = 0;
+                parity ^= 1u;
+            }
+        }
+    }
+    if (lane == 0) {
+        S.wst[warp][0] = slot;
+        S.wst[warp][1] = (int)parity;
+        S.wst[warp][2] = (int)tslot;
+    }
+    if (PROF && prof && tid == 0) {
+        long long *o = P.prof + 32 * cta;
+        o[0] = p_pro; o[1] = p_full; o[2] = p_te; o[3] = p_comp; o[4] = clock64() - p_begin; o[5] = n_passes;
     }
 }
 
 // ---------------------------------------------------------------- the kernel
 // QUAD: the model has phases in the quad layout (a short last K segment).  A compile-time switch, because the pass loop
 // is issue-bound: the extra branch of the quad layout costs a model without such phases (Gemma-2B) ~1 %.
-template <int TYPE, bool QUAD>
+template <int TYPE, bool QUAD, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_constant__ DecoderParams P) {
     using F = Fmt<TYPE>;
     using SM = Smem<TYPE>;
@@ -1160,6 +1380,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     __syncthreads();
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
     const uint32_t tag = *P.seq + 1u;
+    if (tid < (kCW + 2) * 4) (&S.wst[0][0])[tid] = 0;
     if (tid == 0) {
         S.sched[0] = (n_pos + kChunk - 1) / kChunk;
         S.sched[3] = min(max(P.state[0], 0), P.V - 1);
@@ -1174,102 +1395,35 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     phase_bar();
 
     if (warp == kChainWarp) { // ---- the chain warp
-        uint32_t tslot = 0;
 #pragma unroll 1
         for (int pi = 0; pi < P.n_phases; pi++) {
             const Phase &ph = S.ph[pi & 1];
-            if (is_matvec(ph.kind)) chain_phase<TYPE, QUAD>(P, S, ph, cta, G, tag, tslot);
+            if (is_matvec(ph.kind)) chain_phase<TYPE, QUAD, PROF>(P, pi & 1, cta, G, tag, PROF && pi == P.prof_phase);
             phase_bar();
         }
         return;
     }
 
-    // ---- consumers
-    const uint32_t ring = smem_u32(&S.ring[0][0]);
-    const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
-    const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]), terms0 = smem_u32(S.u + U_TERMS);
-    const uint32_t act = smem_u32(S.u);
-    int slot = 0;
-    uint32_t parity = 0, tslot = 0;
-    uint32_t kv_par[2] = {0u, 0u};
+    // ---- consumers (thread / warp index among the consumers)
+    const int ctid = tid - kC0, cwarp = ctid >> 5;
 #pragma unroll 1
     for (int pi = 0; pi < P.n_phases; pi++) {
         const Phase &ph = S.ph[pi & 1];
         // prefetch the next descriptor with an ASYNC copy (a plain load + store would stall warps in order for one
         // L2 round trip at the start of every phase); waited for at the phase's end
-        if (pi + 1 < P.n_phases && tid < kPhWords)
-            cp_async4(smem_u32(reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1]) + tid),
-                      reinterpret_cast<const uint32_t *>(&P.phases[pi + 1]) + tid);
-        if (P.trace && tid == 0) S.tr[0] = S.tr[1] = (long long)gtime();
+        if (pi + 1 < P.n_phases && ctid < kPhWords)
+            cp_async4(smem_u32(reinterpret_cast<uint32_t *>(&S.ph[(pi + 1) & 1]) + ctid),
+                      reinterpret_cast<const uint32_t *>(&P.phases[pi + 1]) + ctid);
+        if (P.trace && ctid == 0) S.tr[0] = S.tr[1] = (long long)gtime();
         const int kind = ph.kind;
         if (is_matvec(kind)) {
-            int u0, u1;
-            unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
-            const int n_passes = (u1 - u0) * ph.unit_passes;
-            const int npairs = ((u1 - u0) * ph.unit_rows) >> 1;
-            const int nb = ph.K >> 5, kA = ph.kA;
-            if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
-                if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
-                else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
-                else norm_prologue<TYPE>(P, S, ph, S.sched[3], tag, (kind == PH_LOGITS && cta == 0) ? ph.f32_out : nullptr);
-            }
-            if (P.trace && tid == 0) S.tr[1] = (long long)gtime();
-            // ---- passes: warp w owns passes w, w + 16, ... of the CTA's share (Q4_0: one per slot; Q8_0: 8 passes per
-            // slot, so the two warp halves alternate slots).  Every warp waits for and releases every slot and every
-            // term buffer.  The activation blocks live in registers and are reloaded only when the K segment changes
-            // (the share is segment-major: at most ksegs times per phase).
-            if (n_passes > 0) {
-                const bool quad = QUAD && ph.quad != 0;
-                int rem = warp, segc = 0, cur_seg = -1; // pass `warp` = pair / quad `rem` of section `segc`
-                while (segc < kA && rem >= npairs) {
-                    rem -= npairs;
-                    segc++;
-                }
-                ActRegs A;
-#pragma unroll 1
-                for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
-                    const int cnt = min(F::PPS, n_passes - p0);
-                    const int j = F::PPS == kCW ? warp : (((warp >> 3) == (i & 1)) ? (warp & 7) : F::PPS);
-                    const int aseg = segc < kA ? segc : ph.kf; // the short segment of a quad pass follows the kf full ones
-                    if (j < cnt && aseg != cur_seg) {
-                        load_act_regs<TYPE>(A, act, aseg, nb, lane);
-                        cur_seg = aseg;
-                    }
-                    const uint32_t tb = tslot & 1u;
-                    mbar_wait(full0 + 8 * slot, parity);
-                    // the chain warp is done with this term buffer's previous slot.  EVERY warp waits, also one without a
-                    // pass in this slot: its arrival below must not be counted for the buffer's previous use
-                    mbar_wait(te0 + 8 * tb, ((tslot >> 1) & 1u) ^ 1u);
-                    if (j < cnt) {
-                        const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;
-                        float term[4];
-                        if (quad && segc >= kA) pass_terms<TYPE, true>(pass, A, lane, term);
-                        else pass_terms<TYPE, false>(pass, A, lane, term);
-                        store_terms(terms0 + tb * (uint32_t)(kTermFloats * 4), j, lane, term);
-                        rem += kCW;
-                        while (segc < kA && rem >= npairs) {
-                            rem -= npairs;
-                            segc++;
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(empty0 + 8 * slot);
-                        mbar_arrive(tf0 + 8 * tb);
-                    }
-                    tslot++;
-                    if (++slot == SM::SLOTS) {
-                        slot = 0;
-                        parity ^= 1u;
-                    }
-                }
-            }
+            matvec_consumer<TYPE, QUAD, PROF>(P, pi & 1, cta, G, tag, PROF && pi == P.prof_phase);
         } else if (kind == PH_SCORE) {
-            score_phase<TYPE>(P, S, ph, cta, G, S.sched[4], tag, kv_par);
+            score_phase<TYPE, PROF>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else if (kind == PH_PV) {
-            pv_phase<TYPE>(P, S, ph, cta, G, S.sched[4], tag);
+            pv_phase<TYPE, PROF>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
-            if (cta == 0 && warp == 0) {
+            if (cta == 0 && cwarp == 0) {
                 Best b{-INFINITY, -1};
                 for (int i = lane; i < P.R * G; i += 32) {
                     const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + P.R * G + i;
@@ -1298,7 +1452,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         // the union region is rewritten by the next phase, and the prefetched descriptor is read
         cp_async_wait_all();
         phase_bar();
-        if (P.trace && tid == 0) {
+        if (P.trace && ctid == 0) {
             long long *t = P.trace + ((size_t)pi * G + cta) * 4;
             const long long tr2 = (long long)gtime();
             t[0] = S.tr[0]; t[1] = S.tr[1]; t[2] = tr2; t[3] = tr2;
@@ -1402,10 +1556,14 @@ struct ggb_decoder {
     bool any_quad = false;         // some phase uses the quad layout -> the QUAD instantiation of the kernel
 };
 
-static const void *decoder_fn(int type, bool quad) {
+static const void *decoder_fn(int type, bool quad, bool prof = false) {
+    if (prof) { // the profiling instantiation (SM-clock sums inside one phase); Q4_0 only keeps the build short
+        if (type == GGB_TYPE_Q4_0)
+            return quad ? (const void *)decoder_kernel<GGB_TYPE_Q4_0, true, true> : (const void *)decoder_kernel<GGB_TYPE_Q4_0, false, true>;
+    }
     if (type == GGB_TYPE_Q4_0)
-        return quad ? (const void *)decoder_kernel<GGB_TYPE_Q4_0, true> : (const void *)decoder_kernel<GGB_TYPE_Q4_0, false>;
-    return quad ? (const void *)decoder_kernel<GGB_TYPE_Q8_0, true> : (const void *)decoder_kernel<GGB_TYPE_Q8_0, false>;
+        return quad ? (const void *)decoder_kernel<GGB_TYPE_Q4_0, true, false> : (const void *)decoder_kernel<GGB_TYPE_Q4_0, false, false>;
+    return quad ? (const void *)decoder_kernel<GGB_TYPE_Q8_0, true, false> : (const void *)decoder_kernel<GGB_TYPE_Q8_0, false, false>;
 }
 static size_t decoder_smem(int type) {
     return type == GGB_TYPE_Q4_0 ? sizeof(Smem<GGB_TYPE_Q4_0>) : sizeof(Smem<GGB_TYPE_Q8_0>);
@@ -1479,17 +1637,18 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     P.exp_table = ggb_exp_table_dev(); P.gelu_table = ggb_gelu_table_dev();
     P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
     {   // does the computed exp reproduce the table?  (GGB_EXP_TABLE=1 forces the lookup)
-        int *d_mis = nullptr, h_mis = -1;
+        int *d_mis = nullptr, h_mis[2] = {-1, -1};
         const char *force = getenv("GGB_EXP_TABLE");
-        if (!(force && atoi(force)) && cudaMalloc(&d_mis, sizeof(int)) == cudaSuccess) {
-            cudaMemsetAsync(d_mis, 0, sizeof(int), ggb_cuda_stream());
+        if (!(force && atoi(force)) && cudaMalloc(&d_mis, 2 * sizeof(int)) == cudaSuccess) {
+            cudaMemsetAsync(d_mis, 0, 2 * sizeof(int), ggb_cuda_stream());
             exp_check_kernel<<<256, 256, 0, ggb_cuda_stream()>>>(P.exp_table, d_mis);
-            if (cudaMemcpyAsync(&h_mis, d_mis, sizeof(int), cudaMemcpyDeviceToHost, ggb_cuda_stream()) != cudaSuccess ||
+            if (cudaMemcpyAsync(h_mis, d_mis, 2 * sizeof(int), cudaMemcpyDeviceToHost, ggb_cuda_stream()) != cudaSuccess ||
                 cudaStreamSynchronize(ggb_cuda_stream()) != cudaSuccess)
-                h_mis = -1;
+                h_mis[0] = h_mis[1] = -1;
             cudaFree(d_mis);
         }
-        P.exp_compute = h_mis == 0 ? 1 : 0;
+        P.exp_compute = h_mis[1] == 0 ? 2 : (h_mis[0] == 0 ? 1 : 0);
+        if (const char *e2 = getenv("GGB_EXP_MODE")) P.exp_compute = std::min(P.exp_compute, std::max(atoi(e2), 0));
     }
     P.rank = rank; P.R = size;
     auto ilog2 = [](int v) { int s = 0; while ((1 << s) < v) s++; return s; };
@@ -1763,7 +1922,7 @@ int ggb_decoder_step(ggb_decoder *D) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(D != nullptr, "null decoder");
     void *args[] = {(void *)&D->P};
-    const void *fn = decoder_fn(D->P.type, D->any_quad);
+    const void *fn = decoder_fn(D->P.type, D->any_quad, D->P.prof != nullptr);
     // cooperative launch: the flagged data flow needs every CTA resident (a waiting CTA spins).  The fp16
     // exp / gelu tables are pinned in the persisting part of L2 for this kernel.
     cudaLaunchConfig_t cfg{};
@@ -1794,13 +1953,23 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
     GGB_CHECK_ARG(D && stamps && kinds && n_phases && grid, "null pointer");
     const int np = (int)D->phases.size();
     GGB_CHECK_ARG(max_phases >= np, "trace buffer holds %d phases, need %d", max_phases, np);
-    const size_t bytes = (size_t)np * D->grid * 4 * sizeof(long long);
+    const size_t bytes1 = (size_t)np * D->grid * 4 * sizeof(long long);
+    const size_t bytes = bytes1 + (size_t)D->grid * 32 * sizeof(long long); // + [grid][32] sums inside phase GGB_PROF_PHASE
+    GGB_CHECK_ARG((size_t)max_phases * D->grid * 4 * sizeof(long long) >= bytes, "trace buffer too small");
     long long *dev = nullptr;
     GGB_CUDA(cudaMalloc(&dev, bytes));
     GGB_CUDA(cudaMemsetAsync(dev, 0, bytes, ggb_cuda_stream()));
     D->P.trace = dev;
+    if (const char *env = getenv("GGB_PROF_PHASE")) {
+        if (D->P.type == GGB_TYPE_Q4_0 && atoi(env) >= 0) {
+            D->P.prof = dev + bytes1 / sizeof(long long);
+            D->P.prof_phase = atoi(env);
+            cudaFuncSetAttribute(decoder_fn(D->P.type, D->any_quad, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D->smem);
+        }
+    }
     int rc = ggb_decoder_step(D);
     D->P.trace = nullptr;
+    D->P.prof = nullptr;
     if (rc == GGB_OK) {
         cudaError_t e = cudaMemcpyAsync(stamps, dev, bytes, cudaMemcpyDeviceToHost, ggb_cuda_stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(ggb_cuda_stream());

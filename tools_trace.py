@@ -46,6 +46,21 @@ def main():
     print("layer 5 detail: phase, critical us, prologue min/max us, work max us, busy CTAs")
     for r in rows[30:36]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
+    if os.environ.get("GGB_PROF_PHASE"):
+        pr = m.prof.astype(np.float64) / 1965.0  # us at 1965 MHz
+        ph = int(os.environ["GGB_PROF_PHASE"]); kind = NAMES[kinds[ph]]
+        np.set_printoptions(linewidth=200, suppress=True)
+        if kind in ("SCORE", "PV"):
+            ok = pr[:, 0] > 0
+            rel = pr[ok, :8] - pr[ok, 0:1]
+            print("inside phase %d (%s): stamps in us since item start, median / max over CTAs" % (ph, kind))
+            print("   median", np.round(np.median(rel, axis=0), 2)); print("   max   ", np.round(rel.max(axis=0), 2))
+        else:
+            print("inside phase %d (%s), us per CTA (median / max): consumer warp 0: prologue, wait weights, wait term buffer, compute, total, passes" % (ph, kind))
+            print("   median", np.round(np.median(pr[:, :6], axis=0), 2)); print("   max   ", np.round(pr[:, :6].max(axis=0), 2))
+            print("   chain warp: wait terms, chain, finish (incl. GeGLU), rounds, total, passes, of chain: adds, row finish")
+            print("   median", np.round(np.median(pr[:, 16:24], axis=0), 2)); print("   max   ", np.round(pr[:, 16:24].max(axis=0), 2))
+            print("   (counts are shown divided by 1965)")
     print("last phases:")
     for r in rows[-2:]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
