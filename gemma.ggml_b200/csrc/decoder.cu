@@ -44,14 +44,12 @@ namespace {
 
 constexpr int kCW = 16;             // consumer warps
 constexpr int kCT = kCW * 32;       // consumer threads
-// warp roles: the chain warp is warp 0, the consumers warps 1..16, the producer warp 17 (GGB_CHAIN_LAST: chain warp 17,
-// consumers 0..15, producer 16 - kept for A/B runs of the warp arbiter's preference)
-#ifdef GGB_CHAIN_LAST
-constexpr int kProdWarp = 16, kChainWarp = 17, kC0 = 0;
-#else
-constexpr int kProdWarp = 17, kChainWarp = 0, kC0 = 32;
-#endif
-constexpr int kThreads = 18 * 32;
+// warp roles: chain warps 0, 18, 19; consumers 1..16; producer 17.  The pass loop keeps the schedulers ~80 % busy, so
+// the chain work (one warp's ~150 instructions per slot) is dealt slot by slot to three warps on three schedulers
+constexpr int kProdWarp = 17, kC0 = 32;
+constexpr int kNCH = 3;             // chain warps: warps 0, 18, 19 (one more warp on three of the four schedulers)
+constexpr int kThreads = 20 * 32;
+constexpr int kMaxBuf = 3;          // term buffers (as many as fit behind the phase's activation row)
 constexpr int kSlots = 5;
 constexpr int kMaxOutstanding = 2;  // ring copies in flight per SM (default; GGB_MAX_OUTSTANDING overrides)
 constexpr int kPrefetchChunks = 0;  // L2 look-ahead of the weight stream in ring chunks (GGB_PREFETCH_CHUNKS overrides)
@@ -128,7 +126,7 @@ struct DecoderParams {
     const uint8_t *emb_qs; // planar embedding table (layer-0 get_rows)
     const __half *emb_d;
     int32_t *state, *history;
-    ll_t *cand_ll;         // [2][R * grid]: per-CTA arg-max candidates (value, index) of every rank
+    ll_t *cand_ll;         // [2][R * grid * kNCH]: arg-max candidates (value, index) of every chain warp of every rank
     int max_outstanding, prefetch_chunks; // producer tuning (see producer_loop)
     int rank, R;           // tensor parallel: this GPU's rank and the number of GPUs (1 = single GPU)
     long long peer_delta[8]; // byte offset from a local flagged word to the same word in rank r's memory (0 for self)
@@ -142,22 +140,31 @@ struct DecoderParams {
 };
 
 // union region: the views are never live at the same time
-//   mat-vec : act_q [kMaxK] | act_d half[kMaxK/32] | bias int[kMaxK/32] | terms float[2][kTermFloats]
-//             + (K <= 8192) at +8192: xs float[kMaxE] during the norm prologue, then acc float[kAccFloats] | gu float[kGuFloats]
+//   mat-vec : act_q [K] | act_d half[K/32] | bias int[K/32] | (K > 6144) terms float[2..3][kTermFloats]
+//             (K <= 6144) at +8192: xs float[kMaxE] during the norm prologue, then acc float[kAccFloats] | gu float[kGuFloats] | terms float[3][kTermFloats]
 //   score   : Kc half[2][32][256] | Sq double[4][256]
 //   pv      : p float[n_ctx <= 8192] | part double[16][32]
-constexpr int U_ACT_D = kMaxK;
-constexpr int U_BIAS = U_ACT_D + kMaxK / 32 * 2;
-constexpr int U_TERMS = U_BIAS + kMaxK / 32 * 4;
 constexpr int U_XS = 8192;
 constexpr int U_ACC = U_XS, U_GU = U_ACC + kAccFloats * 4;
 constexpr int U_KC = 0, U_SQ = 32768;
 constexpr int U_PVP = 0;
-constexpr int U_BYTES = U_TERMS + 2 * kTermFloats * 4;
+constexpr int U_BYTES = kMaxK + kMaxK / 16 + kMaxK / 8 + 2 * kTermFloats * 4;
+constexpr int kAccMaxK = 6144;      // activation rows up to this length (+ scales + biases) end below the overlay at U_ACC
+// the phase's activation row: codes [K] | fp16 scales [K/32] | int biases [K/32]; then (large K) or behind the
+// accumulator overlay (small K) the term buffers
+__host__ __device__ __forceinline__ int act_d_off(int K) { return K; }
+__host__ __device__ __forceinline__ int act_bias_off(int K) { return K + (K >> 4); }
+__host__ __device__ __forceinline__ int terms_off(int K) {
+    return K <= kAccMaxK ? U_XS + (kAccFloats + kGuFloats) * 4 : ((K + (K >> 4) + (K >> 3) + 127) & ~127);
+}
+__host__ __device__ __forceinline__ int terms_nbuf(int K) {
+    const int n = (U_BYTES - terms_off(K)) / (kTermFloats * 4);
+    return n < kMaxBuf ? n : kMaxBuf;
+}
 static_assert(U_SQ + 4 * 256 * 8 <= U_BYTES, "union region too small for the score view");
 static_assert(kMaxCtx * 4 + 16 * 32 * 8 + kCT * 16 <= U_BYTES, "union region too small for the pv view");
-static_assert(U_XS + kMaxE * 4 <= U_ACT_D && kMaxE <= U_XS, "xs overlaps the activation row");
-static_assert(U_GU + kGuFloats * 4 <= U_ACT_D, "accumulator overlay too large");
+static_assert(kMaxE <= U_XS && kMaxE <= kAccMaxK, "xs overlaps the activation row");
+static_assert(kAccMaxK + kAccMaxK / 16 + kAccMaxK / 8 <= U_XS, "small activation rows must end below the overlay");
 
 template <int TYPE> struct Smem {
     static constexpr int SLOTS = kSlots;
@@ -170,10 +177,11 @@ template <int TYPE> struct Smem {
     alignas(8) unsigned long long full_bar[kSlots];
     alignas(8) unsigned long long empty_bar[kSlots];
     alignas(8) unsigned long long kv_bar[2];  // SCORE: the K chunk rows of buffer 0 / 1 have landed
-    alignas(8) unsigned long long tfull[2];   // term buffer b holds a whole slot's terms (16 consumer-warp arrivals)
-    alignas(8) unsigned long long tempty[2];  // the chain warp has consumed term buffer b
+    alignas(8) unsigned long long tfull[kMaxBuf];   // term buffer b holds a whole slot's terms (16 consumer-warp arrivals)
+    alignas(8) unsigned long long tempty[kMaxBuf];  // a chain warp has consumed term buffer b
+    volatile int done_slot; // slots (numbered through the token) whose rows are all chained, committed in order
     long long tr[2]; // trace stamps of the current phase (thread 0)
-    int wst[kCW + 2][4]; // per-warp state that lives across phases: ring slot, ring parity, term slot counter, K-buffer parities
+    int wst[kCW + kNCH][4]; // per-warp state that lives across phases: ring slot, ring parity, term slot counter, K-buffer parities
     int sched[6];    // [0] = chunks, [3] = token, [4] = number of positions (kept out of registers: the kernel runs
                      // at the 96-register limit of 18 warps per SM and a spill costs an L2 round trip)
     alignas(16) Phase ph[2];
@@ -252,7 +260,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // orders this thread's (and, through a preceding barrier, the CTA's) generic-proxy accesses before later async-proxy ones
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kCT) : "memory"); }
-__device__ __forceinline__ void phase_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kCT + 32) : "memory"); } // consumers + chain warp
+__device__ __forceinline__ void phase_bar() { asm volatile("bar.sync 2, %0;" ::"n"(kCT + 32 * kNCH) : "memory"); } // consumers + chain warps
 __device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -469,7 +477,7 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
 // behind WARPSYNC.EXCLUSIVE and costs ~0.5 us).  max is exact: same value as the reference's scan.
 // (activation codes live in TWO planes - bytes 0..15 of every block, then bytes 16..31 at + hi_off = K / 2 - so that
 // load_act_regs' LDS.128 are 16-byte-strided across the warp: conflict-free)
-__device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lane, const float (&v)[4], int hi_off) {
+__device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lane, const float (&v)[4], int hi_off, int K) {
     float amax = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
 #pragma unroll
     for (int off = 1; off <= 4; off <<= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off)); // 8-lane groups
@@ -486,8 +494,8 @@ __device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lan
     if ((lane & 7) == 0) {
         const int b = 4 * quad + (lane >> 3);
         const unsigned short hd = __half_as_ushort(__float2half_rn(d));
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(u + U_ACT_D + 2 * b), "h"(hd) : "memory");
-        asm volatile("st.shared.s32 [%0], %1;" ::"r"(u + U_BIAS + 4 * b), "r"(-8 * qs) : "memory");
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(u + act_d_off(K) + 2 * b), "h"(hd) : "memory");
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(u + act_bias_off(K) + 4 * b), "r"(-8 * qs) : "memory");
     }
 }
 
@@ -558,7 +566,7 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
         v[2] = __fmul_rn(__fmul_rn(x4.z, scale), w4.z);
         v[3] = __fmul_rn(__fmul_rn(x4.w, scale), w4.w);
         if (f32_out) *reinterpret_cast<float4 *>(f32_out + i) = make_float4(v[0], v[1], v[2], v[3]);
-        quant_quad_to_smem(ua, quad, lane, v, E / 2);
+        quant_quad_to_smem(ua, quad, lane, v, E / 2, E);
     }
     consumer_bar();
 }
@@ -577,7 +585,7 @@ __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, in
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) v[e] = ll_get_f(w[e], p + e, tag);
-        quant_quad_to_smem(ua, quad, lane, v, K / 2);
+        quant_quad_to_smem(ua, quad, lane, v, K / 2, K);
     }
     consumer_bar();
 }
@@ -589,8 +597,8 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
     const int tid = (int)threadIdx.x - kC0;
     const int nw = K / 4, ns = K / 32;
     uint32_t *aq = reinterpret_cast<uint32_t *>(S.u);
-    __half *ad = reinterpret_cast<__half *>(S.u + U_ACT_D);
-    int *bias = reinterpret_cast<int *>(S.u + U_BIAS);
+    __half *ad = reinterpret_cast<__half *>(S.u + act_d_off(K));
+    int *bias = reinterpret_cast<int *>(S.u + act_bias_off(K));
 #pragma unroll 1
     for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 4 words in flight per thread (more spills at the 96-register limit)
         ll_t v[4];
@@ -639,15 +647,16 @@ __device__ __forceinline__ void load_act_regs(ActRegs &A, uint32_t act, int seg,
 // runs at the 96-register limit and a spilled value would come back from L2 in the middle of the dp4a chain.
 // (A block index past the row reads some other shared-memory word; its term is never used.)
 template <int TYPE, bool QUADPASS>
-__device__ __forceinline__ void pass_terms(uint32_t base, uint32_t act, int b0, const ActRegs &A, int lane, float (&term)[4]) {
+__device__ __forceinline__ void pass_terms(uint32_t base, uint32_t act_d, uint32_t act_bias, int b0, const ActRegs &A, int lane,
+                                           float (&term)[4]) {
     using F = Fmt<TYPE>;
     const int(&a)[2][8] = A.a;
     float dy[2];
     int bias[2];
 #pragma unroll
     for (int t = 0; t < (QUADPASS ? 1 : 2); t++) {
-        dy[t] = lds_half(act + U_ACT_D + 2 * (b0 + 32 * t));
-        bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act + U_BIAS + 4 * (b0 + 32 * t)) : 0;
+        dy[t] = lds_half(act_d + 2 * (b0 + 32 * t));
+        bias[t] = TYPE == GGB_TYPE_Q4_0 ? lds_s32(act_bias + 4 * (b0 + 32 * t)) : 0;
     }
     if (QUADPASS) {
         dy[1] = dy[0];
@@ -732,23 +741,27 @@ __device__ __forceinline__ float chain_add(uint32_t row, int b0, int len, float 
 }
 
 
-// ---------------------------------------------------------------- the chain warp's share of a mat-vec phase
-// Slot by slot: wait for the consumers' terms, add them to the rows' accumulators in block order (rounds = the
-// passes of one K segment inside the slot: a row occurs once per round), finish the rows whose last segment this was.
+// ---------------------------------------------------------------- a chain warp's share of a mat-vec phase
+// The slots of a CTA's share go round-robin to the kNCH chain warps.  For its slots a chain warp waits for the consumers'
+// terms, adds them to the rows' accumulators in block order (rounds = the passes of one K segment inside the slot: a
+// row occurs once per round) and finishes the rows whose last segment this was.  Rows that continue an accumulator
+// from an earlier slot (multi-segment phases) wait until every earlier slot is committed; slots commit in order
+// (S.done_slot), and the warp that commits the slot which completes a 32-row GATE_UP group does its GeGLU + quantize.
 template <int TYPE, bool QUAD, bool PROF>
-__device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int cta, int G, uint32_t tag, bool prof) {
+__device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int ci, int cta, int G, uint32_t tag, bool prof) {
     long long pt0 = 0, p_wait = 0, p_chain = 0, p_fin = 0, p_rounds = 0, p_begin = 0, p_add = 0, p_row = 0, pta = 0;
     if (PROF) p_begin = clock64();
     using F = Fmt<TYPE>;
-    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem); // (re-derived here: shared addresses stay immediates)
+    Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
     const Phase &ph = S.ph[phi];
     const int lane = threadIdx.x & 31;
-    uint32_t tslot = (uint32_t)S.wst[kCW][2];
+    uint32_t tmask = (uint32_t)S.wst[kCW + ci][2]; // bit b: parity of term buffer b's barriers at its next use
+    int gslot = S.wst[kCW + ci][1];               // slots of earlier phases (the numbering of S.done_slot)
     int u0, u1;
     unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
     const int n_passes = (u1 - u0) * ph.unit_passes;
     const int npairs = ((u1 - u0) * ph.unit_rows) >> 1;
-    const int kA = ph.kA, kind = ph.kind;
+    const int kA = ph.kA, kind = ph.kind, K = ph.K;
     const bool quad = QUAD && ph.quad != 0;
     const int row0 = u0 * ph.unit_rows;
     const bool bcast = ph.bcast != 0;
@@ -758,18 +771,20 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
     const int tail_blocks = ph.tail_blocks, kf = ph.kf, resid_embed = ph.resid_embed;
     float *const out_f = ph.out;
     ll_t *const out_ll = ph.out_ll;
+    const ll_t *const resid = ph.resid_ll;
     auto oidx = [&](int lr) {
         if (lr < sr0) return so0 + lr;
         lr -= sr0;
         return lr < sr1 ? so1 + lr : so2 + lr - sr1;
     };
-    float *A = ph.K <= 8192 ? reinterpret_cast<float *>(S.u + U_ACC) : S.acc_small;
+    float *A = K <= kAccMaxK ? reinterpret_cast<float *>(S.u + U_ACC) : S.acc_small;
     float *GU = reinterpret_cast<float *>(S.u + U_GU);
-    const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]), terms0 = smem_u32(S.u + U_TERMS);
+    const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]);
+    const uint32_t terms0 = smem_u32(S.u) + (uint32_t)terms_off(K);
+    const int nbuf = terms_nbuf(K);
     const int j = lane >> 1, ab = lane & 1;
-    int segc = 0, rem = 0, units_done = 0;
+    int segc = 0, rem = 0;
     Best best{-INFINITY, -1};
-    const ll_t *resid = ph.resid_ll;
 
     auto finish_row = [&](int rl, float total, ll_t rv) {
         const int lr = row0 + rl;
@@ -785,17 +800,16 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
         if (out_ll) ll_put_f(P, bcast, out_ll + gi, total, tag);
         if (total > best.v || best.i < 0) best = Best{total, gi};
     };
-
-    // a lane's code joins three neighbours' in one flagged word of the packed row; the block's fp16 scale and the sum of
-    // its codes (the Q4_0 bias of DOWN's dot products) share one more
-    int pend = -1;
-    uint16_t pend_gl = 0;
+    // GeGLU (fp16 gelu table) + quantize_row_q8_0 of a 32-row group whose gate and up rows are all in: lane = row of
+    // the group.  A lane's code joins three neighbours' in one flagged word of the packed row; the block's fp16 scale and
+    // the sum of its codes (the Q4_0 bias of DOWN's dot products) share one more.
     const int ug0 = ph.u_off + u0;
     float *const act_dump = ph.f32_out;
     ll_t *const oq = out_ll, *const od = out_ll + P.F / 4;
-    auto geglu_finish = [&](int u, uint16_t glb) {
+    auto geglu = [&](int u) {
         const int ug = ug0 + u;
-        const float x = __fmul_rn(half_bits_to_float(glb), GU[64 * u + 32 + lane]);
+        const float gl = half_bits_to_float(__ldg(P.gelu_table + float_to_half_bits(GU[64 * u + lane])));
+        const float x = __fmul_rn(gl, GU[64 * u + 32 + lane]);
         if (act_dump) act_dump[(size_t)ug * 32 + lane] = x;
         const float amax = warp_max_f32(fabsf(x));
         const float dd = __fdiv_rn(amax, 127.0f);
@@ -809,97 +823,148 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
         if (lane == 0)
             ll_put(P, bcast, od + ug, ((uint32_t)qs << 16) | (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
     };
+    // 32-row groups complete once the pass position (section, index) is reached
+    auto complete = [&](int sc, int r) {
+        if (quad) return sc >= kA ? (r >> 4) : 0;
+        return sc >= kA ? (npairs >> 5) : (sc == kA - 1 ? (r >> 5) : 0);
+    };
 
+    // ROW-LANE MODE (multi-segment phases whose CTA share is <= 32 rows: O / DOWN): lane = row for the whole phase, the
+    // accumulator stays in a register from segment to segment, and ONE chain warp takes every slot (the segments of a
+    // row are a dependent chain anyway: handing it from warp to warp only adds latency)
+    const bool rowlane = (kA > 1 || (quad && kf > 0)) && 2 * npairs <= 32 && kind != PH_GATE_UP;
+    // memory fences only where rows are handed from warp to warp (accumulators of multi-segment rows, gate / up rows)
+    const bool handoff = kind == PH_GATE_UP || kA > 1 || (quad && kf > 0);
+    float racc = 0.0f;
+    int tb = 0, turn = 0;
 #pragma unroll 1
-    for (int m0 = 0; m0 < n_passes; m0 += F::PPS) {
+    for (int m0 = 0; m0 < n_passes; m0 += F::PPS, gslot++) {
         const int cnt = min(F::PPS, n_passes - m0);
-        const uint32_t tb = tslot & 1u;
-        if (PROF) pt0 = clock64();
-        mbar_wait(tf0 + 8 * tb, (tslot >> 1) & 1u);
-        if (PROF) p_wait += clock64() - pt0;
-        const uint32_t tbase = terms0 + tb * (uint32_t)(kTermFloats * 4);
+        const bool mine = rowlane ? ci == 0 : turn == ci;
+        const uint32_t tpar = (tmask >> tb) & 1u;
+        if (mine) {
+            if (PROF) pt0 = clock64();
+            mbar_wait(tf0 + 8 * tb, tpar);
+            if (PROF) p_wait += clock64() - pt0;
+        }
+        const uint32_t tbase = terms0 + (uint32_t)tb * (uint32_t)(kTermFloats * 4);
+        const int done_before = complete(segc, rem);
         int jj = 0;
 #pragma unroll 1
         while (jj < cnt) {
             const bool isB = segc >= kA;
             const int run = isB ? cnt - jj : min(cnt - jj, npairs - rem);
-            const bool active = j >= jj && j < jj + run;
-            const int idx = rem + (j - jj);
-            bool last_section;
-            if (PROF) { pt0 = clock64(); p_rounds++; }
-            if (!isB) {
-                const bool last = !quad && segc == kA - 1;
-                last_section = last;
-                const int len = last ? tail_blocks : kSeg;
-                const int rl = 2 * idx + ab;
-                ll_t rv = 0;
-                if (last && active && resid && row0 + rl < n_lr) rv = ll_peek(resid + oidx(row0 + rl));
-                float acc = (active && segc > 0) ? A[rl] : 0.0f;
-                if (PROF) pta = clock64();
-                acc = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 0, len, acc);
-                if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; pta = t1; }
-                if (active) {
-                    if (last) finish_row(rl, acc, rv);
-                    else A[rl] = acc;
+            if (mine) {
+                if (PROF) { pt0 = clock64(); p_rounds++; }
+                if (rowlane) {
+                    if (!isB) {
+                        const int pair = lane >> 1;
+                        const bool act2 = pair >= rem && pair < rem + run;
+                        const bool last = !quad && segc == kA - 1;
+                        const int len = last ? tail_blocks : kSeg;
+                        ll_t rv = 0;
+                        if (last && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
+                        const int c = 2 * (jj + pair - rem) + ab;
+                        const float r = chain_add(tbase + (uint32_t)((c & 31) * kTermRow * 4), 0, len, segc > 0 ? racc : 0.0f);
+                        if (act2) {
+                            racc = r;
+                            if (last) finish_row(lane, r, rv);
+                        }
+                    } else {
+                        const int q = lane >> 2, kq = lane & 3;
+                        const bool act2 = q >= rem && q < rem + run;
+                        ll_t rv = 0;
+                        if (act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
+                        const int c = 2 * (jj + q - rem) + (kq >> 1);
+                        const float r = chain_add(tbase + (uint32_t)((c & 31) * kTermRow * 4), 32 * (kq & 1), tail_blocks, kf > 0 ? racc : 0.0f);
+                        if (act2) finish_row(lane, r, rv);
+                    }
+                } else {
+                    const bool active = j >= jj && j < jj + run;
+                    const int idx = rem + (j - jj);
+                    // rows that continue an accumulator: every earlier slot must be committed
+                    if (isB ? kf > 0 : segc > 0) {
+                        while (S.done_slot < gslot) {}
+                        __threadfence_block();
+                    }
+                    if (!isB) {
+                        const bool last = !quad && segc == kA - 1;
+                        const int len = last ? tail_blocks : kSeg;
+                        const int rl = 2 * idx + ab;
+                        ll_t rv = 0;
+                        if (last && active && resid && row0 + rl < n_lr) rv = ll_peek(resid + oidx(row0 + rl));
+                        float acc = (active && segc > 0) ? A[rl] : 0.0f;
+                        if (PROF) pta = clock64();
+                        acc = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 0, len, acc);
+                        if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; pta = t1; }
+                        if (active) {
+                            if (last) finish_row(rl, acc, rv);
+                            else A[rl] = acc;
+                        }
+                        if (PROF) p_row += clock64() - pta;
+                    } else { // the short segment of rows 4 idx + 2 ab and + 1: two 32-term runs of this lane
+                        const int rl = 4 * idx + 2 * ab;
+                        ll_t rv0 = 0, rv1 = 0;
+                        if (active && resid) {
+                            if (row0 + rl < n_lr) rv0 = ll_peek(resid + oidx(row0 + rl));
+                            if (row0 + rl + 1 < n_lr) rv1 = ll_peek(resid + oidx(row0 + rl + 1));
+                        }
+                        float a0 = (active && kf > 0) ? A[rl] : 0.0f, a1 = (active && kf > 0) ? A[rl + 1] : 0.0f;
+                        a0 = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 0, tail_blocks, a0);
+                        a1 = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 32, tail_blocks, a1);
+                        if (active) {
+                            finish_row(rl, a0, rv0);
+                            finish_row(rl + 1, a1, rv1);
+                        }
+                    }
                 }
-                if (PROF) p_row += clock64() - pta;
-            } else { // the short segment of rows 4 idx + 2 ab and + 1: two 32-term runs of this lane
-                last_section = true;
-                const int rl = 4 * idx + 2 * ab;
-                ll_t rv0 = 0, rv1 = 0;
-                if (active && resid) {
-                    if (row0 + rl < n_lr) rv0 = ll_peek(resid + oidx(row0 + rl));
-                    if (row0 + rl + 1 < n_lr) rv1 = ll_peek(resid + oidx(row0 + rl + 1));
-                }
-                float a0 = (active && kf > 0) ? A[rl] : 0.0f, a1 = (active && kf > 0) ? A[rl + 1] : 0.0f;
-                a0 = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 0, tail_blocks, a0);
-                a1 = chain_add(tbase + (uint32_t)(lane * kTermRow * 4), 32, tail_blocks, a1);
-                if (active) {
-                    finish_row(rl, a0, rv0);
-                    finish_row(rl + 1, a1, rv1);
+                __syncwarp();
+                if (PROF) {
+                    const long long t1 = clock64();
+                    p_chain += t1 - pt0;
+                    if (prof && rowlane && lane == 0 && p_rounds <= 8) P.prof[32 * cta + 23 + p_rounds] = t1 - p_begin; // end of round r
                 }
             }
-            __syncwarp();
-            if (PROF) { const long long t1 = clock64(); p_chain += t1 - pt0; pt0 = t1; }
-            const int idx_end = rem + run;
             jj += run;
             rem += run;
             if (!isB && rem == npairs) {
                 rem = 0;
                 segc++;
             }
-            if (kind == PH_GATE_UP) {
-                // GeGLU (fp16 gelu table) + quantize_row_q8_0 of every 32-row group whose gate and up rows are all in:
-                // lane = row of the group.  The table lookup of a group is issued when the group completes and used one
-                // round later, so its L2 round trip hides behind the next chain.
-                if (pend >= 0) {
-                    geglu_finish(pend, pend_gl);
-                    pend = -1;
-                }
-                if (last_section) {
-                    const int complete = isB ? (idx_end >> 4) : (idx_end >> 5);
-#pragma unroll 1
-                    for (; units_done < complete; units_done++) {
-                        if (pend >= 0) geglu_finish(pend, pend_gl);
-                        pend = units_done;
-                        pend_gl = __ldg(P.gelu_table + float_to_half_bits(GU[64 * units_done + lane]));
-                    }
-                }
-            }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(te0 + 8 * tb);
-        tslot++;
-        if (PROF) p_fin += clock64() - pt0;
+        if (mine) {
+            if (PROF) pt0 = clock64();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(te0 + 8 * tb); // the terms are consumed: the consumers may refill the buffer
+            if (!rowlane) { // commit in slot order; then the GATE_UP groups this slot completed
+                while (S.done_slot != gslot) {}
+                if (handoff) __threadfence_block();
+                if (kind == PH_GATE_UP) {
+                    const int done_after = complete(segc, rem);
+#pragma unroll 1
+                    for (int u = done_before; u < done_after; u++) geglu(u);
+                }
+                if (handoff) __threadfence_block(); // this warp's accumulator / staging writes before the commit
+                __syncwarp();
+                if (lane == 0) S.done_slot = gslot + 1;
+            }
+            if (PROF) p_fin += clock64() - pt0;
+        }
+        tmask ^= 1u << tb;
+        if (++tb == nbuf) tb = 0;
+        if (++turn == kNCH) turn = 0;
     }
-    if (pend >= 0) geglu_finish(pend, pend_gl);
-    if (PROF && prof && lane == 0) {
+    if (PROF && prof && lane == 0 && ci == 0) {
         long long *o = P.prof + 32 * cta + 16;
         o[0] = p_wait; o[1] = p_chain; o[2] = p_fin; o[3] = p_rounds; o[4] = clock64() - p_begin; o[5] = n_passes;
         o[6] = p_add; o[7] = p_row;
     }
-    if (lane == 0) S.wst[kCW][2] = (int)tslot;
-    if (kind == PH_LOGITS) { // this CTA's arg-max candidate (strict '>' / lowest index, ref: src/gemma_model.cpp:538-543)
+    if (lane == 0) {
+        S.wst[kCW + ci][2] = (int)tmask;
+        S.wst[kCW + ci][1] = gslot;
+        if (rowlane && ci == 0) S.done_slot = gslot; // (the other chain warps did not touch this phase's slots)
+    }
+    if (kind == PH_LOGITS) { // this warp's arg-max candidate (strict '>' / lowest index, ref: src/gemma_model.cpp:538-543)
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             Best o;
@@ -908,8 +973,9 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
             best = better(best, o);
         }
         if (lane == 0) {
-            ll_put_f(P, true, P.cand_ll + P.rank * G + cta, best.v, tag);
-            ll_put(P, true, P.cand_ll + P.R * G + P.rank * G + cta, (uint32_t)best.i, tag);
+            const int ce = (P.rank * G + cta) * kNCH + ci;
+            ll_put_f(P, true, P.cand_ll + ce, best.v, tag);
+            ll_put(P, true, P.cand_ll + P.R * G * kNCH + ce, (uint32_t)best.i, tag);
         }
     }
 }
@@ -1273,15 +1339,17 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
     const int kind = ph.kind;
     const uint32_t ring = smem_u32(&S.ring[0][0]);
     const uint32_t full0 = smem_u32(&S.full_bar[0]), empty0 = smem_u32(&S.empty_bar[0]);
-    const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]), terms0 = smem_u32(S.u + U_TERMS);
+    const uint32_t tf0 = smem_u32(&S.tfull[0]), te0 = smem_u32(&S.tempty[0]);
     const uint32_t act = smem_u32(S.u);
     int slot = S.wst[warp][0];
-    uint32_t parity = (uint32_t)S.wst[warp][1], tslot = (uint32_t)S.wst[warp][2];
+    uint32_t parity = (uint32_t)S.wst[warp][1], tmask = (uint32_t)S.wst[warp][2];
     int u0, u1;
     unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
     const int n_passes = (u1 - u0) * ph.unit_passes;
     const int npairs = ((u1 - u0) * ph.unit_rows) >> 1;
     const int nb = ph.K >> 5, kA = ph.kA;
+    const uint32_t terms0 = act + (uint32_t)terms_off(ph.K), act_d = act + (uint32_t)act_d_off(ph.K), act_bias = act + (uint32_t)act_bias_off(ph.K);
+    const int nbuf = terms_nbuf(ph.K);
     if (n_passes > 0 || (cta == 0 && kind == PH_LOGITS)) { // CTA 0 also writes the result_norm dump
         if (kind == PH_O) quant_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
         else if (kind == PH_DOWN) packed_prologue<TYPE>(S, ph.in_ll, ph.K, tag);
@@ -1301,6 +1369,7 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
             segc++;
         }
         ActRegs A;
+        int tb = 0;
 #pragma unroll 1
         for (int p0 = 0, i = 0; p0 < n_passes; p0 += F::PPS, i++) {
             const int cnt = min(F::PPS, n_passes - p0);
@@ -1310,20 +1379,19 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
                 load_act_regs<TYPE>(A, act, aseg, nb, lane);
                 cur_seg = aseg;
             }
-            const uint32_t tb = tslot & 1u;
             if (PROF) pt0 = clock64();
             mbar_wait(full0 + 8 * slot, parity);
             if (PROF) { const long long t1 = clock64(); p_full += t1 - pt0; pt0 = t1; }
             // the chain warp is done with this term buffer's previous slot.  EVERY warp waits, also one without a
             // pass in this slot: its arrival below must not be counted for the buffer's previous use
-            mbar_wait(te0 + 8 * tb, ((tslot >> 1) & 1u) ^ 1u);
+            mbar_wait(te0 + 8 * tb, ((tmask >> tb) & 1u) ^ 1u);
             if (PROF) { const long long t1 = clock64(); p_te += t1 - pt0; pt0 = t1; }
             if (j < cnt) {
                 const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;
                 float term[4];
-                if (quad && segc >= kA) pass_terms<TYPE, true>(pass, act, aseg * kSeg + lane, A, lane, term);
-                else pass_terms<TYPE, false>(pass, act, aseg * kSeg + lane, A, lane, term);
-                store_terms(terms0 + tb * (uint32_t)(kTermFloats * 4), j, lane, term);
+                if (quad && segc >= kA) pass_terms<TYPE, true>(pass, act_d, act_bias, aseg * kSeg + lane, A, lane, term);
+                else pass_terms<TYPE, false>(pass, act_d, act_bias, aseg * kSeg + lane, A, lane, term);
+                store_terms(terms0 + (uint32_t)tb * (uint32_t)(kTermFloats * 4), j, lane, term);
                 rem += kCW;
                 while (segc < kA && rem >= npairs) {
                     rem -= npairs;
@@ -1336,7 +1404,8 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
                 mbar_arrive(empty0 + 8 * slot);
                 mbar_arrive(tf0 + 8 * tb);
             }
-            tslot++;
+            tmask ^= 1u << tb;
+            if (++tb == nbuf) tb = 0;
             if (++slot == SM::SLOTS) {
                 slot = 0;
                 parity ^= 1u;
@@ -1346,7 +1415,7 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
     if (lane == 0) {
         S.wst[warp][0] = slot;
         S.wst[warp][1] = (int)parity;
-        S.wst[warp][2] = (int)tslot;
+        S.wst[warp][2] = (int)tmask;
     }
     if (PROF && prof && tid == 0) {
         long long *o = P.prof + 32 * cta;
@@ -1370,17 +1439,18 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
             mbar_init(smem_u32(&S.full_bar[i]), 1);
             mbar_init(smem_u32(&S.empty_bar[i]), kCW);
         }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(smem_u32(&S.kv_bar[i]), kCW);
+        for (int i = 0; i < 2; i++) mbar_init(smem_u32(&S.kv_bar[i]), kCW);
+        for (int i = 0; i < kMaxBuf; i++) {
             mbar_init(smem_u32(&S.tfull[i]), kCW);
             mbar_init(smem_u32(&S.tempty[i]), 1);
         }
+        S.done_slot = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
     const uint32_t tag = *P.seq + 1u;
-    if (tid < (kCW + 2) * 4) (&S.wst[0][0])[tid] = 0;
+    if (tid < (kCW + kNCH) * 4) (&S.wst[0][0])[tid] = 0;
     if (tid == 0) {
         S.sched[0] = (n_pos + kChunk - 1) / kChunk;
         S.sched[3] = min(max(P.state[0], 0), P.V - 1);
@@ -1394,11 +1464,12 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     if (tid < kPhWords) reinterpret_cast<uint32_t *>(&S.ph[0])[tid] = reinterpret_cast<const uint32_t *>(&P.phases[0])[tid];
     phase_bar();
 
-    if (warp == kChainWarp) { // ---- the chain warp
+    if (warp == 0 || warp > kProdWarp) { // ---- the chain warps
+        const int ci = warp == 0 ? 0 : warp - kProdWarp;
 #pragma unroll 1
         for (int pi = 0; pi < P.n_phases; pi++) {
             const Phase &ph = S.ph[pi & 1];
-            if (is_matvec(ph.kind)) chain_phase<TYPE, QUAD, PROF>(P, pi & 1, cta, G, tag, PROF && pi == P.prof_phase);
+            if (is_matvec(ph.kind)) chain_phase<TYPE, QUAD, PROF>(P, pi & 1, ci, cta, G, tag, PROF && pi == P.prof_phase);
             phase_bar();
         }
         return;
@@ -1425,8 +1496,8 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
             if (cta == 0 && cwarp == 0) {
                 Best b{-INFINITY, -1};
-                for (int i = lane; i < P.R * G; i += 32) {
-                    const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + P.R * G + i;
+                for (int i = lane; i < P.R * G * kNCH; i += 32) {
+                    const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + P.R * G * kNCH + i;
                     const ll_t wv = ll_peek(pv), wi = ll_peek(pi2);
                     b = better(b, Best{ll_get_f(wv, pv, tag), (int)ll_get(wi, pi2, tag)});
                 }
@@ -1680,7 +1751,7 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     const size_t o_s = carve((size_t)L * H * dims->n_ctx);
     const size_t o_kqv = carve((size_t)L * QD), o_sa = carve((size_t)L * E);
     const size_t o_ff = carve((size_t)L * (F / 4 + F / 32));
-    const size_t o_cand = carve((size_t)2 * sms * size), o_seq = carve(1);
+    const size_t o_cand = carve((size_t)2 * sms * size * kNCH), o_seq = carve(1);
     cudaError_t e = cudaMalloc(&D->scratch, off);
     if (e != cudaSuccess) {
         ggb_set_error("decoder scratch cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e));
@@ -1790,8 +1861,9 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
         const long long max_rows = max_units * ph.unit_rows;
         const bool multi = ph.kA > 1 || (ph.quad && ph.kf > 0); // rows keep an accumulator between slots
         if (gate_up && max_rows > kGuFloats) { ok = false; why = "GATE_UP rows per CTA do not fit the staging"; }
-        if (multi && max_rows > (ph.K <= 8192 ? kAccFloats : kAccSmall)) { ok = false; why = "rows per CTA do not fit the accumulators"; }
-        if (gate_up && ph.K > 8192) { ok = false; why = "GATE_UP activation row too long"; }
+        if (multi && max_rows > (ph.K <= kAccMaxK ? kAccFloats : kAccSmall)) { ok = false; why = "rows per CTA do not fit the accumulators"; }
+        if (gate_up && ph.K > kAccMaxK) { ok = false; why = "GATE_UP activation row too long"; }
+        if (terms_nbuf(ph.K) < 2) { ok = false; why = "no room for two term buffers"; }
         if (ph.K > kMaxK) { ok = false; why = "activation row too long"; }
         if (!ok) return ph;
         const size_t n_passes = (size_t)ph.n_units * ph.unit_passes; // this rank's passes only

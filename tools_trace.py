@@ -61,6 +61,7 @@ def main():
             print("   chain warp: wait terms, chain, finish (incl. GeGLU), rounds, total, passes, of chain: adds, row finish")
             print("   median", np.round(np.median(pr[:, 16:24], axis=0), 2)); print("   max   ", np.round(pr[:, 16:24].max(axis=0), 2))
             print("   (counts are shown divided by 1965)")
+            print("   row-lane mode: end of chain rounds 1..8, us since phase start (median)", np.round(np.median(pr[:, 24:32], axis=0), 2))
     print("last phases:")
     for r in rows[-2:]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
