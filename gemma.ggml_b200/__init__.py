@@ -418,7 +418,7 @@ class GemmaModel:
         check(cuda_lib().ggb_decoder_trace(dec, _ptr(stamps), _ptr(kinds), max_ph, C.byref(n), C.byref(g)),
               "ggb_decoder_trace")
         n1 = n.value * g.value * 4
-        self.prof = stamps[n1:n1 + g.value * 32].reshape(g.value, 32).copy()  # GGB_PROF_PHASE sums (SM clocks)
+        self.prof = stamps[n1:n1 + g.value * 64].reshape(g.value, 64).copy()  # GGB_PROF_PHASE sums (SM clocks)
         return stamps[:n1].reshape(n.value, g.value, 4), kinds[:n.value].copy()
 
     @property

@@ -22,7 +22,7 @@ HOST_LIB = os.path.join(HERE, "libggb_host.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", *os.environ.get("GGB_NVCC_EXTRA", "").split(),
     "-fmad=false",                 # no implicit FMA contraction: arithmetic matches the oracle
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",

@@ -132,7 +132,8 @@ struct DecoderParams {
     long long peer_delta[8]; // byte offset from a local flagged word to the same word in rank r's memory (0 for self)
     uint32_t *seq;         // token sequence number = tag of the previous launch
     const uint16_t *exp_table, *gelu_table;
-    int exp_compute;       // 1: exp_f16_computed reproduces exp_table bit for bit (checked at create)
+    int exp_compute;       // 1 / 2: exp_f16_computed / exp_f16_fast reproduce exp_table bit for bit (checked at create)
+    int gelu_compute;      // 1: gelu_f16_computed reproduces gelu_table bit for bit (checked at create)
     const float *rope_cos, *rope_sin;
     long long *trace; // optional [n_phases][grid][4] %globaltimer stamps (ns): start, after prologue (inputs arrived), end, end
     long long *prof;  // PROF instantiation only: [grid][32] SM-clock sums inside phase prof_phase (see tools_trace.py)
@@ -181,7 +182,7 @@ template <int TYPE> struct Smem {
     alignas(8) unsigned long long tempty[kMaxBuf];  // a chain warp has consumed term buffer b
     volatile int done_slot; // slots (numbered through the token) whose rows are all chained, committed in order
     long long tr[2]; // trace stamps of the current phase (thread 0)
-    int wst[kCW + kNCH][4]; // per-warp state that lives across phases: ring slot, ring parity, term slot counter, K-buffer parities
+    int wst[kCW + kNCH][5]; // per-warp state that lives across phases: ring slot, ring parity, term slot counter, K-buffer parities
     int sched[6];    // [0] = chunks, [3] = token, [4] = number of positions (kept out of registers: the kernel runs
                      // at the 96-register limit of 18 warps per SM and a spill costs an L2 round trip)
     alignas(16) Phase ph[2];
@@ -205,25 +206,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 #ifndef GGB_WATCHDOG
 #define GGB_WATCHDOG 0
 #endif
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or the hint runs
+// out) instead of re-issuing the poll - sixteen consumer warps polling a term-buffer barrier took two thirds of the
+// issue slots away from the chain warp they were waiting for.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#if GGB_WATCHDOG
     uint32_t done = 0;
+#if GGB_WATCHDOG
     for (uint32_t spins = 0; !done; spins++) {
+#else
+    while (!done) {
+#endif
         asm volatile(
             "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n}\n"
             : "=r"(done)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(1000000u)
             : "memory");
-        if (spins > (1u << 26)) __trap();
-    }
-#else
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\nbra WAIT_LOOP;\nWAIT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+#if GGB_WATCHDOG
+        if (spins > (1u << 22)) __trap();
 #endif
+    }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier.  The weight stream is read once
 // per token and is 11x the L2: it carries an evict-first policy so that it does not push the small hot data
@@ -303,12 +306,22 @@ __device__ __forceinline__ float exp_f16(const DecoderParams &P, float x) {
     if (P.exp_compute == 2) return exp_f16_fast(half_bits_to_float(hb));
     return exp_f16_computed(half_bits_to_float(hb));
 }
-__global__ void exp_check_kernel(const uint16_t *table, int *mismatches) { // [0]: double form, [1]: fp32 form
+// gelu with the reference's fp16-table semantics, table[h] = fp16(gelu_f32(fp32(h))) ([UPSTREAM] ggml_gelu_f32: the tanh
+// approximation in fp32), COMPUTED with the device tanhf and every operator rounded as the host rounds it; used only
+// after the same exhaustive check (the lookup it replaces is an L2 round trip inside the chain warps' GeGLU)
+__device__ __forceinline__ uint16_t gelu_f16_computed(float x) {
+    const float A = 0.044715f, S = 0.79788456080286535587989211986876f;
+    const float arg = __fmul_rn(__fmul_rn(S, x), __fadd_rn(1.0f, __fmul_rn(__fmul_rn(A, x), x)));
+    return float_to_half_bits(__fmul_rn(__fmul_rn(0.5f, x), __fadd_rn(1.0f, tanhf(arg))));
+}
+__global__ void exp_check_kernel(const uint16_t *table, const uint16_t *gelu_table, int *mismatches) {
+    // [0]: double exp, [1]: fp32 exp, [2]: gelu
     const uint32_t hb = blockIdx.x * blockDim.x + threadIdx.x;
     if (hb >= 65536u || (hb & 0x7FFFu) > 0x7C00u) return;
     const float x = half_bits_to_float((uint16_t)hb);
     if (float_to_half_bits(exp_f16_computed(x)) != table[hb]) atomicAdd(mismatches, 1);
     if (float_to_half_bits(exp_f16_fast(x)) != table[hb]) atomicAdd(mismatches + 1, 1);
+    if (gelu_f16_computed(x) != gelu_table[hb]) atomicAdd(mismatches + 2, 1);
 }
 
 // ---- flagged words.  An aligned 8-byte access is single-copy atomic, so payload and tag are seen together;
@@ -710,6 +723,8 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 // acc + term[b0] + term[b0 + 1] + ... (len terms, one by one: the reference's  sumf += term  loop); row = shared address
 // of the lane's 64-term run; len is the same for every lane of the warp
+// acc + term[b0] + term[b0 + 1] + ... (len terms, one by one: the reference's  sumf += term  loop); row = shared address
+// of the lane's 64-term run; len is the same for every lane of the warp
 __device__ __forceinline__ float chain_add(uint32_t row, int b0, int len, float acc) {
     if (len == 64) { // the common case, fully unrolled: 16 loads up front, then the 64 dependent adds
         float4 t[16];
@@ -740,6 +755,29 @@ __device__ __forceinline__ float chain_add(uint32_t row, int b0, int len, float 
     return acc;
 }
 
+
+// GeGLU (fp16 gelu table) + quantize_row_q8_0 of a 32-row group whose gate and up rows are finished (gu[0..31] = gate
+// rows, gu[32..63] = up rows): lane = row of the group.  A lane's code joins three neighbours' in one flagged word of
+// the packed row; the block's fp16 scale and the sum of its codes (the Q4_0 bias of DOWN's dot products) share one more.
+__device__ __forceinline__ void geglu_unit(const DecoderParams &P, const float *gu, int ug, ll_t *out_ll, float *act_dump,
+                                           bool bcast, uint32_t tag, int lane) {
+    const uint16_t gb = float_to_half_bits(gu[lane]);
+    const float gl = half_bits_to_float((P.gelu_compute && (gb & 0x7FFFu) <= 0x7C00u) ? gelu_f16_computed(half_bits_to_float(gb))
+                                                                                    : __ldg(P.gelu_table + gb));
+    const float x = __fmul_rn(gl, gu[32 + lane]);
+    if (act_dump) act_dump[(size_t)ug * 32 + lane] = x;
+    const float amax = warp_max_f32(fabsf(x));
+    const float dd = __fdiv_rn(amax, 127.0f);
+    const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
+    const int qi = (int)roundf(__fmul_rn(x, id));
+    uint32_t w = (uint32_t)qi & 0xFFu;
+    w |= (__shfl_down_sync(0xffffffffu, w, 1) & 0xFFu) << 8;
+    w |= (__shfl_down_sync(0xffffffffu, w, 2) & 0xFFFFu) << 16;
+    if ((lane & 3) == 0) ll_put(P, bcast, out_ll + (size_t)ug * 8 + (lane >> 2), w, tag);
+    const int qs = __reduce_add_sync(0xffffffffu, qi);
+    if (lane == 0)
+        ll_put(P, bcast, out_ll + P.F / 4 + ug, ((uint32_t)qs << 16) | (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
+}
 
 // ---------------------------------------------------------------- a chain warp's share of a mat-vec phase
 // The slots of a CTA's share go round-robin to the kNCH chain warps.  For its slots a chain warp waits for the consumers'
@@ -800,35 +838,6 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
         if (out_ll) ll_put_f(P, bcast, out_ll + gi, total, tag);
         if (total > best.v || best.i < 0) best = Best{total, gi};
     };
-    // GeGLU (fp16 gelu table) + quantize_row_q8_0 of a 32-row group whose gate and up rows are all in: lane = row of
-    // the group.  A lane's code joins three neighbours' in one flagged word of the packed row; the block's fp16 scale and
-    // the sum of its codes (the Q4_0 bias of DOWN's dot products) share one more.
-    const int ug0 = ph.u_off + u0;
-    float *const act_dump = ph.f32_out;
-    ll_t *const oq = out_ll, *const od = out_ll + P.F / 4;
-    auto geglu = [&](int u) {
-        const int ug = ug0 + u;
-        const float gl = half_bits_to_float(__ldg(P.gelu_table + float_to_half_bits(GU[64 * u + lane])));
-        const float x = __fmul_rn(gl, GU[64 * u + 32 + lane]);
-        if (act_dump) act_dump[(size_t)ug * 32 + lane] = x;
-        const float amax = warp_max_f32(fabsf(x));
-        const float dd = __fdiv_rn(amax, 127.0f);
-        const float id = dd != 0.0f ? __fdiv_rn(1.0f, dd) : 0.0f;
-        const int qi = (int)roundf(__fmul_rn(x, id));
-        uint32_t w = (uint32_t)qi & 0xFFu;
-        w |= (__shfl_down_sync(0xffffffffu, w, 1) & 0xFFu) << 8;
-        w |= (__shfl_down_sync(0xffffffffu, w, 2) & 0xFFFFu) << 16;
-        if ((lane & 3) == 0) ll_put(P, bcast, oq + (size_t)ug * 8 + (lane >> 2), w, tag);
-        const int qs = __reduce_add_sync(0xffffffffu, qi);
-        if (lane == 0)
-            ll_put(P, bcast, od + ug, ((uint32_t)qs << 16) | (uint32_t)__half_as_ushort(__float2half_rn(dd)), tag);
-    };
-    // 32-row groups complete once the pass position (section, index) is reached
-    auto complete = [&](int sc, int r) {
-        if (quad) return sc >= kA ? (r >> 4) : 0;
-        return sc >= kA ? (npairs >> 5) : (sc == kA - 1 ? (r >> 5) : 0);
-    };
-
     // ROW-LANE MODE (multi-segment phases whose CTA share is <= 32 rows: O / DOWN): lane = row for the whole phase, the
     // accumulator stays in a register from segment to segment, and ONE chain warp takes every slot (the segments of a
     // row are a dependent chain anyway: handing it from warp to warp only adds latency)
@@ -845,10 +854,9 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
         if (mine) {
             if (PROF) pt0 = clock64();
             mbar_wait(tf0 + 8 * tb, tpar);
-            if (PROF) p_wait += clock64() - pt0;
+            if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; const int k = m0 / F::PPS; if (prof && lane == 0 && ci == 0 && k < 8) P.prof[64 * cta + 48 + 2 * k] = t1 - p_begin; }
         }
         const uint32_t tbase = terms0 + (uint32_t)tb * (uint32_t)(kTermFloats * 4);
-        const int done_before = complete(segc, rem);
         int jj = 0;
 #pragma unroll 1
         while (jj < cnt) {
@@ -884,7 +892,7 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
                     const int idx = rem + (j - jj);
                     // rows that continue an accumulator: every earlier slot must be committed
                     if (isB ? kf > 0 : segc > 0) {
-                        while (S.done_slot < gslot) {}
+                        while (S.done_slot < gslot) __nanosleep(20);
                         __threadfence_block();
                     }
                     if (!isB) {
@@ -919,11 +927,7 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
                     }
                 }
                 __syncwarp();
-                if (PROF) {
-                    const long long t1 = clock64();
-                    p_chain += t1 - pt0;
-                    if (prof && rowlane && lane == 0 && p_rounds <= 8) P.prof[32 * cta + 23 + p_rounds] = t1 - p_begin; // end of round r
-                }
+                if (PROF) p_chain += clock64() - pt0;
             }
             jj += run;
             rem += run;
@@ -937,25 +941,19 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
             __syncwarp();
             if (lane == 0) mbar_arrive(te0 + 8 * tb); // the terms are consumed: the consumers may refill the buffer
             if (!rowlane) { // commit in slot order; then the GATE_UP groups this slot completed
-                while (S.done_slot != gslot) {}
-                if (handoff) __threadfence_block();
-                if (kind == PH_GATE_UP) {
-                    const int done_after = complete(segc, rem);
-#pragma unroll 1
-                    for (int u = done_before; u < done_after; u++) geglu(u);
-                }
-                if (handoff) __threadfence_block(); // this warp's accumulator / staging writes before the commit
+                if (handoff) __threadfence_block(); // this warp's accumulator / staging writes before its commit
+                while (S.done_slot != gslot) __nanosleep(20);
                 __syncwarp();
                 if (lane == 0) S.done_slot = gslot + 1;
             }
-            if (PROF) p_fin += clock64() - pt0;
+            if (PROF) { const long long t1 = clock64(); p_fin += t1 - pt0; const int k = m0 / F::PPS; if (prof && lane == 0 && ci == 0 && k < 8) P.prof[64 * cta + 49 + 2 * k] = t1 - p_begin; }
         }
         tmask ^= 1u << tb;
         if (++tb == nbuf) tb = 0;
         if (++turn == kNCH) turn = 0;
     }
     if (PROF && prof && lane == 0 && ci == 0) {
-        long long *o = P.prof + 32 * cta + 16;
+        long long *o = P.prof + 64 * cta + 16;
         o[0] = p_wait; o[1] = p_chain; o[2] = p_fin; o[3] = p_rounds; o[4] = clock64() - p_begin; o[5] = n_passes;
         o[6] = p_add; o[7] = p_row;
     }
@@ -980,7 +978,7 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
     }
 }
 
-#define PROF_STAMP(i) do { if (PROF && prof && (int)threadIdx.x == kC0) P.prof[32 * cta + (i)] = clock64(); } while (0)
+#define PROF_STAMP(i) do { if (PROF && prof && (int)threadIdx.x == kC0) P.prof[64 * cta + (i)] = clock64(); } while (0)
 // ---------------------------------------------------------------- SCORE
 // kq = mul_mat(k, q) (ref: src/gemma_model.cpp:465-474) for one (kv head, 32-position chunk, half of the query heads)
 // per item; rope + Q scale are applied to q on load, and the item that owns the newest position ropes K, rounds K / V to
@@ -1343,6 +1341,7 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
     const uint32_t act = smem_u32(S.u);
     int slot = S.wst[warp][0];
     uint32_t parity = (uint32_t)S.wst[warp][1], tmask = (uint32_t)S.wst[warp][2];
+    const int gslot0 = S.wst[warp][4]; // slots of earlier phases (the numbering of S.done_slot)
     int u0, u1;
     unit_range(cta, G, ph.rot, ph.uq, ph.ur, u0, u1);
     const int n_passes = (u1 - u0) * ph.unit_passes;
@@ -1381,11 +1380,11 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
             }
             if (PROF) pt0 = clock64();
             mbar_wait(full0 + 8 * slot, parity);
-            if (PROF) { const long long t1 = clock64(); p_full += t1 - pt0; pt0 = t1; }
+            if (PROF) { const long long t1 = clock64(); p_full += t1 - pt0; pt0 = t1; if (prof && tid == 0 && i < 4) P.prof[64 * cta + 32 + 3 * i] = t1 - p_begin; }
             // the chain warp is done with this term buffer's previous slot.  EVERY warp waits, also one without a
             // pass in this slot: its arrival below must not be counted for the buffer's previous use
             mbar_wait(te0 + 8 * tb, ((tmask >> tb) & 1u) ^ 1u);
-            if (PROF) { const long long t1 = clock64(); p_te += t1 - pt0; pt0 = t1; }
+            if (PROF) { const long long t1 = clock64(); p_te += t1 - pt0; pt0 = t1; if (prof && tid == 0 && i < 4) P.prof[64 * cta + 33 + 3 * i] = t1 - p_begin; }
             if (j < cnt) {
                 const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;
                 float term[4];
@@ -1399,7 +1398,7 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
                 }
             }
             __syncwarp();
-            if (PROF) p_comp += clock64() - pt0;
+            if (PROF) { const long long t1 = clock64(); p_comp += t1 - pt0; if (prof && tid == 0 && i < 4) P.prof[64 * cta + 34 + 3 * i] = t1 - p_begin; }
             if (lane == 0) {
                 mbar_arrive(empty0 + 8 * slot);
                 mbar_arrive(tf0 + 8 * tb);
@@ -1416,9 +1415,26 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
         S.wst[warp][0] = slot;
         S.wst[warp][1] = (int)parity;
         S.wst[warp][2] = (int)tmask;
+        S.wst[warp][4] = gslot0 + (n_passes + F::PPS - 1) / F::PPS;
+    }
+    if (kind == PH_GATE_UP) {
+        // GeGLU + quantize of the CTA's 32-row groups, dealt to the consumer warps once their passes are done (the
+        // chain warps only finish rows: their time per slot is what the pass loop waits for).  Group u is complete when
+        // the slot holding the last pass of its rows is committed.
+        const bool quad = QUAD && ph.quad != 0;
+        const int base_last = quad ? kA * npairs : (kA - 1) * npairs, per = quad ? 16 : 32;
+        const float *GU = reinterpret_cast<const float *>(S.u + U_GU);
+#pragma unroll 1
+        for (int u = warp; u < u1 - u0; u += kCW) {
+            const int m_end = base_last + per * (u + 1) - 1;
+            const int need = gslot0 + m_end / F::PPS + 1;
+            while (S.done_slot < need) __nanosleep(20);
+            __threadfence_block();
+            geglu_unit(P, GU + 64 * u, ph.u_off + u0 + u, ph.out_ll, ph.f32_out, ph.bcast != 0, tag, lane);
+        }
     }
     if (PROF && prof && tid == 0) {
-        long long *o = P.prof + 32 * cta;
+        long long *o = P.prof + 64 * cta;
         o[0] = p_pro; o[1] = p_full; o[2] = p_te; o[3] = p_comp; o[4] = clock64() - p_begin; o[5] = n_passes;
     }
 }
@@ -1450,7 +1466,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
     __syncthreads();
     const int n_pos = min(max(P.state[1], 0), P.n_ctx - 1) + 1;
     const uint32_t tag = *P.seq + 1u;
-    if (tid < (kCW + kNCH) * 4) (&S.wst[0][0])[tid] = 0;
+    if (tid < (kCW + kNCH) * 5) (&S.wst[0][0])[tid] = 0;
     if (tid == 0) {
         S.sched[0] = (n_pos + kChunk - 1) / kChunk;
         S.sched[3] = min(max(P.state[0], 0), P.V - 1);
@@ -1708,16 +1724,17 @@ int ggb_decoder_create_tp(const ggb_decoder_dims *dims, const ggb_decoder_layer 
     P.exp_table = ggb_exp_table_dev(); P.gelu_table = ggb_gelu_table_dev();
     P.rope_cos = ggb_rope_cos_dev(); P.rope_sin = ggb_rope_sin_dev();
     {   // does the computed exp reproduce the table?  (GGB_EXP_TABLE=1 forces the lookup)
-        int *d_mis = nullptr, h_mis[2] = {-1, -1};
+        int *d_mis = nullptr, h_mis[3] = {-1, -1, -1};
         const char *force = getenv("GGB_EXP_TABLE");
-        if (!(force && atoi(force)) && cudaMalloc(&d_mis, 2 * sizeof(int)) == cudaSuccess) {
-            cudaMemsetAsync(d_mis, 0, 2 * sizeof(int), ggb_cuda_stream());
-            exp_check_kernel<<<256, 256, 0, ggb_cuda_stream()>>>(P.exp_table, d_mis);
-            if (cudaMemcpyAsync(h_mis, d_mis, 2 * sizeof(int), cudaMemcpyDeviceToHost, ggb_cuda_stream()) != cudaSuccess ||
+        if (!(force && atoi(force)) && cudaMalloc(&d_mis, 3 * sizeof(int)) == cudaSuccess) {
+            cudaMemsetAsync(d_mis, 0, 3 * sizeof(int), ggb_cuda_stream());
+            exp_check_kernel<<<256, 256, 0, ggb_cuda_stream()>>>(P.exp_table, P.gelu_table, d_mis);
+            if (cudaMemcpyAsync(h_mis, d_mis, 3 * sizeof(int), cudaMemcpyDeviceToHost, ggb_cuda_stream()) != cudaSuccess ||
                 cudaStreamSynchronize(ggb_cuda_stream()) != cudaSuccess)
-                h_mis[0] = h_mis[1] = -1;
+                h_mis[0] = h_mis[1] = h_mis[2] = -1;
             cudaFree(d_mis);
         }
+        P.gelu_compute = h_mis[2] == 0 ? 1 : 0;
         P.exp_compute = h_mis[1] == 0 ? 2 : (h_mis[0] == 0 ? 1 : 0);
         if (const char *e2 = getenv("GGB_EXP_MODE")) P.exp_compute = std::min(P.exp_compute, std::max(atoi(e2), 0));
     }
@@ -2026,7 +2043,7 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
     const int np = (int)D->phases.size();
     GGB_CHECK_ARG(max_phases >= np, "trace buffer holds %d phases, need %d", max_phases, np);
     const size_t bytes1 = (size_t)np * D->grid * 4 * sizeof(long long);
-    const size_t bytes = bytes1 + (size_t)D->grid * 32 * sizeof(long long); // + [grid][32] sums inside phase GGB_PROF_PHASE
+    const size_t bytes = bytes1 + (size_t)D->grid * 64 * sizeof(long long); // + [grid][32] sums inside phase GGB_PROF_PHASE
     GGB_CHECK_ARG((size_t)max_phases * D->grid * 4 * sizeof(long long) >= bytes, "trace buffer too small");
     long long *dev = nullptr;
     GGB_CUDA(cudaMalloc(&dev, bytes));

@@ -1,5 +1,6 @@
 // ubench_chain: how long does one chain round take for a lone warp?  16 x LDS.128 + 64 dependent FADDs.
 #include <cstdio>
+#include <cstdint>
 #include <cuda_runtime.h>
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 r;

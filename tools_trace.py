@@ -61,7 +61,16 @@ def main():
             print("   chain warp: wait terms, chain, finish (incl. GeGLU), rounds, total, passes, of chain: adds, row finish")
             print("   median", np.round(np.median(pr[:, 16:24], axis=0), 2)); print("   max   ", np.round(pr[:, 16:24].max(axis=0), 2))
             print("   (counts are shown divided by 1965)")
+            print("   consumer warp 0, slots 0..3: (weights arrived, term buffer free, terms stored) us since phase start:", np.round(np.median(pr[:, 32:44], axis=0), 2))
+            print("   chain warp 0, its slots: (terms arrived, slot done) us since phase start:", np.round(np.median(pr[:, 48:64], axis=0), 2))
             print("   row-lane mode: end of chain rounds 1..8, us since phase start (median)", np.round(np.median(pr[:, 24:32], axis=0), 2))
+    print("layer 5, per phase: CTA start / inputs-arrived / end relative to the previous phase's last end (min, median, max us)")
+    prev = st[29][:, 2].max()
+    for pi in range(30, 36):
+        s_ = st[pi] - prev
+        f = lambda a: "%5.2f %5.2f %5.2f" % (a.min(), np.median(a), a.max())
+        print("  %-8s start %s | arrived %s | end %s" % (NAMES[kinds[pi]], f(s_[:, 0]), f(s_[:, 1]), f(s_[:, 2])))
+        prev = st[pi][:, 2].max()
     print("last phases:")
     for r in rows[-2:]:
         print("  %-8s crit %6.2f  prologue %5.2f / %5.2f  work %5.2f  ctas %d" % r[1:])
