@@ -111,6 +111,7 @@ _CUDA_SIG = {
     "ggb_op_attn_prefill": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]),
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]),
     "ggb_decoder_create_tp": (i32, [vp, vp, vp, vp, vp, i32, i32, P(vp)]), "ggb_decoder_step": (i32, [vp]),
+    "ggb_decoder_kv_heads_local": (i32, [i32, i32, i32]),
     "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),
     "ggb_decoder_exp_computed": (i32, [vp]),
     "ggb_comm_unique_id": (i32, [vp]), "ggb_comm_init": (i32, [vp, i32, i32]), "ggb_comm_destroy": (i32, []),

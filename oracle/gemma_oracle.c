@@ -296,11 +296,7 @@ void orc_hpc_mul_mat(orc_model *m, int64_t ne01, int64_t ne11, int64_t ne12, int
 /* ggml_mul_mat node: INIT stage quantises the T activation rows to Q8_0 ([UPSTREAM]
  * ggml_compute_forward_mul_mat, "mmstage_init" ref: notes.md:91), COMPUTE = hpc mul_mat.
  * x: [T][K] f32, out: [T][N] f32. */
-int orc_x_mix[3] = {0, 0, 0}; /* EXPERIMENT (order == 2): order of mat-vec, norm, attention */
-extern int orc_x_attn_variant;
-void orc_set_mix(int mv, int nm, int at) { orc_x_mix[0] = mv; orc_x_mix[1] = nm; orc_x_mix[2] = at; orc_x_attn_variant = at; }
 static void node_mul_mat(orc_model *m, const otensor *w, const float *x, int T, float *out, int order) {
-    if (order == 2) order = orc_x_mix[0];
     const int64_t K = w->cols, N = w->rows;
     const size_t rs = orc_row_size(ORC_TYPE_Q8_0, K);
     char *wdata = (char *)malloc(rs * (size_t)T);
@@ -311,10 +307,9 @@ static void node_mul_mat(orc_model *m, const otensor *w, const float *x, int T, 
 }
 
 static void node_norm(const orc_model *m, const float *x, const float *w, int T, int64_t E, float *y, int order) {
-    if (order == 2) order = orc_x_mix[1];
+    (void)order;
     for (int t = 0; t < T; t++) {
-        if (order) orc_rms_norm_dev(E, x + (size_t)t * E, m->cfg.eps, y + (size_t)t * E);
-        else orc_rms_norm(E, x + (size_t)t * E, m->cfg.eps, y + (size_t)t * E);
+        orc_rms_norm(E, x + (size_t)t * E, m->cfg.eps, y + (size_t)t * E);
         orc_mul(E, y + (size_t)t * E, w, y + (size_t)t * E);
     }
 }
@@ -332,11 +327,7 @@ static void attn_run(void *a) {
     const int64_t QD = (int64_t)c->n_head * c->head_dim, KD = (int64_t)c->n_head_kv * c->head_dim;
     for (int t = j->t0; t < j->t1; t++) {
         const int64_t n_pos = j->pos0 + t + 1;
-        if (j->order == 2 ? orc_x_mix[2] : j->order)
-            orc_attn_decode_dev(c->n_head, c->n_head_kv, c->head_dim, n_pos, j->q + (size_t)t * QD, j->m->kc[j->il],
-                                j->m->vc[j->il], KD, j->out + (size_t)t * QD);
-        else
-            orc_attn_decode_ref(c->n_head, c->n_head_kv, c->head_dim, n_pos, c->n_ctx, j->q + (size_t)t * QD,
+        orc_attn_decode_ref(c->n_head, c->n_head_kv, c->head_dim, n_pos, c->n_ctx, j->q + (size_t)t * QD,
                                 j->m->kc[j->il], j->m->vc[j->il], KD, j->out + (size_t)t * QD);
     }
     free(j);

@@ -42,7 +42,7 @@ void orc_model_free(orc_model *m);
 const void *orc_model_tensor(const orc_model *m, int tensor_id, int64_t *rows, int64_t *cols, int64_t *nbytes);
 void orc_model_reset(orc_model *m); /* zero the KV cache */
 void orc_model_fill_kv_synth(orc_model *m, uint64_t seed);
-/* Run n_tokens tokens at positions pos0.. (prefill if n_tokens > 1).  order: 0 REF, 1 DEV.
+/* Run n_tokens tokens at positions pos0.. (prefill if n_tokens > 1).  order: ignored (there is one order, the scalar ggml one).
  * logits_all != 0 computes the output projection for every token as the reference does
  * (ref: src/gemma_model.cpp:740); logits_last receives the last token's n_vocab logits. */
 int orc_model_forward(orc_model *m, const int32_t *tokens, int n_tokens, int pos0, int order,

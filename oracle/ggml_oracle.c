@@ -214,51 +214,6 @@ void orc_vec_dot_q8_0_q8_0(int n, float *s, const void *vx, const void *vy) {
     *s = sumf;
 }
 
-/* xor-butterfly over 32 lanes, offsets 16,8,4,2,1: every lane ends with the same value. */
-static float butterfly32f(float lane[32]) {
-    for (int off = 16; off >= 1; off >>= 1) {
-        float nxt[32];
-        for (int l = 0; l < 32; l++) nxt[l] = lane[l] + lane[l ^ off];
-        memcpy(lane, nxt, sizeof(nxt));
-    }
-    return lane[0];
-}
-static double butterfly32d(double lane[32]) {
-    for (int off = 16; off >= 1; off >>= 1) {
-        double nxt[32];
-        for (int l = 0; l < 32; l++) nxt[l] = lane[l] + lane[l ^ off];
-        memcpy(lane, nxt, sizeof(nxt));
-    }
-    return lane[0];
-}
-
-/* DEV order of the sm_100a mat-vec kernels (gemma.ggml_b200/csrc/matvec.cuh): same per-block
- * terms as the scalar loops, summed as: segments of 64 blocks; lane l of a warp sums blocks
- * seg+l, seg+l+32 (those < nb) sequentially from 0.0f; xor-butterfly;
- * segment totals added in order. */
-#define ORC_DEV_DOT(NAME, XT, TERM)                                                         \
-    void NAME(int n, float *s, const void *vx, const void *vy) {                           \
-        const int nb = n / ORC_QK;                                                          \
-        const XT *x = (const XT *)vx;                                                       \
-        const orc_block_q8_0 *y = (const orc_block_q8_0 *)vy;                               \
-        float total = 0.0f;                                                                 \
-        for (int seg = 0, si = 0; seg < nb; seg += ORC_DEV_SEG_BLOCKS, si++) {              \
-            float lane[32];                                                                 \
-            for (int l = 0; l < 32; l++) {                                                  \
-                float acc = 0.0f;                                                           \
-                for (int t = 0; t < ORC_DEV_SEG_BLOCKS / 32; t++) {                         \
-                    const int b = seg + l + 32 * t;                                         \
-                    if (b < nb) acc += TERM(&x[b], &y[b]);                                  \
-                }                                                                           \
-                lane[l] = acc;                                                              \
-            }                                                                               \
-            const float segsum = butterfly32f(lane);                                        \
-            total = (si == 0) ? segsum : total + segsum;                                    \
-        }                                                                                   \
-        *s = total;                                                                         \
-    }
-ORC_DEV_DOT(orc_vec_dot_q4_0_q8_0_dev, orc_block_q4_0, q4_block_term)
-ORC_DEV_DOT(orc_vec_dot_q8_0_q8_0_dev, orc_block_q8_0, q8_block_term)
 
 /* [UPSTREAM] ggml_vec_dot_f16 scalar branch; ref: src/kernals.cl:158-164 (double accumulator). */
 void orc_vec_dot_f16(int n, float *s, const uint16_t *x, const uint16_t *y) {
@@ -268,12 +223,11 @@ void orc_vec_dot_f16(int n, float *s, const uint16_t *x, const uint16_t *y) {
 }
 
 void orc_vec_dot(int type, int order, int n, float *s, const void *vx, const void *vy) {
+    (void)order; /* there is one order: the scalar ggml one */
     if (type == ORC_TYPE_Q4_0) {
-        if (order) orc_vec_dot_q4_0_q8_0_dev(n, s, vx, vy);
-        else orc_vec_dot_q4_0_q8_0(n, s, vx, vy);
+        orc_vec_dot_q4_0_q8_0(n, s, vx, vy);
     } else if (type == ORC_TYPE_Q8_0) {
-        if (order) orc_vec_dot_q8_0_q8_0_dev(n, s, vx, vy);
-        else orc_vec_dot_q8_0_q8_0(n, s, vx, vy);
+        orc_vec_dot_q8_0_q8_0(n, s, vx, vy);
     } else if (type == ORC_TYPE_F16) {
         orc_vec_dot_f16(n, s, (const uint16_t *)vx, (const uint16_t *)vy);
     } else {
@@ -310,25 +264,6 @@ void orc_rms_norm(int64_t n, const float *x, float eps, float *y) {
     for (int64_t i = 0; i < n; i++) y[i] = x[i] * scale;
 }
 
-/* DEV order (csrc/common.cuh block_sum_f64): 256 threads, thread t sums i = t, t+256, ... in
- * double from 0.0; xor-butterfly per warp; the 8 warp totals added in warp order. */
-void orc_rms_norm_dev(int64_t n, const float *x, float eps, float *y) {
-    double warp_tot[ORC_DEV_NORM_THREADS / 32];
-    for (int w = 0; w < ORC_DEV_NORM_THREADS / 32; w++) {
-        double lane[32];
-        for (int l = 0; l < 32; l++) {
-            double acc = 0.0;
-            for (int64_t i = w * 32 + l; i < n; i += ORC_DEV_NORM_THREADS) acc += (double)(x[i] * x[i]);
-            lane[l] = acc;
-        }
-        warp_tot[w] = butterfly32d(lane);
-    }
-    double sum = warp_tot[0];
-    for (int w = 1; w < ORC_DEV_NORM_THREADS / 32; w++) sum += warp_tot[w];
-    const float mean = (float)(sum / (double)n);
-    const float scale = 1.0f / sqrtf(mean + eps);
-    for (int64_t i = 0; i < n; i++) y[i] = x[i] * scale;
-}
 
 void orc_mul(int64_t n, const float *a, const float *b, float *y) {
     for (int64_t i = 0; i < n; i++) y[i] = a[i] * b[i];
@@ -478,90 +413,6 @@ void orc_attn_decode_ref(int H, int Hkv, int d, int64_t n_pos, int64_t n_ctx, co
         }
     }
     free(q16); free(kq); free(mask); free(p); free(p16); free(vcol);
-}
-
-/* DEV decode attention (csrc/attention.cu): split-K over chunks of 32 positions.
- * Per (head, chunk): score = 32 lane partials (lane l: elements 8l..8l+7, fp32, sequential)
- * + butterfly; m = chunk max; e = exp_table[f16(score - m)]; l = butterfly sum of e over the
- * 32 positions (absent positions contribute 0.0f); acc[i] = sum_p e_p * V[p][i] sequential in p.
- * Combine (per head): M = max m_c; w_c = exp_table[f16(m_c - M)]; L = sum l_c*w_c and
- * O[i] = sum acc_c[i]*w_c sequential in c (mul then add); out = O / L. */
-int orc_x_attn_variant = 0; /* EXPERIMENT: 0 = DEV as built, 2 = w_c in fp32, 3 = global max first */
-void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
-                         const uint16_t *kcache, const uint16_t *vcache, int64_t kv_stride, float *out) {
-    const uint16_t *t = orc_exp_table();
-    const int G = H / Hkv;
-    const int C = ORC_DEV_ATTN_CHUNK;
-    const int64_t nchunk = (n_pos + C - 1) / C;
-    float *pm = (float *)malloc(sizeof(float) * (size_t)nchunk);
-    float *pl = (float *)malloc(sizeof(float) * (size_t)nchunk);
-    float *pacc = (float *)malloc(sizeof(float) * (size_t)nchunk * d);
-    float *q16f = (float *)malloc(sizeof(float) * (size_t)d);
-    for (int h = 0; h < H; h++) {
-        const int g = h / G;
-        for (int i = 0; i < d; i++) q16f[i] = orc_fp16_to_fp32(orc_fp32_to_fp16(q[(size_t)h * d + i]));
-        float GM = -INFINITY;
-        if (orc_x_attn_variant == 3) {
-            for (int64_t pz = 0; pz < n_pos; pz++) {
-                const uint16_t *krow = kcache + pz * kv_stride + (size_t)g * d;
-                float lane[32];
-                for (int l = 0; l < 32; l++) {
-                    float acc = 0.0f;
-                    for (int i = 8 * l; i < 8 * l + 8 && i < d; i++) acc += orc_fp16_to_fp32(krow[i]) * q16f[i];
-                    lane[l] = acc;
-                }
-                const float sc = butterfly32f(lane);
-                GM = sc > GM ? sc : GM;
-            }
-        }
-        for (int64_t c = 0; c < nchunk; c++) {
-            const int64_t p0 = c * C;
-            const int np = (int)((n_pos - p0) < C ? (n_pos - p0) : C);
-            float s[ORC_DEV_ATTN_CHUNK], e[ORC_DEV_ATTN_CHUNK];
-            float m = -INFINITY;
-            for (int j = 0; j < np; j++) {
-                const uint16_t *krow = kcache + (p0 + j) * kv_stride + (size_t)g * d;
-                float lane[32];
-                for (int l = 0; l < 32; l++) {
-                    float acc = 0.0f;
-                    for (int i = 8 * l; i < 8 * l + 8 && i < d; i++) acc += orc_fp16_to_fp32(krow[i]) * q16f[i];
-                    lane[l] = acc;
-                }
-                s[j] = butterfly32f(lane);
-                m = s[j] > m ? s[j] : m;
-            }
-            float lane[32];
-            if (orc_x_attn_variant == 3) m = GM;
-            for (int j = 0; j < 32; j++) {
-                if (j < np) {
-                    e[j] = orc_fp16_to_fp32(t[orc_fp32_to_fp16(s[j] - m)]);
-                    lane[j] = e[j];
-                } else {
-                    lane[j] = 0.0f;
-                }
-            }
-            pm[c] = m;
-            pl[c] = butterfly32f(lane);
-            for (int i = 0; i < d; i++) {
-                float acc = 0.0f;
-                for (int j = 0; j < np; j++)
-                    acc += e[j] * orc_fp16_to_fp32(vcache[(p0 + j) * kv_stride + (size_t)g * d + i]);
-                pacc[(size_t)c * d + i] = acc;
-            }
-        }
-        float M = -INFINITY;
-        for (int64_t c = 0; c < nchunk; c++) M = pm[c] > M ? pm[c] : M;
-        float L = 0.0f;
-        for (int i = 0; i < d; i++) out[(size_t)h * d + i] = 0.0f;
-        for (int64_t c = 0; c < nchunk; c++) {
-            float w = orc_fp16_to_fp32(t[orc_fp32_to_fp16(pm[c] - M)]);
-            if (orc_x_attn_variant >= 2) w = (float)exp((double)(pm[c] - M));
-            L += pl[c] * w;
-            for (int i = 0; i < d; i++) out[(size_t)h * d + i] += pacc[(size_t)c * d + i] * w;
-        }
-        for (int i = 0; i < d; i++) out[(size_t)h * d + i] = out[(size_t)h * d + i] / L;
-    }
-    free(pm); free(pl); free(pacc); free(q16f);
 }
 
 /* ------------------------------------------------------- synthetic weights */

@@ -17,11 +17,10 @@
  *   - loop / indexing / row partition: src/hpc.cpp:15-41, 245-273;
  *   - graph order and shapes: src/gemma_model.cpp:438-530, 665-747.
  *
- * Two accumulation orders are provided for every order-sensitive reduction:
- *   REF  — the scalar ggml order (the specification);
- *   DEV  — the deterministic order the sm_100a kernels use (documented per
- *          function), so GPU results can be compared BIT-EXACTLY, while
- *          REF-vs-DEV deviation is reported against a stated tolerance.
+ * There is ONE accumulation order: the scalar ggml order (one accumulator, elements / blocks in
+ * order; double accumulators where ggml's scalar code has them).  The sm_100a kernels reproduce it
+ * bit for bit, so every comparison in tests/ is a comparison of bits.  (`order` parameters are kept
+ * in a few signatures for ABI stability and are ignored.)
  * Compile with -ffp-contract=off: every fp32 expression below is evaluated
  * with one IEEE rounding per operator, left to right, as ISO C specifies.
  */
@@ -45,10 +44,6 @@ typedef struct { uint16_t d; uint8_t qs[ORC_QK / 2]; } orc_block_q4_0; /* 18 B *
 typedef struct { uint16_t d; int8_t qs[ORC_QK]; } orc_block_q8_0;      /* 34 B */
 #pragma pack(pop)
 
-/* DEV-order parameters (must match include/ggml_b200.h GGB_DEV_*) */
-#define ORC_DEV_SEG_BLOCKS 64 /* mat-vec: K is cut into segments of 64 blocks (2048 elements) */
-#define ORC_DEV_NORM_THREADS 256 /* rms_norm: 256 strided partials */
-#define ORC_DEV_ATTN_CHUNK 32 /* attention: positions per split-K chunk */
 
 /* ---- fp16 ---- */
 float orc_fp16_to_fp32(uint16_t h);
@@ -63,17 +58,12 @@ void orc_dequantize_row_q8_0(const orc_block_q8_0 *x, float *y, int64_t k);
 void orc_dequantize_row(int type, const void *x, float *y, int64_t k);
 
 /* ---- dot products ---- */
-/* REF: scalar ggml order (blocks in order, one fp32 accumulator). */
+/* scalar ggml order (blocks in order, one fp32 accumulator) */
 void orc_vec_dot_q4_0_q8_0(int n, float *s, const void *vx, const void *vy);
 void orc_vec_dot_q8_0_q8_0(int n, float *s, const void *vx, const void *vy);
-/* DEV: segments of 64 blocks; inside a segment 32 lane partials (lane l sums
- * blocks l, l+32 in that order from 0.0f), xor-butterfly 16,8,4,2,1,
- * segment sums added in segment order. */
-void orc_vec_dot_q4_0_q8_0_dev(int n, float *s, const void *vx, const void *vy);
-void orc_vec_dot_q8_0_q8_0_dev(int n, float *s, const void *vx, const void *vy);
 /* fp16·fp16, accumulated in double (src/kernals.cl:158-164). */
 void orc_vec_dot_f16(int n, float *s, const uint16_t *x, const uint16_t *y);
-/* generic dispatcher: order 0 = REF, 1 = DEV */
+/* generic dispatcher (order: ignored) */
 void orc_vec_dot(int type, int order, int n, float *s, const void *vx, const void *vy);
 
 /* ---- mul_mat as the reference's hpc.cpp runs it (single thread) ---- */
@@ -84,7 +74,6 @@ void orc_mul_mat_sub(int64_t start_row, int64_t end_row, int64_t shared_edge, in
 
 /* ---- element-wise / normalisation ops ---- */
 void orc_rms_norm(int64_t n, const float *x, float eps, float *y);     /* REF: sequential double sum */
-void orc_rms_norm_dev(int64_t n, const float *x, float eps, float *y); /* DEV: 256 strided partials */
 void orc_mul(int64_t n, const float *a, const float *b, float *y);
 void orc_add(int64_t n, const float *a, const float *b, float *y);
 void orc_scale(int64_t n, const float *x, float s, float *y);
@@ -107,11 +96,8 @@ int32_t orc_argmax(int64_t n, const float *x);
  * [n_ctx][Hkv*d]; n_pos = number of valid positions (pos+1).  out f32 [H][d].
  * REF restates kq = K16·f16(q) (double acc) -> soft_max_ext -> f16(P)·V16 (double acc),
  * over n_kv = roundup32-padded length with masked tail (src/gemma_model.cpp:326-335,428-436).
- * DEV restates the split-K kernel: chunks of 32 positions, per-chunk softmax via the
- * fp16 exp table, sequential combine in chunk order. */
+ */
 void orc_attn_decode_ref(int H, int Hkv, int d, int64_t n_pos, int64_t n_ctx, const float *q,
-                         const uint16_t *kcache, const uint16_t *vcache, int64_t kv_stride, float *out);
-void orc_attn_decode_dev(int H, int Hkv, int d, int64_t n_pos, const float *q,
                          const uint16_t *kcache, const uint16_t *vcache, int64_t kv_stride, float *out);
 
 /* ---- synthetic weights: counter-based, integer-exact ---- */

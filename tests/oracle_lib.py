@@ -14,7 +14,8 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
 TYPE_F32, TYPE_F16, TYPE_Q4_0, TYPE_Q8_0 = 0, 1, 2, 8
-REF, DEV = 0, 1
+REF = 0
+DEV = REF  # (historical alias: the device order IS the reference order now)
 QK = 32
 BLOCK_BYTES = {TYPE_Q4_0: 18, TYPE_Q8_0: 34}
 
@@ -64,7 +65,6 @@ def lib():
         "orc_vec_dot": (None, [i32, i32, i32, vp, vp, vp]),
         "orc_mul_mat_sub": (None, [i64, i64, i64, i64, i64, i64, i64, i64, i64, i64, vp, vp, vp, i32, i32]),
         "orc_rms_norm": (None, [i64, vp, f32, vp]),
-        "orc_rms_norm_dev": (None, [i64, vp, f32, vp]),
         "orc_mul": (None, [i64, vp, vp, vp]),
         "orc_rope_cache": (None, [i32, i32, f32, vp, vp]),
         "orc_rope_neox": (None, [i32, i32, i32, f32, vp, vp]),
@@ -74,7 +74,6 @@ def lib():
         "orc_soft_max_ext": (None, [i64, vp, vp, f32, vp]),
         "orc_argmax": (i32, [i64, vp]),
         "orc_attn_decode_ref": (None, [i32, i32, i32, i64, i64, vp, vp, vp, i64, vp]),
-        "orc_attn_decode_dev": (None, [i32, i32, i32, i64, vp, vp, vp, i64, vp]),
         "orc_synth_value": (f32, [u64, u64, u64, f32]),
         "orc_synth_row": (None, [u64, u64, i64, i64, f32, f32, vp]),
         "orc_model_create": (vp, [C.POINTER(Config), i32]),
@@ -160,7 +159,7 @@ def mul_mat(wtype, order, w_blocks, act_q8, k):
 def rms_norm(x, eps, order=REF):
     x = np.ascontiguousarray(x, dtype=np.float32)
     y = np.empty_like(x)
-    (lib().orc_rms_norm_dev if order else lib().orc_rms_norm)(x.size, _p(x), eps, _p(y))
+    lib().orc_rms_norm(x.size, _p(x), eps, _p(y))
     return y
 
 
@@ -216,11 +215,8 @@ def attn_decode(order, q, kcache, vcache, n_pos, n_ctx=None):
     stride = kcache.shape[1]
     Hkv = stride // d
     out = np.empty_like(q)
-    if order == DEV:
-        lib().orc_attn_decode_dev(H, Hkv, d, n_pos, _p(q), _p(kcache), _p(vcache), stride, _p(out))
-    else:
-        lib().orc_attn_decode_ref(H, Hkv, d, n_pos, n_ctx or kcache.shape[0], _p(q), _p(kcache), _p(vcache),
-                                  stride, _p(out))
+    lib().orc_attn_decode_ref(H, Hkv, d, n_pos, n_ctx or kcache.shape[0], _p(q), _p(kcache), _p(vcache),
+                              stride, _p(out))
     return out
 
 

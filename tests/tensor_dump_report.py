@@ -43,7 +43,7 @@ def main():
     om = O.Model(wtype=wtype, **dims)
     rep = (C.c_double * 5)()
     rows, summary = [], {}
-    for order, oname in ((O.DEV, "DEV"), (O.REF, "REF")):
+    for order, oname in ((O.REF, "DEV"), (O.REF, "REF")):
         otoks, _, _ = om.generate(prompt, n_decode, order)
         names = [(f"{cap}-{il}", om.capture(cap, il)) for il in range(dims["n_layer"]) for cap in sizes]
         names.append(("result_output", om.capture("result_output")))

@@ -52,7 +52,7 @@ def main():
                 logits = m.logits()  # collective (gathers the shards)
                 if rank == 0:
                     om = O.Model(wtype=wtype, sigma_embd=0.002, **dims)
-                    otoks, _, _ = om.generate(prompt, 7, O.DEV)
+                    otoks, _, _ = om.generate(prompt, 7, O.REF)
                     assert np.array_equal(toks, otoks), (fused, name, wtype, toks, otoks)
                     ol = om.capture("result_output")
                     assert np.array_equal(logits.view(np.uint32), ol.view(np.uint32)), (fused, name, wtype, np.abs(logits - ol).max())
