@@ -133,23 +133,33 @@ def cpu_reference_tokens_per_s(args, n_tokens, warm=1, budget_s=None):
     return done / dt, threads, dt, done
 
 
+def bench_config(args, world, lowering, kernels_per_step):
+    """the `config` object of a line: the SAME keys for both arms (the driver compares them)"""
+    return {"workload": workload_name(args), "parallelism": f"tp{world}" if world > 1 else "single",
+            "l2": "weights (1.41 GB for 2B Q4_0) > 126 MB L2: re-streamed from HBM every step, no flush needed",
+            "lowering": lowering, "graph": "one CUDA graph per token", "kernels_per_step": kernels_per_step}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be compiled
     (un-vendored ggml), so this is the oracle's restatement of its thread_pool mul_mat path
-    with all host threads (kind "port").  One step = one full decode token of the same workload; the timed
-    region is capped at ~150 s."""
+    with all host threads (kind "port": scalar vec_dot, not ggml's hand-written SIMD).  One step = one full decode
+    token of the same workload; the timed region is capped at ~150 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t_all0 = time.perf_counter()
-    warm = max(1, min(args.warmup, 2))
-    tps, threads, dt, done = cpu_reference_tokens_per_s(args, args.steps, warm=warm, budget_s=150.0)
+    warm = max(1, args.warmup)
+    # warm-up tokens are bounded in time as well (a token takes ~1 s on 16 cores): the count actually run is reported
+    tps_w, threads, dt_w, warm_done = cpu_reference_tokens_per_s(args, warm, warm=0, budget_s=20.0)
+    tps, threads, dt, done = cpu_reference_tokens_per_s(args, args.steps, warm=0, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "decode tokens/s", "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": warm, "ms_per_step": 1000.0 * dt / done,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 dot, fp32 accumulate",
+        "steps": args.steps, "warmup": args.warmup, "steps_timed": done, "warmup_run": warm_done,
+        "ms_per_step": 1000.0 * dt / done,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 dot (dp4a), fp32 accumulate",
         "data": "synthetic (seeded random-init Gemma-architecture weights in ggml quant format, synthetic KV)",
-        "config": {"workload": workload_name(args), "l2": "weights > L2 (CPU: > LLC)"},
+        "config": bench_config(args, args.gpus, "fused persistent decode kernel", 1),
         "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
                          "sample": f"{done} full decode tokens (of {args.steps} requested; timed region capped at 150 s), "
                                    f"oracle restatement of src/hpc.cpp thread_pool path (scalar ggml vec_dot, "
@@ -158,6 +168,118 @@ def run_reference(args):
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all0,
     }
     print(json.dumps(line), flush=True)
+
+
+def time_decode(G, L, m, steps, warmup, pos, barrier, dist):
+    """K graph-replayed steps, inputs resident, CUDA events on the launching stream; max over ranks"""
+    m.set_state(4242, pos, 0)
+    m.run_steps(warmup)
+    barrier()
+    L.ggb_prof_enable(1)
+    G.prof_reset()
+    barrier()
+    L.ggb_prof_start(b"bench_timed_region")
+    m.run_steps(steps)
+    L.ggb_prof_stop(b"bench_timed_region")
+    barrier()
+    ms, _ = G.prof_get("bench_timed_region")
+    L.ggb_prof_enable(0)
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def rank_bytes(m, dims, ctx, world):
+    """algorithmic bytes THIS GPU streams per token: its weight pass streams (row shards + replicated phases; 18 | 34 B
+    per 32 weights, the same figure as SURVEY 8d for one GPU) + the KV rows of the heads whose cache it holds"""
+    kv = dims["n_layer"] * 2 * m.rank_kv_heads * dims["head_dim"] * 2 * ctx
+    return m.rank_stream_bytes + kv
+
+
+def sub_record_7b(G, L, args, dist, rank, world, barrier, peak):
+    """BASELINE config 4 on the same run: Gemma-7B Q4_0, n_kv 2048, tensor parallel over the same ranks"""
+    dims = dict(G.GEMMA_7B, n_ctx=2048)
+    m = G.GemmaModel(G.make_config(wtype=2, **dims))
+    if world > 1:
+        m.init_tensor_parallel(dist, rank, world)
+    m.init_synthetic_weights(); m.init_kv_cache(); m.fill_kv_cache_synthetic(99)
+    m.build_compute_graph(capture_acts=False, fused=True)
+    steps = max(16, min(args.steps, 128))
+    ms = time_decode(G, L, m, steps, max(3, min(args.warmup, 8)), 2047, barrier, dist)
+    rb = rank_bytes(m, dims, 2048, world)
+    step_s = ms / steps / 1000.0
+    rec = {"workload": "gemma-7b q4_0 batch-1 decode, n_kv=2048 pinned", "value": steps / (ms / 1000.0), "unit": "tokens/s",
+           "ms_per_step": ms / steps, "steps": steps, "parallelism": f"tp{world}" if world > 1 else "single",
+           "per_gpu_bytes_per_step": rb, "per_gpu_gbs": rb / step_s / 1e9, "per_gpu_frac_of_peak": rb / step_s / 1e9 / peak}
+    m.close()
+    return rec
+
+
+def sub_record_prefill(G, L, args):
+    """BASELINE config 3 on the same run (1 GPU): Gemma-2B Q8_0, prefill of 512 tokens through the tcgen05 GEMMs"""
+    T = 512
+    dims = dict(G.GEMMA_2B, n_ctx=T)
+    m = G.GemmaModel(G.make_config(wtype=8, **dims))
+    m.init_synthetic_weights(); m.init_kv_cache(); m.build_compute_graph(capture_acts=False, fused=True)
+    prompt = ((1 + 7919 * np.arange(T)) % dims["n_vocab"]).astype(np.int32)
+    for _ in range(3):
+        m.prefill(prompt, 0)
+    G.sync()
+    steps = 5
+    L.ggb_prof_enable(1)
+    G.prof_reset()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.prefill(prompt, 0)
+    G.sync()
+    wall = time.perf_counter() - t0
+    gemm_ms, _ = G.prof_get("op_mul_mat")
+    L.ggb_prof_enable(0)
+    peak_tf = 1396.9
+    try:
+        peak_tf = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        pass
+    ach = m.prefill_gemm_flops / (gemm_ms / steps / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+    rec = {"workload": "gemma-2b q8_0 prefill of 512 tokens (host call: H2D ids, per-op launches, D2H token)",
+           "value": T * steps / wall, "unit": "tokens/s", "ms_per_step": 1000.0 * wall / steps,
+           "gemm_tflops": ach, "gemm_frac_of_tensor_peak": ach / peak_tf, "gemm_ms_per_step": gemm_ms / steps,
+           "tensor_peak_tflops": peak_tf, "kernel": "gemm_bf16w_kernel (tcgen05.mma kind::f16, TMEM accumulators)"}
+    m.close()
+    return rec
+
+
+def mul_mat_dropin_us(G):
+    """the plugin boundary itself: the reference's mul_mat entry (host buffers in, host buffer out, src/hpc.h:22-32)
+    per Gemma-2B Q4_0 shape, one column: us per call after the weight is resident (H2D of the Q8_0 row + kernel + D2H)"""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    out = {}
+    L = G.cuda_lib()
+    rng = np.random.default_rng(5)
+    for name, (K, N) in {"q/o 2048x2048": (2048, 2048), "gate/up 2048x16384": (2048, 16384), "down 16384x2048": (16384, 2048)}.items():
+        nb = K // 32
+        w = rng.integers(0, 256, size=(N, nb * 18), dtype=np.uint8)
+        w[:, 0::18] = 0; w[:, 1::18] = 0x1c  # fp16 scales ~ 0.004
+        act = rng.integers(0, 256, size=(nb * 34,), dtype=np.uint8)
+        act[0::34] = 0; act[1::34] = 0x20
+        dst = np.zeros(N, dtype=np.float32)
+        call = lambda: L.ggb_mul_mat(N, 1, 1, nb * 18, 1, N * 4, N * 4, nb * 34, K, w.ctypes.data_as(C.c_void_p),
+                                     dst.ctypes.data_as(C.c_void_p), 2, act.ctypes.data_as(C.c_char_p))
+        if call() != 0:
+            out[name] = None
+            continue
+        for _ in range(5):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            call()
+        out[name] = (time.perf_counter() - t0) / 50 * 1e6
+        L.ggb_mul_mat_forget(w.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def run_ours(args):
@@ -175,6 +297,28 @@ def run_ours(args):
         dist = dist_mod
     G.init(local_rank)
     L = G.cuda_lib()
+
+    def barrier():
+        G.sync()
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- multi-GPU: parity first (tiny MQA + MHA models, both quant types, fused lowering, against the oracle, bit for
+    # bit) - ORACLE USE: the checker, before and outside every timed region
+    tp_parity = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        import tp_worker
+        try:
+            n = tp_worker.check(G, O, dist, rank, world, lowerings=(True,))
+            tp_parity = f"ok ({n} cases: tiny mqa + mha models x q4_0/q8_0, tokens and logits bit-identical to the oracle)"
+        except AssertionError as e:
+            tp_parity = f"FAILED: {e}"
+        barrier()
+
     wtype = WTYPES[args.wtype]
     dims = dict(getattr(G, MODELS[args.model]), n_ctx=args.ctx)
     cfg = G.make_config(wtype=wtype, **dims)
@@ -189,32 +333,9 @@ def run_ours(args):
     kernels_per_step = m.kernels_per_step
     pos = args.ctx - 1
 
-    def barrier():
-        G.sync()
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
     # ---- value: K graph-replayed steps, inputs resident, CUDA events on the launching stream
-    m.set_state(4242, pos, 0)
-    m.run_steps(args.warmup)
-    barrier()
-    L.ggb_prof_enable(1)
-    G.prof_reset()
     with ClockSampler(local_rank) as clocks:
-        barrier()
-        L.ggb_prof_start(b"bench_timed_region")
-        m.run_steps(args.steps)
-        L.ggb_prof_stop(b"bench_timed_region")
-        barrier()
-    ms, _ = G.prof_get("bench_timed_region")
-    L.ggb_prof_enable(0)
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms = time_decode(G, L, m, args.steps, args.warmup, pos, barrier, dist)
     tok_s = args.steps / (ms / 1000.0)
 
     # ---- e2e: the host-buffer call a user makes (pinned H2D of token+pos, graph, D2H of the token)
@@ -235,17 +356,19 @@ def run_ours(args):
         e2e_s = float(t.item())
     e2e_tok_s = e2e_steps / e2e_s
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel: PER GPU (what this GPU streams per launch / its launch time / its peak)
     peak, peak_src = load_peaks()
     kv_bytes = dims["n_layer"] * 2 * dims["n_head_kv"] * dims["head_dim"] * 2 * args.ctx
-    step_bytes = (m.weight_bytes + kv_bytes / world)
     step_s = ms / args.steps / 1000.0
     per_class = {}
+    wname = "Q4_0" if wtype == 2 else "Q8_0"
     if fused:
-        # one persistent kernel per token: algorithmic bytes per launch = weights + KV read,
+        # one persistent kernel per token: algorithmic bytes per launch = weights + KV this GPU reads,
         # duration = the CUDA-event time of the timed region / launches
+        step_bytes = (m.weight_bytes + kv_bytes) if world == 1 else rank_bytes(m, dims, args.ctx, world)
         achieved = step_bytes / step_s / 1e9
-        roof_kernel = "decoder_kernel<Q4_0> (persistent, one cooperative launch per token)"
+        quad = "true" if args.model == "7b" else "false"
+        roof_kernel = f"decoder_kernel<{wname}, QUAD={quad}, PROF=false> (persistent, one cooperative launch per token)"
         roof_bytes, roof_launches, roof_us = step_bytes, 1.0, step_s * 1e6
     else:
         # per-operator lowering: cudaEvent probes around every launch of an eager pass, mat-vec class
@@ -257,32 +380,48 @@ def run_ours(args):
         for name in ("op_mul_mat", "op_attn", "op_rms_norm", "op_rope", "op_get_rows", "op_argmax"):
             tms, calls = G.prof_get(name)
             per_class[name] = {"ms_per_step": tms / prof_steps, "launches_per_step": calls / prof_steps}
+        step_bytes = (m.weight_bytes + kv_bytes) / world
         roof_bytes = matvec_bytes_per_step(dims, wtype) / world
         mv_ms = per_class["op_mul_mat"]["ms_per_step"]
         roof_launches = per_class["op_mul_mat"]["launches_per_step"]
         achieved = roof_bytes / (mv_ms / 1000.0) / 1e9 if mv_ms > 0 else 0.0
-        roof_kernel = "matvec_kernel / gate_up_kernel (all weight mat-vecs of a step, eager + cudaEvent probes)"
+        roof_kernel = f"matvec_kernel<{wname}> / gate_up_kernel<{wname}> (all weight mat-vecs of a step, eager + cudaEvent probes)"
         roof_us = 1000.0 * mv_ms / roof_launches if roof_launches else None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("fused" if fused else "ops")
-        except Exception:
-            traffic = None
+    if world == 1:  # one ncu --set full capture of this kernel on this workload (profiles/traffic.json); not valid for shards
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and args.model == "2b" and args.wtype == "q4_0" and args.ctx == 2048:
+            try:
+                traffic = json.load(open(tpath)).get("fused" if fused else "ops")
+            except Exception:
+                traffic = None
+    exp_mode = int(L.ggb_decoder_exp_computed(m.H.gm_decoder(m.h))) if fused else None
+    m.close()
 
+    # ---- sub-records measured in the same run
+    extra = {}
+    if fused and args.model == "2b" and not args.no_sub_records:
+        try:
+            extra["config4_7b_q4_0"] = sub_record_7b(G, L, args, dist, rank, world, barrier, peak)
+        except Exception as e:
+            extra["config4_7b_q4_0"] = {"failed": str(e)}
+        if world == 1:
+            try:
+                extra["config3_prefill_2b_q8_0"] = sub_record_prefill(G, L, args)
+            except Exception as e:
+                extra["config3_prefill_2b_q8_0"] = {"failed": str(e)}
+            try:
+                extra["mul_mat_dropin_us_per_call"] = mul_mat_dropin_us(G)
+            except Exception as e:
+                extra["mul_mat_dropin_us_per_call"] = {"failed": str(e)}
     if rank != 0:
-        m.close()
         return
     line = {
         "metric": "decode tokens/s", "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int8 dot (dp4a), fp32 accumulate",
         "data": "synthetic (seeded random-init Gemma-architecture weights in ggml quant format, synthetic KV)",
-        "config": {"workload": workload_name(args), "parallelism": f"tp{world}" if world > 1 else "single",
-                   "l2": "weights (1.41 GB for 2B Q4_0) > 126 MB L2: re-streamed from HBM every step, no flush needed",
-                   "lowering": "fused persistent decode kernel" if fused else "per-operator kernels",
-                   "graph": "one CUDA graph per token", "kernels_per_step": kernels_per_step},
+        "config": bench_config(args, world, "fused persistent decode kernel" if fused else "per-operator kernels", kernels_per_step),
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4,
                 "steps": e2e_steps},
@@ -291,18 +430,24 @@ def run_ours(args):
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "kernel": roof_kernel, "algorithmic_bytes_per_launch": roof_bytes / roof_launches,
                      "launches_per_step": roof_launches, "avg_launch_us": roof_us,
-                     "step_achieved_gbs": step_bytes / step_s / 1e9,
-                     "step_frac_of_peak": step_bytes / step_s / 1e9 / peak,
+                     "scope": "per GPU: bytes this GPU streams per launch / its launch time / its measured peak",
                      "step_frac_of_8tbs": step_bytes / step_s / 1e9 / 8000.0},
+        "parity": "tokens and logits bit-identical to the oracle's scalar ggml order (tests/test_model_gpu.py; config 1 "
+                  "at full size from tests/golden/)",
+        "softmax_exp": {2: "computed (fp32 expf, proved equal to the fp16 table)", 1: "computed (double exp, proved equal)",
+                        0: "fp16 table lookup", None: None}[exp_mode],
         "op_classes": per_class,
     }
-    m.close()
+    if tp_parity is not None:
+        line["tp_parity"] = tp_parity
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         try:
             tps, threads, dt, done = cpu_reference_tokens_per_s(args, args.cpu_tokens, budget_s=30.0)
             line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
                                     "sample": f"{done} full decode tokens of the same workload in {dt:.1f} s "
-                                              f"(oracle restatement of the reference thread_pool path, scalar vec_dot)"}
+                                              f"(oracle restatement of the reference thread_pool path, scalar vec_dot; "
+                                              f"upstream ggml's hand-written SIMD kernels are not reproduced)"}
         except Exception as e:  # the baseline must not take the GPU number down with it
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e}"}
@@ -377,6 +522,7 @@ def main():
     ap.add_argument("--prefill-tokens", type=int, default=512)
     ap.add_argument("--cpu-tokens", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub-records", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

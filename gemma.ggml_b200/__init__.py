@@ -112,6 +112,7 @@ _CUDA_SIG = {
     "ggb_decoder_create": (i32, [vp, vp, vp, vp, vp, P(vp)]),
     "ggb_decoder_create_tp": (i32, [vp, vp, vp, vp, vp, i32, i32, P(vp)]), "ggb_decoder_step": (i32, [vp]),
     "ggb_decoder_kv_heads_local": (i32, [i32, i32, i32]),
+    "ggb_decoder_stream_bytes": (C.c_longlong, [vp]), "ggb_decoder_kv_heads": (i32, [vp]),
     "ggb_decoder_free": (i32, [vp]), "ggb_decoder_trace": (i32, [vp, vp, vp, i32, P(i32), P(i32)]),
     "ggb_decoder_exp_computed": (i32, [vp]),
     "ggb_comm_unique_id": (i32, [vp]), "ggb_comm_init": (i32, [vp, i32, i32]), "ggb_comm_destroy": (i32, []),
@@ -353,6 +354,27 @@ def mul_mat_host(wtype, w_blocks, act_blocks, k):
     return dst
 
 
+_comm_world = 0
+
+
+def init_comm(dist, rank, world):
+    """bring up the library's NCCL communicator (idempotent)"""
+    global _comm_world
+    if _comm_world == world:
+        return
+    import torch
+    L = cuda_lib()
+    ident = np.zeros(128, dtype=np.uint8)
+    if rank == 0:
+        check(L.ggb_comm_unique_id(_ptr(ident)), "ggb_comm_unique_id")
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(ident).to(dev)
+    dist.broadcast(t, src=0)
+    ident = t.cpu().numpy().copy()
+    check(L.ggb_comm_init(_ptr(ident), rank, world), "ggb_comm_init")
+    _comm_world = world
+
+
 class GemmaModel:
     """ctypes face of host/gemma_model.{h,cpp}."""
 
@@ -374,18 +396,9 @@ class GemmaModel:
             pass
 
     def init_tensor_parallel(self, dist, rank, world):
-        """Row-sharded tensor parallelism over `world` ranks (one process per GPU).  `dist` is an initialised
-        torch.distributed module/backend used only to ship the 128-byte NCCL unique id from rank 0."""
-        import torch
-        L = cuda_lib()
-        ident = np.zeros(128, dtype=np.uint8)
-        if rank == 0:
-            check(L.ggb_comm_unique_id(_ptr(ident)), "ggb_comm_unique_id")
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        t = torch.from_numpy(ident).to(dev)
-        dist.broadcast(t, src=0)
-        ident = t.cpu().numpy().copy()
-        check(L.ggb_comm_init(_ptr(ident), rank, world), "ggb_comm_init")
+        """Tensor parallelism over `world` ranks (one process per GPU).  `dist` is an initialised torch.distributed
+        module/backend used only to ship the 128-byte NCCL unique id from rank 0 (once per process)."""
+        init_comm(dist, rank, world)
         check(self.H.gm_init_tensor_parallel(self.h, rank, world), "gm_init_tensor_parallel")
 
     def init_synthetic_weights(self):
@@ -421,6 +434,17 @@ class GemmaModel:
         n1 = n.value * g.value * 4
         self.prof = stamps[n1:n1 + g.value * 64].reshape(g.value, 64).copy()  # GGB_PROF_PHASE sums (SM clocks)
         return stamps[:n1].reshape(n.value, g.value, 4), kinds[:n.value].copy()
+
+    @property
+    def rank_stream_bytes(self):
+        """bytes of weight pass stream this rank reads per token (fused lowering)"""
+        dec = self.H.gm_decoder(self.h)
+        return int(cuda_lib().ggb_decoder_stream_bytes(dec)) if dec else 0
+
+    @property
+    def rank_kv_heads(self):
+        dec = self.H.gm_decoder(self.h)
+        return int(cuda_lib().ggb_decoder_kv_heads(dec)) if dec else 0
 
     @property
     def exp_computed(self):

@@ -2076,6 +2076,11 @@ int ggb_decoder_trace(ggb_decoder *D, long long *stamps, int32_t *kinds, int max
 
 int ggb_decoder_exp_computed(const ggb_decoder *D) { return D ? D->P.exp_compute : 0; }
 
+// bytes of pass stream THIS rank reads per token (its shards + the phases it runs replicated)
+long long ggb_decoder_stream_bytes(const ggb_decoder *D) { return D ? (long long)D->stream_bytes : 0; }
+// KV heads whose cache rows this rank reads per token
+int ggb_decoder_kv_heads(const ggb_decoder *D) { return D ? D->P.ng : 0; }
+
 int ggb_decoder_free(ggb_decoder *D) {
     if (!D) return GGB_OK;
     cudaStreamSynchronize(ggb_cuda_stream());

@@ -256,8 +256,13 @@ int ggb_decoder_free(ggb_decoder *d);
  * 4 GATE_UP, 5 DOWN, 6 LOGITS, 7 SAMPLE) */
 int ggb_decoder_trace(ggb_decoder *d, long long *stamps, int32_t *kinds, int max_phases, int *n_phases, int *grid);
 /* 1 if the kernel computes the soft-max exp (double exp -> fp32 -> fp16) instead of reading the reference's fp16 table:
- * enabled only when an exhaustive check at create time found the two identical for every non-NaN fp16 input */
+ * (2: fp32 expf, 1: double exp; 0: table lookup); enabled only when an exhaustive check at create time found the computed
+ * form identical to the table for every non-NaN fp16 input */
 int ggb_decoder_exp_computed(const ggb_decoder *d);
+/* what THIS rank streams per token: bytes of its pass streams (its row shards plus the phases it runs replicated) and
+ * the KV heads whose cache it reads - the per-GPU roofline of a tensor-parallel run is computed from these */
+long long ggb_decoder_stream_bytes(const ggb_decoder *d);
+int ggb_decoder_kv_heads(const ggb_decoder *d);
 
 /* ------------------------------------------------------------------ multi-GPU (row-sharded TP)
  * one process per GPU; the 128-byte NCCL unique id is created on rank 0 and shipped by the
