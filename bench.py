@@ -290,6 +290,9 @@ def run_ours(args):
 
     dist = None
     if world > 1:
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION: the line rank 0 prints must stay the only one
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)

@@ -128,6 +128,12 @@ _HOST_SIG = {
     "gm_set_state": (i32, [vp, i32, i32, i32]), "gm_run_steps": (i32, [vp, i32]), "gm_run_steps_profiled": (i32, [vp, i32]),
     "gm_get_state": (i32, [vp, P(i32), P(i32)]),
     "gm_generate": (i32, [vp, vp, i32, i32, vp, P(i32), P(C.c_double), P(C.c_double)]),
+    "gm_last_error": (C.c_char_p, []),
+    "gm_gguf_probe": (i32, [C.c_char_p, vp, P(i32), P(i32), P(i32), P(i32), P(i32)]),
+    "gm_gguf_detokenize": (i32, [C.c_char_p, vp, i32, C.c_char_p, i32]),
+    "gm_load_model_from_file": (vp, [C.c_char_p, i32]),
+    "gm_get_config": (i32, [vp, vp]),
+    "gm_begin_one_round_inference": (i32, [vp, vp, i32, i32, vp, P(i32), C.c_char_p, i32, P(C.c_double), P(C.c_double)]),
     "gm_prefill": (i32, [vp, vp, i32, i32, P(i32)]), "gm_get_prefill_logits": (i32, [vp, i32, vp]),
     "gm_last_prefill_gemm_flops": (C.c_double, [vp]),
     "gm_get_logits": (i32, [vp, vp]), "gm_get_capture": (i32, [vp, C.c_char_p, i32, vp, i64]),
@@ -354,6 +360,28 @@ def mul_mat_host(wtype, w_blocks, act_blocks, k):
     return dst
 
 
+def gguf_probe(path):
+    """host-only parse of a Gemma GGUF: (Config, n_tensors, n_kv, n_tokens, bos, eos)"""
+    H = host_lib()
+    cfg = Config()
+    v = [i32() for _ in range(5)]
+    rc = H.gm_gguf_probe(os.fsencode(path), C.byref(cfg), *[C.byref(x) for x in v])
+    if rc:
+        raise GgbError("gguf_probe(%s): %s" % (path, H.gm_last_error().decode(errors="replace")))
+    return (cfg,) + tuple(x.value for x in v)
+
+
+def gguf_detokenize(path, ids):
+    """host-only: the text of `ids` with the file's vocabulary (ref: print_tokens, src/gemma_model.cpp:762-772)"""
+    H = host_lib()
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    buf = C.create_string_buffer(64 * ids.size + 64)
+    n = H.gm_gguf_detokenize(os.fsencode(path), _ptr(ids), ids.size, buf, len(buf))
+    if n < 0:
+        raise GgbError("gguf_detokenize: %s" % H.gm_last_error().decode(errors="replace"))
+    return buf.value.decode("utf-8", errors="replace")
+
+
 _comm_world = 0
 
 
@@ -378,11 +406,34 @@ def init_comm(dist, rank, world):
 class GemmaModel:
     """ctypes face of host/gemma_model.{h,cpp}."""
 
-    def __init__(self, cfg):
+    def __init__(self, cfg, _handle=None):
         init()
         self.cfg = cfg
         self.H = host_lib()
-        self.h = self.H.gm_create(C.byref(cfg))
+        self.h = _handle if _handle is not None else self.H.gm_create(C.byref(cfg))
+
+    @classmethod
+    def load_model_from_file(cls, path, n_ctx=0):
+        """ref: gemma_model::load_model_from_file (src/gemma_model.cpp:19-51): a Q4_0 / Q8_0 Gemma GGUF -> device."""
+        init()
+        H = host_lib()
+        h = H.gm_load_model_from_file(os.fsencode(path), int(n_ctx))
+        if not h:
+            raise GgbError("load_model_from_file(%s): %s" % (path, H.gm_last_error().decode(errors="replace")))
+        cfg = Config()
+        H.gm_get_config(h, C.byref(cfg))
+        return cls(cfg, _handle=h)
+
+    def begin_one_round_inference(self, prompt, max_tokens):
+        """ref: begin_one_round_inference (src/gemma_model.cpp:548-575): prefill, decode until EOS / max_tokens.
+        Returns (new token ids, the text the reference would print, prefill ms, decode ms)."""
+        prompt = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.empty(max_tokens + 2, dtype=np.int32)
+        text = C.create_string_buffer(64 * (prompt.size + max_tokens + 2) + 64)
+        n_out, pm, dm = i32(), C.c_double(), C.c_double()
+        check(self.H.gm_begin_one_round_inference(self.h, _ptr(prompt), prompt.size, int(max_tokens), _ptr(out), C.byref(n_out),
+                                                  text, len(text), C.byref(pm), C.byref(dm)), "gm_begin_one_round_inference")
+        return out[:n_out.value].copy(), text.value.decode("utf-8", errors="replace"), pm.value, dm.value
 
     def close(self):
         if self.h:

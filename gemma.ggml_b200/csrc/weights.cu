@@ -120,14 +120,23 @@ int ggb_weight_upload(int type, int64_t rows, int64_t cols, const void *host_blo
     cudaStream_t st = ggb_cuda_stream();
     void *staging = nullptr;
     const size_t raw = (size_t)(rows - 1) * nb01 + min_stride;
-    GGB_CUDA(cudaMalloc(&staging, raw));
-    GGB_CUDA(cudaMemcpyAsync(staging, host_blocks, raw, cudaMemcpyHostToDevice, st));
-    const int64_t total = rows * w->nb;
-    repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint8_t *)staging, nb01, type, rows, w->nb,
-                                                                  w->qs, w->d);
-    GGB_LAUNCH_CHECK();
-    GGB_CUDA(cudaStreamSynchronize(st));
-    GGB_CUDA(cudaFree(staging));
+    // (every failure below releases the weight and the staging buffer)
+    cudaError_t e = cudaMalloc(&staging, raw);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(staging, host_blocks, raw, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const int64_t total = rows * w->nb;
+        repack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint8_t *)staging, nb01, type, rows, w->nb,
+                                                                      w->qs, w->d);
+        e = cudaGetLastError();
+        ggb_count_launch();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(staging);
+    if (e != cudaSuccess) {
+        ggb_weight_free(w);
+        ggb_set_error("ggb_weight_upload -> %s", cudaGetErrorString(e));
+        return GGB_ERR_CUDA;
+    }
     *out = w;
     return GGB_OK;
 }

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "gemma_model.h"
+#include "gguf_loader.h"
 #include "tensor_dump.h"
 
 extern "C" {
@@ -49,6 +50,59 @@ int gm_generate(void *m, const int32_t *prompt, int n_prompt, int n_decode, int3
     if (rc) return rc;
     if (n_out) *n_out = (int)o.size();
     memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    return 0;
+}
+// ---- GGUF loader + tokenizer.  gm_gguf_probe parses a file on the host only (no GPU needed).
+static thread_local std::string g_capi_err;
+const char *gm_last_error() { return g_capi_err.c_str(); }
+int gm_gguf_probe(const char *path, gemma_config *cfg, int32_t *n_tensors, int32_t *n_kv, int32_t *n_tokens, int32_t *bos, int32_t *eos) {
+    gguf_file f;
+    if (f.open(path) != 0) { g_capi_err = f.error(); return -1; }
+    if (gguf_gemma_config(f, 0, cfg, &g_capi_err) != 0) return -2;
+    gemma_tokenizer tok;
+    const bool has_tok = gguf_gemma_tokenizer(f, &tok) == 0;
+    if (n_tensors) *n_tensors = (int32_t)f.tensors().size();
+    if (n_kv) *n_kv = (int32_t)f.n_kv();
+    if (n_tokens) *n_tokens = has_tok ? (int32_t)tok.tokens.size() : 0;
+    if (bos) *bos = tok.special_bos_id;
+    if (eos) *eos = tok.special_eos_id;
+    return 0;
+}
+// detokenise with the vocabulary of a GGUF file (host only): "▁" -> " ", leading "<bos>" dropped; returns the length
+int gm_gguf_detokenize(const char *path, const int32_t *ids, int n, char *buf, int cap) {
+    gguf_file f;
+    if (f.open(path) != 0) { g_capi_err = f.error(); return -1; }
+    gemma_tokenizer tok;
+    if (gguf_gemma_tokenizer(f, &tok) != 0) { g_capi_err = "no tokenizer.ggml.tokens in the file"; return -2; }
+    const std::string t = tok.tokens_text(std::vector<token_id>(ids, ids + n));
+    if (buf && cap > 0) {
+        const size_t k = t.size() < (size_t)cap - 1 ? t.size() : (size_t)cap - 1;
+        memcpy(buf, t.data(), k);
+        buf[k] = 0;
+    }
+    return (int)t.size();
+}
+void *gm_load_model_from_file(const char *path, int32_t n_ctx) {
+    gemma_model *m = gemma_model::load_model_from_file(path, n_ctx, &g_capi_err);
+    return m;
+}
+int gm_get_config(void *m, gemma_config *cfg) {
+    *cfg = ((gemma_model *)m)->config();
+    return 0;
+}
+int gm_begin_one_round_inference(void *m, const int32_t *prompt, int n_prompt, int max_tokens, int32_t *out, int *n_out,
+                                 char *text, int text_cap, double *prefill_ms, double *decode_ms) {
+    std::vector<token_id> p(prompt, prompt + n_prompt), o;
+    std::string t;
+    const int rc = ((gemma_model *)m)->begin_one_round_inference(p, max_tokens, o, text ? &t : nullptr, prefill_ms, decode_ms);
+    if (rc) return rc;
+    if (n_out) *n_out = (int)o.size();
+    memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    if (text && text_cap > 0) {
+        const size_t k = t.size() < (size_t)text_cap - 1 ? t.size() : (size_t)text_cap - 1;
+        memcpy(text, t.data(), k);
+        text[k] = 0;
+    }
     return 0;
 }
 int gm_prefill(void *m, const int32_t *tokens, int T, int32_t pos0, int32_t *next) {

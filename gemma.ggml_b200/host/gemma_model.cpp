@@ -2,6 +2,7 @@
 // (tensor binding :159-194, KV cache :361-401 / :428-436, graph builder :438-530 / :665-747,
 // inference :231-286, greedy round :548-575) with every node lowered to the C-ABI CUDA layer.
 #include "gemma_model.h"
+#include "gguf_loader.h"
 #include <cstdlib>
 
 #include <chrono>
@@ -86,7 +87,54 @@ int gemma_model::make_shards() {
     return sl(token_embd_, plan_.logits, &sh_logits_);
 }
 
-gemma_model::~gemma_model() { free_all(); }
+gemma_model::~gemma_model() {
+    free_all();
+    delete tokenizer_;
+}
+
+gemma_model *gemma_model::load_model_from_file(const char *file_path, int32_t n_ctx, std::string *err) {
+    gguf_file f;
+    if (f.open(file_path) != 0) {
+        if (err) *err = f.error();
+        return nullptr;
+    }
+    gemma_config cfg;
+    if (gguf_gemma_config(f, n_ctx, &cfg, err) != 0) return nullptr;
+    gemma_model *m = new gemma_model(cfg);
+    if (gguf_bind_tensors(f, *m, err) != 0) {
+        delete m;
+        return nullptr;
+    }
+    m->tokenizer_ = new gemma_tokenizer();
+    if (gguf_gemma_tokenizer(f, m->tokenizer_) != 0) { // a file without a vocabulary still runs: ids only
+        delete m->tokenizer_;
+        m->tokenizer_ = nullptr;
+    }
+    return m;
+}
+
+int gemma_model::begin_one_round_inference(const std::vector<token_id> &prompt, int max_tokens, std::vector<token_id> &out,
+                                           std::string *text, double *prefill_ms, double *decode_ms) {
+    using clk = std::chrono::high_resolution_clock;
+    if (prompt.empty() || (int)prompt.size() >= cfg_.n_ctx) return GGB_ERR_ARG;
+    const token_id eos = tokenizer_ ? tokenizer_->special_eos_id : -1;
+    std::vector<token_id> input = prompt;
+    if (text && tokenizer_) *text = tokenizer_->tokens_text(input); // ref: print_tokens(input)
+    GM_TRY(init_kv_cache());
+    const auto t0 = clk::now();
+    GM_TRY(inference(input, inference_stage::PREFILL));
+    const auto t1 = clk::now();
+    // ref :559-563: while (last != eos && size < DEFAULT_TOKEN_NUM) { print_token(last); inference(DECODE); }
+    while (input.back() != eos && (int)(input.size() - prompt.size()) < max_tokens && (int)input.size() < cfg_.n_ctx) {
+        if (text && tokenizer_) *text += tokenizer_->token_text(input.back());
+        GM_TRY(inference(input, inference_stage::DECODE));
+    }
+    const auto t2 = clk::now();
+    out.assign(input.begin() + (long)prompt.size(), input.end());
+    if (prefill_ms) *prefill_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    if (decode_ms) *decode_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    return 0;
+}
 
 void gemma_model::free_all() {
     ggb_sync();
@@ -162,6 +210,16 @@ int gemma_model::init_synthetic_weights() {
 // upload one tensor from host memory (ggml AoS blocks for matrices, f32 for norms)
 int gemma_model::set_tensor(int tensor_id, const void *host_data, int64_t nbytes) {
     const gemma_config &c = cfg_;
+    // the captured graph, the persistent kernel's pass streams and the tensor-parallel shard views all hold pointers
+    // into the weights: replacing one invalidates them (build_compute_graph must be called again)
+    if (built_ || graph_ || decoder_) {
+        ggb_sync();
+        ggb_graph_free(graph_);
+        graph_ = nullptr;
+        ggb_decoder_free(decoder_);
+        decoder_ = nullptr;
+        built_ = false;
+    }
     const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
     const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
     auto mat = [&](ggb_weight **slot, int64_t rows, int64_t cols) -> int {
@@ -404,7 +462,8 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
             return rc;
         }
     }
-    if (ggb_capture_begin() == 0) {
+    const int rcb = ggb_capture_begin();
+    if (rcb == 0) {
         const int rc = decoder_ ? ggb_decoder_step(decoder_)
                                 : (plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step());
         ggb_graph *g = nullptr;
@@ -415,6 +474,8 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
             ggb_graph_free(g);
             if (!decoder_) return rc ? rc : rc2; // the op sequence must be capturable
         }
+    } else if (!decoder_) {
+        return rcb; // no graph and no persistent kernel: there would be nothing to launch
     }
     built_ = true;
     return 0;
@@ -543,7 +604,7 @@ int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *
     if (!tokens || T <= 0 || pos0 < 0 || pos0 + T > c.n_ctx || !built_ || plan_.size > 1) return GGB_ERR_ARG;
     GM_TRY(alloc_prefill(T));
     const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab, t = T;
-    const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim;
     const float q_scale = 1.0f / sqrtf((float)c.head_dim);
     std::vector<int32_t> pos((size_t)T);
     for (int i = 0; i < T; i++) pos[(size_t)i] = pos0 + i;

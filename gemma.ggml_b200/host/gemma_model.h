@@ -56,10 +56,23 @@ struct tp_plan {
 };
 tp_plan make_tp_plan(const gemma_config &cfg, int rank, int size);
 
+// ref: gemma_tokenizer (src/gemma_model.h; print_token / print_tokens src/gemma_model.cpp:749-793), filled from the
+// GGUF vocabulary by host/gguf_loader.cpp
+struct gemma_tokenizer;
+
 class gemma_model {
   public:
     explicit gemma_model(const gemma_config &cfg);
     ~gemma_model();
+    // ref: load_model_from_file (src/gemma_model.cpp:19-51): hyper-parameters from the GGUF header (:403-415), the
+    // 2 + 9 L tensors bound by the reference's names (:159-194) and uploaded, the tokenizer vocabulary.  n_ctx = 0
+    // takes gemma.context_length.  Returns nullptr and sets *err on failure.
+    static gemma_model *load_model_from_file(const char *file_path, int32_t n_ctx, std::string *err);
+    const gemma_tokenizer *tokenizer() const { return tokenizer_; }
+    // ref: begin_one_round_inference (:548-575): prefill, then decode until the EOS token or max_tokens / the context
+    // is reached.  `text` (optional) receives what the reference prints: the detokenised prompt and every new token.
+    int begin_one_round_inference(const std::vector<token_id> &prompt, int max_tokens, std::vector<token_id> &out,
+                                  std::string *text, double *prefill_ms, double *decode_ms);
 
     // call before the weights exist; NCCL (ggb_comm_init) must already be up for size > 1
     int init_tensor_parallel(int rank, int size);
@@ -114,6 +127,7 @@ class gemma_model {
     void free_all();
 
     gemma_config cfg_;
+    gemma_tokenizer *tokenizer_ = nullptr;
     ggb_weight *token_embd_ = nullptr; // also the output projection (tied, ref: :163)
     float *output_norm_ = nullptr;
     std::vector<gemma_layer> layers_;

@@ -1,0 +1,37 @@
+"""GGUF loader + tokenizer, host side only (no GPU): header KV / tensor table parse, hyper-parameters by the reference's
+keys (ref: src/gemma_model.cpp:403-415), vocabulary, print_tokens text (ref: :749-793)."""
+import os
+
+import numpy as np
+import pytest
+
+import gemma_ggml_b200 as G
+import oracle_lib as O
+from gguf_fixture import write_gemma_gguf
+
+DIMS = dict(n_embd=256, n_layer=2, n_head=4, n_head_kv=1, head_dim=64, n_ff=512, n_vocab=512, n_ctx=64)
+
+
+@pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
+def test_probe_reads_header_tensors_and_tokenizer(tmp_path, wtype):
+    om = O.Model(wtype=wtype, sigma_embd=0.002, **DIMS)
+    path = os.path.join(tmp_path, "tiny.gguf")
+    toks = write_gemma_gguf(path, om, DIMS, wtype)
+    cfg, n_tensors, n_kv, n_tokens, bos, eos = G.gguf_probe(path)
+    for k, v in DIMS.items():
+        assert getattr(cfg, k) == v, k
+    assert cfg.wtype == wtype and abs(cfg.eps - 1e-6) < 1e-12
+    assert n_tensors == 2 + 9 * DIMS["n_layer"] and n_tokens == len(toks) and (bos, eos) == (2, 1) and n_kv >= 10
+    # "<bos>" dropped, U+2581 -> space (ref: print_tokens)
+    assert G.gguf_detokenize(path, [2, 4, 5, 6]) == " hello world!"
+    om.close()
+
+
+def test_probe_rejects_garbage(tmp_path):
+    path = os.path.join(tmp_path, "bad.gguf")
+    open(path, "wb").write(b"GGUF" + b"\x03\x00\x00\x00" + b"\xff" * 64)
+    with pytest.raises(G.GgbError):
+        G.gguf_probe(path)
+    open(path, "wb").write(b"nope" * 16)
+    with pytest.raises(G.GgbError):
+        G.gguf_probe(path)
