@@ -439,3 +439,162 @@ void orc_synth_row(uint64_t seed, uint64_t tensor_id, int64_t row, int64_t k, fl
     for (int64_t i = 0; i < k; i++)
         out[i] = bias + orc_synth_value(seed, tensor_id, (uint64_t)(row * k + i), sigma);
 }
+
+/* ------------------------------------------------------- K-quants */
+
+static inline int orc_nearest_int(float fval) { /* [UPSTREAM] ggml-quants.c nearest_int: round half to even */
+    float val = fval + 12582912.f;
+    int i;
+    memcpy(&i, &val, sizeof(int));
+    return (i & 0x007fffff) - 0x00400000;
+}
+
+/* [UPSTREAM] quantize_row_q8_K_reference */
+void orc_quantize_row_q8_K(const float *x, orc_block_q8_K *y, int64_t k) {
+    const int64_t nb = k / ORC_QK_K;
+    for (int64_t i = 0; i < nb; i++) {
+        float max = 0, amax = 0;
+        for (int j = 0; j < ORC_QK_K; ++j) {
+            const float ax = fabsf(x[j]);
+            if (ax > amax) { amax = ax; max = x[j]; }
+        }
+        if (!amax) {
+            y[i].d = 0;
+            memset(y[i].qs, 0, ORC_QK_K);
+            memset(y[i].bsums, 0, sizeof(y[i].bsums)); /* (ggml leaves bsums untouched here; zero is what a zeroed wdata holds) */
+            x += ORC_QK_K;
+            continue;
+        }
+        const float iscale = -128.f / max;
+        for (int j = 0; j < ORC_QK_K; ++j) {
+            int v = orc_nearest_int(iscale * x[j]);
+            y[i].qs[j] = (int8_t)(v < 127 ? v : 127);
+        }
+        for (int j = 0; j < ORC_QK_K / 16; ++j) {
+            int sum = 0;
+            for (int ii = 0; ii < 16; ++ii) sum += y[i].qs[j * 16 + ii];
+            y[i].bsums[j] = (int16_t)sum;
+        }
+        y[i].d = 1 / iscale;
+        x += ORC_QK_K;
+    }
+}
+
+/* the 6-bit scales / mins of a Q4_K block, unpacked as the reference does (src/kernals.cl:75-80) */
+static void q4k_scales(const uint8_t *packed, uint8_t *scales /*8*/, uint8_t *mins /*8*/) {
+    const uint32_t kmask1 = 0x3f3f3f3f, kmask2 = 0x0f0f0f0f, kmask3 = 0x03030303;
+    uint32_t utmp[4];
+    memcpy(utmp, packed, 12);
+    utmp[3] = ((utmp[2] >> 4) & kmask2) | (((utmp[1] >> 6) & kmask3) << 4);
+    const uint32_t uaux = utmp[1] & kmask1;
+    utmp[1] = (utmp[2] & kmask2) | (((utmp[0] >> 6) & kmask3) << 4);
+    utmp[2] = uaux;
+    utmp[0] &= kmask1;
+    memcpy(scales, &utmp[0], 8);
+    memcpy(mins, &utmp[2], 8);
+}
+
+/* ref: src/kernals.cl:48-111.  Integer part exact; fp32 part: eight lane sums (lane = element index mod 8) advanced
+ * block by block with d * aux32[l], the mins term subtracted from sumf block by block, lanes added at the end. */
+void orc_vec_dot_q4_K_q8_K(int n, float *s, const void *vx, const void *vy) {
+    const orc_block_q4_K *x = (const orc_block_q4_K *)vx;
+    const orc_block_q8_K *y = (const orc_block_q8_K *)vy;
+    const int nb = n / ORC_QK_K;
+    int8_t aux8[ORC_QK_K];
+    float sums[8] = {0};
+    float sumf = 0;
+    for (int i = 0; i < nb; ++i) {
+        const uint8_t *q4 = x[i].qs;
+        const int8_t *q8 = y[i].qs;
+        int32_t aux32[8] = {0};
+        int8_t *a = aux8;
+        for (int j = 0; j < ORC_QK_K / 64; ++j) {
+            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] & 0xF);
+            a += 32;
+            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] >> 4);
+            a += 32; q4 += 32;
+        }
+        uint8_t scales[8], mins[8];
+        q4k_scales(x[i].scales, scales, mins);
+        int sumi = 0;
+        for (int j = 0; j < ORC_QK_K / 16; ++j) sumi += y[i].bsums[j] * mins[j / 2];
+        a = aux8;
+        for (int j = 0; j < ORC_QK_K / 32; ++j) {
+            const int32_t scale = scales[j];
+            for (int g = 0; g < 4; ++g) {
+                for (int l = 0; l < 8; ++l) aux32[l] += scale * (int16_t)(q8[l] * a[l]);
+                q8 += 8; a += 8;
+            }
+        }
+        const float d = orc_fp16_to_fp32(x[i].d) * y[i].d;
+        for (int l = 0; l < 8; ++l) sums[l] += d * aux32[l];
+        const float dmin = orc_fp16_to_fp32(x[i].dmin) * y[i].d;
+        sumf -= dmin * sumi;
+    }
+    for (int l = 0; l < 8; ++l) sumf += sums[l];
+    *s = sumf;
+}
+
+/* a Q6_K block's 256 weights as int8 (q - 32), [UPSTREAM] ggml QK_K = 256 layout */
+static void q6k_unpack(const orc_block_q6_K *b, int8_t *a) {
+    const uint8_t *q4 = b->ql, *qh = b->qh;
+    for (int j = 0; j < ORC_QK_K; j += 128) {
+        for (int l = 0; l < 32; ++l) {
+            a[l + 0] = (int8_t)((q4[l + 0] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
+            a[l + 32] = (int8_t)((q4[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+            a[l + 64] = (int8_t)((q4[l + 0] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
+            a[l + 96] = (int8_t)((q4[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+        }
+        a += 128; q4 += 64; qh += 32;
+    }
+}
+
+void orc_vec_dot_q6_K_q8_K(int n, float *s, const void *vx, const void *vy) {
+    const orc_block_q6_K *x = (const orc_block_q6_K *)vx;
+    const orc_block_q8_K *y = (const orc_block_q8_K *)vy;
+    const int nb = n / ORC_QK_K;
+    int8_t aux8[ORC_QK_K];
+    float sums[8] = {0};
+    float sumf = 0;
+    for (int i = 0; i < nb; ++i) {
+        const int8_t *q8 = y[i].qs;
+        int32_t aux32[8] = {0};
+        q6k_unpack(&x[i], aux8);
+        const int8_t *a = aux8;
+        for (int j = 0; j < ORC_QK_K / 16; ++j) {
+            const int scale = x[i].scales[j];
+            for (int g = 0; g < 2; ++g) {
+                for (int l = 0; l < 8; ++l) aux32[l] += scale * (int16_t)(q8[l] * a[l]);
+                q8 += 8; a += 8;
+            }
+        }
+        const float d = orc_fp16_to_fp32(x[i].d) * y[i].d;
+        for (int l = 0; l < 8; ++l) sums[l] += d * aux32[l];
+    }
+    for (int l = 0; l < 8; ++l) sumf += sums[l];
+    *s = sumf;
+}
+
+void orc_dequantize_row_q4_K(const orc_block_q4_K *x, float *y, int64_t k) {
+    for (int64_t i = 0; i < k / ORC_QK_K; i++) {
+        const float d = orc_fp16_to_fp32(x[i].d), dmin = orc_fp16_to_fp32(x[i].dmin);
+        uint8_t sc[8], mn[8];
+        q4k_scales(x[i].scales, sc, mn);
+        const uint8_t *q = x[i].qs;
+        for (int j = 0; j < 4; j++) {
+            const float d1 = d * sc[2 * j], m1 = dmin * mn[2 * j], d2 = d * sc[2 * j + 1], m2 = dmin * mn[2 * j + 1];
+            for (int l = 0; l < 32; ++l) *y++ = d1 * (q[l] & 0xF) - m1;
+            for (int l = 0; l < 32; ++l) *y++ = d2 * (q[l] >> 4) - m2;
+            q += 32;
+        }
+    }
+}
+
+void orc_dequantize_row_q6_K(const orc_block_q6_K *x, float *y, int64_t k) {
+    int8_t a[ORC_QK_K];
+    for (int64_t i = 0; i < k / ORC_QK_K; i++) {
+        const float d = orc_fp16_to_fp32(x[i].d);
+        q6k_unpack(&x[i], a);
+        for (int j = 0; j < ORC_QK_K; j++) y[i * ORC_QK_K + j] = d * x[i].scales[j / 16] * a[j];
+    }
+}

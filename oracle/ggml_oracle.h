@@ -105,6 +105,29 @@ uint64_t orc_splitmix64(uint64_t x);
 float orc_synth_value(uint64_t seed, uint64_t tensor_id, uint64_t index, float sigma);
 void orc_synth_row(uint64_t seed, uint64_t tensor_id, int64_t row, int64_t k, float sigma, float bias, float *out);
 
+
+/* ---- K-quants: the formats the reference's own device kernels target ----
+ * block layouts: src/kernals.cl:13-34 (= ggml block_q4_K 144 B, block_q6_K 210 B, block_q8_K 292 B; QK_K = 256) */
+#define ORC_QK_K 256
+#define ORC_TYPE_Q4_K 12
+#define ORC_TYPE_Q6_K 14
+#define ORC_TYPE_Q8_K 15
+#pragma pack(push, 1)
+typedef struct { uint16_t d, dmin; uint8_t scales[12]; uint8_t qs[128]; } orc_block_q4_K;
+typedef struct { uint8_t ql[128]; uint8_t qh[64]; int8_t scales[16]; uint16_t d; } orc_block_q6_K;
+typedef struct { float d; int8_t qs[256]; int16_t bsums[16]; } orc_block_q8_K;
+#pragma pack(pop)
+/* [UPSTREAM] quantize_row_q8_K_reference: the activation quantiser of the K-quant mat-muls (ggml mul_mat INIT) */
+void orc_quantize_row_q8_K(const float *x, orc_block_q8_K *y, int64_t k);
+/* ref: src/kernals.cl:48-111 (restated; pinned against oracle/_ref) */
+void orc_vec_dot_q4_K_q8_K(int n, float *s, const void *vx, const void *vy);
+/* [UPSTREAM] ggml_vec_dot_q6_K_q8_K, scalar branch, QK_K = 256.  (The reference's copy, src/kernals.cl:114-156, is ggml's
+ * QK_K == 64 branch under QK_K = 256: it unpacks 64 of the 256 weights and reads the rest uninitialised - not followed.) */
+void orc_vec_dot_q6_K_q8_K(int n, float *s, const void *vx, const void *vy);
+/* [UPSTREAM] dequantize_row_q4_K / q6_K (checked against gguf-py) */
+void orc_dequantize_row_q4_K(const orc_block_q4_K *x, float *y, int64_t k);
+void orc_dequantize_row_q6_K(const orc_block_q6_K *x, float *y, int64_t k);
+
 #ifdef __cplusplus
 }
 #endif
