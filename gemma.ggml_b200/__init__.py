@@ -84,6 +84,8 @@ _CUDA_SIG = {
     "ggb_q8_row_bytes": (sz, [i64]),
     "ggb_op_quantize_q8_0": (i32, [vp, i64, i64, vp]), "ggb_op_q8_to_blocks": (i32, [vp, i64, i64, vp]),
     "ggb_op_q8_from_blocks": (i32, [vp, i64, i64, i64, vp]),
+    "ggb_type_row_bytes": (sz, [i32, i64]), "ggb_op_quantize_q8_K": (i32, [vp, i64, i64, vp]),
+    "ggb_op_mul_mat_blocks": (i32, [i32, vp, i64, i64, i64, vp, i64, i64, vp, i64]),
     "ggb_op_mul_mat_q8": (i32, [vp, vp, i64, vp, i64, vp]),
     "ggb_op_mul_mat_q8_multi": (i32, [i32, P(vp), vp, P(vp)]),
     "ggb_op_ffn_gate_up": (i32, [vp, vp, vp, vp, vp]),
@@ -345,6 +347,20 @@ def quantize_row_q8_0(x):
     check(L.ggb_op_q8_to_blocks(q8.ptr, cols, T, blocks.ptr), "q8_to_blocks")
     sync()
     return q8, blocks.download(np.uint8).reshape(T, cols // 32 * 34)
+
+
+def quantize_q8_K(x):
+    """[UPSTREAM] quantize_row_q8_K on the device: float32 [T, cols] -> uint8 [T, cols/256*292] block_q8_K rows."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    T, cols = x.shape
+    L = cuda_lib()
+    xd = DeviceBuffer.from_numpy(x)
+    out = DeviceBuffer(cols // 256 * 292 * T)
+    check(L.ggb_op_quantize_q8_K(xd.ptr, cols, T, out.ptr), "quantize_q8_K")
+    sync()
+    return out.download(np.uint8).reshape(T, cols // 256 * 292)
 
 
 def mul_mat_host(wtype, w_blocks, act_blocks, k):

@@ -1,0 +1,288 @@
+// kquants.cu — SURVEY.md 8f-2: the formats the reference's own offload kernels target.
+//   Q4_K x Q8_K   ref: src/kernals.cl:48-111  (matrix_multiply_q4_K :166-214)
+//   Q6_K x Q8_K   ref: src/kernals.cl:114-156 ([UPSTREAM] ggml's QK_K = 256 layout; the reference's copy indexes
+//                 the block as QK_K = 64 and reads an uninitialised aux8 tail - its host never launches it,
+//                 src/hpc.cpp:254-257 - so the pinned behaviour is ggml's scalar vec_dot)
+//   F16 x F16     ref: src/kernals.cl:158-164 (double accumulator)
+//   quantize_row_q8_K  [UPSTREAM] ggml INIT stage of mul_mat for K-quant weights (block at src/kernals.cl:29-34)
+//
+// The reference runs one work-item per output with a private aux8[256] and a serial loop.  Here a warp owns an
+// output row and a super-block is spread over the warp: lane L holds the 8 consecutive aux8 elements 8L..8L+7, so
+// element l of the lane IS the reference's lane-sum index (aux32[l], sums[l], l = e mod 8).  The integer part
+// (aux32[l] = sum over the super-block of scale * q8 * a, sumi = sum bsums * mins) is exact in any order and is
+// reduced with a folding butterfly (9 shuffles for the eight sums); the fp32 part keeps the reference's order: eight
+// chains sums[l] += d * aux32[l] advanced super-block by super-block, sumf -= dmin * sumi, then sumf += sums[0..7].
+// Results are bit-identical to the scalar code (tests compare bits with oracle/_ref, the reference's own source).
+//
+// Weights and activations stay in ggml's AoS blocks (144 / 210 / 292 B): at 4.5 / 6.56 bits per weight a row of a
+// super-block is one 128 B + one 16 B line, so the warp's loads are already contiguous and a repack buys nothing.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kQK = 256;
+constexpr int kQ4K = 144, kQ6K = 210, kQ8K = 292;
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ uint32_t ld_u32(const uint8_t *p) { return *reinterpret_cast<const uint32_t *>(p); }
+__device__ __forceinline__ uint32_t ld_u16(const uint8_t *p) { return *reinterpret_cast<const uint16_t *>(p); }
+// 8 bytes from a 2-byte aligned address
+__device__ __forceinline__ void ld8_a2(const uint8_t *p, uint32_t &lo, uint32_t &hi) {
+    lo = ld_u16(p) | (ld_u16(p + 2) << 16);
+    hi = ld_u16(p + 4) | (ld_u16(p + 6) << 16);
+}
+__device__ __forceinline__ int sx8(uint32_t w, int i) { return (int)(int8_t)(w >> (8 * i)); }
+
+// v[0..7] per lane -> sum over the warp of v[l], returned in every lane of the group {4l .. 4l+3}
+__device__ __forceinline__ int fold8(int (&v)[8], int lane) {
+    int w4[4], w2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int send = b4 ? v[k] : v[4 + k];
+        const int keep = b4 ? v[4 + k] : v[k];
+        w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int send = b3 ? w4[k] : w4[2 + k];
+        const int keep = b3 ? w4[2 + k] : w4[k];
+        w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    int w = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
+    w += __shfl_xor_sync(0xffffffffu, w, 2);
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    return w; // l = 4*bit4 + 2*bit3 + bit2 = lane >> 2
+}
+
+__device__ __forceinline__ int warp_sum_i32(int v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// the eight chains live in lane groups; the final "for l: sumf += sums[l]" reads them in order
+__device__ __forceinline__ float finish_lanes(float sumf, float sums) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) sumf = __fadd_rn(sumf, __shfl_sync(0xffffffffu, sums, 4 * l));
+    return sumf;
+}
+
+__device__ __forceinline__ float dot_q4_K(const uint8_t *x, const uint8_t *y, int nb, int lane) {
+    float sums = 0.0f, sumf = 0.0f;
+    const int c = lane >> 3, hi = lane & 4, j = lane >> 2;
+#pragma unroll 1
+    for (int i = 0; i < nb; i++, x += kQ4K, y += kQ8K) {
+        const uint32_t dd = ld_u32(x);
+        uint32_t u0 = ld_u32(x + 4), u1 = ld_u32(x + 8), u2 = ld_u32(x + 12);
+        // 6-bit scales / mins (src/kernals.cl:75-80)
+        const uint32_t u3 = ((u2 >> 4) & 0x0f0f0f0fu) | (((u1 >> 6) & 0x03030303u) << 4);
+        const uint32_t uaux = u1 & 0x3f3f3f3fu;
+        u1 = (u2 & 0x0f0f0f0fu) | (((u0 >> 6) & 0x03030303u) << 4);
+        u2 = uaux;
+        u0 &= 0x3f3f3f3fu;
+        const int scale = (int)(((j < 4 ? u0 : u1) >> (8 * (j & 3))) & 0xff);
+        const uint8_t *q4 = x + 16 + 32 * c + 8 * (lane & 3);
+        uint32_t w0 = ld_u32(q4), w1 = ld_u32(q4 + 4);
+        if (hi) { w0 >>= 4; w1 >>= 4; }
+        w0 &= 0x0f0f0f0fu;
+        w1 &= 0x0f0f0f0fu;
+        const uint32_t a0 = ld_u32(y + 4 + 8 * lane), a1 = ld_u32(y + 8 + 8 * lane);
+        int v[8];
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            v[l] = scale * (sx8(a0, l) * (int)((w0 >> (8 * l)) & 0xff));
+            v[4 + l] = scale * (sx8(a1, l) * (int)((w1 >> (8 * l)) & 0xff));
+        }
+        const int aux = fold8(v, lane);
+        // sumi = sum_j bsums[j] * mins[j / 2]
+        int sm = 0;
+        if (lane < 16) {
+            const int bs = (int)(int16_t)ld_u16(y + 260 + 2 * lane);
+            const int mj = lane >> 1;
+            sm = bs * (int)(((mj < 4 ? u2 : u3) >> (8 * (mj & 3))) & 0xff);
+        }
+        const int sumi = warp_sum_i32(sm);
+        const float yd = __uint_as_float(ld_u32(y));
+        const float d = __fmul_rn(half_bits_to_float((uint16_t)(dd & 0xffff)), yd);
+        const float dmin = __fmul_rn(half_bits_to_float((uint16_t)(dd >> 16)), yd);
+        sums = __fadd_rn(sums, __fmul_rn(d, (float)aux));
+        sumf = __fsub_rn(sumf, __fmul_rn(dmin, (float)sumi));
+    }
+    return finish_lanes(sumf, sums);
+}
+
+__device__ __forceinline__ float dot_q6_K(const uint8_t *x, const uint8_t *y, int nb, int lane) {
+    float sums = 0.0f;
+    const int c = lane >> 4, quarter = (lane >> 2) & 3, l0 = 8 * (lane & 3);
+#pragma unroll 1
+    for (int i = 0; i < nb; i++, x += kQ6K, y += kQ8K) {
+        uint32_t q0, q1, h0, h1;
+        ld8_a2(x + 64 * c + 32 * (quarter & 1) + l0, q0, q1);
+        ld8_a2(x + 128 + 32 * c + l0, h0, h1);
+        if (quarter & 2) { q0 >>= 4; q1 >>= 4; }
+        q0 &= 0x0f0f0f0fu;
+        q1 &= 0x0f0f0f0fu;
+        h0 = ((h0 >> (2 * quarter)) & 0x03030303u) << 4;
+        h1 = ((h1 >> (2 * quarter)) & 0x03030303u) << 4;
+        q0 |= h0;
+        q1 |= h1;
+        const int scale = (int)(int8_t)x[192 + (lane >> 1)];
+        const uint32_t a0 = ld_u32(y + 4 + 8 * lane), a1 = ld_u32(y + 8 + 8 * lane);
+        int v[8];
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            v[l] = scale * (sx8(a0, l) * ((int)((q0 >> (8 * l)) & 0xff) - 32));
+            v[4 + l] = scale * (sx8(a1, l) * ((int)((q1 >> (8 * l)) & 0xff) - 32));
+        }
+        const int aux = fold8(v, lane);
+        const float d = __fmul_rn(half_bits_to_float((uint16_t)ld_u16(x + 208)), __uint_as_float(ld_u32(y)));
+        sums = __fadd_rn(sums, __fmul_rn(d, (float)aux));
+    }
+    return finish_lanes(0.0f, sums);
+}
+
+// fp16 x fp16 products are exact in fp32 and in double; the double sum is insensitive to its order at the
+// precision the final rounding to fp32 keeps (same argument as attention.cu)
+__device__ __forceinline__ float dot_f16(const uint8_t *x, const uint8_t *y, int64_t n, int lane) {
+    const __half2 *x2 = reinterpret_cast<const __half2 *>(x), *y2 = reinterpret_cast<const __half2 *>(y);
+    const __half *xh = reinterpret_cast<const __half *>(x), *yh = reinterpret_cast<const __half *>(y);
+    double acc = 0.0;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 3) == 0) {
+        for (int64_t i = lane; i < n / 2; i += 32) {
+            const float2 a = __half22float2(x2[i]), b = __half22float2(y2[i]);
+            acc = __fma_rn((double)a.x, (double)b.x, acc);
+            acc = __fma_rn((double)a.y, (double)b.y, acc);
+        }
+        if ((n & 1) && lane == 0)
+            acc = __fma_rn((double)__half2float(xh[n - 1]), (double)__half2float(yh[n - 1]), acc);
+    } else { // odd row pitch: 2-byte loads
+        for (int64_t i = lane; i < n; i += 32)
+            acc = __fma_rn((double)__half2float(xh[i]), (double)__half2float(yh[i]), acc);
+    }
+    return __double2float_rn(warp_sum_f64(acc));
+}
+
+// grid (ceil(rows / 8), T)
+template <int TYPE>
+__global__ void __launch_bounds__(kWarps * 32)
+raw_matvec_kernel(const uint8_t *__restrict__ w, int64_t rows, int64_t nb01, int64_t K, const uint8_t *__restrict__ act,
+                  int64_t row_size, float *__restrict__ dst, int64_t dst_stride) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint8_t *x = w + row * nb01;
+    const uint8_t *y = act + (int64_t)blockIdx.y * row_size;
+    float s;
+    if (TYPE == GGB_TYPE_Q4_K) s = dot_q4_K(x, y, (int)(K / kQK), lane);
+    else if (TYPE == GGB_TYPE_Q6_K) s = dot_q6_K(x, y, (int)(K / kQK), lane);
+    else s = dot_f16(x, y, K, lane);
+    if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = s;
+}
+
+// one warp per 256-element block; lane L holds elements 8L..8L+7
+__global__ void __launch_bounds__(kWarps * 32)
+quantize_q8_K_kernel(const float *__restrict__ x, int64_t n_blocks, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    const float4 f0 = *reinterpret_cast<const float4 *>(x + b * kQK + 8 * lane);
+    const float4 f1 = *reinterpret_cast<const float4 *>(x + b * kQK + 8 * lane + 4);
+    const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    // first element attaining max |x| (strict > in the scalar loop)
+    float amax = 0.0f, mx = 0.0f;
+    int idx = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        const float ax = fabsf(v[l]);
+        if (ax > amax) { amax = ax; mx = v[l]; idx = 8 * lane + l; }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float oa = __shfl_xor_sync(0xffffffffu, amax, off), om = __shfl_xor_sync(0xffffffffu, mx, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (oa > amax || (oa == amax && oi < idx)) { amax = oa; mx = om; idx = oi; }
+    }
+    uint8_t *o = out + b * kQ8K;
+    if (!(amax > 0.0f)) { // "if (!amax)": all zero (a NaN block cannot reach amax > 0 either; ggml leaves it at 0)
+        if (lane == 0) *reinterpret_cast<float *>(o) = 0.0f;
+        *reinterpret_cast<uint32_t *>(o + 4 + 8 * lane) = 0u;
+        *reinterpret_cast<uint32_t *>(o + 8 + 8 * lane) = 0u;
+        if (lane < 8) *reinterpret_cast<uint32_t *>(o + 260 + 4 * lane) = 0u;
+        return;
+    }
+    const float iscale = __fdiv_rn(-128.0f, mx);
+    int q[8], s = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        const float val = __fadd_rn(__fmul_rn(iscale, v[l]), 12582912.0f); // nearest_int: round half to even
+        q[l] = min(127, (__float_as_int(val) & 0x007fffff) - 0x00400000);
+        s += q[l];
+    }
+    const uint32_t p0 = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+    const uint32_t p1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+    *reinterpret_cast<uint32_t *>(o + 4 + 8 * lane) = p0;
+    *reinterpret_cast<uint32_t *>(o + 8 + 8 * lane) = p1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (!(lane & 1)) *reinterpret_cast<int16_t *>(o + 260 + lane) = (int16_t)s; // bsums[lane / 2]
+    if (lane == 0) *reinterpret_cast<float *>(o) = __fdiv_rn(1.0f, iscale);
+}
+
+} // namespace
+
+extern "C" {
+
+size_t ggb_type_row_bytes(int type, int64_t cols) {
+    switch (type) {
+    case GGB_TYPE_F32: return (size_t)cols * 4;
+    case GGB_TYPE_F16: return (size_t)cols * 2;
+    case GGB_TYPE_Q4_0: return (size_t)(cols / 32) * 18;
+    case GGB_TYPE_Q8_0: return (size_t)(cols / 32) * 34;
+    case GGB_TYPE_Q4_K: return (size_t)(cols / kQK) * kQ4K;
+    case GGB_TYPE_Q6_K: return (size_t)(cols / kQK) * kQ6K;
+    case GGB_TYPE_Q8_K: return (size_t)(cols / kQK) * kQ8K;
+    default: return 0;
+    }
+}
+
+int ggb_op_quantize_q8_K(const float *x, int64_t cols, int64_t rows, void *out) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(x && out, "null pointer");
+    GGB_CHECK_ARG(cols > 0 && cols % kQK == 0 && rows > 0, "quantize_q8_K: cols %lld not a multiple of 256", (long long)cols);
+    const int64_t n_blocks = rows * (cols / kQK);
+    quantize_q8_K_kernel<<<(unsigned)((n_blocks + kWarps - 1) / kWarps), kWarps * 32, 0, ggb_cuda_stream()>>>(
+        x, n_blocks, (uint8_t *)out);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_mul_mat_blocks(int type, const void *w, int64_t rows, int64_t nb01, int64_t K, const void *act,
+                          int64_t row_size, int64_t T, float *dst, int64_t dst_stride) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(w && act && dst, "null pointer");
+    GGB_CHECK_ARG(rows > 0 && T > 0 && T <= 65535 && K > 0, "mul_mat_blocks: bad extents");
+    const bool kq = type == GGB_TYPE_Q4_K || type == GGB_TYPE_Q6_K;
+    if (!kq && type != GGB_TYPE_F16) {
+        ggb_set_error("mul_mat_blocks: no kernel for type %d", type);
+        return GGB_ERR_UNSUPPORTED;
+    }
+    GGB_CHECK_ARG(!kq || K % kQK == 0, "mul_mat_blocks: K %lld not a multiple of 256", (long long)K);
+    GGB_CHECK_ARG(nb01 >= (int64_t)ggb_type_row_bytes(type, K) && nb01 % (type == GGB_TYPE_Q4_K ? 4 : 2) == 0,
+                  "mul_mat_blocks: src0 row pitch %lld", (long long)nb01);
+    const int64_t act_row = (int64_t)ggb_type_row_bytes(kq ? GGB_TYPE_Q8_K : GGB_TYPE_F16, K);
+    GGB_CHECK_ARG(row_size >= act_row && row_size % (kq ? 4 : 2) == 0, "mul_mat_blocks: activation row pitch %lld",
+                  (long long)row_size);
+    const dim3 grid((unsigned)((rows + kWarps - 1) / kWarps), (unsigned)T);
+    const uint8_t *wb = (const uint8_t *)w, *ab = (const uint8_t *)act;
+    cudaStream_t st = ggb_cuda_stream();
+    if (type == GGB_TYPE_Q4_K)
+        raw_matvec_kernel<GGB_TYPE_Q4_K><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, ab, row_size, dst, dst_stride);
+    else if (type == GGB_TYPE_Q6_K)
+        raw_matvec_kernel<GGB_TYPE_Q6_K><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, ab, row_size, dst, dst_stride);
+    else
+        raw_matvec_kernel<GGB_TYPE_F16><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, ab, row_size, dst, dst_stride);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+} // extern "C"

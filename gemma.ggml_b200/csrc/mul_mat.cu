@@ -2,8 +2,9 @@
 //   extern "C" void mul_mat(...)   ref: src/hpc.h:22-32, src/hpc.cpp:216-277
 // Same fields, HOST pointers, synchronous.  Where the reference split rows 90/10 between a CPU
 // thread pool and a verify-only OpenCL kernel (src/hpc.cpp:245-277, src/kernals.cl:203-211), every
-// row is computed on the B200; src0 is uploaded + repacked once and cached, only the activations
-// (wdata) and the result cross PCIe per call.
+// row is computed on the B200; src0 is uploaded (+ repacked for Q4_0 / Q8_0) once and cached, only the
+// activations (wdata) and the result cross PCIe per call.  Types: Q4_0 / Q8_0 (the benchmark's), and the three
+// the reference's kernels cover, Q4_K / Q6_K / F16 (kquants.cu).
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -22,6 +23,7 @@ struct CacheKey {
 };
 
 std::map<CacheKey, ggb_weight *> g_cache;
+std::map<CacheKey, void *> g_raw_cache; // K-quant / F16 src0 kept in ggml's own layout
 std::mutex g_mu;
 void *g_act_raw = nullptr, *g_act_q8 = nullptr;
 float *g_dst = nullptr;
@@ -37,6 +39,55 @@ int ensure(void **p, size_t *cap, size_t need) {
     return GGB_OK;
 }
 
+// result back with the reference's addressing (ref: src/hpc.cpp:26-31): dst + (col % ne1)*nb1 + (col / ne1)*nb2 + row*4
+int copy_back(void *dst_data, int64_t col_num, int64_t ne01, int64_t ne12, int64_t ne1, int64_t nb1, int64_t nb2,
+              cudaStream_t st) {
+    if (nb1 == ne01 * 4 && (ne12 == 1 || nb2 == nb1 * ne1)) {
+        GGB_CUDA(cudaMemcpyAsync(dst_data, g_dst, (size_t)col_num * ne01 * 4, cudaMemcpyDeviceToHost, st));
+    } else {
+        for (int64_t col = 0; col < col_num; col++) {
+            char *dcol = (char *)dst_data + (col % ne1) * nb1 + (col / ne1) * nb2;
+            GGB_CUDA(cudaMemcpyAsync(dcol, g_dst + col * ne01, (size_t)ne01 * 4, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    GGB_CUDA(cudaStreamSynchronize(st));
+    return GGB_OK;
+}
+
+// Q4_K / Q6_K / F16: the types the reference's own kernels cover (ref: src/hpc.cpp:132-143)
+int mul_mat_blocks(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64_t ne1, int64_t nb1, int64_t nb2,
+                   size_t row_size, int64_t K, const void *src0_data, void *dst_data, int type, const char *wdata) {
+    GGB_CHECK_ARG(nb1 % 4 == 0 && nb2 % 4 == 0 && nb1 >= ne01 * 4, "mul_mat: dst strides must hold %lld floats",
+                  (long long)ne01);
+    GGB_CHECK_ARG(nb01 >= (int64_t)ggb_type_row_bytes(type, K) && K > 0, "mul_mat: src0 row pitch %lld < row",
+                  (long long)nb01);
+    std::lock_guard<std::mutex> lk(g_mu);
+    void *w = nullptr;
+    const CacheKey key{src0_data, type, ne01, K, nb01};
+    auto it = g_raw_cache.find(key);
+    cudaStream_t st = ggb_cuda_stream();
+    if (it == g_raw_cache.end()) {
+        GGB_CUDA(cudaMalloc(&w, (size_t)ne01 * nb01));
+        cudaError_t e = cudaMemcpyAsync(w, src0_data, (size_t)ne01 * nb01, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cudaFree(w);
+            ggb_set_error("mul_mat: src0 upload -> %s", cudaGetErrorString(e));
+            return GGB_ERR_CUDA;
+        }
+        g_raw_cache[key] = w;
+    } else {
+        w = it->second;
+    }
+    const int64_t col_num = ne11 * ne12;
+    int rc;
+    if ((rc = ensure(&g_act_raw, &g_act_raw_cap, (size_t)col_num * row_size))) return rc;
+    if ((rc = ensure((void **)&g_dst, &g_dst_cap, (size_t)col_num * ne01 * 4))) return rc;
+    GGB_CUDA(cudaMemcpyAsync(g_act_raw, wdata, (size_t)col_num * row_size, cudaMemcpyHostToDevice, st));
+    if ((rc = ggb_op_mul_mat_blocks(type, w, ne01, nb01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01))) return rc;
+    return copy_back(dst_data, col_num, ne01, ne12, ne1, nb1, nb2, st);
+}
+
 } // namespace
 
 extern "C" {
@@ -44,14 +95,18 @@ extern "C" {
 int ggb_mul_mat(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64_t ne1, int64_t nb1, int64_t nb2,
                 size_t row_size, int64_t shared_edge, const void *src0_data, void *dst_data, int src0_type,
                 const char *wdata) {
-    GGB_REQUIRE_INIT();
-    if (src0_type != GGB_TYPE_Q4_0 && src0_type != GGB_TYPE_Q8_0) {
+    // the type check comes first: "no kernel for this type" does not depend on the device
+    const bool blocks = src0_type == GGB_TYPE_Q4_K || src0_type == GGB_TYPE_Q6_K || src0_type == GGB_TYPE_F16;
+    if (!blocks && src0_type != GGB_TYPE_Q4_0 && src0_type != GGB_TYPE_Q8_0) {
         ggb_set_error("mul_mat: no kernel for src0 type %d (ref behaviour: \"kernel is null\", src/hpc.cpp:162-166)",
                       src0_type);
         return GGB_ERR_UNSUPPORTED;
     }
+    GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(src0_data && dst_data && wdata, "mul_mat: null pointer");
     GGB_CHECK_ARG(ne01 > 0 && ne11 > 0 && ne12 > 0 && ne1 > 0, "mul_mat: bad extents");
+    if (blocks) return mul_mat_blocks(ne01, ne11, ne12, nb01, ne1, nb1, nb2, row_size, shared_edge, src0_data, dst_data,
+                                      src0_type, wdata);
     GGB_CHECK_ARG(shared_edge > 0 && shared_edge % GGB_QK == 0, "mul_mat: K %lld not a multiple of 32",
                   (long long)shared_edge);
     const int64_t K = shared_edge, nb = K / GGB_QK;
@@ -86,18 +141,8 @@ int ggb_mul_mat(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64_t 
     // 3. every column through the mat-vec kernel (grid.y = column)
     if ((rc = ggb_op_mul_mat_q8(w, g_act_q8, col_num, g_dst, ne01, nullptr))) return rc;
 
-    // 4. result back with the reference's addressing (ref: src/hpc.cpp:26-31):
-    //    dst + (col % ne1)*nb1 + (col / ne1)*nb2 + row*4
-    if (nb1 == ne01 * 4 && (ne12 == 1 || nb2 == nb1 * ne1)) {
-        GGB_CUDA(cudaMemcpyAsync(dst_data, g_dst, (size_t)col_num * ne01 * 4, cudaMemcpyDeviceToHost, st));
-    } else {
-        for (int64_t col = 0; col < col_num; col++) {
-            char *dcol = (char *)dst_data + (col % ne1) * nb1 + (col / ne1) * nb2;
-            GGB_CUDA(cudaMemcpyAsync(dcol, g_dst + col * ne01, (size_t)ne01 * 4, cudaMemcpyDeviceToHost, st));
-        }
-    }
-    GGB_CUDA(cudaStreamSynchronize(st));
-    return GGB_OK;
+    // 4. result back
+    return copy_back(dst_data, col_num, ne01, ne12, ne1, nb1, nb2, st);
 }
 
 int ggb_mul_mat_forget(const void *src0_data) {
@@ -106,6 +151,14 @@ int ggb_mul_mat_forget(const void *src0_data) {
         if (src0_data == nullptr || it->first.ptr == src0_data) {
             ggb_weight_free(it->second);
             it = g_cache.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    for (auto it = g_raw_cache.begin(); it != g_raw_cache.end();) {
+        if (src0_data == nullptr || it->first.ptr == src0_data) {
+            cudaFree(it->second);
+            it = g_raw_cache.erase(it);
         } else {
             ++it;
         }

@@ -21,12 +21,14 @@ struct ggml_tensor {
     void *data;
 };
 typedef void (*ggml_vec_dot_t)(int n, float *s, size_t bs, const void *x, size_t bx, const void *y, size_t by, int nrc);
-enum ggml_type { GGML_TYPE_F32 = 0, GGML_TYPE_F16 = 1, GGML_TYPE_Q4_0 = 2, GGML_TYPE_Q8_0 = 8 };
+enum ggml_type { GGML_TYPE_F32 = 0, GGML_TYPE_F16 = 1, GGML_TYPE_Q4_0 = 2, GGML_TYPE_Q8_0 = 8, GGML_TYPE_Q4_K = 12,
+                 GGML_TYPE_Q6_K = 14, GGML_TYPE_Q8_K = 15 };
 #endif
 
-/* ref: src/hpc.h:22-32.  vec_dot is accepted for signature compatibility and ignored: the device
- * kernel is selected by src0_type.  As in the reference there is no return value; a failure prints
- * the library's error text and exits (ref: src/hpc.cpp:163-166, src/opencl.cpp:13-17). */
+/* ref: src/hpc.h:22-32.  The device kernel is selected by src0_type (Q4_0, Q8_0, Q4_K, Q6_K, F16); for any other
+ * type the rows are computed with the caller's vec_dot, as the reference's mul_mat_sub does (src/hpc.cpp:15-41).
+ * As in the reference there is no return value; a device failure prints the library's error text and exits
+ * (ref: src/hpc.cpp:163-166, src/opencl.cpp:13-17). */
 void mul_mat(int64_t ne01, int64_t ne11, int64_t ne12,
              int64_t nb01,
              int64_t ne1,

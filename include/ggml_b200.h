@@ -32,7 +32,8 @@ typedef enum {
 } ggb_status;
 
 /* ggml_type values the path uses (upstream enum ids; ref: src/hpc.cpp:132-143) */
-enum { GGB_TYPE_F32 = 0, GGB_TYPE_F16 = 1, GGB_TYPE_Q4_0 = 2, GGB_TYPE_Q8_0 = 8 };
+enum { GGB_TYPE_F32 = 0, GGB_TYPE_F16 = 1, GGB_TYPE_Q4_0 = 2, GGB_TYPE_Q8_0 = 8,
+       GGB_TYPE_Q4_K = 12, GGB_TYPE_Q6_K = 14, GGB_TYPE_Q8_K = 15 }; /* ggml_type ids */
 
 /* Deterministic reduction orders of the kernels ("DEV order"; the oracle mirrors them):
  * mat-vec: K cut into segments of GGB_DEV_SEG_BLOCKS blocks, 32 lane-strided partials per
@@ -109,9 +110,12 @@ int ggb_vector_synth(float *dst_dev, int64_t n, uint64_t seed, uint64_t tensor_i
  * replaces: extern "C" void mul_mat(...) (src/hpc.h:22-32, src/hpc.cpp:216-277) — same
  * fields, HOST pointers, synchronous: on return all of dst is written.  src0_data/dst_data
  * are src0->data / dst->data of the ggml tensors; vec_dot is gone (the kernel is chosen by
- * src0_type).  wdata = src1 already converted to Q8_0 rows of `row_size` bytes by ggml's INIT
- * stage.  src0 is uploaded and repacked on first use and cached by (pointer, shape); call
- * ggb_mul_mat_forget(ptr) if the host copy changes. */
+ * src0_type).  wdata = src1 already converted by ggml's INIT stage to rows of `row_size` bytes in the
+ * type's vec_dot_type: Q8_0 for Q4_0 / Q8_0 weights, Q8_K for Q4_K / Q6_K (the types the reference's
+ * own kernels cover, src/hpc.cpp:132-143), F16 for F16.  Any other src0_type returns
+ * GGB_ERR_UNSUPPORTED (the host mirror host/hpc.cpp then runs the caller's vec_dot, as the reference's
+ * CPU share does).  src0 is uploaded (Q4_0 / Q8_0: repacked) on first use and cached by
+ * (pointer, shape); call ggb_mul_mat_forget(ptr) if the host copy changes. */
 int ggb_mul_mat(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64_t ne1, int64_t nb1, int64_t nb2,
                 size_t row_size, int64_t shared_edge, const void *src0_data, void *dst_data, int src0_type,
                 const char *wdata);
@@ -127,6 +131,18 @@ size_t ggb_q8_row_bytes(int64_t cols);
 int ggb_op_quantize_q8_0(const float *x, int64_t cols, int64_t T, void *q8);
 int ggb_op_q8_to_blocks(const void *q8, int64_t cols, int64_t T, void *blocks);   /* planar -> ggml AoS (34 B) */
 int ggb_op_q8_from_blocks(const void *blocks, int64_t cols, int64_t T, int64_t row_size, void *q8);
+
+/* K-quants.  Blocks stay in ggml's AoS layout on the device.
+ * ggb_type_row_bytes: bytes of one row of `cols` elements in `type` (0 for an unknown type).
+ * ggb_op_quantize_q8_K: [UPSTREAM] quantize_row_q8_K (block: src/kernals.cl:29-34), rows x cols floats ->
+ *   rows x cols/256 block_q8_K (292 B), bit-exact.
+ * ggb_op_mul_mat_blocks: dst[t][row] = vec_dot(w row, act row t) for type Q4_K / Q6_K (act = Q8_K rows) or F16
+ *   (act = fp16 rows); replaces matrix_multiply_q4_K / _q6_K / _f16 (src/kernals.cl:166-265) - which only
+ *   compared against the CPU result - with kernels that produce it, in the scalar code's summation order. */
+size_t ggb_type_row_bytes(int type, int64_t cols);
+int ggb_op_quantize_q8_K(const float *x, int64_t cols, int64_t rows, void *out);
+int ggb_op_mul_mat_blocks(int type, const void *w, int64_t rows, int64_t nb01, int64_t K, const void *act,
+                          int64_t row_size, int64_t T, float *dst, int64_t dst_stride);
 
 /* K2/K3 — dst[t][row] = dot(w[row], q8[t]) (+ residual[t][row]); dst row pitch dst_stride floats */
 int ggb_op_mul_mat_q8(const ggb_weight *w, const void *q8, int64_t T, float *dst, int64_t dst_stride,

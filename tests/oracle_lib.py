@@ -88,6 +88,9 @@ def lib():
         "orc_model_vcache": (vp, [vp, i32]),
         "orc_hpc_mul_mat": (None, [vp, i64, i64, i64, i64, i64, i64, i64, C.c_size_t, i64, vp, vp, i32, vp, i32]),
         "orc_model_threads": (i32, [vp]),
+        "orc_vec_dot_q4_K_q8_K": (None, [i32, vp, vp, vp]), "orc_vec_dot_q6_K_q8_K": (None, [i32, vp, vp, vp]),
+        "orc_quantize_row_q8_K": (None, [vp, vp, i64]),
+        "orc_dequantize_row_q4_K": (None, [vp, vp, i64]), "orc_dequantize_row_q6_K": (None, [vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -295,3 +298,49 @@ class Model:
 
 def tensor_id(layer, which):
     return 2 + 9 * layer + which
+
+
+# ---- K-quants -------------------------------------------------------------
+TYPE_F16, TYPE_Q4_K, TYPE_Q6_K, TYPE_Q8_K = 1, 12, 14, 15
+KQ_BLOCK = {TYPE_Q4_K: 144, TYPE_Q6_K: 210, TYPE_Q8_K: 292}
+
+
+def random_kquant_rows(rng, wtype, rows, k):
+    """valid random Q4_K / Q6_K rows: every bit pattern is a block; the fp16 super-scales are kept moderate"""
+    nb, size = k // 256, KQ_BLOCK[wtype]
+    b = rng.integers(0, 256, size=(rows, nb, size), dtype=np.uint8)
+    d = (rng.random((rows, nb)) * 0.01 + 0.001).astype(np.float16).view(np.uint16)
+    if wtype == TYPE_Q4_K:
+        b[:, :, 0:2] = d.view(np.uint8).reshape(rows, nb, 2)
+        b[:, :, 2:4] = (d // 2 * 2).view(np.uint8).reshape(rows, nb, 2)
+    else:
+        b[:, :, 208:210] = d.view(np.uint8).reshape(rows, nb, 2)
+    return np.ascontiguousarray(b.reshape(rows, nb * size))
+
+
+def quantize_q8_K(x):
+    """float32 [T, k] -> uint8 [T, k/256*292] block_q8_K rows ([UPSTREAM] quantize_row_q8_K_reference)"""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 1:
+        x = x[None, :]
+    out = np.zeros((x.shape[0], x.shape[1] // 256 * 292), dtype=np.uint8)
+    for r in range(x.shape[0]):
+        L.orc_quantize_row_q8_K(_p(x[r]), _p(out[r]), x.shape[1])
+    return out
+
+
+def mul_mat_blocks(wtype, w, act, k):
+    """w uint8 [N, row bytes] (Q4_K / Q6_K / F16), act uint8 [T, row bytes] (Q8_K / F16) -> float32 [T, N],
+    each element one scalar vec_dot (the loop of ref: src/hpc.cpp:15-41)"""
+    L = lib()
+    fn = {TYPE_Q4_K: L.orc_vec_dot_q4_K_q8_K, TYPE_Q6_K: L.orc_vec_dot_q6_K_q8_K, TYPE_F16: L.orc_vec_dot_f16}[wtype]
+    fn.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    out = np.zeros((act.shape[0], w.shape[0]), dtype=np.float32)
+    s = C.c_float(0)
+    for t in range(act.shape[0]):
+        for r in range(w.shape[0]):
+            fn(k, C.byref(s), _p(w[r]), _p(act[t]))
+            out[t, r] = s.value
+    return out

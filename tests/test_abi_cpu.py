@@ -14,7 +14,7 @@ import gemma_ggml_b200 as G
 def _declared_symbols():
     src = open(G.HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ggb_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ggb_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported():
@@ -75,3 +75,38 @@ def test_config_struct_layout_matches_oracle():
     import oracle_lib as O
     assert C.sizeof(G.Config) == C.sizeof(O.Config)
     assert [f[0] for f in G.Config._fields_] == [f[0] for f in O.Config._fields_]
+
+
+def test_mul_mat_without_a_device_kernel_runs_the_callers_vec_dot():
+    """ref: src/hpc.cpp:15-41 — the reference computes rows with the vec_dot it is handed; the drop-in keeps that for
+    src0 types that have no device kernel (here F32 x F32, no GPU needed: the type check precedes the device check)."""
+    import ctypes as C
+    import numpy as np
+    host = G.host_lib()
+
+    class Tensor(C.Structure):
+        _fields_ = [("data", C.c_void_p)]
+
+    VD = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_float), C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int)
+    calls = []
+
+    def vec_dot(n, s, bs, x, bx, y, by, nrc):
+        a = np.ctypeslib.as_array(C.cast(x, C.POINTER(C.c_float)), (n,))
+        b = np.ctypeslib.as_array(C.cast(y, C.POINTER(C.c_float)), (n,))
+        s[0] = float(np.dot(a.astype(np.float64), b.astype(np.float64)))
+        calls.append(n)
+
+    rng = np.random.default_rng(0)
+    n, k, t = 6, 40, 3
+    w = rng.standard_normal((n, k)).astype(np.float32)
+    a = rng.standard_normal((t, k)).astype(np.float32)
+    dst = np.zeros((t, n), np.float32)
+    src0, src1, d = Tensor(w.ctypes.data), Tensor(a.ctypes.data), Tensor(dst.ctypes.data)
+    host.mul_mat.restype = None
+    host.mul_mat.argtypes = [C.c_int64] * 7 + [C.c_size_t, C.c_int64, C.POINTER(Tensor), C.POINTER(Tensor),
+                                               C.POINTER(Tensor), VD, C.c_int, C.c_char_p]
+    cb = VD(vec_dot)
+    host.mul_mat(n, t, 1, k * 4, t, n * 4, n * 4 * t, k * 4, k, C.byref(src0), C.byref(src1), C.byref(d), cb, 0,
+                 C.cast(a.ctypes.data, C.c_char_p))
+    assert len(calls) == n * t
+    assert np.allclose(dst, a @ w.T, rtol=1e-6, atol=1e-6)

@@ -15,35 +15,17 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libkernals_ref.so")
 
 def _oracle():
     L = O.lib()
-    for name in ("orc_vec_dot_q4_K_q8_K", "orc_vec_dot_q6_K_q8_K"):
-        getattr(L, name).argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        getattr(L, name).restype = None
-    L.orc_quantize_row_q8_K.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-    L.orc_dequantize_row_q4_K.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
-    L.orc_dequantize_row_q6_K.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.orc_vec_dot_f16.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_vec_dot_f16.restype = None
     return L
 
 
 def random_blocks(rng, wtype, rows, k):
-    """valid random K-quant rows (every bit pattern is a valid block; the fp16 scales are kept moderate)"""
-    nb = k // 256
-    size = {12: 144, 14: 210}[wtype]
-    b = rng.integers(0, 256, size=(rows, nb, size), dtype=np.uint8)
-    d = (rng.random((rows, nb)) * 0.01 + 0.001).astype(np.float16).view(np.uint16)
-    if wtype == 12:
-        b[:, :, 0:2] = d.view(np.uint8).reshape(rows, nb, 2)
-        b[:, :, 2:4] = (d // 2 * 2).view(np.uint8).reshape(rows, nb, 2)
-    else:
-        b[:, :, 208:210] = d.view(np.uint8).reshape(rows, nb, 2)
-    return np.ascontiguousarray(b.reshape(rows, nb * size))
+    return O.random_kquant_rows(rng, wtype, rows, k)
 
 
 def q8k(L, x):
-    x = np.ascontiguousarray(x, dtype=np.float32)
-    out = np.zeros((x.shape[0], x.shape[1] // 256 * 292), dtype=np.uint8)
-    for r in range(x.shape[0]):
-        L.orc_quantize_row_q8_K(x[r].ctypes.data, out[r].ctypes.data, x.shape[1])
-    return out
+    return O.quantize_q8_K(x)
 
 
 def dot(fn, k, w, a):
