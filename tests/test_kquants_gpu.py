@@ -13,16 +13,8 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
 
 
-@pytest.fixture(scope="module")
-def G():
-    import importlib
-    g = importlib.import_module("gemma.ggml_b200")
-    g.init()
-    return g
-
-
 @pytest.mark.parametrize("k", [256, 2048, 16384])
-def test_quantize_row_q8_K_bitwise(G, k):
+def test_quantize_row_q8_K_bitwise(gpu, k):
     rng = np.random.default_rng(k)
     x = (rng.standard_normal((5, k)) * rng.choice([1e-3, 1.0, 40.0], size=(5, 1))).astype(np.float32)
     x[1, :256] = 0.0                      # an all-zero block
@@ -30,25 +22,25 @@ def test_quantize_row_q8_K_bitwise(G, k):
     x[3, 10] = x[3, 3] = np.float32(3.5)  # a tie: the first maximum decides the sign
     x[3, 11] = np.float32(-3.5)
     x[3, :256] = np.clip(x[3, :256], -3.5, 3.5)
-    assert np.array_equal(G.quantize_q8_K(x), O.quantize_q8_K(x))
+    assert np.array_equal(gpu.quantize_q8_K(x), O.quantize_q8_K(x))
 
 
 @pytest.mark.parametrize("wtype", [O.TYPE_Q4_K, O.TYPE_Q6_K])
 @pytest.mark.parametrize("n,k,t", [(64, 2048, 1), (40, 16384, 3), (13, 256, 2), (256, 3072, 1)])
-def test_kquant_mul_mat_matches_scalar_reference_order(G, wtype, n, k, t):
+def test_kquant_mul_mat_matches_scalar_reference_order(gpu, wtype, n, k, t):
     rng = np.random.default_rng(n + k + wtype)
     w = O.random_kquant_rows(rng, wtype, n, k)
     act = O.quantize_q8_K(rng.standard_normal((t, k)) * 2)
     want = O.mul_mat_blocks(wtype, w, act, k)
-    got = G.mul_mat_host(wtype, w, act, k)
+    got = gpu.mul_mat_host(wtype, w, act, k)
     assert np.array_equal(bits(got), bits(want))
     # the device quantizer feeds the same kernel: end to end from fp32 activations
-    act_dev = G.quantize_q8_K(np.ascontiguousarray(rng.standard_normal((1, k)), dtype=np.float32))
-    assert np.array_equal(bits(G.mul_mat_host(wtype, w, act_dev, k)), bits(O.mul_mat_blocks(wtype, w, act_dev, k)))
+    act_dev = gpu.quantize_q8_K(np.ascontiguousarray(rng.standard_normal((1, k)), dtype=np.float32))
+    assert np.array_equal(bits(gpu.mul_mat_host(wtype, w, act_dev, k)), bits(O.mul_mat_blocks(wtype, w, act_dev, k)))
 
 
 @pytest.mark.parametrize("n,k,t", [(32, 256, 1), (17, 2050, 2), (8, 8191, 1)])
-def test_f16_mul_mat_double_accumulator(G, n, k, t):
+def test_f16_mul_mat_double_accumulator(gpu, n, k, t):
     rng = np.random.default_rng(k)
     kp = k + (k & 1)  # row pitch stays 4-byte friendly; the dot runs over k elements
     w = np.zeros((n, kp), np.float16)
@@ -57,11 +49,11 @@ def test_f16_mul_mat_double_accumulator(G, n, k, t):
     a[:, :k] = rng.standard_normal((t, k)) * 8
     wb, ab = w.view(np.uint8).reshape(n, kp * 2), a.view(np.uint8).reshape(t, kp * 2)
     want = O.mul_mat_blocks(O.TYPE_F16, wb, ab, k)
-    got = G.mul_mat_host(O.TYPE_F16, wb, ab, k)
+    got = gpu.mul_mat_host(O.TYPE_F16, wb, ab, k)
     assert np.array_equal(bits(got), bits(want))
 
 
-def test_mul_mat_strided_dst_and_batches(G):
+def test_mul_mat_strided_dst_and_batches(gpu):
     """ne12 > 1 and a padded dst pitch: the reference's addressing dst + (col % ne1)*nb1 + (col / ne1)*nb2"""
     import ctypes as C
     rng = np.random.default_rng(1)
@@ -71,16 +63,16 @@ def test_mul_mat_strided_dst_and_batches(G):
     want = O.mul_mat_blocks(O.TYPE_Q4_K, w, act, k)
     pitch = n + 8
     dst = np.full((ne12, ne11, pitch), np.float32(-7), dtype=np.float32)
-    L = G.cuda_lib()
-    G.check(L.ggb_mul_mat(n, ne11, ne12, w.shape[1], ne11, pitch * 4, pitch * 4 * ne11, act.shape[1], k,
+    L = gpu.cuda_lib()
+    gpu.check(L.ggb_mul_mat(n, ne11, ne12, w.shape[1], ne11, pitch * 4, pitch * 4 * ne11, act.shape[1], k,
                           w.ctypes.data, dst.ctypes.data, O.TYPE_Q4_K, act.ctypes.data), "ggb_mul_mat")
     L.ggb_mul_mat_forget(w.ctypes.data)
     assert np.array_equal(bits(dst[:, :, :n].reshape(-1, n)), bits(want))
     assert np.all(dst[:, :, n:] == -7)
 
 
-def test_unsupported_type_is_reported_not_computed(G):
-    L = G.cuda_lib()
+def test_unsupported_type_is_reported_not_computed(gpu):
+    L = gpu.cuda_lib()
     buf = np.zeros(1024, np.uint8)
     assert L.ggb_mul_mat(1, 1, 1, 64, 1, 4, 4, 64, 32, buf.ctypes.data, buf.ctypes.data, 10, buf.ctypes.data) == -4
     assert b"no kernel" in L.ggb_last_error()
