@@ -846,6 +846,64 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
     const bool handoff = kind == PH_GATE_UP || kA > 1 || (quad && kf > 0);
     float racc = 0.0f;
     int tb = 0, turn = 0;
+    // SEGMENT-DRIVEN ROW-LANE CHAIN (O / DOWN of the Gemma shapes): one round per K segment, for every row at once - a
+    // row's 512 (DOWN, 2B) terms are 8 rounds of 64 dependent adds and nothing else.  Round k starts when the slot
+    // holding the last pass of segment k has its terms; a lane reads its pass wherever it lies (a segment's passes
+    // span at most two slots, so two term buffers are live at a time), and a buffer is handed back as soon as the
+    // rounds have consumed all of its passes.  The slot-driven loop below costs a round per (slot, segment) piece -
+    // 11 instead of 8 for DOWN - and ~300 cycles of scalar bookkeeping per round.
+    const bool seg_driven = rowlane && !quad && n_passes == npairs * kA && (npairs + F::PPS - 2) / F::PPS + 1 <= nbuf;
+    if (seg_driven) {
+        const int n_slots = (n_passes + F::PPS - 1) / F::PPS;
+        if (ci == 0) {
+            const int pair = lane >> 1;
+            const bool act2 = pair < npairs;
+            uint32_t wmask = tmask;
+            int wb = 0, rb = 0, waited = 0, released = 0;
+            int p = act2 ? pair : 0, ls = 0, lb = 0; // this lane's pass of segment k, its slot and that slot's buffer
+#pragma unroll 1
+            for (int k = 0; k < kA; k++, p += npairs) {
+                const bool last = k == kA - 1;
+                const int done = (k + 1) * npairs; // passes consumed once this round is over
+                const int need = (done - 1) / F::PPS;
+                if (PROF) pt0 = clock64();
+                while (waited <= need) {
+                    mbar_wait(tf0 + 8 * wb, (wmask >> wb) & 1u);
+                    if (PROF && prof && lane == 0 && waited < 8) P.prof[64 * cta + 48 + 2 * waited] = clock64() - p_begin;
+                    wmask ^= 1u << wb;
+                    if (++wb == nbuf) wb = 0;
+                    waited++;
+                }
+                if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; }
+                const int ns = p / F::PPS;
+                while (ls < ns) {
+                    ls++;
+                    if (++lb == nbuf) lb = 0;
+                }
+                ll_t rv = 0;
+                if (last && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
+                const uint32_t addr = terms0 + (uint32_t)lb * (uint32_t)(kTermFloats * 4) +
+                                      (uint32_t)((2 * (p & (F::PPS - 1)) + ab) * kTermRow * 4);
+                if (PROF) pta = clock64();
+                racc = chain_add(addr, 0, last ? tail_blocks : kSeg, racc);
+                if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; if (prof && lane == 0 && k < 8) P.prof[64 * cta + 24 + k] = t1 - p_begin; }
+                if (last && act2) finish_row(lane, racc, rv);
+                __syncwarp();
+                while (released < waited && ((released + 1) * F::PPS <= done || last)) {
+                    if (lane == 0) mbar_arrive(te0 + 8 * rb);
+                    if (PROF && prof && lane == 0 && released < 8) P.prof[64 * cta + 49 + 2 * released] = clock64() - p_begin;
+                    if (++rb == nbuf) rb = 0;
+                    released++;
+                }
+                if (PROF) p_chain += clock64() - pt0;
+            }
+        }
+        for (int sl = 0; sl < n_slots; sl++) {
+            tmask ^= 1u << tb;
+            if (++tb == nbuf) tb = 0;
+        }
+        gslot += n_slots;
+    } else
 #pragma unroll 1
     for (int m0 = 0; m0 < n_passes; m0 += F::PPS, gslot++) {
         const int cnt = min(F::PPS, n_passes - m0);
@@ -873,7 +931,9 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
                         ll_t rv = 0;
                         if (last && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
                         const int c = 2 * (jj + pair - rem) + ab;
+                        if (PROF) pta = clock64();
                         const float r = chain_add(tbase + (uint32_t)((c & 31) * kTermRow * 4), 0, len, segc > 0 ? racc : 0.0f);
+                        if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; if (prof && lane == 0 && p_rounds <= 8) P.prof[64 * cta + 23 + p_rounds] = t1 - p_begin; }
                         if (act2) {
                             racc = r;
                             if (last) finish_row(lane, r, rv);

@@ -59,8 +59,8 @@ def main():
             print("inside phase %d (%s), us per CTA (median / max): consumer warp 0: prologue, wait weights, wait term buffer, compute, total, passes" % (ph, kind))
             print("   median", np.round(np.median(pr[:, :6], axis=0), 2)); print("   max   ", np.round(pr[:, :6].max(axis=0), 2))
             print("   chain warp: wait terms, chain, finish (incl. GeGLU), rounds, total, passes, of chain: adds, row finish")
-            print("   median", np.round(np.median(pr[:, 16:24], axis=0), 2)); print("   max   ", np.round(pr[:, 16:24].max(axis=0), 2))
-            print("   (counts are shown divided by 1965)")
+            ch = pr[:, 16:24].copy(); ch[:, 3] *= 1965.0; ch[:, 5] *= 1965.0  # rounds / passes are counts
+            print("   median", np.round(np.median(ch, axis=0), 2)); print("   max   ", np.round(ch.max(axis=0), 2))
             print("   consumer warp 0, slots 0..3: (weights arrived, term buffer free, terms stored) us since phase start:", np.round(np.median(pr[:, 32:44], axis=0), 2))
             print("   chain warp 0, its slots: (terms arrived, slot done) us since phase start:", np.round(np.median(pr[:, 48:64], axis=0), 2))
             print("   row-lane mode: end of chain rounds 1..8, us since phase start (median)", np.round(np.median(pr[:, 24:32], axis=0), 2))
