@@ -903,6 +903,37 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
             if (++tb == nbuf) tb = 0;
         }
         gslot += n_slots;
+    } else if (!rowlane && kA == 1 && !quad) {
+        // SINGLE-SEGMENT PHASES (K <= 2048: QKV / GATE_UP / LOGITS of Gemma-2B): a slot is one round, lane = row of the
+        // slot, nothing is carried from slot to slot.  Same arithmetic as the general loop below with its bookkeeping
+        // (a single warp runs scalar control code at ~5 cycles per instruction) stripped to what this case needs.
+#pragma unroll 1
+        for (int m0 = 0; m0 < n_passes; m0 += F::PPS, gslot++) {
+            if (turn == ci) {
+                const int cnt = min(F::PPS, n_passes - m0);
+                if (PROF) pt0 = clock64();
+                mbar_wait(tf0 + 8 * tb, (tmask >> tb) & 1u);
+                if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; const int k = m0 / F::PPS; if (prof && lane == 0 && ci == 0 && k < 8) P.prof[64 * cta + 48 + 2 * k] = t1 - p_begin; }
+                const int rl = 2 * m0 + lane;
+                const bool active = j < cnt;
+                ll_t rv = 0;
+                if (active && resid && row0 + rl < n_lr) rv = ll_peek(resid + oidx(row0 + rl));
+                const float acc = chain_add(terms0 + (uint32_t)tb * (uint32_t)(kTermFloats * 4) + (uint32_t)(lane * kTermRow * 4), 0, tail_blocks, 0.0f);
+                if (PROF) { const long long t1 = clock64(); p_add += t1 - pt0; }
+                if (active) finish_row(rl, acc, rv);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(te0 + 8 * tb);
+                if (PROF) { const long long t1 = clock64(); p_chain += t1 - pt0; pt0 = t1; }
+                if (handoff) __threadfence_block();
+                while (S.done_slot != gslot) __nanosleep(20);
+                __syncwarp();
+                if (lane == 0) S.done_slot = gslot + 1;
+                if (PROF) { const long long t1 = clock64(); p_fin += t1 - pt0; const int k = m0 / F::PPS; if (prof && lane == 0 && ci == 0 && k < 8) P.prof[64 * cta + 49 + 2 * k] = t1 - p_begin; }
+            }
+            tmask ^= 1u << tb;
+            if (++tb == nbuf) tb = 0;
+            if (++turn == kNCH) turn = 0;
+        }
     } else
 #pragma unroll 1
     for (int m0 = 0; m0 < n_passes; m0 += F::PPS, gslot++) {
@@ -1360,14 +1391,26 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int ct
             fma8(raw, pos);
         }
         PROF_STAMP(6);
-        // lanes with the same octet, then the 16 warps (any order: double)
-        for (int off = 1 << P.pv_oct_shift; off <= 16; off <<= 1) {
+        // lanes with the same octet (they differ in lane bits oct_shift .. 4), then the 16 warps (any order: double).
+        // Folded butterfly: a lane hands over half of its sums at every step (4 + 2 + 1 doubles instead of 8 + 8 + 8)
+        // and ends with dim e = 4 bit4 + 2 bit3 + bit2 of its octet.
+        {
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            double k4[4], k2[2];
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[e] = __dadd_rn(acc[e], __shfl_xor_sync(0xffffffffu, acc[e], off));
-        }
-        if (lane < (1 << P.pv_oct_shift)) {
+            for (int v = 0; v < 4; v++) {
+                const double send = b4 ? acc[v] : acc[4 + v], keep = b4 ? acc[4 + v] : acc[v];
+                k4[v] = __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
 #pragma unroll
-            for (int e = 0; e < 8; e++) part[warp * 32 + 8 * lane + e] = acc[e];
+            for (int v = 0; v < 2; v++) {
+                const double send = b3 ? k4[v] : k4[2 + v], keep = b3 ? k4[2 + v] : k4[v];
+                k2[v] = __dadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            double k1 = __dadd_rn(b2 ? k2[1] : k2[0], __shfl_xor_sync(0xffffffffu, b2 ? k2[0] : k2[1], 4));
+            if (P.pv_oct_shift == 1) k1 = __dadd_rn(k1, __shfl_xor_sync(0xffffffffu, k1, 2));
+            const int oct = lane & ((1 << P.pv_oct_shift) - 1), e = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+            if (P.pv_oct_shift == 2 || !(lane & 2)) part[warp * 32 + 8 * oct + e] = k1;
         }
         consumer_bar();
         if (tid < W) {
