@@ -359,6 +359,30 @@ __device__ __forceinline__ uint32_t ll_get(ll_t v, const ll_t *p, uint32_t tag) 
     return (uint32_t)v;
 }
 __device__ __forceinline__ float ll_get_f(ll_t v, const ll_t *p, uint32_t tag) { return __uint_as_float(ll_get(v, p, tag)); }
+// A thread's N flagged words p[0], p[stride], ... (the first n of them), requested together.  When the data is there this
+// is ONE L2 round trip.  When it is not, polling the words one after the other (ll_get on each) would cost a round trip
+// PER WORD after the data has arrived - every stale word has to be re-read, serially; instead the thread spins on one
+// missing word and then re-reads all of them at once: the wait ends at most two round trips after the last store.
+template <int N>
+__device__ __forceinline__ void ll_gather(ll_t (&v)[N], const ll_t *p, int stride, int n, uint32_t tag) {
+#pragma unroll
+    for (int u = 0; u < N; u++) v[u] = u < n ? ll_peek(p + (size_t)stride * u) : 0ull;
+    for (;;) {
+        int bad = -1;
+#pragma unroll
+        for (int u = N - 1; u >= 0; u--) bad = (u < n && (uint32_t)(v[u] >> 32) != tag) ? u : bad;
+        if (bad < 0) return;
+        const ll_t *pb = p + (size_t)stride * bad;
+#if GGB_WATCHDOG
+        for (uint32_t spins = 0; (uint32_t)(ll_peek(pb) >> 32) != tag; spins++)
+            if (spins > (1u << 24)) __trap();
+#else
+        while ((uint32_t)(ll_peek(pb) >> 32) != tag) {}
+#endif
+#pragma unroll
+        for (int u = 0; u < N; u++) v[u] = u < n ? ll_peek(p + (size_t)stride * u) : 0ull;
+    }
+}
 
 __device__ __forceinline__ unsigned long long gtime() { // ns, one clock for the whole GPU (SM clocks are not aligned)
     unsigned long long t;
@@ -538,12 +562,11 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
         for (int k0 = 0; k0 < nk; k0 += NV) {
             ll_t v[NV];
             const ll_t *pw = in + GGB_DEV_NORM_THREADS * k0 + base;
-#pragma unroll
-            for (int u = 0; u < NV; u++) v[u] = k0 + u < nk ? ll_peek(pw + GGB_DEV_NORM_THREADS * u) : 0ull;
+            ll_gather<NV>(v, pw, GGB_DEV_NORM_THREADS, nk - k0, tag);
 #pragma unroll
             for (int u = 0; u < NV; u++) {
                 if (k0 + u < nk) {
-                    const float x = ll_get_f(v[u], pw + GGB_DEV_NORM_THREADS * u, tag);
+                    const float x = __uint_as_float((uint32_t)v[u]);
                     xs[GGB_DEV_NORM_THREADS * (k0 + u) + base] = x;
                     acc = __dadd_rn(acc, (double)__fmul_rn(x, x));
                 }
@@ -593,11 +616,10 @@ __device__ __forceinline__ void quant_prologue(Smem<TYPE> &S, const ll_t *in, in
     for (int quad = warp; quad < K / 128; quad += kCW) {
         const ll_t *p = in + 128 * quad + 4 * lane;
         ll_t w[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) w[e] = ll_peek(p + e);
+        ll_gather<4>(w, p, 1, 4, tag);
         float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) v[e] = ll_get_f(w[e], p + e, tag);
+        for (int e = 0; e < 4; e++) v[e] = __uint_as_float((uint32_t)w[e]);
         quant_quad_to_smem(ua, quad, lane, v, K / 2, K);
     }
     consumer_bar();
@@ -615,13 +637,12 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
 #pragma unroll 1
     for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 4 words in flight per thread (more spills at the 96-register limit)
         ll_t v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) v[u] = i0 + kCT * u < nw + ns ? ll_peek(in + i0 + kCT * u) : 0ull;
+        ll_gather<4>(v, in + i0, kCT, (nw + ns - i0 + kCT - 1) / kCT, tag);
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int i = i0 + kCT * u;
             if (i < nw + ns) {
-                const uint32_t w = ll_get(v[u], in + i, tag);
+                const uint32_t w = (uint32_t)v[u];
                 if (i < nw) aq[((i & 4) ? nw / 2 : 0) + 4 * (i >> 3) + (i & 3)] = w; // two planes (see quant_quad_to_smem)
                 else {
                     ad[i - nw] = __ushort_as_half((unsigned short)w);
@@ -1151,9 +1172,10 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
         for (int i = tid; i < Gh * halfd; i += kCT) {
             const int jh = i >> P.hd_shift, e = i & (halfd - 1);
             const ll_t *qh = q_all + (size_t)(h0 + jh) * d;
-            const ll_t w0 = ll_peek(qh + e), w1 = ll_peek(qh + e + halfd);
             const float cs = cosr[e], sn = sinr[e];
-            const float x0 = ll_get_f(w0, qh + e, tag), x1 = ll_get_f(w1, qh + e + halfd, tag);
+            ll_t w[2];
+            ll_gather<2>(w, qh + e, halfd, 2, tag);
+            const float x0 = __uint_as_float((uint32_t)w[0]), x1 = __uint_as_float((uint32_t)w[1]);
             const float r0 = __fmul_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(x1, sn)), P.q_scale);
             const float r1 = __fmul_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, cs)), P.q_scale);
             // a lane's dims 8l .. 8l+7 as four 16-byte pieces, piece k of all lanes contiguous: conflict-free LDS.128
@@ -1297,13 +1319,12 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int ct
 #pragma unroll 1
         for (int i0 = tid; i0 < n_pos; i0 += 4 * kCT) {
             ll_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = i0 + kCT * u < n_pos ? ll_peek(srow + i0 + kCT * u) : 0ull;
+            ll_gather<4>(v, srow + i0, kCT, (n_pos - i0 + kCT - 1) / kCT, tag);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int i = i0 + kCT * u;
                 if (i < n_pos) {
-                    const float s = ll_get_f(v[u], srow + i, tag);
+                    const float s = __uint_as_float((uint32_t)v[u]);
                     sp[i] = s;
                     mx = fmaxf(mx, s);
                 }
