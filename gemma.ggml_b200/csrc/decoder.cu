@@ -380,7 +380,8 @@ __device__ __forceinline__ void ll_gather(ll_t (&v)[N], const ll_t *p, int strid
         while ((uint32_t)(ll_peek(pb) >> 32) != tag) {}
 #endif
 #pragma unroll
-        for (int u = 0; u < N; u++) v[u] = u < n ? ll_peek(p + (size_t)stride * u) : 0ull;
+        for (int u = 0; u < N; u++) // only the words that were missing (the others would be N reads per round for nothing)
+            if (u < n && (uint32_t)(v[u] >> 32) != tag) v[u] = ll_peek(p + (size_t)stride * u);
     }
 }
 
@@ -635,11 +636,12 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
     __half *ad = reinterpret_cast<__half *>(S.u + act_d_off(K));
     int *bias = reinterpret_cast<int *>(S.u + act_bias_off(K));
 #pragma unroll 1
-    for (int i0 = tid; i0 < nw + ns; i0 += 4 * kCT) { // 4 words in flight per thread (more spills at the 96-register limit)
-        ll_t v[4];
-        ll_gather<4>(v, in + i0, kCT, (nw + ns - i0 + kCT - 1) / kCT, tag);
+    constexpr int NW = 5; // words in flight per thread (9 = a whole Gemma-2B DOWN row at once measured 9 % SLOWER per token; 4 and 5 tie)
+    for (int i0 = tid; i0 < nw + ns; i0 += NW * kCT) {
+        ll_t v[NW];
+        ll_gather<NW>(v, in + i0, kCT, (nw + ns - i0 + kCT - 1) / kCT, tag);
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < NW; u++) {
             const int i = i0 + kCT * u;
             if (i < nw + ns) {
                 const uint32_t w = (uint32_t)v[u];
@@ -1634,13 +1636,15 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         } else if (kind == PH_PV) {
             pv_phase<TYPE, PROF>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
-            if (cta == 0 && cwarp == 0) {
+            if (cta == 0) { // all consumer warps: one candidate per thread, i.e. ONE round trip instead of one per 32
+                const int nc = P.R * G * kNCH;
                 Best b{-INFINITY, -1};
-                for (int i = lane; i < P.R * G * kNCH; i += 32) {
-                    const ll_t *pv = P.cand_ll + i, *pi2 = P.cand_ll + P.R * G * kNCH + i;
-                    const ll_t wv = ll_peek(pv), wi = ll_peek(pi2);
-                    b = better(b, Best{ll_get_f(wv, pv, tag), (int)ll_get(wi, pi2, tag)});
+                for (int i = ctid; i < nc; i += kCT) {
+                    ll_t w[2];
+                    ll_gather<2>(w, P.cand_ll + i, nc, 2, tag);
+                    b = better(b, Best{__uint_as_float((uint32_t)w[0]), (int)(uint32_t)w[1]});
                 }
+                int *redi = reinterpret_cast<int *>(S.red);
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
                     Best o;
@@ -1649,6 +1653,21 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
                     b = better(b, o);
                 }
                 if (lane == 0) {
+                    S.redf[cwarp] = b.v;
+                    redi[cwarp] = b.i;
+                }
+                consumer_bar();
+                if (cwarp == 0) {
+                    b = lane < kCW ? Best{S.redf[lane], redi[lane]} : Best{-INFINITY, -1};
+#pragma unroll
+                    for (int off = 8; off >= 1; off >>= 1) {
+                        Best o;
+                        o.v = __shfl_xor_sync(0xffffffffu, b.v, off);
+                        o.i = __shfl_xor_sync(0xffffffffu, b.i, off);
+                        b = better(b, o);
+                    }
+                }
+                if (cwarp == 0 && lane == 0) {
                     // every CTA has published its candidate, i.e. has long read state and seq.  The position stops at
                     // n_ctx - 1 (the KV cache, the rope table and history[n_ctx + 2] end there).
                     int np = P.state[1] + P.state[2];
