@@ -1218,33 +1218,37 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
         {
             const bool in = 8 * lane < d;
             const int j0 = warp, j1 = warp + kCW;
-            // one position at a time (its K row as 8 doubles, a head's q as 8 more: the register budget of the kernel)
+            // both positions of the warp against one read of q (the fp64 q rows in shared memory are the phase's
+            // bandwidth: 4 wavefronts per LDS.128, once per (head, dim quad) instead of once per position)
             double acc[2][4];
+            double kd[2][8];
 #pragma unroll
             for (int p = 0; p < 2; p++) {
                 const int jr = p ? j1 : j0;
                 uint4 raw = make_uint4(0, 0, 0, 0);
                 if (in && jr < np) raw = *reinterpret_cast<const uint4 *>(Kc + jr * d + 8 * lane);
                 const __half2 *h2 = reinterpret_cast<const __half2 *>(&raw);
-                double kd[8];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     const float2 f = __half22float2(h2[e]);
-                    kd[2 * e] = (double)f.x;
-                    kd[2 * e + 1] = (double)f.y;
+                    kd[p][2 * e] = (double)f.x;
+                    kd[p][2 * e + 1] = (double)f.y;
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    double a = 0.0;
+            for (int u = 0; u < 4; u++) {
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        double2 q2 = make_double2(0.0, 0.0);
-                        if (u < Gh && in) q2 = *reinterpret_cast<const double2 *>(Sq + u * 256 + k * 64 + lane * 2);
-                        a = __fma_rn(kd[2 * k], q2.x, a);
-                        a = __fma_rn(kd[2 * k + 1], q2.y, a);
-                    }
-                    acc[p][u] = a;
+                for (int k = 0; k < 4; k++) {
+                    double2 q2 = make_double2(0.0, 0.0);
+                    if (u < Gh && in) q2 = *reinterpret_cast<const double2 *>(Sq + u * 256 + k * 64 + lane * 2);
+                    a0 = __fma_rn(kd[0][2 * k], q2.x, a0);
+                    a0 = __fma_rn(kd[0][2 * k + 1], q2.y, a0);
+                    a1 = __fma_rn(kd[1][2 * k], q2.x, a1);
+                    a1 = __fma_rn(kd[1][2 * k + 1], q2.y, a1);
                 }
+                acc[0][u] = a0;
+                acc[1][u] = a1;
             }
             // folded butterfly: xor 16 keeps one position per half-warp, xor 8 two heads, xor 4 one head
             const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
