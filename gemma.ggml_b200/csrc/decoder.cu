@@ -879,43 +879,51 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
     if (seg_driven) {
         const int n_slots = (n_passes + F::PPS - 1) / F::PPS;
         if (ci == 0) {
-            const int pair = lane >> 1;
-            const bool act2 = pair < npairs;
+            // (unsigned arithmetic and non-unrolled inner loops on purpose: this is scalar control code that one warp
+            // runs at ~5 cycles per instruction between two rounds of adds; signed divisions by PPS and an unrolled
+            // two-trip loop tripled it)
+            constexpr uint32_t SH = F::PPS == 16 ? 4 : 3;
+            static_assert((1u << SH) == (uint32_t)F::PPS, "PPS must be 8 or 16");
+            const uint32_t pair = (uint32_t)lane >> 1, np_u = (uint32_t)npairs, nbuf_u = (uint32_t)nbuf;
+            const bool act2 = pair < np_u;
             uint32_t wmask = tmask;
-            int wb = 0, rb = 0, waited = 0, released = 0;
-            int p = act2 ? pair : 0, ls = 0, lb = 0; // this lane's pass of segment k, its slot and that slot's buffer
+            uint32_t wb = 0, rb = 0, waited = 0, released = 0;
+            uint32_t p = act2 ? pair : 0u, ls = 0, lb = 0; // this lane's pass of segment k, its slot and that slot's buffer
+            uint32_t done = 0;
 #pragma unroll 1
-            for (int k = 0; k < kA; k++, p += npairs) {
+            for (int k = 0; k < kA; k++, p += np_u) {
                 const bool last = k == kA - 1;
-                const int done = (k + 1) * npairs; // passes consumed once this round is over
-                const int need = (done - 1) / F::PPS;
+                done += np_u; // passes consumed once this round is over
+                const uint32_t need = (done - 1u) >> SH;
                 if (PROF) pt0 = clock64();
+#pragma unroll 1
                 while (waited <= need) {
-                    mbar_wait(tf0 + 8 * wb, (wmask >> wb) & 1u);
+                    mbar_wait(tf0 + 8u * wb, (wmask >> wb) & 1u);
                     if (PROF && prof && lane == 0 && waited < 8) P.prof[64 * cta + 48 + 2 * waited] = clock64() - p_begin;
                     wmask ^= 1u << wb;
-                    if (++wb == nbuf) wb = 0;
+                    wb = wb + 1u == nbuf_u ? 0u : wb + 1u;
                     waited++;
                 }
                 if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; }
-                const int ns = p / F::PPS;
+                const uint32_t ns = p >> SH;
+#pragma unroll 1
                 while (ls < ns) {
                     ls++;
-                    if (++lb == nbuf) lb = 0;
+                    lb = lb + 1u == nbuf_u ? 0u : lb + 1u;
                 }
                 ll_t rv = 0;
                 if (last && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
-                const uint32_t addr = terms0 + (uint32_t)lb * (uint32_t)(kTermFloats * 4) +
-                                      (uint32_t)((2 * (p & (F::PPS - 1)) + ab) * kTermRow * 4);
+                const uint32_t addr = terms0 + lb * (uint32_t)(kTermFloats * 4) + (2u * (p & (uint32_t)(F::PPS - 1)) + (uint32_t)ab) * (uint32_t)(kTermRow * 4);
                 if (PROF) pta = clock64();
                 racc = chain_add(addr, 0, last ? tail_blocks : kSeg, racc);
                 if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; if (prof && lane == 0 && k < 8) P.prof[64 * cta + 24 + k] = t1 - p_begin; }
                 if (last && act2) finish_row(lane, racc, rv);
                 __syncwarp();
-                while (released < waited && ((released + 1) * F::PPS <= done || last)) {
-                    if (lane == 0) mbar_arrive(te0 + 8 * rb);
+#pragma unroll 1
+                while (released < waited && (((released + 1u) << SH) <= done || last)) {
+                    if (lane == 0) mbar_arrive(te0 + 8u * rb);
                     if (PROF && prof && lane == 0 && released < 8) P.prof[64 * cta + 49 + 2 * released] = clock64() - p_begin;
-                    if (++rb == nbuf) rb = 0;
+                    rb = rb + 1u == nbuf_u ? 0u : rb + 1u;
                     released++;
                 }
                 if (PROF) p_chain += clock64() - pt0;
