@@ -890,10 +890,13 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
             uint32_t wb = 0, rb = 0, waited = 0, released = 0;
             uint32_t p = act2 ? pair : 0u, ls = 0, lb = 0; // this lane's pass of segment k, its slot and that slot's buffer
             uint32_t done = 0;
+            // several segments per round when a slot holds them (Gemma-2B DOWN: 7 pairs per segment, 16 passes per slot
+            // -> 2): the wait / release / loop code between two runs of adds is paid once per slot instead of per segment
+            const int spr = min(4, max(1, (int)(F::PPS / np_u)));
 #pragma unroll 1
-            for (int k = 0; k < kA; k++, p += np_u) {
-                const bool last = k == kA - 1;
-                done += np_u; // passes consumed once this round is over
+            for (int k = 0; k < kA; k += spr) {
+                const int nseg = min(spr, kA - k);
+                done += np_u * (uint32_t)nseg; // passes consumed once this round is over
                 const uint32_t need = (done - 1u) >> SH;
                 if (PROF) pt0 = clock64();
 #pragma unroll 1
@@ -905,22 +908,26 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
                     waited++;
                 }
                 if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; }
-                const uint32_t ns = p >> SH;
-#pragma unroll 1
-                while (ls < ns) {
-                    ls++;
-                    lb = lb + 1u == nbuf_u ? 0u : lb + 1u;
-                }
+                const bool fin = k + nseg == kA;
                 ll_t rv = 0;
-                if (last && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
-                const uint32_t addr = terms0 + lb * (uint32_t)(kTermFloats * 4) + (2u * (p & (uint32_t)(F::PPS - 1)) + (uint32_t)ab) * (uint32_t)(kTermRow * 4);
-                if (PROF) pta = clock64();
-                racc = chain_add(addr, 0, last ? tail_blocks : kSeg, racc);
-                if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; if (prof && lane == 0 && k < 8) P.prof[64 * cta + 24 + k] = t1 - p_begin; }
-                if (last && act2) finish_row(lane, racc, rv);
+                if (fin && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
+#pragma unroll 1
+                for (int q = 0; q < nseg; q++, p += np_u) {
+                    const uint32_t ns = p >> SH;
+#pragma unroll 1
+                    while (ls < ns) {
+                        ls++;
+                        lb = lb + 1u == nbuf_u ? 0u : lb + 1u;
+                    }
+                    const uint32_t addr = terms0 + lb * (uint32_t)(kTermFloats * 4) + (2u * (p & (uint32_t)(F::PPS - 1)) + (uint32_t)ab) * (uint32_t)(kTermRow * 4);
+                    if (PROF) pta = clock64();
+                    racc = chain_add(addr, 0, k + q == kA - 1 ? tail_blocks : kSeg, racc);
+                    if (PROF) { const long long t1 = clock64(); p_add += t1 - pta; if (prof && lane == 0 && k + q < 8) P.prof[64 * cta + 24 + k + q] = t1 - p_begin; }
+                }
+                if (fin && act2) finish_row(lane, racc, rv);
                 __syncwarp();
 #pragma unroll 1
-                while (released < waited && (((released + 1u) << SH) <= done || last)) {
+                while (released < waited && (((released + 1u) << SH) <= done || fin)) {
                     if (lane == 0) mbar_arrive(te0 + 8u * rb);
                     if (PROF && prof && lane == 0 && released < 8) P.prof[64 * cta + 49 + 2 * released] = clock64() - p_begin;
                     rb = rb + 1u == nbuf_u ? 0u : rb + 1u;
