@@ -1528,7 +1528,9 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
             if (PROF) { const long long t1 = clock64(); p_full += t1 - pt0; pt0 = t1; if (prof && tid == 0 && i < 4) P.prof[64 * cta + 32 + 3 * i] = t1 - p_begin; }
             // the chain warp is done with this term buffer's previous slot.  EVERY warp waits, also one without a
             // pass in this slot: its arrival below must not be counted for the buffer's previous use
+#ifndef GGB_KO_TEMPTY
             mbar_wait(te0 + 8 * tb, ((tmask >> tb) & 1u) ^ 1u);
+#endif
             if (PROF) { const long long t1 = clock64(); p_te += t1 - pt0; pt0 = t1; if (prof && tid == 0 && i < 4) P.prof[64 * cta + 33 + 3 * i] = t1 - p_begin; }
             if (j < cnt) {
                 const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;

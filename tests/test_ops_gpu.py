@@ -175,7 +175,7 @@ def test_mul_mat_dropin_strided_dst_and_errors(gpu):
     assert (dst[:, n:] == -3).all()
     # a type without a kernel is an error, as in the reference ("kernel is null", src/hpc.cpp:162-166)
     assert L.ggb_mul_mat(n, T, 1, w.shape[1], T, n * 4, n * 4 * T, a.shape[1], k, w.ctypes.data, dst.ctypes.data,
-                         12, a.ctypes.data) == -4
+                         10, a.ctypes.data) == -4  # Q2_K (Q4_K / Q6_K / F16 have kernels: tests/test_kquants_gpu.py)
     assert b"no kernel" in L.ggb_last_error()
 
 
