@@ -317,7 +317,7 @@ def run_ours(args):
         import tp_worker
         try:
             n = tp_worker.check(G, O, dist, rank, world, lowerings=(True,))
-            tp_parity = f"ok ({n} cases: tiny mqa + mha models x q4_0/q8_0, tokens and logits bit-identical to the oracle)"
+            tp_parity = f"ok ({n} cases: small mqa / mha / thin models x q4_0/q8_0, tokens and logits bit-identical to the oracle)"
         except AssertionError as e:
             tp_parity = f"FAILED: {e}"
         barrier()

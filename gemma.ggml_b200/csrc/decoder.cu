@@ -875,7 +875,8 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
     // span at most two slots, so two term buffers are live at a time), and a buffer is handed back as soon as the
     // rounds have consumed all of its passes.  The slot-driven loop below costs a round per (slot, segment) piece -
     // 11 instead of 8 for DOWN - and ~300 cycles of scalar bookkeeping per round.
-    const bool seg_driven = rowlane && !quad && n_passes == npairs * kA && (npairs + F::PPS - 2) / F::PPS + 1 <= nbuf;
+    // (n_passes > 0: a CTA without rows in the phase - tensor parallel with many ranks, thin matrices - has nothing to wait for)
+    const bool seg_driven = rowlane && !quad && n_passes > 0 && n_passes == npairs * kA && (npairs + F::PPS - 2) / F::PPS + 1 <= nbuf;
     if (seg_driven) {
         const int n_slots = (n_passes + F::PPS - 1) / F::PPS;
         if (ci == 0) {

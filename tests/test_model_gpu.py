@@ -29,6 +29,9 @@ SMALL = {
     "plain": dict(n_embd=2048, n_layer=1, n_head=8, n_head_kv=1, head_dim=256, n_ff=4096, n_vocab=512, n_ctx=48),
     # many rows per CTA in a multi-segment phase (rows > 32: accumulators handed from chain warp to chain warp)
     "wide": dict(n_embd=3072, n_layer=1, n_head=2, n_head_kv=2, head_dim=128, n_ff=1024, n_vocab=16384, n_ctx=48),
+    # fewer row pairs than CTAs in a multi-segment phase (DOWN: 128 pairs, K = 4096 = two segments): CTAs WITHOUT rows in
+    # the segment-driven row-lane chain - what tensor parallel at 8 ranks does to Gemma-2B (that case once hung)
+    "thin": dict(n_embd=256, n_layer=2, n_head=4, n_head_kv=1, head_dim=64, n_ff=4096, n_vocab=1024, n_ctx=48),
     # outside the fused kernel's envelope (n_embd % 256 != 0): exercises the per-operator lowering
     "odd": dict(n_embd=384, n_layer=2, n_head=4, n_head_kv=2, head_dim=96, n_ff=1056, n_vocab=777, n_ctx=48),
 }
@@ -45,7 +48,7 @@ def _models(gpu, dims, wtype, capture=True, sigma_embd=0.002, fused=True):
 
 
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "ops"])
-@pytest.mark.parametrize("name", ["mqa", "mha", "k96", "plain", "wide", "odd"])
+@pytest.mark.parametrize("name", ["mqa", "mha", "k96", "plain", "wide", "thin", "odd"])
 @pytest.mark.parametrize("wtype", [O.TYPE_Q4_0, O.TYPE_Q8_0])
 def test_generate_matches_oracle(gpu, name, wtype, fused):
     """Prompt (crossing a 32-position chunk boundary) + greedy tokens: ids, every named intermediate of the last

@@ -15,6 +15,8 @@ CONFIGS = {
     "mha": dict(n_embd=512, n_layer=2, n_head=4, n_head_kv=4, head_dim=128, n_ff=4608, n_vocab=1024, n_ctx=64),
     # MQA: attention block replicated, FFN / logits row-sharded
     "mqa": dict(n_embd=256, n_layer=3, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=2048, n_ctx=96),
+    # multi-segment DOWN with fewer row pairs per rank than CTAs: CTAs without rows in the row-lane chain
+    "thin": dict(n_embd=256, n_layer=2, n_head=4, n_head_kv=1, head_dim=64, n_ff=4096, n_vocab=1024, n_ctx=48),
 }
 
 
