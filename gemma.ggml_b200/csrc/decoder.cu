@@ -11,19 +11,22 @@
 //   * PASS STREAM.  At create time every weight matrix is re-laid out as a stream of PASSES: one pass = two rows x
 //     one 64-block K segment (2304 B Q4_0 / 4352 B Q8_0), payloads then scales = what one consumer warp dots in one
 //     go.  A CTA's share of a phase is ONE contiguous byte range, ordered K-SEGMENT-MAJOR (segment 0 of all its row
-//     pairs, then segment 1, ...), so a trivial producer loop (lane 0 of warp 16: cp.async.bulk, SASS UBLKCP, <= 16
+//     pairs, then segment 1, ...), so a trivial producer loop (lane 0 of warp 17: cp.async.bulk, SASS UBLKCP, <= 16
 //     passes per ring slot, 5 slots, mbarrier completion) runs AHEAD across phase boundaries.
 //   * CONSUMERS = 16 warps.  Warp w owns pass w of every slot: 4 x LDS.128 weights, the lane's two activation
 //     blocks in registers, dp4a, the scalar reference's per-block fp32 term.  The 128 terms of a pass go to a
 //     skewed (conflict-free) shared-memory table — NO in-warp reduction.
-//   * CHAIN WARP (warp 17).  Per ring slot it adds the terms to each row's accumulator strictly in block order
-//     (64 dependent FADDs per lane, 32 rows at once; accumulators of multi-segment rows live in shared memory
-//     between slots), and FINISHES rows as soon as their last segment is in: residual, flagged output, GeGLU +
-//     quantize_row_q8_0 per 32 outputs, arg-max candidates.  The epilogues overlap the pass loop; after the last
-//     slot only its own chain is left.  Consumers and chain warp hand the term buffers over through mbarriers.
+//   * CHAIN WARPS (warps 0, 18, 19).  Per ring slot one of them adds the terms to each row's accumulator strictly in
+//     block order (64 dependent FADDs per lane, 32 rows at once) and FINISHES rows as soon as their last segment is
+//     in: residual, flagged output, arg-max candidates; GATE_UP rows are staged and the consumer warps do GeGLU +
+//     quantize_row_q8_0 per 32 outputs after their passes.  Three loop forms (chain_phase): single-segment phases
+//     (a slot = one round), row-lane segment-driven (O / DOWN: lane = row, register accumulator, one round per K
+//     segment or several), and the general loop (quad layouts, accumulators in shared memory, in-order commit).
+//     Consumers and chain warps hand the term buffers over through mbarriers.
 //   * NO GRID BARRIERS.  Every value that crosses CTAs travels as an 8-byte word {payload, tag} written with one
 //     relaxed store (the NCCL "LL" idea): tag = the token's sequence number, buffers are per layer, a consumer
-//     re-reads a word until its tag matches.  Data and flag arrive together: no fence, no separate wait.
+//     re-reads a word until its tag matches.  Data and flag arrive together: no fence, no separate wait.  A thread
+//     requests all its words at once and, if some are missing, spins on one and re-reads only the missing ones (ll_gather).
 //   * ATTENTION = two phases without a combine: SCORE (items = kv head x 32-position chunk: kq in double, the new
 //     position's K/V roped, rounded and stored) and PV (items = head x 16/32-dim slice: the WHOLE soft_max_ext row of
 //     the head - global max, fp16 exp, exact double sum, fp16 P - then P.V in double).  Double accumulators make
