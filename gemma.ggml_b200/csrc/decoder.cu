@@ -1121,7 +1121,12 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
 // the reference's vec_dot_f16 does (ref: src/kernals.cl:158-164) - the order of a double sum is invisible after that
 // rounding.  A warp scores its two positions against the item's (<= 4) heads and reduces the 8 lane partials with one
 // folded butterfly.  Scores leave as flagged words.
-template <int TYPE, bool PROF>
+// MHA_OPT (= the QUAD instantiation, the one Gemma-7B runs): items in head-major order, a contiguous range per CTA, so
+// that a CTA with several items (16 kv heads x n_kv / 32 chunks = 7 per CTA at n_kv 2048) walks consecutive chunks of one
+// head and stages that head's q once instead of once per item; and a one-head form of the dots and the fold.  Kept out
+// of the other instantiation because its extra live state costs the Gemma-2B kernel 1 % (registers: 96, spills move
+// into the pass loop) for nothing - an MQA model has one item per CTA.
+template <int TYPE, bool PROF, bool MHA_OPT>
 __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int cta, int G, int n_pos, uint32_t tag, bool prof) {
     Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
     const Phase &ph = S.ph[phi];
@@ -1141,9 +1146,20 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
     auto decode = [&](int it, int &hh, int &gl, int &c) {
         hh = hsplit == 2 ? (it & 1) : 0;
         const int gc = hsplit == 2 ? (it >> 1) : it;
-        gl = gc & (ng - 1);
-        c = gc >> P.ng_shift;
+        if (MHA_OPT) { // head-major
+            gl = gc / nchunk;
+            c = gc - gl * nchunk;
+        } else {
+            gl = gc & (ng - 1);
+            c = gc >> P.ng_shift;
+        }
     };
+    // the CTA's items: first, first + G, ... or (MHA_OPT) the contiguous range [first * per, first * per + per)
+    const int per = (n_items + G - 1) / G;
+    const int it_begin = MHA_OPT ? min(first * per, n_items) : first;
+    const int it_end = MHA_OPT ? min(it_begin + per, n_items) : n_items;
+    const int it_step = MHA_OPT ? 1 : G;
+    int q_h0 = -1; // (MHA_OPT) the head whose q is staged in Sq
     // K rows of an item's chunk (the new position's row is computed, not loaded).  One KV head: the rows of a chunk are
     // contiguous in the cache, so warps 0 and 1 issue one copy each (rows before | after the new one); otherwise the
     // warp that scores rows w, w + 16 copies them.  Every warp arrives once on the buffer's barrier.
@@ -1174,9 +1190,9 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
     };
 
     int buf = 0;
-    if (first < n_items) issue_k(first, 0);
+    if (it_begin < it_end) issue_k(it_begin, 0);
 #pragma unroll 1
-    for (int it = first; it < n_items; it += G) {
+    for (int it = it_begin; it < it_end; it += it_step) {
         int hh, gl, c;
         decode(it, hh, gl, c);
         const int g = P.g0 + gl; // global KV head
@@ -1190,7 +1206,7 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
         const float *cosr = P.rope_cos + (size_t)pos * halfd, *sinr = P.rope_sin + (size_t)pos * halfd;
         const ll_t *q_all = ph.in_ll, *k_all = q_all + (size_t)P.H * d, *v_all = k_all + (size_t)P.Hkv * d;
         // q: rope (NEOX pairs i, i + d/2), scale, round to fp16 (ggml mul_mat INIT converts src1 to fp16), widen
-        for (int i = tid; i < Gh * halfd; i += kCT) {
+        for (int i = tid; i < ((!MHA_OPT || h0 != q_h0) ? Gh * halfd : 0); i += kCT) {
             const int jh = i >> P.hd_shift, e = i & (halfd - 1);
             const ll_t *qh = q_all + (size_t)(h0 + jh) * d;
             const float cs = cosr[e], sn = sinr[e];
@@ -1233,7 +1249,8 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
         kvp ^= 1u << buf;
         consumer_bar();
         PROF_STAMP(2);
-        if (it + G < n_items) issue_k(it + G, buf ^ 1); // the other buffer was last read before the barrier above
+        if (MHA_OPT) q_h0 = h0;
+        if (it + it_step < it_end) issue_k(it + it_step, buf ^ 1); // the other buffer was last read before the barrier above
         {
             const bool in = 8 * lane < d;
             const int j0 = warp, j1 = warp + kCW;
@@ -1254,6 +1271,27 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
                     kd[p][2 * e + 1] = (double)f.y;
                 }
             }
+            if (MHA_OPT && Gh == 1) {
+                // one query head per item (MHA): 16 DFMA instead of 64, and a two-value fold (one exchange, four plain
+                // steps) instead of the eight-value one
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    double2 q2 = make_double2(0.0, 0.0);
+                    if (in) q2 = *reinterpret_cast<const double2 *>(Sq + k * 64 + lane * 2);
+                    a0 = __fma_rn(kd[0][2 * k], q2.x, a0);
+                    a0 = __fma_rn(kd[0][2 * k + 1], q2.y, a0);
+                    a1 = __fma_rn(kd[1][2 * k], q2.x, a1);
+                    a1 = __fma_rn(kd[1][2 * k + 1], q2.y, a1);
+                }
+                const bool hb4 = lane & 16;
+                double r = __dadd_rn(hb4 ? a1 : a0, __shfl_xor_sync(0xffffffffu, hb4 ? a0 : a1, 16));
+#pragma unroll
+                for (int off = 8; off >= 1; off >>= 1) r = __dadd_rn(r, __shfl_xor_sync(0xffffffffu, r, off));
+                const int js1 = hb4 ? j1 : j0;
+                if ((lane & 15) == 0 && js1 < np)
+                    ll_put_f(P, false, ph.s_ll + (size_t)h0 * P.n_ctx + p0 + js1, __double2float_rn(r), tag);
+            } else {
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 double a0 = 0.0, a1 = 0.0;
@@ -1292,6 +1330,7 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
             const int js = b4 ? j1 : j0, us = (b3 ? 2 : 0) + (b2 ? 1 : 0);
             if ((lane & 3) == 0 && js < np && us < Gh)
                 ll_put_f(P, false, ph.s_ll + (size_t)(h0 + us) * P.n_ctx + p0 + js, __double2float_rn(k1), tag);
+            }
         }
         PROF_STAMP(3);
         consumer_bar(); // Sq and (after one more item) this K buffer are rewritten
@@ -1657,7 +1696,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         if (is_matvec(kind)) {
             matvec_consumer<TYPE, QUAD, PROF>(P, pi & 1, cta, G, tag, PROF && pi == P.prof_phase);
         } else if (kind == PH_SCORE) {
-            score_phase<TYPE, PROF>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
+            score_phase<TYPE, PROF, QUAD>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else if (kind == PH_PV) {
             pv_phase<TYPE, PROF>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
