@@ -1346,7 +1346,7 @@ __device__ __forceinline__ void score_phase(const DecoderParams &P, int phi, int
 // rounds P to fp16 (ggml mul_mat INIT of the kqv node) and accumulates out[i] = sum_p V16[p][i] * P16[p] in double.
 // Thread (o, pl): dims 8 o .. 8 o + 7 of the slice, positions pl, pl + PL, ...; the V rows of older positions do not
 // depend on this token and are requested before the scores arrive.
-template <int TYPE, bool PROF>
+template <int TYPE, bool PROF, bool MHA_OPT>
 __device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int cta, int G, int n_pos, uint32_t tag, bool prof) {
     Smem<TYPE> &S = *reinterpret_cast<Smem<TYPE> *>(ggb_dec_smem);
     const Phase &ph = S.ph[phi];
@@ -1445,6 +1445,42 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int ct
                 acc[2 * e + 1] = __fma_rn((double)f.y, pd, acc[2 * e + 1]);
             }
         };
+        if (MHA_OPT) {
+            // (the Gemma-7B instantiation) rows beyond the staged and the early-requested ones - 16 rows per thread at
+            // n_kv 2048 with 32-dim slices, 64 at 8192: two register batches in flight alternately, the next batch is
+            // requested before the current one is used (otherwise every batch exposes an L2 round trip)
+            auto load_rows = [&](uint4 (&v)[NPRE], int q0) {
+#pragma unroll
+                for (int k = 0; k < NPRE; k++) {
+                    const int p = q0 + PL * k;
+                    v[k] = p < pos ? __ldcg(reinterpret_cast<const uint4 *>(vbase + (size_t)p * kv_stride)) : make_uint4(0, 0, 0, 0);
+                }
+            };
+            auto fma_rows = [&](const uint4 (&v)[NPRE], int q0) {
+#pragma unroll
+                for (int k = 0; k < NPRE; k++)
+                    if (q0 + PL * k < pos) fma8(v[k], q0 + PL * k);
+            };
+            uint4 vb[NPRE];
+            int q0 = pr0 + PL * NPRE;
+            load_rows(vb, q0);
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            for (int k = 0; k < NST; k++) {
+                const int p = pl + PL * k;
+                if (p < pos) fma8(lds_u4(stage + (uint32_t)k * (kCT * 16)), p);
+            }
+            fma_rows(vr, pr0);
+#pragma unroll 1
+            while (q0 < pos) {
+                const int q1 = q0 + PL * NPRE;
+                load_rows(vr, q1);
+                fma_rows(vb, q0);
+                if (q1 >= pos) break;
+                q0 = q1 + PL * NPRE;
+                load_rows(vb, q0);
+                fma_rows(vr, q1);
+            }
+        } else {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         for (int k = 0; k < NST; k++) {
             const int p = pl + PL * k;
@@ -1463,6 +1499,7 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int ct
 #pragma unroll
             for (int k = 0; k < NPRE; k++)
                 if (p0 + PL * k < pos) fma8(vr[k], p0 + PL * k);
+        }
         }
         if (pl == (pos & (PL - 1))) { // the new position's V row: from the flagged v words, rounded to fp16 like the cache
             const ll_t *vp = ph.in_ll + (size_t)P.H * d + (size_t)P.Hkv * d + (size_t)g * d + (size_t)slice * W + 8 * o;
@@ -1698,7 +1735,7 @@ __global__ void __launch_bounds__(kThreads, 1) decoder_kernel(const __grid_const
         } else if (kind == PH_SCORE) {
             score_phase<TYPE, PROF, QUAD>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else if (kind == PH_PV) {
-            pv_phase<TYPE, PROF>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
+            pv_phase<TYPE, PROF, QUAD>(P, pi & 1, cta, G, S.sched[4], tag, PROF && pi == P.prof_phase);
         } else { // PH_SAMPLE: CTA 0 (of every rank) picks the first maximum of all ranks' per-CTA candidates
             if (cta == 0) { // all consumer warps: one candidate per thread, i.e. ONE round trip instead of one per 32
                 const int nc = P.R * G * kNCH;
