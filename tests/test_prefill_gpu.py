@@ -151,3 +151,50 @@ def test_prefill_agrees_with_token_by_token_decode_path(gpu):
     if top[1] - top[0] > 2 * tol:
         assert nxt == int(toks[0])
     m.close()
+
+
+# Full size (BASELINE.json config 3: Gemma-2B Q8_0, 512-token prompt).  The reference for the comparison is our own decode
+# path run token by token, which is bit-identical to the oracle's scalar ggml order (tests/test_model_gpu.py) - the oracle
+# itself would need ~15 minutes for 512 positions.  The two paths round differently BY DESIGN (bf16 activations and
+# weights vs Q8_0 re-quantised activations), and 18 layers of random-init weights amplify that: the full-size tolerance
+# is therefore looser than PREFILL_TOL and is stated here from the measurement (profiles/r2_config3_prefill_parity.json:
+# what was measured, not just the bound).
+FULL_PREFILL_TOL = 1.2e-1  # measured: logits 5.3 % of their range, K / V rows 0.4 % (layer 0) .. 7.4 % (layer 17); same greedy token
+
+
+def test_config3_full_size_prefill_against_the_bit_exact_path(gpu):
+    import json
+    import os
+    dims = dict(gpu.GEMMA_2B, n_ctx=576)
+    T = 512
+    cfg = gpu.make_config(wtype=O.TYPE_Q8_0, sigma_embd=0.004, **dims)
+    prompt = ((1 + 7919 * np.arange(T)) % dims["n_vocab"]).astype(np.int32)
+    m = gpu.GemmaModel(cfg)
+    m.init_synthetic_weights(); m.init_kv_cache(); m.build_compute_graph(capture_acts=False, fused=True)
+    toks, _, _ = m.generate(prompt, 1)          # token by token through the persistent decode kernel
+    dlog = m.logits().copy()
+    dkv = [tuple(a[:T].view(np.float16).astype(np.float32) for a in m.kv(il)) for il in (0, 8, 17)]
+    m.init_kv_cache()
+    nxt = m.prefill(prompt, 0)
+    glog = m.prefill_logits(T - 1)
+    rng_ = float(np.abs(dlog).max())
+    dev = float(np.abs(glog - dlog).max())
+    top = np.sort(dlog)[-2:]
+    report = {"workload": "gemma-2b q8_0, 512-token prompt, sigma_embd 0.004", "logit_absmax": rng_, "logit_max_abs_dev": dev,
+              "logit_dev_rel": dev / rng_, "top2_margin_exact_path": float(top[1] - top[0]), "token_exact_path": int(toks[0]),
+              "token_prefill": int(nxt), "rank_of_exact_token_in_prefill": int((glog > glog[int(toks[0])]).sum()), "kv": {}}
+    for il, (dk, dv) in zip((0, 8, 17), dkv):
+        gk, gv = (a[:T].view(np.float16).astype(np.float32) for a in m.kv(il))
+        report["kv"][str(il)] = {"k_dev_rel": float(np.abs(gk - dk).max() / max(1.0, np.abs(dk).max())),
+                                 "v_dev_rel": float(np.abs(gv - dv).max() / max(1.0, np.abs(dv).max()))}
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    json.dump(report, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                                        "config3_prefill_parity.json"), "w"), indent=1)
+    print(json.dumps(report))
+    assert dev < FULL_PREFILL_TOL * max(1.0, rng_), report
+    for il in ("0", "8", "17"):
+        assert report["kv"][il]["k_dev_rel"] < FULL_PREFILL_TOL and report["kv"][il]["v_dev_rel"] < FULL_PREFILL_TOL, report
+    if top[1] - top[0] > 2 * dev:               # the greedy token is pinned when the margin exceeds the measured deviation
+        assert nxt == int(toks[0]), report
+    assert report["rank_of_exact_token_in_prefill"] < 8, report  # and is always among the prefill path's top candidates
+    m.close()
