@@ -15,7 +15,6 @@ LIB_PATH = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
 
 TYPE_F32, TYPE_F16, TYPE_Q4_0, TYPE_Q8_0 = 0, 1, 2, 8
 REF = 0
-DEV = REF  # (historical alias: the device order IS the reference order now)
 QK = 32
 BLOCK_BYTES = {TYPE_Q4_0: 18, TYPE_Q8_0: 34}
 

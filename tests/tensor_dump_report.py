@@ -1,6 +1,6 @@
 """Per-layer parity report at FULL model size through the tensor_dump harness (script, not a test: it uses the CPU
 oracle, so it lives under tests/).  Gemma-2B, a short prompt decoded token by token on the GPU (persistent kernel) and by
-the oracle in DEV and REF order; every named intermediate of the LAST step is dumped as <name>-<layer>_source /
+the oracle (scalar ggml order); every named intermediate of the LAST step is dumped as <name>-<layer>_source /
 _target and compared.  Writes gpurun_out/tensor_dump_report_<model>_<wtype>.json; copy it to profiles/.
 
 usage: python tests/tensor_dump_report.py [2b|7b] [q4_0|q8_0] [n_prompt] [n_decode]"""
@@ -43,7 +43,7 @@ def main():
     om = O.Model(wtype=wtype, **dims)
     rep = (C.c_double * 5)()
     rows, summary = [], {}
-    for order, oname in ((O.REF, "DEV"), (O.REF, "REF")):
+    for order, oname in ((O.REF, "REF"),):  # one order since round 2: the scalar ggml order
         otoks, _, _ = om.generate(prompt, n_decode, order)
         names = [(f"{cap}-{il}", om.capture(cap, il)) for il in range(dims["n_layer"]) for cap in sizes]
         names.append(("result_output", om.capture("result_output")))
