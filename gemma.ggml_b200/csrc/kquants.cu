@@ -260,7 +260,7 @@ int ggb_op_mul_mat_blocks(int type, const void *w, int64_t rows, int64_t nb01, i
                           int64_t row_size, int64_t T, float *dst, int64_t dst_stride) {
     GGB_REQUIRE_INIT();
     GGB_CHECK_ARG(w && act && dst, "null pointer");
-    GGB_CHECK_ARG(rows > 0 && T > 0 && T <= 65535 && K > 0, "mul_mat_blocks: bad extents");
+    GGB_CHECK_ARG(rows > 0 && T > 0 && K > 0, "mul_mat_blocks: bad extents");
     const bool kq = type == GGB_TYPE_Q4_K || type == GGB_TYPE_Q6_K;
     if (!kq && type != GGB_TYPE_F16) {
         ggb_set_error("mul_mat_blocks: no kernel for type %d", type);
@@ -272,16 +272,20 @@ int ggb_op_mul_mat_blocks(int type, const void *w, int64_t rows, int64_t nb01, i
     const int64_t act_row = (int64_t)ggb_type_row_bytes(kq ? GGB_TYPE_Q8_K : GGB_TYPE_F16, K);
     GGB_CHECK_ARG(row_size >= act_row && row_size % (kq ? 4 : 2) == 0, "mul_mat_blocks: activation row pitch %lld",
                   (long long)row_size);
-    const dim3 grid((unsigned)((rows + kWarps - 1) / kWarps), (unsigned)T);
     const uint8_t *wb = (const uint8_t *)w, *ab = (const uint8_t *)act;
     cudaStream_t st = ggb_cuda_stream();
-    if (type == GGB_TYPE_Q4_K)
-        raw_matvec_kernel<GGB_TYPE_Q4_K><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, ab, row_size, dst, dst_stride);
-    else if (type == GGB_TYPE_Q6_K)
-        raw_matvec_kernel<GGB_TYPE_Q6_K><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, ab, row_size, dst, dst_stride);
-    else
-        raw_matvec_kernel<GGB_TYPE_F16><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, ab, row_size, dst, dst_stride);
-    GGB_LAUNCH_CHECK();
+    for (int64_t t0 = 0; t0 < T; t0 += 65535) { // grid.y carries the activation row
+        const dim3 grid((unsigned)((rows + kWarps - 1) / kWarps), (unsigned)(T - t0 < 65535 ? T - t0 : 65535));
+        const uint8_t *a0 = ab + t0 * row_size;
+        float *d0 = dst + t0 * dst_stride;
+        if (type == GGB_TYPE_Q4_K)
+            raw_matvec_kernel<GGB_TYPE_Q4_K><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, a0, row_size, d0, dst_stride);
+        else if (type == GGB_TYPE_Q6_K)
+            raw_matvec_kernel<GGB_TYPE_Q6_K><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, a0, row_size, d0, dst_stride);
+        else
+            raw_matvec_kernel<GGB_TYPE_F16><<<grid, kWarps * 32, 0, st>>>(wb, rows, nb01, K, a0, row_size, d0, dst_stride);
+        GGB_LAUNCH_CHECK();
+    }
     return GGB_OK;
 }
 
