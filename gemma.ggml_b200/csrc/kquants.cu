@@ -68,6 +68,13 @@ __device__ __forceinline__ float finish_lanes(float sumf, float sums) {
     return sumf;
 }
 
+// the same with the eight chains in lanes 0..7
+__device__ __forceinline__ float finish_lanes8(float sumf, float sums) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) sumf = __fadd_rn(sumf, __shfl_sync(0xffffffffu, sums, l));
+    return sumf;
+}
+
 __device__ __forceinline__ float dot_q4_K(const uint8_t *x, const uint8_t *y, int nb, int lane) {
     float sums = 0.0f, sumf = 0.0f;
     const int c = lane >> 3, hi = lane & 4, j = lane >> 2;
@@ -228,6 +235,131 @@ quantize_q8_K_kernel(const float *__restrict__ x, int64_t n_blocks, uint8_t *__r
     if (lane == 0) *reinterpret_cast<float *>(o) = __fdiv_rn(1.0f, iscale);
 }
 
+
+// ---------------------------------------------------------------- Q4_K, packed form (resident weights)
+// The AoS kernel above spends 14 shuffles and ~60 instructions on a 144-byte super-block; it reaches 0.8-0.9 TB/s.  For
+// weights that stay on the device (ggb_mul_mat's cache) the super-block is re-laid out ONCE so that the four nibbles a
+// lane-sum index l meets inside a 32-element sub-block - elements l, 8 + l, 16 + l, 24 + l - are adjacent:
+//   block (144 B, same size) = d | dmin | scales[12] | X[8 sub-blocks][4 words], word p of sub-block j:
+//   bits 4g .. 4g+3 = nibble of element 32 j + 8 g + 2 p, bits 16 + 4g .. = nibble of element 32 j + 8 g + 2 p + 1.
+// The activation row is transposed the same way when a CTA stages it in shared memory (once per CTA, for all of its
+// rows): qT[j][l] = bytes q8[32 j + 8 g + l], g = 0..3.  Then lane (s, j) - super-block s of four, sub-block j - turns
+// its 16 bytes into eight dp4a (one per l), multiplies by its 6-bit scale, and a three-step folded butterfly inside
+// the 8-lane group leaves aux32[l = j] of super-block s in lane (s, j).  The fp32 part is the scalar code's, in its
+// order: the products d * aux32[l] of the four super-blocks are made in parallel, then lanes 0..7 add them to
+// sums[l] one by one; lane 0 does the same for sumf -= dmin * sumi.  4 shuffles per super-block instead of 14.
+constexpr int kActSB = 304; // staged activation super-block: qT 256 B | pair sums int[8] | d float | pad
+
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+
+__global__ void __launch_bounds__(256) q4k_repack_kernel(const uint8_t *__restrict__ raw, int64_t rows, int64_t nb01, int nb,
+                                                        uint8_t *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; // (row, super-block, sub-block j)
+    if (idx >= rows * nb * 8) return;
+    const int j = (int)(idx & 7);
+    const int64_t rb = idx >> 3, row = rb / nb;
+    const int sb = (int)(rb - row * nb);
+    const uint8_t *x = raw + row * nb01 + (int64_t)sb * kQ4K;
+    uint8_t *o = out + (row * nb + sb) * kQ4K;
+    if (j < 4) *reinterpret_cast<uint32_t *>(o + 4 * j) = *reinterpret_cast<const uint32_t *>(x + 4 * j); // d, dmin, scales
+    const uint8_t *q = x + 16 + 32 * (j >> 1);
+    const int sh = (j & 1) * 4;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int g = 0; g < 4; g++)
+        for (int l = 0; l < 8; l++) {
+            const uint32_t nib = (q[8 * g + l] >> sh) & 0xFu;
+            w[l >> 1] |= nib << (16 * (l & 1) + 4 * g);
+        }
+    *reinterpret_cast<uint4 *>(o + 16 + 16 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// grid (x: row groups, strided; y: activation row); 8 warps; dynamic shared memory nb * kActSB
+__global__ void __launch_bounds__(256)
+q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uint8_t *__restrict__ act, int64_t row_size,
+                  float *__restrict__ dst, int64_t dst_stride) {
+    extern __shared__ __align__(16) uint8_t s_act[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *y = act + (int64_t)blockIdx.y * row_size;
+    // ---- stage the activation row, transposed
+    for (int i = tid; i < nb * 64; i += 256) { // word (sb, j, l)
+        const int sb = i >> 6, j = (i >> 3) & 7, l = i & 7;
+        const uint8_t *q8 = y + (int64_t)sb * kQ8K + 4 + 32 * j + l;
+        const uint32_t v = (uint32_t)q8[0] | ((uint32_t)q8[8] << 8) | ((uint32_t)q8[16] << 16) | ((uint32_t)q8[24] << 24);
+        *reinterpret_cast<uint32_t *>(s_act + sb * kActSB + (l >> 2) * 128 + j * 16 + (l & 3) * 4) = v;
+    }
+    for (int i = tid; i < nb * 9; i += 256) {
+        const int sb = i / 9, k = i - sb * 9;
+        const uint8_t *yb = y + (int64_t)sb * kQ8K;
+        if (k < 8) {
+            const int16_t *bs = reinterpret_cast<const int16_t *>(yb + 260);
+            *reinterpret_cast<int *>(s_act + sb * kActSB + 256 + 4 * k) = (int)bs[2 * k] + (int)bs[2 * k + 1];
+        } else {
+            *reinterpret_cast<uint32_t *>(s_act + sb * kActSB + 288) = ld_u32(yb);
+        }
+    }
+    __syncthreads();
+    const int s = lane >> 3, j = lane & 7;
+    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += (int64_t)gridDim.x * kWarps) {
+        const uint8_t *xrow = w + row * (int64_t)nb * kQ4K;
+        float sums = 0.0f, sumf = 0.0f;
+#pragma unroll 2
+        for (int sb0 = 0; sb0 < nb; sb0 += 4) {
+            const int sb = sb0 + s;
+            const bool valid = sb < nb;
+            const uint8_t *blk = xrow + (int64_t)(valid ? sb : 0) * kQ4K;
+            const uint4 X = __ldg(reinterpret_cast<const uint4 *>(blk + 16 + 16 * j));
+            const uint32_t dd = ldg_u32(blk);
+            uint32_t u0 = ldg_u32(blk + 4), u1 = ldg_u32(blk + 8), u2 = ldg_u32(blk + 12);
+            // 6-bit scales / mins (src/kernals.cl:75-80)
+            const uint32_t u3 = ((u2 >> 4) & 0x0f0f0f0fu) | (((u1 >> 6) & 0x03030303u) << 4);
+            const uint32_t uaux = u1 & 0x3f3f3f3fu;
+            u1 = (u2 & 0x0f0f0f0fu) | (((u0 >> 6) & 0x03030303u) << 4);
+            u2 = uaux;
+            u0 &= 0x3f3f3f3fu;
+            const int scale = (int)(((j < 4 ? u0 : u1) >> (8 * (j & 3))) & 0xff);
+            const int mn = (int)(((j < 4 ? u2 : u3) >> (8 * (j & 3))) & 0xff);
+            const uint8_t *ya = s_act + (valid ? sb : 0) * kActSB;
+            const uint4 qa = *reinterpret_cast<const uint4 *>(ya + 16 * j);       // qT[j][0..3]
+            const uint4 qb = *reinterpret_cast<const uint4 *>(ya + 128 + 16 * j); // qT[j][4..7]
+            const uint32_t xs[4] = {X.x, X.y, X.z, X.w};
+            const uint32_t qs[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            int v[8];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const uint32_t t1 = xs[p] & 0x0f0f0f0fu, t2 = (xs[p] >> 4) & 0x0f0f0f0fu;
+                const uint32_t a_even = __byte_perm(t1, t2, 0x5140), a_odd = __byte_perm(t1, t2, 0x7362);
+                v[2 * p] = scale * __dp4a((int)a_even, (int)qs[2 * p], 0);
+                v[2 * p + 1] = scale * __dp4a((int)a_odd, (int)qs[2 * p + 1], 0);
+            }
+            // fold inside the 8-lane group: lane (s, j) ends with aux32[l = j]
+            int w4[4], w2[2];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w4[k] = (b2 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b2 ? v[k] : v[4 + k], 4);
+#pragma unroll
+            for (int k = 0; k < 2; k++) w2[k] = (b1 ? w4[2 + k] : w4[k]) + __shfl_xor_sync(0xffffffffu, b1 ? w4[k] : w4[2 + k], 2);
+            const int aux = (b0 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1);
+            int sumi = mn * *reinterpret_cast<const int *>(ya + 256 + 4 * j);
+            sumi += __shfl_xor_sync(0xffffffffu, sumi, 1);
+            sumi += __shfl_xor_sync(0xffffffffu, sumi, 2);
+            sumi += __shfl_xor_sync(0xffffffffu, sumi, 4);
+            const float yd = *reinterpret_cast<const float *>(ya + 288);
+            const float d = __fmul_rn(half_bits_to_float((uint16_t)(dd & 0xffff)), yd);
+            const float dmin = __fmul_rn(half_bits_to_float((uint16_t)(dd >> 16)), yd);
+            const float t = valid ? __fmul_rn(d, (float)aux) : 0.0f;       // x + 0.0f == x: a missing super-block adds nothing
+            const float tm = valid ? __fmul_rn(dmin, (float)sumi) : 0.0f;
+            // the scalar order: super-blocks one after the other (lanes 0..7 own sums[l], lane 0 owns sumf)
+            const float t1 = __shfl_sync(0xffffffffu, t, (lane & 7) + 8), t2 = __shfl_sync(0xffffffffu, t, (lane & 7) + 16),
+                        t3 = __shfl_sync(0xffffffffu, t, (lane & 7) + 24);
+            const float m1 = __shfl_sync(0xffffffffu, tm, 8), m2 = __shfl_sync(0xffffffffu, tm, 16), m3 = __shfl_sync(0xffffffffu, tm, 24);
+            sums = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sums, t), t1), t2), t3); // (meaningful in lanes 0..7: there t is super-block sb0's)
+            sumf = __fsub_rn(__fsub_rn(__fsub_rn(__fsub_rn(sumf, tm), m1), m2), m3); // (meaningful in lane 0)
+        }
+        const float r = finish_lanes8(sumf, sums);
+        if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = r;
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -253,6 +385,39 @@ int ggb_op_quantize_q8_K(const float *x, int64_t cols, int64_t rows, void *out) 
     quantize_q8_K_kernel<<<(unsigned)((n_blocks + kWarps - 1) / kWarps), kWarps * 32, 0, ggb_cuda_stream()>>>(
         x, n_blocks, (uint8_t *)out);
     GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_q4k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, void *packed) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(raw && packed && rows > 0 && K > 0 && K % kQK == 0 && nb01 >= K / kQK * kQ4K && nb01 % 4 == 0,
+                  "q4k_repack: bad arguments");
+    const int nb = (int)(K / kQK);
+    const int64_t n = rows * nb * 8;
+    q4k_repack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>((const uint8_t *)raw, rows, nb01, nb,
+                                                                                 (uint8_t *)packed);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
+                              float *dst, int64_t dst_stride) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(packed && act && dst && rows > 0 && T > 0 && K > 0 && K % kQK == 0, "mul_mat_q4k_packed: bad arguments");
+    const int nb = (int)(K / kQK);
+    GGB_CHECK_ARG(row_size >= (int64_t)nb * kQ8K && row_size % 4 == 0, "mul_mat_q4k_packed: activation row pitch %lld", (long long)row_size);
+    const size_t smem = (size_t)nb * kActSB;
+    GGB_CHECK_ARG(smem <= 200 * 1024, "mul_mat_q4k_packed: K %lld too long for the staged activation row", (long long)K);
+    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(q4k_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t groups = (rows + kWarps - 1) / kWarps;
+    const unsigned gx = (unsigned)(groups < 148 * 8 ? groups : 148 * 8);
+    for (int64_t t0 = 0; t0 < T; t0 += 65535) {
+        const dim3 grid(gx, (unsigned)(T - t0 < 65535 ? T - t0 : 65535));
+        q4k_packed_kernel<<<grid, 256, smem, ggb_cuda_stream()>>>((const uint8_t *)packed, rows, nb,
+                                                                  (const uint8_t *)act + t0 * row_size, row_size,
+                                                                  dst + t0 * dst_stride, dst_stride);
+        GGB_LAUNCH_CHECK();
+    }
     return GGB_OK;
 }
 

@@ -23,7 +23,7 @@ struct CacheKey {
 };
 
 std::map<CacheKey, ggb_weight *> g_cache;
-std::map<CacheKey, void *> g_raw_cache; // K-quant / F16 src0 kept in ggml's own layout
+std::map<CacheKey, void *> g_raw_cache; // Q6_K / F16 src0 in ggml's own layout, Q4_K in the packed layout of kquants.cu
 std::mutex g_mu;
 void *g_act_raw = nullptr, *g_act_q8 = nullptr;
 float *g_dst = nullptr;
@@ -75,6 +75,23 @@ int mul_mat_blocks(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64
             ggb_set_error("mul_mat: src0 upload -> %s", cudaGetErrorString(e));
             return GGB_ERR_CUDA;
         }
+        if (type == GGB_TYPE_Q4_K) { // resident Q4_K: the packed layout of kquants.cu (same size, repacked once)
+            void *packed = nullptr;
+            const size_t bytes = (size_t)ne01 * (size_t)(K / 256) * 144;
+            if (cudaMalloc(&packed, bytes) != cudaSuccess) {
+                cudaFree(w);
+                ggb_set_error("mul_mat: out of device memory for the packed Q4_K copy");
+                return GGB_ERR_CUDA;
+            }
+            int rc2 = ggb_op_q4k_repack(w, ne01, nb01, K, packed);
+            if (rc2 == GGB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc2 = GGB_ERR_CUDA;
+            cudaFree(w);
+            if (rc2 != GGB_OK) {
+                cudaFree(packed);
+                return rc2;
+            }
+            w = packed;
+        }
         g_raw_cache[key] = w;
     } else {
         w = it->second;
@@ -84,7 +101,9 @@ int mul_mat_blocks(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64
     if ((rc = ensure(&g_act_raw, &g_act_raw_cap, (size_t)col_num * row_size))) return rc;
     if ((rc = ensure((void **)&g_dst, &g_dst_cap, (size_t)col_num * ne01 * 4))) return rc;
     GGB_CUDA(cudaMemcpyAsync(g_act_raw, wdata, (size_t)col_num * row_size, cudaMemcpyHostToDevice, st));
-    if ((rc = ggb_op_mul_mat_blocks(type, w, ne01, nb01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01))) return rc;
+    if (type == GGB_TYPE_Q4_K) rc = ggb_op_mul_mat_q4k_packed(w, ne01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01);
+    else rc = ggb_op_mul_mat_blocks(type, w, ne01, nb01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01);
+    if (rc) return rc;
     return copy_back(dst_data, col_num, ne01, ne12, ne1, nb1, nb2, st);
 }
 

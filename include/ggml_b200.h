@@ -143,6 +143,12 @@ size_t ggb_type_row_bytes(int type, int64_t cols);
 int ggb_op_quantize_q8_K(const float *x, int64_t cols, int64_t rows, void *out);
 int ggb_op_mul_mat_blocks(int type, const void *w, int64_t rows, int64_t nb01, int64_t K, const void *act,
                           int64_t row_size, int64_t T, float *dst, int64_t dst_stride);
+/* Q4_K weights that stay on the device: ggb_op_q4k_repack re-lays a matrix out once (same 144 B per super-block, the
+ * nibbles that share a lane-sum index adjacent), ggb_op_mul_mat_q4k_packed is the mat-vec on that layout (same bits as
+ * ggb_op_mul_mat_blocks / src/kernals.cl:48-111, ~4x its throughput).  ggb_mul_mat uses it for its cached src0. */
+int ggb_op_q4k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, void *packed);
+int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
+                              float *dst, int64_t dst_stride);
 
 /* K2/K3 — dst[t][row] = dot(w[row], q8[t]) (+ residual[t][row]); dst row pitch dst_stride floats */
 int ggb_op_mul_mat_q8(const ggb_weight *w, const void *q8, int64_t T, float *dst, int64_t dst_stride,

@@ -76,3 +76,25 @@ def test_unsupported_type_is_reported_not_computed(gpu):
     buf = np.zeros(1024, np.uint8)
     assert L.ggb_mul_mat(1, 1, 1, 64, 1, 4, 4, 64, 32, buf.ctypes.data, buf.ctypes.data, 10, buf.ctypes.data) == -4
     assert b"no kernel" in L.ggb_last_error()
+
+
+@pytest.mark.parametrize("n,k,t", [(40, 2048, 2), (9, 256, 1), (300, 4096, 1), (17, 16384, 3), (64, 1280, 1)])
+def test_q4_K_device_operators_raw_and_packed_layouts(gpu, n, k, t):
+    """the AoS operator (ggb_op_mul_mat_blocks) and the packed one (ggb_op_q4k_repack + ggb_op_mul_mat_q4k_packed) on
+    device pointers: both bit-identical to the scalar code; K with a partial group of four super-blocks included"""
+    rng = np.random.default_rng(n * k + t)
+    L = gpu.cuda_lib()
+    w = O.random_kquant_rows(rng, O.TYPE_Q4_K, n, k)
+    act = O.quantize_q8_K(rng.standard_normal((t, k)) * 1.5)
+    want = O.mul_mat_blocks(O.TYPE_Q4_K, w, act, k)
+    wd, ad = gpu.DeviceBuffer.from_numpy(w), gpu.DeviceBuffer.from_numpy(act)
+    dst = gpu.DeviceBuffer(4 * n * t)
+    gpu.check(L.ggb_op_mul_mat_blocks(O.TYPE_Q4_K, wd.ptr, n, w.shape[1], k, ad.ptr, act.shape[1], t, dst.ptr, n))
+    gpu.sync()
+    assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))
+    packed = gpu.DeviceBuffer(w.nbytes)
+    gpu.check(L.ggb_op_q4k_repack(wd.ptr, n, w.shape[1], k, packed.ptr))
+    gpu.check(L.ggb_buffer_memset(dst.ptr, 0, 4 * n * t))
+    gpu.check(L.ggb_op_mul_mat_q4k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], t, dst.ptr, n))
+    gpu.sync()
+    assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))
