@@ -88,6 +88,8 @@ _CUDA_SIG = {
     "ggb_op_mul_mat_blocks": (i32, [i32, vp, i64, i64, i64, vp, i64, i64, vp, i64]),
     "ggb_op_q4k_repack": (i32, [vp, i64, i64, i64, vp]),
     "ggb_op_mul_mat_q4k_packed": (i32, [vp, i64, i64, vp, i64, i64, vp, i64]),
+    "ggb_q6k_packed_bytes": (sz, [i64, i64]), "ggb_op_q6k_repack": (i32, [vp, i64, i64, i64, vp]),
+    "ggb_op_mul_mat_q6k_packed": (i32, [vp, i64, i64, vp, i64, i64, vp, i64]),
     "ggb_op_mul_mat_q8": (i32, [vp, vp, i64, vp, i64, vp]),
     "ggb_op_mul_mat_q8_multi": (i32, [i32, P(vp), vp, P(vp)]),
     "ggb_op_ffn_gate_up": (i32, [vp, vp, vp, vp, vp]),

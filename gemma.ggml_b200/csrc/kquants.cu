@@ -360,6 +360,100 @@ q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
     }
 }
 
+
+// ---------------------------------------------------------------- Q6_K, packed form (resident weights)
+// Same idea for Q6_K.  The 6-bit codes are expanded to int8 (q - 32) once - a row becomes W[nb][16 sub-blocks][16 B] |
+// scales[nb][16] | d[nb] (274 instead of 210 bytes per super-block: the kernel is bound by instruction issue, not by
+// HBM) - with word p of sub-block j = [a(g0, l = 2p), a(g1, 2p), a(g0, 2p + 1), a(g1, 2p + 1)], element = 16 j + 8 g + l,
+// and the activation words are staged in the same arrangement: two masked dp4a per word give the two lane sums.
+// Lane (s, j): super-block s of two, sub-block j of sixteen; the fold runs over the 16-lane group.
+constexpr int kActSB6 = 272; // staged activation super-block: qT 256 B | d float | pad
+
+__host__ __device__ inline int64_t q6k_packed_pitch(int nb) { return ((int64_t)nb * 274 + 15) & ~(int64_t)15; }
+
+__global__ void __launch_bounds__(256) q6k_repack_kernel(const uint8_t *__restrict__ raw, int64_t rows, int64_t nb01, int nb,
+                                                        uint8_t *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; // (row, super-block, sub-block j)
+    if (idx >= rows * nb * 16) return;
+    const int j = (int)(idx & 15);
+    const int64_t rb = idx >> 4, row = rb / nb;
+    const int sb = (int)(rb - row * nb);
+    const uint8_t *x = raw + row * nb01 + (int64_t)sb * kQ6K;
+    uint8_t *orow = out + row * q6k_packed_pitch(nb);
+    // element e of the scalar code's aux8 (ggml QK_K = 256 layout): chunk c = e / 128, quarter = (e % 128) / 32, i = e % 32
+    auto code = [&](int e) {
+        const int c = e >> 7, quarter = (e >> 5) & 3, i = e & 31;
+        const uint8_t ql = x[64 * c + 32 * (quarter & 1) + i], qh = x[128 + 32 * c + i];
+        const int lo = (quarter & 2) ? (ql >> 4) : (ql & 0xF);
+        return (int)(int8_t)(lo | (((qh >> (2 * quarter)) & 3) << 4)) - 32;
+    };
+    uint32_t w[4];
+    for (int p = 0; p < 4; p++) {
+        const int e0 = 16 * j + 2 * p;
+        w[p] = (uint32_t)(uint8_t)code(e0) | ((uint32_t)(uint8_t)code(e0 + 8) << 8) | ((uint32_t)(uint8_t)code(e0 + 1) << 16) |
+               ((uint32_t)(uint8_t)code(e0 + 9) << 24);
+    }
+    *reinterpret_cast<uint4 *>(orow + ((int64_t)sb * 16 + j) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    orow[(int64_t)nb * 256 + sb * 16 + j] = x[192 + j];
+    if (j == 0) *reinterpret_cast<uint16_t *>(orow + (int64_t)nb * 272 + 2 * sb) = *reinterpret_cast<const uint16_t *>(x + 208);
+}
+
+__global__ void __launch_bounds__(256)
+q6k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uint8_t *__restrict__ act, int64_t row_size,
+                  float *__restrict__ dst, int64_t dst_stride) {
+    extern __shared__ __align__(16) uint8_t s_act[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t *y = act + (int64_t)blockIdx.y * row_size;
+    for (int i = tid; i < nb * 64; i += 256) { // word (sb, j, p)
+        const int sb = i >> 6, j = (i >> 2) & 15, p = i & 3;
+        const uint8_t *q8 = y + (int64_t)sb * kQ8K + 4 + 16 * j + 2 * p;
+        const uint32_t v = (uint32_t)q8[0] | ((uint32_t)q8[8] << 8) | ((uint32_t)q8[1] << 16) | ((uint32_t)q8[9] << 24);
+        *reinterpret_cast<uint32_t *>(s_act + sb * kActSB6 + j * 16 + p * 4) = v;
+    }
+    for (int sb = tid; sb < nb; sb += 256) *reinterpret_cast<uint32_t *>(s_act + sb * kActSB6 + 256) = ld_u32(y + (int64_t)sb * kQ8K);
+    __syncthreads();
+    const int s = lane >> 4, j = lane & 15;
+    const bool b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    const int64_t pitch = q6k_packed_pitch(nb);
+    for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += (int64_t)gridDim.x * kWarps) {
+        const uint8_t *xrow = w + row * pitch;
+        float sums = 0.0f;
+#pragma unroll 2
+        for (int sb0 = 0; sb0 < nb; sb0 += 2) {
+            const int sb = sb0 + s;
+            const bool valid = sb < nb;
+            const int sbc = valid ? sb : 0;
+            const uint4 X = __ldg(reinterpret_cast<const uint4 *>(xrow + ((int64_t)sbc * 16 + j) * 16));
+            const int scale = (int)(int8_t)__ldg(xrow + (int64_t)nb * 256 + sbc * 16 + j);
+            const uint16_t dh = __ldg(reinterpret_cast<const uint16_t *>(xrow + (int64_t)nb * 272 + 2 * sbc));
+            const uint8_t *ya = s_act + sbc * kActSB6;
+            const uint4 q = *reinterpret_cast<const uint4 *>(ya + 16 * j);
+            const uint32_t xs[4] = {X.x, X.y, X.z, X.w}, qs[4] = {q.x, q.y, q.z, q.w};
+            int v[8];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                v[2 * p] = scale * __dp4a((int)(xs[p] & 0x0000ffffu), (int)qs[p], 0);
+                v[2 * p + 1] = scale * __dp4a((int)(xs[p] & 0xffff0000u), (int)qs[p], 0);
+            }
+            int w4[4], w2[2];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w4[k] = (b3 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b3 ? v[k] : v[4 + k], 8);
+#pragma unroll
+            for (int k = 0; k < 2; k++) w2[k] = (b2 ? w4[2 + k] : w4[k]) + __shfl_xor_sync(0xffffffffu, b2 ? w4[k] : w4[2 + k], 4);
+            int aux = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
+            aux += __shfl_xor_sync(0xffffffffu, aux, 1); // lane (s, j): aux32[l = j >> 1] of super-block s
+            const float d = __fmul_rn(half_bits_to_float(dh), *reinterpret_cast<const float *>(ya + 256));
+            const float t = valid ? __fmul_rn(d, (float)aux) : 0.0f;
+            const float t1 = __shfl_sync(0xffffffffu, t, (lane & 15) + 16);
+            sums = __fadd_rn(__fadd_rn(sums, t), t1); // (meaningful in lanes 0..15: lane 2 l and 2 l + 1 hold sums[l])
+        }
+        float sumf = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 8; l++) sumf = __fadd_rn(sumf, __shfl_sync(0xffffffffu, sums, 2 * l));
+        if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = sumf;
+    }
+}
+
 } // namespace
 
 extern "C" {
@@ -414,6 +508,41 @@ int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const
     for (int64_t t0 = 0; t0 < T; t0 += 65535) {
         const dim3 grid(gx, (unsigned)(T - t0 < 65535 ? T - t0 : 65535));
         q4k_packed_kernel<<<grid, 256, smem, ggb_cuda_stream()>>>((const uint8_t *)packed, rows, nb,
+                                                                  (const uint8_t *)act + t0 * row_size, row_size,
+                                                                  dst + t0 * dst_stride, dst_stride);
+        GGB_LAUNCH_CHECK();
+    }
+    return GGB_OK;
+}
+
+size_t ggb_q6k_packed_bytes(int64_t rows, int64_t K) { return (size_t)rows * (size_t)q6k_packed_pitch((int)(K / kQK)); }
+
+int ggb_op_q6k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, void *packed) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(raw && packed && rows > 0 && K > 0 && K % kQK == 0 && nb01 >= K / kQK * kQ6K && nb01 % 2 == 0,
+                  "q6k_repack: bad arguments");
+    const int nb = (int)(K / kQK);
+    const int64_t n = rows * nb * 16;
+    q6k_repack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>((const uint8_t *)raw, rows, nb01, nb,
+                                                                                 (uint8_t *)packed);
+    GGB_LAUNCH_CHECK();
+    return GGB_OK;
+}
+
+int ggb_op_mul_mat_q6k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
+                              float *dst, int64_t dst_stride) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(packed && act && dst && rows > 0 && T > 0 && K > 0 && K % kQK == 0, "mul_mat_q6k_packed: bad arguments");
+    const int nb = (int)(K / kQK);
+    GGB_CHECK_ARG(row_size >= (int64_t)nb * kQ8K && row_size % 4 == 0, "mul_mat_q6k_packed: activation row pitch %lld", (long long)row_size);
+    const size_t smem = (size_t)nb * kActSB6;
+    GGB_CHECK_ARG(smem <= 200 * 1024, "mul_mat_q6k_packed: K %lld too long for the staged activation row", (long long)K);
+    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(q6k_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t groups = (rows + kWarps - 1) / kWarps;
+    const unsigned gx = (unsigned)(groups < 148 * 8 ? groups : 148 * 8);
+    for (int64_t t0 = 0; t0 < T; t0 += 65535) {
+        const dim3 grid(gx, (unsigned)(T - t0 < 65535 ? T - t0 : 65535));
+        q6k_packed_kernel<<<grid, 256, smem, ggb_cuda_stream()>>>((const uint8_t *)packed, rows, nb,
                                                                   (const uint8_t *)act + t0 * row_size, row_size,
                                                                   dst + t0 * dst_stride, dst_stride);
         GGB_LAUNCH_CHECK();

@@ -23,7 +23,7 @@ struct CacheKey {
 };
 
 std::map<CacheKey, ggb_weight *> g_cache;
-std::map<CacheKey, void *> g_raw_cache; // Q6_K / F16 src0 in ggml's own layout, Q4_K in the packed layout of kquants.cu
+std::map<CacheKey, void *> g_raw_cache; // F16 src0 as it is, Q4_K / Q6_K in the packed layouts of kquants.cu
 std::mutex g_mu;
 void *g_act_raw = nullptr, *g_act_q8 = nullptr;
 float *g_dst = nullptr;
@@ -75,15 +75,15 @@ int mul_mat_blocks(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64
             ggb_set_error("mul_mat: src0 upload -> %s", cudaGetErrorString(e));
             return GGB_ERR_CUDA;
         }
-        if (type == GGB_TYPE_Q4_K) { // resident Q4_K: the packed layout of kquants.cu (same size, repacked once)
+        if (type == GGB_TYPE_Q4_K || type == GGB_TYPE_Q6_K) { // resident K-quants: the packed layouts of kquants.cu, repacked once
             void *packed = nullptr;
-            const size_t bytes = (size_t)ne01 * (size_t)(K / 256) * 144;
+            const size_t bytes = type == GGB_TYPE_Q4_K ? (size_t)ne01 * (size_t)(K / 256) * 144 : ggb_q6k_packed_bytes(ne01, K);
             if (cudaMalloc(&packed, bytes) != cudaSuccess) {
                 cudaFree(w);
-                ggb_set_error("mul_mat: out of device memory for the packed Q4_K copy");
+                ggb_set_error("mul_mat: out of device memory for the packed K-quant copy");
                 return GGB_ERR_CUDA;
             }
-            int rc2 = ggb_op_q4k_repack(w, ne01, nb01, K, packed);
+            int rc2 = type == GGB_TYPE_Q4_K ? ggb_op_q4k_repack(w, ne01, nb01, K, packed) : ggb_op_q6k_repack(w, ne01, nb01, K, packed);
             if (rc2 == GGB_OK && cudaStreamSynchronize(st) != cudaSuccess) rc2 = GGB_ERR_CUDA;
             cudaFree(w);
             if (rc2 != GGB_OK) {
@@ -102,6 +102,7 @@ int mul_mat_blocks(int64_t ne01, int64_t ne11, int64_t ne12, int64_t nb01, int64
     if ((rc = ensure((void **)&g_dst, &g_dst_cap, (size_t)col_num * ne01 * 4))) return rc;
     GGB_CUDA(cudaMemcpyAsync(g_act_raw, wdata, (size_t)col_num * row_size, cudaMemcpyHostToDevice, st));
     if (type == GGB_TYPE_Q4_K) rc = ggb_op_mul_mat_q4k_packed(w, ne01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01);
+    else if (type == GGB_TYPE_Q6_K) rc = ggb_op_mul_mat_q6k_packed(w, ne01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01);
     else rc = ggb_op_mul_mat_blocks(type, w, ne01, nb01, K, g_act_raw, (int64_t)row_size, col_num, g_dst, ne01);
     if (rc) return rc;
     return copy_back(dst_data, col_num, ne01, ne12, ne1, nb1, nb2, st);

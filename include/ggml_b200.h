@@ -149,6 +149,12 @@ int ggb_op_mul_mat_blocks(int type, const void *w, int64_t rows, int64_t nb01, i
 int ggb_op_q4k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, void *packed);
 int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
                               float *dst, int64_t dst_stride);
+/* the same for Q6_K: codes expanded to int8 (q - 32) in the transposed arrangement; ggb_q6k_packed_bytes = size of the
+ * packed matrix (274 B per super-block, rows padded to 16 B) */
+size_t ggb_q6k_packed_bytes(int64_t rows, int64_t K);
+int ggb_op_q6k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, void *packed);
+int ggb_op_mul_mat_q6k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
+                              float *dst, int64_t dst_stride);
 
 /* K2/K3 — dst[t][row] = dot(w[row], q8[t]) (+ residual[t][row]); dst row pitch dst_stride floats */
 int ggb_op_mul_mat_q8(const ggb_weight *w, const void *q8, int64_t T, float *dst, int64_t dst_stride,

@@ -98,3 +98,23 @@ def test_q4_K_device_operators_raw_and_packed_layouts(gpu, n, k, t):
     gpu.check(L.ggb_op_mul_mat_q4k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], t, dst.ptr, n))
     gpu.sync()
     assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))
+
+
+@pytest.mark.parametrize("n,k,t", [(40, 2048, 2), (9, 256, 1), (300, 4096, 1), (17, 16384, 3), (64, 1280, 1)])
+def test_q6_K_device_operators_raw_and_packed_layouts(gpu, n, k, t):
+    rng = np.random.default_rng(7 * n * k + t)
+    L = gpu.cuda_lib()
+    w = O.random_kquant_rows(rng, O.TYPE_Q6_K, n, k)
+    act = O.quantize_q8_K(rng.standard_normal((t, k)) * 1.5)
+    want = O.mul_mat_blocks(O.TYPE_Q6_K, w, act, k)
+    wd, ad = gpu.DeviceBuffer.from_numpy(w), gpu.DeviceBuffer.from_numpy(act)
+    dst = gpu.DeviceBuffer(4 * n * t)
+    gpu.check(L.ggb_op_mul_mat_blocks(O.TYPE_Q6_K, wd.ptr, n, w.shape[1], k, ad.ptr, act.shape[1], t, dst.ptr, n))
+    gpu.sync()
+    assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))
+    packed = gpu.DeviceBuffer(L.ggb_q6k_packed_bytes(n, k))
+    gpu.check(L.ggb_op_q6k_repack(wd.ptr, n, w.shape[1], k, packed.ptr))
+    gpu.check(L.ggb_buffer_memset(dst.ptr, 0, 4 * n * t))
+    gpu.check(L.ggb_op_mul_mat_q6k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], t, dst.ptr, n))
+    gpu.sync()
+    assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))

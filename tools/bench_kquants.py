@@ -34,3 +34,12 @@ for wtype, name in ((O.TYPE_Q4_K, "q4_K"), (O.TYPE_Q6_K, "q6_K"), (O.TYPE_F16, "
                     G.check(L.ggb_op_mul_mat_q4k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], 1, dst.ptr, n), "mm")
                 G.sync(); dt = (time.perf_counter() - t0) / 50
             print(f"{name} packed {n}x{k}: {dt * 1e6:8.1f} us  {w.nbytes / dt / 1e9:7.0f} GB/s")
+        if wtype == O.TYPE_Q6_K:
+            packed = G.DeviceBuffer(L.ggb_q6k_packed_bytes(n, k))
+            G.check(L.ggb_op_q6k_repack(wd.ptr, n, w.shape[1], k, packed.ptr), "repack")
+            for rep in range(2):
+                G.sync(); t0 = time.perf_counter()
+                for _ in range(50):
+                    G.check(L.ggb_op_mul_mat_q6k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], 1, dst.ptr, n), "mm")
+                G.sync(); dt = (time.perf_counter() - t0) / 50
+            print(f"{name} packed {n}x{k}: {dt * 1e6:8.1f} us  {w.nbytes / dt / 1e9:7.0f} GB/s (algorithmic 210 B / super-block; the packed copy streams 274)")
