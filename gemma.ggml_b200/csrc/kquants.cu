@@ -298,17 +298,20 @@ q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
         }
     }
     __syncthreads();
-    const int s = lane >> 3, j = lane & 7;
-    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    // lane (s, c): super-block s of EIGHT, sub-blocks 2c and 2c + 1 (64 elements per lane: the fold runs over four lanes
+    // only, and the scalar bookkeeping of an iteration is paid per eight super-blocks)
+    const int s = lane >> 2, c = lane & 3;
+    const bool b1 = lane & 2, b0 = lane & 1;
     for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += (int64_t)gridDim.x * kWarps) {
         const uint8_t *xrow = w + row * (int64_t)nb * kQ4K;
-        float sums = 0.0f, sumf = 0.0f;
-#pragma unroll 2
-        for (int sb0 = 0; sb0 < nb; sb0 += 4) {
+        float sumsA = 0.0f, sumsB = 0.0f, sumf = 0.0f; // lane (0, c): sums[2c], sums[2c + 1]; lane 0: sumf
+#pragma unroll 1
+        for (int sb0 = 0; sb0 < nb; sb0 += 8) {
             const int sb = sb0 + s;
             const bool valid = sb < nb;
             const uint8_t *blk = xrow + (int64_t)(valid ? sb : 0) * kQ4K;
-            const uint4 X = __ldg(reinterpret_cast<const uint4 *>(blk + 16 + 16 * j));
+            const uint4 X0 = __ldg(reinterpret_cast<const uint4 *>(blk + 16 + 32 * c));
+            const uint4 X1 = __ldg(reinterpret_cast<const uint4 *>(blk + 32 + 32 * c));
             const uint32_t dd = ldg_u32(blk);
             uint32_t u0 = ldg_u32(blk + 4), u1 = ldg_u32(blk + 8), u2 = ldg_u32(blk + 12);
             // 6-bit scales / mins (src/kernals.cl:75-80)
@@ -317,49 +320,62 @@ q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
             u1 = (u2 & 0x0f0f0f0fu) | (((u0 >> 6) & 0x03030303u) << 4);
             u2 = uaux;
             u0 &= 0x3f3f3f3fu;
-            const int scale = (int)(((j < 4 ? u0 : u1) >> (8 * (j & 3))) & 0xff);
-            const int mn = (int)(((j < 4 ? u2 : u3) >> (8 * (j & 3))) & 0xff);
+            const uint32_t sc2 = ((c < 2 ? u0 : u1) >> (16 * (c & 1))) & 0xffffu; // scales of sub-blocks 2c, 2c + 1
+            const uint32_t mn2 = ((c < 2 ? u2 : u3) >> (16 * (c & 1))) & 0xffffu;
             const uint8_t *ya = s_act + (valid ? sb : 0) * kActSB;
-            const uint4 qa = *reinterpret_cast<const uint4 *>(ya + 16 * j);       // qT[j][0..3]
-            const uint4 qb = *reinterpret_cast<const uint4 *>(ya + 128 + 16 * j); // qT[j][4..7]
-            const uint32_t xs[4] = {X.x, X.y, X.z, X.w};
-            const uint32_t qs[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
             int v[8];
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const uint32_t t1 = xs[p] & 0x0f0f0f0fu, t2 = (xs[p] >> 4) & 0x0f0f0f0fu;
-                const uint32_t a_even = __byte_perm(t1, t2, 0x5140), a_odd = __byte_perm(t1, t2, 0x7362);
-                v[2 * p] = scale * __dp4a((int)a_even, (int)qs[2 * p], 0);
-                v[2 * p + 1] = scale * __dp4a((int)a_odd, (int)qs[2 * p + 1], 0);
+            for (int h = 0; h < 2; h++) { // sub-block j = 2c + h
+                const uint4 X = h ? X1 : X0;
+                const int scale = (int)((sc2 >> (8 * h)) & 0xff);
+                const uint4 qa = *reinterpret_cast<const uint4 *>(ya + 32 * c + 16 * h);       // qT[j][0..3]
+                const uint4 qb = *reinterpret_cast<const uint4 *>(ya + 128 + 32 * c + 16 * h); // qT[j][4..7]
+                const uint32_t xs[4] = {X.x, X.y, X.z, X.w};
+                const uint32_t qs[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const uint32_t t1 = xs[p] & 0x0f0f0f0fu, t2 = (xs[p] >> 4) & 0x0f0f0f0fu;
+                    const int pe = __dp4a((int)__byte_perm(t1, t2, 0x5140), (int)qs[2 * p], 0);
+                    const int po = __dp4a((int)__byte_perm(t1, t2, 0x7362), (int)qs[2 * p + 1], 0);
+                    v[2 * p] = h ? v[2 * p] + scale * pe : scale * pe;
+                    v[2 * p + 1] = h ? v[2 * p + 1] + scale * po : scale * po;
+                }
             }
-            // fold inside the 8-lane group: lane (s, j) ends with aux32[l = j]
-            int w4[4], w2[2];
+            // fold inside the 4-lane group: lane (s, c) ends with aux32[2c] and aux32[2c + 1]
+            int w4[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) w4[k] = (b2 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b2 ? v[k] : v[4 + k], 4);
-#pragma unroll
-            for (int k = 0; k < 2; k++) w2[k] = (b1 ? w4[2 + k] : w4[k]) + __shfl_xor_sync(0xffffffffu, b1 ? w4[k] : w4[2 + k], 2);
-            const int aux = (b0 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1);
-            int sumi = mn * *reinterpret_cast<const int *>(ya + 256 + 4 * j);
+            for (int k = 0; k < 4; k++) w4[k] = (b1 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b1 ? v[k] : v[4 + k], 2);
+            const int aux0 = (b0 ? w4[2] : w4[0]) + __shfl_xor_sync(0xffffffffu, b0 ? w4[0] : w4[2], 1);
+            const int aux1 = (b0 ? w4[3] : w4[1]) + __shfl_xor_sync(0xffffffffu, b0 ? w4[1] : w4[3], 1);
+            const int *sp = reinterpret_cast<const int *>(ya + 256);
+            int sumi = (int)(mn2 & 0xff) * sp[2 * c] + (int)(mn2 >> 8) * sp[2 * c + 1];
             sumi += __shfl_xor_sync(0xffffffffu, sumi, 1);
             sumi += __shfl_xor_sync(0xffffffffu, sumi, 2);
-            sumi += __shfl_xor_sync(0xffffffffu, sumi, 4);
             const float yd = *reinterpret_cast<const float *>(ya + 288);
             const float d = __fmul_rn(half_bits_to_float((uint16_t)(dd & 0xffff)), yd);
             const float dmin = __fmul_rn(half_bits_to_float((uint16_t)(dd >> 16)), yd);
-            const float t = valid ? __fmul_rn(d, (float)aux) : 0.0f;       // x + 0.0f == x: a missing super-block adds nothing
+            const float tA = valid ? __fmul_rn(d, (float)aux0) : 0.0f; // x + 0.0f == x: a missing super-block adds nothing
+            const float tB = valid ? __fmul_rn(d, (float)aux1) : 0.0f;
             const float tm = valid ? __fmul_rn(dmin, (float)sumi) : 0.0f;
-            // the scalar order: super-blocks one after the other (lanes 0..7 own sums[l], lane 0 owns sumf)
-            const float t1 = __shfl_sync(0xffffffffu, t, (lane & 7) + 8), t2 = __shfl_sync(0xffffffffu, t, (lane & 7) + 16),
-                        t3 = __shfl_sync(0xffffffffu, t, (lane & 7) + 24);
-            const float m1 = __shfl_sync(0xffffffffu, tm, 8), m2 = __shfl_sync(0xffffffffu, tm, 16), m3 = __shfl_sync(0xffffffffu, tm, 24);
-            sums = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sums, t), t1), t2), t3); // (meaningful in lanes 0..7: there t is super-block sb0's)
-            sumf = __fsub_rn(__fsub_rn(__fsub_rn(__fsub_rn(sumf, tm), m1), m2), m3); // (meaningful in lane 0)
+            // the scalar order: the eight super-blocks one after the other
+            sumsA = __fadd_rn(sumsA, tA);
+            sumsB = __fadd_rn(sumsB, tB);
+            sumf = __fsub_rn(sumf, tm);
+#pragma unroll
+            for (int k = 1; k < 8; k++) {
+                sumsA = __fadd_rn(sumsA, __shfl_sync(0xffffffffu, tA, c + 4 * k)); // (meaningful in lanes 0..3)
+                sumsB = __fadd_rn(sumsB, __shfl_sync(0xffffffffu, tB, c + 4 * k));
+                sumf = __fsub_rn(sumf, __shfl_sync(0xffffffffu, tm, 4 * k));       // (meaningful in lane 0)
+            }
         }
-        const float r = finish_lanes8(sumf, sums);
-        if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = r;
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const float a = __shfl_sync(0xffffffffu, (l & 1) ? sumsB : sumsA, l >> 1);
+            sumf = __fadd_rn(sumf, a);
+        }
+        if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = sumf;
     }
 }
-
 
 // ---------------------------------------------------------------- Q6_K, packed form (resident weights)
 // Same idea for Q6_K.  The 6-bit codes are expanded to int8 (q - 32) once - a row becomes W[nb][16 sub-blocks][16 B] |
