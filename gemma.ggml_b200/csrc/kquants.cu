@@ -382,7 +382,7 @@ q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
 // scales[nb][16] | d[nb] (274 instead of 210 bytes per super-block: the kernel is bound by instruction issue, not by
 // HBM) - with word p of sub-block j = [a(g0, l = 2p), a(g1, 2p), a(g0, 2p + 1), a(g1, 2p + 1)], element = 16 j + 8 g + l,
 // and the activation words are staged in the same arrangement: two masked dp4a per word give the two lane sums.
-// Lane (s, j): super-block s of two, sub-block j of sixteen; the fold runs over the 16-lane group.
+// Lane (s, c): super-block s of four, sub-blocks 2c and 2c + 1 of sixteen; the fold runs over the 8-lane group.
 constexpr int kActSB6 = 272; // staged activation super-block: qT 256 B | d float | pad
 
 __host__ __device__ inline int64_t q6k_packed_pitch(int nb) { return ((int64_t)nb * 274 + 15) & ~(int64_t)15; }
@@ -428,44 +428,53 @@ q6k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
     }
     for (int sb = tid; sb < nb; sb += 256) *reinterpret_cast<uint32_t *>(s_act + sb * kActSB6 + 256) = ld_u32(y + (int64_t)sb * kQ8K);
     __syncthreads();
-    const int s = lane >> 4, j = lane & 15;
-    const bool b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    // lane (s, c): super-block s of four, sub-blocks 2c and 2c + 1 (32 elements per lane); the fold runs over the 8-lane group
+    const int s = lane >> 3, c = lane & 7;
+    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
     const int64_t pitch = q6k_packed_pitch(nb);
     for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < rows; row += (int64_t)gridDim.x * kWarps) {
         const uint8_t *xrow = w + row * pitch;
-        float sums = 0.0f;
-#pragma unroll 2
-        for (int sb0 = 0; sb0 < nb; sb0 += 2) {
+        float sums = 0.0f; // lane (0, l): sums[l]
+#pragma unroll 1
+        for (int sb0 = 0; sb0 < nb; sb0 += 4) {
             const int sb = sb0 + s;
             const bool valid = sb < nb;
             const int sbc = valid ? sb : 0;
-            const uint4 X = __ldg(reinterpret_cast<const uint4 *>(xrow + ((int64_t)sbc * 16 + j) * 16));
-            const int scale = (int)(int8_t)__ldg(xrow + (int64_t)nb * 256 + sbc * 16 + j);
+            const uint8_t *xw = xrow + ((int64_t)sbc * 16 + 2 * c) * 16;
+            const uint4 X0 = __ldg(reinterpret_cast<const uint4 *>(xw)), X1 = __ldg(reinterpret_cast<const uint4 *>(xw + 16));
+            const uint32_t sc2 = __ldg(reinterpret_cast<const uint16_t *>(xrow + (int64_t)nb * 256 + sbc * 16 + 2 * c));
             const uint16_t dh = __ldg(reinterpret_cast<const uint16_t *>(xrow + (int64_t)nb * 272 + 2 * sbc));
             const uint8_t *ya = s_act + sbc * kActSB6;
-            const uint4 q = *reinterpret_cast<const uint4 *>(ya + 16 * j);
-            const uint32_t xs[4] = {X.x, X.y, X.z, X.w}, qs[4] = {q.x, q.y, q.z, q.w};
+            const uint4 q0 = *reinterpret_cast<const uint4 *>(ya + 32 * c), q1 = *reinterpret_cast<const uint4 *>(ya + 32 * c + 16);
             int v[8];
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                v[2 * p] = scale * __dp4a((int)(xs[p] & 0x0000ffffu), (int)qs[p], 0);
-                v[2 * p + 1] = scale * __dp4a((int)(xs[p] & 0xffff0000u), (int)qs[p], 0);
+            for (int h = 0; h < 2; h++) {
+                const uint4 X = h ? X1 : X0, q = h ? q1 : q0;
+                const int scale = (int)(int8_t)(sc2 >> (8 * h));
+                const uint32_t xs[4] = {X.x, X.y, X.z, X.w}, qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int pe = __dp4a((int)(xs[p] & 0x0000ffffu), (int)qs[p], 0);
+                    const int po = __dp4a((int)(xs[p] & 0xffff0000u), (int)qs[p], 0);
+                    v[2 * p] = h ? v[2 * p] + scale * pe : scale * pe;
+                    v[2 * p + 1] = h ? v[2 * p + 1] + scale * po : scale * po;
+                }
             }
             int w4[4], w2[2];
 #pragma unroll
-            for (int k = 0; k < 4; k++) w4[k] = (b3 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b3 ? v[k] : v[4 + k], 8);
+            for (int k = 0; k < 4; k++) w4[k] = (b2 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, b2 ? v[k] : v[4 + k], 4);
 #pragma unroll
-            for (int k = 0; k < 2; k++) w2[k] = (b2 ? w4[2 + k] : w4[k]) + __shfl_xor_sync(0xffffffffu, b2 ? w4[k] : w4[2 + k], 4);
-            int aux = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w2[0] : w2[1], 2);
-            aux += __shfl_xor_sync(0xffffffffu, aux, 1); // lane (s, j): aux32[l = j >> 1] of super-block s
+            for (int k = 0; k < 2; k++) w2[k] = (b1 ? w4[2 + k] : w4[k]) + __shfl_xor_sync(0xffffffffu, b1 ? w4[k] : w4[2 + k], 2);
+            const int aux = (b0 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? w2[0] : w2[1], 1); // aux32[l = c]
             const float d = __fmul_rn(half_bits_to_float(dh), *reinterpret_cast<const float *>(ya + 256));
             const float t = valid ? __fmul_rn(d, (float)aux) : 0.0f;
-            const float t1 = __shfl_sync(0xffffffffu, t, (lane & 15) + 16);
-            sums = __fadd_rn(__fadd_rn(sums, t), t1); // (meaningful in lanes 0..15: lane 2 l and 2 l + 1 hold sums[l])
+            sums = __fadd_rn(sums, t); // the scalar order: the four super-blocks one after the other (lanes 0..7)
+#pragma unroll
+            for (int k = 1; k < 4; k++) sums = __fadd_rn(sums, __shfl_sync(0xffffffffu, t, c + 8 * k));
         }
         float sumf = 0.0f;
 #pragma unroll
-        for (int l = 0; l < 8; l++) sumf = __fadd_rn(sumf, __shfl_sync(0xffffffffu, sums, 2 * l));
+        for (int l = 0; l < 8; l++) sumf = __fadd_rn(sumf, __shfl_sync(0xffffffffu, sums, l));
         if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = sumf;
     }
 }
