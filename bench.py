@@ -282,6 +282,54 @@ def mul_mat_dropin_us(G):
     return out
 
 
+def kquant_matvec_record(G, peak_gbs):
+    """SURVEY.md 8f-2 on the record: the resident (packed) K-quant mat-vecs on the tied-embedding shape of Gemma-2B
+    (256000 x 2048, one Q8_K activation row), device-timed; algorithmic bytes = ggml's block bytes (144 / 210 per 256)."""
+    L = G.cuda_lib()
+    rng = np.random.default_rng(11)
+    n, k = 256000, 2048
+    nb = k // 256
+    out = {}
+    x = rng.standard_normal((1, k)).astype(np.float32)
+    act = G.quantize_q8_K(x)
+    ad = G.DeviceBuffer.from_numpy(act)
+    dst = G.DeviceBuffer(4 * n)
+    for name, size, d_off in (("q4_K", 144, 0), ("q6_K", 210, 208)):
+        w = rng.integers(0, 256, size=(n, nb, size), dtype=np.uint8)
+        w[:, :, d_off] = 0
+        w[:, :, d_off + 1] = 0x1c            # fp16 super-scale ~ 0.004
+        if name == "q4_K":
+            w[:, :, 2] = 0
+            w[:, :, 3] = 0x1c
+        w = np.ascontiguousarray(w.reshape(n, nb * size))
+        wd = G.DeviceBuffer.from_numpy(w)
+        if name == "q4_K":
+            packed = G.DeviceBuffer(w.nbytes)
+            G.check(L.ggb_op_q4k_repack(wd.ptr, n, w.shape[1], k, packed.ptr), "repack")
+            call = lambda: L.ggb_op_mul_mat_q4k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], 1, dst.ptr, n)
+        else:
+            packed = G.DeviceBuffer(L.ggb_q6k_packed_bytes(n, k))
+            G.check(L.ggb_op_q6k_repack(wd.ptr, n, w.shape[1], k, packed.ptr), "repack")
+            call = lambda: L.ggb_op_mul_mat_q6k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], 1, dst.ptr, n)
+        for _ in range(5):
+            G.check(call(), "kquant mat-vec")
+        G.sync()
+        L.ggb_prof_enable(1); G.prof_reset()
+        L.ggb_prof_start(b"kq")
+        for _ in range(40):
+            call()
+        L.ggb_prof_stop(b"kq")
+        G.sync()
+        ms, _ = G.prof_get("kq")
+        L.ggb_prof_enable(0)
+        us = ms * 1e3 / 40
+        gbs = w.nbytes / (us * 1e-6) / 1e9
+        out[name] = {"shape": "256000 x 2048 (resident, packed form)", "us_per_launch": us, "algorithmic_gbs": gbs,
+                     "frac_of_hbm_peak": gbs / peak_gbs}
+        del wd, packed
+    return out
+
+
 def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -417,6 +465,10 @@ def run_ours(args):
                 extra["mul_mat_dropin_us_per_call"] = mul_mat_dropin_us(G)
             except Exception as e:
                 extra["mul_mat_dropin_us_per_call"] = {"failed": str(e)}
+            try:
+                extra["kquant_matvec"] = kquant_matvec_record(G, peak)
+            except Exception as e:  # noqa: BLE001
+                extra["kquant_matvec"] = {"failed": str(e)}
     if rank != 0:
         return
     line = {
