@@ -4,7 +4,16 @@
  * Each function cites what it follows.  "[UPSTREAM]" = semantics of the un-vendored ggml
  * (ggml.c / ggml-quants.c, llama.cpp circa Feb-Mar 2024) restated from its published
  * algorithm; "ref:" = a file:line under /root/reference.
- * Build: gcc -O2 -ffp-contract=off (no FMA contraction, no fast-math).
+ * Build: gcc -O3 -ffp-contract=off (no FMA contraction, no fast-math).
+ *
+ * PINNING.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.
+ *   - Q4_K x Q8_K and F16 x F16 dots: bit-identical to the REFERENCE'S OWN CODE (src/kernals.cl compiled where it lies
+ *     into oracle/_ref, tests/test_kquants_cpu.py);
+ *   - Q4_0 / Q8_0 codecs, fp16 conversion, Q4_K / Q6_K block layouts: gguf-py known-answer vectors (tests/golden/);
+ *   - Q4_0 / Q8_0 dots, rms_norm, soft_max_ext, rope, GeGLU, the forward pass: the reference commits no fixture and cannot
+ *     be built here (its patched ggml is un-vendored), so these are PINNED TO THE PUBLISHED SCALAR ggml ALGORITHM AND TO
+ *     float64 MODELS, NOT TO REFERENCE OUTPUT ("parity unpinned" in the tier's sense for exactly these functions).
  */
 #include "ggml_oracle.h"
 
