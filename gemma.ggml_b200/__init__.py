@@ -21,6 +21,7 @@ HOST_LIB = os.path.join(HERE, "libggb_host.so")
 HEADER = os.path.join(ROOT, "include", "ggml_b200.h")
 
 TYPE_F32, TYPE_F16, TYPE_Q4_0, TYPE_Q8_0 = 0, 1, 2, 8
+TYPE_Q4_K, TYPE_Q6_K, TYPE_Q8_K = 12, 14, 15
 BLOCK_BYTES = {TYPE_Q4_0: 18, TYPE_Q8_0: 34}
 
 
@@ -88,6 +89,7 @@ _CUDA_SIG = {
     "ggb_op_mul_mat_blocks": (i32, [i32, vp, i64, i64, i64, vp, i64, i64, vp, i64]),
     "ggb_op_q4k_repack": (i32, [vp, i64, i64, i64, vp]),
     "ggb_op_mul_mat_q4k_packed": (i32, [vp, i64, i64, vp, i64, i64, vp, i64]),
+    "ggb_op_get_rows_blocks": (i32, [i32, vp, i64, i64, i64, vp, i64, f32, vp]),
     "ggb_q6k_packed_bytes": (sz, [i64, i64]), "ggb_op_q6k_repack": (i32, [vp, i64, i64, i64, vp]),
     "ggb_op_mul_mat_q6k_packed": (i32, [vp, i64, i64, vp, i64, i64, vp, i64]),
     "ggb_op_mul_mat_q8": (i32, [vp, vp, i64, vp, i64, vp]),
@@ -129,6 +131,7 @@ _HOST_SIG = {
     "gm_create": (vp, [P(Config)]), "gm_free": (None, [vp]),
     "gm_init_synthetic_weights": (i32, [vp]), "gm_init_tensor_parallel": (i32, [vp, i32, i32]),
     "gm_tp_plan": (i32, [P(Config), i32, i32, P(i64)]), "gm_set_tensor": (i32, [vp, i32, vp, i64]),
+    "gm_set_tensor_typed": (i32, [vp, i32, i32, vp, i64]), "gm_kquant_mode": (i32, [vp]),
     "gm_init_kv_cache": (i32, [vp]), "gm_fill_kv_cache_synthetic": (i32, [vp, u64]),
     "gm_build_compute_graph": (i32, [vp, i32, i32]), "gm_decoder": (vp, [vp]), "gm_is_fused": (i32, [vp]), "gm_decode_step": (i32, [vp, i32, i32, P(i32)]),
     "gm_set_state": (i32, [vp, i32, i32, i32]), "gm_run_steps": (i32, [vp, i32]), "gm_run_steps_profiled": (i32, [vp, i32]),
@@ -478,6 +481,15 @@ class GemmaModel:
     def set_tensor(self, tensor_id, raw):
         raw = np.ascontiguousarray(raw)
         check(self.H.gm_set_tensor(self.h, tensor_id, _ptr(raw), raw.nbytes), f"gm_set_tensor({tensor_id})")
+
+    def set_tensor_typed(self, tensor_id, wtype, raw):
+        """a matrix in ggml type `wtype` (TYPE_Q4_K / TYPE_Q6_K put the model into K-quant mode), or an F32 norm"""
+        raw = np.ascontiguousarray(raw)
+        check(self.H.gm_set_tensor_typed(self.h, tensor_id, wtype, _ptr(raw), raw.nbytes), f"gm_set_tensor_typed({tensor_id})")
+
+    @property
+    def kquant_mode(self):
+        return bool(self.H.gm_kquant_mode(self.h))
 
     def init_kv_cache(self):
         check(self.H.gm_init_kv_cache(self.h), "gm_init_kv_cache")

@@ -479,6 +479,49 @@ q6k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
     }
 }
 
+
+// ---------------------------------------------------------------- get_rows on K-quant blocks (embedding lookup)
+// [UPSTREAM] dequantize_row_q4_K / dequantize_row_q6_K for the rows ids[t], times `scale` (ggml_scale): one thread per
+// element, the scalar code's roundings: Q4_K y = (d * sc) * q - (dmin * m); Q6_K y = (d * scale) * (q - 32).
+__global__ void __launch_bounds__(256)
+get_rows_blocks_kernel(int type, const uint8_t *__restrict__ raw, int64_t n_rows, int64_t nb01, int64_t K,
+                       const int32_t *__restrict__ ids, float scale, float *__restrict__ y) {
+    const int64_t t = blockIdx.y;
+    int64_t row = ids[t];
+    row = row < 0 ? 0 : (row >= n_rows ? n_rows - 1 : row);
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= K) return;
+    const int64_t sb = e >> 8;
+    const int i = (int)(e & 255);
+    float val;
+    if (type == GGB_TYPE_Q4_K) {
+        const uint8_t *x = raw + row * nb01 + sb * kQ4K;
+        const int j = i >> 5; // sub-block
+        uint32_t u0 = ld_u32(x + 4), u1 = ld_u32(x + 8), u2 = ld_u32(x + 12);
+        const uint32_t u3 = ((u2 >> 4) & 0x0f0f0f0fu) | (((u1 >> 6) & 0x03030303u) << 4);
+        const uint32_t uaux = u1 & 0x3f3f3f3fu;
+        u1 = (u2 & 0x0f0f0f0fu) | (((u0 >> 6) & 0x03030303u) << 4);
+        u2 = uaux;
+        u0 &= 0x3f3f3f3fu;
+        const int sc = (int)(((j < 4 ? u0 : u1) >> (8 * (j & 3))) & 0xff), mn = (int)(((j < 4 ? u2 : u3) >> (8 * (j & 3))) & 0xff);
+        const uint32_t dd = ld_u32(x);
+        const float d1 = __fmul_rn(half_bits_to_float((uint16_t)(dd & 0xffff)), (float)sc);
+        const float m1 = __fmul_rn(half_bits_to_float((uint16_t)(dd >> 16)), (float)mn);
+        const uint8_t q = x[16 + 32 * (j >> 1) + (i & 31)];
+        const int nib = (j & 1) ? (q >> 4) : (q & 0xF);
+        val = __fsub_rn(__fmul_rn(d1, (float)nib), m1);
+    } else {
+        const uint8_t *x = raw + row * nb01 + sb * kQ6K;
+        const int c = i >> 7, quarter = (i >> 5) & 3, l = i & 31;
+        const uint8_t ql = x[64 * c + 32 * (quarter & 1) + l], qh = x[128 + 32 * c + l];
+        const int lo = (quarter & 2) ? (ql >> 4) : (ql & 0xF);
+        const int a = (int)(int8_t)(lo | (((qh >> (2 * quarter)) & 3) << 4)) - 32;
+        const float d = half_bits_to_float((uint16_t)ld_u16(x + 208));
+        val = __fmul_rn(__fmul_rn(d, (float)(int8_t)x[192 + (i >> 4)]), (float)a);
+    }
+    y[t * K + e] = __fmul_rn(val, scale);
+}
+
 } // namespace
 
 extern "C" {
@@ -572,6 +615,18 @@ int ggb_op_mul_mat_q6k_packed(const void *packed, int64_t rows, int64_t K, const
                                                                   dst + t0 * dst_stride, dst_stride);
         GGB_LAUNCH_CHECK();
     }
+    return GGB_OK;
+}
+
+int ggb_op_get_rows_blocks(int type, const void *raw, int64_t n_rows, int64_t nb01, int64_t K, const int32_t *ids, int64_t T,
+                           float scale, float *y) {
+    GGB_REQUIRE_INIT();
+    GGB_CHECK_ARG(raw && ids && y && T > 0 && T <= 65535 && n_rows > 0, "get_rows_blocks: bad arguments");
+    GGB_CHECK_ARG((type == GGB_TYPE_Q4_K || type == GGB_TYPE_Q6_K) && K > 0 && K % kQK == 0, "get_rows_blocks: type %d / K %lld", type, (long long)K);
+    GGB_CHECK_ARG(nb01 >= (int64_t)ggb_type_row_bytes(type, K) && nb01 % (type == GGB_TYPE_Q4_K ? 4 : 2) == 0, "get_rows_blocks: row pitch %lld", (long long)nb01);
+    const dim3 grid((unsigned)((K + 255) / 256), (unsigned)T);
+    get_rows_blocks_kernel<<<grid, 256, 0, ggb_cuda_stream()>>>(type, (const uint8_t *)raw, n_rows, nb01, K, ids, scale, y);
+    GGB_LAUNCH_CHECK();
     return GGB_OK;
 }
 

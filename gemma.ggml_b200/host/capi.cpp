@@ -27,6 +27,10 @@ int gm_init_synthetic_weights(void *m) { return ((gemma_model *)m)->init_synthet
 int gm_set_tensor(void *m, int tensor_id, const void *host, int64_t nbytes) {
     return ((gemma_model *)m)->set_tensor(tensor_id, host, nbytes);
 }
+int gm_set_tensor_typed(void *m, int tensor_id, int type, const void *host, int64_t nbytes) {
+    return ((gemma_model *)m)->set_tensor_typed(tensor_id, type, host, nbytes);
+}
+int gm_kquant_mode(void *m) { return ((gemma_model *)m)->kquant_mode() ? 1 : 0; }
 int gm_init_kv_cache(void *m) { return ((gemma_model *)m)->init_kv_cache(); }
 int gm_fill_kv_cache_synthetic(void *m, uint64_t seed) { return ((gemma_model *)m)->fill_kv_cache_synthetic(seed); }
 int gm_build_compute_graph(void *m, int capture_acts, int fused) {

@@ -16,6 +16,11 @@
         if (rc__) return rc__; \
     } while (0)
 
+static void kq_free(void *&p) {
+    if (p) ggb_buffer_free(p);
+    p = nullptr;
+}
+
 static constexpr float kNormSigma = 0.02f; // norm weights: 1 + N(0, 0.02^2)
 
 gemma_model::gemma_model(const gemma_config &cfg) : cfg_(cfg) {
@@ -163,6 +168,20 @@ void gemma_model::free_all() {
         if (b) ggb_buffer_free(b);
     output_norm_ = nullptr; state_ = history_ = nullptr; x0_ = q_ = k_ = v_ = logits_ = result_norm_ = nullptr;
     sa_out_ = l_out_ = kqv_ = ffn_act_ = nullptr; act_e_ = act_q_ = act_f_ = attn_scratch_ = sample_scratch_ = nullptr;
+    kq_free(kq_embd_.raw);
+    kq_free(kq_embd_.packed);
+    for (kq_mat &w : kq_layers_) {
+        kq_free(w.raw);
+        kq_free(w.packed);
+    }
+    kq_layers_.clear();
+    kq_embd_ = kq_mat();
+    kq_mode_ = false;
+    void *kqb[] = {kq_xn_, kq_gate_, kq_up_, kq_q8_};
+    for (void *b : kqb)
+        if (b) ggb_buffer_free(b);
+    kq_xn_ = kq_gate_ = kq_up_ = nullptr;
+    kq_q8_ = nullptr;
     for (void *b : k_cache_) ggb_buffer_free(b);
     for (void *b : v_cache_) ggb_buffer_free(b);
     k_cache_.clear();
@@ -255,6 +274,68 @@ int gemma_model::set_tensor(int tensor_id, const void *host_data, int64_t nbytes
     case GM_L_FFN_DOWN: return mat(&l.ffn_down, E, F);
     }
     return GGB_ERR_ARG;
+}
+
+int gemma_model::set_tensor_typed(int tensor_id, int type, const void *host_data, int64_t nbytes) {
+    if (type != GGB_TYPE_Q4_K && type != GGB_TYPE_Q6_K) {
+        if (kq_mode_ && tensor_id != GM_T_OUTPUT_NORM && (tensor_id < GM_T_LAYER0 || ((tensor_id - GM_T_LAYER0) % GM_T_PER_LAYER != GM_L_ATTN_NORM &&
+                                                                                       (tensor_id - GM_T_LAYER0) % GM_T_PER_LAYER != GM_L_FFN_NORM)))
+            return GGB_ERR_ARG; // a K-quant model takes K-quant matrices only
+        return set_tensor(tensor_id, host_data, nbytes);
+    }
+    const gemma_config &c = cfg_;
+    if (plan_.size > 1) return GGB_ERR_UNSUPPORTED; // K-quant mode is single-GPU
+    if (built_ || graph_ || decoder_) {
+        ggb_sync();
+        ggb_graph_free(graph_);
+        graph_ = nullptr;
+        ggb_decoder_free(decoder_);
+        decoder_ = nullptr;
+        built_ = false;
+    }
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
+    if (kq_layers_.empty()) kq_layers_.resize((size_t)c.n_layer * 7);
+    kq_mat *slot = nullptr;
+    int64_t rows = 0, cols = 0;
+    bool keep_raw = false;
+    if (tensor_id == GM_T_TOKEN_EMBD) {
+        slot = &kq_embd_; rows = V; cols = E; keep_raw = true;
+    } else {
+        const int rel = tensor_id - GM_T_LAYER0;
+        if (rel < 0 || rel >= GM_T_PER_LAYER * c.n_layer) return GGB_ERR_ARG;
+        const int il = rel / GM_T_PER_LAYER;
+        int k = -1;
+        switch (rel % GM_T_PER_LAYER) {
+        case GM_L_ATTN_Q: k = 0; rows = QD; cols = E; break;
+        case GM_L_ATTN_K: k = 1; rows = KD; cols = E; break;
+        case GM_L_ATTN_V: k = 2; rows = KD; cols = E; break;
+        case GM_L_ATTN_OUT: k = 3; rows = E; cols = QD; break;
+        case GM_L_FFN_GATE: k = 4; rows = F; cols = E; break;
+        case GM_L_FFN_UP: k = 5; rows = F; cols = E; break;
+        case GM_L_FFN_DOWN: k = 6; rows = E; cols = F; break;
+        default: return GGB_ERR_ARG; // norms are F32
+        }
+        slot = &kq_layers_[(size_t)il * 7 + (size_t)k];
+    }
+    if (cols % 256 != 0) return GGB_ERR_ARG;
+    const int64_t row_bytes = (int64_t)ggb_type_row_bytes(type, cols);
+    if (nbytes != rows * row_bytes) return GGB_ERR_ARG;
+    if (slot->packed) weight_bytes_ -= (size_t)(slot->rows * (int64_t)ggb_type_row_bytes(slot->type, slot->cols));
+    kq_free(slot->raw);
+    kq_free(slot->packed);
+    GM_TRY(ggb_buffer_alloc((size_t)nbytes, &slot->raw));
+    GM_TRY(ggb_upload(slot->raw, host_data, (size_t)nbytes));
+    const size_t pbytes = type == GGB_TYPE_Q4_K ? (size_t)nbytes : ggb_q6k_packed_bytes(rows, cols);
+    GM_TRY(ggb_buffer_alloc(pbytes, &slot->packed));
+    GM_TRY(type == GGB_TYPE_Q4_K ? ggb_op_q4k_repack(slot->raw, rows, row_bytes, cols, slot->packed)
+                                  : ggb_op_q6k_repack(slot->raw, rows, row_bytes, cols, slot->packed));
+    GM_TRY(ggb_sync());
+    if (!keep_raw) kq_free(slot->raw);
+    slot->type = type; slot->rows = rows; slot->cols = cols;
+    weight_bytes_ += (size_t)nbytes;
+    kq_mode_ = true;
+    return 0;
 }
 
 // ref: init_kv_cache (:361-401): per layer one F16 K and one F16 V tensor, zeroed.  Device layout is
@@ -365,6 +446,54 @@ int gemma_model::emit_decode_step() {
     return 0;
 }
 
+int gemma_model::kq_mv(const kq_mat &w, const float *x, float *dst) {
+    GM_TRY(ggb_op_quantize_q8_K(x, w.cols, 1, kq_q8_));
+    const int64_t row_size = (int64_t)ggb_type_row_bytes(GGB_TYPE_Q8_K, w.cols);
+    return w.type == GGB_TYPE_Q4_K ? ggb_op_mul_mat_q4k_packed(w.packed, w.rows, w.cols, kq_q8_, row_size, 1, dst, w.rows)
+                                   : ggb_op_mul_mat_q6k_packed(w.packed, w.rows, w.cols, kq_q8_, row_size, 1, dst, w.rows);
+}
+
+// The same node list on K-quant weights: every mul_mat node = quantize_row_q8_K of its input (ggml's INIT stage for a
+// K-quant src0) + the K-quant mat-vec; norms, rope, attention, GeGLU, residual adds and the sampler are the Q4_0 / Q8_0
+// path's operators on fp32 rows.
+int gemma_model::emit_decode_step_kq() {
+    const gemma_config &c = cfg_;
+    const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
+    const int64_t QD = (int64_t)c.n_head * c.head_dim;
+    const float q_scale = 1.0f / sqrtf((float)c.head_dim);
+    PROFILE("op_get_rows", ggb_op_get_rows_blocks(kq_embd_.type, kq_embd_.raw, V, (int64_t)ggb_type_row_bytes(kq_embd_.type, E), E,
+                                                   state_, 1, sqrtf((float)c.n_embd), x0_));
+    const float *x_in = x0_;
+    for (int il = 0; il < c.n_layer; il++) {
+        const gemma_layer &l = layers_[(size_t)il];
+        const kq_mat *w = &kq_layers_[(size_t)il * 7];
+        float *sa = sa_out_ + (size_t)il * E, *lo = l_out_ + (size_t)il * E, *kqv = kqv_ + (size_t)il * QD;
+        float *act = ffn_act_ + (size_t)il * F;
+        PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, l.attn_norm, c.eps, E, 1, kq_xn_, nullptr));
+        PROFILE("op_mul_mat", kq_mv(w[0], kq_xn_, q_));
+        PROFILE("op_mul_mat", kq_mv(w[1], kq_xn_, k_));
+        PROFILE("op_mul_mat", kq_mv(w[2], kq_xn_, v_));
+        PROFILE("op_rope", ggb_op_rope_kv_store(q_, k_, v_, state_ + 1, c.n_head, c.n_head_kv, c.head_dim, q_scale,
+                                                k_cache_[(size_t)il], v_cache_[(size_t)il]));
+        PROFILE("op_attn", ggb_op_attn_decode(q_, k_cache_[(size_t)il], v_cache_[(size_t)il], state_ + 1, c.n_head,
+                                              c.n_head_kv, c.head_dim, c.n_ctx, attn_scratch_, kqv, nullptr));
+        PROFILE("op_mul_mat", kq_mv(w[3], kqv, sa));
+        PROFILE("op_add", ggb_op_add(sa, x_in, E, sa));
+        PROFILE("op_rms_norm", ggb_op_rms_norm(sa, l.ffn_norm, c.eps, E, 1, kq_xn_, nullptr));
+        PROFILE("op_mul_mat", kq_mv(w[4], kq_xn_, kq_gate_));
+        PROFILE("op_mul_mat", kq_mv(w[5], kq_xn_, kq_up_));
+        PROFILE("op_gelu", ggb_op_gelu(kq_gate_, F, kq_gate_));
+        PROFILE("op_mul", ggb_op_mul(kq_gate_, kq_up_, F, act));
+        PROFILE("op_mul_mat", kq_mv(w[6], act, lo));
+        PROFILE("op_add", ggb_op_add(lo, sa, E, lo));
+        x_in = lo;
+    }
+    PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, output_norm_, c.eps, E, 1, result_norm_, nullptr));
+    PROFILE("op_mul_mat", kq_mv(kq_embd_, result_norm_, logits_));
+    PROFILE("op_argmax", ggb_op_sample_greedy(logits_, V, state_, history_, sample_scratch_));
+    return 0;
+}
+
 // The same token step, row-sharded over plan_.size ranks.  Every rank keeps the replicated
 // fp32 residual stream; each weight mat-vec computes this rank's rows only and the shards meet in four
 // allgathers per layer: attention output, o-proj (+residual), GeGLU activations (already Q8_0: int8 codes and
@@ -421,7 +550,7 @@ int gemma_model::run_steps_profiled(int steps) {
     if (!built_) return GGB_ERR_ARG;
     ggb_prof_enable(1);
     int rc = 0;
-    for (int i = 0; i < steps && !rc; i++) rc = plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step();
+    for (int i = 0; i < steps && !rc; i++) rc = kq_mode_ ? emit_decode_step_kq() : plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step();
     ggb_sync();
     ggb_prof_enable(0);
     return rc;
@@ -432,8 +561,25 @@ int gemma_model::run_steps_profiled(int steps) {
 // CUDA graph once and replayed per token (a cooperative launch that cannot be captured is
 // launched directly).
 int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
-    if (!token_embd_ || k_cache_.empty()) return GGB_ERR_ARG;
+    if (kq_mode_) {
+        if (!kq_embd_.packed || !output_norm_ || k_cache_.empty() || plan_.size > 1) return GGB_ERR_ARG;
+        for (const kq_mat &w : kq_layers_)
+            if (!w.packed) return GGB_ERR_ARG;
+        for (const gemma_layer &l : layers_)
+            if (!l.attn_norm || !l.ffn_norm) return GGB_ERR_ARG;
+        fused = false; // the persistent kernel streams Q4_0 / Q8_0 only
+    } else if (!token_embd_ || k_cache_.empty()) {
+        return GGB_ERR_ARG;
+    }
     GM_TRY(alloc_buffers());
+    if (kq_mode_ && !kq_q8_) {
+        const gemma_config &c = cfg_;
+        const int64_t kmax = std::max<int64_t>(std::max<int64_t>(c.n_embd, c.n_ff), (int64_t)c.n_head * c.head_dim);
+        GM_TRY(ggb_buffer_alloc((size_t)c.n_embd * 4, (void **)&kq_xn_));
+        GM_TRY(ggb_buffer_alloc((size_t)c.n_ff * 4, (void **)&kq_gate_));
+        GM_TRY(ggb_buffer_alloc((size_t)c.n_ff * 4, (void **)&kq_up_));
+        GM_TRY(ggb_buffer_alloc(ggb_type_row_bytes(GGB_TYPE_Q8_K, kmax), &kq_q8_));
+    }
     capture_acts_ = capture_acts;
     ggb_graph_free(graph_);
     graph_ = nullptr;
@@ -441,7 +587,7 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
     decoder_ = nullptr;
     built_ = false;
     GM_TRY(ggb_sync());
-    GM_TRY(make_shards());
+    if (!kq_mode_) GM_TRY(make_shards());
     if (plan_.size > 1) fused = tp_fused_; // multi-GPU: persistent kernel with peer stores, or ops + NCCL
     if (fused) {
         const gemma_config &c = cfg_;
@@ -465,7 +611,7 @@ int gemma_model::build_compute_graph(bool capture_acts, bool fused) {
     const int rcb = ggb_capture_begin();
     if (rcb == 0) {
         const int rc = decoder_ ? ggb_decoder_step(decoder_)
-                                : (plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step());
+                                : (kq_mode_ ? emit_decode_step_kq() : plan_.size > 1 ? emit_decode_step_tp() : emit_decode_step());
         ggb_graph *g = nullptr;
         const int rc2 = ggb_capture_end(&g);
         if (rc == 0 && rc2 == 0) {
@@ -602,6 +748,7 @@ int gemma_model::alloc_prefill(int T) {
 int gemma_model::prefill(const token_id *tokens, int T, int32_t pos0, token_id *next) {
     const gemma_config &c = cfg_;
     if (!tokens || T <= 0 || pos0 < 0 || pos0 + T > c.n_ctx || !built_ || plan_.size > 1) return GGB_ERR_ARG;
+    if (kq_mode_) return GGB_ERR_UNSUPPORTED; // the GEMM prefill dequantises Q4_0 / Q8_0; a K-quant model prefills token by token
     GM_TRY(alloc_prefill(T));
     const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab, t = T;
     const int64_t QD = (int64_t)c.n_head * c.head_dim;

@@ -80,6 +80,12 @@ class gemma_model {
     // weights: synthetic (generated on the device) or uploaded tensor by tensor
     int init_synthetic_weights();
     int set_tensor(int tensor_id, const void *host_data, int64_t nbytes);
+    // K-quant files (the author's q4_k_m GGUF: matrices Q4_K / Q6_K, norms F32): a matrix of type GGB_TYPE_Q4_K or
+    // GGB_TYPE_Q6_K puts the model into K-QUANT MODE - every matrix must then be a K-quant; the token step is lowered
+    // operator by operator (quantize_row_q8_K, the packed K-quant mat-vecs, get_rows on the blocks: csrc/kquants.cu) and
+    // captured into a CUDA graph like the Q4_0 / Q8_0 per-operator form.  Other types behave like set_tensor.
+    int set_tensor_typed(int tensor_id, int type, const void *host_data, int64_t nbytes);
+    bool kquant_mode() const { return kq_mode_; }
     int init_kv_cache();                       // ref: :361-401
     int fill_kv_cache_synthetic(uint64_t seed); // bandwidth sweeps
     // ref: :665-747.  fused = true lowers the token step to the persistent decode kernel
@@ -122,6 +128,7 @@ class gemma_model {
     int alloc_buffers();
     int emit_decode_step(); // the op sequence of one token
     int emit_decode_step_tp(); // same, row-sharded over tp_size ranks with allgathers at the layer boundaries
+    int emit_decode_step_kq(); // same node list on K-quant weights (Q8_K activations)
     int make_shards();
     int launch_step();      // graph replay, or a direct cooperative launch
     void free_all();
@@ -133,6 +140,19 @@ class gemma_model {
     std::vector<gemma_layer> layers_;
     std::vector<void *> k_cache_, v_cache_; // ref: kv_cache (src/gemma_model.h:83-97)
     size_t weight_bytes_ = 0;
+
+    // K-quant mode: matrices as packed K-quant copies (+ the raw token_embd blocks for get_rows)
+    struct kq_mat {
+        int type = 0;
+        void *raw = nullptr, *packed = nullptr;
+        int64_t rows = 0, cols = 0;
+    };
+    bool kq_mode_ = false;
+    kq_mat kq_embd_;
+    std::vector<kq_mat> kq_layers_; // [n_layer][7]: q, k, v, o, gate, up, down
+    float *kq_xn_ = nullptr, *kq_gate_ = nullptr, *kq_up_ = nullptr;
+    void *kq_q8_ = nullptr; // one Q8_K activation row (longest K)
+    int kq_mv(const kq_mat &w, const float *x, float *dst); // quantize_row_q8_K(x) then the packed mat-vec
 
     // device-resident step state: [token, pos, pos_step]
     int32_t *state_ = nullptr, *history_ = nullptr;

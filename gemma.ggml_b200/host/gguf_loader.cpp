@@ -214,8 +214,11 @@ int gguf_gemma_config(const gguf_file &f, int32_t n_ctx, gemma_config *cfg, std:
     double base;
     if (f.get_f64("gemma.rope.freq_base", &base)) cfg->rope_base = (float)base;
     cfg->wtype = emb->type;
-    if (cfg->wtype != GGB_TYPE_Q4_0 && cfg->wtype != GGB_TYPE_Q8_0)
-        return fail("token_embd.weight has ggml type " + std::to_string(emb->type) + ": this path runs Q4_0 / Q8_0 models");
+    // Q4_0 / Q8_0: the resident decode path; Q4_K / Q6_K (the token_embd of a q4_k_m file is Q6_K): K-quant mode
+    if (cfg->wtype != GGB_TYPE_Q4_0 && cfg->wtype != GGB_TYPE_Q8_0 && cfg->wtype != GGB_TYPE_Q4_K && cfg->wtype != GGB_TYPE_Q6_K)
+        return fail("token_embd.weight has ggml type " + std::to_string(emb->type) + ": this path runs Q4_0 / Q8_0 / Q4_K / Q6_K models");
+    if ((cfg->wtype == GGB_TYPE_Q4_K || cfg->wtype == GGB_TYPE_Q6_K) && (E % 256 || F % 256 || (H * klen) % 256))
+        return fail("K-quant model with a row length that is not a multiple of 256");
     if ((int64_t)E != emb->dims[0]) return fail("token_embd.weight width != gemma.embedding_length");
     return 0;
 }
@@ -235,11 +238,15 @@ int gguf_bind_tensors(const gguf_file &f, gemma_model &m, std::string *err) {
     auto bind = [&](const std::string &name, int id, bool matrix) -> int {
         const gguf_tensor_info *t = f.find(name);
         if (!t) { if (err) *err = "tensor " + name + " not in the file"; return -1; }
-        if (matrix ? t->type != c.wtype : t->type != 0) {
+        // a Q4_0 / Q8_0 file holds ONE matrix type (the resident decode path streams it); a K-quant file (q4_k_m: Q4_K with
+        // some Q6_K tensors) may mix Q4_K and Q6_K tensor by tensor
+        const bool kq_file = c.wtype == GGB_TYPE_Q4_K || c.wtype == GGB_TYPE_Q6_K;
+        const bool ok = !matrix ? t->type == 0 : kq_file ? (t->type == GGB_TYPE_Q4_K || t->type == GGB_TYPE_Q6_K) : t->type == (uint32_t)c.wtype;
+        if (!ok) {
             if (err) *err = "tensor " + name + " has ggml type " + std::to_string(t->type) + " (expected " + std::to_string(matrix ? c.wtype : 0) + ")";
             return -1;
         }
-        const int rc = m.set_tensor(id, f.data(*t), (int64_t)t->nbytes);
+        const int rc = m.set_tensor_typed(id, (int)t->type, f.data(*t), (int64_t)t->nbytes);
         if (rc && err) *err = "tensor " + name + ": shape does not match the hyper-parameters (" + std::to_string(t->nbytes) + " bytes)";
         return rc;
     };

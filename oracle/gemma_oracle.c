@@ -133,6 +133,33 @@ static void gen_rows(void *a) {
     const size_t rs = orc_row_size(t->type, t->cols);
     for (int64_t r = j->r0; r < j->r1; r++) {
         const float sigma = j->tid == ORC_T_TOKEN_EMBD ? j->m->cfg.sigma_embd : j->m->cfg.sigma_mat;
+        if (t->type == ORC_TYPE_Q4_K || t->type == ORC_TYPE_Q6_K) {
+            /* K-quant weights: every bit pattern is a valid block, so the row is counter-based random bytes with the
+             * fp16 super-scales set to sigma-sized values (no K-quant quantiser is restated: the search-based
+             * make_qkx2_quants of ggml is not on the inference path) */
+            unsigned char *b = (unsigned char *)t->data + r * rs;
+            const uint64_t key = j->m->cfg.seed * 0x9E3779B97F4A7C15ull + (uint64_t)j->tid * 0xD1B54A32D192ED03ull + (uint64_t)r;
+            for (size_t i = 0; i < rs; i += 8) {
+                uint64_t z = key + (uint64_t)i * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                memcpy(b + i, &z, rs - i < 8 ? rs - i : 8);
+            }
+            const int64_t nb = t->cols / ORC_QK_K;
+            for (int64_t i = 0; i < nb; i++) {
+                if (t->type == ORC_TYPE_Q4_K) {
+                    orc_block_q4_K *blk = (orc_block_q4_K *)b + i;
+                    const float d = sigma * (1.0f / 256.0f) * (float)(1 + (blk->d & 7));
+                    blk->d = orc_fp32_to_fp16(d);
+                    blk->dmin = orc_fp32_to_fp16(7.5f * d); /* E[d sc q] = E[dmin m]: zero-mean weights */
+                } else {
+                    orc_block_q6_K *blk = (orc_block_q6_K *)b + i;
+                    blk->d = orc_fp32_to_fp16(sigma * (1.0f / 1024.0f) * (float)(1 + (blk->d & 7)));
+                }
+            }
+            continue;
+        }
         orc_synth_row(j->m->cfg.seed, (uint64_t)j->tid, r, t->cols, sigma, 0.0f, row);
         if (t->type == ORC_TYPE_Q4_0) orc_quantize_row_q4_0(row, (orc_block_q4_0 *)((char *)t->data + r * rs), t->cols);
         else orc_quantize_row_q8_0(row, (orc_block_q8_0 *)((char *)t->data + r * rs), t->cols);
@@ -145,7 +172,8 @@ static void make_matrix(orc_model *m, int tid, int64_t rows, int64_t cols) {
     otensor *t = &m->t[tid];
     t->rows = rows;
     t->cols = cols;
-    t->type = m->cfg.wtype;
+    /* wtype Q4_K = the mix of a q4_k_m file in miniature: matrices Q4_K, the (tied) embedding / output matrix Q6_K */
+    t->type = (m->cfg.wtype == ORC_TYPE_Q4_K && tid == ORC_T_TOKEN_EMBD) ? ORC_TYPE_Q6_K : m->cfg.wtype;
     t->nbytes = (int64_t)(orc_row_size(t->type, cols) * (size_t)rows);
     t->data = malloc((size_t)t->nbytes);
     const int64_t chunk = (rows + m->n_threads * 4 - 1) / (m->n_threads * 4);
@@ -298,9 +326,14 @@ void orc_hpc_mul_mat(orc_model *m, int64_t ne01, int64_t ne11, int64_t ne12, int
  * x: [T][K] f32, out: [T][N] f32. */
 static void node_mul_mat(orc_model *m, const otensor *w, const float *x, int T, float *out, int order) {
     const int64_t K = w->cols, N = w->rows;
-    const size_t rs = orc_row_size(ORC_TYPE_Q8_0, K);
-    char *wdata = (char *)malloc(rs * (size_t)T);
-    for (int t = 0; t < T; t++) orc_quantize_row_q8_0(x + (size_t)t * K, (orc_block_q8_0 *)(wdata + rs * t), K);
+    /* vec_dot_type of the weight type: Q8_0 for Q4_0 / Q8_0, Q8_K for the K-quants */
+    const int kq = w->type == ORC_TYPE_Q4_K || w->type == ORC_TYPE_Q6_K;
+    const size_t rs = orc_row_size(kq ? ORC_TYPE_Q8_K : ORC_TYPE_Q8_0, K);
+    char *wdata = (char *)calloc(rs, (size_t)T);
+    for (int t = 0; t < T; t++) {
+        if (kq) orc_quantize_row_q8_K(x + (size_t)t * K, (orc_block_q8_K *)(wdata + rs * t), K);
+        else orc_quantize_row_q8_0(x + (size_t)t * K, (orc_block_q8_0 *)(wdata + rs * t), K);
+    }
     orc_hpc_mul_mat(m, N, T, 1, (int64_t)orc_row_size(w->type, K), T, N * 4, N * 4 * T, rs, K, w->data, out,
                     w->type, wdata, order);
     free(wdata);

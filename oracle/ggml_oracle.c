@@ -93,6 +93,9 @@ size_t orc_row_size(int type, int64_t k) {
     case ORC_TYPE_F16: return (size_t)k * 2;
     case ORC_TYPE_Q4_0: return (size_t)(k / ORC_QK) * sizeof(orc_block_q4_0);
     case ORC_TYPE_Q8_0: return (size_t)(k / ORC_QK) * sizeof(orc_block_q8_0);
+    case ORC_TYPE_Q4_K: return (size_t)(k / ORC_QK_K) * sizeof(orc_block_q4_K);
+    case ORC_TYPE_Q6_K: return (size_t)(k / ORC_QK_K) * sizeof(orc_block_q6_K);
+    case ORC_TYPE_Q8_K: return (size_t)(k / ORC_QK_K) * sizeof(orc_block_q8_K);
     default: return 0;
     }
 }
@@ -169,6 +172,8 @@ void orc_dequantize_row_q8_0(const orc_block_q8_0 *x, float *y, int64_t k) {
 void orc_dequantize_row(int type, const void *x, float *y, int64_t k) {
     if (type == ORC_TYPE_Q4_0) orc_dequantize_row_q4_0((const orc_block_q4_0 *)x, y, k);
     else if (type == ORC_TYPE_Q8_0) orc_dequantize_row_q8_0((const orc_block_q8_0 *)x, y, k);
+    else if (type == ORC_TYPE_Q4_K) orc_dequantize_row_q4_K((const orc_block_q4_K *)x, y, k);
+    else if (type == ORC_TYPE_Q6_K) orc_dequantize_row_q6_K((const orc_block_q6_K *)x, y, k);
     else if (type == ORC_TYPE_F32) memcpy(y, x, (size_t)k * 4);
     else if (type == ORC_TYPE_F16) {
         for (int64_t i = 0; i < k; i++) y[i] = orc_fp16_to_fp32(((const uint16_t *)x)[i]);
@@ -239,6 +244,10 @@ void orc_vec_dot(int type, int order, int n, float *s, const void *vx, const voi
         orc_vec_dot_q8_0_q8_0(n, s, vx, vy);
     } else if (type == ORC_TYPE_F16) {
         orc_vec_dot_f16(n, s, (const uint16_t *)vx, (const uint16_t *)vy);
+    } else if (type == ORC_TYPE_Q4_K) {
+        orc_vec_dot_q4_K_q8_K(n, s, vx, vy);
+    } else if (type == ORC_TYPE_Q6_K) {
+        orc_vec_dot_q6_K_q8_K(n, s, vx, vy);
     } else {
         *s = NAN;
     }

@@ -1,4 +1,4 @@
-"""Writes a small synthetic Gemma GGUF (Q4_0 / Q8_0 matrices from the oracle's generator, f32 norms, a toy vocabulary)
+"""Writes a small synthetic Gemma GGUF (Q4_0 / Q8_0 / K-quant matrices from the oracle's generator, f32 norms, a toy vocabulary)
 with gguf-py's GGUFWriter - the file format the reference loads (ref: src/gemma_model.cpp:19-51)."""
 import numpy as np
 
@@ -24,7 +24,9 @@ def write_gemma_gguf(path, om, dims, wtype, eos_id=1, bos_id=2):
     w.add_token_types([1] * len(toks))
     w.add_bos_token_id(bos_id)
     w.add_eos_token_id(eos_id)
-    qt = gguf.GGMLQuantizationType.Q4_0 if wtype == O.TYPE_Q4_0 else gguf.GGMLQuantizationType.Q8_0
+    QT = gguf.GGMLQuantizationType
+    # (Q4_0 and Q4_K are both 4.5 bits per weight: the family comes from the model's wtype, the member from the block size)
+    block = {144: (QT.Q4_K, 256), 210: (QT.Q6_K, 256)} if wtype in (O.TYPE_Q4_K, O.TYPE_Q6_K) else {18: (QT.Q4_0, 32), 34: (QT.Q8_0, 32)}
     names = ["token_embd.weight", "output_norm.weight"]
     per = ["attn_norm", "attn_q", "attn_k", "attn_v", "attn_output", "ffn_norm", "ffn_gate", "ffn_up", "ffn_down"]
     for il in range(dims["n_layer"]):
@@ -34,6 +36,8 @@ def write_gemma_gguf(path, om, dims, wtype, eos_id=1, bos_id=2):
         if "norm" in name:
             w.add_tensor(name, raw.view(np.float32).copy())
         else:
+            # the ggml type of THIS tensor from its block size (a K-quant model mixes Q4_K and Q6_K tensors)
+            qt = next(t for bs, (t, per) in block.items() if raw.nbytes == rows * (cols // per) * bs)
             w.add_tensor(name, raw.reshape(rows, -1).copy(), raw_dtype=qt)
     w.write_header_to_file()
     w.write_kv_data_to_file()

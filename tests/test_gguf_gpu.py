@@ -50,3 +50,23 @@ def test_generation_stops_at_eos(gpu, tmp_path):
     assert list(ids) == list(stream[:first + 1])  # ends with the EOS id, nothing after it
     m.close()
     om.close()
+
+
+def test_k_quant_gguf_loads_into_k_quant_mode(gpu, tmp_path):
+    """a q4_k_m-like file (Q4_K matrices, Q6_K token_embd): loaded, run operator by operator on the K-quant kernels,
+    same tokens and logits as the oracle on the same blocks"""
+    dims = dict(n_embd=256, n_layer=2, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=512, n_ctx=48)
+    om = O.Model(wtype=O.TYPE_Q4_K, sigma_embd=0.005, **dims)
+    path = os.path.join(tmp_path, "tiny_q4_k_m.gguf")
+    write_gemma_gguf(path, om, dims, O.TYPE_Q4_K)
+    m = gpu.GemmaModel.load_model_from_file(path)
+    assert m.kquant_mode and all(getattr(m.cfg, k) == v for k, v in dims.items())
+    m.init_kv_cache()
+    m.build_compute_graph()
+    prompt = ((1 + 7919 * np.arange(7)) % dims["n_vocab"]).astype(np.int32)
+    got, _, _ = m.generate(prompt, 8)
+    want, _, _ = om.generate(prompt, 8, O.REF)
+    assert np.array_equal(got, want)
+    assert np.array_equal(m.logits().view(np.uint32), om.capture("result_output").view(np.uint32))
+    m.close()
+    om.close()

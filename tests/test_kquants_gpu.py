@@ -118,3 +118,44 @@ def test_q6_K_device_operators_raw_and_packed_layouts(gpu, n, k, t):
     gpu.check(L.ggb_op_mul_mat_q6k_packed(packed.ptr, n, k, ad.ptr, act.shape[1], t, dst.ptr, n))
     gpu.sync()
     assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))
+
+
+# ------------------------------------------------------------------ a K-quant MODEL (the author's q4_k_m mix in miniature)
+KQ_MODELS = {
+    # Q4_K matrices, Q6_K tied embedding / output matrix (what a q4_k_m file holds)
+    "mqa-q4_K": (O.TYPE_Q4_K, dict(n_embd=256, n_layer=2, n_head=4, n_head_kv=1, head_dim=64, n_ff=1024, n_vocab=512, n_ctx=48)),
+    # all Q6_K, MHA, n_head * head_dim != n_embd, K = 2048 in the down projection (eight super-blocks)
+    "mha-q6_K": (O.TYPE_Q6_K, dict(n_embd=512, n_layer=2, n_head=4, n_head_kv=4, head_dim=256, n_ff=2048, n_vocab=768, n_ctx=40)),
+}
+
+
+@pytest.mark.parametrize("name", list(KQ_MODELS))
+def test_kquant_model_generate_matches_oracle_bitwise(gpu, name):
+    """K-quant mode of the host model (set_tensor_typed -> packed K-quant mat-vecs, quantize_row_q8_K, get_rows on the
+    blocks, the fp32 operators of the Q4_0 / Q8_0 path) against the oracle running the same node list on the same
+    blocks: tokens, every captured intermediate of every layer and the logits, bit for bit."""
+    wtype, dims = KQ_MODELS[name]
+    om = O.Model(wtype=wtype, sigma_embd=0.005, **dims)
+    cfg = gpu.make_config(wtype=wtype, sigma_embd=0.005, **dims)
+    m = gpu.GemmaModel(cfg)
+    for tid in range(2 + 9 * dims["n_layer"]):
+        raw, rows, cols = om.tensor(tid)
+        is_norm = tid == 1 or (tid >= 2 and (tid - 2) % 9 in (0, 5))
+        if is_norm:
+            m.set_tensor_typed(tid, gpu.TYPE_F32, raw)
+        else:
+            ttype = gpu.TYPE_Q6_K if raw.nbytes == rows * (cols // 256) * 210 else gpu.TYPE_Q4_K
+            m.set_tensor_typed(tid, ttype, raw)
+    assert m.kquant_mode
+    m.init_kv_cache()
+    m.build_compute_graph(capture_acts=True)
+    assert not m.is_fused
+    prompt = ((1 + 7919 * np.arange(7)) % dims["n_vocab"]).astype(np.int32)
+    toks, _, _ = m.generate(prompt, 10)
+    otoks, _, _ = om.generate(prompt, 10, O.REF)
+    assert np.array_equal(toks, otoks), (toks, otoks)
+    assert np.array_equal(bits(m.logits()), bits(om.capture("result_output")))
+    for il in range(dims["n_layer"]):
+        for cap in ("kqv_out", "sa_out", "ffn_act", "l_out"):
+            assert np.array_equal(bits(m.capture(cap, il)), bits(om.capture(cap, il))), (cap, il)
+    m.close(); om.close()
