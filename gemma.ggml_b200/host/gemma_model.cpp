@@ -194,6 +194,7 @@ void gemma_model::free_all() {
 // projection), output_norm, and nine tensors per block.  Here every matrix is generated and
 // quantised ON the device with the shared counter-based generator (seed, tensor id).
 int gemma_model::init_synthetic_weights() {
+    if (kq_mode_ || (cfg_.wtype != GGB_TYPE_Q4_0 && cfg_.wtype != GGB_TYPE_Q8_0)) return GGB_ERR_UNSUPPORTED; // the device generator makes Q4_0 / Q8_0
     const gemma_config &c = cfg_;
     const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
     const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
@@ -242,6 +243,7 @@ int gemma_model::set_tensor(int tensor_id, const void *host_data, int64_t nbytes
     const int64_t E = c.n_embd, F = c.n_ff, V = c.n_vocab;
     const int64_t QD = (int64_t)c.n_head * c.head_dim, KD = (int64_t)c.n_head_kv * c.head_dim;
     auto mat = [&](ggb_weight **slot, int64_t rows, int64_t cols) -> int {
+        if (kq_mode_ || (c.wtype != GGB_TYPE_Q4_0 && c.wtype != GGB_TYPE_Q8_0)) return GGB_ERR_ARG; // K-quant matrices: set_tensor_typed
         const int64_t need = rows * (cols / 32) * (c.wtype == GGB_TYPE_Q4_0 ? 18 : 34);
         if (nbytes != need) return GGB_ERR_ARG;
         if (*slot) weight_bytes_ -= ggb_weight_algorithmic_bytes(*slot);
@@ -285,6 +287,9 @@ int gemma_model::set_tensor_typed(int tensor_id, int type, const void *host_data
     }
     const gemma_config &c = cfg_;
     if (plan_.size > 1) return GGB_ERR_UNSUPPORTED; // K-quant mode is single-GPU
+    if (token_embd_) return GGB_ERR_ARG;            // a model is either Q4_0 / Q8_0 or K-quant, not both
+    for (const gemma_layer &l : layers_)
+        if (l.attn_q || l.attn_k || l.attn_v || l.attn_output || l.ffn_gate || l.ffn_up || l.ffn_down) return GGB_ERR_ARG;
     if (built_ || graph_ || decoder_) {
         ggb_sync();
         ggb_graph_free(graph_);
