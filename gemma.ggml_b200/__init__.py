@@ -89,6 +89,7 @@ _CUDA_SIG = {
     "ggb_op_mul_mat_blocks": (i32, [i32, vp, i64, i64, i64, vp, i64, i64, vp, i64]),
     "ggb_op_q4k_repack": (i32, [vp, i64, i64, i64, vp]),
     "ggb_op_mul_mat_q4k_packed": (i32, [vp, i64, i64, vp, i64, i64, vp, i64]),
+    "ggb_op_mul_mat_kq_packed_f32": (i32, [i32, vp, i64, i64, vp, i64, vp, i64]),
     "ggb_op_get_rows_blocks": (i32, [i32, vp, i64, i64, i64, vp, i64, f32, vp]),
     "ggb_q6k_packed_bytes": (sz, [i64, i64]), "ggb_op_q6k_repack": (i32, [vp, i64, i64, i64, vp]),
     "ggb_op_mul_mat_q6k_packed": (i32, [vp, i64, i64, vp, i64, i64, vp, i64]),

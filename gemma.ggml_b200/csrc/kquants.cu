@@ -187,15 +187,10 @@ raw_matvec_kernel(const uint8_t *__restrict__ w, int64_t rows, int64_t nb01, int
     if (lane == 0) dst[(int64_t)blockIdx.y * dst_stride + row] = s;
 }
 
-// one warp per 256-element block; lane L holds elements 8L..8L+7
-__global__ void __launch_bounds__(kWarps * 32)
-quantize_q8_K_kernel(const float *__restrict__ x, int64_t n_blocks, uint8_t *__restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t b = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
-    if (b >= n_blocks) return;
-    const float4 f0 = *reinterpret_cast<const float4 *>(x + b * kQK + 8 * lane);
-    const float4 f1 = *reinterpret_cast<const float4 *>(x + b * kQK + 8 * lane + 4);
-    const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+// [UPSTREAM] quantize_row_q8_K_reference for one 256-element block spread over a warp: lane L holds elements 8L..8L+7.
+// Returns the lane's eight codes and the block's d (0 for an all-zero block); shared by the stand-alone quantiser and by
+// the mat-vec kernels that quantise their fp32 activation row while they stage it.
+__device__ __forceinline__ float q8k_quantize_lane(const float (&v)[8], int lane, int (&q)[8]) {
     // first element attaining max |x| (strict > in the scalar loop)
     float amax = 0.0f, mx = 0.0f;
     int idx = 0;
@@ -210,29 +205,42 @@ quantize_q8_K_kernel(const float *__restrict__ x, int64_t n_blocks, uint8_t *__r
         const int oi = __shfl_xor_sync(0xffffffffu, idx, off);
         if (oa > amax || (oa == amax && oi < idx)) { amax = oa; mx = om; idx = oi; }
     }
-    uint8_t *o = out + b * kQ8K;
     if (!(amax > 0.0f)) { // "if (!amax)": all zero (a NaN block cannot reach amax > 0 either; ggml leaves it at 0)
-        if (lane == 0) *reinterpret_cast<float *>(o) = 0.0f;
-        *reinterpret_cast<uint32_t *>(o + 4 + 8 * lane) = 0u;
-        *reinterpret_cast<uint32_t *>(o + 8 + 8 * lane) = 0u;
-        if (lane < 8) *reinterpret_cast<uint32_t *>(o + 260 + 4 * lane) = 0u;
-        return;
+#pragma unroll
+        for (int l = 0; l < 8; l++) q[l] = 0;
+        return 0.0f;
     }
     const float iscale = __fdiv_rn(-128.0f, mx);
-    int q[8], s = 0;
 #pragma unroll
     for (int l = 0; l < 8; l++) {
         const float val = __fadd_rn(__fmul_rn(iscale, v[l]), 12582912.0f); // nearest_int: round half to even
         q[l] = min(127, (__float_as_int(val) & 0x007fffff) - 0x00400000);
-        s += q[l];
     }
+    return __fdiv_rn(1.0f, iscale);
+}
+
+// one warp per 256-element block
+__global__ void __launch_bounds__(kWarps * 32)
+quantize_q8_K_kernel(const float *__restrict__ x, int64_t n_blocks, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    const float4 f0 = *reinterpret_cast<const float4 *>(x + b * kQK + 8 * lane);
+    const float4 f1 = *reinterpret_cast<const float4 *>(x + b * kQK + 8 * lane + 4);
+    const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+    int q[8];
+    const float d = q8k_quantize_lane(v, lane, q);
+    uint8_t *o = out + b * kQ8K;
+    int s = 0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) s += q[l];
     const uint32_t p0 = (q[0] & 0xff) | ((q[1] & 0xff) << 8) | ((q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
     const uint32_t p1 = (q[4] & 0xff) | ((q[5] & 0xff) << 8) | ((q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
     *reinterpret_cast<uint32_t *>(o + 4 + 8 * lane) = p0;
     *reinterpret_cast<uint32_t *>(o + 8 + 8 * lane) = p1;
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     if (!(lane & 1)) *reinterpret_cast<int16_t *>(o + 260 + lane) = (int16_t)s; // bsums[lane / 2]
-    if (lane == 0) *reinterpret_cast<float *>(o) = __fdiv_rn(1.0f, iscale);
+    if (lane == 0) *reinterpret_cast<float *>(o) = d;
 }
 
 
@@ -274,6 +282,9 @@ __global__ void __launch_bounds__(256) q4k_repack_kernel(const uint8_t *__restri
 }
 
 // grid (x: row groups, strided; y: activation row); 8 warps; dynamic shared memory nb * kActSB
+// F32ACT: `act` is the fp32 activation row (pitch row_size bytes); the CTA quantises it to Q8_K itself while staging
+// (ggml's INIT stage of the mul_mat node, fused: the stand-alone quantiser launch per node goes away)
+template <bool F32ACT>
 __global__ void __launch_bounds__(256)
 q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uint8_t *__restrict__ act, int64_t row_size,
                   float *__restrict__ dst, int64_t dst_stride) {
@@ -281,6 +292,29 @@ q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *y = act + (int64_t)blockIdx.y * row_size;
     // ---- stage the activation row, transposed
+    if (F32ACT) {
+        const float *xf = reinterpret_cast<const float *>(y);
+        for (int sb = warp; sb < nb; sb += kWarps) { // a warp quantises one super-block at a time: lane = elements 8L..8L+7
+            const float4 f0 = *reinterpret_cast<const float4 *>(xf + sb * kQK + 8 * lane);
+            const float4 f1 = *reinterpret_cast<const float4 *>(xf + sb * kQK + 8 * lane + 4);
+            const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            int q[8];
+            const float d = q8k_quantize_lane(v, lane, q);
+            // element 8L + l = sub-block j = L / 4, group g = L % 4, lane-sum index l: byte g of qT[j][l]
+            const int j = lane >> 2, g = lane & 3;
+            uint8_t *base = s_act + sb * kActSB + j * 16 + g;
+            int ssum = 0;
+#pragma unroll
+            for (int l = 0; l < 8; l++) {
+                base[(l >> 2) * 128 + (l & 3) * 4] = (uint8_t)q[l];
+                ssum += q[l];
+            }
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+            if (g == 0) *reinterpret_cast<int *>(s_act + sb * kActSB + 256 + 4 * j) = ssum; // bsums[2j] + bsums[2j + 1]
+            if (lane == 0) *reinterpret_cast<float *>(s_act + sb * kActSB + 288) = d;
+        }
+    } else {
     for (int i = tid; i < nb * 64; i += 256) { // word (sb, j, l)
         const int sb = i >> 6, j = (i >> 3) & 7, l = i & 7;
         const uint8_t *q8 = y + (int64_t)sb * kQ8K + 4 + 32 * j + l;
@@ -296,6 +330,7 @@ q4k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
         } else {
             *reinterpret_cast<uint32_t *>(s_act + sb * kActSB + 288) = ld_u32(yb);
         }
+    }
     }
     __syncthreads();
     // lane (s, c): super-block s of EIGHT, sub-blocks 2c and 2c + 1 (64 elements per lane: the fold runs over four lanes
@@ -414,12 +449,28 @@ __global__ void __launch_bounds__(256) q6k_repack_kernel(const uint8_t *__restri
     if (j == 0) *reinterpret_cast<uint16_t *>(orow + (int64_t)nb * 272 + 2 * sb) = *reinterpret_cast<const uint16_t *>(x + 208);
 }
 
+template <bool F32ACT>
 __global__ void __launch_bounds__(256)
 q6k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uint8_t *__restrict__ act, int64_t row_size,
                   float *__restrict__ dst, int64_t dst_stride) {
     extern __shared__ __align__(16) uint8_t s_act[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint8_t *y = act + (int64_t)blockIdx.y * row_size;
+    if (F32ACT) {
+        const float *xf = reinterpret_cast<const float *>(y);
+        for (int sb = warp; sb < nb; sb += kWarps) {
+            const float4 f0 = *reinterpret_cast<const float4 *>(xf + sb * kQK + 8 * lane);
+            const float4 f1 = *reinterpret_cast<const float4 *>(xf + sb * kQK + 8 * lane + 4);
+            const float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            int q[8];
+            const float d = q8k_quantize_lane(v, lane, q);
+            // element 8L + l = sub-block j = L / 2 (of sixteen), group g = L % 2: word l / 2, byte 2 (l % 2) + g
+            uint8_t *base = s_act + sb * kActSB6 + (lane >> 1) * 16 + (lane & 1);
+#pragma unroll
+            for (int l = 0; l < 8; l++) base[(l >> 1) * 4 + (l & 1) * 2] = (uint8_t)q[l];
+            if (lane == 0) *reinterpret_cast<float *>(s_act + sb * kActSB6 + 256) = d;
+        }
+    } else {
     for (int i = tid; i < nb * 64; i += 256) { // word (sb, j, p)
         const int sb = i >> 6, j = (i >> 2) & 15, p = i & 3;
         const uint8_t *q8 = y + (int64_t)sb * kQ8K + 4 + 16 * j + 2 * p;
@@ -427,6 +478,7 @@ q6k_packed_kernel(const uint8_t *__restrict__ w, int64_t rows, int nb, const uin
         *reinterpret_cast<uint32_t *>(s_act + sb * kActSB6 + j * 16 + p * 4) = v;
     }
     for (int sb = tid; sb < nb; sb += 256) *reinterpret_cast<uint32_t *>(s_act + sb * kActSB6 + 256) = ld_u32(y + (int64_t)sb * kQ8K);
+    }
     __syncthreads();
     // lane (s, c): super-block s of four, sub-blocks 2c and 2c + 1 (32 elements per lane); the fold runs over the 8-lane group
     const int s = lane >> 3, c = lane & 7;
@@ -562,25 +614,44 @@ int ggb_op_q4k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, vo
     return GGB_OK;
 }
 
-int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
-                              float *dst, int64_t dst_stride) {
+static int launch_packed(int type, bool f32act, const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size,
+                         int64_t T, float *dst, int64_t dst_stride) {
     GGB_REQUIRE_INIT();
-    GGB_CHECK_ARG(packed && act && dst && rows > 0 && T > 0 && K > 0 && K % kQK == 0, "mul_mat_q4k_packed: bad arguments");
+    GGB_CHECK_ARG(packed && act && dst && rows > 0 && T > 0 && K > 0 && K % kQK == 0, "mul_mat_packed: bad arguments");
     const int nb = (int)(K / kQK);
-    GGB_CHECK_ARG(row_size >= (int64_t)nb * kQ8K && row_size % 4 == 0, "mul_mat_q4k_packed: activation row pitch %lld", (long long)row_size);
-    const size_t smem = (size_t)nb * kActSB;
-    GGB_CHECK_ARG(smem <= 200 * 1024, "mul_mat_q4k_packed: K %lld too long for the staged activation row", (long long)K);
-    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(q4k_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t need = f32act ? K * 4 : (int64_t)nb * kQ8K;
+    GGB_CHECK_ARG(row_size >= need && row_size % (f32act ? 16 : 4) == 0, "mul_mat_packed: activation row pitch %lld", (long long)row_size);
+    const bool q4 = type == GGB_TYPE_Q4_K;
+    const size_t smem = (size_t)nb * (q4 ? kActSB : kActSB6);
+    GGB_CHECK_ARG(smem <= 200 * 1024, "mul_mat_packed: K %lld too long for the staged activation row", (long long)K);
+    auto kern = q4 ? (f32act ? q4k_packed_kernel<true> : q4k_packed_kernel<false>)
+                   : (f32act ? q6k_packed_kernel<true> : q6k_packed_kernel<false>);
+    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t groups = (rows + kWarps - 1) / kWarps;
     const unsigned gx = (unsigned)(groups < 148 * 8 ? groups : 148 * 8);
     for (int64_t t0 = 0; t0 < T; t0 += 65535) {
         const dim3 grid(gx, (unsigned)(T - t0 < 65535 ? T - t0 : 65535));
-        q4k_packed_kernel<<<grid, 256, smem, ggb_cuda_stream()>>>((const uint8_t *)packed, rows, nb,
-                                                                  (const uint8_t *)act + t0 * row_size, row_size,
-                                                                  dst + t0 * dst_stride, dst_stride);
+        kern<<<grid, 256, smem, ggb_cuda_stream()>>>((const uint8_t *)packed, rows, nb, (const uint8_t *)act + t0 * row_size,
+                                                     row_size, dst + t0 * dst_stride, dst_stride);
         GGB_LAUNCH_CHECK();
     }
     return GGB_OK;
+}
+
+int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
+                              float *dst, int64_t dst_stride) {
+    return launch_packed(GGB_TYPE_Q4_K, false, packed, rows, K, act, row_size, T, dst, dst_stride);
+}
+
+int ggb_op_mul_mat_q6k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
+                              float *dst, int64_t dst_stride) {
+    return launch_packed(GGB_TYPE_Q6_K, false, packed, rows, K, act, row_size, T, dst, dst_stride);
+}
+
+int ggb_op_mul_mat_kq_packed_f32(int type, const void *packed, int64_t rows, int64_t K, const float *x, int64_t T, float *dst,
+                                 int64_t dst_stride) {
+    GGB_CHECK_ARG(type == GGB_TYPE_Q4_K || type == GGB_TYPE_Q6_K, "mul_mat_kq_packed_f32: type %d", type);
+    return launch_packed(type, true, packed, rows, K, x, K * 4, T, dst, dst_stride);
 }
 
 size_t ggb_q6k_packed_bytes(int64_t rows, int64_t K) { return (size_t)rows * (size_t)q6k_packed_pitch((int)(K / kQK)); }
@@ -594,27 +665,6 @@ int ggb_op_q6k_repack(const void *raw, int64_t rows, int64_t nb01, int64_t K, vo
     q6k_repack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ggb_cuda_stream()>>>((const uint8_t *)raw, rows, nb01, nb,
                                                                                  (uint8_t *)packed);
     GGB_LAUNCH_CHECK();
-    return GGB_OK;
-}
-
-int ggb_op_mul_mat_q6k_packed(const void *packed, int64_t rows, int64_t K, const void *act, int64_t row_size, int64_t T,
-                              float *dst, int64_t dst_stride) {
-    GGB_REQUIRE_INIT();
-    GGB_CHECK_ARG(packed && act && dst && rows > 0 && T > 0 && K > 0 && K % kQK == 0, "mul_mat_q6k_packed: bad arguments");
-    const int nb = (int)(K / kQK);
-    GGB_CHECK_ARG(row_size >= (int64_t)nb * kQ8K && row_size % 4 == 0, "mul_mat_q6k_packed: activation row pitch %lld", (long long)row_size);
-    const size_t smem = (size_t)nb * kActSB6;
-    GGB_CHECK_ARG(smem <= 200 * 1024, "mul_mat_q6k_packed: K %lld too long for the staged activation row", (long long)K);
-    if (smem > 48 * 1024) GGB_CUDA(cudaFuncSetAttribute(q6k_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t groups = (rows + kWarps - 1) / kWarps;
-    const unsigned gx = (unsigned)(groups < 148 * 8 ? groups : 148 * 8);
-    for (int64_t t0 = 0; t0 < T; t0 += 65535) {
-        const dim3 grid(gx, (unsigned)(T - t0 < 65535 ? T - t0 : 65535));
-        q6k_packed_kernel<<<grid, 256, smem, ggb_cuda_stream()>>>((const uint8_t *)packed, rows, nb,
-                                                                  (const uint8_t *)act + t0 * row_size, row_size,
-                                                                  dst + t0 * dst_stride, dst_stride);
-        GGB_LAUNCH_CHECK();
-    }
     return GGB_OK;
 }
 

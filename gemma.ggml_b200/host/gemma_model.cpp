@@ -452,7 +452,11 @@ int gemma_model::emit_decode_step() {
 }
 
 int gemma_model::kq_mv(const kq_mat &w, const float *x, float *dst) {
-    if (x) GM_TRY(ggb_op_quantize_q8_K(x, w.cols, 1, kq_q8_)); // x == nullptr: the row quantised for the previous matrix
+    // quantize_row_q8_K of the input row (ggml's INIT stage for a K-quant src0): inside the mat-vec's staging for short
+    // rows (every CTA quantises the row itself: one launch less); as a launch of its own for long rows (the down
+    // projection: 64 KB of fp32 per CTA would be read a thousand times)
+    if (w.cols <= 4096) return ggb_op_mul_mat_kq_packed_f32(w.type, w.packed, w.rows, w.cols, x, 1, dst, w.rows);
+    GM_TRY(ggb_op_quantize_q8_K(x, w.cols, 1, kq_q8_));
     const int64_t row_size = (int64_t)ggb_type_row_bytes(GGB_TYPE_Q8_K, w.cols);
     return w.type == GGB_TYPE_Q4_K ? ggb_op_mul_mat_q4k_packed(w.packed, w.rows, w.cols, kq_q8_, row_size, 1, dst, w.rows)
                                    : ggb_op_mul_mat_q6k_packed(w.packed, w.rows, w.cols, kq_q8_, row_size, 1, dst, w.rows);
@@ -476,8 +480,8 @@ int gemma_model::emit_decode_step_kq() {
         float *act = ffn_act_ + (size_t)il * F;
         PROFILE("op_rms_norm", ggb_op_rms_norm(x_in, l.attn_norm, c.eps, E, 1, kq_xn_, nullptr));
         PROFILE("op_mul_mat", kq_mv(w[0], kq_xn_, q_));
-        PROFILE("op_mul_mat", kq_mv(w[1], nullptr, k_)); // Q, K, V share one Q8_K row
-        PROFILE("op_mul_mat", kq_mv(w[2], nullptr, v_));
+        PROFILE("op_mul_mat", kq_mv(w[1], kq_xn_, k_));
+        PROFILE("op_mul_mat", kq_mv(w[2], kq_xn_, v_));
         PROFILE("op_rope", ggb_op_rope_kv_store(q_, k_, v_, state_ + 1, c.n_head, c.n_head_kv, c.head_dim, q_scale,
                                                 k_cache_[(size_t)il], v_cache_[(size_t)il]));
         PROFILE("op_attn", ggb_op_attn_decode(q_, k_cache_[(size_t)il], v_cache_[(size_t)il], state_ + 1, c.n_head,
@@ -486,7 +490,7 @@ int gemma_model::emit_decode_step_kq() {
         PROFILE("op_add", ggb_op_add(sa, x_in, E, sa));
         PROFILE("op_rms_norm", ggb_op_rms_norm(sa, l.ffn_norm, c.eps, E, 1, kq_xn_, nullptr));
         PROFILE("op_mul_mat", kq_mv(w[4], kq_xn_, kq_gate_));
-        PROFILE("op_mul_mat", kq_mv(w[5], nullptr, kq_up_));
+        PROFILE("op_mul_mat", kq_mv(w[5], kq_xn_, kq_up_));
         PROFILE("op_gelu", ggb_op_gelu(kq_gate_, F, kq_gate_));
         PROFILE("op_mul", ggb_op_mul(kq_gate_, kq_up_, F, act));
         PROFILE("op_mul_mat", kq_mv(w[6], act, lo));

@@ -152,7 +152,7 @@ class gemma_model {
     std::vector<kq_mat> kq_layers_; // [n_layer][7]: q, k, v, o, gate, up, down
     float *kq_xn_ = nullptr, *kq_gate_ = nullptr, *kq_up_ = nullptr;
     void *kq_q8_ = nullptr; // one Q8_K activation row (longest K)
-    int kq_mv(const kq_mat &w, const float *x, float *dst); // quantize_row_q8_K(x) (x != null) then the packed mat-vec
+    int kq_mv(const kq_mat &w, const float *x, float *dst); // the packed mat-vec on the fp32 row x (quantised to Q8_K in its staging)
 
     // device-resident step state: [token, pos, pos_step]
     int32_t *state_ = nullptr, *history_ = nullptr;

@@ -151,6 +151,10 @@ int ggb_op_mul_mat_q4k_packed(const void *packed, int64_t rows, int64_t K, const
                               float *dst, int64_t dst_stride);
 /* the same for Q6_K: codes expanded to int8 (q - 32) in the transposed arrangement; ggb_q6k_packed_bytes = size of the
  * packed matrix (274 B per super-block, rows padded to 16 B) */
+/* the packed mat-vecs on an fp32 activation row x[t][K]: the kernel quantises the row to Q8_K itself while it stages it
+ * (ggml's INIT stage of the mul_mat node fused into the COMPUTE stage; same bits as quantize + packed mat-vec) */
+int ggb_op_mul_mat_kq_packed_f32(int type, const void *packed, int64_t rows, int64_t K, const float *x, int64_t T, float *dst,
+                                 int64_t dst_stride);
 /* get_rows on ggml's AoS K-quant blocks (embedding lookup): y[t] = dequantize_row(raw row ids[t]) * scale */
 int ggb_op_get_rows_blocks(int type, const void *raw, int64_t n_rows, int64_t nb01, int64_t K, const int32_t *ids, int64_t T,
                            float scale, float *y);

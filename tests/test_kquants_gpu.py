@@ -159,3 +159,26 @@ def test_kquant_model_generate_matches_oracle_bitwise(gpu, name):
         for cap in ("kqv_out", "sa_out", "ffn_act", "l_out"):
             assert np.array_equal(bits(m.capture(cap, il)), bits(om.capture(cap, il))), (cap, il)
     m.close(); om.close()
+
+
+@pytest.mark.parametrize("wtype", [O.TYPE_Q4_K, O.TYPE_Q6_K])
+@pytest.mark.parametrize("n,k,t", [(40, 2048, 2), (9, 256, 1), (33, 4096, 3)])
+def test_packed_mat_vec_on_fp32_activations_quantises_like_quantize_row_q8_K(gpu, wtype, n, k, t):
+    """INIT stage fused into the mat-vec: fp32 rows in, same bits as quantize_row_q8_K + vec_dot of the scalar code"""
+    rng = np.random.default_rng(n + k + t + wtype)
+    L = gpu.cuda_lib()
+    w = O.random_kquant_rows(rng, wtype, n, k)
+    x = (rng.standard_normal((t, k)) * 1.5).astype(np.float32)
+    x[0, :256] = 0.0  # an all-zero super-block
+    want = O.mul_mat_blocks(wtype, w, O.quantize_q8_K(x), k)
+    wd, xd = gpu.DeviceBuffer.from_numpy(w), gpu.DeviceBuffer.from_numpy(x)
+    if wtype == O.TYPE_Q4_K:
+        packed = gpu.DeviceBuffer(w.nbytes)
+        gpu.check(L.ggb_op_q4k_repack(wd.ptr, n, w.shape[1], k, packed.ptr))
+    else:
+        packed = gpu.DeviceBuffer(L.ggb_q6k_packed_bytes(n, k))
+        gpu.check(L.ggb_op_q6k_repack(wd.ptr, n, w.shape[1], k, packed.ptr))
+    dst = gpu.DeviceBuffer(4 * n * t)
+    gpu.check(L.ggb_op_mul_mat_kq_packed_f32(wtype, packed.ptr, n, k, xd.ptr, t, dst.ptr, n))
+    gpu.sync()
+    assert np.array_equal(bits(dst.download(np.float32).reshape(t, n)), bits(want))
