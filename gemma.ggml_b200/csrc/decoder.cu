@@ -498,8 +498,12 @@ __device__ __forceinline__ void producer_loop(const DecoderParams &P, Smem<TYPE>
             const int old = issued - max_out;
             mbar_wait(full0 + 8 * (old % SLOTS), (uint32_t)((old / SLOTS) & 1));
         }
+#ifdef GGB_KO_STREAM // knock-out build (timing only, wrong results): the slot "arrives" without a copy
+        mbar_expect_tx(full0 + 8 * slot, 0u);
+#else
         mbar_expect_tx(full0 + 8 * slot, bytes);
         bulk_g2s(ring + slot * F::SLOT_BYTES, src, bytes, full0 + 8 * slot, pol);
+#endif
         issued++;
         if (++slot == SLOTS) {
             slot = 0;
@@ -752,6 +756,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 // acc + term[b0] + term[b0 + 1] + ... (len terms, one by one: the reference's  sumf += term  loop); row = shared address
 // of the lane's 64-term run; len is the same for every lane of the warp
 __device__ __forceinline__ float chain_add(uint32_t row, int b0, int len, float acc) {
+#ifdef GGB_KO_FADD // knock-out build (timing only, wrong results): one add per round instead of len
+    { const float4 t0 = lds_f4(row); return __fadd_rn(acc, t0.x); }
+#endif
     if (len == 64) { // the common case, fully unrolled: 16 loads up front, then the 64 dependent adds
         float4 t[16];
 #pragma unroll
@@ -1615,8 +1622,12 @@ __device__ __forceinline__ void matvec_consumer(const DecoderParams &P, int phi,
             if (j < cnt) {
                 const uint32_t pass = ring + slot * F::SLOT_BYTES + j * F::PASS_BYTES;
                 float term[4];
+#ifdef GGB_KO_COMPUTE // knock-out build (timing only, wrong results): no term arithmetic, a loaded word is stored
+                term[0] = term[1] = term[2] = term[3] = __uint_as_float(lds_u4(pass + 16 * lane).x & 0x3fffffffu);
+#else
                 if (quad && segc >= kA) pass_terms<TYPE, true>(pass, act_d, act_bias, aseg * kSeg + lane, A, lane, term);
                 else pass_terms<TYPE, false>(pass, act_d, act_bias, aseg * kSeg + lane, A, lane, term);
+#endif
                 store_terms(terms0 + (uint32_t)tb * (uint32_t)(kTermFloats * 4), j, lane, term);
                 rem += kCW;
                 while (segc < kA && rem >= npairs) {

@@ -1,5 +1,7 @@
 #!/bin/bash
-# tools/build_variant.sh NAME "-DFLAG=1 ..." : variants/NAME/libggb_cuda.so = the library with decoder.cu rebuilt under the flags
+# tools/build_variant.sh NAME "-DFLAG=1 ..." : variants/NAME/libggb_cuda.so = the library with decoder.cu rebuilt under the flags.
+# Knock-out flags of decoder.cu (timing experiments, wrong results): -DGGB_KO_STREAM (no weight copies), -DGGB_KO_COMPUTE
+# (no term arithmetic), -DGGB_KO_FADD (one chain add per round).  tools/run_variants.sh NAME... benches them on the GPU box.
 set -e
 cd "$(dirname "$0")/.."
 name=$1; flags=$2
