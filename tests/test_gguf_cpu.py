@@ -35,3 +35,32 @@ def test_probe_rejects_garbage(tmp_path):
     open(path, "wb").write(b"nope" * 16)
     with pytest.raises(G.GgbError):
         G.gguf_probe(path)
+
+
+def test_probe_accepts_k_quant_files(tmp_path):
+    """a q4_k_m-like file (Q4_K matrices, Q6_K token_embd): hyper-parameters read, wtype = the embedding's K-quant type"""
+    dims = dict(DIMS, n_ff=1024)  # every row length a multiple of 256
+    om = O.Model(wtype=O.TYPE_Q4_K, sigma_embd=0.005, **dims)
+    path = os.path.join(tmp_path, "tiny_q4_k_m.gguf")
+    write_gemma_gguf(path, om, dims, O.TYPE_Q4_K)
+    cfg, n_tensors, _, _, _, _ = G.gguf_probe(path)
+    assert cfg.wtype == O.TYPE_Q6_K and cfg.n_ff == 1024 and n_tensors == 2 + 9 * dims["n_layer"]
+    om.close()
+
+
+def test_oracle_k_quant_model_forward_is_finite_and_deterministic():
+    dims = dict(DIMS, n_ff=1024, n_ctx=32)
+    for wt in (O.TYPE_Q4_K, O.TYPE_Q6_K):
+        m = O.Model(wtype=wt, sigma_embd=0.005, **dims)
+        prompt = ((1 + 7919 * np.arange(5)) % dims["n_vocab"]).astype(np.int32)
+        a, _, _ = m.generate(prompt, 4, O.REF)
+        la = m.capture("result_output").copy()
+        b, _, _ = m.generate(prompt, 4, O.REF)
+        assert np.array_equal(a, b) and np.array_equal(la.view(np.uint32), m.capture("result_output").view(np.uint32))
+        assert np.isfinite(la).all() and np.abs(la).max() > 0
+        # the tied embedding of a Q4_K model is Q6_K (the q4_k_m mix)
+        raw, rows, cols = m.tensor(0)
+        assert raw.nbytes == rows * (cols // 256) * 210
+        raw, rows, cols = m.tensor(3)
+        assert raw.nbytes == rows * (cols // 256) * (144 if wt == O.TYPE_Q4_K else 210)
+        m.close()
