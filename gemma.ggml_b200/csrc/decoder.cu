@@ -563,17 +563,20 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp < nquad) w4 = *reinterpret_cast<const float4 *>(norm_w + 128 * warp + 4 * lane);
     double acc = 0.0;
-    // a thread's words are requested 8 at a time (all of them for E <= 2048): ONE L2 round trip when x is there
-    constexpr int NV = 8;
+    // the sixteen warps share the row: warp half h takes the upper or lower half of a thread column's words (both halves
+    // used to gather ALL of them: twice the polling traffic for nothing).  A thread's words are requested together
+    // (all of them for E <= 2048): ONE L2 round trip when x is there
+    constexpr int NV = 4;
+    const int nk_half = (nk + 1) >> 1, k_lo = (warp >> 3) * nk_half, k_hi = min(nk, k_lo + nk_half);
     if (in) {
 #pragma unroll 1
-        for (int k0 = 0; k0 < nk; k0 += NV) {
+        for (int k0 = k_lo; k0 < k_hi; k0 += NV) {
             ll_t v[NV];
             const ll_t *pw = in + GGB_DEV_NORM_THREADS * k0 + base;
-            ll_gather<NV>(v, pw, GGB_DEV_NORM_THREADS, nk - k0, tag);
+            ll_gather<NV>(v, pw, GGB_DEV_NORM_THREADS, k_hi - k0, tag);
 #pragma unroll
             for (int u = 0; u < NV; u++) {
-                if (k0 + u < nk) {
+                if (k0 + u < k_hi) {
                     const float x = __uint_as_float((uint32_t)v[u]);
                     xs[GGB_DEV_NORM_THREADS * (k0 + u) + base] = x;
                     acc = __dadd_rn(acc, (double)__fmul_rn(x, x));
@@ -582,7 +585,7 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
         }
     } else { // layer 0: the embedding row of the token
 #pragma unroll 1
-        for (int k = 0; k < nk; k++) {
+        for (int k = k_lo; k < k_hi; k++) {
             const int i = GGB_DEV_NORM_THREADS * k + base;
             const float x = embed_value<TYPE>(P, token, i);
             xs[i] = x;
@@ -590,11 +593,11 @@ __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE>
         }
     }
     acc = warp_sum_f64(acc);
-    if (warp < 8 && lane == 0) S.red[warp] = acc;
+    if (lane == 0) S.red[warp] = acc;
     consumer_bar();
     double sum = S.red[0];
 #pragma unroll
-    for (int i = 1; i < GGB_DEV_NORM_THREADS / 32; i++) sum = __dadd_rn(sum, S.red[i]);
+    for (int i = 1; i < kCW; i++) sum = __dadd_rn(sum, S.red[i]);
     // sum / E: a power-of-two E scales exactly (same bits as the division, which is a ~600-cycle routine)
     const float mean = __double2float_rn((E & (E - 1)) == 0 ? __dmul_rn(sum, 1.0 / (double)E) : __ddiv_rn(sum, (double)E));
     const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, P.eps)));
