@@ -370,12 +370,19 @@ template <int N>
 __device__ __forceinline__ void ll_gather(ll_t (&v)[N], const ll_t *p, int stride, int n, uint32_t tag) {
 #pragma unroll
     for (int u = 0; u < N; u++) v[u] = u < n ? ll_peek(p + (size_t)stride * u) : 0ull;
+    // The lanes that called together wait together: while anything is missing they all spin on ONE word (the first
+    // missing word of the lowest such lane - 32 loads of one address are one L2 request, where 32 private spins were 32
+    // requests per round trip, from every warp of every waiting CTA, competing with the weight stream of the CTAs that
+    // are still working), then every lane re-reads only its own missing words, together.
+    const unsigned am = __activemask();
     for (;;) {
         int bad = -1;
 #pragma unroll
         for (int u = N - 1; u >= 0; u--) bad = (u < n && (uint32_t)(v[u] >> 32) != tag) ? u : bad;
-        if (bad < 0) return;
-        const ll_t *pb = p + (size_t)stride * bad;
+        const unsigned need = __ballot_sync(am, bad >= 0);
+        if (!need) return;
+        const ll_t *mine = p + (size_t)stride * (bad < 0 ? 0 : bad);
+        const ll_t *pb = reinterpret_cast<const ll_t *>(__shfl_sync(am, (unsigned long long)mine, __ffs(need) - 1));
 #if GGB_WATCHDOG
         for (uint32_t spins = 0; (uint32_t)(ll_peek(pb) >> 32) != tag; spins++)
             if (spins > (1u << 24)) __trap();
@@ -387,7 +394,6 @@ __device__ __forceinline__ void ll_gather(ll_t (&v)[N], const ll_t *p, int strid
             if (u < n && (uint32_t)(v[u] >> 32) != tag) v[u] = ll_peek(p + (size_t)stride * u);
     }
 }
-
 __device__ __forceinline__ unsigned long long gtime() { // ns, one clock for the whole GPU (SM clocks are not aligned)
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
