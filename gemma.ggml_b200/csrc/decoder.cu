@@ -1521,11 +1521,11 @@ __device__ __forceinline__ void pv_phase(const DecoderParams &P, int phi, int ct
             const ll_t *vp = ph.in_ll + (size_t)P.H * d + (size_t)P.Hkv * d + (size_t)g * d + (size_t)slice * W + 8 * o;
             uint4 raw;
             __half2 *h2 = reinterpret_cast<__half2 *>(&raw);
+            ll_t vw[8]; // the eight words together: one round trip (one after the other they were eight, in every PV item)
+            ll_gather<8>(vw, vp, 1, 8, tag);
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const float a = ll_get_f(ll_peek(vp + 2 * e), vp + 2 * e, tag), b = ll_get_f(ll_peek(vp + 2 * e + 1), vp + 2 * e + 1, tag);
-                h2[e] = __halves2half2(__float2half_rn(a), __float2half_rn(b));
-            }
+            for (int e = 0; e < 4; e++)
+                h2[e] = __halves2half2(__float2half_rn(__uint_as_float((uint32_t)vw[2 * e])), __float2half_rn(__uint_as_float((uint32_t)vw[2 * e + 1])));
             fma8(raw, pos);
         }
         PROF_STAMP(6);
