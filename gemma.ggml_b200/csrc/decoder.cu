@@ -651,7 +651,7 @@ __device__ __forceinline__ void packed_prologue(Smem<TYPE> &S, const ll_t *in, i
     uint32_t *aq = reinterpret_cast<uint32_t *>(S.u);
     __half *ad = reinterpret_cast<__half *>(S.u + act_d_off(K));
     int *bias = reinterpret_cast<int *>(S.u + act_bias_off(K));
-    constexpr int NW = 5; // words in flight per thread (9 = a whole Gemma-2B DOWN row at once measured 9 % SLOWER per token; 4 and 5 tie)
+    constexpr int NW = 5; // words in flight per thread (9 = a whole Gemma-2B DOWN row at once measured 9-14 % SLOWER per token, before and after the polling fixes; 4 and 5 tie)
 #pragma unroll 1
     for (int i0 = tid; i0 < nw + ns; i0 += NW * kCT) {
         ll_t v[NW];
