@@ -26,7 +26,9 @@
 //   * NO GRID BARRIERS.  Every value that crosses CTAs travels as an 8-byte word {payload, tag} written with one
 //     relaxed store (the NCCL "LL" idea): tag = the token's sequence number, buffers are per layer, a consumer
 //     re-reads a word until its tag matches.  Data and flag arrive together: no fence, no separate wait.  A thread
-//     requests all its words at once and, if some are missing, spins on one and re-reads only the missing ones (ll_gather).
+//     requests all its words at once; if some are missing, the lanes that wait together spin on ONE shared word (a
+//     spinning load is an L2 request that competes with the weight stream of the CTAs still working) and then re-read
+//     only their own missing words (ll_gather).  Serial polls on a critical path cost a round trip each.
 //   * ATTENTION = two phases without a combine: SCORE (items = kv head x 32-position chunk: kq in double, the new
 //     position's K/V roped, rounded and stored) and PV (items = head x 16/32-dim slice: the WHOLE soft_max_ext row of
 //     the head - global max, fp16 exp, exact double sum, fp16 P - then P.V in double).  Double accumulators make
