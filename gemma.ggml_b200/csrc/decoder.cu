@@ -553,10 +553,11 @@ __device__ __forceinline__ void quant_quad_to_smem(uint32_t u, int quad, int lan
 }
 
 // rms_norm (+ weight mul) + quantize_row_q8_0 of the phase input; every CTA recomputes it (16 KB of flagged
-// words from L2) instead of making it a phase of its own.  Sum of squares in the DEV order: 256 strided double
-// partials (partial t = elements t, t + 256, ...), butterfly per warp, the 8 warp sums in order.  Thread
-// (warp w, lane l) loads exactly the elements of partial 32 * (w & 7) + l, so both warp halves hold the
-// partials in registers and no staging pass is needed; the halves then split the quantisation by blocks.
+// words from L2) instead of making it a phase of its own.  Sum of squares ([UPSTREAM] ggml_float = double, of the
+// fp32-rounded products x * x): the sixteen warps share the row - thread (warp w, lane l) takes the lower (w < 8) or
+// upper half of the elements 32 * (w & 7) + l + 256 k -, a butterfly per warp, the sixteen warp sums in order.  A
+// double sum of these terms does not depend on its grouping at the precision the rounding to fp32 keeps, so the result
+// is the scalar loop's (bitwise in every test); the warps then split the quantisation by blocks.
 template <int TYPE>
 __device__ __forceinline__ void norm_prologue(const DecoderParams &P, Smem<TYPE> &S, const Phase &ph, int token,
                                               uint32_t tag, float *f32_out) {

@@ -52,7 +52,8 @@ __global__ void q8_from_blocks_kernel(const uint8_t *__restrict__ blocks, int64_
 
 // ---------------------------------------------------------------- K5 rms_norm (+mul, +quantize)
 // [UPSTREAM] ggml_compute_forward_rms_norm_f32 then ggml_mul (ref: src/gemma_model.cpp:438-442).
-// Sum of squares in double in the DEV order: 256 strided partials, butterfly, warps in order.
+// Sum of squares in double (ggml_float) of the fp32-rounded products: 256 strided partials, butterfly, warps in order - the
+// grouping of a double sum is invisible after the rounding to fp32, so this is the scalar loop's result.
 __global__ void __launch_bounds__(GGB_DEV_NORM_THREADS)
 rms_norm_kernel(const float *__restrict__ x, const float *__restrict__ w, float eps, int64_t E, float *__restrict__ y,
                 uint8_t *__restrict__ q8, int64_t q8_stride) {

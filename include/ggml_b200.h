@@ -35,10 +35,11 @@ typedef enum {
 enum { GGB_TYPE_F32 = 0, GGB_TYPE_F16 = 1, GGB_TYPE_Q4_0 = 2, GGB_TYPE_Q8_0 = 8,
        GGB_TYPE_Q4_K = 12, GGB_TYPE_Q6_K = 14, GGB_TYPE_Q8_K = 15 }; /* ggml_type ids */
 
-/* Deterministic reduction orders of the kernels ("DEV order"; the oracle mirrors them):
- * mat-vec: K cut into segments of GGB_DEV_SEG_BLOCKS blocks, 32 lane-strided partials per
- * segment, xor-butterfly, segments added in order.  rms_norm: GGB_DEV_NORM_THREADS strided
- * double partials.  attention: split-K chunks of GGB_DEV_ATTN_CHUNK positions. */
+/* Arithmetic: every result of the Q4_0 / Q8_0 decode path and of the K-quant operators is BIT-IDENTICAL to the scalar
+ * ggml code the reference's CPU path runs (one fp32 accumulator per row, blocks in order; double accumulators where
+ * ggml has them) - there is no kernel-specific summation order.  The constants below are tiling
+ * parameters only: blocks per K segment of the decode kernel's pass stream, threads of the rms_norm partial sums
+ * (double: insensitive to their grouping at fp32 precision), positions per attention item. */
 #define GGB_DEV_SEG_BLOCKS 64
 #define GGB_DEV_NORM_THREADS 256
 #define GGB_DEV_ATTN_CHUNK 32
