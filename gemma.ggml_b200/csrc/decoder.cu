@@ -913,6 +913,8 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
             uint32_t wb = 0, rb = 0, waited = 0, released = 0;
             uint32_t p = act2 ? pair : 0u, ls = 0, lb = 0; // this lane's pass of segment k, its slot and that slot's buffer
             uint32_t done = 0;
+            ll_t rv = 0; // the residual word: requested now, used after the last round
+            if (act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
             // several segments per round when a slot holds them (Gemma-2B DOWN: 7 pairs per segment, 16 passes per slot
             // -> 2): the wait / release / loop code between two runs of adds is paid once per slot instead of per segment
             const int spr = min(4, max(1, (int)(F::PPS / np_u)));
@@ -932,8 +934,6 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
                 }
                 if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; }
                 const bool fin = k + nseg == kA;
-                ll_t rv = 0;
-                if (fin && act2 && resid && row0 + lane < n_lr) rv = ll_peek(resid + oidx(row0 + lane));
 #pragma unroll 1
                 for (int q = 0; q < nseg; q++, p += np_u) {
                     const uint32_t ns = p >> SH;
@@ -972,13 +972,15 @@ __device__ __forceinline__ void chain_phase(const DecoderParams &P, int phi, int
         for (int m0 = 0; m0 < n_passes; m0 += F::PPS, gslot++) {
             if (turn == ci) {
                 const int cnt = min(F::PPS, n_passes - m0);
-                if (PROF) pt0 = clock64();
-                mbar_wait(tf0 + 8 * tb, (tmask >> tb) & 1u);
-                if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; const int k = m0 / F::PPS; if (prof && lane == 0 && ci == 0 && k < 8) P.prof[64 * cta + 48 + 2 * k] = t1 - p_begin; }
+                // the residual word is requested BEFORE the wait for the terms (it is there since the previous phase): its
+                // L2 round trip used to sit behind the 64 adds, on the tail of O
                 const int rl = 2 * m0 + lane;
                 const bool active = j < cnt;
                 ll_t rv = 0;
                 if (active && resid && row0 + rl < n_lr) rv = ll_peek(resid + oidx(row0 + rl));
+                if (PROF) pt0 = clock64();
+                mbar_wait(tf0 + 8 * tb, (tmask >> tb) & 1u);
+                if (PROF) { const long long t1 = clock64(); p_wait += t1 - pt0; pt0 = t1; p_rounds++; const int k = m0 / F::PPS; if (prof && lane == 0 && ci == 0 && k < 8) P.prof[64 * cta + 48 + 2 * k] = t1 - p_begin; }
                 const float acc = chain_add(terms0 + (uint32_t)tb * (uint32_t)(kTermFloats * 4) + (uint32_t)(lane * kTermRow * 4), 0, tail_blocks, 0.0f);
                 if (PROF) { const long long t1 = clock64(); p_add += t1 - pt0; }
                 if (active) finish_row(rl, acc, rv);
